@@ -1,0 +1,412 @@
+"""Thin ctypes binding of the C ABI in include/cdsgpu.h (libcdsgpu.so).
+
+This is plumbing for tests and bench.py: every call goes straight to the shared library; there is no Python or CPU
+implementation of anything behind it, and loading fails loudly when the library has not been built.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcdsgpu.so")
+
+CDS_OK = 0
+CDS_ERR_BAD_ARG = 1
+CDS_ERR_SIZE_MISMATCH = 2
+CDS_ERR_NO_DEVICE = 3
+CDS_ERR_CUDA = 4
+CDS_ERR_OOM = 5
+CDS_ERR_CAPACITY = 6
+CDS_ERR_UNSUPPORTED = 7
+CDS_MAX_RECTS = 8
+
+
+class CdsError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("libcdsgpu status %d: %s" % (status, message))
+        self.status = status
+        self.message = message
+
+
+class CdsIllegalArgument(CdsError, ValueError):
+    """CDS_ERR_BAD_ARG / CDS_ERR_SIZE_MISMATCH: where the Java reference throws IllegalArgumentException."""
+
+
+class Rect(C.Structure):
+    _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32)]
+
+
+class PixParams(C.Structure):
+    _fields_ = [("mask_threshold", C.c_int32), ("data_threshold", C.c_int32), ("z_tolerance", C.c_double),
+                ("xy_shift", C.c_int32), ("mirror", C.c_int32), ("n_rects", C.c_int32), ("rects", Rect * CDS_MAX_RECTS)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("match_kernel_launches", C.c_int64), ("match_kernel_ms", C.c_double),
+                ("total_device_ms", C.c_double), ("comparisons", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+_lib = None
+_vp = C.c_void_p
+_u8p = C.POINTER(C.c_uint8)
+_u16p = C.POINTER(C.c_uint16)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); the single source of truth for the Python side of the ABI
+SIGNATURES = {
+    "cds_abi_version": (C.c_int32, []),
+    "cds_ctx_create": (C.c_int32, [_i32p, C.c_int32, C.POINTER(_vp)]),
+    "cds_ctx_destroy": (None, [_vp]),
+    "cds_ctx_num_devices": (C.c_int32, [_vp]),
+    "cds_last_error": (C.c_char_p, [_vp]),
+    "cds_host_alloc": (C.c_int32, [_vp, C.c_uint64, C.POINTER(_vp)]),
+    "cds_host_free": (C.c_int32, [_vp, _vp]),
+    "cds_library_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int64, C.POINTER(_vp)]),
+    "cds_library_destroy": (None, [_vp]),
+    "cds_library_add_rgb": (C.c_int32, [_vp, _vp, C.c_int64, _i64p]),
+    "cds_library_generate_synthetic": (C.c_int32, [_vp, C.c_uint64, C.c_int64, C.c_int64, _i64p]),
+    "cds_library_size": (C.c_int64, [_vp]),
+    "cds_library_clear": (C.c_int32, [_vp]),
+    "cds_maskset_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.POINTER(PixParams), C.POINTER(_vp)]),
+    "cds_maskset_destroy": (None, [_vp]),
+    "cds_maskset_add_rgb": (C.c_int32, [_vp, _vp, C.c_int32, _i32p]),
+    "cds_maskset_size": (C.c_int32, [_vp]),
+    "cds_maskset_get_mask_sizes": (C.c_int32, [_vp, _i32p]),
+    "cds_search_dense": (C.c_int32, [_vp, _vp, _vp, _i32p, _u8p]),
+    "cds_search_topk": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_double, _i32p, _i64p, _u8p, _i32p]),
+    "cds_score_pair_rgb": (C.c_int32, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
+    "cds_shape_maskset_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Rect), C.c_int32, _vp, C.POINTER(_vp)]),
+    "cds_shape_maskset_destroy": (None, [_vp]),
+    "cds_shape_maskset_add_rgb": (C.c_int32, [_vp, _vp, C.c_int32, _i64p, _i64p]),
+    "cds_shape_maskset_size": (C.c_int32, [_vp]),
+    "cds_shape_score_pairs": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i32p, _i64p, C.c_int64, _i64p, _i64p, _u8p]),
+    "cds_make_zgap": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.POINTER(Rect), C.c_int32, _vp]),
+    "cds_shape_score_2d": (C.c_int64, [C.c_int64, C.c_int64]),
+    "cds_normalized_score": (C.c_double, [C.c_int32, C.c_int64, C.c_int64, C.c_int64]),
+    "cds_normalize_scores": (C.c_int32, [_i32p, _i64p, _i64p, C.c_int64, _f32p]),
+    "cds_synth_rgb": (C.c_int32, [_vp, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "cds_synth_gradient": (C.c_int32, [_vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "cds_get_last_stats": (C.c_int32, [_vp, C.POINTER(SearchStats)]),
+    "cds_debug_encode_colors": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, _u32p]),
+    "cds_debug_class_intervals": (C.c_int32, [C.c_double, C.c_int32, C.c_int32, _u32p, _u32p, _u32p, _u32p]),
+}
+
+
+def lib():
+    """Loads libcdsgpu.so.  Raises if it has not been built: there is no fallback of any kind."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libcdsgpu.so is missing (%s): run `python -m colormipsearch_b200.build`; "
+                               "there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)      # AttributeError here = the library does not export what the header declares
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(status, ctx=None):
+    if status == CDS_OK:
+        return
+    msg = lib().cds_last_error(ctx)
+    msg = msg.decode("utf-8", "replace") if msg else ""
+    if status in (CDS_ERR_BAD_ARG, CDS_ERR_SIZE_MISMATCH):
+        raise CdsIllegalArgument(status, msg)
+    raise CdsError(status, msg)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def make_rects(rects):
+    rects = np.asarray(rects if rects is not None else [], dtype=np.int32).reshape(-1, 4)
+    arr = (Rect * max(len(rects), 1))()
+    for i, r in enumerate(rects):
+        arr[i] = Rect(int(r[0]), int(r[1]), int(r[2]), int(r[3]))
+    return arr, len(rects)
+
+
+class Context:
+    def __init__(self, device_ids=None, n_dev=None):
+        h = _vp()
+        if device_ids is not None:
+            ids = (C.c_int32 * len(device_ids))(*device_ids)
+            st = lib().cds_ctx_create(ids, len(device_ids), C.byref(h))
+        else:
+            st = lib().cds_ctx_create(None, 1 if n_dev is None else int(n_dev), C.byref(h))
+        _check(st, None)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().cds_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def num_devices(self):
+        return lib().cds_ctx_num_devices(self.h)
+
+    def host_alloc(self, nbytes):
+        """Pinned host buffer as a numpy uint8 array (freed with host_free)."""
+        p = _vp()
+        _check(lib().cds_host_alloc(self.h, int(nbytes), C.byref(p)), self.h)
+        buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        arr._cds_ptr = p.value if hasattr(arr, "__dict__") else None
+        return arr, p
+
+    def host_free(self, p):
+        _check(lib().cds_host_free(self.h, p), self.h)
+
+    def last_stats(self):
+        s = SearchStats()
+        _check(lib().cds_get_last_stats(self.h, C.byref(s)), self.h)
+        return {f[0]: getattr(s, f[0]) for f in SearchStats._fields_}
+
+    def synth_rgb(self, kind, seed, first_index, n, W, H, on_device=True):
+        out = np.empty((n, H, W, 3), np.uint8)
+        _check(lib().cds_synth_rgb(self.h, int(kind), int(seed), int(first_index), int(n), W, H, int(on_device), _ptr(out)), self.h)
+        return out
+
+    def synth_gradient(self, seed, first_index, n, W, H, on_device=True):
+        out = np.empty((n, H, W), np.uint16)
+        _check(lib().cds_synth_gradient(self.h, int(seed), int(first_index), int(n), W, H, int(on_device), _ptr(out)), self.h)
+        return out
+
+    def debug_encode_colors(self, rgb, data_threshold):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+        out = np.empty(len(rgb), np.uint32)
+        _check(lib().cds_debug_encode_colors(self.h, _ptr(rgb), len(rgb), int(data_threshold), out.ctypes.data_as(_u32p)), self.h)
+        return out
+
+    def make_zgap(self, rgb, threshold, radius, rects):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if rgb.ndim == 3:
+            rgb = rgb[None]
+        n, H, W, _ = rgb.shape
+        out = np.empty_like(rgb)
+        ra, nr = make_rects(rects)
+        _check(lib().cds_make_zgap(self.h, _ptr(rgb), n, W, H, int(threshold), float(radius), ra, nr, _ptr(out)), self.h)
+        return out
+
+
+def synth_rgb_host(kind, seed, first_index, n, W, H):
+    """Host build of the synthetic generator (no device needed)."""
+    out = np.empty((n, H, W, 3), np.uint8)
+    _check(lib().cds_synth_rgb(None, int(kind), int(seed), int(first_index), int(n), W, H, 0, _ptr(out)))
+    return out
+
+
+def synth_gradient_host(seed, first_index, n, W, H):
+    out = np.empty((n, H, W), np.uint16)
+    _check(lib().cds_synth_gradient(None, int(seed), int(first_index), int(n), W, H, 0, _ptr(out)))
+    return out
+
+
+class Library:
+    def __init__(self, ctx, W, H, capacity):
+        self.ctx = ctx
+        self.W, self.H = W, H
+        h = _vp()
+        _check(lib().cds_library_create(ctx.h, W, H, int(capacity), C.byref(h)), ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().cds_library_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def add_rgb(self, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if rgb.ndim == 3:
+            rgb = rgb[None]
+        if rgb.shape[1:] != (self.H, self.W, 3):
+            raise CdsIllegalArgument(CDS_ERR_SIZE_MISMATCH, "image shape %s does not match the library (%d, %d)" % (rgb.shape, self.H, self.W))
+        first = C.c_int64()
+        _check(lib().cds_library_add_rgb(self.h, _ptr(rgb), rgb.shape[0], C.byref(first)), self.ctx.h)
+        return first.value
+
+    def add_rgb_ptr(self, ptr, n):
+        first = C.c_int64()
+        _check(lib().cds_library_add_rgb(self.h, ptr, int(n), C.byref(first)), self.ctx.h)
+        return first.value
+
+    def generate_synthetic(self, seed, first_synth_index, n):
+        first = C.c_int64()
+        _check(lib().cds_library_generate_synthetic(self.h, int(seed), int(first_synth_index), int(n), C.byref(first)), self.ctx.h)
+        return first.value
+
+    def clear(self):
+        _check(lib().cds_library_clear(self.h), self.ctx.h)
+
+    def __len__(self):
+        return lib().cds_library_size(self.h)
+
+
+class MaskSet:
+    def __init__(self, ctx, W, H, mask_threshold, data_threshold, z_tolerance, xy_shift, mirror, rects):
+        self.ctx = ctx
+        self.W, self.H = W, H
+        p = PixParams()
+        p.mask_threshold = int(mask_threshold)
+        p.data_threshold = int(data_threshold)
+        p.z_tolerance = float(z_tolerance)
+        p.xy_shift = int(xy_shift)
+        p.mirror = int(bool(mirror))
+        rects = np.asarray(rects if rects is not None else [], dtype=np.int32).reshape(-1, 4)
+        p.n_rects = len(rects)
+        for i, r in enumerate(rects[:CDS_MAX_RECTS]):
+            p.rects[i] = Rect(int(r[0]), int(r[1]), int(r[2]), int(r[3]))
+        h = _vp()
+        _check(lib().cds_maskset_create(ctx.h, W, H, C.byref(p), C.byref(h)), ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().cds_maskset_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def add_rgb(self, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if rgb.ndim == 3:
+            rgb = rgb[None]
+        if rgb.shape[1:] != (self.H, self.W, 3):
+            raise CdsIllegalArgument(CDS_ERR_SIZE_MISMATCH, "mask shape %s does not match the mask set (%d, %d)" % (rgb.shape, self.H, self.W))
+        sizes = np.zeros(rgb.shape[0], np.int32)
+        _check(lib().cds_maskset_add_rgb(self.h, _ptr(rgb), rgb.shape[0], sizes.ctypes.data_as(_i32p)), self.ctx.h)
+        return sizes
+
+    def add_rgb_ptr(self, ptr, n):
+        sizes = np.zeros(n, np.int32)
+        _check(lib().cds_maskset_add_rgb(self.h, ptr, int(n), sizes.ctypes.data_as(_i32p)), self.ctx.h)
+        return sizes
+
+    def __len__(self):
+        return lib().cds_maskset_size(self.h)
+
+    def sizes(self):
+        out = np.zeros(max(len(self), 1), np.int32)
+        _check(lib().cds_maskset_get_mask_sizes(self.h, out.ctypes.data_as(_i32p)), self.ctx.h)
+        return out[: len(self)]
+
+    def search_dense(self, library):
+        M, T = len(self), len(library)
+        scores = np.zeros((M, T), np.int32)
+        mirrored = np.zeros((M, T), np.uint8)
+        _check(lib().cds_search_dense(self.ctx.h, self.h, library.h, scores.ctypes.data_as(_i32p), mirrored.ctypes.data_as(_u8p)), self.ctx.h)
+        return scores, mirrored
+
+    def search_topk(self, library, k, pct_positive_pixels=0.0):
+        M = len(self)
+        score = np.zeros((M, k), np.int32)
+        target = np.full((M, k), -1, np.int64)
+        mirrored = np.zeros((M, k), np.uint8)
+        count = np.zeros(M, np.int32)
+        _check(lib().cds_search_topk(self.ctx.h, self.h, library.h, int(k), float(pct_positive_pixels),
+                                     score.ctypes.data_as(_i32p), target.ctypes.data_as(_i64p),
+                                     mirrored.ctypes.data_as(_u8p), count.ctypes.data_as(_i32p)), self.ctx.h)
+        return score, target, mirrored, count
+
+    def score_pair(self, mask_index, target_rgb):
+        target_rgb = np.ascontiguousarray(target_rgb, dtype=np.uint8)
+        s = C.c_int32()
+        r = C.c_double()
+        m = C.c_int32()
+        _check(lib().cds_score_pair_rgb(self.ctx.h, self.h, int(mask_index), _ptr(target_rgb), target_rgb.shape[1], target_rgb.shape[0],
+                                        C.byref(s), C.byref(r), C.byref(m)), self.ctx.h)
+        return s.value, r.value, bool(m.value)
+
+
+class ShapeMaskSet:
+    def __init__(self, ctx, W, H, query_threshold, mirror, rects, border=0, roi=None):
+        self.ctx = ctx
+        self.W, self.H = W, H
+        ra, nr = make_rects(rects)
+        if roi is not None:
+            roi = np.ascontiguousarray(roi, dtype=np.uint8)
+        self._roi = roi
+        h = _vp()
+        _check(lib().cds_shape_maskset_create(ctx.h, W, H, int(query_threshold), int(border), int(bool(mirror)), ra, nr, _ptr(roi), C.byref(h)), ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().cds_shape_maskset_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def add_rgb(self, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if rgb.ndim == 3:
+            rgb = rgb[None]
+        n = rgb.shape[0]
+        qm = np.zeros(n, np.int64)
+        he = np.zeros(n, np.int64)
+        _check(lib().cds_shape_maskset_add_rgb(self.h, _ptr(rgb), n, qm.ctypes.data_as(_i64p), he.ctypes.data_as(_i64p)), self.ctx.h)
+        return qm, he
+
+    def __len__(self):
+        return lib().cds_shape_maskset_size(self.h)
+
+    def score_pairs(self, target_rgb, gradient, zgap_rgb, pair_mask, pair_target, has_variants=None):
+        target_rgb = np.ascontiguousarray(target_rgb, dtype=np.uint8)
+        n_targets = target_rgb.shape[0]
+        gradient = None if gradient is None else np.ascontiguousarray(gradient, dtype=np.uint16)
+        zgap_rgb = None if zgap_rgb is None else np.ascontiguousarray(zgap_rgb, dtype=np.uint8)
+        has_variants = None if has_variants is None else np.ascontiguousarray(has_variants, dtype=np.uint8)
+        pair_mask = np.ascontiguousarray(pair_mask, dtype=np.int32)
+        pair_target = np.ascontiguousarray(pair_target, dtype=np.int64)
+        n = len(pair_mask)
+        gap = np.zeros(n, np.int64)
+        he = np.zeros(n, np.int64)
+        mir = np.zeros(n, np.uint8)
+        _check(lib().cds_shape_score_pairs(self.ctx.h, self.h, _ptr(target_rgb), _ptr(gradient), _ptr(zgap_rgb), _ptr(has_variants),
+                                           n_targets, pair_mask.ctypes.data_as(_i32p), pair_target.ctypes.data_as(_i64p), n,
+                                           gap.ctypes.data_as(_i64p), he.ctypes.data_as(_i64p), mir.ctypes.data_as(_u8p)), self.ctx.h)
+        return gap, he, mir.astype(bool)
+
+
+def shape_score_2d(gap, he):
+    return lib().cds_shape_score_2d(int(gap), int(he))
+
+
+def normalized_score(pix, shape, max_pix, max_shape):
+    return lib().cds_normalized_score(int(pix), int(shape), int(max_pix), int(max_shape))
+
+
+def normalize_scores(pixel_scores, gaps, high_exprs):
+    pixel_scores = np.ascontiguousarray(pixel_scores, dtype=np.int32)
+    gaps = np.ascontiguousarray(gaps, dtype=np.int64)
+    high_exprs = np.ascontiguousarray(high_exprs, dtype=np.int64)
+    out = np.zeros(len(pixel_scores), np.float32)
+    _check(lib().cds_normalize_scores(pixel_scores.ctypes.data_as(_i32p), gaps.ctypes.data_as(_i64p), high_exprs.ctypes.data_as(_i64p),
+                                      len(pixel_scores), out.ctypes.data_as(_f32p)))
+    return out
+
+
+def class_intervals(z_tolerance, sector, rank):
+    lo1, len1, lo2, len2 = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    _check(lib().cds_debug_class_intervals(float(z_tolerance), int(sector), int(rank), C.byref(lo1), C.byref(len1), C.byref(lo2), C.byref(len2)))
+    return lo1.value, len1.value, lo2.value, len2.value

@@ -1,0 +1,941 @@
+// cds_api.cu -- implementation of the C ABI declared in include/cdsgpu.h: contexts, target library, mask sets and the
+// pixel-match searches.  Shape scoring lives in cds_shape.cu, synthetic inputs in cds_synth.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "cds_runtime.h"
+#include "cds_band.cuh"
+#include "cds_topk.cuh"
+
+using namespace cds;
+
+namespace cds {
+static thread_local std::string g_tls_err;
+void set_tls_error(const std::string &msg) { g_tls_err = msg; }
+}  // namespace cds
+
+cds_status cds_ctx::fail(cds_status code, const std::string &msg) const
+{
+    err = msg;
+    set_tls_error(msg);
+    return code;
+}
+
+cds_status cds_ctx::check(cudaError_t e, const char *what) const
+{
+    if (e == cudaSuccess) return CDS_OK;
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? CDS_ERR_OOM : CDS_ERR_CUDA, msg);
+}
+
+#define CDS_TRY(expr) do { cds_status _s = (expr); if (_s != CDS_OK) return _s; } while (0)
+#define CDS_CUDA(ctx, expr) CDS_TRY((ctx)->check((expr), #expr))
+
+cds_status cds_ctx::ensure_staging(DevState &d, size_t bytes)
+{
+    if (d.staging_bytes >= bytes) return CDS_OK;
+    CDS_CUDA(this, cudaSetDevice(d.dev));
+    if (d.staging) { CDS_CUDA(this, cudaStreamSynchronize(d.stream)); cudaFree(d.staging); d.staging = nullptr; d.staging_bytes = 0; }
+    CDS_CUDA(this, cudaMalloc(&d.staging, bytes + 64));
+    d.staging_bytes = bytes;
+    return CDS_OK;
+}
+
+cds_status cds_ctx::ensure_pinned(DevState &d, size_t bytes)
+{
+    if (d.h_pinned_bytes >= bytes) return CDS_OK;
+    CDS_CUDA(this, cudaSetDevice(d.dev));
+    if (d.h_pinned) { CDS_CUDA(this, cudaStreamSynchronize(d.stream)); cudaFreeHost(d.h_pinned); d.h_pinned = nullptr; d.h_pinned_bytes = 0; }
+    CDS_CUDA(this, cudaMallocHost(&d.h_pinned, bytes));
+    d.h_pinned_bytes = bytes;
+    return CDS_OK;
+}
+
+cds_status cds_ctx::class_table_on(DevState &d, double tol, const cds_class_interval **out)
+{
+    uint64_t key;
+    std::memcpy(&key, &tol, sizeof key);
+    auto it = d.d_class_tabs.find(key);
+    if (it != d.d_class_tabs.end()) { *out = it->second; return CDS_OK; }
+    std::shared_ptr<const ClassTable> t = class_table(tol);
+    if (!t) return fail(CDS_ERR_UNSUPPORTED, "match-interval table self-check failed for this zTolerance");
+    cds_class_interval *dp = nullptr;
+    CDS_CUDA(this, cudaSetDevice(d.dev));
+    CDS_CUDA(this, cudaMalloc(&dp, t->iv.size() * sizeof(cds_class_interval)));
+    CDS_CUDA(this, cudaMemcpyAsync(dp, t->iv.data(), t->iv.size() * sizeof(cds_class_interval), cudaMemcpyHostToDevice, d.stream));
+    CDS_CUDA(this, cudaStreamSynchronize(d.stream));
+    d.d_class_tabs[key] = dp;
+    *out = dp;
+    return CDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ context
+extern "C" int32_t cds_abi_version(void) { return CDSGPU_ABI_VERSION; }
+
+extern "C" const char *cds_last_error(const cds_ctx *ctx)
+{
+    if (ctx) {
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        g_tls_err = ctx->err;
+    }
+    return g_tls_err.c_str();
+}
+
+extern "C" cds_status cds_ctx_create(const int32_t *device_ids, int32_t n_dev, cds_ctx **out)
+{
+    if (!out) { set_tls_error("cds_ctx_create: out is NULL"); return CDS_ERR_BAD_ARG; }
+    *out = nullptr;
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible == 0) {
+        cudaGetLastError();
+        set_tls_error(std::string("cds_ctx_create: no CUDA device (") + (e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)) +
+                      "); libcdsgpu has no CPU fallback");
+        return CDS_ERR_NO_DEVICE;
+    }
+    if (n_dev < 0) { set_tls_error("cds_ctx_create: n_dev < 0"); return CDS_ERR_BAD_ARG; }
+    if (n_dev == 0) { n_dev = visible; device_ids = nullptr; }
+    auto ctx = new cds_ctx();
+    for (int i = 0; i < n_dev; i++) {
+        int id = device_ids ? device_ids[i] : i;
+        if (id < 0 || id >= visible) {
+            set_tls_error("cds_ctx_create: device id out of range");
+            cds_ctx_destroy(ctx);
+            return CDS_ERR_NO_DEVICE;
+        }
+        DevState d;
+        d.dev = id;
+        ctx->devs.push_back(d);
+    }
+    const RatioTable &rt = ratio_table();
+    if ((int) rt.ratios.size() != CDS_NUM_RANKS) {
+        set_tls_error("cds_ctx_create: ratio table self-check failed");
+        cds_ctx_destroy(ctx);
+        return CDS_ERR_UNSUPPORTED;
+    }
+    for (DevState &d : ctx->devs) {
+        cds_status s = ctx->check(cudaSetDevice(d.dev), "cudaSetDevice");
+        if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev0), "cudaEventCreate");
+        if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev1), "cudaEventCreate");
+        if (s == CDS_OK) s = ctx->check(cudaMalloc(&d.d_rank_tab, rt.rank.size() * sizeof(uint16_t)), "cudaMalloc(rank table)");
+        if (s == CDS_OK) s = ctx->check(cudaMemcpy(d.d_rank_tab, rt.rank.data(), rt.rank.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "cudaMemcpy(rank table)");
+        if (s != CDS_OK) { cds_ctx_destroy(ctx); return s; }
+    }
+    // peer access between the context's devices (mask replication); failure is not fatal
+    for (DevState &a : ctx->devs)
+        for (DevState &b : ctx->devs) {
+            if (a.dev == b.dev) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a.dev, b.dev) == cudaSuccess && can) {
+                cudaSetDevice(a.dev);
+                cudaDeviceEnablePeerAccess(b.dev, 0);
+                cudaGetLastError();
+            }
+        }
+    *out = ctx;
+    return CDS_OK;
+}
+
+extern "C" void cds_ctx_destroy(cds_ctx *ctx)
+{
+    if (!ctx) return;
+    for (DevState &d : ctx->devs) {
+        if (cudaSetDevice(d.dev) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.d_rank_tab) cudaFree(d.d_rank_tab);
+        for (auto &kv : d.d_class_tabs) cudaFree(kv.second);
+        if (d.staging) cudaFree(d.staging);
+        if (d.h_pinned) cudaFreeHost(d.h_pinned);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    cudaGetLastError();
+    delete ctx;
+}
+
+extern "C" int32_t cds_ctx_num_devices(const cds_ctx *ctx) { return ctx ? (int32_t) ctx->devs.size() : 0; }
+
+extern "C" cds_status cds_host_alloc(cds_ctx *ctx, uint64_t bytes, void **out)
+{
+    if (!ctx || !out) { set_tls_error("cds_host_alloc: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    *out = nullptr;
+    CDS_CUDA(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CDS_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return CDS_OK;
+}
+
+extern "C" cds_status cds_host_free(cds_ctx *ctx, void *p)
+{
+    if (!ctx) { set_tls_error("cds_host_free: NULL ctx"); return CDS_ERR_BAD_ARG; }
+    if (!p) return CDS_OK;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CDS_CUDA(ctx, cudaFreeHost(p));
+    return CDS_OK;
+}
+
+extern "C" cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out)
+{
+    if (!ctx || !out) { set_tls_error("cds_get_last_stats: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    *out = ctx->stats;
+    return CDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ library
+static int choose_pitch(int W)
+{
+    // multiple of 4 words (16-byte rows for bulk copies), at least CDS_MIN_PAD_COLS pad words, and pitch mod 32 in
+    // {8, 24} so that the same column of consecutive rows falls into different shared-memory banks
+    int p = (W + CDS_MIN_PAD_COLS + 3) / 4 * 4;
+    while ((p % 32) != 8 && (p % 32) != 24) p += 4;
+    return p;
+}
+
+int64_t cds_library::local_size(int dev) const
+{
+    // number of global indices < size that map to dev
+    int D = n_dev();
+    int64_t full_blocks = size / kLibBlock;
+    int64_t rem = size % kLibBlock;
+    int64_t blocks_on_dev = full_blocks / D + ((full_blocks % D) > dev ? 1 : 0);
+    int64_t n = blocks_on_dev * kLibBlock;
+    if (rem && (full_blocks % D) == dev) n += rem;
+    return n;
+}
+
+cds_status cds_library::bake(int threshold)
+{
+    if (threshold == baked_threshold) return CDS_OK;
+    for (int d = 0; d < n_dev(); d++) {
+        DevState &ds = ctx->devs[d];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        int64_t n_local = local_size(d);
+        if (n_local == 0) continue;
+        launch_rebake(shards[d].planes, g.total_words(n_local), threshold, ds.stream);
+        ctx->stats.kernel_launches++;
+        CDS_CUDA(ctx, cudaGetLastError());
+    }
+    for (int d = 0; d < n_dev(); d++) {
+        CDS_CUDA(ctx, cudaSetDevice(ctx->devs[d].dev));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ctx->devs[d].stream));
+    }
+    baked_threshold = threshold;
+    return CDS_OK;
+}
+
+extern "C" cds_status cds_library_create(cds_ctx *ctx, int32_t width, int32_t height, int64_t capacity, cds_library **out)
+{
+    if (!ctx || !out) { set_tls_error("cds_library_create: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || width > 16384 || height > 16384 || capacity <= 0)
+        return ctx->fail(CDS_ERR_BAD_ARG, "cds_library_create: width/height must be in 1..16384 and capacity > 0");
+    auto lib = new cds_library();
+    lib->ctx = ctx;
+    lib->g.W = width;
+    lib->g.H = height;
+    lib->g.pitch = choose_pitch(width);
+    lib->g.guard = CDS_GUARD_ROWS;
+    lib->capacity = capacity;
+    lib->baked_threshold = 20;
+    int D = (int) ctx->devs.size();
+    lib->shards.resize(D);
+    int64_t blocks = (capacity + kLibBlock - 1) / kLibBlock;
+    int64_t blocks_per_dev = (blocks + D - 1) / D;
+    for (int d = 0; d < D; d++) {
+        DevState &ds = ctx->devs[d];
+        cds_status s = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+        int64_t cap_local = blocks_per_dev * kLibBlock;
+        if (cap_local > capacity && D == 1) cap_local = capacity;
+        size_t words = lib->g.total_words(cap_local);
+        if (s == CDS_OK) s = ctx->check(cudaMalloc(&lib->shards[d].planes, words * sizeof(uint32_t)), "cudaMalloc(library planes)");
+        if (s == CDS_OK) {
+            lib->shards[d].cap_local = cap_local;
+            launch_fill_words(lib->shards[d].planes, words, CDS_CODE_PAD_WORD, ds.stream);
+            s = ctx->check(cudaGetLastError(), "fill_words_kernel");
+        }
+        if (s != CDS_OK) { cds_library_destroy(lib); return s; }
+    }
+    for (int d = 0; d < D; d++) {
+        cudaSetDevice(ctx->devs[d].dev);
+        cds_status s = ctx->check(cudaStreamSynchronize(ctx->devs[d].stream), "library init");
+        if (s != CDS_OK) { cds_library_destroy(lib); return s; }
+    }
+    *out = lib;
+    return CDS_OK;
+}
+
+extern "C" void cds_library_destroy(cds_library *lib)
+{
+    if (!lib) return;
+    std::lock_guard<std::recursive_mutex> lk(lib->ctx->mu);
+    for (int d = 0; d < lib->n_dev(); d++) {
+        if (!lib->shards[d].planes) continue;
+        cudaSetDevice(lib->ctx->devs[d].dev);
+        cudaStreamSynchronize(lib->ctx->devs[d].stream);
+        cudaFree(lib->shards[d].planes);
+    }
+    cudaGetLastError();
+    delete lib;
+}
+
+extern "C" int64_t cds_library_size(const cds_library *lib) { return lib ? lib->size : 0; }
+
+extern "C" cds_status cds_library_clear(cds_library *lib)
+{
+    if (!lib) { set_tls_error("cds_library_clear: NULL library"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(lib->ctx->mu);
+    lib->size = 0;
+    return CDS_OK;
+}
+
+// Upload `n` RGB images that occupy consecutive global indices starting at lib->size.  `src` supplies the pixels of a run
+// of images [i0, i0+cnt) (relative to the call) into a device staging pointer; used by add_rgb (H2D copy) and by the
+// synthetic generator (kernel).
+namespace cds {
+cds_status library_append(cds_library *lib, int64_t n,
+                          const std::function<cds_status(DevState &, int64_t i0, int64_t cnt, uint8_t *d_rgb)> &src,
+                          int64_t *first_index)
+{
+    cds_ctx *ctx = lib->ctx;
+    if (n < 0) return ctx->fail(CDS_ERR_BAD_ARG, "negative image count");
+    if (lib->size + n > lib->capacity) return ctx->fail(CDS_ERR_CAPACITY, "library capacity exceeded");
+    if (first_index) *first_index = lib->size;
+    const size_t img_bytes = (size_t) lib->g.W * lib->g.H * 3;
+    int64_t done = 0;
+    while (done < n) {
+        int64_t gidx = lib->size + done;
+        int64_t in_block = kLibBlock - gidx % kLibBlock;
+        int64_t cnt = std::min<int64_t>(in_block, n - done);
+        int dev; int64_t local;
+        lib->locate(gidx, dev, local);
+        DevState &ds = ctx->devs[dev];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        CDS_TRY(ctx->ensure_staging(ds, (size_t) kLibBlock * img_bytes));
+        // the staging buffer is reused by consecutive runs on the same device: stream order keeps copy k+1 behind encode k
+        CDS_TRY(src(ds, done, cnt, (uint8_t *) ds.staging));
+        launch_encode_rgb((const uint8_t *) ds.staging, cnt, lib->shards[dev].planes, lib->g, local, ds.d_rank_tab,
+                          lib->baked_threshold, ds.stream);
+        ctx->stats.kernel_launches++;
+        CDS_CUDA(ctx, cudaGetLastError());
+        done += cnt;
+    }
+    for (DevState &ds : ctx->devs) {
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+    }
+    lib->size += n;
+    return CDS_OK;
+}
+}  // namespace cds
+
+extern "C" cds_status cds_library_add_rgb(cds_library *lib, const uint8_t *rgb, int64_t n, int64_t *first_index)
+{
+    if (!lib) { set_tls_error("cds_library_add_rgb: NULL library"); return CDS_ERR_BAD_ARG; }
+    cds_ctx *ctx = lib->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!rgb && n > 0) return ctx->fail(CDS_ERR_BAD_ARG, "cds_library_add_rgb: rgb is NULL");
+    const size_t img_bytes = (size_t) lib->g.W * lib->g.H * 3;
+    return library_append(lib, n, [&](DevState &ds, int64_t i0, int64_t cnt, uint8_t *d_rgb) -> cds_status {
+        CDS_CUDA(ctx, cudaMemcpyAsync(d_rgb, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, ds.stream));
+        ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
+        return CDS_OK;
+    }, first_index);
+}
+
+// ------------------------------------------------------------------------------------------------------------------ mask sets
+static cds_status make_shift_set(int xy_shift, int mirror, ShiftSet &out)
+{
+    // offsets in the order of generateShiftedMasks (API/cds/PixelMatchColorDepthSearchAlgorithm.java:113-130); duplicates of
+    // (0,0) in outer rings are dropped, they cannot change a max
+    out.n = 0;
+    out.mirror = mirror ? 1 : 0;
+    if (xy_shift < 2) { out.dx[0] = 0; out.dy[0] = 0; out.n = 1; return CDS_OK; }
+    for (int i = 2; i <= xy_shift; i += 2)
+        for (int xx = -i; xx <= i; xx += i)
+            for (int yy = -i; yy <= i; yy += i) {
+                if (i > 2 && xx == 0 && yy == 0) continue;
+                if (out.n >= CDS_MAX_SHIFT_OFFSETS) return CDS_ERR_UNSUPPORTED;
+                out.dx[out.n] = (int8_t) xx;
+                out.dy[out.n] = (int8_t) yy;
+                out.n++;
+            }
+    return CDS_OK;
+}
+
+extern "C" cds_status cds_maskset_create(cds_ctx *ctx, int32_t width, int32_t height, const cds_pixparams *params, cds_maskset **out)
+{
+    if (!ctx || !out || !params) { set_tls_error("cds_maskset_create: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || width > 16384 || height > 16384)
+        return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: width/height must be in 1..16384");
+    if (params->xy_shift & 1) return ctx->fail(CDS_ERR_BAD_ARG, "XY shift parameter must be an even number.");
+    if (params->xy_shift < 0) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: xy_shift < 0");
+    if (params->xy_shift > CDS_MAX_XY_SHIFT) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: xy_shift > CDS_MAX_XY_SHIFT");
+    if (params->n_rects < 0 || params->n_rects > CDS_MAX_RECTS) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: n_rects out of range");
+    if (!(params->z_tolerance < 1000.0) && !std::isnan(params->z_tolerance))
+        return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: z_tolerance >= 1000 is not supported");
+    auto ms = new cds_maskset();
+    ms->ctx = ctx;
+    ms->W = width;
+    ms->H = height;
+    ms->params = *params;
+    if (make_shift_set(params->xy_shift, params->mirror, ms->shifts) != CDS_OK) {
+        delete ms;
+        return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: too many shift offsets");
+    }
+    ms->rects.n = params->n_rects;
+    for (int i = 0; i < params->n_rects; i++) {
+        ms->rects.x0[i] = params->rects[i].x0; ms->rects.y0[i] = params->rects[i].y0;
+        ms->rects.x1[i] = params->rects[i].x1; ms->rects.y1[i] = params->rects[i].y1;
+    }
+    ms->d_descs.assign(ctx->devs.size(), nullptr);
+    // build (or fetch) the interval table now so that a bad tolerance fails here
+    for (DevState &ds : ctx->devs) {
+        const cds_class_interval *tab;
+        cds_status s = ctx->class_table_on(ds, params->z_tolerance, &tab);
+        if (s != CDS_OK) { delete ms; return s; }
+    }
+    *out = ms;
+    return CDS_OK;
+}
+
+extern "C" void cds_maskset_destroy(cds_maskset *ms)
+{
+    if (!ms) return;
+    cds_ctx *ctx = ms->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    for (size_t d = 0; d < ctx->devs.size(); d++) {
+        cudaSetDevice(ctx->devs[d].dev);
+        cudaStreamSynchronize(ctx->devs[d].stream);
+        for (auto &b : ms->batches) {
+            if (d < b.records.size() && b.records[d]) cudaFree(b.records[d]);
+            if (d < b.rowstart.size() && b.rowstart[d]) cudaFree(b.rowstart[d]);
+        }
+        if (ms->d_descs[d]) cudaFree(ms->d_descs[d]);
+    }
+    cudaGetLastError();
+    delete ms;
+}
+
+extern "C" int32_t cds_maskset_size(const cds_maskset *ms) { return ms ? (int32_t) ms->sizes.size() : 0; }
+
+extern "C" cds_status cds_maskset_get_mask_sizes(const cds_maskset *ms, int32_t *sizes_out)
+{
+    if (!ms || !sizes_out) { set_tls_error("cds_maskset_get_mask_sizes: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ms->ctx->mu);
+    std::copy(ms->sizes.begin(), ms->sizes.end(), sizes_out);
+    return CDS_OK;
+}
+
+extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, int32_t n, int32_t *mask_size_out)
+{
+    if (!ms) { set_tls_error("cds_maskset_add_rgb: NULL mask set"); return CDS_ERR_BAD_ARG; }
+    cds_ctx *ctx = ms->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || (!rgb && n > 0)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_rgb: bad arguments");
+    const int D = (int) ctx->devs.size();
+    const size_t img_bytes = (size_t) ms->W * ms->H * 3;
+    const int H = ms->H;
+    const int kChunk = 64;
+    DevState &d0 = ctx->devs[0];
+    for (int i0 = 0; i0 < n; i0 += kChunk) {
+        const int cnt = std::min(kChunk, n - i0);
+        CDS_CUDA(ctx, cudaSetDevice(d0.dev));
+        CDS_TRY(ctx->ensure_staging(d0, (size_t) kChunk * img_bytes));
+        const cds_class_interval *class_tab;
+        CDS_TRY(ctx->class_table_on(d0, ms->params.z_tolerance, &class_tab));
+        cds_maskset::Batch b;
+        b.n = cnt;
+        b.records.assign(D, nullptr);
+        b.rowstart.assign(D, nullptr);
+        const size_t rs_words = (size_t) cnt * (H + 1);
+        int32_t *d_sizes = nullptr;
+        uint64_t *d_off = nullptr;
+        cds_status st = CDS_OK;
+        auto cleanup = [&]() {
+            if (d_sizes) cudaFree(d_sizes);
+            if (d_off) cudaFree(d_off);
+        };
+        auto bail = [&](cds_status s) {
+            cleanup();
+            for (int d = 0; d < D; d++) {
+                cudaSetDevice(ctx->devs[d].dev);
+                if (b.records[d]) cudaFree(b.records[d]);
+                if (b.rowstart[d]) cudaFree(b.rowstart[d]);
+            }
+            return s;
+        };
+        if ((st = ctx->check(cudaMemcpyAsync(d0.staging, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, d0.stream), "mask upload")) != CDS_OK) return bail(st);
+        ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
+        if ((st = ctx->check(cudaMalloc(&b.rowstart[0], rs_words * sizeof(uint32_t)), "cudaMalloc(rowstart)")) != CDS_OK) return bail(st);
+        if ((st = ctx->check(cudaMalloc(&d_sizes, cnt * sizeof(int32_t)), "cudaMalloc(sizes)")) != CDS_OK) return bail(st);
+        if ((st = ctx->check(cudaMalloc(&d_off, cnt * sizeof(uint64_t)), "cudaMalloc(offsets)")) != CDS_OK) return bail(st);
+        launch_mask_count_rows((const uint8_t *) d0.staging, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, b.rowstart[0], d0.stream);
+        launch_mask_scan_rows(b.rowstart[0], cnt, H, d_sizes, d0.stream);
+        ctx->stats.kernel_launches += 2;
+        std::vector<int32_t> sizes(cnt);
+        if ((st = ctx->check(cudaMemcpyAsync(sizes.data(), d_sizes, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d0.stream), "sizes D2H")) != CDS_OK) return bail(st);
+        if ((st = ctx->check(cudaStreamSynchronize(d0.stream), "mask count")) != CDS_OK) return bail(st);
+        b.rec_offset.resize(cnt);
+        uint64_t total = 0;
+        for (int i = 0; i < cnt; i++) { b.rec_offset[i] = total; total += (uint64_t) sizes[i]; }
+        b.total_records = total;
+        if ((st = ctx->check(cudaMalloc(&b.records[0], std::max<uint64_t>(total, 1) * sizeof(cds_mask_record)), "cudaMalloc(mask records)")) != CDS_OK) return bail(st);
+        if ((st = ctx->check(cudaMemcpyAsync(d_off, b.rec_offset.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, d0.stream), "offsets H2D")) != CDS_OK) return bail(st);
+        launch_mask_write_records((const uint8_t *) d0.staging, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, b.rowstart[0], d_off,
+                                  d0.d_rank_tab, class_tab, b.records[0], d0.stream);
+        ctx->stats.kernel_launches++;
+        if ((st = ctx->check(cudaGetLastError(), "mask_write_records_kernel")) != CDS_OK) return bail(st);
+        if ((st = ctx->check(cudaStreamSynchronize(d0.stream), "mask write")) != CDS_OK) return bail(st);
+        // replicate on the other devices
+        for (int d = 1; d < D; d++) {
+            DevState &dd = ctx->devs[d];
+            if ((st = ctx->check(cudaSetDevice(dd.dev), "cudaSetDevice")) != CDS_OK) return bail(st);
+            if ((st = ctx->check(cudaMalloc(&b.rowstart[d], rs_words * sizeof(uint32_t)), "cudaMalloc(rowstart)")) != CDS_OK) return bail(st);
+            if ((st = ctx->check(cudaMalloc(&b.records[d], std::max<uint64_t>(total, 1) * sizeof(cds_mask_record)), "cudaMalloc(mask records)")) != CDS_OK) return bail(st);
+            if ((st = ctx->check(cudaMemcpyPeerAsync(b.rowstart[d], dd.dev, b.rowstart[0], d0.dev, rs_words * sizeof(uint32_t), dd.stream), "peer copy")) != CDS_OK) return bail(st);
+            if (total && (st = ctx->check(cudaMemcpyPeerAsync(b.records[d], dd.dev, b.records[0], d0.dev, total * sizeof(cds_mask_record), dd.stream), "peer copy")) != CDS_OK) return bail(st);
+        }
+        for (int d = 1; d < D; d++) {
+            cudaSetDevice(ctx->devs[d].dev);
+            if ((st = ctx->check(cudaStreamSynchronize(ctx->devs[d].stream), "mask replicate")) != CDS_OK) return bail(st);
+        }
+        cudaSetDevice(d0.dev);
+        cleanup();
+        for (int i = 0; i < cnt; i++) {
+            ms->sizes.push_back(sizes[i]);
+            if (mask_size_out) mask_size_out[i0 + i] = sizes[i];
+        }
+        ms->batches.push_back(std::move(b));
+        ms->descs_dirty = true;
+    }
+    return CDS_OK;
+}
+
+cds_status cds_maskset::sync_descs()
+{
+    if (!descs_dirty) return CDS_OK;
+    const int D = (int) ctx->devs.size();
+    const int M = (int) sizes.size();
+    for (int d = 0; d < D; d++) {
+        DevState &ds = ctx->devs[d];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        std::vector<MaskDesc> h(std::max(M, 1));
+        int mi = 0;
+        for (const Batch &b : batches)
+            for (int i = 0; i < b.n; i++, mi++) {
+                h[mi].records = b.records[d] + b.rec_offset[i];
+                h[mi].rowstart = b.rowstart[d] + (size_t) i * (H + 1);
+                h[mi].P = sizes[mi];
+                h[mi].pad = 0;
+            }
+        if (d_descs[d]) { CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream)); cudaFree(d_descs[d]); d_descs[d] = nullptr; }
+        CDS_CUDA(ctx, cudaMalloc(&d_descs[d], h.size() * sizeof(MaskDesc)));
+        CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+    }
+    descs_dirty = false;
+    return CDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ searches
+namespace {
+
+struct SearchPlan {
+    bool use_band;
+};
+
+// Runs the match kernel of one device for masks [m0, m0+mc) against the device's local targets [0, n_local):
+// d_scores[(m - m0) * n_local + t] = score word.
+cds_status launch_match(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, int d, int m0, int mc, int64_t n_local,
+                        int32_t *d_scores)
+{
+    DevState &ds = ctx->devs[d];
+    const bool band_ok = band_kernel_supported(ms->params.xy_shift, lib->g) && mc >= band_min_masks();
+    cudaEventRecord(ds.ev0, ds.stream);
+    if (band_ok) {
+        int launches = launch_pixelmatch_band(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local,
+                                              ms->params.xy_shift, ms->params.mirror != 0, d_scores, ds.stream);
+        ctx->stats.kernel_launches += launches;
+        ctx->stats.match_kernel_launches += launches;
+    } else {
+        launch_pixelmatch_gather(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local, ms->shifts, d_scores, ds.stream);
+        int launches = (mc + 32767) / 32768;
+        ctx->stats.kernel_launches += launches;
+        ctx->stats.match_kernel_launches += launches;
+    }
+    cudaEventRecord(ds.ev1, ds.stream);
+    return ctx->check(cudaGetLastError(), "pixel match kernel");
+}
+
+cds_status check_search_args(cds_ctx *ctx, const cds_maskset *ms, const cds_library *lib)
+{
+    if (ms->ctx != ctx || lib->ctx != ctx) return ctx->fail(CDS_ERR_BAD_ARG, "mask set / library belong to another context");
+    if (ms->W != lib->g.W || ms->H != lib->g.H) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "Invalid image size - target's image size (%d, %d) must match query's image size: (%d, %d)",
+                 ms->W, ms->H, lib->g.W, lib->g.H);
+        return ctx->fail(CDS_ERR_SIZE_MISMATCH, buf);
+    }
+    return CDS_OK;
+}
+
+void reset_stats(cds_ctx *ctx)
+{
+    ctx->stats = cds_search_stats{};
+}
+
+}  // namespace
+
+extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cds_library *lib, int32_t *scores, uint8_t *mirrored)
+{
+    if (!ctx || !ms_c || !lib) { set_tls_error("cds_search_dense: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
+    CDS_TRY(check_search_args(ctx, ms, lib));
+    const int M = (int) ms->sizes.size();
+    const int64_t T = lib->size;
+    if (M == 0 || T == 0) return CDS_OK;
+    if (!scores) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_dense: scores is NULL");
+    reset_stats(ctx);
+    CDS_TRY(ms->sync_descs());
+    CDS_TRY(lib->bake(ms->params.data_threshold));
+    const int D = lib->n_dev();
+    // mask chunking bounds the per-device score buffer to ~256 MiB
+    std::vector<int32_t *> d_scores(D, nullptr);
+    cds_status st = CDS_OK;
+    int64_t max_local = 0;
+    for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
+    int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 64 << 20) / std::max<int64_t>(max_local, 1)));
+    auto free_all = [&]() {
+        for (int d = 0; d < D; d++) if (d_scores[d]) { cudaSetDevice(ctx->devs[d].dev); cudaFree(d_scores[d]); }
+    };
+    for (int d = 0; d < D && st == CDS_OK; d++) {
+        st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
+        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_scores[d], (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t)), "cudaMalloc(scores)");
+        if (st == CDS_OK) st = ctx->ensure_pinned(ctx->devs[d], (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t));
+    }
+    double match_ms = 0;
+    for (int m0 = 0; m0 < M && st == CDS_OK; m0 += mchunk) {
+        const int mc = std::min(mchunk, M - m0);
+        for (int d = 0; d < D && st == CDS_OK; d++) {
+            const int64_t nl = lib->local_size(d);
+            if (nl == 0) continue;
+            DevState &ds = ctx->devs[d];
+            st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+            if (st == CDS_OK) st = launch_match(ctx, ms, lib, d, m0, mc, nl, d_scores[d]);
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(ds.h_pinned, d_scores[d], (size_t) mc * nl * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "scores D2H");
+            ctx->stats.d2h_bytes += (int64_t) mc * nl * (int64_t) sizeof(int32_t);
+        }
+        double chunk_ms = 0;
+        for (int d = 0; d < D && st == CDS_OK; d++) {
+            const int64_t nl = lib->local_size(d);
+            if (nl == 0) continue;
+            DevState &ds = ctx->devs[d];
+            cudaSetDevice(ds.dev);
+            st = ctx->check(cudaStreamSynchronize(ds.stream), "pixel match");
+            if (st != CDS_OK) break;
+            float ms_f = 0;
+            cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev1);
+            chunk_ms = std::max(chunk_ms, (double) ms_f);
+            const int32_t *h = (const int32_t *) ds.h_pinned;
+            for (int mi = 0; mi < mc; mi++)
+                for (int64_t l = 0; l < nl; l++) {
+                    int32_t w = h[(size_t) mi * nl + l];
+                    size_t o = (size_t) (m0 + mi) * T + lib->global_of(d, l);
+                    scores[o] = w & ~CDS_SCORE_MIRROR_BIT;
+                    if (mirrored) mirrored[o] = (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0;
+                }
+        }
+        match_ms += chunk_ms;
+    }
+    free_all();
+    ctx->stats.match_kernel_ms = match_ms;
+    ctx->stats.total_device_ms = match_ms;
+    ctx->stats.comparisons = (int64_t) M * T;
+    return st;
+}
+
+// smallest score s in [1, P] with ColorMIPSearch.isMatch true (API/cds/ColorMIPSearch.java:42-45); P+1 when none.
+static int32_t min_matching_score(int32_t P, double pct_positive_pixels)
+{
+    if (P <= 0) return 1;   // empty mask scores 0 and never matches (score > 0 fails)
+    const double thr = pct_positive_pixels / 100;
+    auto ok = [&](int32_t s) { return s > 0 && (double) (float) ((double) s / (double) P) > thr; };
+    if (!ok(P)) return P + 1;
+    int32_t a = 1, b = P;    // invariant: ok(b)
+    while (a < b) { int32_t mid = a + (b - a) / 2; if (ok(mid)) b = mid; else a = mid + 1; }
+    return b;
+}
+
+extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds_library *lib, int32_t k, double pct_positive_pixels,
+                                      int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
+{
+    if (!ctx || !ms_c || !lib) { set_tls_error("cds_search_topk: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
+    CDS_TRY(check_search_args(ctx, ms, lib));
+    if (k <= 0 || k > topk_max_k()) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_topk: k must be in 1..4096");
+    const int M = (int) ms->sizes.size();
+    const int64_t T = lib->size;
+    if (M == 0) return CDS_OK;
+    if (!out_score || !out_target || !out_count) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_topk: NULL output");
+    reset_stats(ctx);
+    for (int m = 0; m < M; m++) out_count[m] = 0;
+    if (T == 0) return CDS_OK;
+    CDS_TRY(ms->sync_descs());
+    CDS_TRY(lib->bake(ms->params.data_threshold));
+    const int D = lib->n_dev();
+    std::vector<int32_t> min_score(M);
+    for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);
+
+    int64_t max_local = 0;
+    for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
+    const int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 512 << 20) / std::max<int64_t>(max_local, 1)));
+    std::vector<int32_t *> d_scores(D, nullptr);
+    std::vector<int32_t *> d_min(D, nullptr);
+    std::vector<uint64_t *> d_keys(D, nullptr);
+    std::vector<int32_t *> d_counts(D, nullptr);
+    cds_status st = CDS_OK;
+    auto free_all = [&]() {
+        for (int d = 0; d < D; d++) {
+            cudaSetDevice(ctx->devs[d].dev);
+            if (d_scores[d]) cudaFree(d_scores[d]);
+            if (d_min[d]) cudaFree(d_min[d]);
+            if (d_keys[d]) cudaFree(d_keys[d]);
+            if (d_counts[d]) cudaFree(d_counts[d]);
+        }
+    };
+    const size_t keys_bytes = (size_t) M * k * sizeof(uint64_t);
+    for (int d = 0; d < D && st == CDS_OK; d++) {
+        DevState &ds = ctx->devs[d];
+        st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_scores[d], (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t)), "cudaMalloc(scores)");
+        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_min[d], M * sizeof(int32_t)), "cudaMalloc(min scores)");
+        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_keys[d], keys_bytes), "cudaMalloc(topk keys)");
+        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_counts[d], M * sizeof(int32_t)), "cudaMalloc(topk counts)");
+        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_min[d], min_score.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream), "min scores H2D");
+        if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_counts[d], 0, M * sizeof(int32_t), ds.stream), "memset");
+        if (st == CDS_OK) st = ctx->ensure_pinned(ds, keys_bytes + M * sizeof(int32_t));
+    }
+    double match_ms = 0, total_ms = 0;
+    for (int m0 = 0; m0 < M && st == CDS_OK; m0 += mchunk) {
+        const int mc = std::min(mchunk, M - m0);
+        for (int d = 0; d < D && st == CDS_OK; d++) {
+            const int64_t nl = lib->local_size(d);
+            if (nl == 0) continue;
+            DevState &ds = ctx->devs[d];
+            st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+            if (st == CDS_OK) st = launch_match(ctx, ms, lib, d, m0, mc, nl, d_scores[d]);
+            if (st == CDS_OK) {
+                launch_topk(d_scores[d], mc, nl, d_min[d] + m0, k, d_keys[d] + (size_t) m0 * k, d_counts[d] + m0, ds.stream);
+                ctx->stats.kernel_launches++;
+                st = ctx->check(cudaGetLastError(), "topk kernel");
+            }
+        }
+        double chunk_ms = 0;
+        for (int d = 0; d < D && st == CDS_OK; d++) {
+            if (lib->local_size(d) == 0) continue;
+            DevState &ds = ctx->devs[d];
+            cudaSetDevice(ds.dev);
+            st = ctx->check(cudaStreamSynchronize(ds.stream), "pixel match + topk");
+            if (st != CDS_OK) break;
+            float ms_f = 0;
+            cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev1);
+            chunk_ms = std::max(chunk_ms, (double) ms_f);
+        }
+        match_ms += chunk_ms;
+    }
+    total_ms = match_ms;
+    // read back per-device lists and merge on the host (no collective: nothing is reduced across devices)
+    std::vector<std::vector<uint64_t>> h_keys(D);
+    std::vector<std::vector<int32_t>> h_counts(D);
+    for (int d = 0; d < D && st == CDS_OK; d++) {
+        if (lib->local_size(d) == 0) continue;
+        DevState &ds = ctx->devs[d];
+        cudaSetDevice(ds.dev);
+        uint8_t *hp = (uint8_t *) ds.h_pinned;
+        st = ctx->check(cudaMemcpyAsync(hp, d_keys[d], keys_bytes, cudaMemcpyDeviceToHost, ds.stream), "keys D2H");
+        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(hp + keys_bytes, d_counts[d], M * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "counts D2H");
+        ctx->stats.d2h_bytes += (int64_t) keys_bytes + (int64_t) M * 4;
+    }
+    for (int d = 0; d < D && st == CDS_OK; d++) {
+        if (lib->local_size(d) == 0) continue;
+        DevState &ds = ctx->devs[d];
+        cudaSetDevice(ds.dev);
+        st = ctx->check(cudaStreamSynchronize(ds.stream), "topk D2H");
+        if (st != CDS_OK) break;
+        const uint8_t *hp = (const uint8_t *) ds.h_pinned;
+        h_keys[d].assign((const uint64_t *) hp, (const uint64_t *) hp + (size_t) M * k);
+        h_counts[d].assign((const int32_t *) (hp + keys_bytes), (const int32_t *) (hp + keys_bytes) + M);
+    }
+    if (st == CDS_OK) {
+        struct Item { int32_t score; int64_t target; uint8_t mir; };
+        std::vector<Item> items;
+        for (int m = 0; m < M; m++) {
+            items.clear();
+            for (int d = 0; d < D; d++) {
+                if (h_counts[d].empty()) continue;
+                int c = std::min(h_counts[d][m], k);
+                for (int i = 0; i < c; i++) {
+                    uint64_t key = h_keys[d][(size_t) m * k + i];
+                    Item it;
+                    topk_decode_key(key, it.score, it.target, it.mir);
+                    it.target = lib->global_of(d, it.target);
+                    items.push_back(it);
+                }
+            }
+            std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+                if (a.score != b.score) return a.score > b.score;
+                return a.target < b.target;
+            });
+            int c = (int) std::min<size_t>(items.size(), (size_t) k);
+            out_count[m] = c;
+            for (int i = 0; i < c; i++) {
+                out_score[(size_t) m * k + i] = items[i].score;
+                out_target[(size_t) m * k + i] = items[i].target;
+                if (out_mirrored) out_mirrored[(size_t) m * k + i] = items[i].mir;
+            }
+        }
+    }
+    free_all();
+    ctx->stats.match_kernel_ms = match_ms;
+    ctx->stats.total_device_ms = total_ms;
+    ctx->stats.comparisons = (int64_t) M * T;
+    return st;
+}
+
+extern "C" cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, int32_t mask_index, const uint8_t *target_rgb,
+                                         int32_t target_width, int32_t target_height,
+                                         int32_t *score_out, double *ratio_out, int32_t *mirrored_out)
+{
+    if (!ctx || !ms || !score_out || !ratio_out || !mirrored_out) { set_tls_error("cds_score_pair_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (mask_index < 0 || mask_index >= (int) ms->sizes.size()) return ctx->fail(CDS_ERR_BAD_ARG, "cds_score_pair_rgb: mask index out of range");
+    const int P = ms->sizes[mask_index];
+    if (P == 0) { *score_out = 0; *ratio_out = 0; *mirrored_out = 0; return CDS_OK; }   // PixelMatch...:169-170 (before the size check)
+    if (target_width != ms->W || target_height != ms->H) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "Invalid image size - target's image size (%d, %d) must match query's image size: (%d, %d)",
+                 ms->W, ms->H, target_width, target_height);
+        return ctx->fail(CDS_ERR_SIZE_MISMATCH, buf);
+    }
+    if (!target_rgb) return ctx->fail(CDS_ERR_BAD_ARG, "cds_score_pair_rgb: target is NULL");
+    // a one-slot library on device 0 only
+    cds_ctx *c = ctx;
+    cds_maskset *msm = const_cast<cds_maskset *>(ms);
+    CDS_TRY(msm->sync_descs());
+    DevState &d0 = c->devs[0];
+    CDS_CUDA(c, cudaSetDevice(d0.dev));
+    PlaneGeom g;
+    g.W = ms->W; g.H = ms->H; g.pitch = choose_pitch(ms->W); g.guard = CDS_GUARD_ROWS;
+    const size_t words = g.total_words(1);
+    const size_t img_bytes = (size_t) g.W * g.H * 3;
+    uint32_t *plane = nullptr;
+    int32_t *d_score = nullptr;
+    CDS_TRY(c->ensure_staging(d0, (size_t) kLibBlock * img_bytes));
+    cds_status st = c->check(cudaMalloc(&plane, words * sizeof(uint32_t) + sizeof(int32_t)), "cudaMalloc(pair plane)");
+    if (st != CDS_OK) return st;
+    d_score = (int32_t *) (plane + words);
+    launch_fill_words(plane, words, CDS_CODE_PAD_WORD, d0.stream);
+    st = c->check(cudaMemcpyAsync(d0.staging, target_rgb, img_bytes, cudaMemcpyHostToDevice, d0.stream), "pair H2D");
+    if (st == CDS_OK) {
+        launch_encode_rgb((const uint8_t *) d0.staging, 1, plane, g, 0, d0.d_rank_tab, ms->params.data_threshold, d0.stream);
+        launch_pixelmatch_gather(msm->d_descs[0] + mask_index, 1, plane, g, 1, ms->shifts, d_score, d0.stream);
+        st = c->check(cudaGetLastError(), "pair kernels");
+    }
+    int32_t w = 0;
+    if (st == CDS_OK) st = c->check(cudaMemcpyAsync(&w, d_score, sizeof w, cudaMemcpyDeviceToHost, d0.stream), "pair D2H");
+    if (st == CDS_OK) st = c->check(cudaStreamSynchronize(d0.stream), "pair sync");
+    cudaFree(plane);
+    if (st != CDS_OK) return st;
+    *score_out = w & ~CDS_SCORE_MIRROR_BIT;
+    *mirrored_out = (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0;
+    *ratio_out = (double) *score_out / (double) P;     // :194
+    return CDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ post-processing
+extern "C" int64_t cds_shape_score_2d(int64_t gradient_area_gap, int64_t high_expression_area)
+{
+    // GradientAreaGapUtils.calculate2DShapeScore, API/cds/GradientAreaGapUtils.java:199-207
+    if (gradient_area_gap >= 0 && high_expression_area >= 0) return gradient_area_gap + high_expression_area / 3;
+    return -1;
+}
+
+extern "C" double cds_normalized_score(int32_t pixel_match_score, int64_t shape_score, int64_t max_pixel_match, int64_t max_shape_score)
+{
+    // GradientAreaGapUtils.calculateNormalizedScore, API/cds/GradientAreaGapUtils.java:219-235
+    if (pixel_match_score == 0 || max_pixel_match == 0 || shape_score < 0 || max_shape_score <= 0) return pixel_match_score;
+    double normalized_pixel_score = (double) pixel_match_score / (double) max_pixel_match;
+    double normalized_shape_score = (double) shape_score / (double) max_shape_score;
+    double bounded = std::fmin(std::fmax(normalized_shape_score * 2.5, 0.002), 1.);
+    return normalized_pixel_score / bounded * 100;
+}
+
+extern "C" cds_status cds_normalize_scores(const int32_t *pixel_scores, const int64_t *gaps, const int64_t *high_exprs, int64_t n,
+                                           float *normalized_out)
+{
+    // CalculateGradientScoresCmd.normalizeScores, TOOLS/CalculateGradientScoresCmd.java:616-645: the maxima run over the
+    // mask's matches, the normalised score is stored as float
+    if (n < 0 || (n > 0 && (!pixel_scores || !gaps || !high_exprs || !normalized_out))) {
+        set_tls_error("cds_normalize_scores: bad arguments");
+        return CDS_ERR_BAD_ARG;
+    }
+    int64_t max_pix = 0, max_shape = -1;
+    bool any = false;
+    for (int64_t i = 0; i < n; i++) {
+        max_pix = std::max<int64_t>(max_pix, pixel_scores[i]);
+        int64_t s = cds_shape_score_2d(gaps[i], high_exprs[i]);
+        if (!any || s > max_shape) { max_shape = s; any = true; }
+    }
+    for (int64_t i = 0; i < n; i++) {
+        int64_t s = cds_shape_score_2d(gaps[i], high_exprs[i]);
+        normalized_out[i] = (float) cds_normalized_score(pixel_scores[i], s, max_pix, max_shape);
+    }
+    return CDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ test hooks
+extern "C" cds_status cds_debug_encode_colors(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t data_threshold, uint32_t *codes_out)
+{
+    if (!ctx || (n > 0 && (!rgb || !codes_out))) { set_tls_error("cds_debug_encode_colors: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n <= 0) return CDS_OK;
+    DevState &d0 = ctx->devs[0];
+    CDS_CUDA(ctx, cudaSetDevice(d0.dev));
+    uint8_t *d_rgb = nullptr;
+    uint32_t *d_codes = nullptr;
+    cds_status st = ctx->check(cudaMalloc(&d_rgb, (size_t) n * 3), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_codes, (size_t) n * 4), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_rgb, rgb, (size_t) n * 3, cudaMemcpyHostToDevice, d0.stream), "H2D");
+    if (st == CDS_OK) {
+        launch_encode_colors(d_rgb, n, d0.d_rank_tab, data_threshold, d_codes, d0.stream);
+        st = ctx->check(cudaGetLastError(), "encode_colors_kernel");
+    }
+    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(codes_out, d_codes, (size_t) n * 4, cudaMemcpyDeviceToHost, d0.stream), "D2H");
+    if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "sync");
+    if (d_rgb) cudaFree(d_rgb);
+    if (d_codes) cudaFree(d_codes);
+    return st;
+}
+
+extern "C" cds_status cds_debug_class_intervals(double z_tolerance, int32_t sector, int32_t rank,
+                                                uint32_t *lo1, uint32_t *len1, uint32_t *lo2, uint32_t *len2)
+{
+    if (sector < 0 || sector >= CDS_NUM_SECTORS || rank < 0 || rank >= CDS_NUM_RANKS || !lo1 || !len1 || !lo2 || !len2) {
+        set_tls_error("cds_debug_class_intervals: bad arguments");
+        return CDS_ERR_BAD_ARG;
+    }
+    cds_class_interval iv = class_interval(z_tolerance, sector, rank);
+    *lo1 = iv.lo1; *len1 = iv.len1; *lo2 = iv.lo2; *len2 = iv.len2;
+    return CDS_OK;
+}

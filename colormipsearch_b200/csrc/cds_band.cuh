@@ -1,0 +1,19 @@
+// cds_band.cuh -- the batched, shared-memory pixel-match kernel (the hot path at scale).
+#ifndef CDS_BAND_CUH
+#define CDS_BAND_CUH
+
+#include "cds_kernels.cuh"
+
+namespace cds {
+
+// xyShift in {0, 2, 4} and a row pitch that fits at least a few rows in shared memory
+bool band_kernel_supported(int xy_shift, const PlaneGeom &g);
+// below this many masks per launch the gather kernel is used instead
+int band_min_masks();
+// Launches the band kernel for masks [0, n_masks) x targets [0, n_targets) of one device; returns the number of
+// kernel launches issued (0 on configuration error, cudaGetLastError has it).
+int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
+                           int xy_shift, bool mirror, int32_t *scores, cudaStream_t s);
+
+}  // namespace cds
+#endif

@@ -1,0 +1,311 @@
+// cds_kernels.cu -- library encoding, mask preparation and the generic (any xyShift) pixel-match kernel.
+//
+// Reference semantics (API/ = colormipsearch-api/src/main/java/org/janelia/colormipsearch/):
+//   encode        : the target side of calculatePixelGap, API/cds/AbstractColorDepthSearchAlgorithm.java:225-257, folded
+//                   into the integer code word described in cds_common.h
+//   mask records  : getMaskPosArray, API/cds/AbstractColorDepthSearchAlgorithm.java:96-126 (+ the mask side of calculatePixelGap)
+//   gather kernel : calculateScore / calculateMaxScoreForAllTargetTransformations / calculateMatchingScore,
+//                   API/cds/PixelMatchColorDepthSearchAlgorithm.java:166-263, with the shifted / mirrored position lists of
+//                   :113-158 evaluated on the fly instead of being materialised.
+#include "cds_kernels.cuh"
+
+namespace cds {
+
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int classify_color_dev(int r, int g, int b, int &second, int &maxv)
+{
+    if (b > r && b > g) { maxv = b; if (r > g) { second = r; return 0; } second = g; return 1; }
+    if (g > b && g > r) { maxv = g; if (b > r) { second = b; return 2; } second = r; return 3; }
+    if (r > b && r > g) { maxv = r; if (g > b) { second = g; return 4; } second = b; return 5; }
+    maxv = max(r, max(g, b));
+    second = 0;
+    return -1;
+}
+
+__device__ __forceinline__ uint32_t encode_color_dev(int r, int g, int b, const uint16_t *__restrict__ rank_tab, int thr)
+{
+    int second, maxv;
+    int sector = classify_color_dev(r, g, b, second, maxv);
+    uint32_t sr = sector < 0 ? (uint32_t) CDS_SR_NONE
+                             : (uint32_t) sector * CDS_SECTOR_STRIDE + __ldg(rank_tab + second * 256 + maxv);
+    uint32_t code = (sr << CDS_CODE_SR_SHIFT) | (uint32_t) maxv;
+    if (!(maxv > thr)) code |= CDS_CODE_BELOW_BIT;
+    return code;
+}
+
+__global__ void fill_words_kernel(uint32_t *__restrict__ p, size_t n, uint32_t v)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t) gridDim.x * blockDim.x;
+    // 128-bit stores on the aligned body
+    size_t n4 = n / 4;
+    uint4 v4 = make_uint4(v, v, v, v);
+    uint4 *p4 = reinterpret_cast<uint4 *>(p);
+    for (size_t k = i; k < n4; k += stride) p4[k] = v4;
+    for (size_t k = n4 * 4 + i; k < n; k += stride) p[k] = v;
+}
+
+void launch_fill_words(uint32_t *p, size_t n, uint32_t v, cudaStream_t s)
+{
+    if (n == 0) return;
+    fill_words_kernel<<<148 * 8, 256, 0, s>>>(p, n, v);
+}
+
+// One CTA per (image row, image).  The RGB row (3W bytes, arbitrary alignment) is staged through shared memory with
+// aligned 32-bit loads; each thread then encodes pixels and writes coalesced code words, pads included.
+__global__ void __launch_bounds__(256) encode_rgb_kernel(const uint8_t *__restrict__ rgb, uint32_t *__restrict__ planes, PlaneGeom g,
+                                                         int64_t first_slot, const uint16_t *__restrict__ rank_tab, int thr)
+{
+    extern __shared__ uint32_t srow[];
+    const int y = blockIdx.x;
+    const int64_t img = blockIdx.y;
+    const size_t row_bytes = (size_t) g.W * 3;
+    const uint8_t *src = rgb + ((size_t) img * g.H + y) * row_bytes;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const int off = (int) (a & 3);
+    const uint32_t *asrc = reinterpret_cast<const uint32_t *>(a - off);
+    const int n_words = (int) ((off + row_bytes + 3) / 4);
+    for (int k = threadIdx.x; k < n_words; k += blockDim.x) srow[k] = asrc[k];
+    __syncthreads();
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(srow) + off;
+    uint32_t *dst = planes + g.row_offset(first_slot + img, y);
+    for (int x = threadIdx.x; x < g.pitch; x += blockDim.x) {
+        uint32_t code = CDS_CODE_PAD_WORD;
+        if (x < g.W) code = encode_color_dev(sb[3 * x], sb[3 * x + 1], sb[3 * x + 2], rank_tab, thr);
+        dst[x] = code;
+    }
+}
+
+void launch_encode_rgb(const uint8_t *rgb, int64_t n, uint32_t *planes, PlaneGeom g, int64_t first_slot,
+                       const uint16_t *rank_tab, int data_threshold, cudaStream_t s)
+{
+    if (n == 0) return;
+    size_t smem = ((size_t) g.W * 3 + 8 + 3) / 4 * 4;
+    // gridDim.y is limited to 65535: chunk
+    for (int64_t i0 = 0; i0 < n; i0 += 32768) {
+        int64_t cnt = n - i0 < 32768 ? n - i0 : 32768;
+        dim3 grid(g.H, (unsigned) cnt);
+        encode_rgb_kernel<<<grid, 256, smem, s>>>(rgb + (size_t) i0 * g.H * g.W * 3, planes, g, first_slot + i0, rank_tab, data_threshold);
+    }
+}
+
+__global__ void rebake_kernel(uint32_t *__restrict__ p, size_t n, int thr)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t) gridDim.x * blockDim.x;
+    size_t n4 = n / 4;
+    uint4 *p4 = reinterpret_cast<uint4 *>(p);
+    auto bake = [thr](uint32_t c) -> uint32_t {
+        if (c & CDS_CODE_PAD_BIT) return c;
+        uint32_t below = ((int) (c & 0xFFu) > thr) ? 0u : CDS_CODE_BELOW_BIT;
+        return (c & ~CDS_CODE_BELOW_BIT) | below;
+    };
+    for (size_t k = i; k < n4; k += stride) {
+        uint4 v = p4[k];
+        v.x = bake(v.x); v.y = bake(v.y); v.z = bake(v.z); v.w = bake(v.w);
+        p4[k] = v;
+    }
+    for (size_t k = n4 * 4 + i; k < n; k += stride) p[k] = bake(p[k]);
+}
+
+void launch_rebake(uint32_t *planes, size_t n_words, int data_threshold, cudaStream_t s)
+{
+    if (n_words == 0) return;
+    rebake_kernel<<<148 * 8, 256, 0, s>>>(planes, n_words, data_threshold);
+}
+
+__global__ void encode_colors_kernel(const uint8_t *__restrict__ rgb, int64_t n, const uint16_t *__restrict__ rank_tab, int thr,
+                                     uint32_t *__restrict__ codes)
+{
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) codes[i] = encode_color_dev(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], rank_tab, thr);
+}
+
+void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_tab, int data_threshold, uint32_t *codes, cudaStream_t s)
+{
+    if (n == 0) return;
+    encode_colors_kernel<<<148 * 4, 256, 0, s>>>(rgb, n, rank_tab, data_threshold, codes);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Mask preparation: ordered compaction of the pixels above the mask threshold and outside the label regions.
+// Pass 1 counts per (mask, row); pass 2 turns counts into row starts; pass 3 writes the records.  One warp per row.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool in_rects(const RectSet &r, int x, int y)
+{
+    bool in = false;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < r.n) in |= (x >= r.x0[i] && x < r.x1[i] && y >= r.y0[i] && y < r.y1[i]);
+    return in;
+}
+
+__global__ void __launch_bounds__(128) mask_count_rows_kernel(const uint8_t *__restrict__ rgb, int W, int H, int thr, RectSet rects,
+                                                              uint32_t *__restrict__ rowcount)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * 4 + warp;
+    const int m = blockIdx.y;
+    if (y >= H) return;
+    const uint8_t *row = rgb + ((size_t) m * H + y) * W * 3;
+    int cnt = 0;
+    for (int x = lane; x < W; x += 32) {
+        int r = row[3 * x], g = row[3 * x + 1], b = row[3 * x + 2];
+        bool pass = (r > thr || g > thr || b > thr) && !in_rects(rects, x, y);
+        cnt += pass ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) rowcount[(size_t) m * (H + 1) + y] = (uint32_t) cnt;
+}
+
+void launch_mask_count_rows(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,
+                            uint32_t *rowcount, cudaStream_t s)
+{
+    if (n_masks == 0) return;
+    dim3 grid((H + 3) / 4, n_masks);
+    mask_count_rows_kernel<<<grid, 128, 0, s>>>(rgb, W, H, threshold, rects, rowcount);
+}
+
+// in place: rowcount[m][0..H) counts  ->  rowcount[m][0..H] exclusive starts (last = P)
+__global__ void mask_scan_rows_kernel(uint32_t *__restrict__ rowcount, int n_masks, int H, int32_t *__restrict__ sizes)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_masks) return;
+    uint32_t *rc = rowcount + (size_t) m * (H + 1);
+    uint32_t acc = 0;
+    for (int y = 0; y < H; y++) { uint32_t c = rc[y]; rc[y] = acc; acc += c; }
+    rc[H] = acc;
+    sizes[m] = (int32_t) acc;
+}
+
+void launch_mask_scan_rows(uint32_t *rowcount, int n_masks, int H, int32_t *sizes, cudaStream_t s)
+{
+    if (n_masks == 0) return;
+    mask_scan_rows_kernel<<<(n_masks + 63) / 64, 64, 0, s>>>(rowcount, n_masks, H, sizes);
+}
+
+__global__ void __launch_bounds__(128) mask_write_records_kernel(const uint8_t *__restrict__ rgb, int W, int H, int thr, RectSet rects,
+                                                                 const uint32_t *__restrict__ rowstart, const uint64_t *__restrict__ rec_offset,
+                                                                 const uint16_t *__restrict__ rank_tab,
+                                                                 const cds_class_interval *__restrict__ class_tab,
+                                                                 cds_mask_record *__restrict__ records)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * 4 + warp;
+    const int m = blockIdx.y;
+    if (y >= H) return;
+    const uint8_t *row = rgb + ((size_t) m * H + y) * W * 3;
+    cds_mask_record *out = records + rec_offset[m] + rowstart[(size_t) m * (H + 1) + y];
+    int run = 0;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        int x = x0 + lane;
+        bool pass = false;
+        int r = 0, g = 0, b = 0;
+        if (x < W) {
+            r = row[3 * x]; g = row[3 * x + 1]; b = row[3 * x + 2];
+            pass = (r > thr || g > thr || b > thr) && !in_rects(rects, x, y);
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+            int second, maxv;
+            int sector = classify_color_dev(r, g, b, second, maxv);
+            cds_mask_record rec;
+            rec.xy = (uint32_t) x | ((uint32_t) y << 16);
+            rec.lo1 = CDS_EMPTY_LO; rec.lo2 = CDS_EMPTY_LO; rec.lens = 0;
+            if (sector >= 0) {
+                int rank = __ldg(rank_tab + second * 256 + maxv);
+                cds_class_interval iv = class_tab[sector * CDS_NUM_RANKS + rank];
+                uint32_t len1 = 0, len2 = 0;
+                if (iv.lo1 != CDS_IV_EMPTY) { rec.lo1 = iv.lo1 << CDS_CODE_SR_SHIFT; len1 = iv.len1; }
+                if (iv.lo2 != CDS_IV_EMPTY) { rec.lo2 = iv.lo2 << CDS_CODE_SR_SHIFT; len2 = iv.len2; }
+                rec.lens = len1 | (len2 << 16);
+            }
+            int idx = run + __popc(bal & ((1u << lane) - 1));
+            out[idx] = rec;
+        }
+        run += __popc(bal);
+    }
+}
+
+void launch_mask_write_records(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,
+                               const uint32_t *rowstart, const uint64_t *rec_offset, const uint16_t *rank_tab,
+                               const cds_class_interval *class_tab, cds_mask_record *records, cudaStream_t s)
+{
+    if (n_masks == 0) return;
+    dim3 grid((H + 3) / 4, n_masks);
+    mask_write_records_kernel<<<grid, 128, 0, s>>>(rgb, W, H, threshold, rects, rowstart, rec_offset, rank_tab, class_tab, records);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Generic pixel match: one CTA per (target, mask); gathers straight from the HBM/L2-resident code plane with explicit
+// bounds checks, so any even xyShift works.  Used when the band kernel does not apply (few masks, xyShift > 4) and as
+// the simple second implementation the band kernel is cross-checked against.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool code_matches(uint32_t c, uint32_t lo1, uint32_t len1, uint32_t lo2, uint32_t len2)
+{
+    return (c - lo1 <= len1) | (c - lo2 <= len2);
+}
+
+__global__ void __launch_bounds__(256) pixelmatch_gather_kernel(const MaskDesc *__restrict__ masks, const uint32_t *__restrict__ planes,
+                                                                PlaneGeom g, int64_t n_targets, ShiftSet shifts,
+                                                                int32_t *__restrict__ scores)
+{
+    __shared__ int warp_sums[8];
+    __shared__ int s_total;
+    const int64_t t = blockIdx.x;
+    const int m = blockIdx.y;
+    const MaskDesc md = masks[m];
+    const uint32_t *plane = planes + g.row_offset(t, 0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int best[2] = {0, 0};
+    const int n_orient = shifts.mirror ? 2 : 1;
+    for (int o = 0; o < n_orient; o++) {
+        for (int v = 0; v < shifts.n; v++) {
+            const int dx = shifts.dx[v], dy = shifts.dy[v];
+            int cnt = 0;
+            for (int i = threadIdx.x; i < md.P; i += blockDim.x) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(md.records + i));
+                int x = (int) (q.x & 0xFFFFu) + dx;
+                int y = (int) (q.x >> 16) + dy;
+                if (x >= 0 && x < g.W && y >= 0 && y < g.H) {          // shiftMaskPosArray :138-141
+                    if (o) x = g.W - 1 - x;                             // mirrorMask :153-154 (applied after the shift)
+                    uint32_t c = __ldg(plane + (size_t) y * g.pitch + x);
+                    uint32_t len1 = ((q.w & 0xFFFFu) << CDS_CODE_SR_SHIFT) | 0xFFu;
+                    uint32_t len2 = ((q.w >> 16) << CDS_CODE_SR_SHIFT) | 0xFFu;
+                    cnt += code_matches(c, q.y, len1, q.z, len2) ? 1 : 0;
+                }
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) warp_sums[warp] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+                for (int w = 0; w < (int) (blockDim.x >> 5); w++) tot += warp_sums[w];
+                s_total = tot;
+            }
+            __syncthreads();
+            best[o] = max(best[o], s_total);
+        }
+    }
+    if (threadIdx.x == 0) {
+        int score = best[0];
+        int mir = 0;
+        if (shifts.mirror && best[1] > best[0]) { score = best[1]; mir = 1; }   // strict :189
+        scores[(size_t) m * n_targets + t] = score | (mir ? CDS_SCORE_MIRROR_BIT : 0);
+    }
+}
+
+void launch_pixelmatch_gather(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g,
+                              int64_t n_targets, ShiftSet shifts, int32_t *scores, cudaStream_t s)
+{
+    if (n_masks == 0 || n_targets == 0) return;
+    // gridDim.y <= 65535
+    for (int m0 = 0; m0 < n_masks; m0 += 32768) {
+        int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
+        dim3 grid((unsigned) n_targets, (unsigned) cnt);
+        pixelmatch_gather_kernel<<<grid, 256, 0, s>>>(masks + m0, planes, g, n_targets, shifts, scores + (size_t) m0 * n_targets);
+    }
+}
+
+}  // namespace cds

@@ -1,0 +1,64 @@
+// cds_kernels.cuh -- launch wrappers of the CUDA kernels (implemented in the .cu files of this directory).
+#ifndef CDS_KERNELS_CUH
+#define CDS_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "cds_common.h"
+
+namespace cds {
+
+// Geometry of the encoded library planes in HBM (all in 32-bit words).
+//   plane t, image row y (0 <= y < H), column x  ->  base[(guard + t * (H + guard) + y) * pitch + x]
+// Every row has pitch - W >= CDS_MIN_PAD_COLS trailing pad words; `guard` pad rows separate consecutive planes and
+// precede the first one, so a band of rows [y0 - s, y1 + s) of any plane is ONE contiguous, 16-byte aligned span that
+// already contains the out-of-image pixels as never-matching pad words.
+struct PlaneGeom {
+    int W, H, pitch, guard;
+    __host__ __device__ size_t plane_stride() const { return (size_t) (H + guard) * pitch; }
+    __host__ __device__ size_t total_words(int64_t capacity) const { return ((size_t) capacity * (H + guard) + guard) * pitch; }
+    __host__ __device__ size_t row_offset(int64_t t, int y) const { return ((size_t) guard + (size_t) t * (H + guard) + y) * pitch; }
+};
+
+struct RectSet {
+    int n;
+    int x0[8], y0[8], x1[8], y1[8];
+};
+
+// Per-mask descriptor on the device.
+struct MaskDesc {
+    const cds_mask_record *records;   // P records, ascending pixel index
+    const uint32_t *rowstart;         // H + 1 entries: records of image row y are [rowstart[y], rowstart[y+1])
+    int P;
+    int pad;
+};
+
+struct ShiftSet {
+    int n;                            // offsets per orientation
+    int mirror;
+    int8_t dx[CDS_MAX_SHIFT_OFFSETS];
+    int8_t dy[CDS_MAX_SHIFT_OFFSETS];
+};
+
+// score word written by the match kernels: matching pixels | mirrored << 30
+#define CDS_SCORE_MIRROR_BIT 0x40000000
+
+void launch_fill_words(uint32_t *p, size_t n, uint32_t v, cudaStream_t s);
+void launch_encode_rgb(const uint8_t *rgb, int64_t n, uint32_t *planes, PlaneGeom g, int64_t first_slot,
+                       const uint16_t *rank_tab, int data_threshold, cudaStream_t s);
+void launch_rebake(uint32_t *planes, size_t n_words, int data_threshold, cudaStream_t s);
+void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_tab, int data_threshold, uint32_t *codes, cudaStream_t s);
+
+void launch_mask_count_rows(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,
+                            uint32_t *rowcount, cudaStream_t s);
+void launch_mask_scan_rows(uint32_t *rowcount, int n_masks, int H, int32_t *sizes, cudaStream_t s);
+void launch_mask_write_records(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,
+                               const uint32_t *rowstart, const uint64_t *rec_offset, const uint16_t *rank_tab,
+                               const cds_class_interval *class_tab, cds_mask_record *records, cudaStream_t s);
+
+void launch_pixelmatch_gather(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g,
+                              int64_t n_targets, ShiftSet shifts, int32_t *scores /* [n_masks][n_targets] */,
+                              cudaStream_t s);
+
+}  // namespace cds
+#endif

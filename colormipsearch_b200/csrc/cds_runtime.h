@@ -1,0 +1,105 @@
+// cds_runtime.h -- host-side object model behind the C ABI (include/cdsgpu.h).  Internal.
+#ifndef CDS_RUNTIME_H
+#define CDS_RUNTIME_H
+
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cdsgpu.h"
+#include "cds_common.h"
+#include "cds_kernels.cuh"
+#include "cds_tables.h"
+
+namespace cds {
+
+constexpr int64_t kLibBlock = 64;   // targets per block of the block-cyclic device sharding
+
+struct DevState {
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint16_t *d_rank_tab = nullptr;
+    std::map<uint64_t, cds_class_interval *> d_class_tabs;   // keyed by the bits of zTolerance
+    void *staging = nullptr;       // device staging for uploads
+    size_t staging_bytes = 0;
+    void *h_pinned = nullptr;      // pinned host scratch for read-backs
+    size_t h_pinned_bytes = 0;
+};
+
+void set_tls_error(const std::string &msg);
+
+}  // namespace cds
+
+struct cds_ctx {
+    std::vector<cds::DevState> devs;
+    mutable std::recursive_mutex mu;
+    mutable std::string err;
+    cds_search_stats stats{};
+
+    cds_status fail(cds_status code, const std::string &msg) const;
+    cds_status check(cudaError_t e, const char *what) const;
+    cds_status ensure_staging(cds::DevState &d, size_t bytes);
+    cds_status ensure_pinned(cds::DevState &d, size_t bytes);
+    cds_status class_table_on(cds::DevState &d, double tol, const cds_class_interval **out);
+};
+
+struct cds_library {
+    cds_ctx *ctx = nullptr;
+    cds::PlaneGeom g{};
+    int64_t capacity = 0;
+    int64_t size = 0;
+    int baked_threshold = 0;
+    struct Shard { uint32_t *planes = nullptr; int64_t cap_local = 0; };
+    std::vector<Shard> shards;
+
+    int n_dev() const { return (int) shards.size(); }
+    // block-cyclic mapping global <-> (device, local)
+    void locate(int64_t gidx, int &dev, int64_t &local) const {
+        int64_t blk = gidx / cds::kLibBlock;
+        dev = (int) (blk % n_dev());
+        local = (blk / n_dev()) * cds::kLibBlock + gidx % cds::kLibBlock;
+    }
+    int64_t global_of(int dev, int64_t local) const {
+        int64_t blk_local = local / cds::kLibBlock;
+        return (blk_local * n_dev() + dev) * cds::kLibBlock + local % cds::kLibBlock;
+    }
+    int64_t local_size(int dev) const;   // number of targets currently on `dev`
+    cds_status bake(int threshold);      // make the below-threshold flags match `threshold`
+};
+
+struct cds_maskset {
+    cds_ctx *ctx = nullptr;
+    int W = 0, H = 0;
+    cds_pixparams params{};
+    cds::ShiftSet shifts{};
+    cds::RectSet rects{};
+    std::vector<int32_t> sizes;          // getQuerySize() per mask
+    struct Batch {
+        int n = 0;
+        std::vector<uint64_t> rec_offset;              // [n] record offset of each mask inside `records`
+        uint64_t total_records = 0;
+        std::vector<cds_mask_record *> records;        // per device
+        std::vector<uint32_t *> rowstart;              // per device, [n][H+1]
+    };
+    std::vector<Batch> batches;
+    std::vector<cds::MaskDesc *> d_descs;              // per device, rebuilt when dirty
+    bool descs_dirty = true;
+    cds_status sync_descs();
+};
+
+
+namespace cds {
+// Appends n images at consecutive global indices; `src` fills the device staging buffer with the RGB pixels of images
+// [i0, i0 + cnt) of the call (an H2D copy or a generator kernel) on ds.stream.
+cds_status library_append(cds_library *lib, int64_t n,
+                          const std::function<cds_status(DevState &, int64_t i0, int64_t cnt, uint8_t *d_rgb)> &src,
+                          int64_t *first_index);
+}  // namespace cds
+
+#endif

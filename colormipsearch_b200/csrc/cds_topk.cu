@@ -1,0 +1,167 @@
+// cds_topk.cu -- per-mask top-K on the device.
+//
+// The reference keeps every pair that passes ColorMIPSearch.isMatch (API/cds/ColorMIPSearch.java:42-45) and sorts by
+// descending matchingPixels with a stable sort (TOOLS/ColorDepthSearchCmd.java:403-409, API/results/ItemsHandling.java:61-63);
+// the K best of that list, ties in ascending target order, is what this kernel returns.
+// One CTA per mask: a 3-pass radix select (10 bits per pass) finds the K-th largest count exactly, then one ordered
+// pass collects everything above it plus the first ties, and a shared-memory bitonic sort orders the <= 4096 keys.
+#include "cds_topk.cuh"
+#include "cds_kernels.cuh"
+
+namespace cds {
+
+namespace {
+constexpr int kThreads = 256;
+constexpr int kMaxK = 4096;
+
+__device__ __forceinline__ int block_exclusive_scan_flags(bool flag, int *warp_tot, int &block_total)
+{
+    // returns the number of set flags in threads before this one; block_total = all of them
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned bal = __ballot_sync(0xffffffffu, flag);
+    int before = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) {
+        int c = warp_tot[w];
+        if (w < warp) off += c;
+        tot += c;
+    }
+    __syncthreads();
+    block_total = tot;
+    return off + before;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads) topk_kernel(const int32_t *__restrict__ scores, int64_t n_targets,
+                                                        const int32_t *__restrict__ min_score, int k,
+                                                        uint64_t *__restrict__ keys_out, int32_t *__restrict__ counts_out)
+{
+    __shared__ uint64_t s_keys[kMaxK];
+    __shared__ int s_hist[1024];
+    __shared__ int s_warp[kThreads / 32];
+    __shared__ int s_sel_bin, s_sel_above, s_gt_count;
+
+    const int m = blockIdx.x;
+    const int32_t *row = scores + (size_t) m * n_targets;
+    const int minsc = max(min_score[m], 1);
+
+    // ---- radix select of the k-th largest count among entries with count >= minsc
+    int prefix = 0;          // high bits fixed so far
+    int prefix_mask = 0;
+    int need = k;            // rank (1-based, from the top) still to locate inside the current prefix
+    int total_pass = 0;
+    bool take_all = false;
+    for (int pass = 0; pass < 3; pass++) {
+        const int shift = 20 - 10 * pass;
+        for (int i = threadIdx.x; i < 1024; i += kThreads) s_hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = threadIdx.x; i < n_targets; i += kThreads) {
+            int c = row[i] & ~CDS_SCORE_MIRROR_BIT;
+            if (c >= minsc && (c & prefix_mask) == prefix) atomicAdd(&s_hist[(c >> shift) & 1023], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0, bin = -1, above = 0;
+            for (int b = 1023; b >= 0; b--) {
+                if (acc + s_hist[b] >= need) { bin = b; above = acc; break; }
+                acc += s_hist[b];
+            }
+            if (bin < 0) above = acc;     // fewer than `need` entries under this prefix
+            s_sel_bin = bin;
+            s_sel_above = above;
+        }
+        __syncthreads();
+        const int bin = s_sel_bin, above = s_sel_above;
+        if (pass == 0) {
+            int t = 0;
+            // total passing entries = sum of the first histogram (every thread computes it identically)
+            for (int b = 0; b < 1024; b++) t += s_hist[b];
+            total_pass = t;
+        }
+        if (bin < 0) { take_all = true; break; }   // only possible in pass 0: fewer than k passing entries
+        need -= above;
+        prefix |= bin << shift;
+        prefix_mask |= 1023 << shift;
+        __syncthreads();
+    }
+    const int sK = take_all ? minsc : prefix;       // k-th largest count (or the filter floor)
+    // entries with count > sK are all kept; of the ties (== sK) the first `need` in index order
+    const int ties_wanted = take_all ? 0x7fffffff : need;
+
+    if (threadIdx.x == 0) s_gt_count = 0;
+    __syncthreads();
+    // pass A: count entries strictly above sK so that ties can be placed after them
+    {
+        int local = 0;
+        for (int64_t i = threadIdx.x; i < n_targets; i += kThreads) {
+            int c = row[i] & ~CDS_SCORE_MIRROR_BIT;
+            local += (c >= minsc && c > sK) ? 1 : 0;
+        }
+        local = __reduce_add_sync(0xffffffffu, local);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_gt_count, local);
+    }
+    __syncthreads();
+    const int n_gt = take_all ? 0 : s_gt_count;
+    __syncthreads();
+    if (threadIdx.x == 0) s_gt_count = 0;           // reuse as the running slot for "above" entries
+    __syncthreads();
+
+    // pass B: ordered collection
+    int ties_seen = 0;
+    for (int64_t base = 0; base < n_targets; base += kThreads) {
+        const int64_t i = base + threadIdx.x;
+        int w = 0, c = 0;
+        bool valid = i < n_targets;
+        if (valid) { w = row[i]; c = w & ~CDS_SCORE_MIRROR_BIT; }
+        const bool pass = valid && c >= minsc;
+        const bool gt = pass && !take_all && c > sK;
+        const bool eq = pass && (take_all ? true : c == sK);
+        int eq_total;
+        int eq_rank = block_exclusive_scan_flags(eq, s_warp, eq_total);
+        if (gt) {
+            int slot = atomicAdd(&s_gt_count, 1);
+            s_keys[slot] = topk_make_key(c, i, (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0);
+        }
+        if (eq) {
+            int r = ties_seen + eq_rank;
+            if (r < ties_wanted && n_gt + r < k) s_keys[n_gt + r] = topk_make_key(c, i, (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0);
+        }
+        ties_seen += eq_total;
+    }
+    __syncthreads();
+    int n_out = n_gt + min(ties_seen, ties_wanted);
+    n_out = min(n_out, k);
+    (void) total_pass;
+
+    // ---- bitonic sort of s_keys[0..n_out) (padded with the largest key)
+    int n_pow2 = 1;
+    while (n_pow2 < n_out) n_pow2 <<= 1;
+    for (int i = n_out + threadIdx.x; i < n_pow2; i += kThreads) s_keys[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= n_pow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < n_pow2 / 2; t += kThreads) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool asc = ((lo & size) == 0);
+                uint64_t a = s_keys[lo], b = s_keys[hi];
+                if ((a > b) == asc) { s_keys[lo] = b; s_keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n_out; i += kThreads) keys_out[(size_t) m * k + i] = s_keys[i];
+    if (threadIdx.x == 0) counts_out[m] = n_out;
+}
+
+void launch_topk(const int32_t *scores, int n_masks, int64_t n_targets, const int32_t *min_score, int k,
+                 uint64_t *keys_out, int32_t *counts_out, cudaStream_t s)
+{
+    if (n_masks == 0) return;
+    topk_kernel<<<n_masks, kThreads, 0, s>>>(scores, n_targets, min_score, k, keys_out, counts_out);
+}
+
+}  // namespace cds

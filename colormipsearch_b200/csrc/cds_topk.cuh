@@ -1,0 +1,32 @@
+// cds_topk.cuh -- per-mask top-K selection over the score words of one device.
+#ifndef CDS_TOPK_CUH
+#define CDS_TOPK_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cds {
+
+// key: ascending order == (score descending, local target index ascending)
+//   bits 34..63 = 0x3FFFFFFF - score, bits 1..33 = local target index, bit 0 = mirrored
+__host__ __device__ inline uint64_t topk_make_key(int32_t score, int64_t idx, int mir)
+{
+    return ((uint64_t) (0x3FFFFFFF - score) << 34) | ((uint64_t) idx << 1) | (uint64_t) (mir & 1);
+}
+inline void topk_decode_key(uint64_t key, int32_t &score, int64_t &idx, uint8_t &mir)
+{
+    score = 0x3FFFFFFF - (int32_t) (key >> 34);
+    idx = (int64_t) ((key >> 1) & ((1ull << 33) - 1));
+    mir = (uint8_t) (key & 1);
+}
+
+inline int topk_max_k() { return 4096; }
+
+// scores: [n_masks][n_targets] score words (count | mirrored << 30).  For mask m keeps the entries with
+// count >= min_score[m], selects the k best by (count desc, index asc) and writes their keys, sorted, to
+// keys_out[m * k ..]; counts_out[m] = number written.
+void launch_topk(const int32_t *scores, int n_masks, int64_t n_targets, const int32_t *min_score, int k,
+                 uint64_t *keys_out, int32_t *counts_out, cudaStream_t s);
+
+}  // namespace cds
+#endif

@@ -1,0 +1,227 @@
+/*
+ * cdsgpu.h -- C ABI of the B200-native colour-depth MIP matching library (libcdsgpu.so).
+ *
+ * This is the drop-in boundary for ONE hot path of JaneliaSciComp/colormipsearch v3.1.1:
+ *   - pixel-match colour depth search  (PixelMatchColorDepthSearchAlgorithm)
+ *   - 2D shape / gradient-area-gap score (Shape2DMatchColorDepthSearchAlgorithm)
+ * The reference is pure Java and has no FFI of its own; these entry points are what a JNI or
+ * Panama-FFM binding behind its ColorDepthSearchAlgorithmProvider / ColorDepthSearchAlgorithm /
+ * ColorMIPSearchProcessor interfaces calls (INTEGRATION.md shows the binding).  Every function
+ * cites the reference interface it replaces; API/ abbreviates
+ * colormipsearch-api/src/main/java/org/janelia/colormipsearch/ and TOOLS/ abbreviates
+ * colormipsearch-tools/src/main/java/org/janelia/colormipsearch/cmd/.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is caller-owned HOST memory; calls block until results are
+ *     in the caller's buffers; nothing retains caller pointers after return.
+ *   - every function returns a cds_status; on failure cds_last_error() has the message.  Nothing
+ *     aborts or throws across the ABI.  CDS_ERR_BAD_ARG / CDS_ERR_SIZE_MISMATCH correspond to the
+ *     reference's IllegalArgumentException sites, everything else to IllegalStateException.
+ *   - there is NO CPU fallback: without a CUDA device cds_ctx_create fails with CDS_ERR_NO_DEVICE.
+ *   - images: RGB = uint8[H][W][3] in R,G,B order (API/imageprocessing/ColorImageArray.java:6-31),
+ *     gray16 = uint16[H][W] (ShortImageArray.java:4-16), gray8 = uint8[H][W] (ByteImageArray.java:3-16).
+ *   - a cds_ctx may be used from several host threads; calls on one ctx are serialised internally.
+ */
+#ifndef CDSGPU_H
+#define CDSGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden; these are its only exports */
+#endif
+
+#define CDSGPU_ABI_VERSION 1
+
+typedef int32_t cds_status;
+enum {
+    CDS_OK = 0,
+    CDS_ERR_BAD_ARG = 1,        /* IllegalArgumentException: odd xyShift (API/cds/ColorDepthSearchAlgorithmProviderFactory.java:57-60), bad sizes, null pointers */
+    CDS_ERR_SIZE_MISMATCH = 2,  /* IllegalArgumentException: image size differs from the query's (API/cds/PixelMatchColorDepthSearchAlgorithm.java:171-175) */
+    CDS_ERR_NO_DEVICE = 3,      /* no CUDA device / device id out of range */
+    CDS_ERR_CUDA = 4,           /* a CUDA runtime call or kernel failed */
+    CDS_ERR_OOM = 5,            /* device or host allocation failed */
+    CDS_ERR_CAPACITY = 6,       /* library / mask set is full */
+    CDS_ERR_UNSUPPORTED = 7     /* parameter combination outside the supported envelope (documented per call) */
+};
+
+typedef struct cds_ctx cds_ctx;
+typedef struct cds_library cds_library;
+typedef struct cds_maskset cds_maskset;
+typedef struct cds_shape_maskset cds_shape_maskset;
+
+/* Half-open rectangle [x0,x1) x [y0,y1): one label region excluded from matching
+ * (TOOLS/AbstractColorDepthMatchArgs.java:101-119 getRegionGeneratorForTextLabels;
+ *  API/imageprocessing/ImageRegionDefinition.java). */
+typedef struct cds_rect { int32_t x0, y0, x1, y1; } cds_rect;
+
+#define CDS_MAX_RECTS 8
+
+/* Parameters of the pixel-match provider: the arguments of
+ * ColorDepthSearchAlgorithmProviderFactory.createPixMatchCDSAlgorithmProvider
+ * (API/cds/ColorDepthSearchAlgorithmProviderFactory.java:30-74) plus the query threshold that
+ * createColorDepthSearchAlgorithm receives per mask (:45-48). */
+typedef struct cds_pixparams {
+    int32_t mask_threshold;     /* queryThreshold: mask pixel kept when R|G|B > threshold (API/cds/AbstractColorDepthSearchAlgorithm.java:116) */
+    int32_t data_threshold;     /* targetThreshold / dataThreshold (API/cds/PixelMatchColorDepthSearchAlgorithm.java:250) */
+    double  z_tolerance;        /* pixColorFluctuation / 100 (ProviderFactory :55-56); must be < 1000 */
+    int32_t xy_shift;           /* even, 0..CDS_MAX_XY_SHIFT; 0 and 2 are the values the Java reference can run (see oracle) */
+    int32_t mirror;             /* mirrorMask */
+    int32_t n_rects;            /* 0..CDS_MAX_RECTS */
+    cds_rect rects[CDS_MAX_RECTS];
+} cds_pixparams;
+
+#define CDS_MAX_XY_SHIFT 8
+
+/* ---------------------------------------------------------------- context ---------------------------------------------------------------- */
+
+/* Create a context over n_dev CUDA devices (device_ids may be NULL = devices 0..n_dev-1; n_dev = 0 = all visible).
+ * Replaces: nothing in the reference (it has no device); lifetime = one ColorDepthSearchAlgorithmProvider / one command run. */
+cds_status cds_ctx_create(const int32_t *device_ids, int32_t n_dev, cds_ctx **out);
+void       cds_ctx_destroy(cds_ctx *ctx);
+int32_t    cds_ctx_num_devices(const cds_ctx *ctx);
+/* Message of the last failing call on this thread (ctx may be NULL for cds_ctx_create failures). Never NULL. */
+const char *cds_last_error(const cds_ctx *ctx);
+int32_t    cds_abi_version(void);
+
+/* Pinned host memory for callers that want full-rate uploads (optional; any host pointer is accepted everywhere). */
+cds_status cds_host_alloc(cds_ctx *ctx, uint64_t bytes, void **out);
+cds_status cds_host_free(cds_ctx *ctx, void *p);
+
+/* ---------------------------------------------------------------- target library --------------------------------------------------------- */
+
+/* A device-resident library of target MIPs of one size, sharded block-cyclically over the context's devices.
+ * Replaces: the Guava cache of decoded target ImageArrays (TOOLS/CachedMIPsUtils.java:60-110) that
+ * LocalColorMIPSearchProcessor re-reads for every mask (TOOLS/cdsprocess/LocalColorMIPSearchProcessor.java:93-105). */
+cds_status cds_library_create(cds_ctx *ctx, int32_t width, int32_t height, int64_t capacity, cds_library **out);
+void       cds_library_destroy(cds_library *lib);
+/* Append n RGB images (uint8[n][H][W][3]); *first_index (may be NULL) receives the index of the first one. */
+cds_status cds_library_add_rgb(cds_library *lib, const uint8_t *rgb, int64_t n, int64_t *first_index);
+/* Append n deterministic synthetic LM-like targets generated on the device (bench / scale tests); indices continue
+ * from the current size and image i is synth target number (first_synth_index + i) of `seed`. */
+cds_status cds_library_generate_synthetic(cds_library *lib, uint64_t seed, int64_t first_synth_index, int64_t n, int64_t *first_index);
+int64_t    cds_library_size(const cds_library *lib);
+cds_status cds_library_clear(cds_library *lib);   /* forget all targets, keep the allocation */
+
+/* ---------------------------------------------------------------- pixel match ------------------------------------------------------------ */
+
+/* A set of prepared query masks sharing one parameter set; replicated on every device.
+ * Replaces: one PixelMatchColorDepthSearchAlgorithm per mask, i.e.
+ * ColorDepthSearchAlgorithmProvider.createColorDepthSearchAlgorithm (API/cds/ColorDepthSearchAlgorithmProvider.java:20-32)
+ * and the constructor work at API/cds/PixelMatchColorDepthSearchAlgorithm.java:29-101
+ * (getMaskPosArray, generateShiftedMasks, mirrorMask).
+ * Errors: CDS_ERR_BAD_ARG for odd xy_shift (Java: IllegalArgumentException), CDS_ERR_UNSUPPORTED for xy_shift > CDS_MAX_XY_SHIFT
+ * or z_tolerance >= 1000. */
+cds_status cds_maskset_create(cds_ctx *ctx, int32_t width, int32_t height, const cds_pixparams *params, cds_maskset **out);
+void       cds_maskset_destroy(cds_maskset *ms);
+/* Add n masks (uint8[n][H][W][3]).  mask_size_out[n] (may be NULL) receives getQuerySize() of each
+ * (API/cds/AbstractColorDepthSearchAlgorithm.java:71-73).  An empty mask is legal (scores 0, :169-170). */
+cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, int32_t n, int32_t *mask_size_out);
+int32_t    cds_maskset_size(const cds_maskset *ms);
+cds_status cds_maskset_get_mask_sizes(const cds_maskset *ms, int32_t *sizes_out /* [M] */);
+
+/* calculateMatchingScore of every mask against every target (API/cds/PixelMatchColorDepthSearchAlgorithm.java:166-219):
+ * scores[m*T + t] = matching pixels, mirrored[m*T + t] = bestScoreMirrored (may be NULL).  T = cds_library_size(lib).
+ * Used by the single-pair provider and by parity tests.  CDS_ERR_SIZE_MISMATCH when the library's image size differs. */
+cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, int32_t *scores, uint8_t *mirrored);
+
+/* Per mask, the K best targets that pass ColorMIPSearch.isMatch (API/cds/ColorMIPSearch.java:42-45:
+ * score > 0 && (float)(score/maskSize) > pct_positive_pixels/100), ordered by score descending, ties by ascending target
+ * index (= a single-threaded run of TOOLS/cdsprocess/LocalColorMIPSearchProcessor.java:55-116 followed by the
+ * stable sort of TOOLS/ColorDepthSearchCmd.java:403-409).  Selection happens on the devices; per-device lists are merged on
+ * the host.  out_score/out_target/out_mirrored are [M][K]; out_count[m] = entries filled for mask m (<= K). */
+cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, int32_t k, double pct_positive_pixels,
+                           int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count);
+
+/* One mask x one target held in host memory: the literal single-pair call of the Java API
+ * (ColorDepthSearchAlgorithm.calculateMatchingScore, API/cds/ColorDepthSearchAlgorithm.java:60-61). */
+cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, int32_t mask_index, const uint8_t *target_rgb,
+                              int32_t target_width, int32_t target_height,
+                              int32_t *score_out, double *ratio_out, int32_t *mirrored_out);
+
+/* ---------------------------------------------------------------- shape score ------------------------------------------------------------ */
+
+/* Prepared queries of the shape score.  Replaces createShapeMatchCDSAlgorithmProvider + its per-mask
+ * createColorDepthSearchAlgorithm (API/cds/ColorDepthSearchAlgorithmProviderFactory.java:76-127): label clearing,
+ * maxFilter(60)/maxFilter(20) high-expression ring, gray>2 query mask.
+ * roi_rgb may be NULL.  border must be 0 (CDS_ERR_UNSUPPORTED otherwise; the reference's own unsafeMaxFilter misbehaves
+ * for border > kernel radius). */
+cds_status cds_shape_maskset_create(cds_ctx *ctx, int32_t width, int32_t height, int32_t query_threshold, int32_t border,
+                                    int32_t mirror, const cds_rect *rects, int32_t n_rects, const uint8_t *roi_rgb,
+                                    cds_shape_maskset **out);
+void       cds_shape_maskset_destroy(cds_shape_maskset *sms);
+/* qm_size_out / he_size_out (may be NULL): number of set pixels of the query mask and of the high-expression mask
+ * (the quantities pinned at 17340 / 70640 by .../cds/Shape2DMatchColorDepthSearchAlgorithmTest.java:53-54). */
+cds_status cds_shape_maskset_add_rgb(cds_shape_maskset *sms, const uint8_t *rgb, int32_t n,
+                                     int64_t *qm_size_out, int64_t *he_size_out);
+int32_t    cds_shape_maskset_size(const cds_shape_maskset *sms);
+
+/* Shape2DMatchColorDepthSearchAlgorithm.calculateMatchingScore for n_pairs (mask, target) pairs
+ * (API/cds/Shape2DMatchColorDepthSearchAlgorithm.java:150-245).  Target images come in pair-independent arrays of
+ * n_targets images: target_rgb uint8[n_targets][H][W][3], gradient uint16[n_targets][H][W] (gray8 callers widen),
+ * zgap_rgb uint8[n_targets][H][W][3] or NULL = derive the zgap image on the device as
+ * maxFilter(10)(mask(threshold)(clearLabels(target))) -- what the reference's tests do when no zgap file exists
+ * (.../cds/Shape2DMatchColorDepthSearchAlgorithmTest.java:171-174).
+ * has_variants uint8[n_targets] (may be NULL = all 1): 0 marks a target whose gradient / zgap supplier is missing;
+ * its pairs get gap = high_expr = -1 (:155-158).
+ * Outputs per pair: gradientAreaGap, highExpressionArea, mirrored. */
+cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskset *sms,
+                                 const uint8_t *target_rgb, const uint16_t *gradient, const uint8_t *zgap_rgb,
+                                 const uint8_t *has_variants, int64_t n_targets,
+                                 const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
+                                 int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out);
+
+/* The zgap image alone (f3 in SURVEY.md section 8f): maxFilter(radius)(mask(threshold)(clearLabels(rgb))) for n images. */
+cds_status cds_make_zgap(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t width, int32_t height, int32_t threshold,
+                         double radius, const cds_rect *rects, int32_t n_rects, uint8_t *zgap_out);
+
+/* ---------------------------------------------------------------- score post-processing -------------------------------------------------- */
+
+/* GradientAreaGapUtils.calculate2DShapeScore (API/cds/GradientAreaGapUtils.java:199-207) and
+ * calculateNormalizedScore (:219-235); pure host arithmetic in IEEE double, exposed so bindings do not re-implement it. */
+int64_t cds_shape_score_2d(int64_t gradient_area_gap, int64_t high_expression_area);
+double  cds_normalized_score(int32_t pixel_match_score, int64_t shape_score, int64_t max_pixel_match, int64_t max_shape_score);
+/* CalculateGradientScoresCmd.normalizeScores for one mask's matches (TOOLS/CalculateGradientScoresCmd.java:616-645). */
+cds_status cds_normalize_scores(const int32_t *pixel_scores, const int64_t *gaps, const int64_t *high_exprs, int64_t n,
+                                float *normalized_out);
+
+/* ---------------------------------------------------------------- synthetic inputs + instrumentation ------------------------------------- */
+
+/* Deterministic synthetic images, identical bit for bit on host and device (bench.py, scale tests).
+ * kind: 0 = EM-like mask, 1 = LM-like target.  Writes n RGB images for indices first_index.. into rgb_out (host).
+ * on_device != 0 generates with the CUDA generator and copies back; 0 uses the host build of the same generator. */
+cds_status cds_synth_rgb(cds_ctx *ctx, int32_t kind, uint64_t seed, int64_t first_index, int64_t n,
+                         int32_t width, int32_t height, int32_t on_device, uint8_t *rgb_out);
+/* gradient image (gray16) of synthetic target `index`: capped distance to the nearest generated neurite. */
+cds_status cds_synth_gradient(cds_ctx *ctx, uint64_t seed, int64_t first_index, int64_t n,
+                              int32_t width, int32_t height, int32_t on_device, uint16_t *grad_out);
+
+/* Counters of the last search on this ctx (bench.py reads them): kernel launches, device milliseconds of the
+ * dominant kernel summed over launches (CUDA events on the launch stream, max over devices), comparisons done. */
+typedef struct cds_search_stats {
+    int64_t kernel_launches;
+    int64_t match_kernel_launches;
+    double  match_kernel_ms;
+    double  total_device_ms;
+    int64_t comparisons;
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} cds_search_stats;
+cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out);
+
+/* Test hooks (tests/ only): the encoded form of colours and the per-class match intervals, so that the integer
+ * predicate used on the device can be checked exhaustively against the oracle's double arithmetic. */
+cds_status cds_debug_encode_colors(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t data_threshold, uint32_t *codes_out);
+cds_status cds_debug_class_intervals(double z_tolerance, int32_t sector, int32_t rank,
+                                     uint32_t *lo1, uint32_t *len1, uint32_t *lo2, uint32_t *len2);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDSGPU_H */

@@ -1,0 +1,261 @@
+"""GPU parity tests of the pixel-match path, through the C ABI, against the CPU oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+
+from colormipsearch_b200 import capi
+from oracle import oracle as O
+from tests import golden_vectors as GV
+
+pytestmark = pytest.mark.gpu
+
+W, H = 1210, 566
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(n_dev=1)
+    yield c
+    c.close()
+
+
+def _np_expected_codes(rgb, thr):
+    """numpy restatement of the code word (cds_common.h) from the sector ladder of calculatePixelGap."""
+    r, g, b = (rgb[:, i].astype(np.int64) for i in range(3))
+    a_, b_ = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    valid = a_ < b_
+    uniq = np.unique((a_ / np.maximum(b_, 1))[valid])
+    rank_tab = np.searchsorted(uniq, a_ / np.maximum(b_, 1))
+    sector = np.full(len(r), -1)
+    second = np.zeros(len(r), np.int64)
+    mx = np.maximum(np.maximum(r, g), b)
+    bmax = (b > r) & (b > g)
+    gmax = (g > b) & (g > r) & ~bmax
+    rmax = (r > b) & (r > g) & ~bmax & ~gmax
+    sector[bmax & (r > g)] = 0; second[bmax & (r > g)] = r[bmax & (r > g)]
+    sector[bmax & ~(r > g)] = 1; second[bmax & ~(r > g)] = g[bmax & ~(r > g)]
+    sector[gmax & (b > r)] = 2; second[gmax & (b > r)] = b[gmax & (b > r)]
+    sector[gmax & ~(b > r)] = 3; second[gmax & ~(b > r)] = r[gmax & ~(b > r)]
+    sector[rmax & (g > b)] = 4; second[rmax & (g > b)] = g[rmax & (g > b)]
+    sector[rmax & ~(g > b)] = 5; second[rmax & ~(g > b)] = b[rmax & ~(g > b)]
+    sr = np.where(sector >= 0, sector * 32768 + rank_tab[second, np.maximum(mx, 1)], 6 * 32768)
+    code = (sr.astype(np.uint64) << 8) | mx.astype(np.uint64)
+    code = np.where(mx > thr, code, code | 0x80000000)
+    return code.astype(np.uint32)
+
+
+def test_encode_all_16M_colours(ctx):
+    v = np.arange(1 << 24, dtype=np.uint32)
+    rgb = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=1).astype(np.uint8)
+    for thr in (20, 100):
+        got = ctx.debug_encode_colors(rgb, thr)
+        exp = _np_expected_codes(rgb, thr)
+        assert np.array_equal(got, exp)
+
+
+def _maskset(ctx, case_or_params, rects):
+    mthr, dthr, ztol, xys, mirror = case_or_params
+    return capi.MaskSet(ctx, W, H, mthr, dthr, ztol, xys, mirror, rects)
+
+
+@pytest.mark.parametrize("case", GV.PIXEL_MATCH, ids=lambda c: f"{c[0]}-{c[1]}")
+def test_golden_pair_call(ctx, fixtures, case):
+    mask, target, mthr, dthr, ztol, xys, mirror, csw, exp_score, exp_mir = case
+    ms = _maskset(ctx, (mthr, dthr, ztol, xys, mirror), O.label_rects(W, H, csw))
+    sizes = ms.add_rgb(fixtures[mask])
+    score, ratio, mirrored = ms.score_pair(0, fixtures[target])
+    assert (score, mirrored) == (exp_score, exp_mir)
+    assert ratio == score / sizes[0]
+    ms.close()
+
+
+def test_golden_dense_both_kernels(ctx, fixtures):
+    """All five provider vectors in one dense search; the mask set is padded with synthetic masks so that the batched
+    band kernel runs, and a 2-mask set exercises the gather kernel on the same library."""
+    rects = O.label_rects(W, H, 270)
+    lm_keys = ["lm_VT033614", "lm_BJD", "lm_VT016795", "lm_GMR"]
+    lib = capi.Library(ctx, W, H, 16)
+    lib.add_rgb(np.stack([fixtures[k] for k in lm_keys]))
+    extra = capi.synth_rgb_host(0, 77, 0, 18, W, H)
+    masks = np.concatenate([np.stack([fixtures["em_12191"], fixtures["em_12191_FL"]]), extra])
+    for n_masks in (20, 2):
+        ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
+        sizes = ms.add_rgb(masks[:n_masks])
+        assert sizes[0] == 10299 and sizes[1] == 17340
+        scores, mirrored = ms.search_dense(lib)
+        exp = {(0, 0): (439, 0), (0, 1): (414, 0), (1, 0): (515, 0), (1, 2): (483, 0), (0, 2): (426, 1)}
+        for (m, t), (s, mir) in exp.items():
+            assert (scores[m, t], mirrored[m, t]) == (s, mir), (n_masks, m, t)
+        # and every cell against the oracle
+        oms = [O.PixelMatchMask(x, 20, True, 20, 0.01, 2, rects) for x in masks[:n_masks]]
+        es, em, _ = O.search_dense(oms, np.stack([fixtures[k] for k in lm_keys]))
+        assert np.array_equal(scores, es)
+        assert np.array_equal(mirrored, em)
+        ms.close()
+    lib.close()
+
+
+@pytest.fixture(scope="module")
+def synth(ctx):
+    masks = capi.synth_rgb_host(0, 0xC0FFEE, 0, 24, W, H)
+    targets = capi.synth_rgb_host(1, 0xC0FFEE, 0, 70, W, H)   # 70 > one library block of 64
+    lib = capi.Library(ctx, W, H, 80)
+    lib.add_rgb(targets)
+    yield masks, targets, lib
+    lib.close()
+
+
+PARAMS = [
+    # (maskThr, dataThr, zTol, xyShift, mirror)
+    (20, 20, 0.01, 2, True),      # production (cdsparams.sh)
+    (100, 100, 0.02, 0, True),    # CLI defaults + mirror (BASELINE config 1)
+    (100, 100, 0.02, 0, False),
+    (20, 20, 0.005, 4, True),     # BASELINE config 4 (the Java reference throws for xyShift 4; the oracle is the spec)
+    (20, 40, 0.01, 2, False),
+    (20, 20, 0.01, 6, True),      # gather kernel only
+]
+
+
+@pytest.mark.parametrize("params", PARAMS, ids=lambda p: "thr%d-%d_tol%g_xy%d_mir%d" % p)
+@pytest.mark.parametrize("n_masks", [24, 3])
+def test_dense_matches_oracle_on_synthetic(ctx, synth, params, n_masks):
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    mthr, dthr, ztol, xys, mirror = params
+    ms = _maskset(ctx, params, rects)
+    sizes = ms.add_rgb(masks[:n_masks])
+    oms = [O.PixelMatchMask(x, mthr, mirror, dthr, ztol, xys, rects) for x in masks[:n_masks]]
+    assert sizes.tolist() == [m.size for m in oms]
+    scores, mirrored = ms.search_dense(lib)
+    es, em, _ = O.search_dense(oms, targets)
+    assert np.array_equal(scores, es)
+    assert np.array_equal(mirrored, em)
+    assert es.max() > 200          # the embedded copies give real matches
+    ms.close()
+
+
+def test_topk_matches_sorted_dense(ctx, synth):
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
+    sizes = ms.add_rgb(masks)
+    oms = [O.PixelMatchMask(x, 20, True, 20, 0.01, 2, rects) for x in masks]
+    es, em, _ = O.search_dense(oms, targets)
+    for k, pct in ((5, 0.0), (300, 0.0), (16, 1.0)):
+        score, target, mirrored, count = ms.search_topk(lib, k, pct)
+        for m in range(len(masks)):
+            cand = [(-int(es[m, t]), t) for t in range(len(targets)) if O.is_match(es[m, t], es[m, t] / sizes[m], pct)]
+            cand.sort()
+            cand = cand[:k]
+            assert count[m] == len(cand)
+            assert score[m, :count[m]].tolist() == [-s for s, _ in cand]
+            assert target[m, :count[m]].tolist() == [t for _, t in cand]
+            assert mirrored[m, :count[m]].tolist() == [int(em[m, t]) for _, t in cand]
+    ms.close()
+
+
+def test_threshold_rebake_roundtrip(ctx, synth):
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    res = {}
+    for dthr in (20, 120, 20):
+        ms = _maskset(ctx, (20, dthr, 0.01, 2, True), rects)
+        ms.add_rgb(masks[:3])
+        res.setdefault(dthr, []).append(ms.search_dense(lib)[0])
+        ms.close()
+    assert np.array_equal(res[20][0], res[20][1])
+    om = [O.PixelMatchMask(x, 20, True, 120, 0.01, 2, rects) for x in masks[:3]]
+    assert np.array_equal(res[120][0], O.search_dense(om, targets)[0])
+
+
+def test_device_generator_equals_host_generator(ctx):
+    for kind in (0, 1):
+        dev = ctx.synth_rgb(kind, 123, 3, 3, W, H, on_device=True)
+        host = capi.synth_rgb_host(kind, 123, 3, 3, W, H)
+        assert np.array_equal(dev, host)
+    assert np.array_equal(ctx.synth_gradient(123, 3, 1, W, H, on_device=True), capi.synth_gradient_host(123, 3, 1, W, H))
+
+
+def test_generated_library_equals_uploaded_library(ctx):
+    rects = O.label_rects(W, H)
+    masks = capi.synth_rgb_host(0, 9, 0, 17, W, H)
+    lib_a = capi.Library(ctx, W, H, 70)
+    lib_a.generate_synthetic(9, 100, 66)
+    lib_b = capi.Library(ctx, W, H, 70)
+    lib_b.add_rgb(capi.synth_rgb_host(1, 9, 100, 66, W, H))
+    ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
+    ms.add_rgb(masks)
+    a = ms.search_dense(lib_a)
+    b = ms.search_dense(lib_b)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for x in (ms, lib_a, lib_b):
+        x.close()
+
+
+@pytest.mark.parametrize("shape", [(100, 50), (100, 300), (37, 23), (640, 480)])
+def test_small_and_odd_image_sizes(ctx, shape):
+    w, h = shape
+    rng = np.random.default_rng(w * 1000 + h)
+    lut = O.lut().astype(np.uint8)
+
+    def rand_img(density):
+        img = np.zeros((h, w, 3), np.uint8)
+        sel = rng.random((h, w)) < density
+        z = rng.integers(0, 256, (h, w))
+        br = rng.integers(20, 256, (h, w, 1))
+        col = (lut[z].astype(np.int64) * br // 255).astype(np.uint8)
+        img[sel] = col[sel]
+        return img
+
+    masks = np.stack([rand_img(0.2) for _ in range(18)])
+    targets = np.stack([rand_img(0.5) for _ in range(9)])
+    rects = np.array([[0, 0, w // 3, h // 4]], np.int32)
+    lib = capi.Library(ctx, w, h, 9)
+    lib.add_rgb(targets)
+    for params in ((20, 20, 0.02, 2, True), (20, 20, 0.02, 0, True), (20, 20, 0.02, 4, False)):
+        mthr, dthr, ztol, xys, mirror = params
+        for n in (18, 2):
+            ms = capi.MaskSet(ctx, w, h, mthr, dthr, ztol, xys, mirror, rects)
+            ms.add_rgb(masks[:n])
+            oms = [O.PixelMatchMask(x, mthr, mirror, dthr, ztol, xys, rects) for x in masks[:n]]
+            scores, mirrored = ms.search_dense(lib)
+            es, em, _ = O.search_dense(oms, targets)
+            assert np.array_equal(scores, es), (shape, params, n)
+            assert np.array_equal(mirrored, em), (shape, params, n)
+            ms.close()
+    lib.close()
+
+
+def test_edge_cases_and_errors(ctx, fixtures):
+    rects = O.label_rects(W, H)
+    # odd xyShift -> IllegalArgumentException (ColorDepthSearchAlgorithmProviderFactory.java:57-60)
+    with pytest.raises(capi.CdsIllegalArgument) as e:
+        capi.MaskSet(ctx, W, H, 20, 20, 0.01, 3, True, rects)
+    assert "even number" in e.value.message
+    # empty mask -> score 0, ratio 0, not mirrored; checked BEFORE the size test (PixelMatch...:169-175)
+    ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    sizes = ms.add_rgb(np.stack([np.zeros((H, W, 3), np.uint8), fixtures["em_LPLC2"]]))
+    assert sizes.tolist() == [0, 1897]
+    assert ms.score_pair(0, fixtures["lm_GMR"]) == (0, 0.0, False)
+    assert ms.score_pair(0, np.zeros((10, 10, 3), np.uint8)) == (0, 0.0, False)
+    with pytest.raises(capi.CdsIllegalArgument) as e:
+        ms.score_pair(1, np.zeros((10, 10, 3), np.uint8))
+    assert e.value.status == capi.CDS_ERR_SIZE_MISMATCH and "Invalid image size" in e.value.message
+    # size mismatch between mask set and library
+    lib = capi.Library(ctx, 100, 50, 4)
+    lib.add_rgb(np.zeros((1, 50, 100, 3), np.uint8))
+    with pytest.raises(capi.CdsIllegalArgument):
+        ms.search_dense(lib)
+    # empty library / capacity
+    lib2 = capi.Library(ctx, W, H, 2)
+    s, m = ms.search_dense(lib2)
+    assert s.shape == (2, 0)
+    lib2.add_rgb(np.stack([fixtures["lm_GMR"], fixtures["lm_BJD"]]))
+    with pytest.raises(capi.CdsError) as e:
+        lib2.add_rgb(fixtures["lm_GMR"])
+    assert e.value.status == capi.CDS_ERR_CAPACITY
+    s, m = ms.search_dense(lib2)
+    assert s[0].tolist() == [0, 0] and s[1, 0] > 0
+    score, target, mirrored, count = ms.search_topk(lib2, 4, 0.0)
+    assert count.tolist()[0] == 0 and count[1] >= 1
+    for x in (ms, lib, lib2):
+        x.close()
