@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the colour-depth pixel-match hot path (BASELINE.json metric: mask x target CDS comparisons / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1], "1,000 EM masks x 100,000 LM targets pixel-match search, 1210x566, on
+8xB200", i.e. 12,500 targets per GPU.  100,000 encoded targets do not fit one GPU, so the benchmark is weak-scaled: every
+rank holds its own 12,500-target shard (masks replicated, no data-path collective), N = 8 is the full configuration and
+N = 1 is one GPU's share of it.  Parameters are the production ones (cdsparams.sh): mask/data threshold 20, zTolerance
+0.01, xyShift 2, mirror, top-300 per mask, pctPositivePixels 1.  One step = all masks against the rank's resident
+library, per-mask top-K on the device, results on the host.  Inputs are synthetic (cds_synth.h).
+
+One JSON line on stdout (rank 0).  `value` uses device time (CUDA events on the library's launch stream, summed over the
+step's kernels, max over ranks); `e2e` is wall clock through the C ABI with host buffers (uploads + encoding + mask
+preparation + search + read-back inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1210, 566
+ALGO_BYTES_PER_COMPARISON = 3 * W * H          # the target's RGB bytes as the reference stores them
+SEED = 0xC0FFEE
+PARAMS = dict(mask_threshold=20, data_threshold=20, z_tolerance=0.01, xy_shift=2, mirror=True)
+TOPK = 300
+PCT_POSITIVE = 1.0
+
+
+def label_rects():
+    return np.array([[W - 270, 0, W, 90], [0, 0, 330, 100]], np.int32)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local_rank, world
+
+
+def cpu_baseline(n_masks_pool, masks_host, targets_fn, budget_s=15.0):
+    """The oracle (CPU port of the Java algorithm), OpenMP over all host cores, on a bounded sample of the workload."""
+    from oracle import oracle as O
+    rects = label_rects()
+    cores = O.num_threads()
+    p = PARAMS
+    pilot_m, pilot_t = 2, max(cores, 8)
+    oms = [O.PixelMatchMask(m, p["mask_threshold"], p["mirror"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], rects)
+           for m in masks_host[:pilot_m]]
+    tg = targets_fn(pilot_t)
+    t0 = time.perf_counter()
+    O.search_dense(oms, tg, 0)
+    dt = time.perf_counter() - t0
+    per_cmp = dt / (pilot_m * pilot_t)
+    want = int(budget_s / max(per_cmp, 1e-9))
+    n_m = int(min(len(masks_host), max(2, min(16, want // 64))))
+    n_t = int(max(cores, min(512, want // n_m)))
+    oms = [O.PixelMatchMask(m, p["mask_threshold"], p["mirror"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], rects)
+           for m in masks_host[:n_m]]
+    tg = targets_fn(n_t)
+    t0 = time.perf_counter()
+    O.search_dense(oms, tg, 0)
+    dt = time.perf_counter() - t0
+    return {"value": n_m * n_t / dt, "unit": "comparisons/s", "cores": cores, "kind": "port",
+            "sample": "%d masks x %d targets of the same synthetic workload, %.1f s, OpenMP over targets" % (n_m, n_t, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Java and there is no JVM on
+    this image, so this is the oracle port (oracle/cds_oracle.c, pinned on the reference's golden vectors) on all host
+    cores; each step is a bounded sample of the workload."""
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    from colormipsearch_b200 import capi
+    from oracle import oracle as O
+    rects = label_rects()
+    cores = O.num_threads()
+    p = PARAMS
+    n_m, n_t = args.ref_masks, max(args.ref_targets, cores)
+    masks = capi.synth_rgb_host(0, SEED, 0, n_m, W, H)
+    targets = capi.synth_rgb_host(1, SEED, 0, n_t, W, H)
+    oms = [O.PixelMatchMask(m, p["mask_threshold"], p["mirror"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], rects)
+           for m in masks]
+    for _ in range(args.warmup):
+        O.search_dense(oms, targets[: max(cores, 8)], 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.search_dense(oms, targets, 0)
+    dt = time.perf_counter() - t0
+    value = n_m * n_t * args.steps / dt
+    sample = "%d masks x %d targets per step (bounded sample of the workload), OpenMP over targets" % (n_m, n_t)
+    line = {
+        "impl": "reference", "metric": "mask x target CDS comparisons/sec", "value": value, "unit": "comparisons/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "comparisons/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "comparisons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Java reference cannot run here (no JVM); this is the C port of its algorithm pinned on its golden vectors",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": "BASELINE configs[1]: %d masks x %d targets per GPU (x%d GPUs = %d targets), 1210x566, maskThr 20, dataThr 20, "
+                    "zTol 0.01, xyShift 2, mirror (18 variants), top-%d per mask, pctPositivePixels %g"
+                    % (args.masks, args.targets_per_gpu, world, args.targets_per_gpu * world, TOPK, PCT_POSITIVE),
+        "masks": args.masks, "targets_per_gpu": args.targets_per_gpu, "image": [W, H],
+        "parallelism": "targets sharded over %d GPU(s), masks replicated, host merge, no collective" % world,
+        "l2": "library shard (%.1f GB) is far larger than L2; every step re-streams it" % (args.targets_per_gpu * 2.79e-3),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--masks", type=int, default=1000)
+    ap.add_argument("--targets-per-gpu", type=int, default=12500)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-targets", type=int, default=0, help="targets per e2e step (0 = same as --targets-per-gpu)")
+    ap.add_argument("--ref-masks", type=int, default=8)
+    ap.add_argument("--ref-targets", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank, local_rank, world = dist_env()
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from colormipsearch_b200 import capi
+    ctx = capi.Context(device_ids=[local_rank])
+    rects = label_rects()
+    M, T = args.masks, args.targets_per_gpu
+    t_first = rank * T                       # this rank's shard of the synthetic target numbering
+
+    # ---- resident inputs: synthetic library generated on the device, masks generated on the device and prepared
+    t0 = time.perf_counter()
+    lib = capi.Library(ctx, W, H, T)
+    lib.generate_synthetic(SEED, t_first, T)
+    masks_host = np.concatenate([ctx.synth_rgb(0, SEED, i, min(64, M - i), W, H, on_device=True) for i in range(0, M, 64)])
+    ms = capi.MaskSet(ctx, W, H, PARAMS["mask_threshold"], PARAMS["data_threshold"], PARAMS["z_tolerance"], PARAMS["xy_shift"],
+                      PARAMS["mirror"], rects)
+    mask_sizes = ms.add_rgb(masks_host)
+    setup_s = time.perf_counter() - t0
+
+    def step():
+        out = ms.search_topk(lib, TOPK, PCT_POSITIVE)
+        return out, ctx.last_stats()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev_ms, match_ms, launches, match_launches = 0.0, 0.0, 0, 0
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last, st = step()
+        dev_ms += st["total_device_ms"]
+        match_ms += st["match_kernel_ms"]
+        launches += st["kernel_launches"]
+        match_launches += st["match_kernel_launches"]
+    barrier()
+    wall_s = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join()
+
+    # max over ranks of the device time
+    times = torch.tensor([dev_ms, match_ms, wall_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, match_ms, wall_ms = [float(x) for x in times.tolist()]
+    comparisons_per_step = M * T * world
+    value = comparisons_per_step * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (pinned), every step: upload + encode targets, upload +
+    # prepare masks, search, top-K back on the host
+    e2e = None
+    if not args.no_e2e:
+        Te = args.e2e_targets or T
+        img_bytes = 3 * W * H
+        avail = 0
+        try:
+            for ln in open("/proc/meminfo"):
+                if ln.startswith("MemAvailable"):
+                    avail = int(ln.split()[1]) * 1024
+        except Exception:
+            pass
+        pool_t = Te
+        budget = int(avail * 0.5 / max(world, 1)) if avail else 8 << 30
+        if pool_t * img_bytes > budget:
+            pool_t = max(64, budget // img_bytes // 64 * 64)
+        pool_arr, pool_ptr = ctx.host_alloc(pool_t * img_bytes)
+        mask_arr, mask_ptr = ctx.host_alloc(M * img_bytes)
+        np.copyto(mask_arr, masks_host.reshape(-1))
+        for i in range(0, pool_t, 64):
+            n = min(64, pool_t - i)
+            pool_arr[i * img_bytes:(i + n) * img_bytes] = ctx.synth_rgb(1, SEED, t_first + i, n, W, H, on_device=True).reshape(-1)
+        lib.close()
+        ms.close()
+        barrier()
+        e2e_steps = max(1, args.e2e_steps)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            lib_e = capi.Library(ctx, W, H, Te)
+            done = 0
+            while done < Te:                      # cycle the pinned pool when it is smaller than the step's library
+                n = min(pool_t, Te - done)
+                lib_e.add_rgb_ptr(pool_ptr, n)
+                done += n
+            ms_e = capi.MaskSet(ctx, W, H, PARAMS["mask_threshold"], PARAMS["data_threshold"], PARAMS["z_tolerance"],
+                                PARAMS["xy_shift"], PARAMS["mirror"], rects)
+            ms_e.add_rgb_ptr(mask_ptr, M)
+            res = ms_e.search_topk(lib_e, TOPK, PCT_POSITIVE)
+            ms_e.close()
+            lib_e.close()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        d2h = M * TOPK * (4 + 8 + 1) + M * 4
+        e2e = {"value": M * Te * world * e2e_steps / e2e_s, "unit": "comparisons/s",
+               "h2d_bytes_per_step": (Te + M) * img_bytes * world, "d2h_bytes_per_step": d2h * world,
+               "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "targets_per_gpu": Te,
+               "pinned_pool_targets": pool_t,
+               "what": "cds_library_create + cds_library_add_rgb (H2D + encode) + cds_maskset_add_rgb (H2D + mask preparation) + "
+                       "cds_search_topk (+ result D2H, host merge), pinned host buffers"}
+        ctx.host_free(pool_ptr)
+        ctx.host_free(mask_ptr)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_launch_cmp = M * T / max(match_launches / args.steps, 1)
+        avg_launch_s = match_ms * 1e-3 / max(match_launches, 1)
+        achieved = per_launch_cmp * ALGO_BYTES_PER_COMPARISON / avg_launch_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "mask x target CDS comparisons/sec", "value": value, "unit": "comparisons/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": sampler.summary(), "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "pixelmatch_band_kernel<1,true>",
+                         "algorithmic_bytes_per_comparison": ALGO_BYTES_PER_COMPARISON,
+                         "comparisons_per_launch": per_launch_cmp, "avg_launch_ms": avg_launch_s * 1e3,
+                         "note": "algorithmic bytes = 3*W*H per comparison (SURVEY 8d); a mask group shares one pass over the "
+                                 "target, so frac can exceed 1 -- physical DRAM traffic is in `traffic` / profiles/"},
+            "e2e": e2e,
+            "mask_pixels_mean": float(np.mean(mask_sizes)), "setup_s": setup_s,
+            "matches_returned": int(last[3].sum()) if last is not None else None,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            def targets_fn(n):
+                return capi.synth_rgb_host(1, SEED, 0, n, W, H)
+            line["cpu_baseline"] = cpu_baseline(M, masks_host, targets_fn)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -169,7 +169,6 @@ class Context:
         _check(lib().cds_host_alloc(self.h, int(nbytes), C.byref(p)), self.h)
         buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=np.uint8)
-        arr._cds_ptr = p.value if hasattr(arr, "__dict__") else None
         return arr, p
 
     def host_free(self, p):

@@ -121,6 +121,7 @@ extern "C" cds_status cds_ctx_create(const int32_t *device_ids, int32_t n_dev, c
         if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate");
         if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev0), "cudaEventCreate");
         if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev1), "cudaEventCreate");
+        if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev2), "cudaEventCreate");
         if (s == CDS_OK) s = ctx->check(cudaMalloc(&d.d_rank_tab, rt.rank.size() * sizeof(uint16_t)), "cudaMalloc(rank table)");
         if (s == CDS_OK) s = ctx->check(cudaMemcpy(d.d_rank_tab, rt.rank.data(), rt.rank.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "cudaMemcpy(rank table)");
         if (s != CDS_OK) { cds_ctx_destroy(ctx); return s; }
@@ -152,6 +153,7 @@ extern "C" void cds_ctx_destroy(cds_ctx *ctx)
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.ev2) cudaEventDestroy(d.ev2);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     cudaGetLastError();
@@ -738,10 +740,11 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
             if (st == CDS_OK) {
                 launch_topk(d_scores[d], mc, nl, d_min[d] + m0, k, d_keys[d] + (size_t) m0 * k, d_counts[d] + m0, ds.stream);
                 ctx->stats.kernel_launches++;
+                cudaEventRecord(ds.ev2, ds.stream);
                 st = ctx->check(cudaGetLastError(), "topk kernel");
             }
         }
-        double chunk_ms = 0;
+        double chunk_ms = 0, chunk_total_ms = 0;
         for (int d = 0; d < D && st == CDS_OK; d++) {
             if (lib->local_size(d) == 0) continue;
             DevState &ds = ctx->devs[d];
@@ -751,10 +754,12 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
             float ms_f = 0;
             cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev1);
             chunk_ms = std::max(chunk_ms, (double) ms_f);
+            cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev2);
+            chunk_total_ms = std::max(chunk_total_ms, (double) ms_f);
         }
         match_ms += chunk_ms;
+        total_ms += chunk_total_ms;
     }
-    total_ms = match_ms;
     // read back per-device lists and merge on the host (no collective: nothing is reduced across devices)
     std::vector<std::vector<uint64_t>> h_keys(D);
     std::vector<std::vector<int32_t>> h_counts(D);

@@ -23,7 +23,7 @@ constexpr int64_t kLibBlock = 64;   // targets per block of the block-cyclic dev
 struct DevState {
     int dev = -1;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;   // match kernel start / end, search end
     uint16_t *d_rank_tab = nullptr;
     std::map<uint64_t, cds_class_interval *> d_class_tabs;   // keyed by the bits of zTolerance
     void *staging = nullptr;       // device staging for uploads
