@@ -32,6 +32,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kGroup = 64;          // masks per work item
 constexpr int kStages = 2;
 constexpr int kMaxBands = 128;
+constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy destination aligned)
 
 struct BandParams {
     const MaskDesc *masks;
@@ -99,8 +100,11 @@ __global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const Band
     constexpr int S = 2 * NRINGS;                     // halo rows = xyShift
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw);                       // kStages * stage_words
-    int *s_acc = reinterpret_cast<int *>(s_stage + (size_t) kStages * p.stage_words); // [kGroup][NV]
+    // every stage is preceded by kPrePad never-matching words: a pixel in the first row of a band whose shifted / mirrored
+    // column is -1 or -2 reads just below the stage
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw) + kPrePad;             // kStages * (stage_words + kPrePad)
+    const int stage_stride = p.stage_words + kPrePad;
+    int *s_acc = reinterpret_cast<int *>(s_stage - kPrePad + (size_t) kStages * stage_stride); // [kGroup][NV]
     uint32_t *s_seg = reinterpret_cast<uint32_t *>(s_acc + kGroup * NV);              // [kGroup][n_bands + 1]
     const cds_mask_record **s_rec = reinterpret_cast<const cds_mask_record **>(s_seg + kGroup * (p.n_bands + 1));
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_rec + kGroup);   // kStages mbarriers
@@ -120,6 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const Band
         s_work[1] = (long long) atomicAdd(p.work_counter, 1ull);
     }
     for (int i = tid; i < kGroup * NV; i += kThreads) s_acc[i] = 0;
+    if (tid < kStages * kPrePad) s_stage[(tid / kPrePad) * stage_stride - kPrePad + (tid % kPrePad)] = CDS_CODE_PAD_WORD;
     __syncthreads();
 
     // issue the load of band `b` of item `w` into stage `stage` (thread 0 only)
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const Band
         const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
         const uint32_t bar = smem_u32(s_bar + stage);
         mbar_expect_tx(bar, bytes);
-        bulk_load(smem_u32(s_stage + (size_t) stage * p.stage_words), src, bytes, bar);
+        bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
     };
 
     long long w = s_work[0];
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const Band
         for (int b = 0; b < p.n_bands; b++, seq++) {
             const int stage = seq & 1;
             mbar_wait(smem_u32(s_bar + stage), (seq >> 1) & 1);
-            const uint32_t *band = s_stage + (size_t) stage * p.stage_words;
+            const uint32_t *band = s_stage + (size_t) stage * stage_stride;
             const int y0 = b * R;
 
             // warps pull (mask, band) segments
@@ -280,7 +285,7 @@ BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
         int n_bands = (g.H + R - 1) / R;
         if (n_bands > kMaxBands) break;
         size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
-        size_t bytes = kStages * stage_words * 4 + (size_t) kGroup * NV * 4 + (size_t) kGroup * (n_bands + 1) * 4 +
+        size_t bytes = kStages * (stage_words + kPrePad) * 4 + (size_t) kGroup * NV * 4 + (size_t) kGroup * (n_bands + 1) * 4 +
                        (size_t) kGroup * 8 + kStages * 8 + 2 * 4 + 2 * 8 + 64;
         if (bytes <= budget && stage_words * 4 < (1u << 20)) {
             c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = bytes; c.ok = true;
