@@ -51,7 +51,8 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons while the timed region runs (NVML in-process; nvidia-smi would do the same query
+    but spawning it every 200 ms stalls CUDA calls of this process)."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
@@ -60,32 +61,40 @@ class ClockSampler(threading.Thread):
         self.stop_flag = threading.Event()
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            hnd = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            mx = nv.nvmlDeviceGetMaxClockInfo(hnd, nv.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(hnd, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+                self.samples.append((float(sm), float(mx), [k for k, b in bits.items() if r & b]))
+                self.stop_flag.wait(0.1)
+        except Exception:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            while not self.stop_flag.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append((float(out[0]), float(out[1]),
+                                         [n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")]))
+                except Exception:
+                    pass
+                self.stop_flag.wait(1.0)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx.append(float(s[1]))
-            except Exception:
-                continue
-            for name, v in zip(names, s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted({r for s in self.samples for r in s[2]})
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": float(max(s[1] for s in self.samples)),
+                "reasons": reasons, "samples": len(self.samples)}
 
 
 def dist_env():

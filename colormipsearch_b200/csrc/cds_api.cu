@@ -54,6 +54,18 @@ cds_status cds_ctx::ensure_pinned(DevState &d, size_t bytes)
     return CDS_OK;
 }
 
+cds_status cds_ctx::ensure_scratch(DevState &d, int slot, size_t bytes, void **out)
+{
+    if (d.scratch_bytes[slot] < bytes) {
+        CDS_CUDA(this, cudaSetDevice(d.dev));
+        if (d.scratch[slot]) { CDS_CUDA(this, cudaStreamSynchronize(d.stream)); cudaFree(d.scratch[slot]); d.scratch[slot] = nullptr; d.scratch_bytes[slot] = 0; }
+        CDS_CUDA(this, cudaMalloc(&d.scratch[slot], bytes));
+        d.scratch_bytes[slot] = bytes;
+    }
+    *out = d.scratch[slot];
+    return CDS_OK;
+}
+
 cds_status cds_ctx::class_table_on(DevState &d, double tol, const cds_class_interval **out)
 {
     uint64_t key;
@@ -150,6 +162,7 @@ extern "C" void cds_ctx_destroy(cds_ctx *ctx)
         if (d.d_rank_tab) cudaFree(d.d_rank_tab);
         for (auto &kv : d.d_class_tabs) cudaFree(kv.second);
         if (d.staging) cudaFree(d.staging);
+        for (int i = 0; i < 4; i++) if (d.scratch[i]) cudaFree(d.scratch[i]);
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
@@ -617,12 +630,10 @@ extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cd
     int64_t max_local = 0;
     for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
     int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 64 << 20) / std::max<int64_t>(max_local, 1)));
-    auto free_all = [&]() {
-        for (int d = 0; d < D; d++) if (d_scores[d]) { cudaSetDevice(ctx->devs[d].dev); cudaFree(d_scores[d]); }
-    };
+    auto free_all = [&]() {};
     for (int d = 0; d < D && st == CDS_OK; d++) {
         st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
-        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_scores[d], (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t)), "cudaMalloc(scores)");
+        if (st == CDS_OK) st = ctx->ensure_scratch(ctx->devs[d], 0, (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t), (void **) &d_scores[d]);
         if (st == CDS_OK) st = ctx->ensure_pinned(ctx->devs[d], (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t));
     }
     double match_ms = 0;
@@ -707,23 +718,15 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
     std::vector<uint64_t *> d_keys(D, nullptr);
     std::vector<int32_t *> d_counts(D, nullptr);
     cds_status st = CDS_OK;
-    auto free_all = [&]() {
-        for (int d = 0; d < D; d++) {
-            cudaSetDevice(ctx->devs[d].dev);
-            if (d_scores[d]) cudaFree(d_scores[d]);
-            if (d_min[d]) cudaFree(d_min[d]);
-            if (d_keys[d]) cudaFree(d_keys[d]);
-            if (d_counts[d]) cudaFree(d_counts[d]);
-        }
-    };
+    auto free_all = [&]() {};
     const size_t keys_bytes = (size_t) M * k * sizeof(uint64_t);
     for (int d = 0; d < D && st == CDS_OK; d++) {
         DevState &ds = ctx->devs[d];
         st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
-        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_scores[d], (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t)), "cudaMalloc(scores)");
-        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_min[d], M * sizeof(int32_t)), "cudaMalloc(min scores)");
-        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_keys[d], keys_bytes), "cudaMalloc(topk keys)");
-        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_counts[d], M * sizeof(int32_t)), "cudaMalloc(topk counts)");
+        if (st == CDS_OK) st = ctx->ensure_scratch(ds, 0, (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t), (void **) &d_scores[d]);
+        if (st == CDS_OK) st = ctx->ensure_scratch(ds, 1, M * sizeof(int32_t), (void **) &d_min[d]);
+        if (st == CDS_OK) st = ctx->ensure_scratch(ds, 2, keys_bytes, (void **) &d_keys[d]);
+        if (st == CDS_OK) st = ctx->ensure_scratch(ds, 3, M * sizeof(int32_t), (void **) &d_counts[d]);
         if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_min[d], min_score.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream), "min scores H2D");
         if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_counts[d], 0, M * sizeof(int32_t), ds.stream), "memset");
         if (st == CDS_OK) st = ctx->ensure_pinned(ds, keys_bytes + M * sizeof(int32_t));

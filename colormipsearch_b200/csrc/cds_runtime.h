@@ -30,6 +30,8 @@ struct DevState {
     size_t staging_bytes = 0;
     void *h_pinned = nullptr;      // pinned host scratch for read-backs
     size_t h_pinned_bytes = 0;
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device scratch (scores, min scores, keys, counts)
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
 };
 
 void set_tls_error(const std::string &msg);
@@ -46,6 +48,7 @@ struct cds_ctx {
     cds_status check(cudaError_t e, const char *what) const;
     cds_status ensure_staging(cds::DevState &d, size_t bytes);
     cds_status ensure_pinned(cds::DevState &d, size_t bytes);
+    cds_status ensure_scratch(cds::DevState &d, int slot, size_t bytes, void **out);
     cds_status class_table_on(cds::DevState &d, double tol, const cds_class_interval **out);
 };
 
