@@ -5,6 +5,7 @@ implementation of anything behind it, and loading fails loudly when the library 
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -145,9 +146,12 @@ class Context:
             st = lib().cds_ctx_create(None, 1 if n_dev is None else int(n_dev), C.byref(h))
         _check(st, None)
         self.h = h
+        self._children = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(self._children):      # libraries / mask sets die before their context
+                child.close()
             lib().cds_ctx_destroy(self.h)
             self.h = None
 
@@ -226,6 +230,7 @@ class Library:
         h = _vp()
         _check(lib().cds_library_create(ctx.h, W, H, int(capacity), C.byref(h)), ctx.h)
         self.h = h
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "h", None):
@@ -278,6 +283,7 @@ class MaskSet:
         h = _vp()
         _check(lib().cds_maskset_create(ctx.h, W, H, C.byref(p), C.byref(h)), ctx.h)
         self.h = h
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "h", None):
@@ -348,6 +354,7 @@ class ShapeMaskSet:
         h = _vp()
         _check(lib().cds_shape_maskset_create(ctx.h, W, H, int(query_threshold), int(border), int(bool(mirror)), ra, nr, _ptr(roi), C.byref(h)), ctx.h)
         self.h = h
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "h", None):
