@@ -8,17 +8,20 @@
 // the mirrored ones, mirrored wins only when strictly greater.
 //
 // How (B200):
-//   * work item = (mask group of kGroup masks, target).  Items are ordered group-major so that all CTAs stream the SAME
-//     group's pixel records (L2-resident, ~10 MB) while each target plane is read from HBM once per group.
-//   * a persistent grid of one 512-thread CTA per SM pulls items from a global counter.  The target is consumed as
-//     bands of R rows (+ s = xyShift halo rows on both sides).  A band of a plane is ONE contiguous span of HBM
-//     (cds_kernels.cuh PlaneGeom), fetched by a single cp.async.bulk (TMA bulk copy, SASS UBLKCP) that completes on an
-//     mbarrier; two stages double-buffer the copy of band b+2 (or of the next item's first bands) behind the compute of b, b+1.
+//   * work item = (mask group of GROUP masks, target).  Items are ordered group-major so that all CTAs stream the SAME
+//     group's pixel records (L2-resident) while each target plane is read from HBM once per group.
+//   * a persistent grid of one CTA per SM: NCW consumer warps + 1 producer warp.  The target is consumed as bands of R rows
+//     (+ s = xyShift halo rows on both sides).  A band of a plane is ONE contiguous span of HBM (cds_kernels.cuh PlaneGeom),
+//     fetched by a single cp.async.bulk (TMA bulk copy, SASS UBLKCP) that completes on a "full" mbarrier.  Two stages; the
+//     producer refills a stage as soon as every consumer warp has arrived on its "empty" mbarrier, so there is no CTA-wide
+//     barrier per band and warps may run one band ahead of stragglers.  The producer also pulls the work items from a
+//     global counter and publishes them to the consumers through shared memory.
 //   * out-of-image pixels of shifted / mirrored variants need no bounds test: they land in the pad columns / guard rows of
-//     the plane, whose code words can never match.
-//   * inside a band, warps grab (mask, band) segments from a shared counter; a lane owns one mask pixel per iteration:
-//     one LDG.128 for the record, one LDS per variant, 4 integer ops for the two-interval test, one predicated add into a
-//     packed counter.  A segment ends with one REDUX per packed register and plain adds into per-(mask, variant) accumulators.
+//     the plane (or the pad words placed below each stage), whose code words can never match.
+//   * inside a band, consumer warps grab tickets = (mask, chunk of CHUNK records of that mask inside the band) from a shared
+//     counter; a lane owns one mask pixel per iteration: one LDG.128 for the record (prefetched one iteration ahead), one
+//     LDS per variant, two subtract/compare pairs and one predicated add into a packed counter.  A ticket ends with one
+//     REDUX per packed register and shared-memory atomic adds into the per-(mask, variant) accumulators.
 #include "cds_band.cuh"
 
 #include <cstdlib>
@@ -27,12 +30,10 @@ namespace cds {
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kGroup = 64;          // masks per work item
 constexpr int kStages = 2;
 constexpr int kMaxBands = 128;
 constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy destination aligned)
+constexpr int kChunk = 256;         // records per ticket
 
 struct BandParams {
     const MaskDesc *masks;
@@ -58,6 +59,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -71,8 +76,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+template <int N>
+__device__ __forceinline__ void consumer_barrier()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
+}
 
-// shift offsets of ring structure NRINGS (0: none, 1: +-2, 2: +-2 and +-4), in the order of the maskset's ShiftSet
+// cnt += INC when the code word c lies in [lo1, lo1+len1] or [lo2, lo2+len2]: two subtracts, two compares, one predicated add
+template <uint32_t INC>
+__device__ __forceinline__ void count_hit(uint32_t &cnt, uint32_t c, uint32_t lo1, uint32_t len1, uint32_t lo2, uint32_t len2)
+{
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 a, b;\n\t"
+        "sub.u32 a, %1, %2;\n\t"
+        "sub.u32 b, %1, %4;\n\t"
+        "setp.le.u32 p, a, %3;\n\t"
+        "setp.le.or.u32 p, b, %5, p;\n\t"
+        "@p add.u32 %0, %0, %6;\n\t}"
+        : "+r"(cnt) : "r"(c), "r"(lo1), "r"(len1), "r"(lo2), "r"(len2), "n"(INC));
+}
+
+// shift offsets of ring structure NRINGS (0: none, 1: +-2, 2: +-2 and +-4)
 template <int NRINGS> struct Offsets;
 template <> struct Offsets<0> { static constexpr int N = 1; };
 template <> struct Offsets<1> { static constexpr int N = 9; };
@@ -91,104 +114,163 @@ __device__ __forceinline__ void offset_of(int v, int &dx, int &dy)
     dy = (k % 3 - 1) * 4;
 }
 
-template <int NRINGS, bool MIRROR>
-__global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const BandParams p)
+// Shared-memory layout, identical on host (sizing) and device (carving).
+template <int GROUP>
+struct BandSmem {
+    size_t stage_off, acc_off, seg_off, tick_off, rec_off, bar_off, next_off, item_off, total;
+    __host__ __device__ BandSmem(int stage_words, int n_bands, int NV)
+    {
+        size_t o = 0;
+        stage_off = o; o += (size_t) kStages * (stage_words + kPrePad) * 4;
+        acc_off = o;   o += (size_t) GROUP * NV * 4;
+        seg_off = o;   o += (size_t) GROUP * (n_bands + 1) * 4;
+        tick_off = o;  o += ((size_t) n_bands * (GROUP + 1) * 2 + 15) / 16 * 16;
+        rec_off = o;   o += (size_t) GROUP * 8;
+        bar_off = o;   o += 2 * kStages * 8;
+        next_off = o;  o += 16;
+        item_off = o;  o += 16;
+        total = o;
+    }
+};
+
+template <int NRINGS, bool MIRROR, int GROUP, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(const BandParams p)
 {
     constexpr int NS = Offsets<NRINGS>::N;            // variants per orientation
     constexpr int NV = MIRROR ? 2 * NS : NS;          // variants
     constexpr int NREG = (NV + 1) / 2;                // packed 16-bit counter registers
     constexpr int S = 2 * NRINGS;                     // halo rows = xyShift
+    constexpr int NCT = NCW * 32;                     // consumer threads
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // every stage is preceded by kPrePad never-matching words: a pixel in the first row of a band whose shifted / mirrored
-    // column is -1 or -2 reads just below the stage
-    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw) + kPrePad;             // kStages * (stage_words + kPrePad)
+    const BandSmem<GROUP> L(p.stage_words, p.n_bands, NV);
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
-    int *s_acc = reinterpret_cast<int *>(s_stage - kPrePad + (size_t) kStages * stage_stride); // [kGroup][NV]
-    uint32_t *s_seg = reinterpret_cast<uint32_t *>(s_acc + kGroup * NV);              // [kGroup][n_bands + 1]
-    const cds_mask_record **s_rec = reinterpret_cast<const cds_mask_record **>(s_seg + kGroup * (p.n_bands + 1));
-    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_rec + kGroup);   // kStages mbarriers
-    int *s_next = reinterpret_cast<int *>(s_bar + kStages);                           // [2] segment tickets
-    long long *s_work = reinterpret_cast<long long *>(s_next + 2);                    // [2] current / next item
+    int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
+    uint32_t *s_seg = reinterpret_cast<uint32_t *>(smem_raw + L.seg_off);               // [GROUP][n_bands + 1] record index at band starts
+    uint16_t *s_tick = reinterpret_cast<uint16_t *>(smem_raw + L.tick_off);             // [n_bands][GROUP + 1] ticket prefix sums
+    const cds_mask_record **s_rec = reinterpret_cast<const cds_mask_record **>(smem_raw + L.rec_off);
+    unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
+    unsigned long long *s_empty = s_full + kStages;
+    int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
+    long long *s_item = reinterpret_cast<long long *>(smem_raw + L.item_off);           // [2] published work items
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int pitch = p.g.pitch, W = p.g.W, H = p.g.H, R = p.rows_per_band;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pitch = p.g.pitch, W = p.g.W, H = p.g.H, R = p.rows_per_band, NB = p.n_bands;
     const long long n_items = (long long) p.n_groups * p.n_targets;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) mbar_init(smem_u32(s_bar + s), 1);
-        s_next[0] = 0; s_next[1] = 0;
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(smem_u32(s_full + s), 1);
+            mbar_init(smem_u32(s_empty + s), NCW);
+            s_next[s] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        s_work[0] = (long long) atomicAdd(p.work_counter, 1ull);
-        s_work[1] = (long long) atomicAdd(p.work_counter, 1ull);
     }
-    for (int i = tid; i < kGroup * NV; i += kThreads) s_acc[i] = 0;
+    for (int i = tid; i < GROUP * NV; i += blockDim.x) s_acc[i] = 0;
+    // never-matching words below each stage: a pixel in the first row of a band whose shifted / mirrored column is -1..-4
     if (tid < kStages * kPrePad) s_stage[(tid / kPrePad) * stage_stride - kPrePad + (tid % kPrePad)] = CDS_CODE_PAD_WORD;
     __syncthreads();
 
-    // issue the load of band `b` of item `w` into stage `stage` (thread 0 only)
-    auto issue_load = [&](long long w, int b, int stage) {
-        const int64_t t = w % p.n_targets;
-        const int y0 = b * R;
-        const int y1 = min(y0 + R, H);
-        const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
-        const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
-        const uint32_t bar = smem_u32(s_bar + stage);
-        mbar_expect_tx(bar, bytes);
-        bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
-    };
-
-    long long w = s_work[0];
-    long long w_next = s_work[1];
-    uint32_t seq = 0;                     // running band number across items: stage = seq & 1, parity = (seq >> 1) & 1
-    if (tid == 0 && w < n_items) {
-        issue_load(w, 0, 0);
-        if (p.n_bands > 1) issue_load(w, 1, 1);
-        else if (w_next < n_items) issue_load(w_next, 0, 1);
+    if (warp == NCW) {
+        // ------------------------------------------------------------------ producer (one lane)
+        if (lane == 0) {
+            uint32_t q = 0;                 // running band number across items: stage = q & 1, use = q >> 1
+            uint32_t iseq = 0;
+            for (;;) {
+                const long long w = (long long) atomicAdd(p.work_counter, 1ull);
+                const bool done = w >= n_items;
+                const int nb = done ? 1 : NB;
+                for (int b = 0; b < nb; b++, q++) {
+                    const int stage = q & 1;
+                    if (q >= kStages) mbar_wait(smem_u32(s_empty + stage), ((q >> 1) - 1) & 1);
+                    s_next[stage] = 0;
+                    if (b == 0) s_item[iseq & 1] = done ? -1 : w;
+                    const uint32_t bar = smem_u32(s_full + stage);
+                    if (done) { mbar_arrive(bar); break; }
+                    const int64_t t = w % p.n_targets;
+                    const int y0 = b * R;
+                    const int y1 = min(y0 + R, H);
+                    const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
+                    const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
+                    mbar_expect_tx(bar, bytes);
+                    bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
+                }
+                if (done) break;
+                iseq++;
+            }
+        }
+        return;
     }
 
-    while (w < n_items) {
+    // ---------------------------------------------------------------------- consumers
+    uint32_t q = 0, iseq = 0;
+    int cur_gi = -1;
+    for (;;) {
+        mbar_wait(smem_u32(s_full + (q & 1)), (q >> 1) & 1);
+        const long long w = *reinterpret_cast<volatile long long *>(s_item + (iseq & 1));
+        if (w < 0) break;
         const int gi = (int) (w / p.n_targets);
         const int64_t t = w % p.n_targets;
-        const int m0 = gi * kGroup;
-        const int mb = min(kGroup, p.n_masks - m0);
+        const int m0 = gi * GROUP;
+        const int mb = min(GROUP, p.n_masks - m0);
 
-        // per-item tables: record base pointers and band boundaries of every mask of the group
-        for (int i = tid; i < mb; i += kThreads) s_rec[i] = p.masks[m0 + i].records;
-        for (int i = tid; i < mb * (p.n_bands + 1); i += kThreads) {
-            const int mi = i / (p.n_bands + 1), b = i % (p.n_bands + 1);
-            s_seg[i] = __ldg(p.masks[m0 + mi].rowstart + min(b * R, H));
+        if (gi != cur_gi) {
+            // per-group tables: record base pointers, band boundaries and per-band ticket prefix sums.  Every consumer passed
+            // the barrier that ends the previous item, so nobody still reads the old tables.
+            for (int i = tid; i < mb; i += NCT) s_rec[i] = p.masks[m0 + i].records;
+            for (int i = tid; i < mb * (NB + 1); i += NCT) {
+                const int mi = i / (NB + 1), b = i % (NB + 1);
+                s_seg[i] = __ldg(p.masks[m0 + mi].rowstart + min(b * R, H));
+            }
+            consumer_barrier<NCT>();
+            for (int b = tid; b < NB; b += NCT) {
+                uint32_t acc = 0;
+                uint16_t *row = s_tick + b * (GROUP + 1);
+                for (int mi = 0; mi < GROUP; mi++) {
+                    row[mi] = (uint16_t) acc;
+                    if (mi < mb) acc += (s_seg[mi * (NB + 1) + b + 1] - s_seg[mi * (NB + 1) + b] + kChunk - 1) / kChunk;
+                }
+                row[GROUP] = (uint16_t) acc;
+            }
+            consumer_barrier<NCT>();
+            cur_gi = gi;
         }
-        __syncthreads();
 
-        for (int b = 0; b < p.n_bands; b++, seq++) {
-            const int stage = seq & 1;
-            mbar_wait(smem_u32(s_bar + stage), (seq >> 1) & 1);
+        for (int b = 0; b < NB; b++, q++) {
+            const int stage = q & 1;
+            if (b > 0) mbar_wait(smem_u32(s_full + stage), (q >> 1) & 1);
             const uint32_t *band = s_stage + (size_t) stage * stage_stride;
             const int y0 = b * R;
+            const uint16_t *tick = s_tick + b * (GROUP + 1);
+            const int n_tickets = tick[GROUP];
 
-            // warps pull (mask, band) segments
             for (;;) {
-                int mi = 0;
-                if (lane == 0) mi = atomicAdd(&s_next[b & 1], 1);
-                mi = __shfl_sync(0xffffffffu, mi, 0);
-                if (mi >= mb) break;
-                const uint32_t seg0 = s_seg[mi * (p.n_bands + 1) + b];
-                const uint32_t seg1 = s_seg[mi * (p.n_bands + 1) + b + 1];
-                if (seg0 == seg1) continue;
+                int tk = 0;
+                if (lane == 0) tk = atomicAdd(&s_next[stage], 1);
+                tk = __shfl_sync(0xffffffffu, tk, 0);
+                if (tk >= n_tickets) break;
+                // mask of the ticket: the last mi with tick[mi] <= tk
+                int le = 0;
+#pragma unroll
+                for (int k = 0; k < GROUP / 32; k++) le += __popc(__ballot_sync(0xffffffffu, (int) tick[k * 32 + lane] <= tk));
+                const int mi = le - 1;
+                const uint32_t seg_end = s_seg[mi * (NB + 1) + b + 1];
+                const uint32_t seg0 = s_seg[mi * (NB + 1) + b] + (uint32_t) (tk - tick[mi]) * kChunk;
+                const uint32_t seg1 = min(seg0 + kChunk, seg_end);
                 const cds_mask_record *rec = s_rec[mi];
                 uint32_t cnt[NREG];
 #pragma unroll
                 for (int j = 0; j < NREG; j++) cnt[j] = 0;
 
                 uint32_t i = seg0 + lane;
-                uint4 q = make_uint4(0, 0, 0, 0);
-                if (i < seg1) q = __ldg(reinterpret_cast<const uint4 *>(rec + i));
+                uint4 qr = make_uint4(0, 0, 0, 0);
+                if (i < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + i));
                 while (i < seg1) {
-                    const uint4 cur = q;
+                    const uint4 cur = qr;
                     const uint32_t inext = i + 32;
-                    if (inext < seg1) q = __ldg(reinterpret_cast<const uint4 *>(rec + inext));   // prefetch behind the compute
+                    if (inext < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + inext));   // prefetch behind the compute
                     const int x = (int) (cur.x & 0xFFFFu);
                     const int row = (int) (cur.x >> 16) - y0 + S;
                     const uint32_t lo1 = cur.y, lo2 = cur.z;
@@ -201,8 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const Band
                         int dx, dy;
                         offset_of<NRINGS>(v, dx, dy);
                         const uint32_t c = pc[dy * pitch + dx];
-                        const bool hit = (c - lo1 <= len1) | (c - lo2 <= len2);
-                        if (hit) cnt[v >> 1] += (v & 1) ? 0x10000u : 1u;
+                        if (v & 1) count_hit<0x10000u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
+                        else count_hit<1u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
                     }
                     if (MIRROR) {
 #pragma unroll
@@ -210,13 +292,13 @@ __global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const Band
                             int dx, dy;
                             offset_of<NRINGS>(v, dx, dy);
                             const uint32_t c = pm[dy * pitch - dx];              // mirror of (x + dx) is (W-1-x) - dx
-                            const bool hit = (c - lo1 <= len1) | (c - lo2 <= len2);
-                            if (hit) cnt[(NS + v) >> 1] += ((NS + v) & 1) ? 0x10000u : 1u;
+                            if ((NS + v) & 1) count_hit<0x10000u>(cnt[(NS + v) >> 1], c, lo1, len1, lo2, len2);
+                            else count_hit<1u>(cnt[(NS + v) >> 1], c, lo1, len1, lo2, len2);
                         }
                     }
                     i = inext;
                 }
-                // segment done: warp totals (a segment has < 65536 pixels, so the packed halves cannot carry)
+                // ticket done: warp totals (a ticket has <= kChunk pixels, so the packed halves cannot carry)
                 uint32_t mine0 = 0, mine1 = 0;
 #pragma unroll
                 for (int j = 0; j < NREG; j++) {
@@ -224,23 +306,21 @@ __global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const Band
                     if ((lane >> 1) == j) mine0 = tot;
                     if (((lane + 32) >> 1) == j) mine1 = tot;
                 }
-                if (lane < NV) s_acc[mi * NV + lane] += (int) ((lane & 1) ? (mine0 >> 16) : (mine0 & 0xFFFFu));
-                if (NV > 32 && lane + 32 < NV) s_acc[mi * NV + lane + 32] += (int) ((lane & 1) ? (mine1 >> 16) : (mine1 & 0xFFFFu));
-            }
-            __syncthreads();      // everyone is done with this stage and with this band's tickets
-            if (tid == 0) {
-                s_next[b & 1] = 0;
-                // refill this stage with the band two ahead: of this item, or of the next one
-                if (b + 2 < p.n_bands) issue_load(w, b + 2, stage);
-                else if (w_next < n_items) {
-                    const int nb = b + 2 - p.n_bands;
-                    if (nb < p.n_bands) issue_load(w_next, nb, stage);
+                const int v0 = (int) ((lane & 1) ? (mine0 >> 16) : (mine0 & 0xFFFFu));
+                if (lane < NV && v0) atomicAdd(&s_acc[mi * NV + lane], v0);
+                if (NV > 32) {
+                    const int v1 = (int) ((lane & 1) ? (mine1 >> 16) : (mine1 & 0xFFFFu));
+                    if (lane + 32 < NV && v1) atomicAdd(&s_acc[mi * NV + lane + 32], v1);
                 }
             }
+            // this warp is done with the stage: let the producer refill it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(s_empty + stage));
         }
 
         // item epilogue: max over variants per orientation; mirrored wins only when strictly greater
-        for (int mi = tid; mi < mb; mi += kThreads) {
+        consumer_barrier<NCT>();
+        for (int mi = tid; mi < mb; mi += NCT) {
             int best = 0, bestm = 0;
 #pragma unroll
             for (int v = 0; v < NS; v++) best = max(best, s_acc[mi * NV + v]);
@@ -254,16 +334,8 @@ __global__ void __launch_bounds__(kThreads, 1) pixelmatch_band_kernel(const Band
 #pragma unroll
             for (int v = 0; v < NV; v++) s_acc[mi * NV + v] = 0;
         }
-        if (tid == 0) {
-            s_work[0] = w_next;
-            s_work[1] = (long long) atomicAdd(p.work_counter, 1ull);
-        }
-        __syncthreads();
-        w = s_work[0];
-        w_next = s_work[1];
-        // a single-band image never prefetched the item after next: top it up
-        if (p.n_bands == 1 && tid == 0 && w < n_items && w_next < n_items) issue_load(w_next, 0, (seq + 1) & 1);
-        __syncthreads();
+        consumer_barrier<NCT>();
+        iseq++;
     }
 }
 
@@ -273,6 +345,7 @@ struct BandConfig {
     bool ok;
 };
 
+template <int GROUP>
 BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
 {
     BandConfig c{};
@@ -280,15 +353,14 @@ BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
     const int NS = xy_shift == 0 ? 1 : (xy_shift == 2 ? 9 : 17);
     const int NV = mirror ? 2 * NS : NS;
     const size_t budget = 227 * 1024;
-    // fixed part: accumulators, record pointers, barriers, tickets, work slots (+ slack for the seg table, solved below)
-    for (int R = (int) (65535 / g.W); R >= 1; R--) {
+    for (int R = g.H; R >= 1; R--) {
         int n_bands = (g.H + R - 1) / R;
         if (n_bands > kMaxBands) break;
         size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
-        size_t bytes = kStages * (stage_words + kPrePad) * 4 + (size_t) kGroup * NV * 4 + (size_t) kGroup * (n_bands + 1) * 4 +
-                       (size_t) kGroup * 8 + kStages * 8 + 2 * 4 + 2 * 8 + 64;
-        if (bytes <= budget && stage_words * 4 < (1u << 20)) {
-            c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = bytes; c.ok = true;
+        if (stage_words * 4 >= (1u << 20)) continue;
+        BandSmem<GROUP> L((int) stage_words, n_bands, NV);
+        if (L.total <= budget) {
+            c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = L.total; c.ok = true;
             return c;
         }
     }
@@ -298,6 +370,37 @@ BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
 
 unsigned long long *g_work_counter[64] = {nullptr};
 
+int env_int(const char *name, int dflt)
+{
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+template <int GROUP, int NCW>
+int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
+               int xy_shift, bool mirror, int32_t *scores, cudaStream_t s, int dev)
+{
+    BandConfig c = band_config<GROUP>(xy_shift, mirror, g);
+    if (!c.ok) return 0;
+    BandParams p;
+    p.masks = masks; p.n_masks = n_masks; p.planes = planes; p.g = g; p.n_targets = n_targets; p.scores = scores;
+    p.work_counter = g_work_counter[dev];
+    p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
+    p.n_groups = (n_masks + GROUP - 1) / GROUP;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    long long n_items = (long long) p.n_groups * n_targets;
+    int grid = (int) std::min<long long>(n_sm, n_items);
+    void (*kern)(const BandParams) = nullptr;
+    const int rings = xy_shift / 2;
+    if (rings == 0) kern = mirror ? pixelmatch_band_kernel<0, true, GROUP, NCW> : pixelmatch_band_kernel<0, false, GROUP, NCW>;
+    else if (rings == 1) kern = mirror ? pixelmatch_band_kernel<1, true, GROUP, NCW> : pixelmatch_band_kernel<1, false, GROUP, NCW>;
+    else kern = mirror ? pixelmatch_band_kernel<2, true, GROUP, NCW> : pixelmatch_band_kernel<2, false, GROUP, NCW>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem_bytes);
+    kern<<<grid, (NCW + 1) * 32, c.smem_bytes, s>>>(p);
+    return 1;
+}
+
 }  // namespace
 
 bool band_kernel_supported(int xy_shift, const PlaneGeom &g)
@@ -305,13 +408,13 @@ bool band_kernel_supported(int xy_shift, const PlaneGeom &g)
     static const bool disabled = std::getenv("CDSGPU_DISABLE_BAND") != nullptr;
     if (disabled) return false;
     if (!(xy_shift == 0 || xy_shift == 2 || xy_shift == 4)) return false;
-    if (xy_shift > g.guard || xy_shift > g.pitch - g.W) return false;
-    return band_config(xy_shift, true, g).ok;
+    if (xy_shift > g.guard || xy_shift > g.pitch - g.W || xy_shift > kPrePad) return false;
+    return band_config<128>(xy_shift, true, g).ok && band_config<64>(xy_shift, true, g).ok;
 }
 
 int band_min_masks()
 {
-    static const int v = [] { const char *e = std::getenv("CDSGPU_BAND_MIN_MASKS"); return e ? std::atoi(e) : 16; }();
+    static const int v = env_int("CDSGPU_BAND_MIN_MASKS", 16);
     return v;
 }
 
@@ -326,25 +429,16 @@ int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *p
         if (cudaMalloc(&g_work_counter[dev], sizeof(unsigned long long)) != cudaSuccess) return 0;
     }
     cudaMemsetAsync(g_work_counter[dev], 0, sizeof(unsigned long long), s);
-    BandConfig c = band_config(xy_shift, mirror, g);
-    if (!c.ok) return 0;
-    BandParams p;
-    p.masks = masks; p.n_masks = n_masks; p.planes = planes; p.g = g; p.n_targets = n_targets; p.scores = scores;
-    p.work_counter = g_work_counter[dev];
-    p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
-    p.n_groups = (n_masks + kGroup - 1) / kGroup;
-    int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    long long n_items = (long long) p.n_groups * n_targets;
-    int grid = (int) std::min<long long>(n_sm, n_items);
-    void (*kern)(const BandParams) = nullptr;
-    const int rings = xy_shift / 2;
-    if (rings == 0) kern = mirror ? pixelmatch_band_kernel<0, true> : pixelmatch_band_kernel<0, false>;
-    else if (rings == 1) kern = mirror ? pixelmatch_band_kernel<1, true> : pixelmatch_band_kernel<1, false>;
-    else kern = mirror ? pixelmatch_band_kernel<2, true> : pixelmatch_band_kernel<2, false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem_bytes);
-    kern<<<grid, kThreads, c.smem_bytes, s>>>(p);
-    return 1;
+    // tuning knobs (defaults picked from profiles/): masks per work item, consumer warps per CTA
+    static const int group_env = env_int("CDSGPU_BAND_GROUP", 0);
+    static const int warps_env = env_int("CDSGPU_BAND_WARPS", 16);
+    const int group = group_env ? group_env : (n_masks > 96 ? 128 : 64);
+    if (group == 128) {
+        if (warps_env == 24) return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
+        return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
+    }
+    if (warps_env == 24) return launch_cfg<64, 24>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
+    return launch_cfg<64, 16>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
 }
 
 }  // namespace cds
