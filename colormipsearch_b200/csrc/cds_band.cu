@@ -431,7 +431,7 @@ int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *p
     cudaMemsetAsync(g_work_counter[dev], 0, sizeof(unsigned long long), s);
     // tuning knobs (defaults picked from profiles/): masks per work item, consumer warps per CTA
     static const int group_env = env_int("CDSGPU_BAND_GROUP", 0);
-    static const int warps_env = env_int("CDSGPU_BAND_WARPS", 16);
+    static const int warps_env = env_int("CDSGPU_BAND_WARPS", 24);
     const int group = group_env ? group_env : (n_masks > 96 ? 128 : 64);
     if (group == 128) {
         if (warps_env == 24) return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
