@@ -244,6 +244,39 @@ cds_status cds_library::bake(int threshold)
     return CDS_OK;
 }
 
+cds_status cds_library::ensure_occupancy(int rings)
+{
+    if (occ_rings != rings || occ_threshold != baked_threshold) {
+        for (auto &sh : shards) sh.occ_done = 0;
+        occ_rings = rings;
+        occ_threshold = baked_threshold;
+    }
+    const size_t plane_words = (size_t) g.H * bpitch;
+    bool launched = false;
+    for (int d = 0; d < n_dev(); d++) {
+        Shard &sh = shards[d];
+        const int64_t nl = local_size(d);
+        if (sh.occ_done >= nl) continue;
+        DevState &ds = ctx->devs[d];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        if (!sh.occ) {
+            CDS_CUDA(ctx, cudaMalloc(&sh.occ, (size_t) sh.cap_local * plane_words * sizeof(uint32_t)));
+            CDS_CUDA(ctx, cudaMalloc(&sh.valid, (size_t) sh.cap_local * plane_words * sizeof(uint32_t)));
+        }
+        launch_occupancy(sh.planes, g, sh.occ_done, nl - sh.occ_done, rings, bpitch, sh.valid, sh.occ, ds.stream);
+        ctx->stats.kernel_launches += 2;
+        CDS_CUDA(ctx, cudaGetLastError());
+        sh.occ_done = nl;
+        launched = true;
+    }
+    if (launched)
+        for (int d = 0; d < n_dev(); d++) {
+            CDS_CUDA(ctx, cudaSetDevice(ctx->devs[d].dev));
+            CDS_CUDA(ctx, cudaStreamSynchronize(ctx->devs[d].stream));
+        }
+    return CDS_OK;
+}
+
 extern "C" cds_status cds_library_create(cds_ctx *ctx, int32_t width, int32_t height, int64_t capacity, cds_library **out)
 {
     if (!ctx || !out) { set_tls_error("cds_library_create: NULL argument"); return CDS_ERR_BAD_ARG; }
@@ -257,6 +290,7 @@ extern "C" cds_status cds_library_create(cds_ctx *ctx, int32_t width, int32_t he
     lib->g.H = height;
     lib->g.pitch = choose_pitch(width);
     lib->g.guard = CDS_GUARD_ROWS;
+    lib->bpitch = occupancy_pitch(width);
     lib->capacity = capacity;
     lib->baked_threshold = 20;
     int D = (int) ctx->devs.size();
@@ -295,6 +329,8 @@ extern "C" void cds_library_destroy(cds_library *lib)
         cudaSetDevice(lib->ctx->devs[d].dev);
         cudaStreamSynchronize(lib->ctx->devs[d].stream);
         cudaFree(lib->shards[d].planes);
+        if (lib->shards[d].occ) cudaFree(lib->shards[d].occ);
+        if (lib->shards[d].valid) cudaFree(lib->shards[d].valid);
     }
     cudaGetLastError();
     delete lib;
@@ -307,6 +343,7 @@ extern "C" cds_status cds_library_clear(cds_library *lib)
     if (!lib) { set_tls_error("cds_library_clear: NULL library"); return CDS_ERR_BAD_ARG; }
     std::lock_guard<std::recursive_mutex> lk(lib->ctx->mu);
     lib->size = 0;
+    for (auto &sh : lib->shards) sh.occ_done = 0;
     return CDS_OK;
 }
 
@@ -574,10 +611,12 @@ cds_status launch_match(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, i
                         int32_t *d_scores)
 {
     DevState &ds = ctx->devs[d];
-    const bool band_ok = band_kernel_supported(ms->params.xy_shift, lib->g) && mc >= band_min_masks();
+    const bool band_ok = band_kernel_supported(ms->params.xy_shift, lib->g) && mc >= band_min_masks() && lib->shards[d].occ &&
+                         lib->shards[d].occ_done >= n_local;
     cudaEventRecord(ds.ev0, ds.stream);
     if (band_ok) {
         int launches = launch_pixelmatch_band(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local,
+                                              lib->shards[d].occ, lib->bpitch,
                                               ms->params.xy_shift, ms->params.mirror != 0, d_scores, ds.stream);
         ctx->stats.kernel_launches += launches;
         ctx->stats.match_kernel_launches += launches;
@@ -623,6 +662,7 @@ extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cd
     reset_stats(ctx);
     CDS_TRY(ms->sync_descs());
     CDS_TRY(lib->bake(ms->params.data_threshold));
+    if (band_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
     const int D = lib->n_dev();
     // mask chunking bounds the per-device score buffer to ~256 MiB
     std::vector<int32_t *> d_scores(D, nullptr);
@@ -706,6 +746,7 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
     if (T == 0) return CDS_OK;
     CDS_TRY(ms->sync_descs());
     CDS_TRY(lib->bake(ms->params.data_threshold));
+    if (band_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
     const int D = lib->n_dev();
     std::vector<int32_t> min_score(M);
     for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);

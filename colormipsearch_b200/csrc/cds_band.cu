@@ -18,6 +18,10 @@
 //     global counter and publishes them to the consumers through shared memory.
 //   * out-of-image pixels of shifted / mirrored variants need no bounds test: they land in the pad columns / guard rows of
 //     the plane (or the pad words placed below each stage), whose code words can never match.
+//   * next to every band the producer also fetches the matching rows of the library's occupancy bitmap (one bit per pixel:
+//     "some shifted position of this pixel is above the data threshold").  A warp skips the 9 (17) evaluations of an
+//     orientation when none of its 32 mask pixels has its bit set -- exact, because a clear bit means every shifted target
+//     pixel is below the threshold.  Colour-depth MIPs are ~95 % black, so most warp iterations are skipped.
 //   * inside a band, consumer warps grab tickets = (mask, chunk of CHUNK records of that mask inside the band) from a shared
 //     counter; a lane owns one mask pixel per iteration: one LDG.128 for the record (prefetched one iteration ahead), one
 //     LDS per variant, two subtract/compare pairs and one predicated add into a packed counter.  A ticket ends with one
@@ -47,6 +51,8 @@ struct BandParams {
     int n_bands;
     int stage_words;                // (R + 2s) * pitch
     int n_groups;
+    const uint32_t *occ;            // occupancy bitmap [n_targets][H][bpitch]
+    int bpitch;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -117,11 +123,12 @@ __device__ __forceinline__ void offset_of(int v, int &dx, int &dy)
 // Shared-memory layout, identical on host (sizing) and device (carving).
 template <int GROUP>
 struct BandSmem {
-    size_t stage_off, acc_off, seg_off, tick_off, rec_off, bar_off, next_off, item_off, total;
-    __host__ __device__ BandSmem(int stage_words, int n_bands, int NV)
+    size_t stage_off, bits_off, acc_off, seg_off, tick_off, rec_off, bar_off, next_off, item_off, total;
+    __host__ __device__ BandSmem(int stage_words, int n_bands, int NV, int bits_words)
     {
         size_t o = 0;
         stage_off = o; o += (size_t) kStages * (stage_words + kPrePad) * 4;
+        bits_off = o;  o += (size_t) kStages * bits_words * 4;
         acc_off = o;   o += (size_t) GROUP * NV * 4;
         seg_off = o;   o += (size_t) GROUP * (n_bands + 1) * 4;
         tick_off = o;  o += ((size_t) n_bands * (GROUP + 1) * 2 + 15) / 16 * 16;
@@ -143,9 +150,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
     constexpr int NCT = NCW * 32;                     // consumer threads
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const BandSmem<GROUP> L(p.stage_words, p.n_bands, NV);
+    const int bits_words = p.rows_per_band * p.bpitch;
+    const BandSmem<GROUP> L(p.stage_words, p.n_bands, NV, bits_words);
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
+    const uint32_t *s_bits = reinterpret_cast<const uint32_t *>(smem_raw + L.bits_off);  // [kStages][R * bpitch]
     int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
     uint32_t *s_seg = reinterpret_cast<uint32_t *>(smem_raw + L.seg_off);               // [GROUP][n_bands + 1] record index at band starts
     uint16_t *s_tick = reinterpret_cast<uint16_t *>(smem_raw + L.tick_off);             // [n_bands][GROUP + 1] ticket prefix sums
@@ -194,8 +203,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
                     const int y1 = min(y0 + R, H);
                     const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
                     const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
-                    mbar_expect_tx(bar, bytes);
+                    const uint32_t bbytes = (uint32_t) ((y1 - y0) * p.bpitch) * 4u;
+                    const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * p.bpitch;
+                    mbar_expect_tx(bar, bytes + bbytes);
                     bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
+                    bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
                 }
                 if (done) break;
                 iseq++;
@@ -264,39 +276,53 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
 #pragma unroll
                 for (int j = 0; j < NREG; j++) cnt[j] = 0;
 
-                uint32_t i = seg0 + lane;
-                uint4 qr = make_uint4(0, 0, 0, 0);
-                if (i < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + i));
-                while (i < seg1) {
+                // every lane runs the same number of iterations (the occupancy votes are warp-wide); lanes past the end of
+                // the chunk carry a record that cannot match and sits on a valid address
+                const uint4 idle = make_uint4((uint32_t) y0 << 16, CDS_EMPTY_LO, CDS_EMPTY_LO, 0u);
+                const uint32_t *bits = s_bits + (size_t) stage * bits_words;
+                uint4 qr = idle;
+                if (seg0 + lane < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + seg0 + lane));
+                for (uint32_t base = seg0; base < seg1; base += 32) {
                     const uint4 cur = qr;
-                    const uint32_t inext = i + 32;
+                    const uint32_t inext = base + 32 + lane;
+                    qr = idle;
                     if (inext < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + inext));   // prefetch behind the compute
                     const int x = (int) (cur.x & 0xFFFFu);
-                    const int row = (int) (cur.x >> 16) - y0 + S;
+                    const int brow = (int) (cur.x >> 16) - y0;
+                    const int xm = W - 1 - x;
+                    const bool live = base + lane < seg1;
+                    const uint32_t wn = bits[brow * p.bpitch + (x >> 5)];
+                    const uint32_t wm = bits[brow * p.bpitch + (xm >> 5)];
+                    const bool occ_n = live && ((wn >> (x & 31)) & 1u);
+                    const bool occ_m = live && ((wm >> (xm & 31)) & 1u);
+                    const bool any_n = __any_sync(0xffffffffu, occ_n);
+                    const bool any_m = MIRROR && __any_sync(0xffffffffu, occ_m);
+                    if (!any_n && !any_m) continue;
                     const uint32_t lo1 = cur.y, lo2 = cur.z;
                     const uint32_t len1 = ((cur.w & 0xFFFFu) << CDS_CODE_SR_SHIFT) | 0xFFu;
                     const uint32_t len2 = ((cur.w >> 16) << CDS_CODE_SR_SHIFT) | 0xFFu;
-                    const uint32_t *pc = band + row * pitch + x;                 // unmirrored centre
-                    const uint32_t *pm = band + row * pitch + (W - 1 - x);       // mirrored centre
-#pragma unroll
-                    for (int v = 0; v < NS; v++) {
-                        int dx, dy;
-                        offset_of<NRINGS>(v, dx, dy);
-                        const uint32_t c = pc[dy * pitch + dx];
-                        if (v & 1) count_hit<0x10000u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
-                        else count_hit<1u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
-                    }
-                    if (MIRROR) {
+                    if (any_n) {
+                        const uint32_t *pc = band + (brow + S) * pitch + x;              // unmirrored centre
 #pragma unroll
                         for (int v = 0; v < NS; v++) {
                             int dx, dy;
                             offset_of<NRINGS>(v, dx, dy);
-                            const uint32_t c = pm[dy * pitch - dx];              // mirror of (x + dx) is (W-1-x) - dx
+                            const uint32_t c = pc[dy * pitch + dx];
+                            if (v & 1) count_hit<0x10000u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
+                            else count_hit<1u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
+                        }
+                    }
+                    if (MIRROR && any_m) {
+                        const uint32_t *pm = band + (brow + S) * pitch + xm;             // mirrored centre
+#pragma unroll
+                        for (int v = 0; v < NS; v++) {
+                            int dx, dy;
+                            offset_of<NRINGS>(v, dx, dy);
+                            const uint32_t c = pm[dy * pitch - dx];                      // mirror of (x + dx) is (W-1-x) - dx
                             if ((NS + v) & 1) count_hit<0x10000u>(cnt[(NS + v) >> 1], c, lo1, len1, lo2, len2);
                             else count_hit<1u>(cnt[(NS + v) >> 1], c, lo1, len1, lo2, len2);
                         }
                     }
-                    i = inext;
                 }
                 // ticket done: warp totals (a ticket has <= kChunk pixels, so the packed halves cannot carry)
                 uint32_t mine0 = 0, mine1 = 0;
@@ -348,6 +374,7 @@ struct BandConfig {
 template <int GROUP>
 BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
 {
+    const int bpitch = occupancy_pitch(g.W);
     BandConfig c{};
     const int S = xy_shift;
     const int NS = xy_shift == 0 ? 1 : (xy_shift == 2 ? 9 : 17);
@@ -358,7 +385,7 @@ BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
         if (n_bands > kMaxBands) break;
         size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
         if (stage_words * 4 >= (1u << 20)) continue;
-        BandSmem<GROUP> L((int) stage_words, n_bands, NV);
+        BandSmem<GROUP> L((int) stage_words, n_bands, NV, R * bpitch);
         if (L.total <= budget) {
             c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = L.total; c.ok = true;
             return c;
@@ -378,7 +405,7 @@ int env_int(const char *name, int dflt)
 
 template <int GROUP, int NCW>
 int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
-               int xy_shift, bool mirror, int32_t *scores, cudaStream_t s, int dev)
+               const uint32_t *occ, int bpitch, int xy_shift, bool mirror, int32_t *scores, cudaStream_t s, int dev)
 {
     BandConfig c = band_config<GROUP>(xy_shift, mirror, g);
     if (!c.ok) return 0;
@@ -387,6 +414,7 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     p.work_counter = g_work_counter[dev];
     p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
     p.n_groups = (n_masks + GROUP - 1) / GROUP;
+    p.occ = occ; p.bpitch = bpitch;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     long long n_items = (long long) p.n_groups * n_targets;
@@ -419,9 +447,10 @@ int band_min_masks()
 }
 
 int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
-                           int xy_shift, bool mirror, int32_t *scores, cudaStream_t s)
+                           const uint32_t *occ, int bpitch, int xy_shift, bool mirror, int32_t *scores, cudaStream_t s)
 {
     if (n_masks == 0 || n_targets == 0) return 0;
+    if (!occ || bpitch != occupancy_pitch(g.W)) return 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 64) return 0;
@@ -434,11 +463,11 @@ int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *p
     static const int warps_env = env_int("CDSGPU_BAND_WARPS", 24);
     const int group = group_env ? group_env : (n_masks > 96 ? 128 : 64);
     if (group == 128) {
-        if (warps_env == 24) return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
-        return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
+        if (warps_env == 24) return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, xy_shift, mirror, scores, s, dev);
+        return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, xy_shift, mirror, scores, s, dev);
     }
-    if (warps_env == 24) return launch_cfg<64, 24>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
-    return launch_cfg<64, 16>(masks, n_masks, planes, g, n_targets, xy_shift, mirror, scores, s, dev);
+    if (warps_env == 24) return launch_cfg<64, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, xy_shift, mirror, scores, s, dev);
+    return launch_cfg<64, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, xy_shift, mirror, scores, s, dev);
 }
 
 }  // namespace cds

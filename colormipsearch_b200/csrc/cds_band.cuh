@@ -12,8 +12,9 @@ bool band_kernel_supported(int xy_shift, const PlaneGeom &g);
 int band_min_masks();
 // Launches the band kernel for masks [0, n_masks) x targets [0, n_targets) of one device; returns the number of
 // kernel launches issued (0 on configuration error, cudaGetLastError has it).
+// `occ` is the library's occupancy bitmap for this xy_shift (cds_kernels.cuh launch_occupancy), row pitch `bpitch` words.
 int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
-                           int xy_shift, bool mirror, int32_t *scores, cudaStream_t s);
+                           const uint32_t *occ, int bpitch, int xy_shift, bool mirror, int32_t *scores, cudaStream_t s);
 
 }  // namespace cds
 #endif

@@ -129,6 +129,72 @@ void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_ta
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Occupancy bitmap (see cds_kernels.cuh).  Pass 1: one bit per pixel "inside the image and above the threshold";
+// pass 2: OR of the bits at the shift offsets, done 32 pixels at a time with word shifts.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restrict__ planes, PlaneGeom g, int64_t t0, int bpitch,
+                                                         uint32_t *__restrict__ valid)
+{
+    const int y = blockIdx.x;
+    const int64_t t = t0 + blockIdx.y;
+    const uint32_t *row = planes + g.row_offset(t, y);
+    uint32_t *out = valid + ((size_t) t * g.H + y) * bpitch;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < bpitch; k += (int) (blockDim.x >> 5)) {
+        const int x = k * 32 + lane;
+        bool v = false;
+        if (x < g.W) v = (row[x] & (CDS_CODE_BELOW_BIT | CDS_CODE_PAD_BIT)) == 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) out[k] = bal;
+    }
+}
+
+__device__ __forceinline__ uint32_t hspread(const uint32_t *__restrict__ vrow, int k, int bpitch, int s)
+{
+    // bit x of the result = valid(x - s) | valid(x) | valid(x + s)
+    const uint32_t c = vrow[k];
+    const uint32_t l = k > 0 ? vrow[k - 1] : 0u;
+    const uint32_t r = k + 1 < bpitch ? vrow[k + 1] : 0u;
+    return c | (c << s) | (l >> (32 - s)) | (c >> s) | (r << (32 - s));
+}
+
+__global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restrict__ valid, int H, int bpitch, int64_t t0, int64_t n,
+                                                        int rings, uint32_t *__restrict__ occ)
+{
+    const size_t total = (size_t) n * H * bpitch;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const int k = (int) (i % bpitch);
+        const int y = (int) ((i / bpitch) % H);
+        const int64_t t = t0 + (int64_t) (i / ((size_t) bpitch * H));
+        const uint32_t *vplane = valid + (size_t) t * H * bpitch;
+        uint32_t o;
+        if (rings == 0) {
+            o = vplane[(size_t) y * bpitch + k];
+        } else {
+            o = 0;
+            for (int dy = -2; dy <= 2; dy += 2)
+                if (y + dy >= 0 && y + dy < H) o |= hspread(vplane + (size_t) (y + dy) * bpitch, k, bpitch, 2);
+            if (rings >= 2)
+                for (int dy = -4; dy <= 4; dy += 4)
+                    if (y + dy >= 0 && y + dy < H) o |= hspread(vplane + (size_t) (y + dy) * bpitch, k, bpitch, 4);
+        }
+        occ[((size_t) t * H + y) * bpitch + k] = o;
+    }
+}
+
+void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int bpitch,
+                      uint32_t *valid_scratch, uint32_t *occ, cudaStream_t s)
+{
+    if (n == 0) return;
+    for (int64_t i0 = 0; i0 < n; i0 += 32768) {
+        int64_t cnt = n - i0 < 32768 ? n - i0 : 32768;
+        dim3 grid(g.H, (unsigned) cnt);
+        valid_bits_kernel<<<grid, 256, 0, s>>>(planes, g, t0 + i0, bpitch, valid_scratch);
+    }
+    occupancy_kernel<<<148 * 8, 256, 0, s>>>(valid_scratch, g.H, bpitch, t0, n, rings, occ);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Mask preparation: ordered compaction of the pixels above the mask threshold and outside the label regions.
 // Pass 1 counts per (mask, row); pass 2 turns counts into row starts; pass 3 writes the records.  One warp per row.
 // ------------------------------------------------------------------------------------------------------------------

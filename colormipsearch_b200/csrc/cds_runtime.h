@@ -58,7 +58,15 @@ struct cds_library {
     int64_t capacity = 0;
     int64_t size = 0;
     int baked_threshold = 0;
-    struct Shard { uint32_t *planes = nullptr; int64_t cap_local = 0; };
+    struct Shard {
+        uint32_t *planes = nullptr;
+        int64_t cap_local = 0;
+        uint32_t *occ = nullptr;        // occupancy bitmap [cap_local][H][bpitch] (cds_kernels.cuh), built on demand
+        uint32_t *valid = nullptr;      // its scratch
+        int64_t occ_done = 0;           // local targets covered by `occ`
+    };
+    int bpitch = 0;
+    int occ_threshold = 0, occ_rings = -1;   // parameters `occ` was built for
     std::vector<Shard> shards;
 
     int n_dev() const { return (int) shards.size(); }
@@ -74,6 +82,7 @@ struct cds_library {
     }
     int64_t local_size(int dev) const;   // number of targets currently on `dev`
     cds_status bake(int threshold);      // make the below-threshold flags match `threshold`
+    cds_status ensure_occupancy(int rings);   // occupancy bitmap for the baked threshold and this shift set, all devices
 };
 
 struct cds_maskset {
