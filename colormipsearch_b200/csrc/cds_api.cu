@@ -449,6 +449,8 @@ extern "C" cds_status cds_maskset_create(cds_ctx *ctx, int32_t width, int32_t he
         ms->rects.x1[i] = params->rects[i].x1; ms->rects.y1[i] = params->rects[i].y1;
     }
     ms->d_descs.assign(ctx->devs.size(), nullptr);
+    ms->d_groups.assign(ctx->devs.size(), nullptr);
+    ms->d_palettes.assign(ctx->devs.size(), nullptr);
     // build (or fetch) the interval table now so that a bad tolerance fails here
     for (DevState &ds : ctx->devs) {
         const cds_class_interval *tab;
@@ -470,8 +472,12 @@ extern "C" void cds_maskset_destroy(cds_maskset *ms)
         for (auto &b : ms->batches) {
             if (d < b.records.size() && b.records[d]) cudaFree(b.records[d]);
             if (d < b.rowstart.size() && b.rowstart[d]) cudaFree(b.rowstart[d]);
+            if (d < b.classes.size() && b.classes[d]) cudaFree(b.classes[d]);
+            if (d < b.crec.size() && b.crec[d]) cudaFree(b.crec[d]);
         }
         if (ms->d_descs[d]) cudaFree(ms->d_descs[d]);
+        if (ms->d_groups[d]) cudaFree(ms->d_groups[d]);
+        if (ms->d_palettes[d]) cudaFree(ms->d_palettes[d]);
     }
     cudaGetLastError();
     delete ms;
@@ -508,6 +514,8 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
         b.n = cnt;
         b.records.assign(D, nullptr);
         b.rowstart.assign(D, nullptr);
+        b.classes.assign(D, nullptr);
+        b.crec.assign(D, nullptr);
         const size_t rs_words = (size_t) cnt * (H + 1);
         int32_t *d_sizes = nullptr;
         uint64_t *d_off = nullptr;
@@ -522,6 +530,8 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
                 cudaSetDevice(ctx->devs[d].dev);
                 if (b.records[d]) cudaFree(b.records[d]);
                 if (b.rowstart[d]) cudaFree(b.rowstart[d]);
+                if (b.classes[d]) cudaFree(b.classes[d]);
+                if (b.crec[d]) cudaFree(b.crec[d]);
             }
             return s;
         };
@@ -541,9 +551,11 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
         for (int i = 0; i < cnt; i++) { b.rec_offset[i] = total; total += (uint64_t) sizes[i]; }
         b.total_records = total;
         if ((st = ctx->check(cudaMalloc(&b.records[0], std::max<uint64_t>(total, 1) * sizeof(cds_mask_record)), "cudaMalloc(mask records)")) != CDS_OK) return bail(st);
+        if ((st = ctx->check(cudaMalloc(&b.classes[0], std::max<uint64_t>(total, 1) * sizeof(uint32_t)), "cudaMalloc(mask classes)")) != CDS_OK) return bail(st);
+        if ((st = ctx->check(cudaMalloc(&b.crec[0], std::max<uint64_t>(total, 1) * sizeof(uint32_t)), "cudaMalloc(compact records)")) != CDS_OK) return bail(st);
         if ((st = ctx->check(cudaMemcpyAsync(d_off, b.rec_offset.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, d0.stream), "offsets H2D")) != CDS_OK) return bail(st);
         launch_mask_write_records((const uint8_t *) d0.staging, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, b.rowstart[0], d_off,
-                                  d0.d_rank_tab, class_tab, b.records[0], d0.stream);
+                                  d0.d_rank_tab, class_tab, b.records[0], b.classes[0], d0.stream);
         ctx->stats.kernel_launches++;
         if ((st = ctx->check(cudaGetLastError(), "mask_write_records_kernel")) != CDS_OK) return bail(st);
         if ((st = ctx->check(cudaStreamSynchronize(d0.stream), "mask write")) != CDS_OK) return bail(st);
@@ -553,6 +565,9 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
             if ((st = ctx->check(cudaSetDevice(dd.dev), "cudaSetDevice")) != CDS_OK) return bail(st);
             if ((st = ctx->check(cudaMalloc(&b.rowstart[d], rs_words * sizeof(uint32_t)), "cudaMalloc(rowstart)")) != CDS_OK) return bail(st);
             if ((st = ctx->check(cudaMalloc(&b.records[d], std::max<uint64_t>(total, 1) * sizeof(cds_mask_record)), "cudaMalloc(mask records)")) != CDS_OK) return bail(st);
+            if ((st = ctx->check(cudaMalloc(&b.classes[d], std::max<uint64_t>(total, 1) * sizeof(uint32_t)), "cudaMalloc(mask classes)")) != CDS_OK) return bail(st);
+            if ((st = ctx->check(cudaMalloc(&b.crec[d], std::max<uint64_t>(total, 1) * sizeof(uint32_t)), "cudaMalloc(compact records)")) != CDS_OK) return bail(st);
+            if (total && (st = ctx->check(cudaMemcpyPeerAsync(b.classes[d], dd.dev, b.classes[0], d0.dev, total * sizeof(uint32_t), dd.stream), "peer copy")) != CDS_OK) return bail(st);
             if ((st = ctx->check(cudaMemcpyPeerAsync(b.rowstart[d], dd.dev, b.rowstart[0], d0.dev, rs_words * sizeof(uint32_t), dd.stream), "peer copy")) != CDS_OK) return bail(st);
             if (total && (st = ctx->check(cudaMemcpyPeerAsync(b.records[d], dd.dev, b.records[0], d0.dev, total * sizeof(cds_mask_record), dd.stream), "peer copy")) != CDS_OK) return bail(st);
         }
@@ -577,21 +592,80 @@ cds_status cds_maskset::sync_descs()
     if (!descs_dirty) return CDS_OK;
     const int D = (int) ctx->devs.size();
     const int M = (int) sizes.size();
+    const int n_groups = (M + CDS_PALETTE_GROUP - 1) / CDS_PALETTE_GROUP;
+    std::shared_ptr<const ClassTable> ctab = class_table(params.z_tolerance);
+    const bool compact_ok = ctab && ctab->max_len <= CDS_PAL_MAX_LEN && W <= 2048 && H <= 1024 && M > 0;
+    n_compact_groups = 0;
     for (int d = 0; d < D; d++) {
         DevState &ds = ctx->devs[d];
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
         std::vector<MaskDesc> h(std::max(M, 1));
+        std::vector<MaskClassRef> refs(std::max(M, 1));
         int mi = 0;
         for (const Batch &b : batches)
             for (int i = 0; i < b.n; i++, mi++) {
                 h[mi].records = b.records[d] + b.rec_offset[i];
                 h[mi].rowstart = b.rowstart[d] + (size_t) i * (H + 1);
+                h[mi].crec = nullptr;
                 h[mi].P = sizes[mi];
                 h[mi].pad = 0;
+                refs[mi].classes = b.classes[d] + b.rec_offset[i];
+                refs[mi].records = h[mi].records;
+                refs[mi].crec = b.crec[d] + b.rec_offset[i];
+                refs[mi].P = sizes[mi];
+                refs[mi].pad = 0;
             }
-        if (d_descs[d]) { CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream)); cudaFree(d_descs[d]); d_descs[d] = nullptr; }
+        if (d_descs[d]) { cudaFree(d_descs[d]); d_descs[d] = nullptr; }
+        if (d_groups[d]) { cudaFree(d_groups[d]); d_groups[d] = nullptr; }
+        if (d_palettes[d]) { cudaFree(d_palettes[d]); d_palettes[d] = nullptr; }
+        std::vector<PaletteGroup> groups(std::max(n_groups, 1));
+        for (auto &g : groups) { g.palette = nullptr; g.n_pal = 0; g.pad = 0; }
+        if (compact_ok) {
+            // palettes of the compact records: mark classes per group, number them, pack intervals, rewrite records
+            const size_t slots = (size_t) n_groups * (CDS_NUM_CLASSES + 1);
+            MaskClassRef *d_refs = nullptr;
+            uint32_t *d_flags = nullptr, *d_pidx = nullptr;
+            int32_t *d_npal = nullptr;
+            const cds_class_interval *class_tab = nullptr;
+            cds_status st = ctx->class_table_on(ds, params.z_tolerance, &class_tab);
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_refs, refs.size() * sizeof(MaskClassRef)), "cudaMalloc(class refs)");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_flags, slots * sizeof(uint32_t)), "cudaMalloc(palette flags)");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_pidx, slots * sizeof(uint32_t)), "cudaMalloc(palette index)");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_npal, n_groups * sizeof(int32_t)), "cudaMalloc(palette sizes)");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_palettes[d], (size_t) n_groups * CDS_PALETTE_SIZE * sizeof(uint2)), "cudaMalloc(palettes)");
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_refs, refs.data(), refs.size() * sizeof(MaskClassRef), cudaMemcpyHostToDevice, ds.stream), "class refs H2D");
+            if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_flags, 0, slots * sizeof(uint32_t), ds.stream), "memset(palette flags)");
+            std::vector<int32_t> n_pal(n_groups, 0);
+            if (st == CDS_OK) {
+                launch_palette_mark(d_refs, M, d_flags, ds.stream);
+                launch_palette_scan(d_flags, n_groups, d_pidx, d_npal, ds.stream);
+                launch_palette_fill(d_flags, d_pidx, n_groups, class_tab, d_palettes[d], ds.stream);
+                launch_palette_records(d_refs, M, d_pidx, d_npal, ds.stream);
+                ctx->stats.kernel_launches += 4;
+                st = ctx->check(cudaGetLastError(), "palette kernels");
+            }
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(n_pal.data(), d_npal, n_groups * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "palette sizes D2H");
+            if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "palette build");
+            if (d_refs) cudaFree(d_refs);
+            if (d_flags) cudaFree(d_flags);
+            if (d_pidx) cudaFree(d_pidx);
+            if (d_npal) cudaFree(d_npal);
+            if (st != CDS_OK) return st;
+            int compact = 0;
+            for (int g = 0; g < n_groups; g++) {
+                if (n_pal[g] >= CDS_PALETTE_SIZE) continue;   // the last palette index is reserved for idle lanes
+                groups[g].palette = d_palettes[d] + (size_t) g * CDS_PALETTE_SIZE;
+                groups[g].n_pal = n_pal[g];
+                compact++;
+                for (int m = g * CDS_PALETTE_GROUP; m < std::min(M, (g + 1) * CDS_PALETTE_GROUP); m++) h[m].crec = refs[m].crec;
+            }
+            n_compact_groups = compact;
+        }
         CDS_CUDA(ctx, cudaMalloc(&d_descs[d], h.size() * sizeof(MaskDesc)));
+        CDS_CUDA(ctx, cudaMalloc(&d_groups[d], groups.size() * sizeof(PaletteGroup)));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
+        CDS_CUDA(ctx, cudaMemcpyAsync(d_groups[d], groups.data(), groups.size() * sizeof(PaletteGroup), cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
     }
     descs_dirty = false;
@@ -612,11 +686,12 @@ cds_status launch_match(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, i
 {
     DevState &ds = ctx->devs[d];
     const bool band_ok = band_kernel_supported(ms->params.xy_shift, lib->g) && mc >= band_min_masks() && lib->shards[d].occ &&
+                         (m0 % CDS_PALETTE_GROUP) == 0 &&
                          lib->shards[d].occ_done >= n_local;
     cudaEventRecord(ds.ev0, ds.stream);
     if (band_ok) {
         int launches = launch_pixelmatch_band(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local,
-                                              lib->shards[d].occ, lib->bpitch,
+                                              lib->shards[d].occ, lib->bpitch, ms->d_groups[d] + m0 / CDS_PALETTE_GROUP,
                                               ms->params.xy_shift, ms->params.mirror != 0, d_scores, ds.stream);
         ctx->stats.kernel_launches += launches;
         ctx->stats.match_kernel_launches += launches;
@@ -670,6 +745,7 @@ extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cd
     int64_t max_local = 0;
     for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
     int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 64 << 20) / std::max<int64_t>(max_local, 1)));
+    if (mchunk < M && mchunk > CDS_PALETTE_GROUP) mchunk -= mchunk % CDS_PALETTE_GROUP;   // keep chunks aligned to palette groups
     auto free_all = [&]() {};
     for (int d = 0; d < D && st == CDS_OK; d++) {
         st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
@@ -753,7 +829,8 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
 
     int64_t max_local = 0;
     for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
-    const int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 512 << 20) / std::max<int64_t>(max_local, 1)));
+    int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 512 << 20) / std::max<int64_t>(max_local, 1)));
+    if (mchunk < M && mchunk > CDS_PALETTE_GROUP) mchunk -= mchunk % CDS_PALETTE_GROUP;   // keep chunks aligned to palette groups
     std::vector<int32_t *> d_scores(D, nullptr);
     std::vector<int32_t *> d_min(D, nullptr);
     std::vector<uint64_t *> d_keys(D, nullptr);

@@ -53,6 +53,7 @@ struct BandParams {
     int n_groups;
     const uint32_t *occ;            // occupancy bitmap [n_targets][H][bpitch]
     int bpitch;
+    const PaletteGroup *groups;     // palette group of masks[0] onwards (masks[0] is CDS_PALETTE_GROUP aligned in the mask set)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -120,15 +121,47 @@ __device__ __forceinline__ void offset_of(int v, int &dx, int &dy)
     dy = (k % 3 - 1) * 4;
 }
 
+// The evaluations of one mask pixel against the band in shared memory: NS shifted reads around the pixel (if any lane of
+// the warp can match there) and NS around its mirror image.
+template <int NRINGS, bool MIRROR, int NREG>
+__device__ __forceinline__ void eval_pixel(const uint32_t *__restrict__ rowbase, int pitch, int x, int xm, bool any_n, bool any_m,
+                                           uint32_t lo1, uint32_t len1, uint32_t lo2, uint32_t len2, uint32_t (&cnt)[NREG])
+{
+    constexpr int NS = Offsets<NRINGS>::N;
+    if (any_n) {
+        const uint32_t *pc = rowbase + x;                                    // unmirrored centre
+#pragma unroll
+        for (int v = 0; v < NS; v++) {
+            int dx, dy;
+            offset_of<NRINGS>(v, dx, dy);
+            const uint32_t c = pc[dy * pitch + dx];
+            if (v & 1) count_hit<0x10000u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
+            else count_hit<1u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
+        }
+    }
+    if (MIRROR && any_m) {
+        const uint32_t *pm = rowbase + xm;                                   // mirrored centre
+#pragma unroll
+        for (int v = 0; v < NS; v++) {
+            int dx, dy;
+            offset_of<NRINGS>(v, dx, dy);
+            const uint32_t c = pm[dy * pitch - dx];                          // mirror of (x + dx) is (W-1-x) - dx
+            if ((NS + v) & 1) count_hit<0x10000u>(cnt[(NS + v) >> 1], c, lo1, len1, lo2, len2);
+            else count_hit<1u>(cnt[(NS + v) >> 1], c, lo1, len1, lo2, len2);
+        }
+    }
+}
+
 // Shared-memory layout, identical on host (sizing) and device (carving).
 template <int GROUP>
 struct BandSmem {
-    size_t stage_off, bits_off, acc_off, seg_off, tick_off, rec_off, bar_off, next_off, item_off, total;
+    size_t stage_off, bits_off, pal_off, acc_off, seg_off, tick_off, rec_off, bar_off, next_off, item_off, total;
     __host__ __device__ BandSmem(int stage_words, int n_bands, int NV, int bits_words)
     {
         size_t o = 0;
         stage_off = o; o += (size_t) kStages * (stage_words + kPrePad) * 4;
         bits_off = o;  o += (size_t) kStages * bits_words * 4;
+        pal_off = o;   o += (size_t) CDS_PALETTE_SIZE * 8;
         acc_off = o;   o += (size_t) GROUP * NV * 4;
         seg_off = o;   o += (size_t) GROUP * (n_bands + 1) * 4;
         tick_off = o;  o += ((size_t) n_bands * (GROUP + 1) * 2 + 15) / 16 * 16;
@@ -155,10 +188,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
     const uint32_t *s_bits = reinterpret_cast<const uint32_t *>(smem_raw + L.bits_off);  // [kStages][R * bpitch]
+    uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
     int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
     uint32_t *s_seg = reinterpret_cast<uint32_t *>(smem_raw + L.seg_off);               // [GROUP][n_bands + 1] record index at band starts
     uint16_t *s_tick = reinterpret_cast<uint16_t *>(smem_raw + L.tick_off);             // [n_bands][GROUP + 1] ticket prefix sums
-    const cds_mask_record **s_rec = reinterpret_cast<const cds_mask_record **>(smem_raw + L.rec_off);
+    const void **s_rec = reinterpret_cast<const void **>(smem_raw + L.rec_off);         // record arrays (compact or 16-byte)
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
     unsigned long long *s_empty = s_full + kStages;
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
@@ -219,6 +253,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
     // ---------------------------------------------------------------------- consumers
     uint32_t q = 0, iseq = 0;
     int cur_gi = -1;
+    bool compact = false;
     for (;;) {
         mbar_wait(smem_u32(s_full + (q & 1)), (q >> 1) & 1);
         const long long w = *reinterpret_cast<volatile long long *>(s_item + (iseq & 1));
@@ -231,7 +266,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
         if (gi != cur_gi) {
             // per-group tables: record base pointers, band boundaries and per-band ticket prefix sums.  Every consumer passed
             // the barrier that ends the previous item, so nobody still reads the old tables.
-            for (int i = tid; i < mb; i += NCT) s_rec[i] = p.masks[m0 + i].records;
+            const PaletteGroup pg = p.groups[m0 / CDS_PALETTE_GROUP];
+            compact = pg.palette != nullptr;
+            for (int i = tid; i < mb; i += NCT)
+                s_rec[i] = compact ? (const void *) p.masks[m0 + i].crec : (const void *) p.masks[m0 + i].records;
+            if (compact) {
+                for (int i = tid; i < pg.n_pal; i += NCT) s_pal[i] = pg.palette[i];
+                if (tid == 0) s_pal[CDS_PALETTE_SIZE - 1] = make_uint2(CDS_PAL_EMPTY_LO, CDS_PAL_EMPTY_LO);   // idle lanes point here
+            }
             for (int i = tid; i < mb * (NB + 1); i += NCT) {
                 const int mi = i / (NB + 1), b = i % (NB + 1);
                 s_seg[i] = __ldg(p.masks[m0 + mi].rowstart + min(b * R, H));
@@ -271,57 +313,66 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
                 const uint32_t seg_end = s_seg[mi * (NB + 1) + b + 1];
                 const uint32_t seg0 = s_seg[mi * (NB + 1) + b] + (uint32_t) (tk - tick[mi]) * kChunk;
                 const uint32_t seg1 = min(seg0 + kChunk, seg_end);
-                const cds_mask_record *rec = s_rec[mi];
                 uint32_t cnt[NREG];
 #pragma unroll
                 for (int j = 0; j < NREG; j++) cnt[j] = 0;
+                const uint32_t *bits = s_bits + (size_t) stage * bits_words;
 
                 // every lane runs the same number of iterations (the occupancy votes are warp-wide); lanes past the end of
                 // the chunk carry a record that cannot match and sits on a valid address
-                const uint4 idle = make_uint4((uint32_t) y0 << 16, CDS_EMPTY_LO, CDS_EMPTY_LO, 0u);
-                const uint32_t *bits = s_bits + (size_t) stage * bits_words;
-                uint4 qr = idle;
-                if (seg0 + lane < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + seg0 + lane));
-                for (uint32_t base = seg0; base < seg1; base += 32) {
-                    const uint4 cur = qr;
-                    const uint32_t inext = base + 32 + lane;
-                    qr = idle;
-                    if (inext < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + inext));   // prefetch behind the compute
-                    const int x = (int) (cur.x & 0xFFFFu);
-                    const int brow = (int) (cur.x >> 16) - y0;
-                    const int xm = W - 1 - x;
-                    const bool live = base + lane < seg1;
-                    const uint32_t wn = bits[brow * p.bpitch + (x >> 5)];
-                    const uint32_t wm = bits[brow * p.bpitch + (xm >> 5)];
-                    const bool occ_n = live && ((wn >> (x & 31)) & 1u);
-                    const bool occ_m = live && ((wm >> (xm & 31)) & 1u);
-                    const bool any_n = __any_sync(0xffffffffu, occ_n);
-                    const bool any_m = MIRROR && __any_sync(0xffffffffu, occ_m);
-                    if (!any_n && !any_m) continue;
-                    const uint32_t lo1 = cur.y, lo2 = cur.z;
-                    const uint32_t len1 = ((cur.w & 0xFFFFu) << CDS_CODE_SR_SHIFT) | 0xFFu;
-                    const uint32_t len2 = ((cur.w >> 16) << CDS_CODE_SR_SHIFT) | 0xFFu;
-                    if (any_n) {
-                        const uint32_t *pc = band + (brow + S) * pitch + x;              // unmirrored centre
-#pragma unroll
-                        for (int v = 0; v < NS; v++) {
-                            int dx, dy;
-                            offset_of<NRINGS>(v, dx, dy);
-                            const uint32_t c = pc[dy * pitch + dx];
-                            if (v & 1) count_hit<0x10000u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
-                            else count_hit<1u>(cnt[v >> 1], c, lo1, len1, lo2, len2);
-                        }
+                if (compact) {
+                    const uint32_t *cr = static_cast<const uint32_t *>(s_rec[mi]);
+                    const uint32_t idle = ((uint32_t) y0 << 11) | ((uint32_t) (CDS_PALETTE_SIZE - 1) << 21);
+                    // records are prefetched four iterations ahead
+                    uint32_t r0 = idle, r1 = idle, r2 = idle, r3 = idle;
+                    if (seg0 + lane < seg1) r0 = __ldg(cr + seg0 + lane);
+                    if (seg0 + 32 + lane < seg1) r1 = __ldg(cr + seg0 + 32 + lane);
+                    if (seg0 + 64 + lane < seg1) r2 = __ldg(cr + seg0 + 64 + lane);
+                    if (seg0 + 96 + lane < seg1) r3 = __ldg(cr + seg0 + 96 + lane);
+                    for (uint32_t base = seg0; base < seg1; base += 32) {
+                        const uint32_t cur = r0;
+                        r0 = r1; r1 = r2; r2 = r3;
+                        const uint32_t inext = base + 128 + lane;
+                        r3 = idle;
+                        if (inext < seg1) r3 = __ldg(cr + inext);
+                        const int x = (int) (cur & 0x7FFu);
+                        const int brow = (int) ((cur >> 11) & 0x3FFu) - y0;
+                        const int xm = W - 1 - x;
+                        const bool live = base + lane < seg1;
+                        const uint32_t wn = bits[brow * p.bpitch + (x >> 5)];
+                        const uint32_t wm = bits[brow * p.bpitch + (xm >> 5)];
+                        const bool any_n = __any_sync(0xffffffffu, live && ((wn >> (x & 31)) & 1u));
+                        const bool any_m = MIRROR && __any_sync(0xffffffffu, live && ((wm >> (xm & 31)) & 1u));
+                        if (!any_n && !any_m) continue;
+                        const uint2 pe = s_pal[cur >> 21];
+                        const uint32_t lo1 = (pe.x & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
+                        const uint32_t len1 = ((pe.x >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
+                        const uint32_t lo2 = (pe.y & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
+                        const uint32_t len2 = ((pe.y >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
+                        eval_pixel<NRINGS, MIRROR, NREG>(band + (brow + S) * pitch, pitch, x, xm, any_n, any_m, lo1, len1, lo2, len2, cnt);
                     }
-                    if (MIRROR && any_m) {
-                        const uint32_t *pm = band + (brow + S) * pitch + xm;             // mirrored centre
-#pragma unroll
-                        for (int v = 0; v < NS; v++) {
-                            int dx, dy;
-                            offset_of<NRINGS>(v, dx, dy);
-                            const uint32_t c = pm[dy * pitch - dx];                      // mirror of (x + dx) is (W-1-x) - dx
-                            if ((NS + v) & 1) count_hit<0x10000u>(cnt[(NS + v) >> 1], c, lo1, len1, lo2, len2);
-                            else count_hit<1u>(cnt[(NS + v) >> 1], c, lo1, len1, lo2, len2);
-                        }
+                } else {
+                    const cds_mask_record *rec = static_cast<const cds_mask_record *>(s_rec[mi]);
+                    const uint4 idle = make_uint4((uint32_t) y0 << 16, CDS_EMPTY_LO, CDS_EMPTY_LO, 0u);
+                    uint4 qr = idle;
+                    if (seg0 + lane < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + seg0 + lane));
+                    for (uint32_t base = seg0; base < seg1; base += 32) {
+                        const uint4 cur = qr;
+                        const uint32_t inext = base + 32 + lane;
+                        qr = idle;
+                        if (inext < seg1) qr = __ldg(reinterpret_cast<const uint4 *>(rec + inext));   // prefetch behind the compute
+                        const int x = (int) (cur.x & 0xFFFFu);
+                        const int brow = (int) (cur.x >> 16) - y0;
+                        const int xm = W - 1 - x;
+                        const bool live = base + lane < seg1;
+                        const uint32_t wn = bits[brow * p.bpitch + (x >> 5)];
+                        const uint32_t wm = bits[brow * p.bpitch + (xm >> 5)];
+                        const bool any_n = __any_sync(0xffffffffu, live && ((wn >> (x & 31)) & 1u));
+                        const bool any_m = MIRROR && __any_sync(0xffffffffu, live && ((wm >> (xm & 31)) & 1u));
+                        if (!any_n && !any_m) continue;
+                        const uint32_t len1 = ((cur.w & 0xFFFFu) << CDS_CODE_SR_SHIFT) | 0xFFu;
+                        const uint32_t len2 = ((cur.w >> 16) << CDS_CODE_SR_SHIFT) | 0xFFu;
+                        eval_pixel<NRINGS, MIRROR, NREG>(band + (brow + S) * pitch, pitch, x, xm, any_n, any_m, cur.y, len1, cur.z, len2, cnt);
                     }
                 }
                 // ticket done: warp totals (a ticket has <= kChunk pixels, so the packed halves cannot carry)
@@ -405,7 +456,8 @@ int env_int(const char *name, int dflt)
 
 template <int GROUP, int NCW>
 int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
-               const uint32_t *occ, int bpitch, int xy_shift, bool mirror, int32_t *scores, cudaStream_t s, int dev)
+               const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror, int32_t *scores,
+               cudaStream_t s, int dev)
 {
     BandConfig c = band_config<GROUP>(xy_shift, mirror, g);
     if (!c.ok) return 0;
@@ -414,7 +466,7 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     p.work_counter = g_work_counter[dev];
     p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
     p.n_groups = (n_masks + GROUP - 1) / GROUP;
-    p.occ = occ; p.bpitch = bpitch;
+    p.occ = occ; p.bpitch = bpitch; p.groups = groups;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     long long n_items = (long long) p.n_groups * n_targets;
@@ -447,10 +499,11 @@ int band_min_masks()
 }
 
 int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
-                           const uint32_t *occ, int bpitch, int xy_shift, bool mirror, int32_t *scores, cudaStream_t s)
+                           const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror, int32_t *scores,
+                           cudaStream_t s)
 {
     if (n_masks == 0 || n_targets == 0) return 0;
-    if (!occ || bpitch != occupancy_pitch(g.W)) return 0;
+    if (!occ || !groups || bpitch != occupancy_pitch(g.W)) return 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 64) return 0;
@@ -463,11 +516,11 @@ int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *p
     static const int warps_env = env_int("CDSGPU_BAND_WARPS", 24);
     const int group = group_env ? group_env : (n_masks > 96 ? 128 : 64);
     if (group == 128) {
-        if (warps_env == 24) return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, xy_shift, mirror, scores, s, dev);
-        return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, xy_shift, mirror, scores, s, dev);
+        if (warps_env == 24) return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, s, dev);
+        return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, s, dev);
     }
-    if (warps_env == 24) return launch_cfg<64, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, xy_shift, mirror, scores, s, dev);
-    return launch_cfg<64, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, xy_shift, mirror, scores, s, dev);
+    if (warps_env == 24) return launch_cfg<64, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, s, dev);
+    return launch_cfg<64, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, s, dev);
 }
 
 }  // namespace cds

@@ -13,8 +13,11 @@ int band_min_masks();
 // Launches the band kernel for masks [0, n_masks) x targets [0, n_targets) of one device; returns the number of
 // kernel launches issued (0 on configuration error, cudaGetLastError has it).
 // `occ` is the library's occupancy bitmap for this xy_shift (cds_kernels.cuh launch_occupancy), row pitch `bpitch` words.
+// masks[0] must be the first mask of a palette group (index multiple of CDS_PALETTE_GROUP in its mask set) and `groups`
+// that group's descriptor.
 int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
-                           const uint32_t *occ, int bpitch, int xy_shift, bool mirror, int32_t *scores, cudaStream_t s);
+                           const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror,
+                           int32_t *scores, cudaStream_t s);
 
 }  // namespace cds
 #endif

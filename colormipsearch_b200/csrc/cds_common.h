@@ -54,6 +54,20 @@ struct cds_class_interval {
 
 #define CDS_IV_EMPTY 0xFFFFFFFFu
 
+// COMPACT MASK RECORDS.  The two intervals of a mask pixel depend only on its colour class (sector, rank), and the masks
+// of a group share few classes (colour-depth MIPs are rendered with a 256-entry LUT), so the band kernel keeps one
+// PALETTE per group of CDS_PALETTE_GROUP masks in shared memory and streams 4-byte records:
+//     record  = x | y << 11 | palette index << 21              (W <= 2048, H <= 1024, <= CDS_PALETTE_SIZE classes per group)
+//     palette = { lo1 | len1 << 18 , lo2 | len2 << 18 }         SR units, 18 + 14 bits; empty interval: lo = CDS_PAL_EMPTY_LO
+// Groups that do not fit (more classes, larger images, tolerances so wide that an interval spans >= 16384 ranks) use the
+// 16-byte records above.
+#define CDS_PALETTE_GROUP 128
+#define CDS_PALETTE_SIZE 2048
+#define CDS_PAL_LO_BITS 18
+#define CDS_PAL_EMPTY_LO 0x3FFFFu     // an SR no code word has (> CDS_SR_NONE)
+#define CDS_PAL_MAX_LEN 16383u
+#define CDS_CLASS_NONE_INDEX CDS_NUM_CLASSES   // class index of "no sector" pixels in the per-record class array
+
 #define CDS_MAX_VARIANTS 34          // band kernel: 17 offsets x 2 orientations (xyShift 4)
 #define CDS_MAX_SHIFT_OFFSETS 40     // generic kernel: 1 + 9*4 entries for xyShift 8
 

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128) mask_write_records_kernel(const uint8_t *
                                                                  const uint32_t *__restrict__ rowstart, const uint64_t *__restrict__ rec_offset,
                                                                  const uint16_t *__restrict__ rank_tab,
                                                                  const cds_class_interval *__restrict__ class_tab,
-                                                                 cds_mask_record *__restrict__ records)
+                                                                 cds_mask_record *__restrict__ records, uint32_t *__restrict__ classes)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * 4 + warp;
@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(128) mask_write_records_kernel(const uint8_t *
     if (y >= H) return;
     const uint8_t *row = rgb + ((size_t) m * H + y) * W * 3;
     cds_mask_record *out = records + rec_offset[m] + rowstart[(size_t) m * (H + 1) + y];
+    uint32_t *cls_out = classes + rec_offset[m] + rowstart[(size_t) m * (H + 1) + y];
     int run = 0;
     for (int x0 = 0; x0 < W; x0 += 32) {
         int x = x0 + lane;
@@ -279,8 +280,10 @@ __global__ void __launch_bounds__(128) mask_write_records_kernel(const uint8_t *
             cds_mask_record rec;
             rec.xy = (uint32_t) x | ((uint32_t) y << 16);
             rec.lo1 = CDS_EMPTY_LO; rec.lo2 = CDS_EMPTY_LO; rec.lens = 0;
+            uint32_t cls = CDS_CLASS_NONE_INDEX;
             if (sector >= 0) {
                 int rank = __ldg(rank_tab + second * 256 + maxv);
+                cls = (uint32_t) (sector * CDS_NUM_RANKS + rank);
                 cds_class_interval iv = class_tab[sector * CDS_NUM_RANKS + rank];
                 uint32_t len1 = 0, len2 = 0;
                 if (iv.lo1 != CDS_IV_EMPTY) { rec.lo1 = iv.lo1 << CDS_CODE_SR_SHIFT; len1 = iv.len1; }
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(128) mask_write_records_kernel(const uint8_t *
             }
             int idx = run + __popc(bal & ((1u << lane) - 1));
             out[idx] = rec;
+            cls_out[idx] = cls;
         }
         run += __popc(bal);
     }
@@ -296,11 +300,124 @@ __global__ void __launch_bounds__(128) mask_write_records_kernel(const uint8_t *
 
 void launch_mask_write_records(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,
                                const uint32_t *rowstart, const uint64_t *rec_offset, const uint16_t *rank_tab,
-                               const cds_class_interval *class_tab, cds_mask_record *records, cudaStream_t s)
+                               const cds_class_interval *class_tab, cds_mask_record *records, uint32_t *classes, cudaStream_t s)
 {
     if (n_masks == 0) return;
     dim3 grid((H + 3) / 4, n_masks);
-    mask_write_records_kernel<<<grid, 128, 0, s>>>(rgb, W, H, threshold, rects, rowstart, rec_offset, rank_tab, class_tab, records);
+    mask_write_records_kernel<<<grid, 128, 0, s>>>(rgb, W, H, threshold, rects, rowstart, rec_offset, rank_tab, class_tab, records, classes);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Palettes of the compact mask records (cds_common.h): per group of CDS_PALETTE_GROUP masks, mark the colour classes in
+// use, number them, pack their intervals, rewrite the records as x | y << 11 | index << 21.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kClassSlots = CDS_NUM_CLASSES + 1;
+
+__global__ void __launch_bounds__(256) palette_mark_kernel(const MaskClassRef *__restrict__ masks, uint32_t *__restrict__ flags)
+{
+    const int m = blockIdx.y;
+    const MaskClassRef mr = masks[m];
+    uint32_t *f = flags + (size_t) (m / CDS_PALETTE_GROUP) * kClassSlots;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mr.P; i += gridDim.x * blockDim.x) f[mr.classes[i]] = 1u;
+}
+
+void launch_palette_mark(const MaskClassRef *masks, int n_masks, uint32_t *flags, cudaStream_t s)
+{
+    for (int m0 = 0; m0 < n_masks; m0 += 32768) {      // multiple of CDS_PALETTE_GROUP, so group numbering stays aligned
+        int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
+        dim3 grid(8, cnt);
+        palette_mark_kernel<<<grid, 256, 0, s>>>(masks + m0, flags + (size_t) (m0 / CDS_PALETTE_GROUP) * kClassSlots);
+    }
+}
+
+__global__ void __launch_bounds__(1024) palette_scan_kernel(const uint32_t *__restrict__ flags, uint32_t *__restrict__ pidx,
+                                                            int32_t *__restrict__ n_pal)
+{
+    __shared__ uint32_t s_part[1024];
+    const int g = blockIdx.x;
+    const uint32_t *f = flags + (size_t) g * kClassSlots;
+    uint32_t *o = pidx + (size_t) g * kClassSlots;
+    const int per = (kClassSlots + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, kClassSlots);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; i++) sum += f[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 partial sums
+    for (int off = 1; off < 1024; off <<= 1) {
+        uint32_t v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t acc = s_part[threadIdx.x] - sum;
+    for (int i = lo; i < hi; i++) { o[i] = acc; acc += f[i]; }
+    if (threadIdx.x == 1023) n_pal[g] = (int32_t) s_part[1023];
+}
+
+void launch_palette_scan(const uint32_t *flags, int n_groups, uint32_t *pidx, int32_t *n_pal, cudaStream_t s)
+{
+    if (n_groups == 0) return;
+    palette_scan_kernel<<<n_groups, 1024, 0, s>>>(flags, pidx, n_pal);
+}
+
+__device__ __forceinline__ uint32_t pack_palette_word(uint32_t lo, uint32_t len)
+{
+    if (lo == CDS_IV_EMPTY || len > CDS_PAL_MAX_LEN) return CDS_PAL_EMPTY_LO;   // callers never build palettes when a length overflows
+    return lo | (len << CDS_PAL_LO_BITS);
+}
+
+__global__ void __launch_bounds__(256) palette_fill_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pidx,
+                                                           const cds_class_interval *__restrict__ class_tab, uint2 *__restrict__ palettes)
+{
+    const int g = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kClassSlots) return;
+    if (!flags[(size_t) g * kClassSlots + c]) return;
+    const uint32_t idx = pidx[(size_t) g * kClassSlots + c];
+    if (idx >= CDS_PALETTE_SIZE) return;
+    uint2 e = make_uint2(CDS_PAL_EMPTY_LO, CDS_PAL_EMPTY_LO);
+    if (c < CDS_NUM_CLASSES) {
+        const cds_class_interval iv = class_tab[c];
+        e.x = pack_palette_word(iv.lo1, iv.len1);
+        e.y = pack_palette_word(iv.lo2, iv.len2);
+    }
+    palettes[(size_t) g * CDS_PALETTE_SIZE + idx] = e;
+}
+
+void launch_palette_fill(const uint32_t *flags, const uint32_t *pidx, int n_groups, const cds_class_interval *class_tab,
+                         uint2 *palettes, cudaStream_t s)
+{
+    for (int g0 = 0; g0 < n_groups; g0 += 32768) {
+        int cnt = n_groups - g0 < 32768 ? n_groups - g0 : 32768;
+        dim3 grid((kClassSlots + 255) / 256, cnt);
+        palette_fill_kernel<<<grid, 256, 0, s>>>(flags + (size_t) g0 * kClassSlots, pidx + (size_t) g0 * kClassSlots, class_tab,
+                                                 palettes + (size_t) g0 * CDS_PALETTE_SIZE);
+    }
+}
+
+__global__ void __launch_bounds__(256) palette_records_kernel(const MaskClassRef *__restrict__ masks, const uint32_t *__restrict__ pidx,
+                                                              const int32_t *__restrict__ n_pal)
+{
+    const int m = blockIdx.y;
+    const int g = m / CDS_PALETTE_GROUP;
+    if (n_pal[g] >= CDS_PALETTE_SIZE) return;   // the last index is reserved for idle lanes
+    const MaskClassRef mr = masks[m];
+    const uint32_t *px = pidx + (size_t) g * kClassSlots;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mr.P; i += gridDim.x * blockDim.x) {
+        const uint32_t xy = mr.records[i].xy;
+        mr.crec[i] = (xy & 0x7FFu) | (((xy >> 16) & 0x3FFu) << 11) | (px[mr.classes[i]] << 21);
+    }
+}
+
+void launch_palette_records(const MaskClassRef *masks, int n_masks, const uint32_t *pidx, const int32_t *n_pal, cudaStream_t s)
+{
+    for (int m0 = 0; m0 < n_masks; m0 += 32768) {
+        int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
+        dim3 grid(8, cnt);
+        palette_records_kernel<<<grid, 256, 0, s>>>(masks + m0, pidx + (size_t) (m0 / CDS_PALETTE_GROUP) * kClassSlots,
+                                                    n_pal + m0 / CDS_PALETTE_GROUP);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -29,7 +29,15 @@ struct RectSet {
 struct MaskDesc {
     const cds_mask_record *records;   // P records, ascending pixel index
     const uint32_t *rowstart;         // H + 1 entries: records of image row y are [rowstart[y], rowstart[y+1])
+    const uint32_t *crec;             // P compact records (cds_common.h) or nullptr when the mask's palette group is wide
     int P;
+    int pad;
+};
+
+// One palette group = CDS_PALETTE_GROUP consecutive masks.
+struct PaletteGroup {
+    const uint2 *palette;             // n_pal entries, or nullptr: the group uses the 16-byte records
+    int n_pal;
     int pad;
 };
 
@@ -63,7 +71,16 @@ void launch_mask_count_rows(const uint8_t *rgb, int n_masks, int W, int H, int t
 void launch_mask_scan_rows(uint32_t *rowcount, int n_masks, int H, int32_t *sizes, cudaStream_t s);
 void launch_mask_write_records(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,
                                const uint32_t *rowstart, const uint64_t *rec_offset, const uint16_t *rank_tab,
-                               const cds_class_interval *class_tab, cds_mask_record *records, cudaStream_t s);
+                               const cds_class_interval *class_tab, cds_mask_record *records, uint32_t *classes, cudaStream_t s);
+
+// Palette construction for n_groups groups of consecutive masks (descs[g * CDS_PALETTE_GROUP ...]); `classes` pointers come
+// with the descriptors.  flags / pidx: scratch [n_groups][CDS_NUM_CLASSES + 1].
+struct MaskClassRef { const uint32_t *classes; const cds_mask_record *records; uint32_t *crec; int P; int pad; };
+void launch_palette_mark(const MaskClassRef *masks, int n_masks, uint32_t *flags, cudaStream_t s);
+void launch_palette_scan(const uint32_t *flags, int n_groups, uint32_t *pidx, int32_t *n_pal, cudaStream_t s);
+void launch_palette_fill(const uint32_t *flags, const uint32_t *pidx, int n_groups, const cds_class_interval *class_tab,
+                         uint2 *palettes /* [n_groups][CDS_PALETTE_SIZE] */, cudaStream_t s);
+void launch_palette_records(const MaskClassRef *masks, int n_masks, const uint32_t *pidx, const int32_t *n_pal, cudaStream_t s);
 
 void launch_pixelmatch_gather(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g,
                               int64_t n_targets, ShiftSet shifts, int32_t *scores /* [n_masks][n_targets] */,

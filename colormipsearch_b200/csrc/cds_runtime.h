@@ -98,9 +98,14 @@ struct cds_maskset {
         uint64_t total_records = 0;
         std::vector<cds_mask_record *> records;        // per device
         std::vector<uint32_t *> rowstart;              // per device, [n][H+1]
+        std::vector<uint32_t *> classes;               // per device, colour class of every record
+        std::vector<uint32_t *> crec;                  // per device, compact records (filled by sync_descs)
     };
     std::vector<Batch> batches;
     std::vector<cds::MaskDesc *> d_descs;              // per device, rebuilt when dirty
+    std::vector<cds::PaletteGroup *> d_groups;         // per device, one per CDS_PALETTE_GROUP masks
+    std::vector<uint2 *> d_palettes;                   // per device, [n_groups][CDS_PALETTE_SIZE]
+    int n_compact_groups = 0;                          // informational
     bool descs_dirty = true;
     cds_status sync_descs();
 };

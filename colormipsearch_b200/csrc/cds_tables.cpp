@@ -161,11 +161,14 @@ std::shared_ptr<const ClassTable> class_table(double z_tolerance)
     auto t = std::make_shared<ClassTable>();
     t->z_tolerance = z_tolerance;
     t->iv.resize((size_t) CDS_NUM_CLASSES);
+    t->max_len = 0;
     const int NR = (int) ratio_table().ratios.size();
     for (int s = 0; s < CDS_NUM_SECTORS; s++)
         for (int k = 0; k < NR; k++) {
             cds_class_interval iv = compute_interval(z_tolerance, s, k);
             if (iv.lo2 == CDS_IV_EMPTY - 1) return nullptr;
+            if (iv.lo1 != CDS_IV_EMPTY) t->max_len = std::max(t->max_len, iv.len1);
+            if (iv.lo2 != CDS_IV_EMPTY) t->max_len = std::max(t->max_len, iv.len2);
             t->iv[(size_t) s * CDS_NUM_RANKS + k] = iv;
         }
     std::lock_guard<std::mutex> lk(g_mu);

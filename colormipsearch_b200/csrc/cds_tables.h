@@ -33,6 +33,7 @@ uint32_t encode_color(int r, int g, int b, int data_threshold);
 // Match intervals (SR units) of every mask class for one zTolerance: index = sector * CDS_NUM_RANKS + rank.
 struct ClassTable {
     double z_tolerance;
+    uint32_t max_len;                  // longest interval (SR units); compact palettes need it <= CDS_PAL_MAX_LEN
     std::vector<cds_class_interval> iv;
 };
 std::shared_ptr<const ClassTable> class_table(double z_tolerance);
