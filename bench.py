@@ -283,20 +283,27 @@ def main():
         ms.close()
         barrier()
         e2e_steps = max(1, args.e2e_steps)
+        phases = {"library_create": 0.0, "targets_h2d_encode": 0.0, "masks_h2d_prepare": 0.0, "search_topk": 0.0, "destroy": 0.0}
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            ta = time.perf_counter()
             lib_e = capi.Library(ctx, W, H, Te)
+            tb = time.perf_counter(); phases["library_create"] += tb - ta
             done = 0
             while done < Te:                      # cycle the pinned pool when it is smaller than the step's library
                 n = min(pool_t, Te - done)
                 lib_e.add_rgb_ptr(pool_ptr, n)
                 done += n
+            tc = time.perf_counter(); phases["targets_h2d_encode"] += tc - tb
             ms_e = capi.MaskSet(ctx, W, H, PARAMS["mask_threshold"], PARAMS["data_threshold"], PARAMS["z_tolerance"],
                                 PARAMS["xy_shift"], PARAMS["mirror"], rects)
             ms_e.add_rgb_ptr(mask_ptr, M)
+            td = time.perf_counter(); phases["masks_h2d_prepare"] += td - tc
             res = ms_e.search_topk(lib_e, TOPK, PCT_POSITIVE)
+            te_ = time.perf_counter(); phases["search_topk"] += te_ - td
             ms_e.close()
             lib_e.close()
+            phases["destroy"] += time.perf_counter() - te_
         barrier()
         e2e_s = time.perf_counter() - t0
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -307,7 +314,7 @@ def main():
         e2e = {"value": M * Te * world * e2e_steps / e2e_s, "unit": "comparisons/s",
                "h2d_bytes_per_step": (Te + M) * img_bytes * world, "d2h_bytes_per_step": d2h * world,
                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "targets_per_gpu": Te,
-               "pinned_pool_targets": pool_t,
+               "pinned_pool_targets": pool_t, "phase_ms_per_step": {k: v / e2e_steps * 1e3 for k, v in phases.items()},
                "what": "cds_library_create + cds_library_add_rgb (H2D + encode) + cds_maskset_add_rgb (H2D + mask preparation) + "
                        "cds_search_topk (+ result D2H, host merge), pinned host buffers"}
         ctx.host_free(pool_ptr)
@@ -322,7 +329,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp))["dram_bytes_per_comparison"] * per_launch_cmp   # ncu capture scaled to this launch
             except Exception:
                 traffic = None
         line = {
@@ -333,7 +340,7 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pixelmatch_band_kernel<1,true>",
+                         "kernel": "pixelmatch_band_kernel<1,true,128,24>",
                          "algorithmic_bytes_per_comparison": ALGO_BYTES_PER_COMPARISON,
                          "comparisons_per_launch": per_launch_cmp, "avg_launch_ms": avg_launch_s * 1e3,
                          "note": "algorithmic bytes = 3*W*H per comparison (SURVEY 8d); a mask group shares one pass over the "
