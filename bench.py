@@ -126,6 +126,70 @@ def cpu_baseline(masks_host, targets_fn, budget_s=12.0):
             "sample": "%d masks x %d targets of the same synthetic workload x %d passes, %.1f s, OpenMP over targets" % (n_m, n_t, passes, dt)}
 
 
+def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
+    """BASELINE configs[2] in miniature: shape / area-gap scoring of `per_mask` targets for each of `n_masks` masks
+    (thr 20, mirror, zgap derived on the device, synthetic gradient images).  Reports pairs/s of the pair kernel (device
+    events), end-to-end pairs/s through cds_shape_score_pairs with host buffers, mask preparation time, and the oracle."""
+    from colormipsearch_b200 import capi
+    rects = label_rects()
+    masks = np.concatenate([ctx.synth_rgb(0, SEED, i, min(64, n_masks - i), W, H, on_device=True) for i in range(0, n_masks, 64)])
+    targets = np.concatenate([ctx.synth_rgb(1, SEED, i, min(64, n_targets - i), W, H, on_device=True) for i in range(0, n_targets, 64)])
+    grads = ctx.synth_gradient(SEED, 0, n_targets, W, H, on_device=True)
+    t0 = time.perf_counter()
+    sms = capi.ShapeMaskSet(ctx, W, H, 20, True, rects)
+    sms.add_rgb(masks)
+    prep_s = time.perf_counter() - t0
+    pm = np.repeat(np.arange(n_masks, dtype=np.int32), per_mask)
+    pt = ((pm.astype(np.int64) * 7) + np.tile(np.arange(per_mask, dtype=np.int64) * 2, n_masks)) % n_targets
+    sms.score_pairs(targets[:8], grads[:8], None, pm[:16] % 1, pt[:16] % 8)      # warm-up
+    t0 = time.perf_counter()
+    gap, he, mir = sms.score_pairs(targets, grads, None, pm, pt)
+    e2e_s = time.perf_counter() - t0
+    st = ctx.last_stats()
+    n_pairs = len(pm)
+    bytes_per_pair = 3 * W * H + 2 * W * H + 3 * W * H          # SURVEY 8(d): target RGB + gradient + zgap RGB
+    peak, peak_src = measured_peak()
+    kernel_pairs_s = n_pairs / (st["match_kernel_ms"] * 1e-3)
+    out = {"metric": "shape-score pairs/sec", "pairs": n_pairs, "masks": n_masks, "targets": n_targets,
+           "value": kernel_pairs_s, "unit": "pairs/s", "kernel_ms": st["match_kernel_ms"],
+           "e2e": {"value": n_pairs / e2e_s, "unit": "pairs/s", "ms": e2e_s * 1e3,
+                   "h2d_bytes": int(n_targets * (3 * W * H + 2 * W * H)), "what": "cds_shape_score_pairs: H2D of targets + gradients, "
+                   "zgap = maxFilter(10) on device, slice planes, pair kernel, D2H"},
+           "mask_prep_ms_per_mask": prep_s / n_masks * 1e3,
+           "roofline": {"bound": "hbm", "achieved": kernel_pairs_s * bytes_per_pair / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": kernel_pairs_s * bytes_per_pair / 1e9 / peak, "algorithmic_bytes_per_pair": bytes_per_pair,
+                        "kernel": "shape_pair_kernel", "peak_source": peak_src,
+                        "note": "the kernel gathers only the query's non-black pixels, so it moves far fewer bytes than the algorithmic figure"}}
+    # oracle on a few pairs, one pair per host thread
+    try:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle as O
+        cores = O.num_threads()
+        n_cm = 2
+        oms = [O.ShapeMask(masks[i], 20, True, rects) for i in range(n_cm)]
+        zg = [O.make_zgap(targets[int(pt[i])], 20, rects) for i in range(cpu_pairs)]
+
+        def one(i):
+            return oms[i % n_cm].score(targets[int(pt[i])], grads[int(pt[i])], zg[i])
+
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            res = list(ex.map(one, range(cpu_pairs)))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": cpu_pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                               "sample": "%d pairs (zgap images prepared outside the timed region), one pair per host thread" % cpu_pairs}
+        # parity spot check of the bench itself
+        for i in range(min(cpu_pairs, 8)):
+            m = i % n_cm
+            j = int(np.nonzero((pm == m) & (pt == pt[i]))[0][0]) if ((pm == m) & (pt == pt[i])).any() else None
+            if j is not None:
+                assert (int(gap[j]), int(he[j]), bool(mir[j])) == res[i], "shape bench parity"
+    except Exception as e:  # the baseline is reporting only
+        out["cpu_baseline"] = {"error": str(e)}
+    sms.close()
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is Java and there is no JVM on
     this image, so this is the oracle port (oracle/cds_oracle.c, pinned on the reference's golden vectors) on all host
@@ -188,6 +252,7 @@ def main():
     ap.add_argument("--ref-targets", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-shape", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -247,6 +312,14 @@ def main():
     wall_s = time.perf_counter() - t0
     sampler.stop_flag.set()
     sampler.join()
+
+    # the job's result: per-rank top-K lists merged on the host (rank 0); no data-path collective
+    from colormipsearch_b200 import sharding
+    merged = None
+    if world > 1:
+        merged = sharding.gather_and_merge_topk(last, TOPK, t_first)
+    elif last is not None:
+        merged = last
 
     # max over ranks of the device time
     times = torch.tensor([dev_ms, match_ms, wall_s * 1e3], dtype=torch.float64, device="cuda")
@@ -347,8 +420,10 @@ def main():
                                  "target, so frac can exceed 1 -- physical DRAM traffic is in `traffic` / profiles/"},
             "e2e": e2e,
             "mask_pixels_mean": float(np.mean(mask_sizes)), "setup_s": setup_s,
-            "matches_returned": int(last[3].sum()) if last is not None else None,
+            "matches_returned": int(merged[3].sum()) if merged is not None else None,
         }
+        if not args.no_shape and world == 1:
+            line["shape"] = shape_bench(ctx)
         if not args.no_cpu_baseline and world == 1:
             def targets_fn(n):
                 return np.concatenate([ctx.synth_rgb(1, SEED, i, min(64, n - i), W, H, on_device=True) for i in range(0, n, 64)])
