@@ -97,6 +97,25 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what a CPU baseline wants)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def synth_host_parallel(kind, first, n):
+    """Host build of the synthetic generator, one chunk per host thread (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from colormipsearch_b200 import capi
+    nt = host_threads()
+    chunks = [(first + i, min(8, n - i)) for i in range(0, n, 8)]
+    with ThreadPoolExecutor(nt) as ex:
+        parts = list(ex.map(lambda c: capi.synth_rgb_host(kind, SEED, c[0], c[1], W, H), chunks))
+    return np.concatenate(parts)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -109,17 +128,17 @@ def cpu_baseline(masks_host, targets_fn, budget_s=12.0):
     32 masks x 1024 targets, repeated until ~budget_s of CPU work has been timed."""
     from oracle import oracle as O
     rects = label_rects()
-    cores = O.num_threads()
+    cores = host_threads()
     p = PARAMS
     n_m, n_t = min(32, len(masks_host)), 1024
     oms = [O.PixelMatchMask(m, p["mask_threshold"], p["mirror"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], rects)
            for m in masks_host[:n_m]]
     tg = targets_fn(n_t)
-    O.search_dense(oms[:2], tg[:64], 0)          # warm the threads
+    O.search_dense(oms[:2], tg[:64], cores)      # warm the threads
     passes, dt = 0, 0.0
     t0 = time.perf_counter()
     while dt < budget_s and passes < 64:
-        O.search_dense(oms, tg, 0)
+        O.search_dense(oms, tg, cores)
         passes += 1
         dt = time.perf_counter() - t0
     return {"value": n_m * n_t * passes / dt, "unit": "comparisons/s", "cores": cores, "kind": "port",
@@ -164,7 +183,7 @@ def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
     try:
         from concurrent.futures import ThreadPoolExecutor
         from oracle import oracle as O
-        cores = O.num_threads()
+        cores = host_threads()
         n_cm = 2
         oms = [O.ShapeMask(masks[i], 20, True, rects) for i in range(n_cm)]
         zg = [O.make_zgap(targets[int(pt[i])], 20, rects) for i in range(cpu_pairs)]
@@ -197,21 +216,20 @@ def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
         return
-    from colormipsearch_b200 import capi
     from oracle import oracle as O
     rects = label_rects()
-    cores = O.num_threads()
+    cores = host_threads()
     p = PARAMS
     n_m, n_t = args.ref_masks, max(args.ref_targets, cores)
-    masks = capi.synth_rgb_host(0, SEED, 0, n_m, W, H)
-    targets = capi.synth_rgb_host(1, SEED, 0, n_t, W, H)
+    masks = synth_host_parallel(0, 0, n_m)
+    targets = synth_host_parallel(1, 0, n_t)
     oms = [O.PixelMatchMask(m, p["mask_threshold"], p["mirror"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], rects)
            for m in masks]
     for _ in range(args.warmup):
-        O.search_dense(oms, targets[: max(cores, 8)], 0)
+        O.search_dense(oms[:4], targets[: max(cores, 8)], cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.search_dense(oms, targets, 0)
+        O.search_dense(oms, targets, cores)
     dt = time.perf_counter() - t0
     value = n_m * n_t * args.steps / dt
     sample = "%d masks x %d targets per step (bounded sample of the workload), OpenMP over targets" % (n_m, n_t)
@@ -248,8 +266,8 @@ def main():
     ap.add_argument("--targets-per-gpu", type=int, default=12500)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-targets", type=int, default=0, help="targets per e2e step (0 = same as --targets-per-gpu)")
-    ap.add_argument("--ref-masks", type=int, default=8)
-    ap.add_argument("--ref-targets", type=int, default=256)
+    ap.add_argument("--ref-masks", type=int, default=32)
+    ap.add_argument("--ref-targets", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-shape", action="store_true")
