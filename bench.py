@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--e2e-targets", type=int, default=0, help="targets per e2e step (0 = same as --targets-per-gpu)")
     ap.add_argument("--ref-masks", type=int, default=32)
     ap.add_argument("--ref-targets", type=int, default=1024)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "cand", "band"], help="batched match kernel (auto = candidate kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-shape", action="store_true")
@@ -294,6 +295,7 @@ def main():
 
     from colormipsearch_b200 import capi
     ctx = capi.Context(device_ids=[local_rank])
+    ctx.set_match_kernel(args.kernel)
     rects = label_rects()
     M, T = args.masks, args.targets_per_gpu
     t_first = rank * T                       # this rank's shard of the synthetic target numbering
@@ -317,7 +319,7 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    dev_ms, match_ms, launches, match_launches = 0.0, 0.0, 0, 0
+    dev_ms, match_ms, launches, match_launches, kernel_used = 0.0, 0.0, 0, 0, 0
     t0 = time.perf_counter()
     last = None
     for _ in range(args.steps):
@@ -326,6 +328,7 @@ def main():
         match_ms += st["match_kernel_ms"]
         launches += st["kernel_launches"]
         match_launches += st["match_kernel_launches"]
+        kernel_used = st["match_kernel"]
     barrier()
     wall_s = time.perf_counter() - t0
     sampler.stop_flag.set()
@@ -431,7 +434,7 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pixelmatch_band_kernel<1,true,128,24>",
+                         "kernel": {1: "pixelmatch_cand_kernel<1,128,24>", 2: "pixelmatch_band_kernel<1,true,128,24>", 3: "pixelmatch_gather_kernel"}.get(kernel_used, "?"),
                          "algorithmic_bytes_per_comparison": ALGO_BYTES_PER_COMPARISON,
                          "comparisons_per_launch": per_launch_cmp, "avg_launch_ms": avg_launch_s * 1e3,
                          "note": "algorithmic bytes = 3*W*H per comparison (SURVEY 8d); a mask group shares one pass over the "

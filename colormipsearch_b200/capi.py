@@ -45,7 +45,8 @@ class PixParams(C.Structure):
 
 class SearchStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("match_kernel_launches", C.c_int64), ("match_kernel_ms", C.c_double),
-                ("total_device_ms", C.c_double), ("comparisons", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("total_device_ms", C.c_double), ("comparisons", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("match_kernel", C.c_int64)]
 
 
 _lib = None
@@ -65,6 +66,7 @@ SIGNATURES = {
     "cds_ctx_destroy": (None, [_vp]),
     "cds_ctx_num_devices": (C.c_int32, [_vp]),
     "cds_last_error": (C.c_char_p, [_vp]),
+    "cds_ctx_set_option": (C.c_int32, [_vp, C.c_char_p, C.c_int64]),
     "cds_host_alloc": (C.c_int32, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "cds_host_free": (C.c_int32, [_vp, _vp]),
     "cds_library_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int64, C.POINTER(_vp)]),
@@ -166,6 +168,14 @@ class Context:
     @property
     def num_devices(self):
         return lib().cds_ctx_num_devices(self.h)
+
+    MATCH_KERNELS = {"auto": 0, "cand": 1, "band": 2, "gather": 3}
+
+    def set_option(self, name, value):
+        _check(lib().cds_ctx_set_option(self.h, name.encode(), int(value)), self.h)
+
+    def set_match_kernel(self, which):
+        self.set_option("match_kernel", self.MATCH_KERNELS[which])
 
     def host_alloc(self, nbytes):
         """Pinned host buffer as a numpy uint8 array (freed with host_free)."""

@@ -7,6 +7,7 @@
 
 #include "cds_runtime.h"
 #include "cds_band.cuh"
+#include "cds_cand.cuh"
 #include "cds_topk.cuh"
 
 using namespace cds;
@@ -192,6 +193,18 @@ extern "C" cds_status cds_host_free(cds_ctx *ctx, void *p)
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CDS_CUDA(ctx, cudaFreeHost(p));
     return CDS_OK;
+}
+
+extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) { set_tls_error("cds_ctx_set_option: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (std::strcmp(name, "match_kernel") == 0) {
+        if (value < 0 || value > 3) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: match_kernel must be 0..3");
+        ctx->match_kernel = (int) value;
+        return CDS_OK;
+    }
+    return ctx->fail(CDS_ERR_BAD_ARG, std::string("cds_ctx_set_option: unknown option ") + name);
 }
 
 extern "C" cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out)
@@ -451,6 +464,8 @@ extern "C" cds_status cds_maskset_create(cds_ctx *ctx, int32_t width, int32_t he
     ms->d_descs.assign(ctx->devs.size(), nullptr);
     ms->d_groups.assign(ctx->devs.size(), nullptr);
     ms->d_palettes.assign(ctx->devs.size(), nullptr);
+    ms->d_words.assign(ctx->devs.size(), nullptr);
+    ms->d_wstart.assign(ctx->devs.size(), nullptr);
     // build (or fetch) the interval table now so that a bad tolerance fails here
     for (DevState &ds : ctx->devs) {
         const cds_class_interval *tab;
@@ -478,6 +493,8 @@ extern "C" void cds_maskset_destroy(cds_maskset *ms)
         if (ms->d_descs[d]) cudaFree(ms->d_descs[d]);
         if (ms->d_groups[d]) cudaFree(ms->d_groups[d]);
         if (ms->d_palettes[d]) cudaFree(ms->d_palettes[d]);
+        if (ms->d_words[d]) cudaFree(ms->d_words[d]);
+        if (ms->d_wstart[d]) cudaFree(ms->d_wstart[d]);
     }
     cudaGetLastError();
     delete ms;
@@ -608,8 +625,10 @@ cds_status cds_maskset::sync_descs()
                 h[mi].records = b.records[d] + b.rec_offset[i];
                 h[mi].rowstart = b.rowstart[d] + (size_t) i * (H + 1);
                 h[mi].crec = nullptr;
+                h[mi].words = nullptr;
+                h[mi].wstart = nullptr;
                 h[mi].P = sizes[mi];
-                h[mi].pad = 0;
+                h[mi].n_words = 0;
                 refs[mi].classes = b.classes[d] + b.rec_offset[i];
                 refs[mi].records = h[mi].records;
                 refs[mi].crec = b.crec[d] + b.rec_offset[i];
@@ -619,6 +638,8 @@ cds_status cds_maskset::sync_descs()
         if (d_descs[d]) { cudaFree(d_descs[d]); d_descs[d] = nullptr; }
         if (d_groups[d]) { cudaFree(d_groups[d]); d_groups[d] = nullptr; }
         if (d_palettes[d]) { cudaFree(d_palettes[d]); d_palettes[d] = nullptr; }
+        if (d_words[d]) { cudaFree(d_words[d]); d_words[d] = nullptr; }
+        if (d_wstart[d]) { cudaFree(d_wstart[d]); d_wstart[d] = nullptr; }
         std::vector<PaletteGroup> groups(std::max(n_groups, 1));
         for (auto &g : groups) { g.palette = nullptr; g.n_pal = 0; g.pad = 0; }
         if (compact_ok) {
@@ -665,6 +686,37 @@ cds_status cds_maskset::sync_descs()
         CDS_CUDA(ctx, cudaMalloc(&d_descs[d], h.size() * sizeof(MaskDesc)));
         CDS_CUDA(ctx, cudaMalloc(&d_groups[d], groups.size() * sizeof(PaletteGroup)));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
+        // word lists of the candidate kernel (cds_cand.cuh): count per row, scan, size the arrays, fill
+        const bool words_ok = M > 0 && W <= 2048 && H <= 1024 && (params.xy_shift == 0 || params.xy_shift == 2 || params.xy_shift == 4);
+        if (words_ok) {
+            int32_t *d_wsizes = nullptr;
+            cds_status st = ctx->check(cudaMalloc(&d_wstart[d], (size_t) M * (H + 1) * sizeof(uint32_t)), "cudaMalloc(word row starts)");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_wsizes, (size_t) M * sizeof(int32_t)), "cudaMalloc(word counts)");
+            std::vector<int32_t> wsizes(M, 0);
+            if (st == CDS_OK) {
+                launch_words_count(d_descs[d], M, W, H, params.mirror != 0, d_wstart[d], ds.stream);
+                launch_mask_scan_rows(d_wstart[d], M, H, d_wsizes, ds.stream);
+                ctx->stats.kernel_launches += 2;
+                st = ctx->check(cudaGetLastError(), "word count kernels");
+            }
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(wsizes.data(), d_wsizes, (size_t) M * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "word counts D2H");
+            if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "word count");
+            if (d_wsizes) cudaFree(d_wsizes);
+            if (st != CDS_OK) return st;
+            size_t total_words = 0;
+            for (int m = 0; m < M; m++) {
+                h[m].n_words = wsizes[m];
+                h[m].wstart = d_wstart[d] + (size_t) m * (H + 1);
+                total_words += (size_t) wsizes[m];
+            }
+            CDS_CUDA(ctx, cudaMalloc(&d_words[d], std::max<size_t>(total_words, 1) * 3 * sizeof(uint32_t)));
+            size_t off = 0;
+            for (int m = 0; m < M; m++) { h[m].words = d_words[d] + 3 * off; off += (size_t) wsizes[m]; }
+            CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
+            launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, ds.stream);
+            ctx->stats.kernel_launches++;
+            CDS_CUDA(ctx, cudaGetLastError());
+        }
         CDS_CUDA(ctx, cudaMemcpyAsync(d_groups[d], groups.data(), groups.size() * sizeof(PaletteGroup), cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
     }
@@ -679,17 +731,33 @@ struct SearchPlan {
     bool use_band;
 };
 
+bool batched_kernel_supported(const cds_maskset *ms, const cds_library *lib)
+{
+    return cand_kernel_supported(ms->params.xy_shift, lib->g) || band_kernel_supported(ms->params.xy_shift, lib->g);
+}
+
 // Runs the match kernel of one device for masks [m0, m0+mc) against the device's local targets [0, n_local):
 // d_scores[(m - m0) * n_local + t] = score word.
 cds_status launch_match(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, int d, int m0, int mc, int64_t n_local,
                         int32_t *d_scores)
 {
     DevState &ds = ctx->devs[d];
-    const bool band_ok = band_kernel_supported(ms->params.xy_shift, lib->g) && mc >= band_min_masks() && lib->shards[d].occ &&
-                         (m0 % CDS_PALETTE_GROUP) == 0 &&
-                         lib->shards[d].occ_done >= n_local;
+    const int choice = ctx->match_kernel;      // 0 = automatic, 1 = candidate, 2 = band, 3 = gather (cds_ctx_set_option)
+    const bool batched_ok = mc >= band_min_masks() && lib->shards[d].occ && (m0 % CDS_PALETTE_GROUP) == 0 &&
+                            lib->shards[d].occ_done >= n_local && lib->occ_rings == ms->params.xy_shift / 2 &&
+                            lib->occ_threshold == lib->baked_threshold;
+    const bool cand_ok = batched_ok && (choice == 0 || choice == 1) && ms->d_words[d] && cand_kernel_supported(ms->params.xy_shift, lib->g);
+    const bool band_ok = batched_ok && choice != 3 && band_kernel_supported(ms->params.xy_shift, lib->g);
     cudaEventRecord(ds.ev0, ds.stream);
-    if (band_ok) {
+    if (cand_ok) {
+        int launches = launch_pixelmatch_cand(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local,
+                                              lib->shards[d].occ, lib->bpitch, ms->d_groups[d] + m0 / CDS_PALETTE_GROUP,
+                                              ms->params.xy_shift, ms->params.mirror != 0, d_scores, ds.stream);
+        ctx->stats.kernel_launches += launches;
+        ctx->stats.match_kernel_launches += launches;
+        ctx->stats.match_kernel = 1;
+    } else if (band_ok) {
+        ctx->stats.match_kernel = 2;
         int launches = launch_pixelmatch_band(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local,
                                               lib->shards[d].occ, lib->bpitch, ms->d_groups[d] + m0 / CDS_PALETTE_GROUP,
                                               ms->params.xy_shift, ms->params.mirror != 0, d_scores, ds.stream);
@@ -697,6 +765,7 @@ cds_status launch_match(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, i
         ctx->stats.match_kernel_launches += launches;
     } else {
         launch_pixelmatch_gather(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local, ms->shifts, d_scores, ds.stream);
+        ctx->stats.match_kernel = 3;
         int launches = (mc + 32767) / 32768;
         ctx->stats.kernel_launches += launches;
         ctx->stats.match_kernel_launches += launches;
@@ -737,7 +806,7 @@ extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cd
     reset_stats(ctx);
     CDS_TRY(ms->sync_descs());
     CDS_TRY(lib->bake(ms->params.data_threshold));
-    if (band_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
+    if (batched_kernel_supported(ms, lib) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
     const int D = lib->n_dev();
     // mask chunking bounds the per-device score buffer to ~256 MiB
     std::vector<int32_t *> d_scores(D, nullptr);
@@ -822,7 +891,7 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
     if (T == 0) return CDS_OK;
     CDS_TRY(ms->sync_descs());
     CDS_TRY(lib->bake(ms->params.data_threshold));
-    if (band_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
+    if (batched_kernel_supported(ms, lib) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
     const int D = lib->n_dev();
     std::vector<int32_t> min_score(M);
     for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);

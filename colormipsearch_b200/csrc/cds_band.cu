@@ -27,6 +27,7 @@
 //     LDS per variant, two subtract/compare pairs and one predicated add into a packed counter.  A ticket ends with one
 //     REDUX per packed register and shared-memory atomic adds into the per-(mask, variant) accumulators.
 #include "cds_band.cuh"
+#include "cds_ptx.cuh"
 
 #include <cstdlib>
 
@@ -55,39 +56,6 @@ struct BandParams {
     int bpitch;
     const PaletteGroup *groups;     // palette group of masks[0] onwards (masks[0] is CDS_PALETTE_GROUP aligned in the mask set)
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-template <int N>
-__device__ __forceinline__ void consumer_barrier()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
-}
 
 // cnt += INC when the code word c lies in [lo1, lo1+len1] or [lo2, lo2+len2]: two subtracts, two compares, one predicated add
 template <uint32_t INC>
@@ -208,8 +176,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
             mbar_init(smem_u32(s_empty + s), NCW);
             s_next[s] = 0;
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_fence_init();
     }
     for (int i = tid; i < GROUP * NV; i += blockDim.x) s_acc[i] = 0;
     // never-matching words below each stage: a pixel in the first row of a band whose shifted / mirrored column is -1..-4

@@ -1,0 +1,647 @@
+// cds_cand.cu -- batched pixel match, candidate formulation: 32 mask pixels are tested against a target with ONE AND,
+// and only the surviving (pixel, orientation) candidates are evaluated, 32 at a time with every lane busy.
+//
+// What it computes is exactly PixelMatchColorDepthSearchAlgorithm.calculateMatchingScore
+// (colormipsearch-api/src/main/java/org/janelia/colormipsearch/cds/PixelMatchColorDepthSearchAlgorithm.java:166-263) for every
+// (mask, target) of the launch, like cds_band.cu (same pipeline, same data, same outputs).  What differs is the inner loop:
+//
+//   * cds_band.cu gives every lane one mask pixel per iteration and lets a warp skip an orientation when none of its 32
+//     pixels has its occupancy bit set.  On colour-depth MIPs ~8 % of the (pixel, orientation) tests can match but ~34 % of
+//     the 32-pixel warp iterations contain at least one, so most evaluated lanes are dead weight and the per-pixel
+//     bookkeeping (record decode, two bitmap reads, two votes) is paid for every pixel.
+//   * here a lane owns one 32-pixel WORD of the mask bitmap per iteration (cds_cand.cuh): candidates = word & occupancy word.
+//     Set bits are peeled off with warp-aggregated pushes into a per-warp shared-memory queue; whenever 32 candidates are
+//     queued the warp evaluates them: palette lookup, 9 (17) shifted reads of the band, predicated adds into per-lane
+//     counters.  Work is proportional to the candidates, not to the mask size.
+//
+// Mirrored variants need no separate code: orientation-1 words are stored in target coordinates (bit W-1-x), and the 3x3
+// (5x5) shift pattern is symmetric, so both orientations read the same neighbourhood offsets of their centre; only the
+// variant LABEL differs (offset (dx,dy) of a mirrored pixel is the reference's variant (-dx,dy)), and the score is a max
+// over labels.  A candidate's orientation just selects the half (low / high 16 bits) of the packed counters it increments.
+#include "cds_cand.cuh"
+#include "cds_ptx.cuh"
+
+#include <cstdlib>
+
+namespace cds {
+
+namespace {
+
+constexpr int kStages = 2;
+constexpr int kMaxBands = 128;
+constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy destination aligned)
+constexpr int kChunk = 256;         // word-list entries per ticket
+constexpr int kQueue = 64;          // candidate slots per warp (power of two, >= 2 * 32)
+constexpr int kWordQueue = 64;      // word slots per warp (power of two, >= 2 * 32)
+
+struct CandParams {
+    const MaskDesc *masks;
+    int n_masks;
+    const uint32_t *planes;
+    PlaneGeom g;
+    int64_t n_targets;
+    int32_t *scores;                // [n_masks][n_targets]
+    unsigned long long *work_counter;
+    int rows_per_band;              // R
+    int n_bands;
+    int stage_words;                // (R + 2s) * pitch
+    int n_groups;
+    const uint32_t *occ;            // occupancy bitmap [n_targets][H][bpitch]
+    int bpitch;
+    const PaletteGroup *groups;
+};
+
+template <int NRINGS> struct Offsets;
+template <> struct Offsets<0> { static constexpr int N = 1; };
+template <> struct Offsets<1> { static constexpr int N = 9; };
+template <> struct Offsets<2> { static constexpr int N = 17; };
+
+template <int NRINGS>
+__device__ __forceinline__ void offset_of(int v, int &dx, int &dy)
+{
+    if (NRINGS == 0) { dx = 0; dy = 0; return; }
+    if (v < 9) { dx = (v / 3 - 1) * 2; dy = (v % 3 - 1) * 2; return; }
+    int k = v - 9;                  // ring 4 without its centre
+    if (k >= 4) k++;
+    dx = (k / 3 - 1) * 4;
+    dy = (k % 3 - 1) * 4;
+}
+
+// cnt += inc when the code word c lies in [lo1, lo1+len1] or [lo2, lo2+len2]
+__device__ __forceinline__ void count_hit(uint32_t &cnt, uint32_t c, uint32_t lo1, uint32_t len1, uint32_t lo2, uint32_t len2, uint32_t inc)
+{
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 a, b;\n\t"
+        "sub.u32 a, %1, %2;\n\t"
+        "sub.u32 b, %1, %4;\n\t"
+        "setp.le.u32 p, a, %3;\n\t"
+        "setp.le.or.u32 p, b, %5, p;\n\t"
+        "@p add.u32 %0, %0, %6;\n\t}"
+        : "+r"(cnt) : "r"(c), "r"(lo1), "r"(len1), "r"(lo2), "r"(len2), "r"(inc));
+}
+
+template <int GROUP>
+struct CandSmem {
+    size_t stage_off, bits_off, pal_off, acc_off, bseg_off, btick_off, wptr_off, rptr_off, wcnt_off, queue_off, wqueue_off, bar_off, next_off, item_off, total;
+    __host__ __device__ CandSmem(int stage_words, int NS, int bits_words, int n_warps)
+    {
+        size_t o = 0;
+        stage_off = o; o += (size_t) kStages * (stage_words + kPrePad) * 4;
+        bits_off = o;  o += (size_t) kStages * bits_words * 4;
+        pal_off = o;   o += (size_t) CDS_PALETTE_SIZE * 8;
+        wqueue_off = o; o += (size_t) n_warps * kWordQueue * 16;
+        queue_off = o; o += (size_t) n_warps * kQueue * 8;
+        wptr_off = o;  o += (size_t) GROUP * 8;
+        rptr_off = o;  o += (size_t) GROUP * 8;
+        bar_off = o;   o += 2 * kStages * 8;
+        item_off = o;  o += 16;
+        next_off = o;  o += 16;
+        wcnt_off = o;  o += (size_t) GROUP * 4;
+        acc_off = o;   o += (size_t) GROUP * 2 * NS * 4;
+        bseg_off = o;  o += (size_t) kStages * GROUP * 8;                       // per stage: {first, end} word index of every mask in the band
+        btick_off = o; o += ((size_t) kStages * (GROUP + 1) * 2 + 15) / 16 * 16;  // per stage: ticket prefix sums
+        total = o;
+    }
+};
+
+// The evaluations of 32 queued candidates: one per lane.  cand.x = x | y << 11 | orientation << 21 (target coordinates),
+// cand.y = record index inside the mask.
+template <int NRINGS, bool COMPACT>
+__device__ __forceinline__ void eval_candidates(uint2 cand, bool live, const uint32_t *__restrict__ band, int y0, int pitch,
+                                                const void *__restrict__ recs, const uint2 *__restrict__ s_pal,
+                                                uint32_t (&cnt)[Offsets<NRINGS>::N])
+{
+    constexpr int NS = Offsets<NRINGS>::N;
+    constexpr int S = 2 * NRINGS;
+    uint32_t lo1, len1, lo2, len2;
+    if (COMPACT) {
+        uint32_t pi = CDS_PALETTE_SIZE - 1;                                     // the never-matching entry
+        if (live) pi = __ldg(static_cast<const uint32_t *>(recs) + cand.y) >> 21;
+        const uint2 pe = s_pal[pi];
+        lo1 = (pe.x & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
+        len1 = ((pe.x >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
+        lo2 = (pe.y & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
+        len2 = ((pe.y >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
+    } else {
+        uint4 r = make_uint4(0u, CDS_EMPTY_LO, CDS_EMPTY_LO, 0u);
+        if (live) r = __ldg(reinterpret_cast<const uint4 *>(static_cast<const cds_mask_record *>(recs) + cand.y));
+        lo1 = r.y;
+        lo2 = r.z;
+        len1 = ((r.w & 0xFFFFu) << CDS_CODE_SR_SHIFT) | 0xFFu;
+        len2 = ((r.w >> 16) << CDS_CODE_SR_SHIFT) | 0xFFu;
+    }
+    const int x = (int) (cand.x & 0x7FFu);
+    const int yrel = (int) ((cand.x >> 11) & 0x3FFu) - y0;
+    const uint32_t inc = (cand.x & (1u << 21)) ? 0x10000u : 1u;
+    const uint32_t *pc = band + (yrel + S) * pitch + x;
+#pragma unroll
+    for (int v = 0; v < NS; v++) {
+        int dx, dy;
+        offset_of<NRINGS>(v, dx, dy);
+        count_hit(cnt[v], pc[dy * pitch + dx], lo1, len1, lo2, len2, inc);
+    }
+}
+
+template <int NRINGS, int GROUP, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(const CandParams p)
+{
+    constexpr int NS = Offsets<NRINGS>::N;            // shift offsets = variants per orientation
+    constexpr int NV = 2 * NS;                        // accumulators per mask: [0, NS) unmirrored, [NS, 2NS) mirrored
+    constexpr int S = 2 * NRINGS;                     // halo rows = xyShift
+    constexpr int NCT = NCW * 32;                     // consumer threads
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int bits_words = p.rows_per_band * p.bpitch;
+    const CandSmem<GROUP> L(p.stage_words, NS, bits_words, NCW);
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
+    const int stage_stride = p.stage_words + kPrePad;
+    const uint32_t *s_bits = reinterpret_cast<const uint32_t *>(smem_raw + L.bits_off);  // [kStages][R * bpitch]
+    uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
+    uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + L.queue_off);                  // [NCW][kQueue] candidates
+    uint4 *s_wqueue = reinterpret_cast<uint4 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] words with candidates
+    const uint32_t **s_wptr = reinterpret_cast<const uint32_t **>(smem_raw + L.wptr_off);// word lists
+    const void **s_rptr = reinterpret_cast<const void **>(smem_raw + L.rptr_off);        // record arrays (compact or 16-byte)
+    uint32_t *s_wcnt = reinterpret_cast<uint32_t *>(smem_raw + L.wcnt_off);              // word-list lengths
+    int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
+    uint2 *s_bseg = reinterpret_cast<uint2 *>(smem_raw + L.bseg_off);                   // [kStages][GROUP] word range of each mask in the staged band
+    uint16_t *s_btick = reinterpret_cast<uint16_t *>(smem_raw + L.btick_off);           // [kStages][GROUP + 1] ticket prefix sums of the staged band
+    unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
+    unsigned long long *s_empty = s_full + kStages;
+    int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
+    long long *s_item = reinterpret_cast<long long *>(smem_raw + L.item_off);           // [2] published work items
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pitch = p.g.pitch, H = p.g.H, R = p.rows_per_band, NB = p.n_bands;
+    const long long n_items = (long long) p.n_groups * p.n_targets;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(smem_u32(s_full + s), 1);
+            mbar_init(smem_u32(s_empty + s), NCW);
+            s_next[s] = 0;
+        }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < GROUP * NV; i += blockDim.x) s_acc[i] = 0;
+    // never-matching words below each stage: a candidate in the first row of a band whose shifted column is -1..-4
+    if (tid < kStages * kPrePad) s_stage[(tid / kPrePad) * stage_stride - kPrePad + (tid % kPrePad)] = CDS_CODE_PAD_WORD;
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ------------------------------------------------------------------ producer warp
+        // Lane 0 drives the barriers and the bulk copies; all lanes prepare the band's ticket tables: for each mask of the group
+        // the range of word-list entries inside the band's rows and the prefix sums of their ticket counts.  The tables travel
+        // with the stage (written before the arrive on its "full" barrier), so consumers never meet at a CTA-wide barrier.
+        constexpr int MPL = GROUP / 32;     // masks per lane
+        uint32_t q = 0;                     // running band number across items: stage = q & 1, use = q >> 1
+        uint32_t iseq = 0;
+        for (;;) {
+            long long w = 0;
+            if (lane == 0) w = (long long) atomicAdd(p.work_counter, 1ull);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            const bool done = w >= n_items;
+            const int nb = done ? 1 : NB;
+            const int m0 = done ? 0 : (int) (w / p.n_targets) * GROUP;
+            const int mb = done ? 0 : min(GROUP, p.n_masks - m0);
+            const int64_t t = done ? 0 : w % p.n_targets;
+            const uint32_t *wsp[MPL];
+#pragma unroll
+            for (int k = 0; k < MPL; k++) {
+                const int mi = lane * MPL + k;
+                wsp[k] = mi < mb ? p.masks[m0 + mi].wstart : nullptr;
+            }
+            for (int b = 0; b < nb; b++, q++) {
+                const int stage = q & 1;
+                const int y0 = b * R;
+                const int y1 = min(y0 + R, H);
+                // the band's tables, in registers first: their loads overlap the wait for the stage
+                uint32_t st[MPL], en[MPL], nt[MPL], sum = 0;
+#pragma unroll
+                for (int k = 0; k < MPL; k++) {
+                    st[k] = 0; en[k] = 0;
+                    if (wsp[k]) { st[k] = __ldg(wsp[k] + y0); en[k] = __ldg(wsp[k] + y1); }
+                    nt[k] = (en[k] - st[k] + kChunk - 1) / kChunk;
+                    sum += nt[k];
+                }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (q >= kStages) {
+                    if (lane == 0) mbar_wait(smem_u32(s_empty + stage), ((q >> 1) - 1) & 1);
+                    __syncwarp();
+                }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int k = 0; k < MPL; k++) {
+                    const int mi = lane * MPL + k;
+                    s_bseg[stage * GROUP + mi] = make_uint2(st[k], en[k]);
+                    s_btick[stage * (GROUP + 1) + mi] = (uint16_t) run;
+                    run += nt[k];
+                }
+                if (lane == 31) s_btick[stage * (GROUP + 1) + GROUP] = (uint16_t) incl;
+                __syncwarp();
+                if (lane == 0) {
+                    s_next[stage] = 0;
+                    if (b == 0) s_item[iseq & 1] = done ? -1 : w;
+                    const uint32_t bar = smem_u32(s_full + stage);
+                    if (done) {
+                        mbar_arrive(bar);
+                    } else {
+                        const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
+                        const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
+                        const uint32_t bbytes = (uint32_t) ((y1 - y0) * p.bpitch) * 4u;
+                        const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * p.bpitch;
+                        mbar_expect_tx(bar, bytes + bbytes);
+                        bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
+                        bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
+                    }
+                }
+                if (done) break;
+            }
+            if (done) break;
+            iseq++;
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    uint32_t q = 0, iseq = 0;
+    int cur_gi = -1;
+    bool compact = false;
+    uint2 *myq = s_queue + warp * kQueue;
+    uint4 *mywq = s_wqueue + warp * kWordQueue;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (;;) {
+        mbar_wait(smem_u32(s_full + (q & 1)), (q >> 1) & 1);
+        const long long w = *reinterpret_cast<volatile long long *>(s_item + (iseq & 1));
+        if (w < 0) break;
+        const int gi = (int) (w / p.n_targets);
+        const int64_t t = w % p.n_targets;
+        const int m0 = gi * GROUP;
+        const int mb = min(GROUP, p.n_masks - m0);
+
+        if (gi != cur_gi) {
+            // per-group tables.  Every consumer passed the barrier that ends the previous item, so nobody still reads the old ones.
+            const PaletteGroup pg = p.groups[m0 / CDS_PALETTE_GROUP];
+            compact = pg.palette != nullptr;
+            for (int i = tid; i < mb; i += NCT) {
+                const MaskDesc md = p.masks[m0 + i];
+                s_wptr[i] = md.words;
+                s_wcnt[i] = (uint32_t) md.n_words;
+                s_rptr[i] = compact ? (const void *) md.crec : (const void *) md.records;
+            }
+            if (compact) {
+                for (int i = tid; i < pg.n_pal; i += NCT) s_pal[i] = pg.palette[i];
+                if (tid == 0) s_pal[CDS_PALETTE_SIZE - 1] = make_uint2(CDS_PAL_EMPTY_LO, CDS_PAL_EMPTY_LO);   // idle lanes point here
+            }
+            consumer_barrier<NCT>();
+            cur_gi = gi;
+        }
+
+        for (int b = 0; b < NB; b++, q++) {
+            const int stage = q & 1;
+            if (b > 0) mbar_wait(smem_u32(s_full + stage), (q >> 1) & 1);
+            const uint32_t *band = s_stage + (size_t) stage * stage_stride;
+            const uint32_t *bits = s_bits + (size_t) stage * bits_words;
+            const int y0 = b * R;
+            const uint16_t *tick = s_btick + stage * (GROUP + 1);
+            const uint2 *bseg = s_bseg + stage * GROUP;
+            const int n_tickets = tick[GROUP];
+
+            for (;;) {
+                int tk = 0;
+                if (lane == 0) tk = atomicAdd(&s_next[stage], 1);
+                tk = __shfl_sync(0xffffffffu, tk, 0);
+                if (tk >= n_tickets) break;
+                // mask of the ticket: the last mi with tick[mi] <= tk
+                int le = 0;
+#pragma unroll
+                for (int k = 0; k < GROUP / 32; k++) le += __popc(__ballot_sync(0xffffffffu, (int) tick[k * 32 + lane] <= tk));
+                const int mi = le - 1;
+                const uint2 sg = bseg[mi];
+                const uint32_t seg0 = sg.x + (uint32_t) (tk - tick[mi]) * kChunk;
+                const uint32_t seg1 = min(seg0 + kChunk, sg.y);
+                const uint32_t *wb = s_wptr[mi];
+                const uint32_t nw = s_wcnt[mi];
+                const uint32_t *wm = wb + nw, *wr = wm + nw;
+                const void *recs = s_rptr[mi];
+                uint32_t cnt[NS];
+#pragma unroll
+                for (int j = 0; j < NS; j++) cnt[j] = 0;
+                uint32_t qh = 0, qt = 0;            // candidate queue head / tail (free running, slot = index & (kQueue - 1))
+                uint32_t wh = 0, wt = 0;            // word queue head / tail
+
+                // Peels the set bits of 32 queued words (one word per lane; `c` = 0 for idle lanes) into the candidate queue,
+                // lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
+                auto peel = [&](uint4 we) {
+                    uint32_t c = we.x;
+                    const uint32_t base = we.y, rec = we.z, wbits = we.w;
+                    const bool mirrored = (base >> 21) & 1u;
+                    unsigned bal = __ballot_sync(0xffffffffu, c != 0);
+                    while (bal) {
+                        if (c) {
+                            const int bit = __ffs((int) c) - 1;
+                            const uint32_t k = (uint32_t) __popc(wbits & ((1u << bit) - 1u));
+                            uint2 cand;
+                            cand.x = base | (uint32_t) bit;
+                            cand.y = mirrored ? rec - k : rec + k;
+                            myq[(qt + (uint32_t) __popc(bal & lt_mask)) & (kQueue - 1)] = cand;
+                            c &= c - 1;
+                        }
+                        qt += (uint32_t) __popc(bal);
+                        if (qt - qh >= 32) {
+                            __syncwarp();
+                            const uint2 cand = myq[(qh + lane) & (kQueue - 1)];
+                            if (compact) eval_candidates<NRINGS, true>(cand, true, band, y0, pitch, recs, s_pal, cnt);
+                            else eval_candidates<NRINGS, false>(cand, true, band, y0, pitch, recs, s_pal, cnt);
+                            qh += 32;
+                        }
+                        bal = __ballot_sync(0xffffffffu, c != 0);
+                    }
+                };
+
+                // word entries are prefetched two iterations ahead; lanes past the end carry an empty word on a valid row
+                const uint32_t idle_meta = (uint32_t) y0;
+                uint32_t b0 = 0, e0 = idle_meta, r0 = 0, b1 = 0, e1 = idle_meta, r1 = 0;
+                {
+                    uint32_t i = seg0 + lane;
+                    if (i < seg1) { b0 = __ldg(wb + i); e0 = __ldg(wm + i); r0 = __ldg(wr + i); }
+                    i += 32;
+                    if (i < seg1) { b1 = __ldg(wb + i); e1 = __ldg(wm + i); r1 = __ldg(wr + i); }
+                }
+                for (uint32_t base = seg0; base < seg1; base += 32) {
+                    const uint32_t wbits = b0, meta = e0, rec = r0;
+                    b0 = b1; e0 = e1; r0 = r1;
+                    b1 = 0; e1 = idle_meta; r1 = 0;
+                    {
+                        const uint32_t i = base + 64 + lane;
+                        if (i < seg1) { b1 = __ldg(wb + i); e1 = __ldg(wm + i); r1 = __ldg(wr + i); }
+                    }
+                    const uint32_t y = meta & ((1u << kWordMetaYBits) - 1);
+                    const uint32_t xw = (meta >> kWordMetaYBits) & 63u;
+                    const uint32_t c = wbits & bits[((int) y - y0) * p.bpitch + (int) xw];  // mask pixels of this word that can match
+                    // words with candidates are compacted first, so that the bit peeling below runs on full warps
+                    const unsigned has = __ballot_sync(0xffffffffu, c != 0);
+                    if (c) {
+                        const uint32_t orient = (meta >> kWordMetaOrientBit) & 1u;
+                        mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] = make_uint4(c, (xw << 5) | (y << 11) | (orient << 21), rec, wbits);
+                    }
+                    wt += (uint32_t) __popc(has);
+                    if (wt - wh >= 32) {
+                        __syncwarp();
+                        const uint4 we = mywq[(wh + lane) & (kWordQueue - 1)];
+                        wh += 32;
+                        peel(we);
+                    }
+                }
+                // the ticket's last, partly filled batches
+                if (wt != wh) {
+                    __syncwarp();
+                    uint4 we = make_uint4(0u, 0u, 0u, 0u);
+                    if (lane < (int) (wt - wh)) we = mywq[(wh + lane) & (kWordQueue - 1)];
+                    peel(we);
+                }
+                if (qt != qh) {
+                    __syncwarp();
+                    const bool live = lane < (int) (qt - qh);
+                    uint2 cand = make_uint2((uint32_t) y0 << 11, 0u);
+                    if (live) cand = myq[(qh + lane) & (kQueue - 1)];
+                    if (compact) eval_candidates<NRINGS, true>(cand, live, band, y0, pitch, recs, s_pal, cnt);
+                    else eval_candidates<NRINGS, false>(cand, live, band, y0, pitch, recs, s_pal, cnt);
+                }
+                __syncwarp();
+                // ticket done: warp totals (a ticket has <= kChunk * 32 candidates, so the packed halves cannot carry)
+                uint32_t mine = 0;
+#pragma unroll
+                for (int j = 0; j < NS; j++) {
+                    const uint32_t tot = __reduce_add_sync(0xffffffffu, cnt[j]);
+                    if (lane == j) mine = tot;
+                }
+                if (lane < NS) {
+                    const int vn = (int) (mine & 0xFFFFu), vm = (int) (mine >> 16);
+                    if (vn) atomicAdd(&s_acc[mi * NV + lane], vn);
+                    if (vm) atomicAdd(&s_acc[mi * NV + NS + lane], vm);
+                }
+            }
+            // this warp is done with the stage: let the producer refill it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(s_empty + stage));
+        }
+
+        // item epilogue: max over variants per orientation; mirrored wins only when strictly greater
+        consumer_barrier<NCT>();
+        for (int mi = tid; mi < mb; mi += NCT) {
+            int best = 0, bestm = 0;
+#pragma unroll
+            for (int v = 0; v < NS; v++) best = max(best, s_acc[mi * NV + v]);
+#pragma unroll
+            for (int v = 0; v < NS; v++) bestm = max(bestm, s_acc[mi * NV + NS + v]);
+            int word = best;
+            if (bestm > best) word = bestm | CDS_SCORE_MIRROR_BIT;          // no mirrored words in the lists -> bestm stays 0
+            p.scores[(size_t) (m0 + mi) * p.n_targets + t] = word;
+#pragma unroll
+            for (int v = 0; v < NV; v++) s_acc[mi * NV + v] = 0;
+        }
+        consumer_barrier<NCT>();
+        iseq++;
+    }
+}
+
+struct CandConfig {
+    int rows_per_band, n_bands, stage_words;
+    size_t smem_bytes;
+    bool ok;
+};
+
+template <int GROUP>
+CandConfig cand_config(int xy_shift, const PlaneGeom &g, int n_warps)
+{
+    const int bpitch = occupancy_pitch(g.W);
+    CandConfig c{};
+    const int S = xy_shift;
+    const int NS = xy_shift == 0 ? 1 : (xy_shift == 2 ? 9 : 17);
+    const size_t budget = 227 * 1024;
+    for (int R = g.H; R >= 1; R--) {
+        int n_bands = (g.H + R - 1) / R;
+        if (n_bands > kMaxBands) break;
+        size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
+        if (stage_words * 4 >= (1u << 20)) continue;
+        CandSmem<GROUP> L((int) stage_words, NS, R * bpitch, n_warps);
+        if (L.total <= budget) {
+            c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = L.total; c.ok = true;
+            return c;
+        }
+    }
+    c.ok = false;
+    return c;
+}
+
+unsigned long long *g_cand_counter[64] = {nullptr};
+
+int env_int(const char *name, int dflt)
+{
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+template <int GROUP, int NCW>
+int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
+               const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, int32_t *scores,
+               cudaStream_t s, int dev)
+{
+    CandConfig c = cand_config<GROUP>(xy_shift, g, NCW);
+    if (!c.ok) return 0;
+    CandParams p;
+    p.masks = masks; p.n_masks = n_masks; p.planes = planes; p.g = g; p.n_targets = n_targets; p.scores = scores;
+    p.work_counter = g_cand_counter[dev];
+    p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
+    p.n_groups = (n_masks + GROUP - 1) / GROUP;
+    p.occ = occ; p.bpitch = bpitch; p.groups = groups;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    long long n_items = (long long) p.n_groups * n_targets;
+    int grid = (int) std::min<long long>(n_sm, n_items);
+    void (*kern)(const CandParams) = nullptr;
+    const int rings = xy_shift / 2;
+    if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW>;
+    else if (rings == 1) kern = pixelmatch_cand_kernel<1, GROUP, NCW>;
+    else kern = pixelmatch_cand_kernel<2, GROUP, NCW>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem_bytes);
+    kern<<<grid, (NCW + 1) * 32, c.smem_bytes, s>>>(p);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Word lists.  One warp per (mask, row): the row's records are scattered into two shared-memory bitmaps (unmirrored and
+// mirrored target coordinates), whose non-zero words become the entries.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kRowWords = 64;       // W <= 2048
+
+__device__ __forceinline__ void build_row_bitmaps(const MaskDesc &md, int y, int W, bool mirror, uint32_t *bm0, uint32_t *bm1,
+                                                  uint32_t &r0, uint32_t &r1)
+{
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; k < kRowWords; k += 32) { bm0[k] = 0; bm1[k] = 0; }
+    __syncwarp();
+    r0 = __ldg(md.rowstart + y);
+    r1 = __ldg(md.rowstart + y + 1);
+    for (uint32_t i = r0 + lane; i < r1; i += 32) {
+        const int x = (int) (__ldg(&md.records[i].xy) & 0xFFFFu);
+        atomicOr(&bm0[x >> 5], 1u << (x & 31));
+        if (mirror) {
+            const int xm = W - 1 - x;
+            atomicOr(&bm1[xm >> 5], 1u << (xm & 31));
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) words_count_kernel(const MaskDesc *__restrict__ masks, int W, int H, bool mirror,
+                                                          uint32_t *__restrict__ wcount)
+{
+    __shared__ uint32_t s_bm[4][2][kRowWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * 4 + warp;
+    const int m = blockIdx.y;
+    if (y >= H) return;
+    const MaskDesc md = masks[m];
+    uint32_t r0, r1;
+    build_row_bitmaps(md, y, W, mirror, s_bm[warp][0], s_bm[warp][1], r0, r1);
+    int n = 0;
+    for (int k = lane; k < kRowWords; k += 32) n += (s_bm[warp][0][k] != 0) + (s_bm[warp][1][k] != 0);
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) wcount[(size_t) m * (H + 1) + y] = (uint32_t) n;
+}
+
+__global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restrict__ masks, int W, int H, bool mirror)
+{
+    __shared__ uint32_t s_bm[4][2][kRowWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * 4 + warp;
+    const int m = blockIdx.y;
+    if (y >= H) return;
+    const MaskDesc md = masks[m];
+    uint32_t r0, r1;
+    build_row_bitmaps(md, y, W, mirror, s_bm[warp][0], s_bm[warp][1], r0, r1);
+    uint32_t *wb = const_cast<uint32_t *>(md.words);
+    uint32_t *wm = wb + md.n_words, *wr = wm + md.n_words;
+    uint32_t out = __ldg(md.wstart + y);
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int o = 0; o < (mirror ? 2 : 1); o++) {
+        uint32_t px_before = 0;
+        for (int k0 = 0; k0 < kRowWords; k0 += 32) {
+            const int k = k0 + lane;
+            const uint32_t wbits = s_bm[warp][o][k];
+            const unsigned bal = __ballot_sync(0xffffffffu, wbits != 0);
+            const uint32_t pc = (uint32_t) __popc(wbits);
+            uint32_t incl = pc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (wbits) {
+                const uint32_t pos = out + (uint32_t) __popc(bal & lt);
+                const uint32_t before = px_before + incl - pc;          // set bits of this orientation's row before this word
+                wb[pos] = wbits;
+                wm[pos] = (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit);
+                wr[pos] = o == 0 ? r0 + before : r1 - 1u - before;
+            }
+            out += (uint32_t) __popc(bal);
+            px_before += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
+}  // namespace
+
+bool cand_kernel_supported(int xy_shift, const PlaneGeom &g)
+{
+    static const bool disabled = std::getenv("CDSGPU_DISABLE_CAND") != nullptr;
+    if (disabled) return false;
+    if (!(xy_shift == 0 || xy_shift == 2 || xy_shift == 4)) return false;
+    if (xy_shift > g.guard || xy_shift > g.pitch - g.W || xy_shift > kPrePad) return false;
+    if (g.W > 2048 || g.H > 1024) return false;
+    return cand_config<128>(xy_shift, g, 24).ok;
+}
+
+void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, uint32_t *wcount, cudaStream_t s)
+{
+    for (int m0 = 0; m0 < n_masks; m0 += 32768) {
+        int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
+        dim3 grid((H + 3) / 4, cnt);
+        words_count_kernel<<<grid, 128, 0, s>>>(masks + m0, W, H, mirror, wcount + (size_t) m0 * (H + 1));
+    }
+}
+
+void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, cudaStream_t s)
+{
+    for (int m0 = 0; m0 < n_masks; m0 += 32768) {
+        int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
+        dim3 grid((H + 3) / 4, cnt);
+        words_fill_kernel<<<grid, 128, 0, s>>>(masks + m0, W, H, mirror);
+    }
+}
+
+int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
+                           const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror,
+                           int32_t *scores, cudaStream_t s)
+{
+    (void) mirror;      // the word lists already say which orientations exist
+    if (n_masks == 0 || n_targets == 0) return 0;
+    if (!occ || !groups || bpitch != occupancy_pitch(g.W)) return 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64) return 0;
+    if (!g_cand_counter[dev]) {
+        if (cudaMalloc(&g_cand_counter[dev], sizeof(unsigned long long)) != cudaSuccess) return 0;
+    }
+    cudaMemsetAsync(g_cand_counter[dev], 0, sizeof(unsigned long long), s);
+    static const int warps_env = env_int("CDSGPU_CAND_WARPS", 24);
+    if (warps_env == 16) return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev);
+    return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev);
+}
+
+}  // namespace cds

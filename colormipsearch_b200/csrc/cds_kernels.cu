@@ -143,7 +143,12 @@ __global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restr
     for (int k = warp; k < bpitch; k += (int) (blockDim.x >> 5)) {
         const int x = k * 32 + lane;
         bool v = false;
-        if (x < g.W) v = (row[x] & (CDS_CODE_BELOW_BIT | CDS_CODE_PAD_BIT)) == 0;
+        if (x < g.W) {
+            // above the threshold, and in a colour sector: "no sector" pixels (ties for the maximum, e.g. grey) have pixel gap
+            // 10000 against everything (AbstractColorDepthSearchAlgorithm.java:182, 259-388), they can never match
+            const uint32_t cw = row[x];
+            v = (cw & (CDS_CODE_BELOW_BIT | CDS_CODE_PAD_BIT)) == 0 && ((cw >> CDS_CODE_SR_SHIFT) & 0x3FFFFu) < (uint32_t) CDS_SR_NONE;
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, v);
         if (lane == 0) out[k] = bal;
     }

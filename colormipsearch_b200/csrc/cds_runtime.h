@@ -43,6 +43,7 @@ struct cds_ctx {
     mutable std::recursive_mutex mu;
     mutable std::string err;
     cds_search_stats stats{};
+    int match_kernel = 0;      // cds_ctx_set_option("match_kernel"): 0 automatic, 1 candidate, 2 band, 3 gather
 
     cds_status fail(cds_status code, const std::string &msg) const;
     cds_status check(cudaError_t e, const char *what) const;
@@ -105,6 +106,8 @@ struct cds_maskset {
     std::vector<cds::MaskDesc *> d_descs;              // per device, rebuilt when dirty
     std::vector<cds::PaletteGroup *> d_groups;         // per device, one per CDS_PALETTE_GROUP masks
     std::vector<uint2 *> d_palettes;                   // per device, [n_groups][CDS_PALETTE_SIZE]
+    std::vector<uint32_t *> d_words;                   // per device, word lists of all masks (cds_cand.cuh)
+    std::vector<uint32_t *> d_wstart;                  // per device, [M][H+1] word-list row starts
     int n_compact_groups = 0;                          // informational
     bool descs_dirty = true;
     cds_status sync_descs();

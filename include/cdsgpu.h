@@ -86,6 +86,10 @@ int32_t    cds_ctx_num_devices(const cds_ctx *ctx);
 /* Message of the last failing call on this thread (ctx may be NULL for cds_ctx_create failures). Never NULL. */
 const char *cds_last_error(const cds_ctx *ctx);
 int32_t    cds_abi_version(void);
+/* Tuning / test switches.  "match_kernel": 0 = automatic (default), 1 = candidate kernel, 2 = band kernel, 3 = gather kernel;
+ * a kernel that does not support the search's parameters falls through to the next one.  All three compute the same
+ * scores bit for bit (tests/test_pixelmatch_gpu.py cross-checks them).  Unknown names: CDS_ERR_BAD_ARG. */
+cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t value);
 
 /* Pinned host memory for callers that want full-rate uploads (optional; any host pointer is accepted everywhere). */
 cds_status cds_host_alloc(cds_ctx *ctx, uint64_t bytes, void **out);
@@ -209,6 +213,7 @@ typedef struct cds_search_stats {
     int64_t comparisons;
     int64_t h2d_bytes;
     int64_t d2h_bytes;
+    int64_t match_kernel;        /* which match kernel the last launch used: 1 candidate, 2 band, 3 gather */
 } cds_search_stats;
 cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out);
 

@@ -52,6 +52,9 @@ def test_encode_all_16M_colours(ctx):
         assert np.array_equal(got, exp)
 
 
+BATCHED_KERNELS = ("cand", "band")     # the two batched kernels; fewer than 16 masks always take the gather kernel
+
+
 def _maskset(ctx, case_or_params, rects):
     mthr, dthr, ztol, xys, mirror = case_or_params
     return capi.MaskSet(ctx, W, H, mthr, dthr, ztol, xys, mirror, rects)
@@ -77,11 +80,13 @@ def test_golden_dense_both_kernels(ctx, fixtures):
     lib.add_rgb(np.stack([fixtures[k] for k in lm_keys]))
     extra = capi.synth_rgb_host(0, 77, 0, 18, W, H)
     masks = np.concatenate([np.stack([fixtures["em_12191"], fixtures["em_12191_FL"]]), extra])
-    for n_masks in (20, 2):
+    for n_masks, kern in ((20, "cand"), (20, "band"), (2, "auto")):
+        ctx.set_match_kernel(kern)
         ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
         sizes = ms.add_rgb(masks[:n_masks])
         assert sizes[0] == 10299 and sizes[1] == 17340
         scores, mirrored = ms.search_dense(lib)
+        assert ctx.last_stats()["match_kernel"] == {"cand": 1, "band": 2, "auto": 3}[kern]
         exp = {(0, 0): (439, 0), (0, 1): (414, 0), (1, 0): (515, 0), (1, 2): (483, 0), (0, 2): (426, 1)}
         for (m, t), (s, mir) in exp.items():
             assert (scores[m, t], mirrored[m, t]) == (s, mir), (n_masks, m, t)
@@ -91,6 +96,7 @@ def test_golden_dense_both_kernels(ctx, fixtures):
         assert np.array_equal(scores, es)
         assert np.array_equal(mirrored, em)
         ms.close()
+    ctx.set_match_kernel("auto")
     lib.close()
 
 
@@ -125,11 +131,37 @@ def test_dense_matches_oracle_on_synthetic(ctx, synth, params, n_masks):
     sizes = ms.add_rgb(masks[:n_masks])
     oms = [O.PixelMatchMask(x, mthr, mirror, dthr, ztol, xys, rects) for x in masks[:n_masks]]
     assert sizes.tolist() == [m.size for m in oms]
-    scores, mirrored = ms.search_dense(lib)
     es, em, _ = O.search_dense(oms, targets)
-    assert np.array_equal(scores, es)
-    assert np.array_equal(mirrored, em)
     assert es.max() > 200          # the embedded copies give real matches
+    for kern in (BATCHED_KERNELS if n_masks >= 16 else ("auto",)):
+        ctx.set_match_kernel(kern)
+        scores, mirrored = ms.search_dense(lib)
+        assert np.array_equal(scores, es), kern
+        assert np.array_equal(mirrored, em), kern
+        if xys <= 2:
+            assert ctx.last_stats()["match_kernel"] == {"cand": 1, "band": 2, "auto": 3}[kern]
+        elif xys == 4 and kern == "cand":
+            assert ctx.last_stats()["match_kernel"] == 1
+    ctx.set_match_kernel("auto")
+    ms.close()
+
+
+def test_wide_tolerance_uses_16_byte_records(ctx, synth):
+    """pixColorFluctuation 90 makes intervals longer than the compact palette format holds: both batched kernels fall back to
+    the 16-byte records."""
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    params = (20, 20, 0.9, 2, True)
+    ms = _maskset(ctx, params, rects)
+    ms.add_rgb(masks[:17])
+    oms = [O.PixelMatchMask(x, 20, True, 20, 0.9, 2, rects) for x in masks[:17]]
+    es, em, _ = O.search_dense(oms, targets[:20])
+    for kern in BATCHED_KERNELS:
+        ctx.set_match_kernel(kern)
+        scores, mirrored = ms.search_dense(lib)
+        assert np.array_equal(scores[:, :20], es), kern
+        assert np.array_equal(mirrored[:, :20], em), kern
+    ctx.set_match_kernel("auto")
     ms.close()
 
 
@@ -213,15 +245,17 @@ def test_small_and_odd_image_sizes(ctx, shape):
     lib.add_rgb(targets)
     for params in ((20, 20, 0.02, 2, True), (20, 20, 0.02, 0, True), (20, 20, 0.02, 4, False)):
         mthr, dthr, ztol, xys, mirror = params
-        for n in (18, 2):
+        for n, kern in ((18, "cand"), (18, "band"), (2, "auto")):
+            ctx.set_match_kernel(kern)
             ms = capi.MaskSet(ctx, w, h, mthr, dthr, ztol, xys, mirror, rects)
             ms.add_rgb(masks[:n])
             oms = [O.PixelMatchMask(x, mthr, mirror, dthr, ztol, xys, rects) for x in masks[:n]]
             scores, mirrored = ms.search_dense(lib)
             es, em, _ = O.search_dense(oms, targets)
-            assert np.array_equal(scores, es), (shape, params, n)
-            assert np.array_equal(mirrored, em), (shape, params, n)
+            assert np.array_equal(scores, es), (shape, params, n, kern)
+            assert np.array_equal(mirrored, em), (shape, params, n, kern)
             ms.close()
+    ctx.set_match_kernel("auto")
     lib.close()
 
 
