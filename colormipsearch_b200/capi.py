@@ -82,6 +82,7 @@ SIGNATURES = {
     "cds_maskset_get_mask_sizes": (C.c_int32, [_vp, _i32p]),
     "cds_search_dense": (C.c_int32, [_vp, _vp, _vp, _i32p, _u8p]),
     "cds_search_topk": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_double, _i32p, _i64p, _u8p, _i32p]),
+    "cds_search_stream_rgb": (C.c_int32, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_double, _i32p, _i64p, _u8p, _i32p]),
     "cds_score_pair_rgb": (C.c_int32, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
     "cds_shape_maskset_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Rect), C.c_int32, _vp, C.POINTER(_vp)]),
     "cds_shape_maskset_destroy": (None, [_vp]),
@@ -341,6 +342,24 @@ class MaskSet:
         _check(lib().cds_search_topk(self.ctx.h, self.h, library.h, int(k), float(pct_positive_pixels),
                                      score.ctypes.data_as(_i32p), target.ctypes.data_as(_i64p),
                                      mirrored.ctypes.data_as(_u8p), count.ctypes.data_as(_i32p)), self.ctx.h)
+        return score, target, mirrored, count
+
+    def search_stream(self, targets_rgb, k, pct_positive_pixels=0.0, n=None):
+        """cds_search_stream_rgb.  targets_rgb: a uint8 array [n][H][W][3], or a ctypes pointer together with n."""
+        if n is None:
+            targets_rgb = np.ascontiguousarray(targets_rgb, dtype=np.uint8)
+            n = targets_rgb.shape[0] if targets_rgb.ndim == 4 else 1
+            ptr = _ptr(targets_rgb)
+        else:
+            ptr = targets_rgb
+        M = len(self)
+        score = np.zeros((M, k), np.int32)
+        target = np.full((M, k), -1, np.int64)
+        mirrored = np.zeros((M, k), np.uint8)
+        count = np.zeros(M, np.int32)
+        _check(lib().cds_search_stream_rgb(self.ctx.h, self.h, ptr, int(n), int(k), float(pct_positive_pixels),
+                                           score.ctypes.data_as(_i32p), target.ctypes.data_as(_i64p),
+                                           mirrored.ctypes.data_as(_u8p), count.ctypes.data_as(_i32p)), self.ctx.h)
         return score, target, mirrored, count
 
     def score_pair(self, mask_index, target_rgb):

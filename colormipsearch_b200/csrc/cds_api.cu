@@ -165,6 +165,7 @@ extern "C" void cds_ctx_destroy(cds_ctx *ctx)
         if (d.staging) cudaFree(d.staging);
         for (int i = 0; i < 4; i++) if (d.scratch[i]) cudaFree(d.scratch[i]);
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
+        d.sb.release();
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev2) cudaEventDestroy(d.ev2);
@@ -204,6 +205,11 @@ extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t
         ctx->match_kernel = (int) value;
         return CDS_OK;
     }
+    if (std::strcmp(name, "stream_chunk") == 0) {
+        if (value < 1 || value > 65536) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk must be 1..65536");
+        ctx->stream_chunk = value;
+        return CDS_OK;
+    }
     return ctx->fail(CDS_ERR_BAD_ARG, std::string("cds_ctx_set_option: unknown option ") + name);
 }
 
@@ -216,7 +222,8 @@ extern "C" cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *o
 }
 
 // ------------------------------------------------------------------------------------------------------------------ library
-static int choose_pitch(int W)
+namespace cds {
+int choose_pitch(int W)
 {
     // multiple of 4 words (16-byte rows for bulk copies), at least CDS_MIN_PAD_COLS pad words, and pitch mod 32 in
     // {8, 24} so that the same column of consecutive rows falls into different shared-memory banks
@@ -224,6 +231,7 @@ static int choose_pitch(int W)
     while ((p % 32) != 8 && (p % 32) != 24) p += 4;
     return p;
 }
+}  // namespace cds
 
 int64_t cds_library::local_size(int dev) const
 {
@@ -725,16 +733,47 @@ cds_status cds_maskset::sync_descs()
 }
 
 // ------------------------------------------------------------------------------------------------------------------ searches
-namespace {
-
-struct SearchPlan {
-    bool use_band;
-};
-
-bool batched_kernel_supported(const cds_maskset *ms, const cds_library *lib)
+namespace cds {
+cds_status launch_match_view(cds_ctx *ctx, const cds_maskset *ms, const TargetView &tv, int d, int m0, int mc, int32_t *d_scores,
+                             cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1)
 {
-    return cand_kernel_supported(ms->params.xy_shift, lib->g) || band_kernel_supported(ms->params.xy_shift, lib->g);
+    const int choice = ctx->match_kernel;      // 0 = automatic, 1 = candidate, 2 = band, 3 = gather (cds_ctx_set_option)
+    const bool batched_ok = mc >= band_min_masks() && tv.occ_ready && (m0 % CDS_PALETTE_GROUP) == 0;
+    const bool cand_ok = batched_ok && (choice == 0 || choice == 1) && ms->d_words[d] && cand_kernel_supported(ms->params.xy_shift, tv.g);
+    const bool band_ok = batched_ok && choice != 3 && band_kernel_supported(ms->params.xy_shift, tv.g);
+    if (ev0) cudaEventRecord(ev0, stream);
+    if (cand_ok) {
+        int launches = launch_pixelmatch_cand(ms->d_descs[d] + m0, mc, tv.planes, tv.g, tv.n, tv.occ, tv.bpitch,
+                                              ms->d_groups[d] + m0 / CDS_PALETTE_GROUP, ms->params.xy_shift, ms->params.mirror != 0,
+                                              d_scores, stream);
+        ctx->stats.kernel_launches += launches;
+        ctx->stats.match_kernel_launches += launches;
+        ctx->stats.match_kernel = 1;
+    } else if (band_ok) {
+        int launches = launch_pixelmatch_band(ms->d_descs[d] + m0, mc, tv.planes, tv.g, tv.n, tv.occ, tv.bpitch,
+                                              ms->d_groups[d] + m0 / CDS_PALETTE_GROUP, ms->params.xy_shift, ms->params.mirror != 0,
+                                              d_scores, stream);
+        ctx->stats.kernel_launches += launches;
+        ctx->stats.match_kernel_launches += launches;
+        ctx->stats.match_kernel = 2;
+    } else {
+        launch_pixelmatch_gather(ms->d_descs[d] + m0, mc, tv.planes, tv.g, tv.n, ms->shifts, d_scores, stream);
+        int launches = (mc + 32767) / 32768;
+        ctx->stats.kernel_launches += launches;
+        ctx->stats.match_kernel_launches += launches;
+        ctx->stats.match_kernel = 3;
+    }
+    if (ev1) cudaEventRecord(ev1, stream);
+    return ctx->check(cudaGetLastError(), "pixel match kernel");
 }
+
+bool batched_kernel_supported(int xy_shift, const PlaneGeom &g)
+{
+    return cand_kernel_supported(xy_shift, g) || band_kernel_supported(xy_shift, g);
+}
+}  // namespace cds
+
+namespace {
 
 // Runs the match kernel of one device for masks [m0, m0+mc) against the device's local targets [0, n_local):
 // d_scores[(m - m0) * n_local + t] = score word.
@@ -742,36 +781,15 @@ cds_status launch_match(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, i
                         int32_t *d_scores)
 {
     DevState &ds = ctx->devs[d];
-    const int choice = ctx->match_kernel;      // 0 = automatic, 1 = candidate, 2 = band, 3 = gather (cds_ctx_set_option)
-    const bool batched_ok = mc >= band_min_masks() && lib->shards[d].occ && (m0 % CDS_PALETTE_GROUP) == 0 &&
-                            lib->shards[d].occ_done >= n_local && lib->occ_rings == ms->params.xy_shift / 2 &&
-                            lib->occ_threshold == lib->baked_threshold;
-    const bool cand_ok = batched_ok && (choice == 0 || choice == 1) && ms->d_words[d] && cand_kernel_supported(ms->params.xy_shift, lib->g);
-    const bool band_ok = batched_ok && choice != 3 && band_kernel_supported(ms->params.xy_shift, lib->g);
-    cudaEventRecord(ds.ev0, ds.stream);
-    if (cand_ok) {
-        int launches = launch_pixelmatch_cand(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local,
-                                              lib->shards[d].occ, lib->bpitch, ms->d_groups[d] + m0 / CDS_PALETTE_GROUP,
-                                              ms->params.xy_shift, ms->params.mirror != 0, d_scores, ds.stream);
-        ctx->stats.kernel_launches += launches;
-        ctx->stats.match_kernel_launches += launches;
-        ctx->stats.match_kernel = 1;
-    } else if (band_ok) {
-        ctx->stats.match_kernel = 2;
-        int launches = launch_pixelmatch_band(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local,
-                                              lib->shards[d].occ, lib->bpitch, ms->d_groups[d] + m0 / CDS_PALETTE_GROUP,
-                                              ms->params.xy_shift, ms->params.mirror != 0, d_scores, ds.stream);
-        ctx->stats.kernel_launches += launches;
-        ctx->stats.match_kernel_launches += launches;
-    } else {
-        launch_pixelmatch_gather(ms->d_descs[d] + m0, mc, lib->shards[d].planes, lib->g, n_local, ms->shifts, d_scores, ds.stream);
-        ctx->stats.match_kernel = 3;
-        int launches = (mc + 32767) / 32768;
-        ctx->stats.kernel_launches += launches;
-        ctx->stats.match_kernel_launches += launches;
-    }
-    cudaEventRecord(ds.ev1, ds.stream);
-    return ctx->check(cudaGetLastError(), "pixel match kernel");
+    TargetView tv;
+    tv.planes = lib->shards[d].planes;
+    tv.occ = lib->shards[d].occ;
+    tv.g = lib->g;
+    tv.bpitch = lib->bpitch;
+    tv.n = n_local;
+    tv.occ_ready = lib->shards[d].occ && lib->shards[d].occ_done >= n_local && lib->occ_rings == ms->params.xy_shift / 2 &&
+                   lib->occ_threshold == lib->baked_threshold;
+    return launch_match_view(ctx, ms, tv, d, m0, mc, d_scores, ds.stream, ds.ev0, ds.ev1);
 }
 
 cds_status check_search_args(cds_ctx *ctx, const cds_maskset *ms, const cds_library *lib)
@@ -806,7 +824,7 @@ extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cd
     reset_stats(ctx);
     CDS_TRY(ms->sync_descs());
     CDS_TRY(lib->bake(ms->params.data_threshold));
-    if (batched_kernel_supported(ms, lib) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
+    if (batched_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
     const int D = lib->n_dev();
     // mask chunking bounds the per-device score buffer to ~256 MiB
     std::vector<int32_t *> d_scores(D, nullptr);
@@ -863,7 +881,8 @@ extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cd
 }
 
 // smallest score s in [1, P] with ColorMIPSearch.isMatch true (API/cds/ColorMIPSearch.java:42-45); P+1 when none.
-static int32_t min_matching_score(int32_t P, double pct_positive_pixels)
+namespace cds {
+int32_t min_matching_score(int32_t P, double pct_positive_pixels)
 {
     if (P <= 0) return 1;   // empty mask scores 0 and never matches (score > 0 fails)
     const double thr = pct_positive_pixels / 100;
@@ -873,6 +892,7 @@ static int32_t min_matching_score(int32_t P, double pct_positive_pixels)
     while (a < b) { int32_t mid = a + (b - a) / 2; if (ok(mid)) b = mid; else a = mid + 1; }
     return b;
 }
+}  // namespace cds
 
 extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds_library *lib, int32_t k, double pct_positive_pixels,
                                       int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
@@ -891,7 +911,7 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
     if (T == 0) return CDS_OK;
     CDS_TRY(ms->sync_descs());
     CDS_TRY(lib->bake(ms->params.data_threshold));
-    if (batched_kernel_supported(ms, lib) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
+    if (batched_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
     const int D = lib->n_dev();
     std::vector<int32_t> min_score(M);
     for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);
@@ -928,7 +948,7 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
             st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
             if (st == CDS_OK) st = launch_match(ctx, ms, lib, d, m0, mc, nl, d_scores[d]);
             if (st == CDS_OK) {
-                launch_topk(d_scores[d], mc, nl, d_min[d] + m0, k, d_keys[d] + (size_t) m0 * k, d_counts[d] + m0, ds.stream);
+                launch_topk(d_scores[d], mc, nl, d_min[d] + m0, k, 0, d_keys[d] + (size_t) m0 * k, d_counts[d] + m0, ds.stream);
                 ctx->stats.kernel_launches++;
                 cudaEventRecord(ds.ev2, ds.stream);
                 st = ctx->check(cudaGetLastError(), "topk kernel");

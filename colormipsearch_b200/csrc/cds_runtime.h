@@ -20,6 +20,22 @@ namespace cds {
 
 constexpr int64_t kLibBlock = 64;   // targets per block of the block-cyclic device sharding
 
+// Device buffers of the streaming search (cds_search_stream_rgb), kept between calls.
+struct StreamBufs {
+    int W = 0, H = 0;
+    int64_t chunk = 0;                  // targets per chunk the buffers are sized for
+    int64_t m_cap = 0, key_cap = 0;     // masks / (masks * k) the score and key buffers are sized for
+    cudaStream_t copy_stream = nullptr;
+    uint8_t *staging[2] = {nullptr, nullptr};   // RGB chunks as uploaded (double buffered: the next upload overlaps this chunk's kernels)
+    uint32_t *planes = nullptr, *occ = nullptr, *valid = nullptr;
+    int32_t *scores = nullptr;          // [masks][chunk]
+    uint64_t *keys_chunk = nullptr, *keys_run = nullptr;
+    int32_t *counts_chunk = nullptr, *counts_run = nullptr, *min_score = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, enc_done[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> timing;    // pairs around every chunk's match kernel
+    void release();
+};
+
 struct DevState {
     int dev = -1;
     cudaStream_t stream = nullptr;
@@ -32,6 +48,7 @@ struct DevState {
     size_t h_pinned_bytes = 0;
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device scratch (scores, min scores, keys, counts)
     size_t scratch_bytes[4] = {0, 0, 0, 0};
+    StreamBufs sb;
 };
 
 void set_tls_error(const std::string &msg);
@@ -44,6 +61,7 @@ struct cds_ctx {
     mutable std::string err;
     cds_search_stats stats{};
     int match_kernel = 0;      // cds_ctx_set_option("match_kernel"): 0 automatic, 1 candidate, 2 band, 3 gather
+    int64_t stream_chunk = 256;   // cds_ctx_set_option("stream_chunk"): targets per chunk of cds_search_stream_rgb
 
     cds_status fail(cds_status code, const std::string &msg) const;
     cds_status check(cudaError_t e, const char *what) const;
@@ -115,6 +133,24 @@ struct cds_maskset {
 
 
 namespace cds {
+// What a match kernel needs to know about a run of device-resident targets (a library shard or one streamed chunk).
+struct TargetView {
+    const uint32_t *planes = nullptr;   // code planes, PlaneGeom layout
+    const uint32_t *occ = nullptr;      // occupancy bitmap for the mask set's shift set and the baked threshold
+    PlaneGeom g{};
+    int bpitch = 0;
+    int64_t n = 0;                      // targets
+    bool occ_ready = false;
+};
+// Picks and launches the match kernel for masks [m0, m0 + mc) of `ms` against `tv` on `stream`; ev0 / ev1 (may be null) are
+// recorded around it.  d_scores[(m - m0) * tv.n + t] = score word.
+cds_status launch_match_view(cds_ctx *ctx, const cds_maskset *ms, const TargetView &tv, int d, int m0, int mc, int32_t *d_scores,
+                             cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1);
+bool batched_kernel_supported(int xy_shift, const PlaneGeom &g);
+int choose_pitch(int W);
+// smallest score in [1, P] with ColorMIPSearch.isMatch true; P + 1 when none
+int32_t min_matching_score(int32_t P, double pct_positive_pixels);
+
 // Appends n images at consecutive global indices; `src` fills the device staging buffer with the RGB pixels of images
 // [i0, i0 + cnt) of the call (an H2D copy or a generator kernel) on ds.stream.
 cds_status library_append(cds_library *lib, int64_t n,

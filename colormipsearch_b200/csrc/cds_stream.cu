@@ -1,0 +1,243 @@
+// cds_stream.cu -- cds_search_stream_rgb: the batched seam of the reference,
+// ColorMIPSearchProcessor.findAllColorDepthMatches(masks, targets)
+// (colormipsearch-tools/src/main/java/org/janelia/colormipsearch/cmd/cdsprocess/ColorMIPSearchProcessor.java:8-12,
+//  LocalColorMIPSearchProcessor.java:55-116), for targets that live in HOST memory and need not stay on the device.
+//
+// Targets are cut into chunks; chunk c goes to device c mod D.  Per device two streams: the copy stream uploads chunk i+1
+// into the other half of a double-buffered staging area while the compute stream encodes chunk i into code planes, builds
+// its occupancy bitmap, runs the match kernel for ALL masks against it, selects the chunk's per-mask top-K and folds it into
+// the running per-mask lists.  The host only enqueues; it blocks once, at the end, to read the lists back and merge them
+// over the devices.  With pinned host memory the call runs at the rate of the slower of PCIe and the match kernel.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "cds_runtime.h"
+#include "cds_band.cuh"
+#include "cds_topk.cuh"
+
+using namespace cds;
+
+#define CDS_TRY(expr) do { cds_status _s = (expr); if (_s != CDS_OK) return _s; } while (0)
+#define CDS_CUDA(ctx, expr) CDS_TRY((ctx)->check((expr), #expr))
+
+void cds::StreamBufs::release()
+{
+    for (int i = 0; i < 2; i++) {
+        if (staging[i]) cudaFree(staging[i]);
+        if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
+        if (enc_done[i]) cudaEventDestroy(enc_done[i]);
+        staging[i] = nullptr; h2d_done[i] = nullptr; enc_done[i] = nullptr;
+    }
+    void *bufs[] = {planes, occ, valid, scores, keys_chunk, keys_run, counts_chunk, counts_run, min_score};
+    for (void *b : bufs) if (b) cudaFree(b);
+    planes = occ = valid = nullptr; scores = nullptr; keys_chunk = keys_run = nullptr;
+    counts_chunk = counts_run = min_score = nullptr;
+    for (cudaEvent_t e : timing) cudaEventDestroy(e);
+    timing.clear();
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    copy_stream = nullptr;
+    W = H = 0; chunk = 0; m_cap = 0; key_cap = 0;
+}
+
+namespace {
+
+cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, int bpitch, int64_t chunk, int64_t M, int64_t k)
+{
+    StreamBufs &sb = ds.sb;
+    CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+    if (!sb.copy_stream) {
+        CDS_CUDA(ctx, cudaStreamCreateWithFlags(&sb.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CDS_CUDA(ctx, cudaEventCreateWithFlags(&sb.h2d_done[i], cudaEventDisableTiming));
+            CDS_CUDA(ctx, cudaEventCreateWithFlags(&sb.enc_done[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t img_bytes = (size_t) g.W * g.H * 3;
+    if (sb.W != g.W || sb.H != g.H || sb.chunk < chunk) {
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        CDS_CUDA(ctx, cudaStreamSynchronize(sb.copy_stream));
+        for (int i = 0; i < 2; i++) if (sb.staging[i]) { cudaFree(sb.staging[i]); sb.staging[i] = nullptr; }
+        if (sb.planes) { cudaFree(sb.planes); sb.planes = nullptr; }
+        if (sb.occ) { cudaFree(sb.occ); sb.occ = nullptr; }
+        if (sb.valid) { cudaFree(sb.valid); sb.valid = nullptr; }
+        if (sb.scores) { cudaFree(sb.scores); sb.scores = nullptr; }
+        sb.chunk = 0; sb.m_cap = 0;
+        const size_t words = g.total_words(chunk);
+        const size_t bm_words = (size_t) chunk * g.H * bpitch;
+        for (int i = 0; i < 2; i++) CDS_CUDA(ctx, cudaMalloc(&sb.staging[i], (size_t) chunk * img_bytes + 64));
+        CDS_CUDA(ctx, cudaMalloc(&sb.planes, words * sizeof(uint32_t)));
+        CDS_CUDA(ctx, cudaMalloc(&sb.occ, bm_words * sizeof(uint32_t)));
+        CDS_CUDA(ctx, cudaMalloc(&sb.valid, bm_words * sizeof(uint32_t)));
+        launch_fill_words(sb.planes, words, CDS_CODE_PAD_WORD, ds.stream);      // guard rows stay pad words for ever
+        CDS_CUDA(ctx, cudaGetLastError());
+        sb.W = g.W; sb.H = g.H; sb.chunk = chunk;
+    }
+    if (sb.m_cap < M) {
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        if (sb.scores) cudaFree(sb.scores);
+        if (sb.counts_chunk) cudaFree(sb.counts_chunk);
+        if (sb.counts_run) cudaFree(sb.counts_run);
+        if (sb.min_score) cudaFree(sb.min_score);
+        sb.scores = nullptr; sb.counts_chunk = sb.counts_run = sb.min_score = nullptr; sb.m_cap = 0;
+        CDS_CUDA(ctx, cudaMalloc(&sb.scores, (size_t) M * sb.chunk * sizeof(int32_t)));
+        CDS_CUDA(ctx, cudaMalloc(&sb.counts_chunk, (size_t) M * sizeof(int32_t)));
+        CDS_CUDA(ctx, cudaMalloc(&sb.counts_run, (size_t) M * sizeof(int32_t)));
+        CDS_CUDA(ctx, cudaMalloc(&sb.min_score, (size_t) M * sizeof(int32_t)));
+        sb.m_cap = M;
+    }
+    if (sb.key_cap < M * k) {
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        if (sb.keys_chunk) cudaFree(sb.keys_chunk);
+        if (sb.keys_run) cudaFree(sb.keys_run);
+        sb.keys_chunk = sb.keys_run = nullptr; sb.key_cap = 0;
+        CDS_CUDA(ctx, cudaMalloc(&sb.keys_chunk, (size_t) M * k * sizeof(uint64_t)));
+        CDS_CUDA(ctx, cudaMalloc(&sb.keys_run, (size_t) M * k * sizeof(uint64_t)));
+        sb.key_cap = M * k;
+    }
+    return CDS_OK;
+}
+
+}  // namespace
+
+extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms_c, const uint8_t *targets_rgb, int64_t n_targets,
+                                            int32_t k, double pct_positive_pixels,
+                                            int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
+{
+    if (!ctx || !ms_c) { set_tls_error("cds_search_stream_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
+    if (ms->ctx != ctx) return ctx->fail(CDS_ERR_BAD_ARG, "mask set belongs to another context");
+    if (k <= 0 || k > topk_max_k()) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: k must be in 1..4096");
+    if (n_targets < 0 || (n_targets > 0 && !targets_rgb)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: bad target array");
+    const int M = (int) ms->sizes.size();
+    if (M == 0) return CDS_OK;
+    if (!out_score || !out_target || !out_count) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: NULL output");
+    ctx->stats = cds_search_stats{};
+    for (int m = 0; m < M; m++) out_count[m] = 0;
+    if (n_targets == 0) return CDS_OK;
+    CDS_TRY(ms->sync_descs());
+
+    const int D = (int) ctx->devs.size();
+    PlaneGeom g;
+    g.W = ms->W; g.H = ms->H; g.pitch = choose_pitch(ms->W); g.guard = CDS_GUARD_ROWS;
+    const int bpitch = occupancy_pitch(g.W);
+    const size_t img_bytes = (size_t) g.W * g.H * 3;
+    const int64_t chunk = std::min<int64_t>(ctx->stream_chunk, n_targets);
+    const int64_t n_chunks = (n_targets + chunk - 1) / chunk;
+    const int thr = ms->params.data_threshold;
+    const int rings = ms->params.xy_shift / 2;
+    const bool want_occ = batched_kernel_supported(ms->params.xy_shift, g) && M >= band_min_masks();
+
+    std::vector<int32_t> min_score(M);
+    for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);
+    const int used_devs = (int) std::min<int64_t>(D, n_chunks);
+    for (int d = 0; d < used_devs; d++) {
+        DevState &ds = ctx->devs[d];
+        CDS_TRY(ensure_stream_bufs(ctx, ds, g, bpitch, chunk, M, k));
+        CDS_CUDA(ctx, cudaMemcpyAsync(ds.sb.min_score, min_score.data(), (size_t) M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream));
+        CDS_CUDA(ctx, cudaMemsetAsync(ds.sb.counts_run, 0, (size_t) M * sizeof(int32_t), ds.stream));
+        CDS_CUDA(ctx, cudaEventRecord(ds.ev0, ds.stream));
+        const size_t need = (size_t) 2 * ((n_chunks + D - 1) / D);
+        while (ds.sb.timing.size() < need) {
+            cudaEvent_t e;
+            CDS_CUDA(ctx, cudaEventCreate(&e));
+            ds.sb.timing.push_back(e);
+        }
+    }
+
+    // enqueue every chunk; nothing below blocks the host when the source is pinned memory
+    std::vector<int64_t> per_dev(D, 0);
+    for (int64_t c = 0; c < n_chunks; c++) {
+        const int d = (int) (c % D);
+        DevState &ds = ctx->devs[d];
+        StreamBufs &sb = ds.sb;
+        const int64_t j = per_dev[d]++;
+        const int slot = (int) (j & 1);
+        const int64_t first = c * chunk;
+        const int64_t cnt = std::min<int64_t>(chunk, n_targets - first);
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
+        CDS_CUDA(ctx, cudaMemcpyAsync(sb.staging[slot], targets_rgb + (size_t) first * img_bytes, (size_t) cnt * img_bytes,
+                                     cudaMemcpyHostToDevice, sb.copy_stream));
+        ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
+        CDS_CUDA(ctx, cudaEventRecord(sb.h2d_done[slot], sb.copy_stream));
+        CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
+        launch_encode_rgb(sb.staging[slot], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream);
+        CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ds.stream));
+        ctx->stats.kernel_launches++;
+        TargetView tv;
+        tv.planes = sb.planes; tv.g = g; tv.bpitch = bpitch; tv.n = cnt; tv.occ = nullptr; tv.occ_ready = false;
+        if (want_occ) {
+            launch_occupancy(sb.planes, g, 0, cnt, rings, bpitch, sb.valid, sb.occ, ds.stream);
+            ctx->stats.kernel_launches += 2;
+            tv.occ = sb.occ;
+            tv.occ_ready = true;
+        }
+        CDS_CUDA(ctx, cudaGetLastError());
+        CDS_TRY(launch_match_view(ctx, ms, tv, d, 0, M, sb.scores, ds.stream, sb.timing[2 * j], sb.timing[2 * j + 1]));
+        launch_topk(sb.scores, M, cnt, sb.min_score, k, first, sb.keys_chunk, sb.counts_chunk, ds.stream);
+        launch_topk_merge(sb.keys_run, sb.counts_run, sb.keys_chunk, sb.counts_chunk, M, k, ds.stream);
+        ctx->stats.kernel_launches += 2;
+        CDS_CUDA(ctx, cudaGetLastError());
+    }
+
+    // read the per-device lists back and merge them (no collective: nothing is reduced across devices)
+    const size_t keys_bytes = (size_t) M * k * sizeof(uint64_t);
+    for (int d = 0; d < used_devs; d++) {
+        DevState &ds = ctx->devs[d];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        CDS_CUDA(ctx, cudaEventRecord(ds.ev2, ds.stream));
+        CDS_TRY(ctx->ensure_pinned(ds, keys_bytes + (size_t) M * sizeof(int32_t)));
+        uint8_t *hp = (uint8_t *) ds.h_pinned;
+        CDS_CUDA(ctx, cudaMemcpyAsync(hp, ds.sb.keys_run, keys_bytes, cudaMemcpyDeviceToHost, ds.stream));
+        CDS_CUDA(ctx, cudaMemcpyAsync(hp + keys_bytes, ds.sb.counts_run, (size_t) M * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream));
+        ctx->stats.d2h_bytes += (int64_t) keys_bytes + (int64_t) M * 4;
+    }
+    double match_ms = 0, total_ms = 0;
+    for (int d = 0; d < used_devs; d++) {
+        DevState &ds = ctx->devs[d];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        float ms_f = 0;
+        double dev_match = 0;
+        for (int64_t j = 0; j < per_dev[d]; j++) {
+            cudaEventElapsedTime(&ms_f, ds.sb.timing[2 * j], ds.sb.timing[2 * j + 1]);
+            dev_match += ms_f;
+        }
+        match_ms = std::max(match_ms, dev_match);
+        cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev2);
+        total_ms = std::max(total_ms, (double) ms_f);
+    }
+    struct Item { int32_t score; int64_t target; uint8_t mir; };
+    std::vector<Item> items;
+    for (int m = 0; m < M; m++) {
+        items.clear();
+        for (int d = 0; d < used_devs; d++) {
+            const uint8_t *hp = (const uint8_t *) ctx->devs[d].h_pinned;
+            const uint64_t *keys = (const uint64_t *) hp + (size_t) m * k;
+            const int c = std::min(((const int32_t *) (hp + keys_bytes))[m], k);
+            for (int i = 0; i < c; i++) {
+                Item it;
+                topk_decode_key(keys[i], it.score, it.target, it.mir);
+                items.push_back(it);
+            }
+        }
+        if (used_devs > 1)
+            std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+                if (a.score != b.score) return a.score > b.score;
+                return a.target < b.target;
+            });
+        const int c = (int) std::min<size_t>(items.size(), (size_t) k);
+        out_count[m] = c;
+        for (int i = 0; i < c; i++) {
+            out_score[(size_t) m * k + i] = items[i].score;
+            out_target[(size_t) m * k + i] = items[i].target;
+            if (out_mirrored) out_mirrored[(size_t) m * k + i] = items[i].mir;
+        }
+    }
+    ctx->stats.match_kernel_ms = match_ms;
+    ctx->stats.total_device_ms = total_ms;
+    ctx->stats.comparisons = (int64_t) M * n_targets;
+    return CDS_OK;
+}

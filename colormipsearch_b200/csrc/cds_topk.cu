@@ -36,7 +36,7 @@ __device__ __forceinline__ int block_exclusive_scan_flags(bool flag, int *warp_t
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads) topk_kernel(const int32_t *__restrict__ scores, int64_t n_targets,
-                                                        const int32_t *__restrict__ min_score, int k,
+                                                        const int32_t *__restrict__ min_score, int k, int64_t idx_base,
                                                         uint64_t *__restrict__ keys_out, int32_t *__restrict__ counts_out)
 {
     __shared__ uint64_t s_keys[kMaxK];
@@ -52,7 +52,6 @@ __global__ void __launch_bounds__(kThreads) topk_kernel(const int32_t *__restric
     int prefix = 0;          // high bits fixed so far
     int prefix_mask = 0;
     int need = k;            // rank (1-based, from the top) still to locate inside the current prefix
-    int total_pass = 0;
     bool take_all = false;
     for (int pass = 0; pass < 3; pass++) {
         const int shift = 20 - 10 * pass;
@@ -75,12 +74,6 @@ __global__ void __launch_bounds__(kThreads) topk_kernel(const int32_t *__restric
         }
         __syncthreads();
         const int bin = s_sel_bin, above = s_sel_above;
-        if (pass == 0) {
-            int t = 0;
-            // total passing entries = sum of the first histogram (every thread computes it identically)
-            for (int b = 0; b < 1024; b++) t += s_hist[b];
-            total_pass = t;
-        }
         if (bin < 0) { take_all = true; break; }   // only possible in pass 0: fewer than k passing entries
         need -= above;
         prefix |= bin << shift;
@@ -123,18 +116,17 @@ __global__ void __launch_bounds__(kThreads) topk_kernel(const int32_t *__restric
         int eq_rank = block_exclusive_scan_flags(eq, s_warp, eq_total);
         if (gt) {
             int slot = atomicAdd(&s_gt_count, 1);
-            s_keys[slot] = topk_make_key(c, i, (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0);
+            s_keys[slot] = topk_make_key(c, idx_base + i, (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0);
         }
         if (eq) {
             int r = ties_seen + eq_rank;
-            if (r < ties_wanted && n_gt + r < k) s_keys[n_gt + r] = topk_make_key(c, i, (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0);
+            if (r < ties_wanted && n_gt + r < k) s_keys[n_gt + r] = topk_make_key(c, idx_base + i, (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0);
         }
         ties_seen += eq_total;
     }
     __syncthreads();
     int n_out = n_gt + min(ties_seen, ties_wanted);
     n_out = min(n_out, k);
-    (void) total_pass;
 
     // ---- bitonic sort of s_keys[0..n_out) (padded with the largest key)
     int n_pow2 = 1;
@@ -157,11 +149,52 @@ __global__ void __launch_bounds__(kThreads) topk_kernel(const int32_t *__restric
     if (threadIdx.x == 0) counts_out[m] = n_out;
 }
 
-void launch_topk(const int32_t *scores, int n_masks, int64_t n_targets, const int32_t *min_score, int k,
+void launch_topk(const int32_t *scores, int n_masks, int64_t n_targets, const int32_t *min_score, int k, int64_t idx_base,
                  uint64_t *keys_out, int32_t *counts_out, cudaStream_t s)
 {
     if (n_masks == 0) return;
-    topk_kernel<<<n_masks, kThreads, 0, s>>>(scores, n_targets, min_score, k, keys_out, counts_out);
+    topk_kernel<<<n_masks, kThreads, 0, s>>>(scores, n_targets, min_score, k, idx_base, keys_out, counts_out);
+}
+
+// run[m] <- the k smallest keys of run[m] U chunk[m] (both sorted ascending, keys are unique: they carry the target index).
+// One CTA per mask: merge-path ranks, no sort -- element i of one list lands at i + (number of smaller keys in the other).
+__global__ void __launch_bounds__(kThreads) topk_merge_kernel(uint64_t *__restrict__ run_keys, int32_t *__restrict__ run_counts,
+                                                              const uint64_t *__restrict__ chunk_keys,
+                                                              const int32_t *__restrict__ chunk_counts, int k)
+{
+    extern __shared__ uint64_t s_merge[];       // 2 * k keys
+    uint64_t *s_a = s_merge, *s_b = s_merge + k;
+    const int m = blockIdx.x;
+    const int na = min(run_counts[m], k), nb = min(chunk_counts[m], k);
+    if (nb == 0) return;
+    uint64_t *a = run_keys + (size_t) m * k;
+    const uint64_t *b = chunk_keys + (size_t) m * k;
+    for (int i = threadIdx.x; i < na; i += kThreads) s_a[i] = a[i];
+    for (int i = threadIdx.x; i < nb; i += kThreads) s_b[i] = b[i];
+    __syncthreads();
+    auto lower_bound = [](const uint64_t *v, int n, uint64_t key) {
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] < key) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    for (int i = threadIdx.x; i < na; i += kThreads) {
+        const int pos = i + lower_bound(s_b, nb, s_a[i]);
+        if (pos < k) a[pos] = s_a[i];
+    }
+    for (int i = threadIdx.x; i < nb; i += kThreads) {
+        const int pos = i + lower_bound(s_a, na, s_b[i]);
+        if (pos < k) a[pos] = s_b[i];
+    }
+    if (threadIdx.x == 0) run_counts[m] = min(na + nb, k);
+}
+
+void launch_topk_merge(uint64_t *run_keys, int32_t *run_counts, const uint64_t *chunk_keys, const int32_t *chunk_counts,
+                       int n_masks, int k, cudaStream_t s)
+{
+    if (n_masks == 0) return;
+    const size_t smem = (size_t) 2 * k * sizeof(uint64_t);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    topk_merge_kernel<<<n_masks, kThreads, smem, s>>>(run_keys, run_counts, chunk_keys, chunk_counts, k);
 }
 
 }  // namespace cds

@@ -24,9 +24,12 @@ inline int topk_max_k() { return 4096; }
 
 // scores: [n_masks][n_targets] score words (count | mirrored << 30).  For mask m keeps the entries with
 // count >= min_score[m], selects the k best by (count desc, index asc) and writes their keys, sorted, to
-// keys_out[m * k ..]; counts_out[m] = number written.
-void launch_topk(const int32_t *scores, int n_masks, int64_t n_targets, const int32_t *min_score, int k,
+// keys_out[m * k ..]; counts_out[m] = number written.  The index stored in a key is idx_base + column.
+void launch_topk(const int32_t *scores, int n_masks, int64_t n_targets, const int32_t *min_score, int k, int64_t idx_base,
                  uint64_t *keys_out, int32_t *counts_out, cudaStream_t s);
+// Streaming searches: folds one chunk's sorted lists into the running ones (run_keys[m * k ..], run_counts[m]).
+void launch_topk_merge(uint64_t *run_keys, int32_t *run_counts, const uint64_t *chunk_keys, const int32_t *chunk_counts,
+                       int n_masks, int k, cudaStream_t s);
 
 }  // namespace cds
 #endif

@@ -88,7 +88,8 @@ const char *cds_last_error(const cds_ctx *ctx);
 int32_t    cds_abi_version(void);
 /* Tuning / test switches.  "match_kernel": 0 = automatic (default), 1 = candidate kernel, 2 = band kernel, 3 = gather kernel;
  * a kernel that does not support the search's parameters falls through to the next one.  All three compute the same
- * scores bit for bit (tests/test_pixelmatch_gpu.py cross-checks them).  Unknown names: CDS_ERR_BAD_ARG. */
+ * scores bit for bit (tests/test_pixelmatch_gpu.py cross-checks them).
+ * "stream_chunk": targets per chunk of cds_search_stream_rgb (default 256).  Unknown names: CDS_ERR_BAD_ARG. */
 cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t value);
 
 /* Pinned host memory for callers that want full-rate uploads (optional; any host pointer is accepted everywhere). */
@@ -139,6 +140,16 @@ cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms, cds_library *li
  * the host.  out_score/out_target/out_mirrored are [M][K]; out_count[m] = entries filled for mask m (<= K). */
 cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, int32_t k, double pct_positive_pixels,
                            int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count);
+
+/* The batched seam: ColorMIPSearchProcessor.findAllColorDepthMatches(masks, targets)
+ * (TOOLS/cdsprocess/ColorMIPSearchProcessor.java:8-12, LocalColorMIPSearchProcessor.java:55-116) for targets held in HOST memory
+ * that need not stay on the devices: targets_rgb is uint8[n_targets][H][W][3]; the result is what cds_library_add_rgb of all of
+ * them followed by cds_search_topk would return (target = index into targets_rgb), but uploads, encoding and matching of
+ * successive chunks overlap, and device memory use does not grow with n_targets.  Pinned memory (cds_host_alloc) gives full
+ * PCIe rate; any host pointer works.  Image size = the mask set's. */
+cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *targets_rgb, int64_t n_targets,
+                                 int32_t k, double pct_positive_pixels,
+                                 int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count);
 
 /* One mask x one target held in host memory: the literal single-pair call of the Java API
  * (ColorDepthSearchAlgorithm.calculateMatchingScore, API/cds/ColorDepthSearchAlgorithm.java:60-61). */

@@ -185,6 +185,32 @@ def test_topk_matches_sorted_dense(ctx, synth):
     ms.close()
 
 
+@pytest.mark.parametrize("chunk", [256, 16, 7])
+def test_stream_search_equals_library_search(ctx, synth, chunk):
+    """cds_search_stream_rgb (host targets, chunked upload overlapping the search) == cds_library_add_rgb + cds_search_topk."""
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    ctx.set_option("stream_chunk", chunk)
+    for n_masks, k, pct in ((24, 300, 0.0), (24, 5, 1.0), (3, 9, 0.0)):
+        ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
+        ms.add_rgb(masks[:n_masks])
+        exp = ms.search_topk(lib, k, pct)
+        got = ms.search_stream(targets, k, pct)
+        assert np.array_equal(got[3], exp[3])
+        for m in range(n_masks):
+            c = exp[3][m]
+            for a, b in zip(got[:3], exp[:3]):
+                assert np.array_equal(a[m, :c], b[m, :c]), (chunk, n_masks, k, m)
+        ms.close()
+    # degenerate inputs
+    ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
+    ms.add_rgb(masks[:2])
+    s, t, mir, cnt = ms.search_stream(targets[:0], 4, 0.0)
+    assert cnt.tolist() == [0, 0]
+    ms.close()
+    ctx.set_option("stream_chunk", 256)
+
+
 def test_threshold_rebake_roundtrip(ctx, synth):
     masks, targets, lib = synth
     rects = O.label_rects(W, H)
