@@ -63,7 +63,7 @@ cds_status cds_ctx::ensure_scratch(DevState &d, int slot, size_t bytes, void **o
         CDS_CUDA(this, cudaMalloc(&d.scratch[slot], bytes));
         d.scratch_bytes[slot] = bytes;
     }
-    *out = d.scratch[slot];
+    if (out) *out = d.scratch[slot];
     return CDS_OK;
 }
 
@@ -474,6 +474,7 @@ extern "C" cds_status cds_maskset_create(cds_ctx *ctx, int32_t width, int32_t he
     ms->d_palettes.assign(ctx->devs.size(), nullptr);
     ms->d_words.assign(ctx->devs.size(), nullptr);
     ms->d_wstart.assign(ctx->devs.size(), nullptr);
+    ms->store.resize(ctx->devs.size());
     // build (or fetch) the interval table now so that a bad tolerance fails here
     for (DevState &ds : ctx->devs) {
         const cds_class_interval *tab;
@@ -492,11 +493,9 @@ extern "C" void cds_maskset_destroy(cds_maskset *ms)
     for (size_t d = 0; d < ctx->devs.size(); d++) {
         cudaSetDevice(ctx->devs[d].dev);
         cudaStreamSynchronize(ctx->devs[d].stream);
-        for (auto &b : ms->batches) {
-            if (d < b.records.size() && b.records[d]) cudaFree(b.records[d]);
-            if (d < b.rowstart.size() && b.rowstart[d]) cudaFree(b.rowstart[d]);
-            if (d < b.classes.size() && b.classes[d]) cudaFree(b.classes[d]);
-            if (d < b.crec.size() && b.crec[d]) cudaFree(b.crec[d]);
+        if (d < ms->store.size()) {
+            cds_maskset::DevStore &st = ms->store[d];
+            for (cds_maskset::Arena *a : {&st.records, &st.classes, &st.crec, &st.rowstart}) if (a->p) cudaFree(a->p);
         }
         if (ms->d_descs[d]) cudaFree(ms->d_descs[d]);
         if (ms->d_groups[d]) cudaFree(ms->d_groups[d]);
@@ -518,97 +517,107 @@ extern "C" cds_status cds_maskset_get_mask_sizes(const cds_maskset *ms, int32_t 
     return CDS_OK;
 }
 
+// Makes room for `used + more` bytes in a device arena; contents are preserved (device-to-device copy on growth).
+static cds_status arena_reserve(cds_ctx *ctx, DevState &ds, cds_maskset::Arena &a, size_t more)
+{
+    if (a.used + more <= a.cap) return CDS_OK;
+    size_t cap = std::max<size_t>(a.cap * 2, a.used + more);
+    cap = std::max<size_t>(cap, (size_t) 1 << 20);
+    void *np = nullptr;
+    CDS_CUDA(ctx, cudaMalloc(&np, cap));
+    if (a.p) {
+        if (a.used) CDS_CUDA(ctx, cudaMemcpyAsync(np, a.p, a.used, cudaMemcpyDeviceToDevice, ds.stream));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        cudaFree(a.p);
+    }
+    a.p = np;
+    a.cap = cap;
+    return CDS_OK;
+}
+
 extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, int32_t n, int32_t *mask_size_out)
 {
     if (!ms) { set_tls_error("cds_maskset_add_rgb: NULL mask set"); return CDS_ERR_BAD_ARG; }
     cds_ctx *ctx = ms->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (n < 0 || (!rgb && n > 0)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_rgb: bad arguments");
+    if (n == 0) return CDS_OK;
     const int D = (int) ctx->devs.size();
     const size_t img_bytes = (size_t) ms->W * ms->H * 3;
     const int H = ms->H;
     const int kChunk = 64;
     DevState &d0 = ctx->devs[0];
+    cds_maskset::DevStore &s0 = ms->store[0];
+    CDS_CUDA(ctx, cudaSetDevice(d0.dev));
+    // two staging halves: the upload of chunk i+1 is queued behind the kernels of chunk i-1, not behind those of chunk i
+    CDS_TRY(ctx->ensure_staging(d0, (size_t) 2 * kChunk * img_bytes));
+    const cds_class_interval *class_tab;
+    CDS_TRY(ctx->class_table_on(d0, ms->params.z_tolerance, &class_tab));
+    CDS_TRY(ctx->ensure_scratch(d0, 1, (size_t) kChunk * sizeof(int32_t), nullptr));
+    CDS_TRY(ctx->ensure_scratch(d0, 3, (size_t) kChunk * sizeof(uint64_t), nullptr));
+    int32_t *d_sizes = (int32_t *) d0.scratch[1];
+    uint64_t *d_off = (uint64_t *) d0.scratch[3];
+    const size_t first_mask = ms->sizes.size();
+    const size_t rec_used0 = s0.records.used, cls_used0 = s0.classes.used, crec_used0 = s0.crec.used, rs_used0 = s0.rowstart.used;
+    CDS_TRY(arena_reserve(ctx, d0, s0.rowstart, (size_t) n * (H + 1) * sizeof(uint32_t)));
     for (int i0 = 0; i0 < n; i0 += kChunk) {
         const int cnt = std::min(kChunk, n - i0);
-        CDS_CUDA(ctx, cudaSetDevice(d0.dev));
-        CDS_TRY(ctx->ensure_staging(d0, (size_t) kChunk * img_bytes));
-        const cds_class_interval *class_tab;
-        CDS_TRY(ctx->class_table_on(d0, ms->params.z_tolerance, &class_tab));
-        cds_maskset::Batch b;
-        b.n = cnt;
-        b.records.assign(D, nullptr);
-        b.rowstart.assign(D, nullptr);
-        b.classes.assign(D, nullptr);
-        b.crec.assign(D, nullptr);
-        const size_t rs_words = (size_t) cnt * (H + 1);
-        int32_t *d_sizes = nullptr;
-        uint64_t *d_off = nullptr;
-        cds_status st = CDS_OK;
-        auto cleanup = [&]() {
-            if (d_sizes) cudaFree(d_sizes);
-            if (d_off) cudaFree(d_off);
-        };
-        auto bail = [&](cds_status s) {
-            cleanup();
-            for (int d = 0; d < D; d++) {
-                cudaSetDevice(ctx->devs[d].dev);
-                if (b.records[d]) cudaFree(b.records[d]);
-                if (b.rowstart[d]) cudaFree(b.rowstart[d]);
-                if (b.classes[d]) cudaFree(b.classes[d]);
-                if (b.crec[d]) cudaFree(b.crec[d]);
-            }
-            return s;
-        };
-        if ((st = ctx->check(cudaMemcpyAsync(d0.staging, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, d0.stream), "mask upload")) != CDS_OK) return bail(st);
+        uint8_t *stage = (uint8_t *) d0.staging + (size_t) ((i0 / kChunk) & 1) * kChunk * img_bytes;
+        CDS_CUDA(ctx, cudaMemcpyAsync(stage, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, d0.stream));
         ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
-        if ((st = ctx->check(cudaMalloc(&b.rowstart[0], rs_words * sizeof(uint32_t)), "cudaMalloc(rowstart)")) != CDS_OK) return bail(st);
-        if ((st = ctx->check(cudaMalloc(&d_sizes, cnt * sizeof(int32_t)), "cudaMalloc(sizes)")) != CDS_OK) return bail(st);
-        if ((st = ctx->check(cudaMalloc(&d_off, cnt * sizeof(uint64_t)), "cudaMalloc(offsets)")) != CDS_OK) return bail(st);
-        launch_mask_count_rows((const uint8_t *) d0.staging, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, b.rowstart[0], d0.stream);
-        launch_mask_scan_rows(b.rowstart[0], cnt, H, d_sizes, d0.stream);
+        uint32_t *rowstart = (uint32_t *) ((uint8_t *) s0.rowstart.p + s0.rowstart.used);
+        launch_mask_count_rows(stage, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, rowstart, d0.stream);
+        launch_mask_scan_rows(rowstart, cnt, H, d_sizes, d0.stream);
         ctx->stats.kernel_launches += 2;
         std::vector<int32_t> sizes(cnt);
-        if ((st = ctx->check(cudaMemcpyAsync(sizes.data(), d_sizes, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d0.stream), "sizes D2H")) != CDS_OK) return bail(st);
-        if ((st = ctx->check(cudaStreamSynchronize(d0.stream), "mask count")) != CDS_OK) return bail(st);
-        b.rec_offset.resize(cnt);
+        CDS_CUDA(ctx, cudaMemcpyAsync(sizes.data(), d_sizes, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d0.stream));
+        CDS_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+        std::vector<uint64_t> off(cnt);
         uint64_t total = 0;
-        for (int i = 0; i < cnt; i++) { b.rec_offset[i] = total; total += (uint64_t) sizes[i]; }
-        b.total_records = total;
-        if ((st = ctx->check(cudaMalloc(&b.records[0], std::max<uint64_t>(total, 1) * sizeof(cds_mask_record)), "cudaMalloc(mask records)")) != CDS_OK) return bail(st);
-        if ((st = ctx->check(cudaMalloc(&b.classes[0], std::max<uint64_t>(total, 1) * sizeof(uint32_t)), "cudaMalloc(mask classes)")) != CDS_OK) return bail(st);
-        if ((st = ctx->check(cudaMalloc(&b.crec[0], std::max<uint64_t>(total, 1) * sizeof(uint32_t)), "cudaMalloc(compact records)")) != CDS_OK) return bail(st);
-        if ((st = ctx->check(cudaMemcpyAsync(d_off, b.rec_offset.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, d0.stream), "offsets H2D")) != CDS_OK) return bail(st);
-        launch_mask_write_records((const uint8_t *) d0.staging, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, b.rowstart[0], d_off,
-                                  d0.d_rank_tab, class_tab, b.records[0], b.classes[0], d0.stream);
+        const uint64_t base = s0.records.used / sizeof(cds_mask_record);      // records, classes and crec advance in lock step
+        for (int i = 0; i < cnt; i++) { off[i] = base + total; total += (uint64_t) sizes[i]; }
+        CDS_TRY(arena_reserve(ctx, d0, s0.records, total * sizeof(cds_mask_record)));
+        CDS_TRY(arena_reserve(ctx, d0, s0.classes, total * sizeof(uint32_t)));
+        CDS_TRY(arena_reserve(ctx, d0, s0.crec, total * sizeof(uint32_t)));
+        CDS_CUDA(ctx, cudaMemcpyAsync(d_off, off.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, d0.stream));
+        launch_mask_write_records(stage, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, rowstart, d_off, d0.d_rank_tab, class_tab,
+                                  (cds_mask_record *) s0.records.p, (uint32_t *) s0.classes.p, d0.stream);
         ctx->stats.kernel_launches++;
-        if ((st = ctx->check(cudaGetLastError(), "mask_write_records_kernel")) != CDS_OK) return bail(st);
-        if ((st = ctx->check(cudaStreamSynchronize(d0.stream), "mask write")) != CDS_OK) return bail(st);
-        // replicate on the other devices
-        for (int d = 1; d < D; d++) {
-            DevState &dd = ctx->devs[d];
-            if ((st = ctx->check(cudaSetDevice(dd.dev), "cudaSetDevice")) != CDS_OK) return bail(st);
-            if ((st = ctx->check(cudaMalloc(&b.rowstart[d], rs_words * sizeof(uint32_t)), "cudaMalloc(rowstart)")) != CDS_OK) return bail(st);
-            if ((st = ctx->check(cudaMalloc(&b.records[d], std::max<uint64_t>(total, 1) * sizeof(cds_mask_record)), "cudaMalloc(mask records)")) != CDS_OK) return bail(st);
-            if ((st = ctx->check(cudaMalloc(&b.classes[d], std::max<uint64_t>(total, 1) * sizeof(uint32_t)), "cudaMalloc(mask classes)")) != CDS_OK) return bail(st);
-            if ((st = ctx->check(cudaMalloc(&b.crec[d], std::max<uint64_t>(total, 1) * sizeof(uint32_t)), "cudaMalloc(compact records)")) != CDS_OK) return bail(st);
-            if (total && (st = ctx->check(cudaMemcpyPeerAsync(b.classes[d], dd.dev, b.classes[0], d0.dev, total * sizeof(uint32_t), dd.stream), "peer copy")) != CDS_OK) return bail(st);
-            if ((st = ctx->check(cudaMemcpyPeerAsync(b.rowstart[d], dd.dev, b.rowstart[0], d0.dev, rs_words * sizeof(uint32_t), dd.stream), "peer copy")) != CDS_OK) return bail(st);
-            if (total && (st = ctx->check(cudaMemcpyPeerAsync(b.records[d], dd.dev, b.records[0], d0.dev, total * sizeof(cds_mask_record), dd.stream), "peer copy")) != CDS_OK) return bail(st);
-        }
-        for (int d = 1; d < D; d++) {
-            cudaSetDevice(ctx->devs[d].dev);
-            if ((st = ctx->check(cudaStreamSynchronize(ctx->devs[d].stream), "mask replicate")) != CDS_OK) return bail(st);
-        }
-        cudaSetDevice(d0.dev);
-        cleanup();
+        CDS_CUDA(ctx, cudaGetLastError());
+        // `off` is pageable host memory: the copy above has been staged by the time cudaMemcpyAsync returns
+        s0.records.used += total * sizeof(cds_mask_record);
+        s0.classes.used += total * sizeof(uint32_t);
+        s0.crec.used += total * sizeof(uint32_t);
+        s0.rowstart.used += (size_t) cnt * (H + 1) * sizeof(uint32_t);
         for (int i = 0; i < cnt; i++) {
             ms->sizes.push_back(sizes[i]);
+            ms->rec_offset.push_back(off[i]);
             if (mask_size_out) mask_size_out[i0 + i] = sizes[i];
         }
-        ms->batches.push_back(std::move(b));
-        ms->descs_dirty = true;
     }
+    CDS_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+    // replicate the new parts on the other devices
+    for (int d = 1; d < D; d++) {
+        DevState &dd = ctx->devs[d];
+        cds_maskset::DevStore &sd = ms->store[d];
+        CDS_CUDA(ctx, cudaSetDevice(dd.dev));
+        struct Part { cds_maskset::Arena *dst; cds_maskset::Arena *src; size_t from; };
+        const Part parts[] = {{&sd.records, &s0.records, rec_used0}, {&sd.classes, &s0.classes, cls_used0},
+                              {&sd.crec, &s0.crec, crec_used0}, {&sd.rowstart, &s0.rowstart, rs_used0}};
+        for (const Part &pt : parts) {
+            const size_t more = pt.src->used - pt.from;
+            CDS_TRY(arena_reserve(ctx, dd, *pt.dst, more));
+            if (more) CDS_CUDA(ctx, cudaMemcpyPeerAsync((uint8_t *) pt.dst->p + pt.from, dd.dev, (const uint8_t *) pt.src->p + pt.from, d0.dev, more, dd.stream));
+            pt.dst->used = pt.src->used;
+        }
+    }
+    for (int d = 1; d < D; d++) {
+        CDS_CUDA(ctx, cudaSetDevice(ctx->devs[d].dev));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ctx->devs[d].stream));
+    }
+    CDS_CUDA(ctx, cudaSetDevice(d0.dev));
+    (void) first_mask;
+    ms->descs_dirty = true;
     return CDS_OK;
 }
 
@@ -627,22 +636,21 @@ cds_status cds_maskset::sync_descs()
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
         std::vector<MaskDesc> h(std::max(M, 1));
         std::vector<MaskClassRef> refs(std::max(M, 1));
-        int mi = 0;
-        for (const Batch &b : batches)
-            for (int i = 0; i < b.n; i++, mi++) {
-                h[mi].records = b.records[d] + b.rec_offset[i];
-                h[mi].rowstart = b.rowstart[d] + (size_t) i * (H + 1);
-                h[mi].crec = nullptr;
-                h[mi].words = nullptr;
-                h[mi].wstart = nullptr;
-                h[mi].P = sizes[mi];
-                h[mi].n_words = 0;
-                refs[mi].classes = b.classes[d] + b.rec_offset[i];
-                refs[mi].records = h[mi].records;
-                refs[mi].crec = b.crec[d] + b.rec_offset[i];
-                refs[mi].P = sizes[mi];
-                refs[mi].pad = 0;
-            }
+        const DevStore &sd = store[d];
+        for (int mi = 0; mi < M; mi++) {
+            h[mi].records = (const cds_mask_record *) sd.records.p + rec_offset[mi];
+            h[mi].rowstart = (const uint32_t *) sd.rowstart.p + (size_t) mi * (H + 1);
+            h[mi].crec = nullptr;
+            h[mi].words = nullptr;
+            h[mi].wstart = nullptr;
+            h[mi].P = sizes[mi];
+            h[mi].n_words = 0;
+            refs[mi].classes = (const uint32_t *) sd.classes.p + rec_offset[mi];
+            refs[mi].records = h[mi].records;
+            refs[mi].crec = (uint32_t *) sd.crec.p + rec_offset[mi];
+            refs[mi].P = sizes[mi];
+            refs[mi].pad = 0;
+        }
         if (d_descs[d]) { cudaFree(d_descs[d]); d_descs[d] = nullptr; }
         if (d_groups[d]) { cudaFree(d_groups[d]); d_groups[d] = nullptr; }
         if (d_palettes[d]) { cudaFree(d_palettes[d]); d_palettes[d] = nullptr; }

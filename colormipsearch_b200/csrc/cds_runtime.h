@@ -111,16 +111,12 @@ struct cds_maskset {
     cds::ShiftSet shifts{};
     cds::RectSet rects{};
     std::vector<int32_t> sizes;          // getQuerySize() per mask
-    struct Batch {
-        int n = 0;
-        std::vector<uint64_t> rec_offset;              // [n] record offset of each mask inside `records`
-        uint64_t total_records = 0;
-        std::vector<cds_mask_record *> records;        // per device
-        std::vector<uint32_t *> rowstart;              // per device, [n][H+1]
-        std::vector<uint32_t *> classes;               // per device, colour class of every record
-        std::vector<uint32_t *> crec;                  // per device, compact records (filled by sync_descs)
-    };
-    std::vector<Batch> batches;
+    // Growable device arenas, one set per device (identical contents: masks are replicated).  Records, colour classes and
+    // compact records of all masks are contiguous in the order the masks were added; rowstart is [M][H+1].
+    struct Arena { void *p = nullptr; size_t cap = 0, used = 0; };     // bytes
+    struct DevStore { Arena records, classes, crec, rowstart; };
+    std::vector<DevStore> store;                       // per device
+    std::vector<uint64_t> rec_offset;                  // [M] index of each mask's first record inside the arenas
     std::vector<cds::MaskDesc *> d_descs;              // per device, rebuilt when dirty
     std::vector<cds::PaletteGroup *> d_groups;         // per device, one per CDS_PALETTE_GROUP masks
     std::vector<uint2 *> d_palettes;                   // per device, [n_groups][CDS_PALETTE_SIZE]
