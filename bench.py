@@ -152,8 +152,15 @@ def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
     from colormipsearch_b200 import capi
     rects = label_rects()
     masks = np.concatenate([ctx.synth_rgb(0, SEED, i, min(64, n_masks - i), W, H, on_device=True) for i in range(0, n_masks, 64)])
-    targets = np.concatenate([ctx.synth_rgb(1, SEED, i, min(64, n_targets - i), W, H, on_device=True) for i in range(0, n_targets, 64)])
-    grads = ctx.synth_gradient(SEED, 0, n_targets, W, H, on_device=True)
+    # target and gradient images live in pinned host memory, like the pixel-match e2e leg
+    t_arr, t_ptr = ctx.host_alloc(n_targets * 3 * W * H)
+    g_arr, g_ptr = ctx.host_alloc(n_targets * 2 * W * H)
+    targets = t_arr.reshape(n_targets, H, W, 3)
+    grads = g_arr.view(np.uint16).reshape(n_targets, H, W)
+    for i in range(0, n_targets, 64):
+        n = min(64, n_targets - i)
+        targets[i:i + n] = ctx.synth_rgb(1, SEED, i, n, W, H, on_device=True)
+        grads[i:i + n] = ctx.synth_gradient(SEED, i, n, W, H, on_device=True)
     t0 = time.perf_counter()
     sms = capi.ShapeMaskSet(ctx, W, H, 20, True, rects)
     sms.add_rgb(masks)
@@ -206,6 +213,9 @@ def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
     except Exception as e:  # the baseline is reporting only
         out["cpu_baseline"] = {"error": str(e)}
     sms.close()
+    del targets, grads
+    ctx.host_free(t_ptr)
+    ctx.host_free(g_ptr)
     return out
 
 

@@ -23,6 +23,7 @@
 #define CDS_HOST_HPP
 
 #include <cstdint>
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <memory>
@@ -349,9 +350,7 @@ public:
         if (masks.empty() || targets.empty()) return out;
         const int W = masks[0]->width, H = masks[0]->height;
         cds_maskset *ms = nullptr;
-        cds_library *lib = nullptr;
         GpuContext::check(cds_maskset_create(gpu_->get(), W, H, &params_, &ms), gpu_->get());
-        auto cleanup = [&]() { cds_maskset_destroy(ms); if (lib) cds_library_destroy(lib); };
         try {
             std::vector<int32_t> sizes(masks.size());
             for (size_t i = 0; i < masks.size(); i++) {
@@ -359,24 +358,28 @@ public:
                 if (masks[i]->width != W || masks[i]->height != H) throw std::invalid_argument("all masks must have the same size");
                 GpuContext::check(cds_maskset_add_rgb(ms, masks[i]->bytes.data(), 1, &sizes[i]), gpu_->get());
             }
-            GpuContext::check(cds_library_create(gpu_->get(), targets[0]->width, targets[0]->height, (int64_t) targets.size(), &lib), gpu_->get());
-            for (const ImageArray *t : targets) {
-                requireRGB(*t, "target");
-                if (t->width != targets[0]->width || t->height != targets[0]->height) throw std::invalid_argument("all targets must have the same size");
-                GpuContext::check(cds_library_add_rgb(lib, t->bytes.data(), 1, nullptr), gpu_->get());
+            // targets: one contiguous host buffer, streamed to the devices in chunks (upload of chunk i+1 overlaps the search of chunk i)
+            const size_t imgBytes = (size_t) W * H * 3;
+            std::vector<uint8_t> all(imgBytes * targets.size());
+            for (size_t i = 0; i < targets.size(); i++) {
+                requireRGB(*targets[i], "target");
+                if (targets[i]->width != W || targets[i]->height != H)
+                    throw std::invalid_argument("Invalid image size - target's image size must match query's image size");
+                std::copy(targets[i]->bytes.begin(), targets[i]->bytes.end(), all.begin() + i * imgBytes);
             }
             const int K = std::max(1, std::min<int>(maxPerMask, (int) targets.size()));
             std::vector<int32_t> score((size_t) masks.size() * K), count(masks.size());
             std::vector<int64_t> target((size_t) masks.size() * K);
             std::vector<uint8_t> mir((size_t) masks.size() * K);
-            GpuContext::check(cds_search_topk(gpu_->get(), ms, lib, K, pctPositivePixels_, score.data(), target.data(), mir.data(), count.data()), gpu_->get());
+            GpuContext::check(cds_search_stream_rgb(gpu_->get(), ms, all.data(), (int64_t) targets.size(), K, pctPositivePixels_,
+                                                    score.data(), target.data(), mir.data(), count.data()), gpu_->get());
             for (size_t m = 0; m < masks.size(); m++)
                 for (int i = 0; i < count[m]; i++) {
                     const size_t o = m * K + i;
                     out.push_back({(int) m, target[o], score[o], (float) ((double) score[o] / (double) sizes[m]), mir[o] != 0});
                 }
-        } catch (...) { cleanup(); throw; }
-        cleanup();
+        } catch (...) { cds_maskset_destroy(ms); throw; }
+        cds_maskset_destroy(ms);
         return out;
     }
 };
