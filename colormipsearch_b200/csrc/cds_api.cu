@@ -725,9 +725,9 @@ cds_status cds_maskset::sync_descs()
                 h[m].wstart = d_wstart[d] + (size_t) m * (H + 1);
                 total_words += (size_t) wsizes[m];
             }
-            CDS_CUDA(ctx, cudaMalloc(&d_words[d], std::max<size_t>(total_words, 1) * 3 * sizeof(uint32_t)));
+            CDS_CUDA(ctx, cudaMalloc(&d_words[d], std::max<size_t>(total_words, 1) * 4 * sizeof(uint32_t)));
             size_t off = 0;
-            for (int m = 0; m < M; m++) { h[m].words = d_words[d] + 3 * off; off += (size_t) wsizes[m]; }
+            for (int m = 0; m < M; m++) { h[m].words = d_words[d] + 4 * off; off += (size_t) wsizes[m]; }
             CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
             launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, ds.stream);
             ctx->stats.kernel_launches++;

@@ -30,7 +30,6 @@ namespace {
 constexpr int kStages = 2;
 constexpr int kMaxBands = 128;
 constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy destination aligned)
-constexpr int kChunk = 256;         // word-list entries per ticket
 constexpr int kQueue = 64;          // candidate slots per warp (power of two, >= 2 * 32)
 constexpr int kWordQueue = 64;      // word slots per warp (power of two, >= 2 * 32)
 
@@ -67,16 +66,20 @@ __device__ __forceinline__ void offset_of(int v, int &dx, int &dy)
     dy = (k % 3 - 1) * 4;
 }
 
-// cnt += inc when the code word c lies in [lo1, lo1+len1] or [lo2, lo2+len2]
-__device__ __forceinline__ void count_hit(uint32_t &cnt, uint32_t c, uint32_t lo1, uint32_t len1, uint32_t lo2, uint32_t len2, uint32_t inc)
+// acc[OFF / 4] += 1 (shared memory, predicated reduction) when the code word c lies in [lo1, lo1+len1] or [lo2, lo2+len2].
+// Matches are rare (a few per hundred evaluations), so nearly all of these reductions are predicated off.
+template <int OFF>
+__device__ __forceinline__ void count_hit(uint32_t acc, uint32_t c, uint32_t lo1, uint32_t len1, uint32_t lo2, uint32_t len2)
 {
-    asm("{\n\t.reg .pred p;\n\t.reg .u32 a, b;\n\t"
-        "sub.u32 a, %1, %2;\n\t"
-        "sub.u32 b, %1, %4;\n\t"
-        "setp.le.u32 p, a, %3;\n\t"
-        "setp.le.or.u32 p, b, %5, p;\n\t"
-        "@p add.u32 %0, %0, %6;\n\t}"
-        : "+r"(cnt) : "r"(c), "r"(lo1), "r"(len1), "r"(lo2), "r"(len2), "r"(inc));
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 a, b;\n\t"
+                 "sub.u32 a, %1, %2;\n\t"
+                 "sub.u32 b, %1, %4;\n\t"
+                 "setp.le.u32 p, a, %3;\n\t"
+                 "setp.le.or.u32 p, b, %5, p;\n\t"
+                 "@p red.shared.add.u32 [%0+%6], 1;\n\t}"
+                 :: "r"(acc), "r"(c), "r"(lo1), "r"(len1), "r"(lo2), "r"(len2), "n"(OFF));
+    // no "memory" clobber on purpose: the band reads around it may be scheduled freely; the accumulators are only read after a
+    // named barrier (itself a volatile asm with a memory clobber), and volatile asms keep their order
 }
 
 template <int GROUP>
@@ -103,19 +106,49 @@ struct CandSmem {
     }
 };
 
-// The evaluations of 32 queued candidates: one per lane.  cand.x = x | y << 11 | orientation << 21 (target coordinates),
-// cand.y = record index inside the mask.
+// The evaluations of 32 queued candidates: one per lane.
+// cand.x = x | y << 11 | orientation << 21 | mask (inside the group) << 22, in target coordinates; cand.y = record index inside the mask.
+template <int NRINGS, int V>
+struct EvalUnroll {
+    static __device__ __forceinline__ void load(const uint32_t *pc, int pitch, uint32_t (&cw)[Offsets<NRINGS>::N])
+    {
+        int dx, dy;
+        offset_of<NRINGS>(V, dx, dy);
+        cw[V] = pc[dy * pitch + dx];
+        EvalUnroll<NRINGS, V + 1>::load(pc, pitch, cw);
+    }
+    static __device__ __forceinline__ void count(const uint32_t (&cw)[Offsets<NRINGS>::N], uint32_t acc, uint32_t lo1, uint32_t len1,
+                                                 uint32_t lo2, uint32_t len2)
+    {
+        count_hit<4 * V>(acc, cw[V], lo1, len1, lo2, len2);
+        EvalUnroll<NRINGS, V + 1>::count(cw, acc, lo1, len1, lo2, len2);
+    }
+};
+template <int NRINGS>
+struct EvalUnroll<NRINGS, Offsets<NRINGS>::N> {
+    static __device__ __forceinline__ void load(const uint32_t *, int, uint32_t (&)[Offsets<NRINGS>::N]) {}
+    static __device__ __forceinline__ void count(const uint32_t (&)[Offsets<NRINGS>::N], uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
+};
+
+// First half of an evaluation: the candidate's palette index, read from the mask's compact records (an L2 access whose
+// latency the caller hides behind the evaluation of the previous batch).
+template <bool COMPACT>
+__device__ __forceinline__ uint32_t fetch_palette_index(uint2 cand, bool live, const void *const *__restrict__ s_rptr)
+{
+    uint32_t pi = CDS_PALETTE_SIZE - 1;                                         // the never-matching entry
+    if (COMPACT && live) pi = __ldg(static_cast<const uint32_t *>(s_rptr[(cand.x >> 22) & 127u]) + cand.y) >> 21;
+    return pi;
+}
+
 template <int NRINGS, bool COMPACT>
-__device__ __forceinline__ void eval_candidates(uint2 cand, bool live, const uint32_t *__restrict__ band, int y0, int pitch,
-                                                const void *__restrict__ recs, const uint2 *__restrict__ s_pal,
-                                                uint32_t (&cnt)[Offsets<NRINGS>::N])
+__device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pi, bool live, const uint32_t *__restrict__ band, int y0, int pitch,
+                                                const void *const *__restrict__ s_rptr, const uint2 *__restrict__ s_pal, uint32_t acc_base)
 {
     constexpr int NS = Offsets<NRINGS>::N;
     constexpr int S = 2 * NRINGS;
+    const uint32_t mi = (cand.x >> 22) & 127u;
     uint32_t lo1, len1, lo2, len2;
     if (COMPACT) {
-        uint32_t pi = CDS_PALETTE_SIZE - 1;                                     // the never-matching entry
-        if (live) pi = __ldg(static_cast<const uint32_t *>(recs) + cand.y) >> 21;
         const uint2 pe = s_pal[pi];
         lo1 = (pe.x & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
         len1 = ((pe.x >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
@@ -123,7 +156,7 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, bool live, const uin
         len2 = ((pe.y >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
     } else {
         uint4 r = make_uint4(0u, CDS_EMPTY_LO, CDS_EMPTY_LO, 0u);
-        if (live) r = __ldg(reinterpret_cast<const uint4 *>(static_cast<const cds_mask_record *>(recs) + cand.y));
+        if (live) r = __ldg(reinterpret_cast<const uint4 *>(static_cast<const cds_mask_record *>(s_rptr[mi]) + cand.y));
         lo1 = r.y;
         lo2 = r.z;
         len1 = ((r.w & 0xFFFFu) << CDS_CODE_SR_SHIFT) | 0xFFu;
@@ -131,17 +164,16 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, bool live, const uin
     }
     const int x = (int) (cand.x & 0x7FFu);
     const int yrel = (int) ((cand.x >> 11) & 0x3FFu) - y0;
-    const uint32_t inc = (cand.x & (1u << 21)) ? 0x10000u : 1u;
+    const uint32_t orient = (cand.x >> 21) & 1u;
     const uint32_t *pc = band + (yrel + S) * pitch + x;
-#pragma unroll
-    for (int v = 0; v < NS; v++) {
-        int dx, dy;
-        offset_of<NRINGS>(v, dx, dy);
-        count_hit(cnt[v], pc[dy * pitch + dx], lo1, len1, lo2, len2, inc);
-    }
+    // accumulators of this mask: [0, NS) unmirrored, [NS, 2 NS) mirrored
+    const uint32_t acc = acc_base + (mi * 2u * NS + orient * NS) * 4u;
+    uint32_t cw[NS];
+    EvalUnroll<NRINGS, 0>::load(pc, pitch, cw);          // all shifted reads first, then the compares
+    EvalUnroll<NRINGS, 0>::count(cw, acc, lo1, len1, lo2, len2);
 }
 
-template <int NRINGS, int GROUP, int NCW>
+template <int NRINGS, int GROUP, int NCW, int kChunk>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(const CandParams p)
 {
     constexpr int NS = Offsets<NRINGS>::N;            // shift offsets = variants per orientation
@@ -160,7 +192,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint4 *s_wqueue = reinterpret_cast<uint4 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] words with candidates
     const uint32_t **s_wptr = reinterpret_cast<const uint32_t **>(smem_raw + L.wptr_off);// word lists
     const void **s_rptr = reinterpret_cast<const void **>(smem_raw + L.rptr_off);        // record arrays (compact or 16-byte)
-    uint32_t *s_wcnt = reinterpret_cast<uint32_t *>(smem_raw + L.wcnt_off);              // word-list lengths
     int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
     uint2 *s_bseg = reinterpret_cast<uint2 *>(smem_raw + L.bseg_off);                   // [kStages][GROUP] word range of each mask in the staged band
     uint16_t *s_btick = reinterpret_cast<uint16_t *>(smem_raw + L.btick_off);           // [kStages][GROUP + 1] ticket prefix sums of the staged band
@@ -273,6 +304,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint2 *myq = s_queue + warp * kQueue;
     uint4 *mywq = s_wqueue + warp * kWordQueue;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t acc_base = smem_u32(s_acc);
     for (;;) {
         mbar_wait(smem_u32(s_full + (q & 1)), (q >> 1) & 1);
         const long long w = *reinterpret_cast<volatile long long *>(s_item + (iseq & 1));
@@ -289,7 +321,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             for (int i = tid; i < mb; i += NCT) {
                 const MaskDesc md = p.masks[m0 + i];
                 s_wptr[i] = md.words;
-                s_wcnt[i] = (uint32_t) md.n_words;
                 s_rptr[i] = compact ? (const void *) md.crec : (const void *) md.records;
             }
             if (compact) {
@@ -310,6 +341,52 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const uint2 *bseg = s_bseg + stage * GROUP;
             const int n_tickets = tick[GROUP];
 
+            uint32_t qh = 0, qt = 0;            // candidate queue head / tail (free running, slot = index & (kQueue - 1))
+            uint32_t wh = 0, wt = 0;            // word queue head / tail
+            // Both queues live for the whole band: words and candidates of different masks mix freely (they carry the mask's
+            // index), so only the LAST batch of a band runs on a partly filled warp.
+
+            // Peels the set bits of 32 queued words (one word per lane; `c` = 0 for idle lanes) into the candidate queue,
+            // lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
+            // A full batch of candidates: start its palette-index loads, evaluate the batch submitted before it.
+            uint2 pend_cand = make_uint2(0u, 0u);
+            uint32_t pend_pi = 0;
+            bool pend = false, pend_live = false;
+            auto run_pending = [&]() {
+                if (compact) eval_candidates<NRINGS, true>(pend_cand, pend_pi, pend_live, band, y0, pitch, s_rptr, s_pal, acc_base);
+                else eval_candidates<NRINGS, false>(pend_cand, pend_pi, pend_live, band, y0, pitch, s_rptr, s_pal, acc_base);
+            };
+            auto submit = [&](uint2 cand, bool live) {
+                const uint32_t pi = compact ? fetch_palette_index<true>(cand, live, s_rptr) : fetch_palette_index<false>(cand, live, s_rptr);
+                if (pend) run_pending();
+                pend_cand = cand; pend_pi = pi; pend_live = live; pend = true;
+            };
+            auto peel = [&](uint4 we) {
+                uint32_t c = we.x;
+                const uint32_t base = we.y, rec = we.z, wbits = we.w;
+                const bool mirrored = (base >> 21) & 1u;
+                unsigned bal = __ballot_sync(0xffffffffu, c != 0);
+                while (bal) {
+                    if (c) {
+                        const int bit = __ffs((int) c) - 1;
+                        const uint32_t k = (uint32_t) __popc(wbits & ((1u << bit) - 1u));
+                        uint2 cand;
+                        cand.x = base | (uint32_t) bit;
+                        cand.y = mirrored ? rec - k : rec + k;
+                        myq[(qt + (uint32_t) __popc(bal & lt_mask)) & (kQueue - 1)] = cand;
+                        c &= c - 1;
+                    }
+                    qt += (uint32_t) __popc(bal);
+                    if (qt - qh >= 32) {
+                        __syncwarp();
+                        const uint2 cand = myq[(qh + lane) & (kQueue - 1)];
+                        qh += 32;
+                        submit(cand, true);
+                    }
+                    bal = __ballot_sync(0xffffffffu, c != 0);
+                }
+            };
+
             for (;;) {
                 int tk = 0;
                 if (lane == 0) tk = atomicAdd(&s_next[stage], 1);
@@ -323,70 +400,38 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 const uint2 sg = bseg[mi];
                 const uint32_t seg0 = sg.x + (uint32_t) (tk - tick[mi]) * kChunk;
                 const uint32_t seg1 = min(seg0 + kChunk, sg.y);
-                const uint32_t *wb = s_wptr[mi];
-                const uint32_t nw = s_wcnt[mi];
-                const uint32_t *wm = wb + nw, *wr = wm + nw;
-                const void *recs = s_rptr[mi];
-                uint32_t cnt[NS];
-#pragma unroll
-                for (int j = 0; j < NS; j++) cnt[j] = 0;
-                uint32_t qh = 0, qt = 0;            // candidate queue head / tail (free running, slot = index & (kQueue - 1))
-                uint32_t wh = 0, wt = 0;            // word queue head / tail
+                const uint4 *wl = reinterpret_cast<const uint4 *>(s_wptr[mi]);
+                const uint32_t mtag = (uint32_t) mi << 22;
 
-                // Peels the set bits of 32 queued words (one word per lane; `c` = 0 for idle lanes) into the candidate queue,
-                // lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
-                auto peel = [&](uint4 we) {
-                    uint32_t c = we.x;
-                    const uint32_t base = we.y, rec = we.z, wbits = we.w;
-                    const bool mirrored = (base >> 21) & 1u;
-                    unsigned bal = __ballot_sync(0xffffffffu, c != 0);
-                    while (bal) {
-                        if (c) {
-                            const int bit = __ffs((int) c) - 1;
-                            const uint32_t k = (uint32_t) __popc(wbits & ((1u << bit) - 1u));
-                            uint2 cand;
-                            cand.x = base | (uint32_t) bit;
-                            cand.y = mirrored ? rec - k : rec + k;
-                            myq[(qt + (uint32_t) __popc(bal & lt_mask)) & (kQueue - 1)] = cand;
-                            c &= c - 1;
-                        }
-                        qt += (uint32_t) __popc(bal);
-                        if (qt - qh >= 32) {
-                            __syncwarp();
-                            const uint2 cand = myq[(qh + lane) & (kQueue - 1)];
-                            if (compact) eval_candidates<NRINGS, true>(cand, true, band, y0, pitch, recs, s_pal, cnt);
-                            else eval_candidates<NRINGS, false>(cand, true, band, y0, pitch, recs, s_pal, cnt);
-                            qh += 32;
-                        }
-                        bal = __ballot_sync(0xffffffffu, c != 0);
-                    }
-                };
-
-                // word entries are prefetched two iterations ahead; lanes past the end carry an empty word on a valid row
-                const uint32_t idle_meta = (uint32_t) y0;
-                uint32_t b0 = 0, e0 = idle_meta, r0 = 0, b1 = 0, e1 = idle_meta, r1 = 0;
+                // word entries {bits, meta, rec, -} are prefetched three iterations ahead; lanes past the end carry an empty
+                // word on a valid row
+                const uint4 idle = make_uint4(0u, (uint32_t) y0, 0u, 0u);
+                uint4 w0 = idle, w1 = idle, w2 = idle;
                 {
                     uint32_t i = seg0 + lane;
-                    if (i < seg1) { b0 = __ldg(wb + i); e0 = __ldg(wm + i); r0 = __ldg(wr + i); }
+                    if (i < seg1) w0 = __ldg(wl + i);
                     i += 32;
-                    if (i < seg1) { b1 = __ldg(wb + i); e1 = __ldg(wm + i); r1 = __ldg(wr + i); }
+                    if (i < seg1) w1 = __ldg(wl + i);
+                    i += 32;
+                    if (i < seg1) w2 = __ldg(wl + i);
                 }
                 for (uint32_t base = seg0; base < seg1; base += 32) {
-                    const uint32_t wbits = b0, meta = e0, rec = r0;
-                    b0 = b1; e0 = e1; r0 = r1;
-                    b1 = 0; e1 = idle_meta; r1 = 0;
+                    const uint4 w = w0;
+                    w0 = w1;
+                    w1 = w2;
+                    w2 = idle;
                     {
-                        const uint32_t i = base + 64 + lane;
-                        if (i < seg1) { b1 = __ldg(wb + i); e1 = __ldg(wm + i); r1 = __ldg(wr + i); }
+                        const uint32_t i = base + 96 + lane;
+                        if (i < seg1) w2 = __ldg(wl + i);
                     }
-                    const uint32_t y = meta & ((1u << kWordMetaYBits) - 1);
-                    const uint32_t xw = (meta >> kWordMetaYBits) & 63u;
-                    const uint32_t c = wbits & bits[((int) y - y0) * p.bpitch + (int) xw];  // mask pixels of this word that can match
-                    // words with candidates are compacted first, so that the bit peeling below runs on full warps
+                    const uint32_t y = w.y & ((1u << kWordMetaYBits) - 1);
+                    const uint32_t xw = (w.y >> kWordMetaYBits) & 63u;
+                    const uint32_t c = w.x & bits[((int) y - y0) * p.bpitch + (int) xw];    // mask pixels of this word that can match
+                    // words with candidates are compacted first, so that the bit peeling runs on full warps
                     const unsigned has = __ballot_sync(0xffffffffu, c != 0);
                     if (c) {
-                        const uint32_t orient = (meta >> kWordMetaOrientBit) & 1u;
-                        mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] = make_uint4(c, (xw << 5) | (y << 11) | (orient << 21), rec, wbits);
+                        const uint32_t orient = (w.y >> kWordMetaOrientBit) & 1u;
+                        mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] = make_uint4(c, (xw << 5) | (y << 11) | (orient << 21) | mtag, w.z, w.x);
                     }
                     wt += (uint32_t) __popc(has);
                     if (wt - wh >= 32) {
@@ -396,35 +441,22 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                         peel(we);
                     }
                 }
-                // the ticket's last, partly filled batches
-                if (wt != wh) {
-                    __syncwarp();
-                    uint4 we = make_uint4(0u, 0u, 0u, 0u);
-                    if (lane < (int) (wt - wh)) we = mywq[(wh + lane) & (kWordQueue - 1)];
-                    peel(we);
-                }
-                if (qt != qh) {
-                    __syncwarp();
-                    const bool live = lane < (int) (qt - qh);
-                    uint2 cand = make_uint2((uint32_t) y0 << 11, 0u);
-                    if (live) cand = myq[(qh + lane) & (kQueue - 1)];
-                    if (compact) eval_candidates<NRINGS, true>(cand, live, band, y0, pitch, recs, s_pal, cnt);
-                    else eval_candidates<NRINGS, false>(cand, live, band, y0, pitch, recs, s_pal, cnt);
-                }
-                __syncwarp();
-                // ticket done: warp totals (a ticket has <= kChunk * 32 candidates, so the packed halves cannot carry)
-                uint32_t mine = 0;
-#pragma unroll
-                for (int j = 0; j < NS; j++) {
-                    const uint32_t tot = __reduce_add_sync(0xffffffffu, cnt[j]);
-                    if (lane == j) mine = tot;
-                }
-                if (lane < NS) {
-                    const int vn = (int) (mine & 0xFFFFu), vm = (int) (mine >> 16);
-                    if (vn) atomicAdd(&s_acc[mi * NV + lane], vn);
-                    if (vm) atomicAdd(&s_acc[mi * NV + NS + lane], vm);
-                }
             }
+            // the band's last, partly filled batches: everything queued reads this stage, so it is evaluated before the release
+            if (wt != wh) {
+                __syncwarp();
+                uint4 we = make_uint4(0u, 0u, 0u, 0u);
+                if (lane < (int) (wt - wh)) we = mywq[(wh + lane) & (kWordQueue - 1)];
+                peel(we);
+            }
+            if (qt != qh) {
+                __syncwarp();
+                const bool live = lane < (int) (qt - qh);
+                uint2 cand = make_uint2((uint32_t) y0 << 11, 0u);
+                if (live) cand = myq[(qh + lane) & (kQueue - 1)];
+                submit(cand, live);
+            }
+            if (pend) run_pending();
             // this warp is done with the stage: let the producer refill it
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(s_empty + stage));
@@ -486,7 +518,7 @@ int env_int(const char *name, int dflt)
     return e ? std::atoi(e) : dflt;
 }
 
-template <int GROUP, int NCW>
+template <int GROUP, int NCW, int kChunk>
 int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, int32_t *scores,
                cudaStream_t s, int dev)
@@ -505,9 +537,9 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     int grid = (int) std::min<long long>(n_sm, n_items);
     void (*kern)(const CandParams) = nullptr;
     const int rings = xy_shift / 2;
-    if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW>;
-    else if (rings == 1) kern = pixelmatch_cand_kernel<1, GROUP, NCW>;
-    else kern = pixelmatch_cand_kernel<2, GROUP, NCW>;
+    if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW, kChunk>;
+    else if (rings == 1) kern = pixelmatch_cand_kernel<1, GROUP, NCW, kChunk>;
+    else kern = pixelmatch_cand_kernel<2, GROUP, NCW, kChunk>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem_bytes);
     kern<<<grid, (NCW + 1) * 32, c.smem_bytes, s>>>(p);
     return 1;
@@ -565,8 +597,7 @@ __global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restr
     const MaskDesc md = masks[m];
     uint32_t r0, r1;
     build_row_bitmaps(md, y, W, mirror, s_bm[warp][0], s_bm[warp][1], r0, r1);
-    uint32_t *wb = const_cast<uint32_t *>(md.words);
-    uint32_t *wm = wb + md.n_words, *wr = wm + md.n_words;
+    uint4 *wl = reinterpret_cast<uint4 *>(const_cast<uint32_t *>(md.words));
     uint32_t out = __ldg(md.wstart + y);
     const uint32_t lt = (1u << lane) - 1u;
     for (int o = 0; o < (mirror ? 2 : 1); o++) {
@@ -585,9 +616,8 @@ __global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restr
             if (wbits) {
                 const uint32_t pos = out + (uint32_t) __popc(bal & lt);
                 const uint32_t before = px_before + incl - pc;          // set bits of this orientation's row before this word
-                wb[pos] = wbits;
-                wm[pos] = (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit);
-                wr[pos] = o == 0 ? r0 + before : r1 - 1u - before;
+                wl[pos] = make_uint4(wbits, (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit),
+                                     o == 0 ? r0 + before : r1 - 1u - before, 0u);
             }
             out += (uint32_t) __popc(bal);
             px_before += __shfl_sync(0xffffffffu, incl, 31);
@@ -639,9 +669,19 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
         if (cudaMalloc(&g_cand_counter[dev], sizeof(unsigned long long)) != cudaSuccess) return 0;
     }
     cudaMemsetAsync(g_cand_counter[dev], 0, sizeof(unsigned long long), s);
+    // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket
     static const int warps_env = env_int("CDSGPU_CAND_WARPS", 24);
-    if (warps_env == 16) return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev);
-    return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev);
+    static const int chunk_env = env_int("CDSGPU_CAND_CHUNK", 128);
+#define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<128, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev)
+    if (chunk_env == 256) {
+        if (warps_env == 16) return CDS_CAND_LAUNCH(16, 256);
+        if (warps_env == 28) return CDS_CAND_LAUNCH(28, 256);
+        return CDS_CAND_LAUNCH(24, 256);
+    }
+    if (warps_env == 16) return CDS_CAND_LAUNCH(16, 128);
+    if (warps_env == 28) return CDS_CAND_LAUNCH(28, 128);
+    return CDS_CAND_LAUNCH(24, 128);
+#undef CDS_CAND_LAUNCH
 }
 
 }  // namespace cds

@@ -30,7 +30,7 @@ struct MaskDesc {
     const cds_mask_record *records;   // P records, ascending pixel index
     const uint32_t *rowstart;         // H + 1 entries: records of image row y are [rowstart[y], rowstart[y+1])
     const uint32_t *crec;             // P compact records (cds_common.h) or nullptr when the mask's palette group is wide
-    const uint32_t *words;            // word list of the candidate kernel (cds_cand.cuh): bits[n_words], meta[n_words], rec[n_words]; or nullptr
+    const uint32_t *words;            // word list of the candidate kernel (cds_cand.cuh): n_words entries {bits, meta, rec, 0}, 16-byte aligned; or nullptr
     const uint32_t *wstart;           // H + 1 entries: word-list entries of image row y are [wstart[y], wstart[y+1])
     int P;
     int n_words;
