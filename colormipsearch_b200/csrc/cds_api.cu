@@ -165,6 +165,7 @@ extern "C" void cds_ctx_destroy(cds_ctx *ctx)
         if (d.staging) cudaFree(d.staging);
         for (int i = 0; i < 4; i++) if (d.scratch[i]) cudaFree(d.scratch[i]);
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
+        if (d.pair_plane) cudaFree(d.pair_plane);
         d.sb.release();
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
@@ -1052,7 +1053,7 @@ extern "C" cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, in
         return ctx->fail(CDS_ERR_SIZE_MISMATCH, buf);
     }
     if (!target_rgb) return ctx->fail(CDS_ERR_BAD_ARG, "cds_score_pair_rgb: target is NULL");
-    // a one-slot library on device 0 only
+    // a one-slot library on device 0, kept between calls (this is the call the reference's thread pool makes per pair)
     cds_ctx *c = ctx;
     cds_maskset *msm = const_cast<cds_maskset *>(ms);
     CDS_TRY(msm->sync_descs());
@@ -1062,14 +1063,16 @@ extern "C" cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, in
     g.W = ms->W; g.H = ms->H; g.pitch = choose_pitch(ms->W); g.guard = CDS_GUARD_ROWS;
     const size_t words = g.total_words(1);
     const size_t img_bytes = (size_t) g.W * g.H * 3;
-    uint32_t *plane = nullptr;
-    int32_t *d_score = nullptr;
     CDS_TRY(c->ensure_staging(d0, (size_t) kLibBlock * img_bytes));
-    cds_status st = c->check(cudaMalloc(&plane, words * sizeof(uint32_t) + sizeof(int32_t)), "cudaMalloc(pair plane)");
-    if (st != CDS_OK) return st;
-    d_score = (int32_t *) (plane + words);
-    launch_fill_words(plane, words, CDS_CODE_PAD_WORD, d0.stream);
-    st = c->check(cudaMemcpyAsync(d0.staging, target_rgb, img_bytes, cudaMemcpyHostToDevice, d0.stream), "pair H2D");
+    if (d0.pair_W != g.W || d0.pair_H != g.H) {
+        if (d0.pair_plane) { CDS_CUDA(c, cudaStreamSynchronize(d0.stream)); cudaFree(d0.pair_plane); d0.pair_plane = nullptr; }
+        CDS_CUDA(c, cudaMalloc(&d0.pair_plane, words * sizeof(uint32_t) + sizeof(int32_t)));
+        launch_fill_words(d0.pair_plane, words, CDS_CODE_PAD_WORD, d0.stream);     // guard rows / pad columns stay pad words
+        d0.pair_W = g.W; d0.pair_H = g.H;
+    }
+    uint32_t *plane = d0.pair_plane;
+    int32_t *d_score = (int32_t *) (plane + words);
+    cds_status st = c->check(cudaMemcpyAsync(d0.staging, target_rgb, img_bytes, cudaMemcpyHostToDevice, d0.stream), "pair H2D");
     if (st == CDS_OK) {
         launch_encode_rgb((const uint8_t *) d0.staging, 1, plane, g, 0, d0.d_rank_tab, ms->params.data_threshold, d0.stream);
         launch_pixelmatch_gather(msm->d_descs[0] + mask_index, 1, plane, g, 1, ms->shifts, d_score, d0.stream);
@@ -1078,7 +1081,6 @@ extern "C" cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, in
     int32_t w = 0;
     if (st == CDS_OK) st = c->check(cudaMemcpyAsync(&w, d_score, sizeof w, cudaMemcpyDeviceToHost, d0.stream), "pair D2H");
     if (st == CDS_OK) st = c->check(cudaStreamSynchronize(d0.stream), "pair sync");
-    cudaFree(plane);
     if (st != CDS_OK) return st;
     *score_out = w & ~CDS_SCORE_MIRROR_BIT;
     *mirrored_out = (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0;

@@ -48,6 +48,7 @@ struct CandParams {
     const uint32_t *occ;            // occupancy bitmap [n_targets][H][bpitch]
     int bpitch;
     const PaletteGroup *groups;
+    int debug_skip;                 // profiling aid (CDSGPU_CAND_NULL): consumers skip the tickets, only the band pipeline runs
 };
 
 template <int NRINGS> struct Offsets;
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 int tk = 0;
                 if (lane == 0) tk = atomicAdd(&s_next[stage], 1);
                 tk = __shfl_sync(0xffffffffu, tk, 0);
-                if (tk >= n_tickets) break;
+                if (tk >= n_tickets || p.debug_skip) break;
                 // mask of the ticket: the last mi with tick[mi] <= tk
                 int le = 0;
 #pragma unroll
@@ -531,6 +532,8 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
     p.n_groups = (n_masks + GROUP - 1) / GROUP;
     p.occ = occ; p.bpitch = bpitch; p.groups = groups;
+    static const int debug_skip = env_int("CDSGPU_CAND_NULL", 0);
+    p.debug_skip = debug_skip;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     long long n_items = (long long) p.n_groups * n_targets;

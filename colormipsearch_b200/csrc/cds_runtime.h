@@ -49,6 +49,8 @@ struct DevState {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device scratch (scores, min scores, keys, counts)
     size_t scratch_bytes[4] = {0, 0, 0, 0};
     StreamBufs sb;
+    uint32_t *pair_plane = nullptr;   // one code plane + one score word for cds_score_pair_rgb
+    int pair_W = 0, pair_H = 0;
 };
 
 void set_tls_error(const std::string &msg);
