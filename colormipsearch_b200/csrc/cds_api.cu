@@ -642,10 +642,9 @@ cds_status cds_maskset::sync_descs()
             h[mi].records = (const cds_mask_record *) sd.records.p + rec_offset[mi];
             h[mi].rowstart = (const uint32_t *) sd.rowstart.p + (size_t) mi * (H + 1);
             h[mi].crec = nullptr;
-            h[mi].words = nullptr;
             h[mi].wstart = nullptr;
             h[mi].P = sizes[mi];
-            h[mi].n_words = 0;
+            h[mi].pad = 0;
             refs[mi].classes = (const uint32_t *) sd.classes.p + rec_offset[mi];
             refs[mi].records = h[mi].records;
             refs[mi].crec = (uint32_t *) sd.crec.p + rec_offset[mi];
@@ -658,7 +657,7 @@ cds_status cds_maskset::sync_descs()
         if (d_words[d]) { cudaFree(d_words[d]); d_words[d] = nullptr; }
         if (d_wstart[d]) { cudaFree(d_wstart[d]); d_wstart[d] = nullptr; }
         std::vector<PaletteGroup> groups(std::max(n_groups, 1));
-        for (auto &g : groups) { g.palette = nullptr; g.n_pal = 0; g.pad = 0; }
+        for (auto &g : groups) { g.palette = nullptr; g.words = nullptr; g.gstart = nullptr; g.n_pal = 0; g.pad = 0; }
         if (compact_ok) {
             // palettes of the compact records: mark classes per group, number them, pack intervals, rewrite records
             const size_t slots = (size_t) n_groups * (CDS_NUM_CLASSES + 1);
@@ -703,36 +702,46 @@ cds_status cds_maskset::sync_descs()
         CDS_CUDA(ctx, cudaMalloc(&d_descs[d], h.size() * sizeof(MaskDesc)));
         CDS_CUDA(ctx, cudaMalloc(&d_groups[d], groups.size() * sizeof(PaletteGroup)));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
-        // word lists of the candidate kernel (cds_cand.cuh): count per row, scan, size the arrays, fill
+        // word lists of the candidate kernel (cds_cand.cuh): per-(mask, row) counts, per-(group, row) runs, row starts, fill
         const bool words_ok = M > 0 && W <= 2048 && H <= 1024 && (params.xy_shift == 0 || params.xy_shift == 2 || params.xy_shift == 4);
         if (words_ok) {
-            int32_t *d_wsizes = nullptr;
-            cds_status st = ctx->check(cudaMalloc(&d_wstart[d], (size_t) M * (H + 1) * sizeof(uint32_t)), "cudaMalloc(word row starts)");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_wsizes, (size_t) M * sizeof(int32_t)), "cudaMalloc(word counts)");
-            std::vector<int32_t> wsizes(M, 0);
+            uint32_t *d_grow = nullptr;
+            const size_t gs_n = (size_t) n_groups * (H + 1);
+            // d_wstart: [M][H+1] per-mask offsets followed by [n_groups][H+1] row starts
+            cds_status st = ctx->check(cudaMalloc(&d_wstart[d], ((size_t) M * (H + 1) + gs_n) * sizeof(uint32_t)), "cudaMalloc(word row starts)");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_grow, gs_n * sizeof(uint32_t)), "cudaMalloc(group rows)");
+            if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_grow, 0, gs_n * sizeof(uint32_t), ds.stream), "memset(group rows)");
+            std::vector<uint32_t> grow(gs_n, 0);
             if (st == CDS_OK) {
                 launch_words_count(d_descs[d], M, W, H, params.mirror != 0, d_wstart[d], ds.stream);
-                launch_mask_scan_rows(d_wstart[d], M, H, d_wsizes, ds.stream);
+                launch_words_group_rows(d_wstart[d], M, H, d_grow, ds.stream);
                 ctx->stats.kernel_launches += 2;
                 st = ctx->check(cudaGetLastError(), "word count kernels");
             }
-            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(wsizes.data(), d_wsizes, (size_t) M * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "word counts D2H");
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(grow.data(), d_grow, gs_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds.stream), "group rows D2H");
             if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "word count");
-            if (d_wsizes) cudaFree(d_wsizes);
+            if (d_grow) cudaFree(d_grow);
             if (st != CDS_OK) return st;
-            size_t total_words = 0;
-            for (int m = 0; m < M; m++) {
-                h[m].n_words = wsizes[m];
-                h[m].wstart = d_wstart[d] + (size_t) m * (H + 1);
-                total_words += (size_t) wsizes[m];
+            uint64_t total_words = 0;
+            for (int g = 0; g < n_groups; g++) {
+                for (int y = 0; y < H; y++) { const uint32_t c = grow[(size_t) g * (H + 1) + y]; grow[(size_t) g * (H + 1) + y] = (uint32_t) total_words; total_words += c; }
+                grow[(size_t) g * (H + 1) + H] = (uint32_t) total_words;
             }
-            CDS_CUDA(ctx, cudaMalloc(&d_words[d], std::max<size_t>(total_words, 1) * 4 * sizeof(uint32_t)));
-            size_t off = 0;
-            for (int m = 0; m < M; m++) { h[m].words = d_words[d] + 4 * off; off += (size_t) wsizes[m]; }
-            CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
-            launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, ds.stream);
-            ctx->stats.kernel_launches++;
-            CDS_CUDA(ctx, cudaGetLastError());
+            if (total_words < ((uint64_t) 1 << 32)) {
+                uint32_t *d_gstart = d_wstart[d] + (size_t) M * (H + 1);
+                CDS_CUDA(ctx, cudaMalloc(&d_words[d], std::max<uint64_t>(total_words, 1) * sizeof(uint4)));
+                CDS_CUDA(ctx, cudaMemcpyAsync(d_gstart, grow.data(), gs_n * sizeof(uint32_t), cudaMemcpyHostToDevice, ds.stream));
+                for (int m = 0; m < M; m++) h[m].wstart = d_wstart[d] + (size_t) m * (H + 1);
+                for (int g = 0; g < n_groups; g++) {
+                    groups[g].words = reinterpret_cast<const uint4 *>(d_words[d]);
+                    groups[g].gstart = d_gstart + (size_t) g * (H + 1);
+                }
+                CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
+                launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, d_gstart, reinterpret_cast<uint4 *>(d_words[d]), ds.stream);
+                ctx->stats.kernel_launches++;
+                CDS_CUDA(ctx, cudaGetLastError());
+                CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));      // `grow` is pageable memory
+            }
         }
         CDS_CUDA(ctx, cudaMemcpyAsync(d_groups[d], groups.data(), groups.size() * sizeof(PaletteGroup), cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));

@@ -85,7 +85,7 @@ __device__ __forceinline__ void count_hit(uint32_t acc, uint32_t c, uint32_t lo1
 
 template <int GROUP>
 struct CandSmem {
-    size_t stage_off, bits_off, pal_off, acc_off, bseg_off, btick_off, wptr_off, rptr_off, wcnt_off, queue_off, wqueue_off, bar_off, next_off, item_off, total;
+    size_t stage_off, bits_off, pal_off, acc_off, band_off, rptr_off, queue_off, wqueue_off, bar_off, next_off, item_off, total;
     __host__ __device__ CandSmem(int stage_words, int NS, int bits_words, int n_warps)
     {
         size_t o = 0;
@@ -94,15 +94,12 @@ struct CandSmem {
         pal_off = o;   o += (size_t) CDS_PALETTE_SIZE * 8;
         wqueue_off = o; o += (size_t) n_warps * kWordQueue * 16;
         queue_off = o; o += (size_t) n_warps * kQueue * 8;
-        wptr_off = o;  o += (size_t) GROUP * 8;
         rptr_off = o;  o += (size_t) GROUP * 8;
         bar_off = o;   o += 2 * kStages * 8;
         item_off = o;  o += 16;
         next_off = o;  o += 16;
-        wcnt_off = o;  o += (size_t) GROUP * 4;
+        band_off = o;  o += (size_t) kStages * 8;                               // per stage: {first, end} entry of the group's word list
         acc_off = o;   o += (size_t) GROUP * 2 * NS * 4;
-        bseg_off = o;  o += (size_t) kStages * GROUP * 8;                       // per stage: {first, end} word index of every mask in the band
-        btick_off = o; o += ((size_t) kStages * (GROUP + 1) * 2 + 15) / 16 * 16;  // per stage: ticket prefix sums
         total = o;
     }
 };
@@ -191,11 +188,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
     uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + L.queue_off);                  // [NCW][kQueue] candidates
     uint4 *s_wqueue = reinterpret_cast<uint4 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] words with candidates
-    const uint32_t **s_wptr = reinterpret_cast<const uint32_t **>(smem_raw + L.wptr_off);// word lists
     const void **s_rptr = reinterpret_cast<const void **>(smem_raw + L.rptr_off);        // record arrays (compact or 16-byte)
     int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
-    uint2 *s_bseg = reinterpret_cast<uint2 *>(smem_raw + L.bseg_off);                   // [kStages][GROUP] word range of each mask in the staged band
-    uint16_t *s_btick = reinterpret_cast<uint16_t *>(smem_raw + L.btick_off);           // [kStages][GROUP + 1] ticket prefix sums of the staged band
+    uint2 *s_band = reinterpret_cast<uint2 *>(smem_raw + L.band_off);                   // [kStages] range of the group's word list inside the staged band
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
     unsigned long long *s_empty = s_full + kStages;
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
@@ -219,81 +214,41 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     __syncthreads();
 
     if (warp == NCW) {
-        // ------------------------------------------------------------------ producer warp
-        // Lane 0 drives the barriers and the bulk copies; all lanes prepare the band's ticket tables: for each mask of the group
-        // the range of word-list entries inside the band's rows and the prefix sums of their ticket counts.  The tables travel
-        // with the stage (written before the arrive on its "full" barrier), so consumers never meet at a CTA-wide barrier.
-        constexpr int MPL = GROUP / 32;     // masks per lane
-        uint32_t q = 0;                     // running band number across items: stage = q & 1, use = q >> 1
-        uint32_t iseq = 0;
-        for (;;) {
-            long long w = 0;
-            if (lane == 0) w = (long long) atomicAdd(p.work_counter, 1ull);
-            w = __shfl_sync(0xffffffffu, w, 0);
-            const bool done = w >= n_items;
-            const int nb = done ? 1 : NB;
-            const int m0 = done ? 0 : (int) (w / p.n_targets) * GROUP;
-            const int mb = done ? 0 : min(GROUP, p.n_masks - m0);
-            const int64_t t = done ? 0 : w % p.n_targets;
-            const uint32_t *wsp[MPL];
-#pragma unroll
-            for (int k = 0; k < MPL; k++) {
-                const int mi = lane * MPL + k;
-                wsp[k] = mi < mb ? p.masks[m0 + mi].wstart : nullptr;
-            }
-            for (int b = 0; b < nb; b++, q++) {
-                const int stage = q & 1;
-                const int y0 = b * R;
-                const int y1 = min(y0 + R, H);
-                // the band's tables, in registers first: their loads overlap the wait for the stage
-                uint32_t st[MPL], en[MPL], nt[MPL], sum = 0;
-#pragma unroll
-                for (int k = 0; k < MPL; k++) {
-                    st[k] = 0; en[k] = 0;
-                    if (wsp[k]) { st[k] = __ldg(wsp[k] + y0); en[k] = __ldg(wsp[k] + y1); }
-                    nt[k] = (en[k] - st[k] + kChunk - 1) / kChunk;
-                    sum += nt[k];
-                }
-                uint32_t incl = sum;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                if (q >= kStages) {
-                    if (lane == 0) mbar_wait(smem_u32(s_empty + stage), ((q >> 1) - 1) & 1);
-                    __syncwarp();
-                }
-                uint32_t run = incl - sum;
-#pragma unroll
-                for (int k = 0; k < MPL; k++) {
-                    const int mi = lane * MPL + k;
-                    s_bseg[stage * GROUP + mi] = make_uint2(st[k], en[k]);
-                    s_btick[stage * (GROUP + 1) + mi] = (uint16_t) run;
-                    run += nt[k];
-                }
-                if (lane == 31) s_btick[stage * (GROUP + 1) + GROUP] = (uint16_t) incl;
-                __syncwarp();
-                if (lane == 0) {
+        // ------------------------------------------------------------------ producer (one lane)
+        // Drives the barriers and the bulk copies, and publishes with every stage the range of the group's word list that falls
+        // into the band's rows (two reads of the group's row-start table), so consumers never meet at a CTA-wide barrier.
+        if (lane == 0) {
+            uint32_t q = 0;                 // running band number across items: stage = q & 1, use = q >> 1
+            uint32_t iseq = 0;
+            for (;;) {
+                const long long w = (long long) atomicAdd(p.work_counter, 1ull);
+                const bool done = w >= n_items;
+                const int nb = done ? 1 : NB;
+                const int64_t t = done ? 0 : w % p.n_targets;
+                const uint32_t *gstart = done ? nullptr : p.groups[w / p.n_targets].gstart;
+                for (int b = 0; b < nb; b++, q++) {
+                    const int stage = q & 1;
+                    const int y0 = b * R;
+                    const int y1 = min(y0 + R, H);
+                    uint2 range = make_uint2(0u, 0u);
+                    if (!done) range = make_uint2(__ldg(gstart + y0), __ldg(gstart + y1));     // issued before the wait below
+                    if (q >= kStages) mbar_wait(smem_u32(s_empty + stage), ((q >> 1) - 1) & 1);
                     s_next[stage] = 0;
+                    s_band[stage] = range;
                     if (b == 0) s_item[iseq & 1] = done ? -1 : w;
                     const uint32_t bar = smem_u32(s_full + stage);
-                    if (done) {
-                        mbar_arrive(bar);
-                    } else {
-                        const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
-                        const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
-                        const uint32_t bbytes = (uint32_t) ((y1 - y0) * p.bpitch) * 4u;
-                        const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * p.bpitch;
-                        mbar_expect_tx(bar, bytes + bbytes);
-                        bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
-                        bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
-                    }
+                    if (done) { mbar_arrive(bar); break; }
+                    const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
+                    const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
+                    const uint32_t bbytes = (uint32_t) ((y1 - y0) * p.bpitch) * 4u;
+                    const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * p.bpitch;
+                    mbar_expect_tx(bar, bytes + bbytes);
+                    bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
+                    bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
                 }
                 if (done) break;
+                iseq++;
             }
-            if (done) break;
-            iseq++;
         }
         return;
     }
@@ -302,6 +257,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint32_t q = 0, iseq = 0;
     int cur_gi = -1;
     bool compact = false;
+    const uint4 *gwords = nullptr;                   // word list of the current group
     uint2 *myq = s_queue + warp * kQueue;
     uint4 *mywq = s_wqueue + warp * kWordQueue;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -319,9 +275,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             // per-group tables.  Every consumer passed the barrier that ends the previous item, so nobody still reads the old ones.
             const PaletteGroup pg = p.groups[m0 / CDS_PALETTE_GROUP];
             compact = pg.palette != nullptr;
+            gwords = pg.words;
             for (int i = tid; i < mb; i += NCT) {
                 const MaskDesc md = p.masks[m0 + i];
-                s_wptr[i] = md.words;
                 s_rptr[i] = compact ? (const void *) md.crec : (const void *) md.records;
             }
             if (compact) {
@@ -338,9 +294,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const uint32_t *band = s_stage + (size_t) stage * stage_stride;
             const uint32_t *bits = s_bits + (size_t) stage * bits_words;
             const int y0 = b * R;
-            const uint16_t *tick = s_btick + stage * (GROUP + 1);
-            const uint2 *bseg = s_bseg + stage * GROUP;
-            const int n_tickets = tick[GROUP];
+            const uint2 range = s_band[stage];                                   // the group's word-list entries of this band
+            const int n_tickets = (int) ((range.y - range.x + kChunk - 1) / kChunk);
 
             uint32_t qh = 0, qt = 0;            // candidate queue head / tail (free running, slot = index & (kQueue - 1))
             uint32_t wh = 0, wt = 0;            // word queue head / tail
@@ -393,16 +348,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 if (lane == 0) tk = atomicAdd(&s_next[stage], 1);
                 tk = __shfl_sync(0xffffffffu, tk, 0);
                 if (tk >= n_tickets || p.debug_skip) break;
-                // mask of the ticket: the last mi with tick[mi] <= tk
-                int le = 0;
-#pragma unroll
-                for (int k = 0; k < GROUP / 32; k++) le += __popc(__ballot_sync(0xffffffffu, (int) tick[k * 32 + lane] <= tk));
-                const int mi = le - 1;
-                const uint2 sg = bseg[mi];
-                const uint32_t seg0 = sg.x + (uint32_t) (tk - tick[mi]) * kChunk;
-                const uint32_t seg1 = min(seg0 + kChunk, sg.y);
-                const uint4 *wl = reinterpret_cast<const uint4 *>(s_wptr[mi]);
-                const uint32_t mtag = (uint32_t) mi << 22;
+                // a ticket = kChunk consecutive entries of the group's word list; entries carry their mask's index
+                const uint32_t seg0 = range.x + (uint32_t) tk * kChunk;
+                const uint32_t seg1 = min(seg0 + kChunk, range.y);
+                const uint4 *wl = gwords;
 
                 // word entries {bits, meta, rec, -} are prefetched three iterations ahead; lanes past the end carry an empty
                 // word on a valid row
@@ -432,7 +381,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     const unsigned has = __ballot_sync(0xffffffffu, c != 0);
                     if (c) {
                         const uint32_t orient = (w.y >> kWordMetaOrientBit) & 1u;
-                        mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] = make_uint4(c, (xw << 5) | (y << 11) | (orient << 21) | mtag, w.z, w.x);
+                        mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] =
+                            make_uint4(c, (xw << 5) | (y << 11) | (orient << 21) | (w.y & (127u << kWordMetaMaskShift)), w.z, w.x);
                     }
                     wt += (uint32_t) __popc(has);
                     if (wt - wh >= 32) {
@@ -590,18 +540,39 @@ __global__ void __launch_bounds__(128) words_count_kernel(const MaskDesc *__rest
     if (lane == 0) wcount[(size_t) m * (H + 1) + y] = (uint32_t) n;
 }
 
-__global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restrict__ masks, int W, int H, bool mirror)
+// For every (group, row): the number of word-list entries of the group's masks in that row (grow), and for every mask its
+// offset inside that run (moff, in place over the per-mask counts).
+__global__ void __launch_bounds__(128) words_group_rows_kernel(uint32_t *__restrict__ wcount /* [M][H+1] counts -> offsets */, int n_masks, int H,
+                                                                uint32_t *__restrict__ grow /* [n_groups][H+1] */)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (y >= H) return;
+    uint32_t acc = 0;
+    const int m1 = min(n_masks, (g + 1) * CDS_PALETTE_GROUP);
+    for (int m = g * CDS_PALETTE_GROUP; m < m1; m++) {
+        const size_t i = (size_t) m * (H + 1) + y;
+        const uint32_t c = wcount[i];
+        wcount[i] = acc;
+        acc += c;
+    }
+    grow[(size_t) g * (H + 1) + y] = acc;
+}
+
+__global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restrict__ masks, int first_mask, int W, int H, bool mirror,
+                                                         const uint32_t *__restrict__ gstart /* [n_groups][H+1] */, uint4 *__restrict__ words)
 {
     __shared__ uint32_t s_bm[4][2][kRowWords];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * 4 + warp;
-    const int m = blockIdx.y;
+    const int m = first_mask + blockIdx.y;
     if (y >= H) return;
-    const MaskDesc md = masks[m];
+    const MaskDesc md = masks[blockIdx.y];
     uint32_t r0, r1;
     build_row_bitmaps(md, y, W, mirror, s_bm[warp][0], s_bm[warp][1], r0, r1);
-    uint4 *wl = reinterpret_cast<uint4 *>(const_cast<uint32_t *>(md.words));
-    uint32_t out = __ldg(md.wstart + y);
+    const int g = m / CDS_PALETTE_GROUP;
+    const uint32_t mtag = (uint32_t) (m % CDS_PALETTE_GROUP) << kWordMetaMaskShift;
+    uint32_t out = __ldg(gstart + (size_t) g * (H + 1) + y) + __ldg(md.wstart + y);     // start of the row's run + this mask's offset in it
     const uint32_t lt = (1u << lane) - 1u;
     for (int o = 0; o < (mirror ? 2 : 1); o++) {
         uint32_t px_before = 0;
@@ -619,8 +590,8 @@ __global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restr
             if (wbits) {
                 const uint32_t pos = out + (uint32_t) __popc(bal & lt);
                 const uint32_t before = px_before + incl - pc;          // set bits of this orientation's row before this word
-                wl[pos] = make_uint4(wbits, (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit),
-                                     o == 0 ? r0 + before : r1 - 1u - before, 0u);
+                words[pos] = make_uint4(wbits, (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit) | mtag,
+                                        o == 0 ? r0 + before : r1 - 1u - before, 0u);
             }
             out += (uint32_t) __popc(bal);
             px_before += __shfl_sync(0xffffffffu, incl, 31);
@@ -649,12 +620,20 @@ void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool m
     }
 }
 
-void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, cudaStream_t s)
+void launch_words_group_rows(uint32_t *wcount, int n_masks, int H, uint32_t *grow, cudaStream_t s)
+{
+    const int n_groups = (n_masks + CDS_PALETTE_GROUP - 1) / CDS_PALETTE_GROUP;
+    if (n_groups == 0) return;
+    dim3 grid((H + 127) / 128, n_groups);
+    words_group_rows_kernel<<<grid, 128, 0, s>>>(wcount, n_masks, H, grow);
+}
+
+void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const uint32_t *gstart, uint4 *words, cudaStream_t s)
 {
     for (int m0 = 0; m0 < n_masks; m0 += 32768) {
         int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
         dim3 grid((H + 3) / 4, cnt);
-        words_fill_kernel<<<grid, 128, 0, s>>>(masks + m0, W, H, mirror);
+        words_fill_kernel<<<grid, 128, 0, s>>>(masks + m0, m0, W, H, mirror, gstart, words);
     }
 }
 
@@ -677,9 +656,12 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     static const int chunk_env = env_int("CDSGPU_CAND_CHUNK", 128);
 #define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<128, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev)
     if (chunk_env == 256) {
-        if (warps_env == 16) return CDS_CAND_LAUNCH(16, 256);
         if (warps_env == 28) return CDS_CAND_LAUNCH(28, 256);
         return CDS_CAND_LAUNCH(24, 256);
+    }
+    if (chunk_env == 64) {
+        if (warps_env == 28) return CDS_CAND_LAUNCH(28, 64);
+        return CDS_CAND_LAUNCH(24, 64);
     }
     if (warps_env == 16) return CDS_CAND_LAUNCH(16, 128);
     if (warps_env == 28) return CDS_CAND_LAUNCH(28, 128);

@@ -30,15 +30,16 @@ struct MaskDesc {
     const cds_mask_record *records;   // P records, ascending pixel index
     const uint32_t *rowstart;         // H + 1 entries: records of image row y are [rowstart[y], rowstart[y+1])
     const uint32_t *crec;             // P compact records (cds_common.h) or nullptr when the mask's palette group is wide
-    const uint32_t *words;            // word list of the candidate kernel (cds_cand.cuh): n_words entries {bits, meta, rec, 0}, 16-byte aligned; or nullptr
-    const uint32_t *wstart;           // H + 1 entries: word-list entries of image row y are [wstart[y], wstart[y+1])
+    const uint32_t *wstart;           // H + 1 entries: offset of this mask's entries inside its group's run of each row (cds_cand.cuh)
     int P;
-    int n_words;
+    int pad;
 };
 
 // One palette group = CDS_PALETTE_GROUP consecutive masks.
 struct PaletteGroup {
     const uint2 *palette;             // n_pal entries, or nullptr: the group uses the 16-byte records
+    const uint4 *words;               // base of the word lists of the candidate kernel (cds_cand.cuh), or nullptr
+    const uint32_t *gstart;           // H + 1 entries: this group's entries of image row y are words[gstart[y] .. gstart[y+1])
     int n_pal;
     int pad;
 };

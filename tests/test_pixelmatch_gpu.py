@@ -285,6 +285,35 @@ def test_small_and_odd_image_sizes(ctx, shape):
     lib.close()
 
 
+def test_concurrent_callers_on_one_context(ctx, synth):
+    """The reference calls calculateMatchingScore on one shared algorithm instance from a pool of ~40 threads
+    (LocalColorMIPSearchProcessor.java:93-105): calls on one cds_ctx from many host threads must be safe and correct."""
+    from concurrent.futures import ThreadPoolExecutor
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
+    sizes = ms.add_rgb(masks[:17])
+    dense, dmir = ms.search_dense(lib)
+
+    def pair(job):
+        m, t = job
+        return ms.score_pair(m, targets[t])
+
+    jobs = [(m, t) for m in range(0, 17, 4) for t in range(0, 70, 7)]
+    with ThreadPoolExecutor(8) as ex:
+        futs = [ex.submit(pair, j) for j in jobs]
+        tk = ex.submit(lambda: ms.search_topk(lib, 5, 0.0))
+        res = [f.result() for f in futs]
+        topk = tk.result()
+    for (m, t), (score, ratio, mir) in zip(jobs, res):
+        assert (score, mir) == (int(dense[m, t]), bool(dmir[m, t]))
+        assert ratio == score / sizes[m]
+    for m in range(17):
+        order = sorted((j for j in range(70) if dense[m, j] > 0), key=lambda j: (-int(dense[m, j]), j))[:5]
+        assert topk[1][m, :topk[3][m]].tolist() == order
+    ms.close()
+
+
 def test_edge_cases_and_errors(ctx, fixtures):
     rects = O.label_rects(W, H)
     # odd xyShift -> IllegalArgumentException (ColorDepthSearchAlgorithmProviderFactory.java:57-60)
