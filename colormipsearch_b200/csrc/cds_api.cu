@@ -273,7 +273,8 @@ cds_status cds_library::ensure_occupancy(int rings)
         occ_rings = rings;
         occ_threshold = baked_threshold;
     }
-    const size_t plane_words = (size_t) g.H * bpitch;
+    const size_t plane_words = (size_t) g.H * occupancy_row_pitch(bpitch);
+    const int64_t kValidChunk = 256;
     bool launched = false;
     for (int d = 0; d < n_dev(); d++) {
         Shard &sh = shards[d];
@@ -283,10 +284,10 @@ cds_status cds_library::ensure_occupancy(int rings)
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
         if (!sh.occ) {
             CDS_CUDA(ctx, cudaMalloc(&sh.occ, (size_t) sh.cap_local * plane_words * sizeof(uint32_t)));
-            CDS_CUDA(ctx, cudaMalloc(&sh.valid, (size_t) sh.cap_local * plane_words * sizeof(uint32_t)));
+            CDS_CUDA(ctx, cudaMalloc(&sh.valid, (size_t) std::min<int64_t>(sh.cap_local, kValidChunk) * plane_words * sizeof(uint32_t)));
         }
-        launch_occupancy(sh.planes, g, sh.occ_done, nl - sh.occ_done, rings, bpitch, sh.valid, sh.occ, ds.stream);
-        ctx->stats.kernel_launches += 2;
+        launch_occupancy(sh.planes, g, sh.occ_done, nl - sh.occ_done, rings, bpitch, sh.valid, std::min<int64_t>(sh.cap_local, kValidChunk), sh.occ, ds.stream);
+        ctx->stats.kernel_launches += 2 * ((nl - sh.occ_done + kValidChunk - 1) / kValidChunk);
         CDS_CUDA(ctx, cudaGetLastError());
         sh.occ_done = nl;
         launched = true;

@@ -52,7 +52,7 @@ struct BandParams {
     int n_bands;
     int stage_words;                // (R + 2s) * pitch
     int n_groups;
-    const uint32_t *occ;            // occupancy bitmap [n_targets][H][bpitch]
+    const uint32_t *occ;            // occupancy bitmaps [n_targets][H][occupancy_row_pitch(bpitch)]; this kernel uses the all-sector row
     int bpitch;
     const PaletteGroup *groups;     // palette group of masks[0] onwards (masks[0] is CDS_PALETTE_GROUP aligned in the mask set)
 };
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
     constexpr int NCT = NCW * 32;                     // consumer threads
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int bits_words = p.rows_per_band * p.bpitch;
+    const int rowpitch = occupancy_row_pitch(p.bpitch);
+    const int any_off = CDS_NUM_SECTORS * p.bpitch;          // the OR over the sectors
+    const int bits_words = p.rows_per_band * rowpitch;
     const BandSmem<GROUP> L(p.stage_words, p.n_bands, NV, bits_words);
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
@@ -204,8 +206,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
                     const int y1 = min(y0 + R, H);
                     const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
                     const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
-                    const uint32_t bbytes = (uint32_t) ((y1 - y0) * p.bpitch) * 4u;
-                    const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * p.bpitch;
+                    const uint32_t bbytes = (uint32_t) ((y1 - y0) * rowpitch) * 4u;
+                    const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * rowpitch;
                     mbar_expect_tx(bar, bytes + bbytes);
                     bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
                     bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
@@ -306,8 +308,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
                         const int brow = (int) ((cur >> 11) & 0x3FFu) - y0;
                         const int xm = W - 1 - x;
                         const bool live = base + lane < seg1;
-                        const uint32_t wn = bits[brow * p.bpitch + (x >> 5)];
-                        const uint32_t wm = bits[brow * p.bpitch + (xm >> 5)];
+                        const uint32_t wn = bits[brow * rowpitch + any_off + (x >> 5)];
+                        const uint32_t wm = bits[brow * rowpitch + any_off + (xm >> 5)];
                         const bool any_n = __any_sync(0xffffffffu, live && ((wn >> (x & 31)) & 1u));
                         const bool any_m = MIRROR && __any_sync(0xffffffffu, live && ((wm >> (xm & 31)) & 1u));
                         if (!any_n && !any_m) continue;
@@ -332,8 +334,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
                         const int brow = (int) (cur.x >> 16) - y0;
                         const int xm = W - 1 - x;
                         const bool live = base + lane < seg1;
-                        const uint32_t wn = bits[brow * p.bpitch + (x >> 5)];
-                        const uint32_t wm = bits[brow * p.bpitch + (xm >> 5)];
+                        const uint32_t wn = bits[brow * rowpitch + any_off + (x >> 5)];
+                        const uint32_t wm = bits[brow * rowpitch + any_off + (xm >> 5)];
                         const bool any_n = __any_sync(0xffffffffu, live && ((wn >> (x & 31)) & 1u));
                         const bool any_m = MIRROR && __any_sync(0xffffffffu, live && ((wm >> (xm & 31)) & 1u));
                         if (!any_n && !any_m) continue;
@@ -403,7 +405,7 @@ BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
         if (n_bands > kMaxBands) break;
         size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
         if (stage_words * 4 >= (1u << 20)) continue;
-        BandSmem<GROUP> L((int) stage_words, n_bands, NV, R * bpitch);
+        BandSmem<GROUP> L((int) stage_words, n_bands, NV, R * occupancy_row_pitch(bpitch));
         if (L.total <= budget) {
             c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = L.total; c.ok = true;
             return c;

@@ -45,7 +45,7 @@ struct CandParams {
     int n_bands;
     int stage_words;                // (R + 2s) * pitch
     int n_groups;
-    const uint32_t *occ;            // occupancy bitmap [n_targets][H][bpitch]
+    const uint32_t *occ;            // occupancy bitmaps [n_targets][H][occupancy_row_pitch(bpitch)]
     int bpitch;
     const PaletteGroup *groups;
     int debug_skip;                 // profiling aid (CDSGPU_CAND_NULL): consumers skip the tickets, only the band pipeline runs
@@ -180,7 +180,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     constexpr int NCT = NCW * 32;                     // consumer threads
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int bits_words = p.rows_per_band * p.bpitch;
+    const int rowpitch = occupancy_row_pitch(p.bpitch);
+    const int bits_words = p.rows_per_band * rowpitch;
     const CandSmem<GROUP> L(p.stage_words, NS, bits_words, NCW);
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
@@ -240,8 +241,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     if (done) { mbar_arrive(bar); break; }
                     const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
                     const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
-                    const uint32_t bbytes = (uint32_t) ((y1 - y0) * p.bpitch) * 4u;
-                    const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * p.bpitch;
+                    const uint32_t bbytes = (uint32_t) ((y1 - y0) * rowpitch) * 4u;
+                    const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * rowpitch;
                     mbar_expect_tx(bar, bytes + bbytes);
                     bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
                     bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     }
                     const uint32_t y = w.y & ((1u << kWordMetaYBits) - 1);
                     const uint32_t xw = (w.y >> kWordMetaYBits) & 63u;
-                    const uint32_t c = w.x & bits[((int) y - y0) * p.bpitch + (int) xw];    // mask pixels of this word that can match
+                    const uint32_t c = w.x & bits[((int) y - y0) * rowpitch + CDS_NUM_SECTORS * p.bpitch + (int) xw];    // mask pixels of this word that can match
                     // words with candidates are compacted first, so that the bit peeling runs on full warps
                     const unsigned has = __ballot_sync(0xffffffffu, c != 0);
                     if (c) {
@@ -451,7 +452,7 @@ CandConfig cand_config(int xy_shift, const PlaneGeom &g, int n_warps)
         if (n_bands > kMaxBands) break;
         size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
         if (stage_words * 4 >= (1u << 20)) continue;
-        CandSmem<GROUP> L((int) stage_words, NS, R * bpitch, n_warps);
+        CandSmem<GROUP> L((int) stage_words, NS, R * occupancy_row_pitch(bpitch), n_warps);
         if (L.total <= budget) {
             c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = L.total; c.ok = true;
             return c;

@@ -129,74 +129,89 @@ void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_ta
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Occupancy bitmap (see cds_kernels.cuh).  Pass 1: one bit per pixel "inside the image and above the threshold";
-// pass 2: OR of the bits at the shift offsets, done 32 pixels at a time with word shifts.
+// Occupancy bitmaps (see cds_kernels.cuh).  Pass 1: per colour sector one bit per pixel "inside the image, above the
+// threshold, in this sector"; pass 2: OR of the bits at the shift offsets, 32 pixels at a time with word shifts, plus the
+// OR over the sectors in slot CDS_NUM_SECTORS.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restrict__ planes, PlaneGeom g, int64_t t0, int bpitch,
-                                                         uint32_t *__restrict__ valid)
+__global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restrict__ planes, PlaneGeom g, int64_t t0, int bp,
+                                                         uint32_t *__restrict__ valid /* chunk-relative */)
 {
     const int y = blockIdx.x;
     const int64_t t = t0 + blockIdx.y;
+    const int rowpitch = occupancy_row_pitch(bp);
     const uint32_t *row = planes + g.row_offset(t, y);
-    uint32_t *out = valid + ((size_t) t * g.H + y) * bpitch;
+    uint32_t *out = valid + ((size_t) blockIdx.y * g.H + y) * rowpitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < bpitch; k += (int) (blockDim.x >> 5)) {
+    for (int k = warp; k < bp; k += (int) (blockDim.x >> 5)) {
         const int x = k * 32 + lane;
-        bool v = false;
+        int sector = -1;
         if (x < g.W) {
             // above the threshold, and in a colour sector: "no sector" pixels (ties for the maximum, e.g. grey) have pixel gap
             // 10000 against everything (AbstractColorDepthSearchAlgorithm.java:182, 259-388), they can never match
             const uint32_t cw = row[x];
-            v = (cw & (CDS_CODE_BELOW_BIT | CDS_CODE_PAD_BIT)) == 0 && ((cw >> CDS_CODE_SR_SHIFT) & 0x3FFFFu) < (uint32_t) CDS_SR_NONE;
+            const uint32_t sr = (cw >> CDS_CODE_SR_SHIFT) & 0x3FFFFu;
+            if ((cw & (CDS_CODE_BELOW_BIT | CDS_CODE_PAD_BIT)) == 0 && sr < (uint32_t) CDS_SR_NONE) sector = (int) (sr / CDS_SECTOR_STRIDE);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, v);
-        if (lane == 0) out[k] = bal;
+#pragma unroll
+        for (int s = 0; s < CDS_NUM_SECTORS; s++) {
+            const unsigned bal = __ballot_sync(0xffffffffu, sector == s);
+            if (lane == 0) out[s * bp + k] = bal;
+        }
     }
 }
 
-__device__ __forceinline__ uint32_t hspread(const uint32_t *__restrict__ vrow, int k, int bpitch, int s)
+__device__ __forceinline__ uint32_t hspread(const uint32_t *__restrict__ vrow, int k, int bp, int s)
 {
     // bit x of the result = valid(x - s) | valid(x) | valid(x + s)
     const uint32_t c = vrow[k];
     const uint32_t l = k > 0 ? vrow[k - 1] : 0u;
-    const uint32_t r = k + 1 < bpitch ? vrow[k + 1] : 0u;
+    const uint32_t r = k + 1 < bp ? vrow[k + 1] : 0u;
     return c | (c << s) | (l >> (32 - s)) | (c >> s) | (r << (32 - s));
 }
 
-__global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restrict__ valid, int H, int bpitch, int64_t t0, int64_t n,
+__global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restrict__ valid /* chunk-relative */, int H, int bp, int64_t t0, int64_t n,
                                                         int rings, uint32_t *__restrict__ occ)
 {
-    const size_t total = (size_t) n * H * bpitch;
+    const int rowpitch = occupancy_row_pitch(bp);
+    const size_t total = (size_t) n * H * bp;
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
-        const int k = (int) (i % bpitch);
-        const int y = (int) ((i / bpitch) % H);
-        const int64_t t = t0 + (int64_t) (i / ((size_t) bpitch * H));
-        const uint32_t *vplane = valid + (size_t) t * H * bpitch;
-        uint32_t o;
-        if (rings == 0) {
-            o = vplane[(size_t) y * bpitch + k];
-        } else {
-            o = 0;
-            for (int dy = -2; dy <= 2; dy += 2)
-                if (y + dy >= 0 && y + dy < H) o |= hspread(vplane + (size_t) (y + dy) * bpitch, k, bpitch, 2);
-            if (rings >= 2)
-                for (int dy = -4; dy <= 4; dy += 4)
-                    if (y + dy >= 0 && y + dy < H) o |= hspread(vplane + (size_t) (y + dy) * bpitch, k, bpitch, 4);
+        const int k = (int) (i % bp);
+        const int y = (int) ((i / bp) % H);
+        const int64_t tl = (int64_t) (i / ((size_t) bp * H));
+        const uint32_t *vimg = valid + (size_t) tl * H * rowpitch;
+        uint32_t *orow = occ + ((size_t) (t0 + tl) * H + y) * rowpitch;
+        uint32_t any = 0;
+#pragma unroll
+        for (int s = 0; s < CDS_NUM_SECTORS; s++) {
+            uint32_t o;
+            if (rings == 0) {
+                o = vimg[(size_t) y * rowpitch + s * bp + k];
+            } else {
+                o = 0;
+                for (int dy = -2; dy <= 2; dy += 2)
+                    if (y + dy >= 0 && y + dy < H) o |= hspread(vimg + (size_t) (y + dy) * rowpitch + s * bp, k, bp, 2);
+                if (rings >= 2)
+                    for (int dy = -4; dy <= 4; dy += 4)
+                        if (y + dy >= 0 && y + dy < H) o |= hspread(vimg + (size_t) (y + dy) * rowpitch + s * bp, k, bp, 4);
+            }
+            orow[s * bp + k] = o;
+            any |= o;
         }
-        occ[((size_t) t * H + y) * bpitch + k] = o;
+        orow[CDS_NUM_SECTORS * bp + k] = any;
     }
 }
 
-void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int bpitch,
-                      uint32_t *valid_scratch, uint32_t *occ, cudaStream_t s)
+void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int bp,
+                      uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s)
 {
     if (n == 0) return;
-    for (int64_t i0 = 0; i0 < n; i0 += 32768) {
-        int64_t cnt = n - i0 < 32768 ? n - i0 : 32768;
+    if (scratch_targets > 32768) scratch_targets = 32768;      // gridDim.y
+    for (int64_t i0 = 0; i0 < n; i0 += scratch_targets) {
+        const int64_t cnt = n - i0 < scratch_targets ? n - i0 : scratch_targets;
         dim3 grid(g.H, (unsigned) cnt);
-        valid_bits_kernel<<<grid, 256, 0, s>>>(planes, g, t0 + i0, bpitch, valid_scratch);
+        valid_bits_kernel<<<grid, 256, 0, s>>>(planes, g, t0 + i0, bp, valid_scratch);
+        occupancy_kernel<<<148 * 8, 256, 0, s>>>(valid_scratch, g.H, bp, t0 + i0, cnt, rings, occ);
     }
-    occupancy_kernel<<<148 * 8, 256, 0, s>>>(valid_scratch, g.H, bpitch, t0, n, rings, occ);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

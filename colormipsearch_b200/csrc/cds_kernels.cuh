@@ -60,14 +60,17 @@ void launch_encode_rgb(const uint8_t *rgb, int64_t n, uint32_t *planes, PlaneGeo
 void launch_rebake(uint32_t *planes, size_t n_words, int data_threshold, cudaStream_t s);
 void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_tab, int data_threshold, uint32_t *codes, cudaStream_t s);
 
-// Occupancy bitmap of the library (one bit per pixel, row pitch `bpitch` 32-bit words): bit (x, y) of plane t is set when
-// at least one of the pixels (x + dx, y + dy), (dx, dy) in the shift set of `rings` (0: centre only, 1: {-2,0,2}^2,
-// 2: additionally {-4,0,4}^2), is inside the image and above the baked threshold.  A mask pixel whose bit is clear cannot
-// match in any shifted variant, and -- the shift set being symmetric -- the bit of its mirrored position covers the
-// mirrored variants.  `valid` is scratch of the same size.
+// Occupancy bitmaps of the library.  Per target and image row there are CDS_NUM_SECTORS + 1 bit rows of `bp` 32-bit words
+// each (row pitch occupancy_row_pitch(bp)): bit (x, y) of sector row s is set when at least one of the pixels (x + dx, y + dy),
+// (dx, dy) in the shift set of `rings` (0: centre only, 1: {-2,0,2}^2, 2: additionally {-4,0,4}^2), is inside the image, above
+// the baked threshold and of colour sector s; the last bit row is the OR of the sector rows.  A mask pixel can only match
+// target pixels of the sector of one of its (at most two) rank intervals, so a clear bit in that sector's row means "cannot
+// match in any shifted variant"; the shift set being symmetric, the bit of the mirrored position covers the mirrored variants.
+// `valid_scratch` holds scratch_targets * H * occupancy_row_pitch(bp) words.
 inline int occupancy_pitch(int W) { return (((W + 31) / 32) + 3) / 4 * 4; }
-void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int bpitch,
-                      uint32_t *valid_scratch, uint32_t *occ, cudaStream_t s);
+__host__ __device__ inline int occupancy_row_pitch(int bp) { return (CDS_NUM_SECTORS + 1) * bp; }
+void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int bp,
+                      uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s);
 
 void launch_mask_count_rows(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,
                             uint32_t *rowcount, cudaStream_t s);

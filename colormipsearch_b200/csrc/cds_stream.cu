@@ -64,7 +64,7 @@ cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, in
         if (sb.scores) { cudaFree(sb.scores); sb.scores = nullptr; }
         sb.chunk = 0; sb.m_cap = 0;
         const size_t words = g.total_words(chunk);
-        const size_t bm_words = (size_t) chunk * g.H * bpitch;
+        const size_t bm_words = (size_t) chunk * g.H * occupancy_row_pitch(bpitch);
         for (int i = 0; i < 2; i++) CDS_CUDA(ctx, cudaMalloc(&sb.staging[i], (size_t) chunk * img_bytes + 64));
         CDS_CUDA(ctx, cudaMalloc(&sb.planes, words * sizeof(uint32_t)));
         CDS_CUDA(ctx, cudaMalloc(&sb.occ, bm_words * sizeof(uint32_t)));
@@ -169,7 +169,7 @@ extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms_
         TargetView tv;
         tv.planes = sb.planes; tv.g = g; tv.bpitch = bpitch; tv.n = cnt; tv.occ = nullptr; tv.occ_ready = false;
         if (want_occ) {
-            launch_occupancy(sb.planes, g, 0, cnt, rings, bpitch, sb.valid, sb.occ, ds.stream);
+            launch_occupancy(sb.planes, g, 0, cnt, rings, bpitch, sb.valid, sb.chunk, sb.occ, ds.stream);
             ctx->stats.kernel_launches += 2;
             tv.occ = sb.occ;
             tv.occ_ready = true;
