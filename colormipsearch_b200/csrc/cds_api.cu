@@ -632,6 +632,8 @@ cds_status cds_maskset::sync_descs()
     std::shared_ptr<const ClassTable> ctab = class_table(params.z_tolerance);
     const bool compact_ok = ctab && ctab->max_len <= CDS_PAL_MAX_LEN && W <= 2048 && H <= 1024 && M > 0;
     n_compact_groups = 0;
+    words_built = false;
+    bool all_words = true;
     for (int d = 0; d < D; d++) {
         DevState &ds = ctx->devs[d];
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
@@ -643,6 +645,7 @@ cds_status cds_maskset::sync_descs()
             h[mi].records = (const cds_mask_record *) sd.records.p + rec_offset[mi];
             h[mi].rowstart = (const uint32_t *) sd.rowstart.p + (size_t) mi * (H + 1);
             h[mi].crec = nullptr;
+            h[mi].classes = (const uint32_t *) sd.classes.p + rec_offset[mi];
             h[mi].wstart = nullptr;
             h[mi].P = sizes[mi];
             h[mi].pad = 0;
@@ -658,7 +661,7 @@ cds_status cds_maskset::sync_descs()
         if (d_words[d]) { cudaFree(d_words[d]); d_words[d] = nullptr; }
         if (d_wstart[d]) { cudaFree(d_wstart[d]); d_wstart[d] = nullptr; }
         std::vector<PaletteGroup> groups(std::max(n_groups, 1));
-        for (auto &g : groups) { g.palette = nullptr; g.words = nullptr; g.gstart = nullptr; g.n_pal = 0; g.pad = 0; }
+        for (auto &g : groups) { g.palette = nullptr; g.words = nullptr; g.gstart = nullptr; g.lpal = nullptr; g.n_pal = 0; g.pad = 0; }
         if (compact_ok) {
             // palettes of the compact records: mark classes per group, number them, pack intervals, rewrite records
             const size_t slots = (size_t) n_groups * (CDS_NUM_CLASSES + 1);
@@ -703,50 +706,67 @@ cds_status cds_maskset::sync_descs()
         CDS_CUDA(ctx, cudaMalloc(&d_descs[d], h.size() * sizeof(MaskDesc)));
         CDS_CUDA(ctx, cudaMalloc(&d_groups[d], groups.size() * sizeof(PaletteGroup)));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
-        // word lists of the candidate kernel (cds_cand.cuh): per-(mask, row) counts, per-(group, row) runs, row starts, fill
-        const bool words_ok = M > 0 && W <= 2048 && H <= 1024 && (params.xy_shift == 0 || params.xy_shift == 2 || params.xy_shift == 4);
+        // word lists of the candidate kernel (cds_cand.cuh): per-(mask, row) counts, per-(group, row) runs, row starts, fill.
+        // They reference the groups' palettes, so they exist only when every group is compact.
+        const bool words_ok = M > 0 && W <= 2048 && H <= 1024 && (params.xy_shift == 0 || params.xy_shift == 2 || params.xy_shift == 4) &&
+                              compact_ok && n_compact_groups == n_groups;
         if (words_ok) {
             uint32_t *d_grow = nullptr;
-            const size_t gs_n = (size_t) n_groups * (H + 1);
-            // d_wstart: [M][H+1] per-mask offsets followed by [n_groups][H+1] row starts
-            cds_status st = ctx->check(cudaMalloc(&d_wstart[d], ((size_t) M * (H + 1) + gs_n) * sizeof(uint32_t)), "cudaMalloc(word row starts)");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_grow, gs_n * sizeof(uint32_t)), "cudaMalloc(group rows)");
-            if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_grow, 0, gs_n * sizeof(uint32_t), ds.stream), "memset(group rows)");
-            std::vector<uint32_t> grow(gs_n, 0);
+            const size_t gs_n = (size_t) n_groups * (H + 1), ms_n = (size_t) M * (H + 1);
+            const cds_class_interval *class_tab = nullptr;
+            cds_status st = ctx->class_table_on(ds, params.z_tolerance, &class_tab);
+            // d_wstart: per-mask entry offsets [M][H+1], per-mask bit offsets [M][H+1], entry row starts [G][H+1], bit row starts [G][H+1]
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_wstart[d], (2 * ms_n + 2 * gs_n) * sizeof(uint32_t)), "cudaMalloc(word row starts)");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_grow, 2 * gs_n * sizeof(uint32_t)), "cudaMalloc(group rows)");
+            if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_grow, 0, 2 * gs_n * sizeof(uint32_t), ds.stream), "memset(group rows)");
+            std::vector<uint32_t> grow(2 * gs_n, 0);
+            uint32_t *d_wcount = d_wstart[d], *d_bcount = d_wstart[d] + ms_n;
             if (st == CDS_OK) {
-                launch_words_count(d_descs[d], M, W, H, params.mirror != 0, d_wstart[d], ds.stream);
-                launch_words_group_rows(d_wstart[d], M, H, d_grow, ds.stream);
-                ctx->stats.kernel_launches += 2;
+                launch_words_count(d_descs[d], M, W, H, params.mirror != 0, class_tab, d_wcount, d_bcount, ds.stream);
+                launch_words_group_rows(d_wcount, M, H, d_grow, ds.stream);
+                launch_words_group_rows(d_bcount, M, H, d_grow + gs_n, ds.stream);
+                ctx->stats.kernel_launches += 3;
                 st = ctx->check(cudaGetLastError(), "word count kernels");
             }
-            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(grow.data(), d_grow, gs_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds.stream), "group rows D2H");
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(grow.data(), d_grow, 2 * gs_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds.stream), "group rows D2H");
             if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "word count");
             if (d_grow) cudaFree(d_grow);
             if (st != CDS_OK) return st;
-            uint64_t total_words = 0;
-            for (int g = 0; g < n_groups; g++) {
-                for (int y = 0; y < H; y++) { const uint32_t c = grow[(size_t) g * (H + 1) + y]; grow[(size_t) g * (H + 1) + y] = (uint32_t) total_words; total_words += c; }
-                grow[(size_t) g * (H + 1) + H] = (uint32_t) total_words;
-            }
-            if (total_words < ((uint64_t) 1 << 32)) {
-                uint32_t *d_gstart = d_wstart[d] + (size_t) M * (H + 1);
-                CDS_CUDA(ctx, cudaMalloc(&d_words[d], std::max<uint64_t>(total_words, 1) * sizeof(uint4)));
-                CDS_CUDA(ctx, cudaMemcpyAsync(d_gstart, grow.data(), gs_n * sizeof(uint32_t), cudaMemcpyHostToDevice, ds.stream));
-                for (int m = 0; m < M; m++) h[m].wstart = d_wstart[d] + (size_t) m * (H + 1);
+            uint64_t total[2] = {0, 0};
+            for (int a = 0; a < 2; a++)
                 for (int g = 0; g < n_groups; g++) {
-                    groups[g].words = reinterpret_cast<const uint4 *>(d_words[d]);
+                    uint32_t *row = grow.data() + a * gs_n + (size_t) g * (H + 1);
+                    for (int y = 0; y < H; y++) { const uint32_t c = row[y]; row[y] = (uint32_t) total[a]; total[a] += c; }
+                    row[H] = (uint32_t) total[a];
+                }
+            if (total[0] < ((uint64_t) 1 << 32) && total[1] < ((uint64_t) 1 << 32)) {
+                uint32_t *d_gstart = d_wstart[d] + 2 * ms_n, *d_bstart = d_gstart + gs_n;
+                // d_words: the entries, then the palette references
+                CDS_CUDA(ctx, cudaMalloc(&d_words[d], std::max<uint64_t>(total[0], 1) * sizeof(uint4) + std::max<uint64_t>(total[1], 1) * sizeof(uint16_t)));
+                uint4 *d_entries = reinterpret_cast<uint4 *>(d_words[d]);
+                uint16_t *d_lpal = reinterpret_cast<uint16_t *>(d_entries + std::max<uint64_t>(total[0], 1));
+                CDS_CUDA(ctx, cudaMemcpyAsync(d_gstart, grow.data(), 2 * gs_n * sizeof(uint32_t), cudaMemcpyHostToDevice, ds.stream));
+                for (int m = 0; m < M; m++) h[m].wstart = d_wcount + (size_t) m * (H + 1);
+                for (int g = 0; g < n_groups; g++) {
+                    groups[g].words = d_entries;
                     groups[g].gstart = d_gstart + (size_t) g * (H + 1);
+                    groups[g].lpal = d_lpal;
                 }
                 CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
-                launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, d_gstart, reinterpret_cast<uint4 *>(d_words[d]), ds.stream);
+                launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, class_tab, d_gstart, d_bstart, d_bcount, d_entries, d_lpal, ds.stream);
                 ctx->stats.kernel_launches++;
                 CDS_CUDA(ctx, cudaGetLastError());
                 CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));      // `grow` is pageable memory
+            } else {
+                all_words = false;
             }
+        } else {
+            all_words = false;
         }
         CDS_CUDA(ctx, cudaMemcpyAsync(d_groups[d], groups.data(), groups.size() * sizeof(PaletteGroup), cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
     }
+    words_built = all_words;
     descs_dirty = false;
     return CDS_OK;
 }
@@ -758,7 +778,7 @@ cds_status launch_match_view(cds_ctx *ctx, const cds_maskset *ms, const TargetVi
 {
     const int choice = ctx->match_kernel;      // 0 = automatic, 1 = candidate, 2 = band, 3 = gather (cds_ctx_set_option)
     const bool batched_ok = mc >= band_min_masks() && tv.occ_ready && (m0 % CDS_PALETTE_GROUP) == 0;
-    const bool cand_ok = batched_ok && (choice == 0 || choice == 1) && ms->d_words[d] && cand_kernel_supported(ms->params.xy_shift, tv.g);
+    const bool cand_ok = batched_ok && (choice == 0 || choice == 1) && ms->d_words[d] && ms->words_built && cand_kernel_supported(ms->params.xy_shift, tv.g);
     const bool band_ok = batched_ok && choice != 3 && band_kernel_supported(ms->params.xy_shift, tv.g);
     if (ev0) cudaEventRecord(ev0, stream);
     if (cand_ok) {

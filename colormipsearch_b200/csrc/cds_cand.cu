@@ -67,25 +67,23 @@ __device__ __forceinline__ void offset_of(int v, int &dx, int &dy)
     dy = (k % 3 - 1) * 4;
 }
 
-// acc[OFF / 4] += 1 (shared memory, predicated reduction) when the code word c lies in [lo1, lo1+len1] or [lo2, lo2+len2].
+// acc[OFF / 4] += 1 (shared memory, predicated reduction) when the code word c lies in [lo, lo + len].
 // Matches are rare (a few per hundred evaluations), so nearly all of these reductions are predicated off.
 template <int OFF>
-__device__ __forceinline__ void count_hit(uint32_t acc, uint32_t c, uint32_t lo1, uint32_t len1, uint32_t lo2, uint32_t len2)
+__device__ __forceinline__ void count_hit(uint32_t acc, uint32_t c, uint32_t lo, uint32_t len)
 {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 a, b;\n\t"
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 a;\n\t"
                  "sub.u32 a, %1, %2;\n\t"
-                 "sub.u32 b, %1, %4;\n\t"
                  "setp.le.u32 p, a, %3;\n\t"
-                 "setp.le.or.u32 p, b, %5, p;\n\t"
-                 "@p red.shared.add.u32 [%0+%6], 1;\n\t}"
-                 :: "r"(acc), "r"(c), "r"(lo1), "r"(len1), "r"(lo2), "r"(len2), "n"(OFF));
+                 "@p red.shared.add.u32 [%0+%4], 1;\n\t}"
+                 :: "r"(acc), "r"(c), "r"(lo), "r"(len), "n"(OFF));
     // no "memory" clobber on purpose: the band reads around it may be scheduled freely; the accumulators are only read after a
     // named barrier (itself a volatile asm with a memory clobber), and volatile asms keep their order
 }
 
 template <int GROUP>
 struct CandSmem {
-    size_t stage_off, bits_off, pal_off, acc_off, band_off, rptr_off, queue_off, wqueue_off, bar_off, next_off, item_off, total;
+    size_t stage_off, bits_off, pal_off, acc_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, total;
     __host__ __device__ CandSmem(int stage_words, int NS, int bits_words, int n_warps)
     {
         size_t o = 0;
@@ -94,7 +92,6 @@ struct CandSmem {
         pal_off = o;   o += (size_t) CDS_PALETTE_SIZE * 8;
         wqueue_off = o; o += (size_t) n_warps * kWordQueue * 16;
         queue_off = o; o += (size_t) n_warps * kQueue * 8;
-        rptr_off = o;  o += (size_t) GROUP * 8;
         bar_off = o;   o += 2 * kStages * 8;
         item_off = o;  o += 16;
         next_off = o;  o += 16;
@@ -105,7 +102,8 @@ struct CandSmem {
 };
 
 // The evaluations of 32 queued candidates: one per lane.
-// cand.x = x | y << 11 | orientation << 21 | mask (inside the group) << 22, in target coordinates; cand.y = record index inside the mask.
+// cand.x = x | y << 11 | orientation << 21 | mask (inside the group) << 22, in target coordinates; cand.y = index of the
+// candidate's palette reference in the group's lpal array.
 template <int NRINGS, int V>
 struct EvalUnroll {
     static __device__ __forceinline__ void load(const uint32_t *pc, int pitch, uint32_t (&cw)[Offsets<NRINGS>::N])
@@ -115,51 +113,38 @@ struct EvalUnroll {
         cw[V] = pc[dy * pitch + dx];
         EvalUnroll<NRINGS, V + 1>::load(pc, pitch, cw);
     }
-    static __device__ __forceinline__ void count(const uint32_t (&cw)[Offsets<NRINGS>::N], uint32_t acc, uint32_t lo1, uint32_t len1,
-                                                 uint32_t lo2, uint32_t len2)
+    static __device__ __forceinline__ void count(const uint32_t (&cw)[Offsets<NRINGS>::N], uint32_t acc, uint32_t lo, uint32_t len)
     {
-        count_hit<4 * V>(acc, cw[V], lo1, len1, lo2, len2);
-        EvalUnroll<NRINGS, V + 1>::count(cw, acc, lo1, len1, lo2, len2);
+        count_hit<4 * V>(acc, cw[V], lo, len);
+        EvalUnroll<NRINGS, V + 1>::count(cw, acc, lo, len);
     }
 };
 template <int NRINGS>
 struct EvalUnroll<NRINGS, Offsets<NRINGS>::N> {
     static __device__ __forceinline__ void load(const uint32_t *, int, uint32_t (&)[Offsets<NRINGS>::N]) {}
-    static __device__ __forceinline__ void count(const uint32_t (&)[Offsets<NRINGS>::N], uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
+    static __device__ __forceinline__ void count(const uint32_t (&)[Offsets<NRINGS>::N], uint32_t, uint32_t, uint32_t) {}
 };
 
-// First half of an evaluation: the candidate's palette index, read from the mask's compact records (an L2 access whose
-// latency the caller hides behind the evaluation of the previous batch).
-template <bool COMPACT>
-__device__ __forceinline__ uint32_t fetch_palette_index(uint2 cand, bool live, const void *const *__restrict__ s_rptr)
+// First half of an evaluation: the candidate's palette reference (palette index | 0x8000 for the second interval), an L2
+// access whose latency the caller hides behind the evaluation of the previous batch.
+__device__ __forceinline__ uint32_t fetch_palette_ref(uint2 cand, bool live, const uint16_t *__restrict__ lpal)
 {
-    uint32_t pi = CDS_PALETTE_SIZE - 1;                                         // the never-matching entry
-    if (COMPACT && live) pi = __ldg(static_cast<const uint32_t *>(s_rptr[(cand.x >> 22) & 127u]) + cand.y) >> 21;
-    return pi;
+    uint32_t pr = CDS_PALETTE_SIZE - 1;                                         // the never-matching entry
+    if (live) pr = __ldg(lpal + cand.y);
+    return pr;
 }
 
-template <int NRINGS, bool COMPACT>
-__device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pi, bool live, const uint32_t *__restrict__ band, int y0, int pitch,
-                                                const void *const *__restrict__ s_rptr, const uint2 *__restrict__ s_pal, uint32_t acc_base)
+template <int NRINGS>
+__device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const uint32_t *__restrict__ band, int y0, int pitch,
+                                                const uint2 *__restrict__ s_pal, uint32_t acc_base)
 {
     constexpr int NS = Offsets<NRINGS>::N;
     constexpr int S = 2 * NRINGS;
     const uint32_t mi = (cand.x >> 22) & 127u;
-    uint32_t lo1, len1, lo2, len2;
-    if (COMPACT) {
-        const uint2 pe = s_pal[pi];
-        lo1 = (pe.x & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
-        len1 = ((pe.x >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
-        lo2 = (pe.y & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
-        len2 = ((pe.y >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
-    } else {
-        uint4 r = make_uint4(0u, CDS_EMPTY_LO, CDS_EMPTY_LO, 0u);
-        if (live) r = __ldg(reinterpret_cast<const uint4 *>(static_cast<const cds_mask_record *>(s_rptr[mi]) + cand.y));
-        lo1 = r.y;
-        lo2 = r.z;
-        len1 = ((r.w & 0xFFFFu) << CDS_CODE_SR_SHIFT) | 0xFFu;
-        len2 = ((r.w >> 16) << CDS_CODE_SR_SHIFT) | 0xFFu;
-    }
+    const uint2 pe = s_pal[pr & (CDS_PALETTE_SIZE - 1)];
+    const uint32_t iv = (pr & 0x8000u) ? pe.y : pe.x;                           // the interval that lives in this candidate's sector
+    const uint32_t lo = (iv & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
+    const uint32_t len = ((iv >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
     const int x = (int) (cand.x & 0x7FFu);
     const int yrel = (int) ((cand.x >> 11) & 0x3FFu) - y0;
     const uint32_t orient = (cand.x >> 21) & 1u;
@@ -168,7 +153,7 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pi, bool li
     const uint32_t acc = acc_base + (mi * 2u * NS + orient * NS) * 4u;
     uint32_t cw[NS];
     EvalUnroll<NRINGS, 0>::load(pc, pitch, cw);          // all shifted reads first, then the compares
-    EvalUnroll<NRINGS, 0>::count(cw, acc, lo1, len1, lo2, len2);
+    EvalUnroll<NRINGS, 0>::count(cw, acc, lo, len);
 }
 
 template <int NRINGS, int GROUP, int NCW, int kChunk>
@@ -189,7 +174,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
     uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + L.queue_off);                  // [NCW][kQueue] candidates
     uint4 *s_wqueue = reinterpret_cast<uint4 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] words with candidates
-    const void **s_rptr = reinterpret_cast<const void **>(smem_raw + L.rptr_off);        // record arrays (compact or 16-byte)
     int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
     uint2 *s_band = reinterpret_cast<uint2 *>(smem_raw + L.band_off);                   // [kStages] range of the group's word list inside the staged band
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
@@ -257,8 +241,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     // ---------------------------------------------------------------------- consumers
     uint32_t q = 0, iseq = 0;
     int cur_gi = -1;
-    bool compact = false;
     const uint4 *gwords = nullptr;                   // word list of the current group
+    const uint16_t *glpal = nullptr;                 // palette references of its entries' set bits
     uint2 *myq = s_queue + warp * kQueue;
     uint4 *mywq = s_wqueue + warp * kWordQueue;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -275,16 +259,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
         if (gi != cur_gi) {
             // per-group tables.  Every consumer passed the barrier that ends the previous item, so nobody still reads the old ones.
             const PaletteGroup pg = p.groups[m0 / CDS_PALETTE_GROUP];
-            compact = pg.palette != nullptr;
             gwords = pg.words;
-            for (int i = tid; i < mb; i += NCT) {
-                const MaskDesc md = p.masks[m0 + i];
-                s_rptr[i] = compact ? (const void *) md.crec : (const void *) md.records;
-            }
-            if (compact) {
-                for (int i = tid; i < pg.n_pal; i += NCT) s_pal[i] = pg.palette[i];
-                if (tid == 0) s_pal[CDS_PALETTE_SIZE - 1] = make_uint2(CDS_PAL_EMPTY_LO, CDS_PAL_EMPTY_LO);   // idle lanes point here
-            }
+            glpal = pg.lpal;
+            for (int i = tid; i < pg.n_pal; i += NCT) s_pal[i] = pg.palette[i];
+            if (tid == 0) s_pal[CDS_PALETTE_SIZE - 1] = make_uint2(CDS_PAL_EMPTY_LO, CDS_PAL_EMPTY_LO);   // idle lanes point here
             consumer_barrier<NCT>();
             cur_gi = gi;
         }
@@ -307,21 +285,17 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             // lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
             // A full batch of candidates: start its palette-index loads, evaluate the batch submitted before it.
             uint2 pend_cand = make_uint2(0u, 0u);
-            uint32_t pend_pi = 0;
-            bool pend = false, pend_live = false;
-            auto run_pending = [&]() {
-                if (compact) eval_candidates<NRINGS, true>(pend_cand, pend_pi, pend_live, band, y0, pitch, s_rptr, s_pal, acc_base);
-                else eval_candidates<NRINGS, false>(pend_cand, pend_pi, pend_live, band, y0, pitch, s_rptr, s_pal, acc_base);
-            };
+            uint32_t pend_pr = 0;
+            bool pend = false;
+            auto run_pending = [&]() { eval_candidates<NRINGS>(pend_cand, pend_pr, band, y0, pitch, s_pal, acc_base); };
             auto submit = [&](uint2 cand, bool live) {
-                const uint32_t pi = compact ? fetch_palette_index<true>(cand, live, s_rptr) : fetch_palette_index<false>(cand, live, s_rptr);
+                const uint32_t pr = fetch_palette_ref(cand, live, glpal);
                 if (pend) run_pending();
-                pend_cand = cand; pend_pi = pi; pend_live = live; pend = true;
+                pend_cand = cand; pend_pr = pr; pend = true;
             };
             auto peel = [&](uint4 we) {
                 uint32_t c = we.x;
-                const uint32_t base = we.y, rec = we.z, wbits = we.w;
-                const bool mirrored = (base >> 21) & 1u;
+                const uint32_t base = we.y, lrec = we.z, wbits = we.w;
                 unsigned bal = __ballot_sync(0xffffffffu, c != 0);
                 while (bal) {
                     if (c) {
@@ -329,7 +303,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                         const uint32_t k = (uint32_t) __popc(wbits & ((1u << bit) - 1u));
                         uint2 cand;
                         cand.x = base | (uint32_t) bit;
-                        cand.y = mirrored ? rec - k : rec + k;
+                        cand.y = lrec + k;
                         myq[(qt + (uint32_t) __popc(bal & lt_mask)) & (kQueue - 1)] = cand;
                         c &= c - 1;
                     }
@@ -377,7 +351,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     }
                     const uint32_t y = w.y & ((1u << kWordMetaYBits) - 1);
                     const uint32_t xw = (w.y >> kWordMetaYBits) & 63u;
-                    const uint32_t c = w.x & bits[((int) y - y0) * rowpitch + CDS_NUM_SECTORS * p.bpitch + (int) xw];    // mask pixels of this word that can match
+                    const uint32_t sec = (w.y >> kWordMetaSectorShift) & 7u;
+                    const uint32_t c = w.x & bits[((int) y - y0) * rowpitch + (int) sec * p.bpitch + (int) xw];    // mask pixels of this word that can match
                     // words with candidates are compacted first, so that the bit peeling runs on full warps
                     const unsigned has = __ballot_sync(0xffffffffu, c != 0);
                     if (c) {
@@ -504,46 +479,68 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
 // mirrored target coordinates), whose non-zero words become the entries.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kRowWords = 64;       // W <= 2048
+constexpr int kLists = 2 * CDS_NUM_SECTORS;      // (orientation, sector) bitmaps per mask row
 
-__device__ __forceinline__ void build_row_bitmaps(const MaskDesc &md, int y, int W, bool mirror, uint32_t *bm0, uint32_t *bm1,
-                                                  uint32_t &r0, uint32_t &r1)
+// Scatters the records of one mask row into the (orientation, sector) bitmaps.  A mask pixel goes into the list of the sector
+// of each of its non-empty rank intervals: its own sector (interval 1) and, near a sector boundary, one neighbouring sector
+// (interval 2).  `pix` (may be null) receives, per x, the pixel's palette index | own sector << 11.
+__device__ __forceinline__ void build_row_lists(const MaskDesc &md, int y, int W, bool mirror, const cds_class_interval *__restrict__ class_tab,
+                                                uint32_t (*bm)[kRowWords] /* [kLists] */, uint16_t *pix)
 {
     const int lane = threadIdx.x & 31;
-    for (int k = lane; k < kRowWords; k += 32) { bm0[k] = 0; bm1[k] = 0; }
+    for (int k = lane; k < kLists * kRowWords; k += 32) bm[0][k] = 0;
     __syncwarp();
-    r0 = __ldg(md.rowstart + y);
-    r1 = __ldg(md.rowstart + y + 1);
+    const uint32_t r0 = __ldg(md.rowstart + y), r1 = __ldg(md.rowstart + y + 1);
     for (uint32_t i = r0 + lane; i < r1; i += 32) {
+        const uint32_t cls = __ldg(md.classes + i);
+        if (cls >= (uint32_t) CDS_NUM_CLASSES) continue;                       // no colour sector: matches nothing
         const int x = (int) (__ldg(&md.records[i].xy) & 0xFFFFu);
-        atomicOr(&bm0[x >> 5], 1u << (x & 31));
-        if (mirror) {
-            const int xm = W - 1 - x;
-            atomicOr(&bm1[xm >> 5], 1u << (xm & 31));
+        const int xm = W - 1 - x;
+        const int s1 = (int) (cls / CDS_NUM_RANKS);
+        const cds_class_interval iv = class_tab[cls];
+        if (pix) pix[x] = (uint16_t) ((md.crec ? (__ldg(md.crec + i) >> 21) : 0u) | ((uint32_t) s1 << 11));
+        if (iv.lo1 != CDS_IV_EMPTY) {
+            atomicOr(&bm[s1][x >> 5], 1u << (x & 31));
+            if (mirror) atomicOr(&bm[CDS_NUM_SECTORS + s1][xm >> 5], 1u << (xm & 31));
+        }
+        if (iv.lo2 != CDS_IV_EMPTY) {
+            const int s2 = (int) (iv.lo2 / CDS_SECTOR_STRIDE);
+            atomicOr(&bm[s2][x >> 5], 1u << (x & 31));
+            if (mirror) atomicOr(&bm[CDS_NUM_SECTORS + s2][xm >> 5], 1u << (xm & 31));
         }
     }
     __syncwarp();
 }
 
+// counts[m][y] = {word-list entries, set bits} of (mask m, row y)
 __global__ void __launch_bounds__(128) words_count_kernel(const MaskDesc *__restrict__ masks, int W, int H, bool mirror,
-                                                          uint32_t *__restrict__ wcount)
+                                                          const cds_class_interval *__restrict__ class_tab,
+                                                          uint32_t *__restrict__ wcount, uint32_t *__restrict__ bcount)
 {
-    __shared__ uint32_t s_bm[4][2][kRowWords];
+    __shared__ uint32_t s_bm[4][kLists][kRowWords];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * 4 + warp;
     const int m = blockIdx.y;
     if (y >= H) return;
     const MaskDesc md = masks[m];
-    uint32_t r0, r1;
-    build_row_bitmaps(md, y, W, mirror, s_bm[warp][0], s_bm[warp][1], r0, r1);
-    int n = 0;
-    for (int k = lane; k < kRowWords; k += 32) n += (s_bm[warp][0][k] != 0) + (s_bm[warp][1][k] != 0);
-    n = __reduce_add_sync(0xffffffffu, n);
-    if (lane == 0) wcount[(size_t) m * (H + 1) + y] = (uint32_t) n;
+    build_row_lists(md, y, W, mirror, class_tab, s_bm[warp], nullptr);
+    int nw = 0, nb = 0;
+    for (int k = lane; k < kLists * kRowWords; k += 32) {
+        const uint32_t wbits = s_bm[warp][0][k];
+        nw += wbits != 0;
+        nb += __popc(wbits);
+    }
+    nw = __reduce_add_sync(0xffffffffu, nw);
+    nb = __reduce_add_sync(0xffffffffu, nb);
+    if (lane == 0) {
+        wcount[(size_t) m * (H + 1) + y] = (uint32_t) nw;
+        bcount[(size_t) m * (H + 1) + y] = (uint32_t) nb;
+    }
 }
 
-// For every (group, row): the number of word-list entries of the group's masks in that row (grow), and for every mask its
-// offset inside that run (moff, in place over the per-mask counts).
-__global__ void __launch_bounds__(128) words_group_rows_kernel(uint32_t *__restrict__ wcount /* [M][H+1] counts -> offsets */, int n_masks, int H,
+// For every (group, row): the totals of the group's masks in that row (grow), and for every mask its offset inside that run
+// (in place over the per-mask counts).  Run twice: for the entry counts and for the bit counts.
+__global__ void __launch_bounds__(128) words_group_rows_kernel(uint32_t *__restrict__ count /* [M][H+1] counts -> offsets */, int n_masks, int H,
                                                                 uint32_t *__restrict__ grow /* [n_groups][H+1] */)
 {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,34 +550,40 @@ __global__ void __launch_bounds__(128) words_group_rows_kernel(uint32_t *__restr
     const int m1 = min(n_masks, (g + 1) * CDS_PALETTE_GROUP);
     for (int m = g * CDS_PALETTE_GROUP; m < m1; m++) {
         const size_t i = (size_t) m * (H + 1) + y;
-        const uint32_t c = wcount[i];
-        wcount[i] = acc;
+        const uint32_t c = count[i];
+        count[i] = acc;
         acc += c;
     }
     grow[(size_t) g * (H + 1) + y] = acc;
 }
 
 __global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restrict__ masks, int first_mask, int W, int H, bool mirror,
-                                                         const uint32_t *__restrict__ gstart /* [n_groups][H+1] */, uint4 *__restrict__ words)
+                                                         const cds_class_interval *__restrict__ class_tab,
+                                                         const uint32_t *__restrict__ gstart /* [n_groups][H+1] entries */,
+                                                         const uint32_t *__restrict__ bstart /* [n_groups][H+1] bits */,
+                                                         const uint32_t *__restrict__ boff /* [M][H+1] */,
+                                                         uint4 *__restrict__ words, uint16_t *__restrict__ lpal)
 {
-    __shared__ uint32_t s_bm[4][2][kRowWords];
+    __shared__ uint32_t s_bm[4][kLists][kRowWords];
+    __shared__ uint16_t s_pix[4][kRowWords * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * 4 + warp;
     const int m = first_mask + blockIdx.y;
     if (y >= H) return;
     const MaskDesc md = masks[blockIdx.y];
-    uint32_t r0, r1;
-    build_row_bitmaps(md, y, W, mirror, s_bm[warp][0], s_bm[warp][1], r0, r1);
+    build_row_lists(md, y, W, mirror, class_tab, s_bm[warp], s_pix[warp]);
     const int g = m / CDS_PALETTE_GROUP;
     const uint32_t mtag = (uint32_t) (m % CDS_PALETTE_GROUP) << kWordMetaMaskShift;
-    uint32_t out = __ldg(gstart + (size_t) g * (H + 1) + y) + __ldg(md.wstart + y);     // start of the row's run + this mask's offset in it
+    uint32_t out_w = __ldg(gstart + (size_t) g * (H + 1) + y) + __ldg(md.wstart + y);       // start of the row's run + this mask's offset in it
+    uint32_t out_b = __ldg(bstart + (size_t) g * (H + 1) + y) + __ldg(boff + (size_t) m * (H + 1) + y);
     const uint32_t lt = (1u << lane) - 1u;
-    for (int o = 0; o < (mirror ? 2 : 1); o++) {
-        uint32_t px_before = 0;
+    for (int list = 0; list < (mirror ? kLists : CDS_NUM_SECTORS); list++) {
+        const int o = list / CDS_NUM_SECTORS, sec = list % CDS_NUM_SECTORS;
         for (int k0 = 0; k0 < kRowWords; k0 += 32) {
             const int k = k0 + lane;
-            const uint32_t wbits = s_bm[warp][o][k];
+            uint32_t wbits = s_bm[warp][list][k];
             const unsigned bal = __ballot_sync(0xffffffffu, wbits != 0);
+            if (bal == 0) continue;
             const uint32_t pc = (uint32_t) __popc(wbits);
             uint32_t incl = pc;
 #pragma unroll
@@ -589,13 +592,21 @@ __global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restr
                 if (lane >= d) incl += v;
             }
             if (wbits) {
-                const uint32_t pos = out + (uint32_t) __popc(bal & lt);
-                const uint32_t before = px_before + incl - pc;          // set bits of this orientation's row before this word
-                words[pos] = make_uint4(wbits, (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit) | mtag,
-                                        o == 0 ? r0 + before : r1 - 1u - before, 0u);
+                const uint32_t pos = out_w + (uint32_t) __popc(bal & lt);
+                uint32_t lrec = out_b + incl - pc;
+                words[pos] = make_uint4(wbits, (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit) |
+                                                   ((uint32_t) sec << kWordMetaSectorShift) | mtag, lrec, 0u);
+                // palette references of the word's pixels, in bit order: index | (interval 2 ? 0x8000 : 0)
+                while (wbits) {
+                    const int bit = __ffs((int) wbits) - 1;
+                    wbits &= wbits - 1;
+                    const int xt = k * 32 + bit;
+                    const uint32_t pv = s_pix[warp][o ? W - 1 - xt : xt];
+                    lpal[lrec++] = (uint16_t) ((pv & 0x7FFu) | (((pv >> 11) & 7u) != (uint32_t) sec ? 0x8000u : 0u));
+                }
             }
-            out += (uint32_t) __popc(bal);
-            px_before += __shfl_sync(0xffffffffu, incl, 31);
+            out_w += (uint32_t) __popc(bal);
+            out_b += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
@@ -612,29 +623,31 @@ bool cand_kernel_supported(int xy_shift, const PlaneGeom &g)
     return cand_config<128>(xy_shift, g, 24).ok;
 }
 
-void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, uint32_t *wcount, cudaStream_t s)
+void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,
+                        uint32_t *wcount, uint32_t *bcount, cudaStream_t s)
 {
     for (int m0 = 0; m0 < n_masks; m0 += 32768) {
         int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
         dim3 grid((H + 3) / 4, cnt);
-        words_count_kernel<<<grid, 128, 0, s>>>(masks + m0, W, H, mirror, wcount + (size_t) m0 * (H + 1));
+        words_count_kernel<<<grid, 128, 0, s>>>(masks + m0, W, H, mirror, class_tab, wcount + (size_t) m0 * (H + 1), bcount + (size_t) m0 * (H + 1));
     }
 }
 
-void launch_words_group_rows(uint32_t *wcount, int n_masks, int H, uint32_t *grow, cudaStream_t s)
+void launch_words_group_rows(uint32_t *count, int n_masks, int H, uint32_t *grow, cudaStream_t s)
 {
     const int n_groups = (n_masks + CDS_PALETTE_GROUP - 1) / CDS_PALETTE_GROUP;
     if (n_groups == 0) return;
     dim3 grid((H + 127) / 128, n_groups);
-    words_group_rows_kernel<<<grid, 128, 0, s>>>(wcount, n_masks, H, grow);
+    words_group_rows_kernel<<<grid, 128, 0, s>>>(count, n_masks, H, grow);
 }
 
-void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const uint32_t *gstart, uint4 *words, cudaStream_t s)
+void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,
+                       const uint32_t *gstart, const uint32_t *bstart, const uint32_t *boff, uint4 *words, uint16_t *lpal, cudaStream_t s)
 {
     for (int m0 = 0; m0 < n_masks; m0 += 32768) {
         int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
         dim3 grid((H + 3) / 4, cnt);
-        words_fill_kernel<<<grid, 128, 0, s>>>(masks + m0, m0, W, H, mirror, gstart, words);
+        words_fill_kernel<<<grid, 128, 0, s>>>(masks + m0, m0, W, H, mirror, class_tab, gstart, bstart, boff, words, lpal);
     }
 }
 

@@ -30,6 +30,7 @@ struct MaskDesc {
     const cds_mask_record *records;   // P records, ascending pixel index
     const uint32_t *rowstart;         // H + 1 entries: records of image row y are [rowstart[y], rowstart[y+1])
     const uint32_t *crec;             // P compact records (cds_common.h) or nullptr when the mask's palette group is wide
+    const uint32_t *classes;          // P colour classes (sector * CDS_NUM_RANKS + rank, or CDS_CLASS_NONE_INDEX)
     const uint32_t *wstart;           // H + 1 entries: offset of this mask's entries inside its group's run of each row (cds_cand.cuh)
     int P;
     int pad;
@@ -40,6 +41,7 @@ struct PaletteGroup {
     const uint2 *palette;             // n_pal entries, or nullptr: the group uses the 16-byte records
     const uint4 *words;               // base of the word lists of the candidate kernel (cds_cand.cuh), or nullptr
     const uint32_t *gstart;           // H + 1 entries: this group's entries of image row y are words[gstart[y] .. gstart[y+1])
+    const uint16_t *lpal;             // palette references of the entries' set bits (cds_cand.cuh)
     int n_pal;
     int pad;
 };

@@ -122,9 +122,10 @@ struct cds_maskset {
     std::vector<cds::MaskDesc *> d_descs;              // per device, rebuilt when dirty
     std::vector<cds::PaletteGroup *> d_groups;         // per device, one per CDS_PALETTE_GROUP masks
     std::vector<uint2 *> d_palettes;                   // per device, [n_groups][CDS_PALETTE_SIZE]
-    std::vector<uint32_t *> d_words;                   // per device, word lists of all masks (cds_cand.cuh)
-    std::vector<uint32_t *> d_wstart;                  // per device, [M][H+1] word-list row starts
-    int n_compact_groups = 0;                          // informational
+    std::vector<uint32_t *> d_words;                   // per device, word-list entries of all groups followed by their palette references (cds_cand.cuh)
+    std::vector<uint32_t *> d_wstart;                  // per device, per-mask offsets and per-group row starts of the word lists
+    int n_compact_groups = 0;                          // groups whose colour classes fit a shared-memory palette
+    bool words_built = false;                          // the candidate kernel's word lists exist on every device
     bool descs_dirty = true;
     cds_status sync_descs();
 };
