@@ -140,7 +140,7 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const u
 {
     constexpr int NS = Offsets<NRINGS>::N;
     constexpr int S = 2 * NRINGS;
-    const uint32_t mi = (cand.x >> 22) & 127u;
+    const uint32_t mi = (cand.x >> 22) & 255u;
     const uint2 pe = s_pal[pr & (CDS_PALETTE_SIZE - 1)];
     const uint32_t iv = (pr & 0x8000u) ? pe.y : pe.x;                           // the interval that lives in this candidate's sector
     const uint32_t lo = (iv & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     if (c) {
                         const uint32_t orient = (w.y >> kWordMetaOrientBit) & 1u;
                         mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] =
-                            make_uint4(c, (xw << 5) | (y << 11) | (orient << 21) | (w.y & (127u << kWordMetaMaskShift)), w.z, w.x);
+                            make_uint4(c, (xw << 5) | (y << 11) | (orient << 21) | (w.y & (255u << kWordMetaMaskShift)), w.z, w.x);
                     }
                     wt += (uint32_t) __popc(has);
                     if (wt - wh >= 32) {
@@ -620,7 +620,7 @@ bool cand_kernel_supported(int xy_shift, const PlaneGeom &g)
     if (!(xy_shift == 0 || xy_shift == 2 || xy_shift == 4)) return false;
     if (xy_shift > g.guard || xy_shift > g.pitch - g.W || xy_shift > kPrePad) return false;
     if (g.W > 2048 || g.H > 1024) return false;
-    return cand_config<128>(xy_shift, g, 24).ok;
+    return cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok;
 }
 
 void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,
@@ -666,20 +666,20 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     }
     cudaMemsetAsync(g_cand_counter[dev], 0, sizeof(unsigned long long), s);
     // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket
-    static const int warps_env = env_int("CDSGPU_CAND_WARPS", 24);
+    static const int warps_env = env_int("CDSGPU_CAND_WARPS", 28);
     static const int chunk_env = env_int("CDSGPU_CAND_CHUNK", 128);
-#define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<128, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev)
+#define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<CDS_PALETTE_GROUP, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev)
     if (chunk_env == 256) {
-        if (warps_env == 28) return CDS_CAND_LAUNCH(28, 256);
-        return CDS_CAND_LAUNCH(24, 256);
+        if (warps_env == 24) return CDS_CAND_LAUNCH(24, 256);
+        return CDS_CAND_LAUNCH(28, 256);
     }
     if (chunk_env == 64) {
-        if (warps_env == 28) return CDS_CAND_LAUNCH(28, 64);
-        return CDS_CAND_LAUNCH(24, 64);
+        if (warps_env == 24) return CDS_CAND_LAUNCH(24, 64);
+        return CDS_CAND_LAUNCH(28, 64);
     }
     if (warps_env == 16) return CDS_CAND_LAUNCH(16, 128);
-    if (warps_env == 28) return CDS_CAND_LAUNCH(28, 128);
-    return CDS_CAND_LAUNCH(24, 128);
+    if (warps_env == 24) return CDS_CAND_LAUNCH(24, 128);
+    return CDS_CAND_LAUNCH(28, 128);
 #undef CDS_CAND_LAUNCH
 }
 

@@ -15,7 +15,7 @@ namespace cds {
 // sector, column) with a row-start table gstart[H+1], so the entries that concern a band of rows are one contiguous range that
 // is cut into equal tickets regardless of mask boundaries.  One 16-byte entry per word:
 //     bits : the word
-//     meta : y | word column << 10 | orientation << 16 | sector << 17 | mask index inside the group << 22   (H <= 1024, W <= 2048)
+//     meta : y | word column << 10 | orientation << 16 | sector << 17 | mask index inside the group << 22 (8 bits)   (H <= 1024, W <= 2048)
 //     lrec : index into the group's `lpal` array of the palette reference of the word's LOWEST set bit; set bit b has
 //            lpal[lrec + popc(bits below b)] = palette index | 0x8000 when the pixel is in this list through its interval 2
 //     0
