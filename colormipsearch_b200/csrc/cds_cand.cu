@@ -620,7 +620,7 @@ bool cand_kernel_supported(int xy_shift, const PlaneGeom &g)
     if (!(xy_shift == 0 || xy_shift == 2 || xy_shift == 4)) return false;
     if (xy_shift > g.guard || xy_shift > g.pitch - g.W || xy_shift > kPrePad) return false;
     if (g.W > 2048 || g.H > 1024) return false;
-    return cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok;
+    return cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 16).ok;
 }
 
 void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,
@@ -665,21 +665,22 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
         if (cudaMalloc(&g_cand_counter[dev], sizeof(unsigned long long)) != cudaSuccess) return 0;
     }
     cudaMemsetAsync(g_cand_counter[dev], 0, sizeof(unsigned long long), s);
-    // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket
+    // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket.  More warps need more
+    // shared memory for their queues; when the band stages no longer fit (xyShift 4: 34 accumulators per mask) fewer are used.
     static const int warps_env = env_int("CDSGPU_CAND_WARPS", 28);
     static const int chunk_env = env_int("CDSGPU_CAND_CHUNK", 128);
+    int warps = warps_env;
+    if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok) warps = 24;
+    if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24).ok) warps = 16;
 #define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<CDS_PALETTE_GROUP, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev)
     if (chunk_env == 256) {
-        if (warps_env == 24) return CDS_CAND_LAUNCH(24, 256);
-        return CDS_CAND_LAUNCH(28, 256);
+        if (warps >= 28) return CDS_CAND_LAUNCH(28, 256);
+        if (warps >= 24) return CDS_CAND_LAUNCH(24, 256);
+        return CDS_CAND_LAUNCH(16, 256);
     }
-    if (chunk_env == 64) {
-        if (warps_env == 24) return CDS_CAND_LAUNCH(24, 64);
-        return CDS_CAND_LAUNCH(28, 64);
-    }
-    if (warps_env == 16) return CDS_CAND_LAUNCH(16, 128);
-    if (warps_env == 24) return CDS_CAND_LAUNCH(24, 128);
-    return CDS_CAND_LAUNCH(28, 128);
+    if (warps >= 28) return CDS_CAND_LAUNCH(28, 128);
+    if (warps >= 24) return CDS_CAND_LAUNCH(24, 128);
+    return CDS_CAND_LAUNCH(16, 128);
 #undef CDS_CAND_LAUNCH
 }
 
