@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "cds_runtime.h"
@@ -15,6 +16,54 @@ using namespace cds;
 namespace cds {
 static thread_local std::string g_tls_err;
 void set_tls_error(const std::string &msg) { g_tls_err = msg; }
+}  // namespace cds
+
+namespace cds {
+static constexpr size_t kPoolLimit = (size_t) 8 << 30;
+
+cudaError_t DevPool::alloc(void **p, size_t bytes)
+{
+    bytes = std::max<size_t>((bytes + 255) / 256 * 256, 256);
+    auto it = free_blocks.lower_bound(bytes);
+    if (it != free_blocks.end() && it->first <= std::max<size_t>(2 * bytes, (size_t) 1 << 20)) {
+        *p = it->second;
+        live[*p] = it->first;
+        cached_bytes -= it->first;
+        free_blocks.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && !free_blocks.empty()) {      // out of memory with blocks in the cache: give them back and retry
+        cudaGetLastError();
+        for (auto &kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached_bytes = 0;
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) live[*p] = bytes;
+    return e;
+}
+
+void DevPool::free(void *p)
+{
+    if (!p) return;
+    auto it = live.find(p);
+    if (it == live.end()) { cudaFree(p); return; }
+    const size_t bytes = it->second;
+    live.erase(it);
+    if (cached_bytes + bytes > kPoolLimit) { cudaFree(p); return; }
+    free_blocks.emplace(bytes, p);
+    cached_bytes += bytes;
+}
+
+void DevPool::release_all()
+{
+    for (auto &kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+    for (auto &kv : live) cudaFree(kv.first);
+    live.clear();
+}
 }  // namespace cds
 
 cds_status cds_ctx::fail(cds_status code, const std::string &msg) const
@@ -132,6 +181,11 @@ extern "C" cds_status cds_ctx_create(const int32_t *device_ids, int32_t n_dev, c
     for (DevState &d : ctx->devs) {
         cds_status s = ctx->check(cudaSetDevice(d.dev), "cudaSetDevice");
         if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < 2 && s == CDS_OK; i++) {
+            s = ctx->check(cudaEventCreateWithFlags(&d.up_done[i], cudaEventDisableTiming), "cudaEventCreate");
+            if (s == CDS_OK) s = ctx->check(cudaEventCreateWithFlags(&d.up_free[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
         if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev0), "cudaEventCreate");
         if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev1), "cudaEventCreate");
         if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev2), "cudaEventCreate");
@@ -166,10 +220,16 @@ extern "C" void cds_ctx_destroy(cds_ctx *ctx)
         for (int i = 0; i < 4; i++) if (d.scratch[i]) cudaFree(d.scratch[i]);
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
         if (d.pair_plane) cudaFree(d.pair_plane);
+        d.pool.release_all();
         d.sb.release();
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev2) cudaEventDestroy(d.ev2);
+        for (int i = 0; i < 2; i++) {
+            if (d.up_done[i]) cudaEventDestroy(d.up_done[i]);
+            if (d.up_free[i]) cudaEventDestroy(d.up_free[i]);
+        }
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     cudaGetLastError();
@@ -497,13 +557,13 @@ extern "C" void cds_maskset_destroy(cds_maskset *ms)
         cudaStreamSynchronize(ctx->devs[d].stream);
         if (d < ms->store.size()) {
             cds_maskset::DevStore &st = ms->store[d];
-            for (cds_maskset::Arena *a : {&st.records, &st.classes, &st.crec, &st.rowstart}) if (a->p) cudaFree(a->p);
+            for (cds_maskset::Arena *a : {&st.records, &st.classes, &st.crec, &st.rowstart}) ctx->devs[d].pool.free(a->p);
         }
-        if (ms->d_descs[d]) cudaFree(ms->d_descs[d]);
-        if (ms->d_groups[d]) cudaFree(ms->d_groups[d]);
-        if (ms->d_palettes[d]) cudaFree(ms->d_palettes[d]);
-        if (ms->d_words[d]) cudaFree(ms->d_words[d]);
-        if (ms->d_wstart[d]) cudaFree(ms->d_wstart[d]);
+        ctx->devs[d].pool.free(ms->d_descs[d]);
+        ctx->devs[d].pool.free(ms->d_groups[d]);
+        ctx->devs[d].pool.free(ms->d_palettes[d]);
+        ctx->devs[d].pool.free(ms->d_words[d]);
+        ctx->devs[d].pool.free(ms->d_wstart[d]);
     }
     cudaGetLastError();
     delete ms;
@@ -526,11 +586,11 @@ static cds_status arena_reserve(cds_ctx *ctx, DevState &ds, cds_maskset::Arena &
     size_t cap = std::max<size_t>(a.cap * 2, a.used + more);
     cap = std::max<size_t>(cap, (size_t) 1 << 20);
     void *np = nullptr;
-    CDS_CUDA(ctx, cudaMalloc(&np, cap));
+    CDS_CUDA(ctx, ds.pool.alloc(&np, cap));
     if (a.p) {
         if (a.used) CDS_CUDA(ctx, cudaMemcpyAsync(np, a.p, a.used, cudaMemcpyDeviceToDevice, ds.stream));
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
-        cudaFree(a.p);
+        ds.pool.free(a.p);
     }
     a.p = np;
     a.cap = cap;
@@ -562,10 +622,26 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
     const size_t first_mask = ms->sizes.size();
     const size_t rec_used0 = s0.records.used, cls_used0 = s0.classes.used, crec_used0 = s0.crec.used, rs_used0 = s0.rowstart.used;
     CDS_TRY(arena_reserve(ctx, d0, s0.rowstart, (size_t) n * (H + 1) * sizeof(uint32_t)));
+    // uploads run on the copy stream one chunk ahead of the preparation kernels (which need a host round trip per chunk)
+    static const bool overlap = std::getenv("CDSGPU_MASK_OVERLAP") ? std::atoi(std::getenv("CDSGPU_MASK_OVERLAP")) != 0 : true;
+    cudaStream_t up_stream = overlap ? d0.copy_stream : d0.stream;
+    auto enqueue_upload = [&](int i0) -> cds_status {
+        const int cnt = std::min(kChunk, n - i0);
+        const int slot = (i0 / kChunk) & 1;
+        uint8_t *stage = (uint8_t *) d0.staging + (size_t) slot * kChunk * img_bytes;
+        if (i0 >= 2 * kChunk) CDS_CUDA(ctx, cudaStreamWaitEvent(up_stream, d0.up_free[slot], 0));
+        CDS_CUDA(ctx, cudaMemcpyAsync(stage, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, up_stream));
+        CDS_CUDA(ctx, cudaEventRecord(d0.up_done[slot], up_stream));
+        return CDS_OK;
+    };
+    CDS_CUDA(ctx, cudaStreamSynchronize(d0.stream));        // earlier users of the staging buffer are done
+    CDS_TRY(enqueue_upload(0));
     for (int i0 = 0; i0 < n; i0 += kChunk) {
         const int cnt = std::min(kChunk, n - i0);
-        uint8_t *stage = (uint8_t *) d0.staging + (size_t) ((i0 / kChunk) & 1) * kChunk * img_bytes;
-        CDS_CUDA(ctx, cudaMemcpyAsync(stage, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, d0.stream));
+        const int slot = (i0 / kChunk) & 1;
+        uint8_t *stage = (uint8_t *) d0.staging + (size_t) slot * kChunk * img_bytes;
+        if (i0 + kChunk < n) CDS_TRY(enqueue_upload(i0 + kChunk));
+        CDS_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d0.up_done[slot], 0));
         ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
         uint32_t *rowstart = (uint32_t *) ((uint8_t *) s0.rowstart.p + s0.rowstart.used);
         launch_mask_count_rows(stage, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, rowstart, d0.stream);
@@ -578,14 +654,18 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
         uint64_t total = 0;
         const uint64_t base = s0.records.used / sizeof(cds_mask_record);      // records, classes and crec advance in lock step
         for (int i = 0; i < cnt; i++) { off[i] = base + total; total += (uint64_t) sizes[i]; }
-        CDS_TRY(arena_reserve(ctx, d0, s0.records, total * sizeof(cds_mask_record)));
-        CDS_TRY(arena_reserve(ctx, d0, s0.classes, total * sizeof(uint32_t)));
-        CDS_TRY(arena_reserve(ctx, d0, s0.crec, total * sizeof(uint32_t)));
+        // size the arenas once per call from the first chunk's average mask size (they still grow if the guess is short)
+        uint64_t want = total;
+        if (i0 == 0 && n > cnt) want = std::max<uint64_t>(total, (uint64_t) ((double) total / cnt * n * 1.15));
+        CDS_TRY(arena_reserve(ctx, d0, s0.records, want * sizeof(cds_mask_record)));
+        CDS_TRY(arena_reserve(ctx, d0, s0.classes, want * sizeof(uint32_t)));
+        CDS_TRY(arena_reserve(ctx, d0, s0.crec, want * sizeof(uint32_t)));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_off, off.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, d0.stream));
         launch_mask_write_records(stage, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, rowstart, d_off, d0.d_rank_tab, class_tab,
                                   (cds_mask_record *) s0.records.p, (uint32_t *) s0.classes.p, d0.stream);
         ctx->stats.kernel_launches++;
         CDS_CUDA(ctx, cudaGetLastError());
+        CDS_CUDA(ctx, cudaEventRecord(d0.up_free[slot], d0.stream));        // the staging half may be overwritten
         // `off` is pageable host memory: the copy above has been staged by the time cudaMemcpyAsync returns
         s0.records.used += total * sizeof(cds_mask_record);
         s0.classes.used += total * sizeof(uint32_t);
@@ -655,11 +735,11 @@ cds_status cds_maskset::sync_descs()
             refs[mi].P = sizes[mi];
             refs[mi].pad = 0;
         }
-        if (d_descs[d]) { cudaFree(d_descs[d]); d_descs[d] = nullptr; }
-        if (d_groups[d]) { cudaFree(d_groups[d]); d_groups[d] = nullptr; }
-        if (d_palettes[d]) { cudaFree(d_palettes[d]); d_palettes[d] = nullptr; }
-        if (d_words[d]) { cudaFree(d_words[d]); d_words[d] = nullptr; }
-        if (d_wstart[d]) { cudaFree(d_wstart[d]); d_wstart[d] = nullptr; }
+        if (d_descs[d]) { ds.pool.free(d_descs[d]); d_descs[d] = nullptr; }
+        if (d_groups[d]) { ds.pool.free(d_groups[d]); d_groups[d] = nullptr; }
+        if (d_palettes[d]) { ds.pool.free(d_palettes[d]); d_palettes[d] = nullptr; }
+        if (d_words[d]) { ds.pool.free(d_words[d]); d_words[d] = nullptr; }
+        if (d_wstart[d]) { ds.pool.free(d_wstart[d]); d_wstart[d] = nullptr; }
         std::vector<PaletteGroup> groups(std::max(n_groups, 1));
         for (auto &g : groups) { g.palette = nullptr; g.words = nullptr; g.gstart = nullptr; g.lpal = nullptr; g.n_pal = 0; g.pad = 0; }
         if (compact_ok) {
@@ -670,11 +750,11 @@ cds_status cds_maskset::sync_descs()
             int32_t *d_npal = nullptr;
             const cds_class_interval *class_tab = nullptr;
             cds_status st = ctx->class_table_on(ds, params.z_tolerance, &class_tab);
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_refs, refs.size() * sizeof(MaskClassRef)), "cudaMalloc(class refs)");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_flags, slots * sizeof(uint32_t)), "cudaMalloc(palette flags)");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_pidx, slots * sizeof(uint32_t)), "cudaMalloc(palette index)");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_npal, n_groups * sizeof(int32_t)), "cudaMalloc(palette sizes)");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_palettes[d], (size_t) n_groups * CDS_PALETTE_SIZE * sizeof(uint2)), "cudaMalloc(palettes)");
+            if (st == CDS_OK) st = ctx->check(ds.pool.alloc((void **) &d_refs, refs.size() * sizeof(MaskClassRef)), "cudaMalloc(class refs)");
+            if (st == CDS_OK) st = ctx->check(ds.pool.alloc((void **) &d_flags, slots * sizeof(uint32_t)), "cudaMalloc(palette flags)");
+            if (st == CDS_OK) st = ctx->check(ds.pool.alloc((void **) &d_pidx, slots * sizeof(uint32_t)), "cudaMalloc(palette index)");
+            if (st == CDS_OK) st = ctx->check(ds.pool.alloc((void **) &d_npal, n_groups * sizeof(int32_t)), "cudaMalloc(palette sizes)");
+            if (st == CDS_OK) st = ctx->check(ds.pool.alloc((void **) &d_palettes[d], (size_t) n_groups * CDS_PALETTE_SIZE * sizeof(uint2)), "cudaMalloc(palettes)");
             if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_refs, refs.data(), refs.size() * sizeof(MaskClassRef), cudaMemcpyHostToDevice, ds.stream), "class refs H2D");
             if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_flags, 0, slots * sizeof(uint32_t), ds.stream), "memset(palette flags)");
             std::vector<int32_t> n_pal(n_groups, 0);
@@ -688,10 +768,10 @@ cds_status cds_maskset::sync_descs()
             }
             if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(n_pal.data(), d_npal, n_groups * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "palette sizes D2H");
             if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "palette build");
-            if (d_refs) cudaFree(d_refs);
-            if (d_flags) cudaFree(d_flags);
-            if (d_pidx) cudaFree(d_pidx);
-            if (d_npal) cudaFree(d_npal);
+            ds.pool.free(d_refs);
+            ds.pool.free(d_flags);
+            ds.pool.free(d_pidx);
+            ds.pool.free(d_npal);
             if (st != CDS_OK) return st;
             int compact = 0;
             for (int g = 0; g < n_groups; g++) {
@@ -703,8 +783,8 @@ cds_status cds_maskset::sync_descs()
             }
             n_compact_groups = compact;
         }
-        CDS_CUDA(ctx, cudaMalloc(&d_descs[d], h.size() * sizeof(MaskDesc)));
-        CDS_CUDA(ctx, cudaMalloc(&d_groups[d], groups.size() * sizeof(PaletteGroup)));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_descs[d], h.size() * sizeof(MaskDesc)));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_groups[d], groups.size() * sizeof(PaletteGroup)));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
         // word lists of the candidate kernel (cds_cand.cuh): per-(mask, row) counts, per-(group, row) runs, row starts, fill.
         // They reference the groups' palettes, so they exist only when every group is compact.
@@ -716,8 +796,8 @@ cds_status cds_maskset::sync_descs()
             const cds_class_interval *class_tab = nullptr;
             cds_status st = ctx->class_table_on(ds, params.z_tolerance, &class_tab);
             // d_wstart: per-mask entry offsets [M][H+1], per-mask bit offsets [M][H+1], entry row starts [G][H+1], bit row starts [G][H+1]
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_wstart[d], (2 * ms_n + 2 * gs_n) * sizeof(uint32_t)), "cudaMalloc(word row starts)");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_grow, 2 * gs_n * sizeof(uint32_t)), "cudaMalloc(group rows)");
+            if (st == CDS_OK) st = ctx->check(ds.pool.alloc((void **) &d_wstart[d], (2 * ms_n + 2 * gs_n) * sizeof(uint32_t)), "cudaMalloc(word row starts)");
+            if (st == CDS_OK) st = ctx->check(ds.pool.alloc((void **) &d_grow, 2 * gs_n * sizeof(uint32_t)), "cudaMalloc(group rows)");
             if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_grow, 0, 2 * gs_n * sizeof(uint32_t), ds.stream), "memset(group rows)");
             std::vector<uint32_t> grow(2 * gs_n, 0);
             uint32_t *d_wcount = d_wstart[d], *d_bcount = d_wstart[d] + ms_n;
@@ -730,7 +810,7 @@ cds_status cds_maskset::sync_descs()
             }
             if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(grow.data(), d_grow, 2 * gs_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds.stream), "group rows D2H");
             if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "word count");
-            if (d_grow) cudaFree(d_grow);
+            ds.pool.free(d_grow);
             if (st != CDS_OK) return st;
             uint64_t total[2] = {0, 0};
             for (int a = 0; a < 2; a++)
@@ -742,7 +822,7 @@ cds_status cds_maskset::sync_descs()
             if (total[0] < ((uint64_t) 1 << 32) && total[1] < ((uint64_t) 1 << 32)) {
                 uint32_t *d_gstart = d_wstart[d] + 2 * ms_n, *d_bstart = d_gstart + gs_n;
                 // d_words: the entries, then the palette references
-                CDS_CUDA(ctx, cudaMalloc(&d_words[d], std::max<uint64_t>(total[0], 1) * sizeof(uint4) + std::max<uint64_t>(total[1], 1) * sizeof(uint16_t)));
+                CDS_CUDA(ctx, ds.pool.alloc((void **) &d_words[d], std::max<uint64_t>(total[0], 1) * sizeof(uint4) + std::max<uint64_t>(total[1], 1) * sizeof(uint16_t)));
                 uint4 *d_entries = reinterpret_cast<uint4 *>(d_words[d]);
                 uint16_t *d_lpal = reinterpret_cast<uint16_t *>(d_entries + std::max<uint64_t>(total[0], 1));
                 CDS_CUDA(ctx, cudaMemcpyAsync(d_gstart, grow.data(), 2 * gs_n * sizeof(uint32_t), cudaMemcpyHostToDevice, ds.stream));

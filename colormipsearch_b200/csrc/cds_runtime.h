@@ -36,9 +36,23 @@ struct StreamBufs {
     void release();
 };
 
+// Caching device allocator of one device: mask sets are created and destroyed once per batched search, and cudaMalloc /
+// cudaFree cost milliseconds each (and synchronise the device).  Freed blocks are kept (up to a byte limit) and handed
+// out again to requests of similar size.  Everything that uses pooled blocks runs on the device's main stream.
+struct DevPool {
+    std::multimap<size_t, void *> free_blocks;      // by size
+    std::map<void *, size_t> live;                  // blocks handed out
+    size_t cached_bytes = 0;
+    cudaError_t alloc(void **p, size_t bytes);
+    void free(void *p);
+    void release_all();
+};
+
 struct DevState {
     int dev = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                        // uploads that overlap kernels on `stream`
+    cudaEvent_t up_done[2] = {nullptr, nullptr}, up_free[2] = {nullptr, nullptr};   // double-buffered staging hand-off
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;   // match kernel start / end, search end
     uint16_t *d_rank_tab = nullptr;
     std::map<uint64_t, cds_class_interval *> d_class_tabs;   // keyed by the bits of zTolerance
@@ -49,6 +63,7 @@ struct DevState {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device scratch (scores, min scores, keys, counts)
     size_t scratch_bytes[4] = {0, 0, 0, 0};
     StreamBufs sb;
+    DevPool pool;
     uint32_t *pair_plane = nullptr;   // one code plane + one score word for cds_score_pair_rgb
     int pair_W = 0, pair_H = 0;
 };
