@@ -90,7 +90,7 @@ struct CandSmem {
         stage_off = o; o += (size_t) kStages * (stage_words + kPrePad) * 4;
         bits_off = o;  o += (size_t) kStages * bits_words * 4;
         pal_off = o;   o += (size_t) CDS_PALETTE_SIZE * 8;
-        wqueue_off = o; o += (size_t) n_warps * kWordQueue * 16;
+        wqueue_off = o; o += (size_t) n_warps * kWordQueue * 8;
         queue_off = o; o += (size_t) n_warps * kQueue * 8;
         bar_off = o;   o += 2 * kStages * 8;
         item_off = o;  o += 16;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const uint32_t *s_bits = reinterpret_cast<const uint32_t *>(smem_raw + L.bits_off);  // [kStages][R * bpitch]
     uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
     uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + L.queue_off);                  // [NCW][kQueue] candidates
-    uint4 *s_wqueue = reinterpret_cast<uint4 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] words with candidates
+    uint2 *s_wqueue = reinterpret_cast<uint2 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] {candidate bits, entry index} of words with candidates
     int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
     uint2 *s_band = reinterpret_cast<uint2 *>(smem_raw + L.band_off);                   // [kStages] range of the group's word list inside the staged band
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const uint4 *gwords = nullptr;                   // word list of the current group
     const uint16_t *glpal = nullptr;                 // palette references of its entries' set bits
     uint2 *myq = s_queue + warp * kQueue;
-    uint4 *mywq = s_wqueue + warp * kWordQueue;
+    uint2 *mywq = s_wqueue + warp * kWordQueue;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t acc_base = smem_u32(s_acc);
     for (;;) {
@@ -293,9 +293,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 if (pend) run_pending();
                 pend_cand = cand; pend_pr = pr; pend = true;
             };
-            auto peel = [&](uint4 we) {
-                uint32_t c = we.x;
-                const uint32_t base = we.y, lrec = we.z, wbits = we.w;
+            // Peels the candidate bits `c` of 32 queued words (one word per lane, `e` its list entry; c = 0 for idle lanes) into the
+            // candidate queue, lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
+            auto peel = [&](uint32_t c, uint4 e) {
+                const uint32_t wbits = e.x, lrec = e.z;
+                const uint32_t base = (((e.y >> kWordMetaYBits) & 63u) << 5) | ((e.y & ((1u << kWordMetaYBits) - 1)) << 11) |
+                                      (((e.y >> kWordMetaOrientBit) & 1u) << 21) | (e.y & (255u << kWordMetaMaskShift));
                 unsigned bal = __ballot_sync(0xffffffffu, c != 0);
                 while (bal) {
                     if (c) {
@@ -317,6 +320,17 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     bal = __ballot_sync(0xffffffffu, c != 0);
                 }
             };
+            // A full batch of words with candidates: re-read their list entries (the scan only carried bits and position), peel
+            // the batch whose entries were requested one batch earlier.
+            uint32_t wpend_c = 0;
+            uint4 wpend_e = make_uint4(0u, 0u, 0u, 0u);
+            bool wpend = false;
+            auto submit_words = [&](uint2 qe, bool live) {
+                uint4 e = make_uint4(0u, 0u, 0u, 0u);
+                if (live) e = __ldg(gwords + qe.y);
+                if (wpend) peel(wpend_c, wpend_e);
+                wpend_c = live ? qe.x : 0u; wpend_e = e; wpend = true;
+            };
 
             for (;;) {
                 int tk = 0;
@@ -326,28 +340,27 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 // a ticket = kChunk consecutive entries of the group's word list; entries carry their mask's index
                 const uint32_t seg0 = range.x + (uint32_t) tk * kChunk;
                 const uint32_t seg1 = min(seg0 + kChunk, range.y);
+                // the scan reads only the first 8 bytes {bits, meta} of the 16-byte entries, three iterations ahead; lanes past the
+                // end carry an empty word on a valid row
                 const uint4 *wl = gwords;
-
-                // word entries {bits, meta, rec, -} are prefetched three iterations ahead; lanes past the end carry an empty
-                // word on a valid row
-                const uint4 idle = make_uint4(0u, (uint32_t) y0, 0u, 0u);
-                uint4 w0 = idle, w1 = idle, w2 = idle;
+                const uint2 idle = make_uint2(0u, (uint32_t) y0);
+                uint2 w0 = idle, w1 = idle, w2 = idle;
                 {
                     uint32_t i = seg0 + lane;
-                    if (i < seg1) w0 = __ldg(wl + i);
+                    if (i < seg1) w0 = __ldg(reinterpret_cast<const uint2 *>(wl + i));
                     i += 32;
-                    if (i < seg1) w1 = __ldg(wl + i);
+                    if (i < seg1) w1 = __ldg(reinterpret_cast<const uint2 *>(wl + i));
                     i += 32;
-                    if (i < seg1) w2 = __ldg(wl + i);
+                    if (i < seg1) w2 = __ldg(reinterpret_cast<const uint2 *>(wl + i));
                 }
                 for (uint32_t base = seg0; base < seg1; base += 32) {
-                    const uint4 w = w0;
+                    const uint2 w = w0;
                     w0 = w1;
                     w1 = w2;
                     w2 = idle;
                     {
                         const uint32_t i = base + 96 + lane;
-                        if (i < seg1) w2 = __ldg(wl + i);
+                        if (i < seg1) w2 = __ldg(reinterpret_cast<const uint2 *>(wl + i));
                     }
                     const uint32_t y = w.y & ((1u << kWordMetaYBits) - 1);
                     const uint32_t xw = (w.y >> kWordMetaYBits) & 63u;
@@ -355,27 +368,25 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     const uint32_t c = w.x & bits[((int) y - y0) * rowpitch + (int) sec * p.bpitch + (int) xw];    // mask pixels of this word that can match
                     // words with candidates are compacted first, so that the bit peeling runs on full warps
                     const unsigned has = __ballot_sync(0xffffffffu, c != 0);
-                    if (c) {
-                        const uint32_t orient = (w.y >> kWordMetaOrientBit) & 1u;
-                        mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] =
-                            make_uint4(c, (xw << 5) | (y << 11) | (orient << 21) | (w.y & (255u << kWordMetaMaskShift)), w.z, w.x);
-                    }
+                    if (c) mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] = make_uint2(c, base + lane);
                     wt += (uint32_t) __popc(has);
                     if (wt - wh >= 32) {
                         __syncwarp();
-                        const uint4 we = mywq[(wh + lane) & (kWordQueue - 1)];
+                        const uint2 qe = mywq[(wh + lane) & (kWordQueue - 1)];
                         wh += 32;
-                        peel(we);
+                        submit_words(qe, true);
                     }
                 }
             }
             // the band's last, partly filled batches: everything queued reads this stage, so it is evaluated before the release
             if (wt != wh) {
                 __syncwarp();
-                uint4 we = make_uint4(0u, 0u, 0u, 0u);
-                if (lane < (int) (wt - wh)) we = mywq[(wh + lane) & (kWordQueue - 1)];
-                peel(we);
+                const bool live = lane < (int) (wt - wh);
+                uint2 qe = make_uint2(0u, 0u);
+                if (live) qe = mywq[(wh + lane) & (kWordQueue - 1)];
+                submit_words(qe, live);
             }
+            if (wpend) peel(wpend_c, wpend_e);
             if (qt != qh) {
                 __syncwarp();
                 const bool live = lane < (int) (qt - qh);
@@ -668,7 +679,7 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket.  More warps need more
     // shared memory for their queues; when the band stages no longer fit (xyShift 4: 34 accumulators per mask) fewer are used.
     static const int warps_env = env_int("CDSGPU_CAND_WARPS", 28);
-    static const int chunk_env = env_int("CDSGPU_CAND_CHUNK", 128);
+    static const int chunk_env = env_int("CDSGPU_CAND_CHUNK", 256);
     int warps = warps_env;
     if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok) warps = 24;
     if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24).ok) warps = 16;
