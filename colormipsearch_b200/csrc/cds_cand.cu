@@ -245,6 +245,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const uint16_t *glpal = nullptr;                 // palette references of its entries' set bits
     uint2 *myq = s_queue + warp * kQueue;
     uint2 *mywq = s_wqueue + warp * kWordQueue;
+    const uint32_t mywq_addr = smem_u32(mywq);
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t acc_base = smem_u32(s_acc);
     for (;;) {
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const int stage = q & 1;
             if (b > 0) mbar_wait(smem_u32(s_full + stage), (q >> 1) & 1);
             const uint32_t *band = s_stage + (size_t) stage * stage_stride;
-            const uint32_t *bits = s_bits + (size_t) stage * bits_words;
+            const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - (size_t) (b * R) * rowpitch;   // indexed by the entries' absolute occupancy word index
             const int y0 = b * R;
             const uint2 range = s_band[stage];                                   // the group's word-list entries of this band
             const int n_tickets = (int) ((range.y - range.x + kChunk - 1) / kChunk);
@@ -297,8 +298,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             // candidate queue, lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
             auto peel = [&](uint32_t c, uint4 e) {
                 const uint32_t wbits = e.x, lrec = e.z;
-                const uint32_t base = (((e.y >> kWordMetaYBits) & 63u) << 5) | ((e.y & ((1u << kWordMetaYBits) - 1)) << 11) |
-                                      (((e.y >> kWordMetaOrientBit) & 1u) << 21) | (e.y & (255u << kWordMetaMaskShift));
+                const uint32_t base = (((e.w >> kWordMetaYBits) & 63u) << 5) | ((e.w & ((1u << kWordMetaYBits) - 1)) << 11) |
+                                      (((e.w >> kWordMetaOrientBit) & 1u) << 21) | (e.w & (255u << kWordMetaMaskShift));
                 unsigned bal = __ballot_sync(0xffffffffu, c != 0);
                 while (bal) {
                     if (c) {
@@ -340,35 +341,23 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 // a ticket = kChunk consecutive entries of the group's word list; entries carry their mask's index
                 const uint32_t seg0 = range.x + (uint32_t) tk * kChunk;
                 const uint32_t seg1 = min(seg0 + kChunk, range.y);
-                // the scan reads only the first 8 bytes {bits, meta} of the 16-byte entries, three iterations ahead; lanes past the
-                // end carry an empty word on a valid row
+                // The scan reads only the first 8 bytes {bits, occupancy word index} of the 16-byte entries, three iterations
+                // ahead; lanes past the end carry an empty word on a valid address.
                 const uint4 *wl = gwords;
-                const uint2 idle = make_uint2(0u, (uint32_t) y0);
-                uint2 w0 = idle, w1 = idle, w2 = idle;
-                {
-                    uint32_t i = seg0 + lane;
-                    if (i < seg1) w0 = __ldg(reinterpret_cast<const uint2 *>(wl + i));
-                    i += 32;
-                    if (i < seg1) w1 = __ldg(reinterpret_cast<const uint2 *>(wl + i));
-                    i += 32;
-                    if (i < seg1) w2 = __ldg(reinterpret_cast<const uint2 *>(wl + i));
-                }
-                for (uint32_t base = seg0; base < seg1; base += 32) {
-                    const uint2 w = w0;
-                    w0 = w1;
-                    w1 = w2;
-                    w2 = idle;
-                    {
-                        const uint32_t i = base + 96 + lane;
-                        if (i < seg1) w2 = __ldg(reinterpret_cast<const uint2 *>(wl + i));
-                    }
-                    const uint32_t y = w.y & ((1u << kWordMetaYBits) - 1);
-                    const uint32_t xw = (w.y >> kWordMetaYBits) & 63u;
-                    const uint32_t sec = (w.y >> kWordMetaSectorShift) & 7u;
-                    const uint32_t c = w.x & bits[((int) y - y0) * rowpitch + (int) sec * p.bpitch + (int) xw];    // mask pixels of this word that can match
+                const uint2 idle = make_uint2(0u, (uint32_t) (y0 * rowpitch));
+                auto load = [&](uint32_t i) -> uint2 {
+                    uint2 w = idle;
+                    if (i < seg1) w = __ldg(reinterpret_cast<const uint2 *>(wl + i));
+                    return w;
+                };
+                auto scan_one = [&](uint2 w, uint32_t entry) {
+                    const uint32_t c = w.x & bits_y0[w.y];                  // mask pixels of this word that can match
                     // words with candidates are compacted first, so that the bit peeling runs on full warps
                     const unsigned has = __ballot_sync(0xffffffffu, c != 0);
-                    if (c) mywq[(wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1)] = make_uint2(c, base + lane);
+                    if (c) {
+                        const uint32_t slot = (wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1);
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(mywq_addr + slot * 8u), "r"(c), "r"(entry) : "memory");
+                    }
                     wt += (uint32_t) __popc(has);
                     if (wt - wh >= 32) {
                         __syncwarp();
@@ -376,6 +365,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                         wh += 32;
                         submit_words(qe, true);
                     }
+                };
+                uint2 w0 = load(seg0 + lane), w1 = load(seg0 + 32 + lane), w2 = load(seg0 + 64 + lane);
+                for (uint32_t base = seg0; base < seg1; base += 32) {
+                    const uint2 w = w0;
+                    w0 = w1;
+                    w1 = w2;
+                    w2 = load(base + 96 + lane);
+                    scan_one(w, base + lane);
                 }
             }
             // the band's last, partly filled batches: everything queued reads this stage, so it is evaluated before the release
@@ -588,6 +585,7 @@ __global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restr
     uint32_t out_w = __ldg(gstart + (size_t) g * (H + 1) + y) + __ldg(md.wstart + y);       // start of the row's run + this mask's offset in it
     uint32_t out_b = __ldg(bstart + (size_t) g * (H + 1) + y) + __ldg(boff + (size_t) m * (H + 1) + y);
     const uint32_t lt = (1u << lane) - 1u;
+    const int bp = occupancy_pitch(W);
     for (int list = 0; list < (mirror ? kLists : CDS_NUM_SECTORS); list++) {
         const int o = list / CDS_NUM_SECTORS, sec = list % CDS_NUM_SECTORS;
         for (int k0 = 0; k0 < kRowWords; k0 += 32) {
@@ -605,8 +603,9 @@ __global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restr
             if (wbits) {
                 const uint32_t pos = out_w + (uint32_t) __popc(bal & lt);
                 uint32_t lrec = out_b + incl - pc;
-                words[pos] = make_uint4(wbits, (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit) |
-                                                   ((uint32_t) sec << kWordMetaSectorShift) | mtag, lrec, 0u);
+                words[pos] = make_uint4(wbits, (uint32_t) ((y * occupancy_row_pitch(bp)) + sec * bp + k), lrec,
+                                        (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit) |
+                                            ((uint32_t) sec << kWordMetaSectorShift) | mtag);
                 // palette references of the word's pixels, in bit order: index | (interval 2 ? 0x8000 : 0)
                 while (wbits) {
                     const int bit = __ffs((int) wbits) - 1;

@@ -15,10 +15,11 @@ namespace cds {
 // sector, column) with a row-start table gstart[H+1], so the entries that concern a band of rows are one contiguous range that
 // is cut into equal tickets regardless of mask boundaries.  One 16-byte entry per word:
 //     bits : the word
-//     meta : y | word column << 10 | orientation << 16 | sector << 17 | mask index inside the group << 22 (8 bits)   (H <= 1024, W <= 2048)
+//     occ  : index of the matching occupancy word inside a target's bitmaps: y * occupancy_row_pitch + sector * pitch + column
 //     lrec : index into the group's `lpal` array of the palette reference of the word's LOWEST set bit; set bit b has
 //            lpal[lrec + popc(bits below b)] = palette index | 0x8000 when the pixel is in this list through its interval 2
-//     0
+//     meta : y | word column << 10 | orientation << 16 | sector << 17 | mask index inside the group << 22 (8 bits)   (H <= 1024, W <= 2048)
+// The scan touches only {bits, occ}; the second half is read for the words that have candidates.
 // ANDing `bits` with the library's occupancy word of the same (row, sector, column) leaves exactly the mask pixels that can
 // match in some shifted variant of that orientation -- 32 pixels per instruction -- and an evaluation tests ONE interval: the
 // two lists of a boundary pixel partition its matches by target sector, so nothing is counted twice.

@@ -69,7 +69,7 @@ void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_ta
 // target pixels of the sector of one of its (at most two) rank intervals, so a clear bit in that sector's row means "cannot
 // match in any shifted variant"; the shift set being symmetric, the bit of the mirrored position covers the mirrored variants.
 // `valid_scratch` holds scratch_targets * H * occupancy_row_pitch(bp) words.
-inline int occupancy_pitch(int W) { return (((W + 31) / 32) + 3) / 4 * 4; }
+__host__ __device__ inline int occupancy_pitch(int W) { return (((W + 31) / 32) + 3) / 4 * 4; }
 __host__ __device__ inline int occupancy_row_pitch(int bp) { return (CDS_NUM_SECTORS + 1) * bp; }
 void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int bp,
                       uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s);
