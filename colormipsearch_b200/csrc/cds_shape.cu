@@ -444,10 +444,11 @@ extern "C" void cds_shape_maskset_destroy(cds_shape_maskset *sms)
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cudaSetDevice(ctx->devs[0].dev);
     cudaStreamSynchronize(ctx->devs[0].stream);
+    DevPool &pool = ctx->devs[0].pool;
     for (auto &m : sms->masks) {
-        if (m.gap_list) cudaFree(m.gap_list);
-        if (m.he_n) cudaFree(m.he_n);
-        if (m.he_m) cudaFree(m.he_m);
+        pool.free(m.gap_list);
+        pool.free(m.he_n);
+        pool.free(m.he_m);
     }
     if (sms->d_roi) cudaFree(sms->d_roi);
     if (sms->d_descs) cudaFree(sms->d_descs);
@@ -471,16 +472,17 @@ extern "C" cds_status cds_shape_maskset_add_rgb(cds_shape_maskset *sms, const ui
     uint8_t *d_raw = nullptr, *d_q = nullptr, *d_m60 = nullptr, *d_m20 = nullptr;
     uint32_t *d_list = nullptr;
     unsigned long long *d_cnt = nullptr;
-    cds_status st = ctx->check(cudaMalloc(&d_raw, bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_q, bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_m60, bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_m20, bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_list, px * sizeof(uint32_t)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_cnt, 4 * sizeof(unsigned long long)), "cudaMalloc");
+    DevPool &pool = d0.pool;
+    cds_status st = ctx->check(pool.alloc((void **) &d_raw, bytes), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_q, bytes), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_m60, bytes), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_m20, bytes), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_list, px * sizeof(uint32_t)), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_cnt, 4 * sizeof(unsigned long long)), "cudaMalloc");
     for (int i = 0; i < n && st == CDS_OK; i++) {
         cds_shape_maskset::Mask m;
-        st = ctx->check(cudaMalloc(&m.he_n, bm_words * sizeof(uint32_t)), "cudaMalloc(he bitmap)");
-        if (st == CDS_OK) st = ctx->check(cudaMalloc(&m.he_m, bm_words * sizeof(uint32_t)), "cudaMalloc(he bitmap)");
+        st = ctx->check(pool.alloc((void **) &m.he_n, bm_words * sizeof(uint32_t)), "cudaMalloc(he bitmap)");
+        if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &m.he_m, bm_words * sizeof(uint32_t)), "cudaMalloc(he bitmap)");
         if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_raw, rgb + (size_t) i * bytes, bytes, cudaMemcpyHostToDevice, d0.stream), "mask H2D");
         if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), d0.stream), "memset");
         if (st == CDS_OK) {
@@ -496,14 +498,14 @@ extern "C" cds_status cds_shape_maskset_add_rgb(cds_shape_maskset *sms, const ui
         if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "shape mask");
         if (st == CDS_OK) {
             m.n_gap = (int) cnt[2];
-            st = ctx->check(cudaMalloc(&m.gap_list, std::max<size_t>(1, (size_t) m.n_gap) * sizeof(uint32_t)), "cudaMalloc(gap list)");
+            st = ctx->check(pool.alloc((void **) &m.gap_list, std::max<size_t>(1, (size_t) m.n_gap) * sizeof(uint32_t)), "cudaMalloc(gap list)");
             if (st == CDS_OK && m.n_gap) st = ctx->check(cudaMemcpyAsync(m.gap_list, d_list, (size_t) m.n_gap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d0.stream), "gap list copy");
             if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "gap list");
         }
         if (st != CDS_OK) {
-            if (m.he_n) cudaFree(m.he_n);
-            if (m.he_m) cudaFree(m.he_m);
-            if (m.gap_list) cudaFree(m.gap_list);
+            pool.free(m.he_n);
+            pool.free(m.he_m);
+            pool.free(m.gap_list);
             break;
         }
         if (qm_size_out) qm_size_out[i] = (int64_t) cnt[0];
@@ -511,12 +513,13 @@ extern "C" cds_status cds_shape_maskset_add_rgb(cds_shape_maskset *sms, const ui
         sms->masks.push_back(m);
         sms->descs_dirty = true;
     }
-    if (d_raw) cudaFree(d_raw);
-    if (d_q) cudaFree(d_q);
-    if (d_m60) cudaFree(d_m60);
-    if (d_m20) cudaFree(d_m20);
-    if (d_list) cudaFree(d_list);
-    if (d_cnt) cudaFree(d_cnt);
+    cudaStreamSynchronize(d0.stream);
+    pool.free(d_raw);
+    pool.free(d_q);
+    pool.free(d_m60);
+    pool.free(d_m20);
+    pool.free(d_list);
+    pool.free(d_cnt);
     return st;
 }
 
@@ -602,44 +605,63 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
     uint8_t *d_mir = nullptr;
     const int64_t chunk = 32;
     const int64_t nt = std::max<int64_t>(n_targets, 1);
-    cds_status st = ctx->check(cudaMalloc(&d_zslice, nt * px * sizeof(uint16_t)), "cudaMalloc(zslice)");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_grad, nt * px * sizeof(uint16_t)), "cudaMalloc(gradient)");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_tsig, nt * bm_words * sizeof(uint32_t)), "cudaMalloc(tsig)");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_t, chunk * bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_z, chunk * bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_tmp, chunk * bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_pm, n_pairs * sizeof(int32_t)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_pt, n_pairs * sizeof(int64_t)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_gap, n_pairs * sizeof(long long)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_he, n_pairs * sizeof(long long)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_mir, n_pairs), "cudaMalloc");
+    // buffers come from the device's caching pool: consecutive calls (one per mask batch in gradientScores) reuse them
+    DevPool &pool = d0.pool;
+    cds_status st = ctx->check(pool.alloc((void **) &d_zslice, nt * px * sizeof(uint16_t)), "cudaMalloc(zslice)");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_grad, nt * px * sizeof(uint16_t)), "cudaMalloc(gradient)");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_tsig, nt * bm_words * sizeof(uint32_t)), "cudaMalloc(tsig)");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_t, 2 * chunk * bytes), "cudaMalloc");          // two upload halves
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_z, 2 * chunk * bytes), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_tmp, chunk * bytes), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_pm, n_pairs * sizeof(int32_t)), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_pt, n_pairs * sizeof(int64_t)), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_gap, n_pairs * sizeof(long long)), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_he, n_pairs * sizeof(long long)), "cudaMalloc");
+    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_mir, n_pairs), "cudaMalloc");
     if (st == CDS_OK && has_variants) {
-        st = ctx->check(cudaMalloc(&d_has, nt), "cudaMalloc");
+        st = ctx->check(pool.alloc((void **) &d_has, nt), "cudaMalloc");
         if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_has, has_variants, n_targets, cudaMemcpyHostToDevice, d0.stream), "has_variants H2D");
     }
     if (st == CDS_OK && any_scored) {
-        st = ctx->check(cudaMemcpyAsync(d_grad, gradient, n_targets * px * sizeof(uint16_t), cudaMemcpyHostToDevice, d0.stream), "gradient H2D");
-        ctx->stats.h2d_bytes += (int64_t) (n_targets * px * sizeof(uint16_t));
+        // Uploads (target, its gradient, its zgap image when given) run on the copy stream one chunk ahead of the kernels that
+        // turn chunk i into slice / signal planes on the main stream.
+        if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "shape pairs");     // pooled buffers may still be in use by an earlier call
+        auto enqueue_upload = [&](int64_t i0) -> cds_status {
+            const int64_t cnt = std::min<int64_t>(chunk, n_targets - i0);
+            const int slot = (int) ((i0 / chunk) & 1);
+            cds_status s2 = CDS_OK;
+            if (i0 >= 2 * chunk) s2 = ctx->check(cudaStreamWaitEvent(d0.copy_stream, d0.up_free[slot], 0), "wait");
+            if (s2 == CDS_OK) s2 = ctx->check(cudaMemcpyAsync(d_t + (size_t) slot * chunk * bytes, target_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.copy_stream), "target H2D");
+            if (s2 == CDS_OK) s2 = ctx->check(cudaMemcpyAsync(d_grad + (size_t) i0 * px, gradient + (size_t) i0 * px, (size_t) cnt * px * sizeof(uint16_t), cudaMemcpyHostToDevice, d0.copy_stream), "gradient H2D");
+            ctx->stats.h2d_bytes += (int64_t) (cnt * bytes) + (int64_t) (cnt * px * sizeof(uint16_t));
+            if (s2 == CDS_OK && zgap_rgb) {
+                s2 = ctx->check(cudaMemcpyAsync(d_z + (size_t) slot * chunk * bytes, zgap_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.copy_stream), "zgap H2D");
+                ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
+            }
+            if (s2 == CDS_OK) s2 = ctx->check(cudaEventRecord(d0.up_done[slot], d0.copy_stream), "record");
+            return s2;
+        };
+        if (st == CDS_OK && n_targets > 0) st = enqueue_upload(0);
         for (int64_t i0 = 0; i0 < n_targets && st == CDS_OK; i0 += chunk) {
             const int64_t cnt = std::min<int64_t>(chunk, n_targets - i0);
-            st = ctx->check(cudaMemcpyAsync(d_t, target_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.stream), "target H2D");
-            ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
+            const int slot = (int) ((i0 / chunk) & 1);
+            uint8_t *ct = d_t + (size_t) slot * chunk * bytes, *cz = d_z + (size_t) slot * chunk * bytes;
+            if (i0 + chunk < n_targets) st = enqueue_upload(i0 + chunk);
             if (st != CDS_OK) break;
-            if (zgap_rgb) {
-                st = ctx->check(cudaMemcpyAsync(d_z, zgap_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.stream), "zgap H2D");
-                ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
-            } else {
+            st = ctx->check(cudaStreamWaitEvent(d0.stream, d0.up_done[slot], 0), "wait");
+            if (st != CDS_OK) break;
+            if (!zgap_rgb) {
                 // the zgap image the reference's tests derive: maxFilter(10)(mask(threshold)(clearLabels(target)))
-                clear_and_mask_kernel<<<148 * 4, 256, 0, d0.stream>>>(d_t, d_tmp, cnt, W, H, sms->rects, sms->query_threshold, 1);
-                launch_max_filter(d_tmp, d_z, cnt, W, H, 3, 10, d0.stream);
+                clear_and_mask_kernel<<<148 * 4, 256, 0, d0.stream>>>(ct, d_tmp, cnt, W, H, sms->rects, sms->query_threshold, 1);
+                launch_max_filter(d_tmp, cz, cnt, W, H, 3, 10, d0.stream);
                 ctx->stats.kernel_launches += 2;
             }
-            if (st != CDS_OK) break;
             dim3 grid(H, (unsigned) cnt);
-            target_planes_kernel<<<grid, 256, 0, d0.stream>>>(d_t, d_z, W, H, sms->rects, sms->query_threshold, bpitch,
+            target_planes_kernel<<<grid, 256, 0, d0.stream>>>(ct, cz, W, H, sms->rects, sms->query_threshold, bpitch,
                                                               d_zslice + (size_t) i0 * px, d_tsig + (size_t) i0 * bm_words);
             ctx->stats.kernel_launches++;
             st = ctx->check(cudaGetLastError(), "target planes");
+            if (st == CDS_OK) st = ctx->check(cudaEventRecord(d0.up_free[slot], d0.stream), "record");
         }
     }
     if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_pm, pair_mask, n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, d0.stream), "pairs H2D");
@@ -668,8 +690,9 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
         ctx->stats.comparisons = n_pairs;
         ctx->stats.d2h_bytes = n_pairs * 17;
     }
+    if (st != CDS_OK) { cudaStreamSynchronize(d0.copy_stream); cudaStreamSynchronize(d0.stream); cudaGetLastError(); }
     for (void *p : {(void *) d_zslice, (void *) d_grad, (void *) d_tsig, (void *) d_t, (void *) d_z, (void *) d_tmp, (void *) d_has, (void *) d_pm,
                     (void *) d_pt, (void *) d_gap, (void *) d_he, (void *) d_mir})
-        if (p) cudaFree(p);
+        pool.free(p);
     return st;
 }
