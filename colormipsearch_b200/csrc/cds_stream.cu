@@ -9,6 +9,7 @@
 // the running per-mask lists.  The host only enqueues; it blocks once, at the end, to read the lists back and merge them
 // over the devices.  With pinned host memory the call runs at the rate of the slower of PCIe and the match kernel.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -100,21 +101,38 @@ cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, in
 
 }  // namespace
 
-extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms_c, const uint8_t *targets_rgb, int64_t n_targets,
-                                            int32_t k, double pct_positive_pixels,
-                                            int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
+namespace {
+
+// `all` selects the second mode of the streaming search: instead of per-mask top-K lists, every pair that passes isMatch.
+struct AllMatchesOut {
+    int64_t capacity;
+    int32_t *mask;
+    int64_t *target;
+    int32_t *score;
+    uint8_t *mirrored;
+    int64_t *count;
+};
+
+cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8_t *targets_rgb, int64_t n_targets,
+                              int32_t k, double pct_positive_pixels,
+                              int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count, const AllMatchesOut *all)
 {
-    if (!ctx || !ms_c) { set_tls_error("cds_search_stream_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
     if (ms->ctx != ctx) return ctx->fail(CDS_ERR_BAD_ARG, "mask set belongs to another context");
-    if (k <= 0 || k > topk_max_k()) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: k must be in 1..4096");
+    if (!all && (k <= 0 || k > topk_max_k())) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: k must be in 1..4096");
+    if (all) k = 1;
     if (n_targets < 0 || (n_targets > 0 && !targets_rgb)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: bad target array");
     const int M = (int) ms->sizes.size();
+    if (all) {
+        if (!all->count || all->capacity < 0 || (all->capacity > 0 && (!all->mask || !all->target || !all->score)))
+            return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_matches_rgb: bad output arrays");
+        *all->count = 0;
+    }
     if (M == 0) return CDS_OK;
-    if (!out_score || !out_target || !out_count) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: NULL output");
+    if (!all && (!out_score || !out_target || !out_count)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: NULL output");
     ctx->stats = cds_search_stats{};
-    for (int m = 0; m < M; m++) out_count[m] = 0;
+    if (!all) for (int m = 0; m < M; m++) out_count[m] = 0;
     if (n_targets == 0) return CDS_OK;
     CDS_TRY(ms->sync_descs());
 
@@ -132,11 +150,32 @@ extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms_
     std::vector<int32_t> min_score(M);
     for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);
     const int used_devs = (int) std::min<int64_t>(D, n_chunks);
+    std::vector<uint64_t *> all_keys(D, nullptr);
+    std::vector<int32_t *> all_masks(D, nullptr);
+    std::vector<unsigned long long *> all_counter(D, nullptr);
+    auto release_all = [&]() {
+        for (int d = 0; d < D; d++) {
+            if (!all_keys[d] && !all_masks[d] && !all_counter[d]) continue;
+            cudaSetDevice(ctx->devs[d].dev);
+            cudaStreamSynchronize(ctx->devs[d].stream);
+            ctx->devs[d].pool.free(all_keys[d]);
+            ctx->devs[d].pool.free(all_masks[d]);
+            ctx->devs[d].pool.free(all_counter[d]);
+        }
+    };
+    struct Releaser { std::function<void()> f; ~Releaser() { f(); } } releaser{release_all};
     for (int d = 0; d < used_devs; d++) {
         DevState &ds = ctx->devs[d];
         CDS_TRY(ensure_stream_bufs(ctx, ds, g, bpitch, chunk, M, k));
         CDS_CUDA(ctx, cudaMemcpyAsync(ds.sb.min_score, min_score.data(), (size_t) M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaMemsetAsync(ds.sb.counts_run, 0, (size_t) M * sizeof(int32_t), ds.stream));
+        if (all) {
+            const size_t cap = (size_t) std::max<int64_t>(all->capacity, 1);
+            CDS_CUDA(ctx, ds.pool.alloc((void **) &all_keys[d], cap * sizeof(uint64_t)));
+            CDS_CUDA(ctx, ds.pool.alloc((void **) &all_masks[d], cap * sizeof(int32_t)));
+            CDS_CUDA(ctx, ds.pool.alloc((void **) &all_counter[d], sizeof(unsigned long long)));
+            CDS_CUDA(ctx, cudaMemsetAsync(all_counter[d], 0, sizeof(unsigned long long), ds.stream));
+        }
         CDS_CUDA(ctx, cudaEventRecord(ds.ev0, ds.stream));
         const size_t need = (size_t) 2 * ((n_chunks + D - 1) / D);
         while (ds.sb.timing.size() < need) {
@@ -176,18 +215,29 @@ extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms_
         }
         CDS_CUDA(ctx, cudaGetLastError());
         CDS_TRY(launch_match_view(ctx, ms, tv, d, 0, M, sb.scores, ds.stream, sb.timing[2 * j], sb.timing[2 * j + 1]));
-        launch_topk(sb.scores, M, cnt, sb.min_score, k, first, sb.keys_chunk, sb.counts_chunk, ds.stream);
-        launch_topk_merge(sb.keys_run, sb.counts_run, sb.keys_chunk, sb.counts_chunk, M, k, ds.stream);
-        ctx->stats.kernel_launches += 2;
+        if (all) {
+            launch_collect_matches(sb.scores, M, cnt, sb.min_score, 0, first, all_keys[d], all_masks[d], all_counter[d],
+                                   (unsigned long long) all->capacity, ds.stream);
+            ctx->stats.kernel_launches++;
+        } else {
+            launch_topk(sb.scores, M, cnt, sb.min_score, k, first, sb.keys_chunk, sb.counts_chunk, ds.stream);
+            launch_topk_merge(sb.keys_run, sb.counts_run, sb.keys_chunk, sb.counts_chunk, M, k, ds.stream);
+            ctx->stats.kernel_launches += 2;
+        }
         CDS_CUDA(ctx, cudaGetLastError());
     }
 
     // read the per-device lists back and merge them (no collective: nothing is reduced across devices)
     const size_t keys_bytes = (size_t) M * k * sizeof(uint64_t);
+    std::vector<unsigned long long> all_n(D, 0);
     for (int d = 0; d < used_devs; d++) {
         DevState &ds = ctx->devs[d];
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
         CDS_CUDA(ctx, cudaEventRecord(ds.ev2, ds.stream));
+        if (all) {
+            CDS_CUDA(ctx, cudaMemcpyAsync(&all_n[d], all_counter[d], sizeof(unsigned long long), cudaMemcpyDeviceToHost, ds.stream));
+            continue;
+        }
         CDS_TRY(ctx->ensure_pinned(ds, keys_bytes + (size_t) M * sizeof(int32_t)));
         uint8_t *hp = (uint8_t *) ds.h_pinned;
         CDS_CUDA(ctx, cudaMemcpyAsync(hp, ds.sb.keys_run, keys_bytes, cudaMemcpyDeviceToHost, ds.stream));
@@ -208,6 +258,45 @@ extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms_
         match_ms = std::max(match_ms, dev_match);
         cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev2);
         total_ms = std::max(total_ms, (double) ms_f);
+    }
+    ctx->stats.match_kernel_ms = match_ms;
+    ctx->stats.total_device_ms = total_ms;
+    ctx->stats.comparisons = (int64_t) M * n_targets;
+    if (all) {
+        // every passing pair, ordered like the reference's writer: by mask, descending matchingPixels, ascending target
+        uint64_t total = 0;
+        for (int d = 0; d < used_devs; d++) total += all_n[d];
+        *all->count = (int64_t) total;
+        if (total > (uint64_t) all->capacity) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "cds_search_stream_matches_rgb: %llu pairs pass isMatch, capacity is %lld", (unsigned long long) total, (long long) all->capacity);
+            return ctx->fail(CDS_ERR_CAPACITY, buf);
+        }
+        struct Pair { int32_t mask; uint64_t key; };
+        std::vector<Pair> pairs;
+        pairs.reserve(total);
+        std::vector<uint64_t> hk;
+        std::vector<int32_t> hm;
+        for (int d = 0; d < used_devs; d++) {
+            const size_t n = (size_t) all_n[d];
+            if (!n) continue;
+            hk.resize(n); hm.resize(n);
+            CDS_CUDA(ctx, cudaSetDevice(ctx->devs[d].dev));
+            CDS_CUDA(ctx, cudaMemcpy(hk.data(), all_keys[d], n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            CDS_CUDA(ctx, cudaMemcpy(hm.data(), all_masks[d], n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            ctx->stats.d2h_bytes += (int64_t) (n * 12);
+            for (size_t i = 0; i < n; i++) pairs.push_back({hm[i], hk[i]});
+        }
+        std::sort(pairs.begin(), pairs.end(), [](const Pair &a, const Pair &b) { return a.mask != b.mask ? a.mask < b.mask : a.key < b.key; });
+        for (size_t i = 0; i < pairs.size(); i++) {
+            int32_t sc; int64_t tg; uint8_t mir;
+            topk_decode_key(pairs[i].key, sc, tg, mir);
+            all->mask[i] = pairs[i].mask;
+            all->target[i] = tg;
+            all->score[i] = sc;
+            if (all->mirrored) all->mirrored[i] = mir;
+        }
+        return CDS_OK;
     }
     struct Item { int32_t score; int64_t target; uint8_t mir; };
     std::vector<Item> items;
@@ -236,8 +325,25 @@ extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms_
             if (out_mirrored) out_mirrored[(size_t) m * k + i] = items[i].mir;
         }
     }
-    ctx->stats.match_kernel_ms = match_ms;
-    ctx->stats.total_device_ms = total_ms;
-    ctx->stats.comparisons = (int64_t) M * n_targets;
     return CDS_OK;
+}
+
+}  // namespace
+
+extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *targets_rgb, int64_t n_targets,
+                                            int32_t k, double pct_positive_pixels,
+                                            int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
+{
+    if (!ctx || !ms) { set_tls_error("cds_search_stream_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
+    return stream_search_impl(ctx, ms, targets_rgb, n_targets, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr);
+}
+
+extern "C" cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *targets_rgb, int64_t n_targets,
+                                                    double pct_positive_pixels, int64_t capacity,
+                                                    int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored,
+                                                    int64_t *out_count)
+{
+    if (!ctx || !ms) { set_tls_error("cds_search_stream_matches_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
+    const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
+    return stream_search_impl(ctx, ms, targets_rgb, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all);
 }

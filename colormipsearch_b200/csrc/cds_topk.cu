@@ -197,4 +197,47 @@ void launch_topk_merge(uint64_t *run_keys, int32_t *run_counts, const uint64_t *
     topk_merge_kernel<<<n_masks, kThreads, smem, s>>>(run_keys, run_counts, chunk_keys, chunk_counts, k);
 }
 
+// Every (mask, target) whose count reaches the mask's isMatch floor: key + mask index appended to an unordered device list.
+// `counter` keeps counting past `capacity`, so the caller learns how much room a retry needs.
+__global__ void __launch_bounds__(kThreads) collect_matches_kernel(const int32_t *__restrict__ scores, int64_t n_targets,
+                                                                   const int32_t *__restrict__ min_score, int first_mask, int64_t idx_base,
+                                                                   uint64_t *__restrict__ keys, int32_t *__restrict__ masks,
+                                                                   unsigned long long *__restrict__ counter, unsigned long long capacity)
+{
+    const int64_t t = (int64_t) blockIdx.x * kThreads + threadIdx.x;
+    const int m = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    int w = 0, c = 0;
+    bool pass = false;
+    if (t < n_targets) {
+        w = scores[(size_t) m * n_targets + t];
+        c = w & ~CDS_SCORE_MIRROR_BIT;
+        pass = c >= max(min_score[m], 1);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (bal == 0) return;
+    unsigned long long base = 0;
+    if (lane == __ffs((int) bal) - 1) base = atomicAdd(counter, (unsigned long long) __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs((int) bal) - 1);
+    if (pass) {
+        const unsigned long long slot = base + (unsigned long long) __popc(bal & ((1u << lane) - 1u));
+        if (slot < capacity) {
+            keys[slot] = topk_make_key(c, idx_base + t, (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0);
+            masks[slot] = first_mask + m;
+        }
+    }
+}
+
+void launch_collect_matches(const int32_t *scores, int n_masks, int64_t n_targets, const int32_t *min_score, int first_mask, int64_t idx_base,
+                            uint64_t *keys, int32_t *masks, unsigned long long *counter, unsigned long long capacity, cudaStream_t s)
+{
+    if (n_targets == 0) return;
+    for (int m0 = 0; m0 < n_masks; m0 += 32768) {
+        const int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
+        dim3 grid((unsigned) ((n_targets + kThreads - 1) / kThreads), (unsigned) cnt);
+        collect_matches_kernel<<<grid, kThreads, 0, s>>>(scores + (size_t) m0 * n_targets, n_targets, min_score + m0, first_mask + m0, idx_base,
+                                                        keys, masks, counter, capacity);
+    }
+}
+
 }  // namespace cds

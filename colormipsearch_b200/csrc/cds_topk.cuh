@@ -31,5 +31,10 @@ void launch_topk(const int32_t *scores, int n_masks, int64_t n_targets, const in
 void launch_topk_merge(uint64_t *run_keys, int32_t *run_counts, const uint64_t *chunk_keys, const int32_t *chunk_counts,
                        int n_masks, int k, cudaStream_t s);
 
+// Appends every (mask, target) of scores[n_masks][n_targets] whose count reaches min_score[mask] to an unordered device list
+// (keys as above with index idx_base + column; masks[slot] = first_mask + row).  *counter counts all of them, also past capacity.
+void launch_collect_matches(const int32_t *scores, int n_masks, int64_t n_targets, const int32_t *min_score, int first_mask, int64_t idx_base,
+                            uint64_t *keys, int32_t *masks, unsigned long long *counter, unsigned long long capacity, cudaStream_t s);
+
 }  // namespace cds
 #endif

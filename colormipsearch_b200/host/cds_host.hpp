@@ -343,7 +343,8 @@ public:
         params_.xy_shift = xyShift; params_.mirror = mirrorMask ? 1 : 0; params_.n_rects = (int32_t) rects.size();
         for (size_t i = 0; i < rects.size() && i < CDS_MAX_RECTS; i++) params_.rects[i] = rects[i];
     }
-    // every pair that passes ColorMIPSearch.isMatch, per mask in descending matchingPixels (ties: ascending target), at most maxPerMask each
+    // every pair that passes ColorMIPSearch.isMatch, per mask in descending matchingPixels (ties: ascending target); maxPerMask <= 0 keeps
+    // all of them (the reference's behaviour), a positive value only the best maxPerMask of each mask
     std::vector<CDMatch> findAllColorDepthMatches(const std::vector<const ImageArray *> &masks, const std::vector<const ImageArray *> &targets, int maxPerMask)
     {
         std::vector<CDMatch> out;
@@ -367,17 +368,33 @@ public:
                     throw std::invalid_argument("Invalid image size - target's image size must match query's image size");
                 std::copy(targets[i]->bytes.begin(), targets[i]->bytes.end(), all.begin() + i * imgBytes);
             }
-            const int K = std::max(1, std::min<int>(maxPerMask, (int) targets.size()));
-            std::vector<int32_t> score((size_t) masks.size() * K), count(masks.size());
-            std::vector<int64_t> target((size_t) masks.size() * K);
-            std::vector<uint8_t> mir((size_t) masks.size() * K);
-            GpuContext::check(cds_search_stream_rgb(gpu_->get(), ms, all.data(), (int64_t) targets.size(), K, pctPositivePixels_,
-                                                    score.data(), target.data(), mir.data(), count.data()), gpu_->get());
-            for (size_t m = 0; m < masks.size(); m++)
-                for (int i = 0; i < count[m]; i++) {
-                    const size_t o = m * K + i;
-                    out.push_back({(int) m, target[o], score[o], (float) ((double) score[o] / (double) sizes[m]), mir[o] != 0});
+            if (maxPerMask <= 0) {
+                // the reference keeps EVERY pair that passes isMatch (LocalColorMIPSearchProcessor.java:93-105)
+                int64_t cap = std::max<int64_t>(1024, 4 * (int64_t) masks.size()), n = 0;
+                std::vector<int32_t> mk, sc; std::vector<int64_t> tg; std::vector<uint8_t> mir;
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    mk.resize(cap); sc.resize(cap); tg.resize(cap); mir.resize(cap);
+                    cds_status st = cds_search_stream_matches_rgb(gpu_->get(), ms, all.data(), (int64_t) targets.size(), pctPositivePixels_, cap,
+                                                                  mk.data(), tg.data(), sc.data(), mir.data(), &n);
+                    if (st == CDS_ERR_CAPACITY && attempt == 0) { cap = n; continue; }
+                    GpuContext::check(st, gpu_->get());
+                    break;
                 }
+                for (int64_t i = 0; i < n; i++)
+                    out.push_back({mk[i], tg[i], sc[i], (float) ((double) sc[i] / (double) sizes[mk[i]]), mir[i] != 0});
+            } else {
+                const int K = std::max(1, std::min<int>(maxPerMask, (int) targets.size()));
+                std::vector<int32_t> score((size_t) masks.size() * K), count(masks.size());
+                std::vector<int64_t> target((size_t) masks.size() * K);
+                std::vector<uint8_t> mir((size_t) masks.size() * K);
+                GpuContext::check(cds_search_stream_rgb(gpu_->get(), ms, all.data(), (int64_t) targets.size(), K, pctPositivePixels_,
+                                                        score.data(), target.data(), mir.data(), count.data()), gpu_->get());
+                for (size_t m = 0; m < masks.size(); m++)
+                    for (int i = 0; i < count[m]; i++) {
+                        const size_t o = m * K + i;
+                        out.push_back({(int) m, target[o], score[o], (float) ((double) score[o] / (double) sizes[m]), mir[o] != 0});
+                    }
+            }
         } catch (...) { cds_maskset_destroy(ms); throw; }
         cds_maskset_destroy(ms);
         return out;

@@ -151,6 +151,16 @@ cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms, const uint
                                  int32_t k, double pct_positive_pixels,
                                  int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count);
 
+/* The same streaming search without a K: EVERY (mask, target) pair that passes ColorMIPSearch.isMatch -- what
+ * LocalColorMIPSearchProcessor keeps (TOOLS/cdsprocess/LocalColorMIPSearchProcessor.java:93-105: filter(m -> m.isMatchFound())) --
+ * ordered by mask, then descending matchingPixels, then ascending target (the stable sort of TOOLS/ColorDepthSearchCmd.java:403-409
+ * after a single-threaded run).  out_* hold `capacity` entries; *out_count receives the number of passing pairs.  When more than
+ * `capacity` pairs pass, nothing is written, *out_count still tells how many there are and the call returns CDS_ERR_CAPACITY. */
+cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *targets_rgb, int64_t n_targets,
+                                         double pct_positive_pixels, int64_t capacity,
+                                         int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored,
+                                         int64_t *out_count);
+
 /* One mask x one target held in host memory: the literal single-pair call of the Java API
  * (ColorDepthSearchAlgorithm.calculateMatchingScore, API/cds/ColorDepthSearchAlgorithm.java:60-61). */
 cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, int32_t mask_index, const uint8_t *target_rgb,

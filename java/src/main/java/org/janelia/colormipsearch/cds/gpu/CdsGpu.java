@@ -24,7 +24,7 @@ import static java.lang.foreign.ValueLayout.JAVA_LONG;
  * ctypes (colormipsearch_b200/capi.py) by the test suite.
  */
 public final class CdsGpu {
-    public static final int CDS_OK = 0, CDS_ERR_BAD_ARG = 1, CDS_ERR_SIZE_MISMATCH = 2;
+    public static final int CDS_OK = 0, CDS_ERR_BAD_ARG = 1, CDS_ERR_SIZE_MISMATCH = 2, CDS_ERR_CAPACITY = 6;
     public static final int CDS_MAX_RECTS = 8;
 
     /** cds_rect {int32 x0, y0, x1, y1} */
@@ -56,6 +56,7 @@ public final class CdsGpu {
     static final MethodHandle masksetAddRgb = h("cds_maskset_add_rgb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
     static final MethodHandle searchTopk = h("cds_search_topk", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_DOUBLE, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle searchStream = h("cds_search_stream_rgb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_DOUBLE, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle searchStreamMatches = h("cds_search_stream_matches_rgb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_DOUBLE, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle scorePairRgb = h("cds_score_pair_rgb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle shapeMasksetCreate = h("cds_shape_maskset_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle shapeMasksetDestroy = h("cds_shape_maskset_destroy", FunctionDescriptor.ofVoid(ADDRESS));

@@ -77,30 +77,52 @@ public class GpuColorMIPSearchProcessor<M extends AbstractNeuronEntity, T extend
             MemorySegment pinned = out.get(ValueLayout.ADDRESS, 0).reinterpret(imgBytes * targets.size());
             for (int i = 0; i < targets.size(); i++)
                 MemorySegment.copy(ImageArrayAccess.rgbBytes(targets.get(i).getImageArray()), 0, pinned, ValueLayout.JAVA_BYTE, imgBytes * i, (int) imgBytes);
-            MemorySegment score = a.allocate(4L * masks.size() * k, 4), target = a.allocate(8L * masks.size() * k, 8);
-            MemorySegment mirrored = a.allocate((long) masks.size() * k), count = a.allocate(4L * masks.size(), 4);
-            CdsGpu.check((int) CdsGpu.searchStream.invokeExact(ctx, ms, pinned, (long) targets.size(), k, pctPositivePixels, score, target, mirrored, count));
-            for (int m = 0; m < masks.size(); m++) {
-                int n = count.get(ValueLayout.JAVA_INT, 4L * m);
-                for (int i = 0; i < n; i++) {
-                    long o = (long) m * k + i;
-                    int pix = score.get(ValueLayout.JAVA_INT, 4 * o);
-                    CDMatchEntity<M, T> r = new CDMatchEntity<>();
-                    r.setMaskImage((M) masks.get(m).getNeuronInfo().addProcessedTags(ProcessingType.ColorDepthSearch, tags));
-                    r.setMatchedImage((T) targets.get((int) target.get(ValueLayout.JAVA_LONG, 8 * o)).getNeuronInfo().addProcessedTags(ProcessingType.ColorDepthSearch, tags));
-                    r.setSessionRefId(cdsRunId);
-                    r.setMatchFound(true);                                              // only isMatch pairs are returned
-                    r.setMatchingPixels(pix);
-                    r.setMatchingPixelsRatio((float) ((double) pix / maskSizes[m]));     // PixelMatchScore.getNormalizedScore
-                    r.setMirrored(mirrored.get(ValueLayout.JAVA_BYTE, o) != 0);
-                    r.addAllTags(tags);
-                    results.add(r);
+            if (maxMatchesPerMask <= 0) {
+                // like LocalColorMIPSearchProcessor: every pair that passes ColorMIPSearch.isMatch
+                long cap = Math.max(1024L, 4L * masks.size());
+                MemorySegment count = a.allocate(ValueLayout.JAVA_LONG);
+                for (int attempt = 0; ; attempt++) {
+                    MemorySegment mk = a.allocate(4 * cap, 4), tg = a.allocate(8 * cap, 8), sc = a.allocate(4 * cap, 4), mir = a.allocate(cap);
+                    int st = (int) CdsGpu.searchStreamMatches.invokeExact(ctx, ms, pinned, (long) targets.size(), pctPositivePixels, cap, mk, tg, sc, mir, count);
+                    long n = count.get(ValueLayout.JAVA_LONG, 0);
+                    if (st == CdsGpu.CDS_ERR_CAPACITY && attempt == 0) { cap = n; continue; }
+                    CdsGpu.check(st);
+                    for (long i = 0; i < n; i++)
+                        results.add(newMatch(masks, targets, maskSizes, mk.get(ValueLayout.JAVA_INT, 4 * i), (int) tg.get(ValueLayout.JAVA_LONG, 8 * i),
+                                sc.get(ValueLayout.JAVA_INT, 4 * i), mir.get(ValueLayout.JAVA_BYTE, i) != 0));
+                    break;
+                }
+            } else {
+                MemorySegment score = a.allocate(4L * masks.size() * k, 4), target = a.allocate(8L * masks.size() * k, 8);
+                MemorySegment mirrored = a.allocate((long) masks.size() * k), count = a.allocate(4L * masks.size(), 4);
+                CdsGpu.check((int) CdsGpu.searchStream.invokeExact(ctx, ms, pinned, (long) targets.size(), k, pctPositivePixels, score, target, mirrored, count));
+                for (int m = 0; m < masks.size(); m++) {
+                    int n = count.get(ValueLayout.JAVA_INT, 4L * m);
+                    for (int i = 0; i < n; i++) {
+                        long o = (long) m * k + i;
+                        results.add(newMatch(masks, targets, maskSizes, m, (int) target.get(ValueLayout.JAVA_LONG, 8 * o),
+                                score.get(ValueLayout.JAVA_INT, 4 * o), mirrored.get(ValueLayout.JAVA_BYTE, o) != 0));
+                    }
                 }
             }
             CdsGpu.check((int) CdsGpu.hostFree.invokeExact(ctx, pinned));
             CdsGpu.masksetDestroy.invokeExact(ms);
         } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
         return results;
+    }
+
+    @SuppressWarnings("unchecked")
+    private CDMatchEntity<M, T> newMatch(List<NeuronMIP<M>> masks, List<NeuronMIP<T>> targets, int[] maskSizes, int m, int t, int pix, boolean mirrored) {
+        CDMatchEntity<M, T> r = new CDMatchEntity<>();
+        r.setMaskImage((M) masks.get(m).getNeuronInfo().addProcessedTags(ProcessingType.ColorDepthSearch, tags));
+        r.setMatchedImage((T) targets.get(t).getNeuronInfo().addProcessedTags(ProcessingType.ColorDepthSearch, tags));
+        r.setSessionRefId(cdsRunId);
+        r.setMatchFound(true);                                              // only isMatch pairs are returned
+        r.setMatchingPixels(pix);
+        r.setMatchingPixelsRatio((float) ((double) pix / maskSizes[m]));     // PixelMatchScore.getNormalizedScore
+        r.setMirrored(mirrored);
+        r.addAllTags(tags);
+        return r;
     }
 
     @Override

@@ -72,6 +72,9 @@ int main(int argc, char **argv)
             auto matches = proc.findAllColorDepthMatches({&em1, &em2}, {&lmA, &lmB, &lmC}, 3);
             for (const CDMatch &m : matches)
                 std::printf("batched mask %d target %lld pixels %d mirrored %d\n", m.maskIndex, m.targetIndex, m.matchingPixels, m.mirrored ? 1 : 0);
+            auto every = proc.findAllColorDepthMatches({&em1, &em2}, {&lmA, &lmB, &lmC}, 0);      // no limit: every isMatch pair
+            for (const CDMatch &m : every)
+                std::printf("allpairs mask %d target %lld pixels %d mirrored %d\n", m.maskIndex, m.targetIndex, m.matchingPixels, m.mirrored ? 1 : 0);
         }
 
         // ---- Shape2DMatchColorDepthSearchAlgorithmTest: provider(mirror), thr 20; zgap = the on-disk file for BJD

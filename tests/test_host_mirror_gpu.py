@@ -52,6 +52,8 @@ def test_reference_scenarios_through_the_cpp_mirror(tmp_path, fixtures):
     got = [(int(b[2]), int(b[4]), int(b[6]), int(b[8])) for b in batched]
     assert got[:3] == [(0, 0, 439, 0), (0, 2, 426, 1), (0, 1, 414, 0)]
     assert (1, 0, 515, 0) in got and (1, 2, 483, 0) in got
+    every = [ln.split() for ln in out if ln.startswith("allpairs")]
+    assert [(int(b[2]), int(b[4]), int(b[6]), int(b[8])) for b in every] == got       # 3 targets, K = 3: the same six pairs
     # Shape2DMatchColorDepthSearchAlgorithmTest.java:53-54, 230-291
     assert lines["shape_masks 17340"][:1] == ["70640"] and lines["shape_masks 17340"][2] == "2"
     assert lines["shape 12191xBJD_zgapfile"] == ["33884", "523", "34058", "0"]

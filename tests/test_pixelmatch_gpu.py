@@ -211,6 +211,32 @@ def test_stream_search_equals_library_search(ctx, synth, chunk):
     ctx.set_option("stream_chunk", 256)
 
 
+@pytest.mark.parametrize("pct", [0.0, 1.0])
+def test_all_matches_search(ctx, synth, pct):
+    """cds_search_stream_matches_rgb returns EVERY pair passing ColorMIPSearch.isMatch (the reference keeps all of them,
+    LocalColorMIPSearchProcessor.java:93-105), ordered by mask, descending score, ascending target."""
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
+    sizes = ms.add_rgb(masks)
+    oms = [O.PixelMatchMask(x, 20, True, 20, 0.01, 2, rects) for x in masks]
+    es, em, _ = O.search_dense(oms, targets)
+    exp = []
+    for m in range(len(masks)):
+        row = [(m, t, int(es[m, t]), int(em[m, t])) for t in range(len(targets)) if O.is_match(es[m, t], es[m, t] / sizes[m], pct)]
+        exp += sorted(row, key=lambda r: (-r[2], r[1]))
+    ctx.set_option("stream_chunk", 16)
+    got = ms.search_stream_matches(targets, pct)
+    assert list(zip(got[0].tolist(), got[1].tolist(), got[2].tolist(), got[3].tolist())) == exp
+    # too small a buffer: CDS_ERR_CAPACITY and the required size
+    if len(exp) > 1:
+        with pytest.raises(capi.CdsError) as e:
+            ms.search_stream_matches(targets, pct, capacity=len(exp) - 1)
+        assert e.value.status == capi.CDS_ERR_CAPACITY and str(len(exp)) in e.value.message
+    ctx.set_option("stream_chunk", 256)
+    ms.close()
+
+
 def test_threshold_rebake_roundtrip(ctx, synth):
     masks, targets, lib = synth
     rects = O.label_rects(W, H)
