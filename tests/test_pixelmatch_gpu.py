@@ -311,6 +311,38 @@ def test_small_and_odd_image_sizes(ctx, shape):
     lib.close()
 
 
+def test_extreme_masks_in_a_batch(ctx, synth):
+    """An empty mask, a mask that covers the whole image and a one-pixel mask next to ordinary ones, through every kernel."""
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    lut = O.lut().astype(np.uint8)
+    full = np.zeros((H, W, 3), np.uint8)
+    full[:] = lut[(np.arange(W)[None, :] // 5 + np.arange(H)[:, None] // 3) % 256]          # every pixel set, slowly varying slices
+    one = np.zeros((H, W, 3), np.uint8)
+    one[300, 700] = lut[100]
+    batch = np.concatenate([np.zeros((1, H, W, 3), np.uint8), full[None], one[None], masks[:15]])
+    tg = targets[:6]
+    small = capi.Library(ctx, W, H, 6)
+    small.add_rgb(tg)
+    params = (20, 20, 0.01, 2, True)
+    oms = [O.PixelMatchMask(x, 20, True, 20, 0.01, 2, rects) for x in batch]
+    es, em, _ = O.search_dense(oms, tg)
+    assert oms[0].size == 0 and oms[1].size > 600000 and oms[2].size == 1
+    for kern in ("cand", "band", "gather"):
+        ctx.set_match_kernel(kern)
+        ms = _maskset(ctx, params, rects)
+        sizes = ms.add_rgb(batch)
+        assert sizes.tolist() == [m.size for m in oms]
+        scores, mirrored = ms.search_dense(small)
+        assert np.array_equal(scores, es), kern
+        assert np.array_equal(mirrored, em), kern
+        s, t, m, c = ms.search_topk(small, 4, 0.0)
+        assert c[0] == 0                                   # an empty mask never matches
+        ms.close()
+    ctx.set_match_kernel("auto")
+    small.close()
+
+
 def test_concurrent_callers_on_one_context(ctx, synth):
     """The reference calls calculateMatchingScore on one shared algorithm instance from a pool of ~40 threads
     (LocalColorMIPSearchProcessor.java:93-105): calls on one cds_ctx from many host threads must be safe and correct."""
