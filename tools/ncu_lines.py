@@ -1,4 +1,4 @@
-"""Rank CUDA source lines of an ncu report by executed instructions / stall samples:  python scratch/ncu_lines.py report.ncu-rep [min_pct]"""
+"""Rank CUDA source lines of an ncu report by executed instructions / stall samples:  python tools/ncu_lines.py report.ncu-rep [min_pct]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.6
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
