@@ -952,7 +952,6 @@ extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cd
     for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
     int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 64 << 20) / std::max<int64_t>(max_local, 1)));
     if (mchunk < M && mchunk > CDS_PALETTE_GROUP) mchunk -= mchunk % CDS_PALETTE_GROUP;   // keep chunks aligned to palette groups
-    auto free_all = [&]() {};
     for (int d = 0; d < D && st == CDS_OK; d++) {
         st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
         if (st == CDS_OK) st = ctx->ensure_scratch(ctx->devs[d], 0, (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t), (void **) &d_scores[d]);
@@ -992,7 +991,6 @@ extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cd
         }
         match_ms += chunk_ms;
     }
-    free_all();
     ctx->stats.match_kernel_ms = match_ms;
     ctx->stats.total_device_ms = match_ms;
     ctx->stats.comparisons = (int64_t) M * T;
@@ -1044,7 +1042,6 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
     std::vector<uint64_t *> d_keys(D, nullptr);
     std::vector<int32_t *> d_counts(D, nullptr);
     cds_status st = CDS_OK;
-    auto free_all = [&]() {};
     const size_t keys_bytes = (size_t) M * k * sizeof(uint64_t);
     for (int d = 0; d < D && st == CDS_OK; d++) {
         DevState &ds = ctx->devs[d];
@@ -1140,7 +1137,6 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
             }
         }
     }
-    free_all();
     ctx->stats.match_kernel_ms = match_ms;
     ctx->stats.total_device_ms = total_ms;
     ctx->stats.comparisons = (int64_t) M * T;
