@@ -46,7 +46,7 @@ class PixParams(C.Structure):
 class SearchStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("match_kernel_launches", C.c_int64), ("match_kernel_ms", C.c_double),
                 ("total_device_ms", C.c_double), ("comparisons", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("match_kernel", C.c_int64)]
+                ("match_kernel", C.c_int64), ("chunked", C.c_int64)]
 
 
 _lib = None
@@ -84,6 +84,7 @@ SIGNATURES = {
     "cds_search_topk": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_double, _i32p, _i64p, _u8p, _i32p]),
     "cds_search_stream_rgb": (C.c_int32, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_double, _i32p, _i64p, _u8p, _i32p]),
     "cds_search_stream_matches_rgb": (C.c_int32, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_int64, _i32p, _i64p, _i32p, _u8p, _i64p]),
+    "cds_search_matches": (C.c_int32, [_vp, _vp, _vp, C.c_double, C.c_int64, _i32p, _i64p, _i32p, _u8p, _i64p]),
     "cds_score_pair_rgb": (C.c_int32, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
     "cds_shape_maskset_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Rect), C.c_int32, _vp, C.POINTER(_vp)]),
     "cds_shape_maskset_destroy": (None, [_vp]),
@@ -375,6 +376,22 @@ class MaskSet:
             st = lib().cds_search_stream_matches_rgb(self.ctx.h, self.h, _ptr(targets_rgb), int(n), float(pct_positive_pixels), cap,
                                                      mask.ctypes.data_as(_i32p), target.ctypes.data_as(_i64p), score.ctypes.data_as(_i32p),
                                                      mir.ctypes.data_as(_u8p), C.byref(count))
+            if st == CDS_ERR_CAPACITY and capacity is None:
+                cap = int(count.value)
+                continue
+            _check(st, self.ctx.h)
+            c = int(count.value)
+            return mask[:c], target[:c], score[:c], mir[:c]
+        _check(st, self.ctx.h)
+
+    def search_matches(self, library, pct_positive_pixels=0.0, capacity=None):
+        """cds_search_matches: every pair that passes isMatch over a resident library."""
+        cap = int(capacity) if capacity is not None else max(1024, 4 * len(self))
+        for _ in range(2):
+            mask = np.zeros(cap, np.int32); target = np.zeros(cap, np.int64); score = np.zeros(cap, np.int32); mir = np.zeros(cap, np.uint8)
+            count = C.c_int64(0)
+            st = lib().cds_search_matches(self.ctx.h, self.h, library.h, float(pct_positive_pixels), cap, mask.ctypes.data_as(_i32p),
+                                          target.ctypes.data_as(_i64p), score.ctypes.data_as(_i32p), mir.ctypes.data_as(_u8p), C.byref(count))
             if st == CDS_ERR_CAPACITY and capacity is None:
                 cap = int(count.value)
                 continue

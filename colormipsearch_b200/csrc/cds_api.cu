@@ -266,6 +266,10 @@ extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t
         ctx->match_kernel = (int) value;
         return CDS_OK;
     }
+    if (std::strcmp(name, "resident_occupancy") == 0) {
+        ctx->resident_occupancy = value != 0;
+        return CDS_OK;
+    }
     if (std::strcmp(name, "stream_chunk") == 0) {
         if (value < 1 || value > 65536) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk must be 1..65536");
         ctx->stream_chunk = value;
@@ -328,6 +332,7 @@ cds_status cds_library::bake(int threshold)
 
 cds_status cds_library::ensure_occupancy(int rings)
 {
+    if (occ_on_the_fly) return CDS_OK;
     if (occ_rings != rings || occ_threshold != baked_threshold) {
         for (auto &sh : shards) sh.occ_done = 0;
         occ_rings = rings;
@@ -343,8 +348,20 @@ cds_status cds_library::ensure_occupancy(int rings)
         DevState &ds = ctx->devs[d];
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
         if (!sh.occ) {
-            CDS_CUDA(ctx, cudaMalloc(&sh.occ, (size_t) sh.cap_local * plane_words * sizeof(uint32_t)));
-            CDS_CUDA(ctx, cudaMalloc(&sh.valid, (size_t) std::min<int64_t>(sh.cap_local, kValidChunk) * plane_words * sizeof(uint32_t)));
+            cudaError_t e = cudaMalloc(&sh.occ, (size_t) sh.cap_local * plane_words * sizeof(uint32_t));
+            if (e == cudaSuccess) e = cudaMalloc(&sh.valid, (size_t) std::min<int64_t>(sh.cap_local, kValidChunk) * plane_words * sizeof(uint32_t));
+            if (e == cudaErrorMemoryAllocation) {
+                // no room for resident bitmaps next to the code planes: searches over this library build them per target chunk
+                cudaGetLastError();
+                for (auto &x : shards) {
+                    if (x.occ) { cudaFree(x.occ); x.occ = nullptr; }
+                    if (x.valid) { cudaFree(x.valid); x.valid = nullptr; }
+                    x.occ_done = 0;
+                }
+                occ_on_the_fly = true;
+                return CDS_OK;
+            }
+            CDS_CUDA(ctx, e);
         }
         launch_occupancy(sh.planes, g, sh.occ_done, nl - sh.occ_done, rings, bpitch, sh.valid, std::min<int64_t>(sh.cap_local, kValidChunk), sh.occ, ds.stream);
         ctx->stats.kernel_launches += 2 * ((nl - sh.occ_done + kValidChunk - 1) / kValidChunk);
@@ -1028,7 +1045,10 @@ extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds
     if (T == 0) return CDS_OK;
     CDS_TRY(ms->sync_descs());
     CDS_TRY(lib->bake(ms->params.data_threshold));
-    if (batched_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
+    const bool batched = batched_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks();
+    if (batched && ctx->resident_occupancy) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
+    if (batched && (lib->occ_on_the_fly || !ctx->resident_occupancy))
+        return search_library_chunked(ctx, ms, lib, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count);
     const int D = lib->n_dev();
     std::vector<int32_t> min_score(M);
     for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);

@@ -78,6 +78,7 @@ struct cds_ctx {
     mutable std::string err;
     cds_search_stats stats{};
     int match_kernel = 0;      // cds_ctx_set_option("match_kernel"): 0 automatic, 1 candidate, 2 band, 3 gather
+    int resident_occupancy = 1;   // cds_ctx_set_option("resident_occupancy"): 0 = always build occupancy bitmaps per target chunk
     int64_t stream_chunk = 256;   // cds_ctx_set_option("stream_chunk"): targets per chunk of cds_search_stream_rgb
 
     cds_status fail(cds_status code, const std::string &msg) const;
@@ -103,6 +104,7 @@ struct cds_library {
     };
     int bpitch = 0;
     int occ_threshold = 0, occ_rings = -1;   // parameters `occ` was built for
+    bool occ_on_the_fly = false;             // the bitmaps do not fit next to the planes: searches build them per target chunk
     std::vector<Shard> shards;
 
     int n_dev() const { return (int) shards.size(); }
@@ -164,6 +166,9 @@ bool batched_kernel_supported(int xy_shift, const PlaneGeom &g);
 int choose_pitch(int W);
 // smallest score in [1, P] with ColorMIPSearch.isMatch true; P + 1 when none
 int32_t min_matching_score(int32_t P, double pct_positive_pixels);
+// cds_search_topk over a resident library with occupancy bitmaps built per target chunk (cds_stream.cu)
+cds_status search_library_chunked(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, int32_t k, double pct_positive_pixels,
+                                  int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count);
 
 // Appends n images at consecutive global indices; `src` fills the device staging buffer with the RGB pixels of images
 // [i0, i0 + cnt) of the call (an H2D copy or a generator kernel) on ds.stream.

@@ -43,7 +43,7 @@ void cds::StreamBufs::release()
 
 namespace {
 
-cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, int bpitch, int64_t chunk, int64_t M, int64_t k)
+cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, int bpitch, int64_t chunk, int64_t M, int64_t k, bool upload)
 {
     StreamBufs &sb = ds.sb;
     CDS_CUDA(ctx, cudaSetDevice(ds.dev));
@@ -66,13 +66,18 @@ cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, in
         sb.chunk = 0; sb.m_cap = 0;
         const size_t words = g.total_words(chunk);
         const size_t bm_words = (size_t) chunk * g.H * occupancy_row_pitch(bpitch);
-        for (int i = 0; i < 2; i++) CDS_CUDA(ctx, cudaMalloc(&sb.staging[i], (size_t) chunk * img_bytes + 64));
-        CDS_CUDA(ctx, cudaMalloc(&sb.planes, words * sizeof(uint32_t)));
+        (void) words;
         CDS_CUDA(ctx, cudaMalloc(&sb.occ, bm_words * sizeof(uint32_t)));
         CDS_CUDA(ctx, cudaMalloc(&sb.valid, bm_words * sizeof(uint32_t)));
+        sb.W = g.W; sb.H = g.H; sb.chunk = chunk;
+    }
+    if (upload && !sb.planes) {
+        // staging for the uploads and code planes of one chunk: only searches over host targets need them
+        const size_t words = g.total_words(sb.chunk);
+        for (int i = 0; i < 2; i++) CDS_CUDA(ctx, cudaMalloc(&sb.staging[i], (size_t) sb.chunk * img_bytes + 64));
+        CDS_CUDA(ctx, cudaMalloc(&sb.planes, words * sizeof(uint32_t)));
         launch_fill_words(sb.planes, words, CDS_CODE_PAD_WORD, ds.stream);      // guard rows stay pad words for ever
         CDS_CUDA(ctx, cudaGetLastError());
-        sb.W = g.W; sb.H = g.H; sb.chunk = chunk;
     }
     if (sb.m_cap < M) {
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
@@ -115,14 +120,16 @@ struct AllMatchesOut {
 
 cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8_t *targets_rgb, int64_t n_targets,
                               int32_t k, double pct_positive_pixels,
-                              int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count, const AllMatchesOut *all)
+                              int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count, const AllMatchesOut *all,
+                              cds_library *resident)
 {
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
     if (ms->ctx != ctx) return ctx->fail(CDS_ERR_BAD_ARG, "mask set belongs to another context");
     if (!all && (k <= 0 || k > topk_max_k())) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: k must be in 1..4096");
     if (all) k = 1;
-    if (n_targets < 0 || (n_targets > 0 && !targets_rgb)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: bad target array");
+    if (resident) n_targets = resident->size;
+    if (!resident && (n_targets < 0 || (n_targets > 0 && !targets_rgb))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: bad target array");
     const int M = (int) ms->sizes.size();
     if (all) {
         if (!all->count || all->capacity < 0 || (all->capacity > 0 && (!all->mask || !all->target || !all->score)))
@@ -141,15 +148,33 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     g.W = ms->W; g.H = ms->H; g.pitch = choose_pitch(ms->W); g.guard = CDS_GUARD_ROWS;
     const int bpitch = occupancy_pitch(g.W);
     const size_t img_bytes = (size_t) g.W * g.H * 3;
+    if (resident) {
+        if (resident->ctx != ctx) return ctx->fail(CDS_ERR_BAD_ARG, "library belongs to another context");
+        g = resident->g;
+        CDS_TRY(resident->bake(ms->params.data_threshold));
+    }
     const int64_t chunk = std::min<int64_t>(ctx->stream_chunk, n_targets);
-    const int64_t n_chunks = (n_targets + chunk - 1) / chunk;
+    // the chunk plan: (device, first target, count); host targets go round-robin over the devices, a resident library is
+    // walked shard by shard (first = index LOCAL to the shard)
+    struct Chunk { int d; int64_t first, cnt; };
+    std::vector<Chunk> plan;
+    if (resident) {
+        int64_t longest = 0;
+        for (int d = 0; d < D; d++) longest = std::max(longest, resident->local_size(d));
+        for (int64_t f = 0; f < longest; f += chunk)
+            for (int d = 0; d < D; d++)
+                if (f < resident->local_size(d)) plan.push_back({d, f, std::min<int64_t>(chunk, resident->local_size(d) - f)});
+    } else {
+        for (int64_t c = 0, f = 0; f < n_targets; c++, f += chunk) plan.push_back({(int) (c % D), f, std::min<int64_t>(chunk, n_targets - f)});
+    }
+    const int64_t n_chunks = (int64_t) plan.size();
     const int thr = ms->params.data_threshold;
     const int rings = ms->params.xy_shift / 2;
     const bool want_occ = batched_kernel_supported(ms->params.xy_shift, g) && M >= band_min_masks();
 
     std::vector<int32_t> min_score(M);
     for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);
-    const int used_devs = (int) std::min<int64_t>(D, n_chunks);
+    const int used_devs = resident ? D : (int) std::min<int64_t>(D, n_chunks);
     std::vector<uint64_t *> all_keys(D, nullptr);
     std::vector<int32_t *> all_masks(D, nullptr);
     std::vector<unsigned long long *> all_counter(D, nullptr);
@@ -166,7 +191,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     struct Releaser { std::function<void()> f; ~Releaser() { f(); } } releaser{release_all};
     for (int d = 0; d < used_devs; d++) {
         DevState &ds = ctx->devs[d];
-        CDS_TRY(ensure_stream_bufs(ctx, ds, g, bpitch, chunk, M, k));
+        CDS_TRY(ensure_stream_bufs(ctx, ds, g, bpitch, chunk, M, k, resident == nullptr));
         CDS_CUDA(ctx, cudaMemcpyAsync(ds.sb.min_score, min_score.data(), (size_t) M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaMemsetAsync(ds.sb.counts_run, 0, (size_t) M * sizeof(int32_t), ds.stream));
         if (all) {
@@ -177,7 +202,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             CDS_CUDA(ctx, cudaMemsetAsync(all_counter[d], 0, sizeof(unsigned long long), ds.stream));
         }
         CDS_CUDA(ctx, cudaEventRecord(ds.ev0, ds.stream));
-        const size_t need = (size_t) 2 * ((n_chunks + D - 1) / D);
+        const size_t need = (size_t) 2 * (n_chunks / std::max(used_devs, 1) + 2);
         while (ds.sb.timing.size() < need) {
             cudaEvent_t e;
             CDS_CUDA(ctx, cudaEventCreate(&e));
@@ -187,28 +212,32 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
 
     // enqueue every chunk; nothing below blocks the host when the source is pinned memory
     std::vector<int64_t> per_dev(D, 0);
-    for (int64_t c = 0; c < n_chunks; c++) {
-        const int d = (int) (c % D);
+    for (const Chunk &ch : plan) {
+        const int d = ch.d;
         DevState &ds = ctx->devs[d];
         StreamBufs &sb = ds.sb;
         const int64_t j = per_dev[d]++;
         const int slot = (int) (j & 1);
-        const int64_t first = c * chunk;
-        const int64_t cnt = std::min<int64_t>(chunk, n_targets - first);
+        const int64_t first = ch.first, cnt = ch.cnt;
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
-        if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
-        CDS_CUDA(ctx, cudaMemcpyAsync(sb.staging[slot], targets_rgb + (size_t) first * img_bytes, (size_t) cnt * img_bytes,
-                                     cudaMemcpyHostToDevice, sb.copy_stream));
-        ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
-        CDS_CUDA(ctx, cudaEventRecord(sb.h2d_done[slot], sb.copy_stream));
-        CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
-        launch_encode_rgb(sb.staging[slot], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream);
-        CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ds.stream));
-        ctx->stats.kernel_launches++;
+        const uint32_t *planes = sb.planes;
+        if (resident) {
+            planes = resident->shards[d].planes + (size_t) first * g.plane_stride();      // the same geometry, starting at plane `first`
+        } else {
+            if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
+            CDS_CUDA(ctx, cudaMemcpyAsync(sb.staging[slot], targets_rgb + (size_t) first * img_bytes, (size_t) cnt * img_bytes,
+                                         cudaMemcpyHostToDevice, sb.copy_stream));
+            ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
+            CDS_CUDA(ctx, cudaEventRecord(sb.h2d_done[slot], sb.copy_stream));
+            CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
+            launch_encode_rgb(sb.staging[slot], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream);
+            CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ds.stream));
+            ctx->stats.kernel_launches++;
+        }
         TargetView tv;
-        tv.planes = sb.planes; tv.g = g; tv.bpitch = bpitch; tv.n = cnt; tv.occ = nullptr; tv.occ_ready = false;
+        tv.planes = planes; tv.g = g; tv.bpitch = bpitch; tv.n = cnt; tv.occ = nullptr; tv.occ_ready = false;
         if (want_occ) {
-            launch_occupancy(sb.planes, g, 0, cnt, rings, bpitch, sb.valid, sb.chunk, sb.occ, ds.stream);
+            launch_occupancy(planes, g, 0, cnt, rings, bpitch, sb.valid, sb.chunk, sb.occ, ds.stream);
             ctx->stats.kernel_launches += 2;
             tv.occ = sb.occ;
             tv.occ_ready = true;
@@ -262,6 +291,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     ctx->stats.match_kernel_ms = match_ms;
     ctx->stats.total_device_ms = total_ms;
     ctx->stats.comparisons = (int64_t) M * n_targets;
+    ctx->stats.chunked = 1;
     if (all) {
         // every passing pair, ordered like the reference's writer: by mask, descending matchingPixels, ascending target
         uint64_t total = 0;
@@ -285,7 +315,15 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             CDS_CUDA(ctx, cudaMemcpy(hk.data(), all_keys[d], n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
             CDS_CUDA(ctx, cudaMemcpy(hm.data(), all_masks[d], n * sizeof(int32_t), cudaMemcpyDeviceToHost));
             ctx->stats.d2h_bytes += (int64_t) (n * 12);
-            for (size_t i = 0; i < n; i++) pairs.push_back({hm[i], hk[i]});
+            for (size_t i = 0; i < n; i++) {
+                uint64_t key = hk[i];
+                if (resident) {       // keys of a resident library carry shard-local indices
+                    int32_t sc; int64_t tg; uint8_t mir;
+                    topk_decode_key(key, sc, tg, mir);
+                    key = topk_make_key(sc, resident->global_of(d, tg), mir);
+                }
+                pairs.push_back({hm[i], key});
+            }
         }
         std::sort(pairs.begin(), pairs.end(), [](const Pair &a, const Pair &b) { return a.mask != b.mask ? a.mask < b.mask : a.key < b.key; });
         for (size_t i = 0; i < pairs.size(); i++) {
@@ -309,6 +347,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             for (int i = 0; i < c; i++) {
                 Item it;
                 topk_decode_key(keys[i], it.score, it.target, it.mir);
+                if (resident) it.target = resident->global_of(d, it.target);
                 items.push_back(it);
             }
         }
@@ -335,7 +374,7 @@ extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms,
                                             int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
 {
     if (!ctx || !ms) { set_tls_error("cds_search_stream_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
-    return stream_search_impl(ctx, ms, targets_rgb, n_targets, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr);
+    return stream_search_impl(ctx, ms, targets_rgb, n_targets, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr, nullptr);
 }
 
 extern "C" cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *targets_rgb, int64_t n_targets,
@@ -345,5 +384,29 @@ extern "C" cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_mask
 {
     if (!ctx || !ms) { set_tls_error("cds_search_stream_matches_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
     const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
-    return stream_search_impl(ctx, ms, targets_rgb, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all);
+    return stream_search_impl(ctx, ms, targets_rgb, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, nullptr);
+}
+
+// The same chunked search over a device-resident library: occupancy bitmaps are built per chunk instead of being kept for
+// the whole library (cds_search_topk uses this when they do not fit next to the code planes, e.g. 50 000 targets per GPU).
+namespace cds {
+cds_status search_library_chunked(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, int32_t k, double pct_positive_pixels,
+                                  int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
+{
+    return stream_search_impl(ctx, ms, nullptr, 0, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr, lib);
+}
+}  // namespace cds
+
+extern "C" cds_status cds_search_matches(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, double pct_positive_pixels, int64_t capacity,
+                                         int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored, int64_t *out_count)
+{
+    if (!ctx || !ms || !lib) { set_tls_error("cds_search_matches: NULL argument"); return CDS_ERR_BAD_ARG; }
+    if (ms->W != lib->g.W || ms->H != lib->g.H) {
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        char buf[200];
+        snprintf(buf, sizeof buf, "Invalid image size - target's image size (%d, %d) must match query's image size: (%d, %d)", ms->W, ms->H, lib->g.W, lib->g.H);
+        return ctx->fail(CDS_ERR_SIZE_MISMATCH, buf);
+    }
+    const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
+    return stream_search_impl(ctx, ms, nullptr, 0, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, lib);
 }

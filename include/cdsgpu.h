@@ -89,7 +89,10 @@ int32_t    cds_abi_version(void);
 /* Tuning / test switches.  "match_kernel": 0 = automatic (default), 1 = candidate kernel, 2 = band kernel, 3 = gather kernel;
  * a kernel that does not support the search's parameters falls through to the next one.  All three compute the same
  * scores bit for bit (tests/test_pixelmatch_gpu.py cross-checks them).
- * "stream_chunk": targets per chunk of cds_search_stream_rgb (default 256).  Unknown names: CDS_ERR_BAD_ARG. */
+ * "stream_chunk": targets per chunk of the chunked searches (default 256).
+ * "resident_occupancy": 1 (default) keeps a library's occupancy bitmaps on the device next to its code planes (+23 % memory) and
+ * falls back to building them per target chunk inside cds_search_topk when they do not fit; 0 always builds them per chunk.
+ * Unknown names: CDS_ERR_BAD_ARG. */
 cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t value);
 
 /* Pinned host memory for callers that want full-rate uploads (optional; any host pointer is accepted everywhere). */
@@ -160,6 +163,11 @@ cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_maskset *ms, co
                                          double pct_positive_pixels, int64_t capacity,
                                          int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored,
                                          int64_t *out_count);
+
+/* Every pair that passes isMatch, for a device-resident library (same outputs and conventions as cds_search_stream_matches_rgb;
+ * target = index in the library). */
+cds_status cds_search_matches(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, double pct_positive_pixels, int64_t capacity,
+                              int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored, int64_t *out_count);
 
 /* One mask x one target held in host memory: the literal single-pair call of the Java API
  * (ColorDepthSearchAlgorithm.calculateMatchingScore, API/cds/ColorDepthSearchAlgorithm.java:60-61). */
@@ -235,6 +243,7 @@ typedef struct cds_search_stats {
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     int64_t match_kernel;        /* which match kernel the last launch used: 1 candidate, 2 band, 3 gather */
+    int64_t chunked;             /* 1 when the search walked its targets in chunks (streamed targets, or occupancy bitmaps built per chunk) */
 } cds_search_stats;
 cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out);
 

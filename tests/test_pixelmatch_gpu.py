@@ -228,12 +228,35 @@ def test_all_matches_search(ctx, synth, pct):
     ctx.set_option("stream_chunk", 16)
     got = ms.search_stream_matches(targets, pct)
     assert list(zip(got[0].tolist(), got[1].tolist(), got[2].tolist(), got[3].tolist())) == exp
+    got = ms.search_matches(lib, pct)                       # the same over the resident library
+    assert list(zip(got[0].tolist(), got[1].tolist(), got[2].tolist(), got[3].tolist())) == exp
     # too small a buffer: CDS_ERR_CAPACITY and the required size
     if len(exp) > 1:
         with pytest.raises(capi.CdsError) as e:
             ms.search_stream_matches(targets, pct, capacity=len(exp) - 1)
         assert e.value.status == capi.CDS_ERR_CAPACITY and str(len(exp)) in e.value.message
     ctx.set_option("stream_chunk", 256)
+    ms.close()
+
+
+def test_topk_with_occupancy_built_per_chunk(ctx, synth):
+    """cds_search_topk when the occupancy bitmaps are not kept next to the planes (libraries near the memory limit)."""
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    ms = _maskset(ctx, (20, 20, 0.01, 2, True), rects)
+    ms.add_rgb(masks)
+    exp = ms.search_topk(lib, 40, 1.0)
+    ctx.set_option("resident_occupancy", 0)
+    ctx.set_option("stream_chunk", 24)
+    got = ms.search_topk(lib, 40, 1.0)
+    assert ctx.last_stats()["match_kernel"] == 1 and ctx.last_stats()["chunked"] == 1
+    ctx.set_option("resident_occupancy", 1)
+    ctx.set_option("stream_chunk", 256)
+    assert np.array_equal(got[3], exp[3])
+    for m in range(len(masks)):
+        c = exp[3][m]
+        for a, b in zip(got[:3], exp[:3]):
+            assert np.array_equal(a[m, :c], b[m, :c])
     ms.close()
 
 
