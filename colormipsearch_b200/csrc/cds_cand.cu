@@ -677,20 +677,25 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     cudaMemsetAsync(g_cand_counter[dev], 0, sizeof(unsigned long long), s);
     // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket.  More warps need more
     // shared memory for their queues; when the band stages no longer fit (xyShift 4: 34 accumulators per mask) fewer are used.
-    static const int warps_env = env_int("CDSGPU_CAND_WARPS", 28);
+    static const int warps_env = env_int("CDSGPU_CAND_WARPS", 31);
     static const int chunk_env = env_int("CDSGPU_CAND_CHUNK", 256);
     int warps = warps_env;
+    if (warps >= 31 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 31).ok) warps = 28;
     if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok) warps = 24;
     if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24).ok) warps = 16;
 #define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<CDS_PALETTE_GROUP, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev)
-    if (chunk_env == 256) {
-        if (warps >= 28) return CDS_CAND_LAUNCH(28, 256);
-        if (warps >= 24) return CDS_CAND_LAUNCH(24, 256);
-        return CDS_CAND_LAUNCH(16, 256);
+    if (chunk_env == 512) {
+        if (warps >= 31) return CDS_CAND_LAUNCH(31, 512);
+        return CDS_CAND_LAUNCH(28, 512);
     }
-    if (warps >= 28) return CDS_CAND_LAUNCH(28, 128);
-    if (warps >= 24) return CDS_CAND_LAUNCH(24, 128);
-    return CDS_CAND_LAUNCH(16, 128);
+    if (chunk_env == 128) {
+        if (warps >= 28) return CDS_CAND_LAUNCH(28, 128);
+        return CDS_CAND_LAUNCH(24, 128);
+    }
+    if (warps >= 31) return CDS_CAND_LAUNCH(31, 256);
+    if (warps >= 28) return CDS_CAND_LAUNCH(28, 256);
+    if (warps >= 24) return CDS_CAND_LAUNCH(24, 256);
+    return CDS_CAND_LAUNCH(16, 256);
 #undef CDS_CAND_LAUNCH
 }
 
