@@ -95,6 +95,8 @@ SIGNATURES = {
     "cds_shape_score_2d": (C.c_int64, [C.c_int64, C.c_int64]),
     "cds_normalized_score": (C.c_double, [C.c_int32, C.c_int64, C.c_int64, C.c_int64]),
     "cds_normalize_scores": (C.c_int32, [_i32p, _i64p, _i64p, C.c_int64, _f32p]),
+    "cds_select_best_matches": (C.c_int32, [_i32p, _i32p, _i32p, C.c_int64, _i32p, C.c_int32, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64p, _i64p]),
+    "cds_java_string_hash": (C.c_int32, [C.c_char_p]),
     "cds_synth_rgb": (C.c_int32, [_vp, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "cds_synth_gradient": (C.c_int32, [_vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "cds_get_last_stats": (C.c_int32, [_vp, C.POINTER(SearchStats)]),
@@ -483,3 +485,30 @@ def class_intervals(z_tolerance, sector, rank):
     lo1, len1, lo2, len2 = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     _check(lib().cds_debug_class_intervals(float(z_tolerance), int(sector), int(rank), C.byref(lo1), C.byref(len1), C.byref(lo2), C.byref(len2)))
     return lo1.value, len1.value, lo2.value, len2.value
+
+
+def java_string_hash(s):
+    return int(lib().cds_java_string_hash(s.encode("ascii")))
+
+
+def select_best_matches(lines, samples, scores, top_lines, top_samples_per_line, top_matches_per_sample):
+    """ColorMIPProcessUtils.selectBestMatches over one mask's matches.  lines / samples: sequences of key strings (ASCII);
+    returns the indices of the kept matches in the reference's output order."""
+    def ids(keys):
+        table, out = {}, []
+        for k in keys:
+            k = k if k and k.strip() else "UNKNOWN"            # StringUtils.defaultIfBlank
+            out.append(table.setdefault(k, len(table)))
+        names = sorted(table, key=table.get)
+        return np.asarray(out, np.int32), np.asarray([java_string_hash(nm) for nm in names], np.int32)
+    lid, lhash = ids(lines)
+    sid, shash = ids(samples)
+    sc = np.ascontiguousarray(scores, np.int32)
+    n = len(sc)
+    sel = np.zeros(max(n, 1), np.int64)
+    cnt = C.c_int64(0)
+    _check(lib().cds_select_best_matches(lid.ctypes.data_as(_i32p), sid.ctypes.data_as(_i32p), sc.ctypes.data_as(_i32p), n,
+                                         lhash.ctypes.data_as(_i32p), len(lhash), shash.ctypes.data_as(_i32p), len(shash),
+                                         int(top_lines), int(top_samples_per_line), int(top_matches_per_sample),
+                                         sel.ctypes.data_as(_i64p), C.byref(cnt)))
+    return sel[: cnt.value]

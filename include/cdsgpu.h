@@ -221,6 +221,23 @@ double  cds_normalized_score(int32_t pixel_match_score, int64_t shape_score, int
 cds_status cds_normalize_scores(const int32_t *pixel_scores, const int64_t *gaps, const int64_t *high_exprs, int64_t n,
                                 float *normalized_out);
 
+/* ---------------------------------------------------------------- match selection (host logic) ------------------------------------------- */
+
+/* ColorMIPProcessUtils.selectBestMatches (TOOLS/cdsprocess/ColorMIPProcessUtils.java:12-34, two nested
+ * ItemsHandling.selectTopRankedElements, API/results/ItemsHandling.java:80-109) over the n matches of ONE mask, in the order the
+ * reference would hold them: line[i] / sample[i] = dense ids of the target's published name / neuron id (blank names already
+ * mapped to "UNKNOWN" by the caller), score[i] = matchingPixels.  line_hash[id] / sample_hash[id] = Java hashCode() of the key
+ * string: groups with equal best scores keep java.util.HashMap iteration order, which this call reproduces from the hashes.
+ * top_* <= 0 mean "no limit".  selected[] (room for n) receives the indices of the kept matches in the reference's output order:
+ * lines by descending best score, inside a line samples by descending best score, inside a sample matches by descending score
+ * (ties: input order). */
+cds_status cds_select_best_matches(const int32_t *line, const int32_t *sample, const int32_t *score, int64_t n,
+                                   const int32_t *line_hash, int32_t n_lines, const int32_t *sample_hash, int32_t n_samples,
+                                   int32_t top_lines, int32_t top_samples_per_line, int32_t top_matches_per_sample,
+                                   int64_t *selected, int64_t *n_selected);
+/* java.lang.String.hashCode() of an ASCII string (helper for non-Java callers of cds_select_best_matches). */
+int32_t cds_java_string_hash(const char *ascii);
+
 /* ---------------------------------------------------------------- synthetic inputs + instrumentation ------------------------------------- */
 
 /* Deterministic synthetic images, identical bit for bit on host and device (bench.py, scale tests).

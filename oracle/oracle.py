@@ -304,3 +304,79 @@ class ShapeMask:
 
 def num_threads():
     return lib().cdso_num_threads()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# f1: the selection of the matches that go on to shape scoring.  Pure-Python restatement (small inputs) of
+#   ItemsHandling.selectTopRankedElements   colormipsearch-api/src/main/java/org/janelia/colormipsearch/results/ItemsHandling.java:80-109
+#   ColorMIPProcessUtils.selectBestMatches   colormipsearch-tools/src/main/java/org/janelia/colormipsearch/cmd/cdsprocess/ColorMIPProcessUtils.java:12-34
+# including the iteration order of the java.util.HashMap that Collectors.groupingBy fills (ties between groups keep it).
+# ------------------------------------------------------------------------------------------------------------------
+def java_string_hash(s):
+    """java.lang.String.hashCode()."""
+    h = 0
+    for ch in s:
+        h = (31 * h + ord(ch)) & 0xFFFFFFFF
+    return h
+
+
+class JavaHashMap:
+    """Insertion and iteration order of java.util.HashMap<String, list> (OpenJDK 8+): table of 16 buckets, doubled when
+    ++size > 0.75 * capacity, resize splits every bucket preserving order; bins are kept as lists (no treeification)."""
+
+    def __init__(self):
+        self.table = [[] for _ in range(16)]
+        self.size = 0
+
+    @staticmethod
+    def _spread(key):
+        h = java_string_hash(key)
+        return h ^ (h >> 16)
+
+    def get_or_create(self, key):
+        b = self.table[self._spread(key) & (len(self.table) - 1)]
+        for k, v in b:
+            if k == key:
+                return v
+        v = []
+        b.append((key, v))
+        self.size += 1
+        if self.size > 0.75 * len(self.table):
+            old, cap = self.table, 2 * len(self.table)
+            self.table = [[] for _ in range(cap)]
+            for bucket in old:                      # lo / hi split keeps relative order
+                for k, val in bucket:
+                    self.table[self._spread(k) & (cap - 1)].append((k, val))
+        return v
+
+    def entries(self):
+        return [(k, v) for bucket in self.table for k, v in bucket]
+
+
+def select_top_ranked(items, key_fn, score_fn, top_results, limit_sub_results):
+    """ItemsHandling.selectTopRankedElements -> list of (key, best score, sorted items)."""
+    groups = JavaHashMap()
+    for it in items:
+        k = key_fn(it)
+        if k is None or not k.strip():
+            k = "UNKNOWN"                            # StringUtils.defaultIfBlank
+        groups.get_or_create(k).append(it)
+    scored = []
+    for k, r in groups.entries():
+        r.sort(key=lambda it: -float(score_fn(it)))      # List.sort(comparator.reversed()): stable
+        if 0 < limit_sub_results < len(r):
+            r = r[:limit_sub_results]
+        scored.append((k, max(float(score_fn(it)) for it in r), r))
+    scored.sort(key=lambda e: -e[1])                     # Stream.sorted: stable on HashMap order
+    if top_results > 0 and len(scored) > top_results:
+        scored = scored[:top_results]
+    return scored
+
+
+def select_best_matches(matches, top_lines, top_samples_per_line, top_matches_per_sample):
+    """matches: list of (line, sample, score, ...).  Returns the kept matches in the reference's output order."""
+    out = []
+    for _, _, line_items in select_top_ranked(matches, lambda m: m[0], lambda m: m[2], top_lines, -1):
+        for _, _, sample_items in select_top_ranked(line_items, lambda m: m[1], lambda m: m[2], top_samples_per_line, top_matches_per_sample):
+            out.extend(sample_items)
+    return out
