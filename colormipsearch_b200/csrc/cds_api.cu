@@ -338,7 +338,8 @@ cds_status cds_library::ensure_occupancy(int rings)
         occ_rings = rings;
         occ_threshold = baked_threshold;
     }
-    const size_t plane_words = (size_t) g.H * occupancy_row_pitch(bpitch);
+    const size_t plane_words = occupancy_target_words(g.W, g.H);
+    const size_t valid_words = (size_t) g.H * CDS_NUM_SECTORS * occupancy_valid_pitch(g.W);
     const int64_t kValidChunk = 256;
     bool launched = false;
     for (int d = 0; d < n_dev(); d++) {
@@ -349,7 +350,8 @@ cds_status cds_library::ensure_occupancy(int rings)
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
         if (!sh.occ) {
             cudaError_t e = cudaMalloc(&sh.occ, (size_t) sh.cap_local * plane_words * sizeof(uint32_t));
-            if (e == cudaSuccess) e = cudaMalloc(&sh.valid, (size_t) std::min<int64_t>(sh.cap_local, kValidChunk) * plane_words * sizeof(uint32_t));
+            if (e == cudaSuccess) e = cudaMalloc(&sh.valid, (size_t) std::min<int64_t>(sh.cap_local, kValidChunk) * valid_words * sizeof(uint32_t));
+            if (e == cudaSuccess) e = cudaMemsetAsync(sh.occ, 0, (size_t) sh.cap_local * plane_words * sizeof(uint32_t), ds.stream);   // rows beyond the image stay clear
             if (e == cudaErrorMemoryAllocation) {
                 // no room for resident bitmaps next to the code planes: searches over this library build them per target chunk
                 cudaGetLastError();
@@ -390,7 +392,7 @@ extern "C" cds_status cds_library_create(cds_ctx *ctx, int32_t width, int32_t he
     lib->g.H = height;
     lib->g.pitch = choose_pitch(width);
     lib->g.guard = CDS_GUARD_ROWS;
-    lib->bpitch = occupancy_pitch(width);
+    lib->bpitch = occupancy_tile_pitch(width);
     lib->capacity = capacity;
     lib->baked_threshold = 20;
     int D = (int) ctx->devs.size();
@@ -809,7 +811,8 @@ cds_status cds_maskset::sync_descs()
                               compact_ok && n_compact_groups == n_groups;
         if (words_ok) {
             uint32_t *d_grow = nullptr;
-            const size_t gs_n = (size_t) n_groups * (H + 1), ms_n = (size_t) M * (H + 1);
+            const int HT = occupancy_tile_rows(H);              // the lists are ordered by rows of 8 x 4 tiles
+            const size_t gs_n = (size_t) n_groups * (HT + 1), ms_n = (size_t) M * (HT + 1);
             const cds_class_interval *class_tab = nullptr;
             cds_status st = ctx->class_table_on(ds, params.z_tolerance, &class_tab);
             // d_wstart: per-mask entry offsets [M][H+1], per-mask bit offsets [M][H+1], entry row starts [G][H+1], bit row starts [G][H+1]
@@ -820,8 +823,8 @@ cds_status cds_maskset::sync_descs()
             uint32_t *d_wcount = d_wstart[d], *d_bcount = d_wstart[d] + ms_n;
             if (st == CDS_OK) {
                 launch_words_count(d_descs[d], M, W, H, params.mirror != 0, class_tab, d_wcount, d_bcount, ds.stream);
-                launch_words_group_rows(d_wcount, M, H, d_grow, ds.stream);
-                launch_words_group_rows(d_bcount, M, H, d_grow + gs_n, ds.stream);
+                launch_words_group_rows(d_wcount, M, HT, d_grow, ds.stream);
+                launch_words_group_rows(d_bcount, M, HT, d_grow + gs_n, ds.stream);
                 ctx->stats.kernel_launches += 3;
                 st = ctx->check(cudaGetLastError(), "word count kernels");
             }
@@ -832,9 +835,9 @@ cds_status cds_maskset::sync_descs()
             uint64_t total[2] = {0, 0};
             for (int a = 0; a < 2; a++)
                 for (int g = 0; g < n_groups; g++) {
-                    uint32_t *row = grow.data() + a * gs_n + (size_t) g * (H + 1);
-                    for (int y = 0; y < H; y++) { const uint32_t c = row[y]; row[y] = (uint32_t) total[a]; total[a] += c; }
-                    row[H] = (uint32_t) total[a];
+                    uint32_t *row = grow.data() + a * gs_n + (size_t) g * (HT + 1);
+                    for (int y = 0; y < HT; y++) { const uint32_t c = row[y]; row[y] = (uint32_t) total[a]; total[a] += c; }
+                    row[HT] = (uint32_t) total[a];
                 }
             if (total[0] < ((uint64_t) 1 << 32) && total[1] < ((uint64_t) 1 << 32)) {
                 uint32_t *d_gstart = d_wstart[d] + 2 * ms_n, *d_bstart = d_gstart + gs_n;
@@ -843,10 +846,10 @@ cds_status cds_maskset::sync_descs()
                 uint4 *d_entries = reinterpret_cast<uint4 *>(d_words[d]);
                 uint16_t *d_lpal = reinterpret_cast<uint16_t *>(d_entries + std::max<uint64_t>(total[0], 1));
                 CDS_CUDA(ctx, cudaMemcpyAsync(d_gstart, grow.data(), 2 * gs_n * sizeof(uint32_t), cudaMemcpyHostToDevice, ds.stream));
-                for (int m = 0; m < M; m++) h[m].wstart = d_wcount + (size_t) m * (H + 1);
+                for (int m = 0; m < M; m++) h[m].wstart = d_wcount + (size_t) m * (HT + 1);
                 for (int g = 0; g < n_groups; g++) {
                     groups[g].words = d_entries;
-                    groups[g].gstart = d_gstart + (size_t) g * (H + 1);
+                    groups[g].gstart = d_gstart + (size_t) g * (HT + 1);
                     groups[g].lpal = d_lpal;
                 }
                 CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));

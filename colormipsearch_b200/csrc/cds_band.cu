@@ -52,7 +52,7 @@ struct BandParams {
     int n_bands;
     int stage_words;                // (R + 2s) * pitch
     int n_groups;
-    const uint32_t *occ;            // occupancy bitmaps [n_targets][H][occupancy_row_pitch(bpitch)]; this kernel uses the all-sector row
+    const uint32_t *occ;            // occupancy bitmaps in 8 x 4 tiles (cds_kernels.cuh); this kernel uses the all-sector row
     int bpitch;
     const PaletteGroup *groups;     // palette group of masks[0] onwards (masks[0] is CDS_PALETTE_GROUP aligned in the mask set)
 };
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int rowpitch = occupancy_row_pitch(p.bpitch);
     const int any_off = CDS_NUM_SECTORS * p.bpitch;          // the OR over the sectors
-    const int bits_words = p.rows_per_band * rowpitch;
+    const int bits_words = (p.rows_per_band / 4) * rowpitch;       // rows_per_band is a multiple of the tile height
     const BandSmem<GROUP> L(p.stage_words, p.n_bands, NV, bits_words);
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
                     const int y1 = min(y0 + R, H);
                     const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
                     const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
-                    const uint32_t bbytes = (uint32_t) ((y1 - y0) * rowpitch) * 4u;
-                    const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * rowpitch;
+                    const uint32_t bbytes = (uint32_t) (((y1 - y0 + 3) / 4) * rowpitch) * 4u;
+                    const uint32_t *bsrc = p.occ + ((size_t) t * occupancy_tile_rows(H) + y0 / 4) * rowpitch;
                     mbar_expect_tx(bar, bytes + bbytes);
                     bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
                     bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
@@ -308,10 +308,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
                         const int brow = (int) ((cur >> 11) & 0x3FFu) - y0;
                         const int xm = W - 1 - x;
                         const bool live = base + lane < seg1;
-                        const uint32_t wn = bits[brow * rowpitch + any_off + (x >> 5)];
-                        const uint32_t wm = bits[brow * rowpitch + any_off + (xm >> 5)];
-                        const bool any_n = __any_sync(0xffffffffu, live && ((wn >> (x & 31)) & 1u));
-                        const bool any_m = MIRROR && __any_sync(0xffffffffu, live && ((wm >> (xm & 31)) & 1u));
+                        const uint32_t wn = bits[(brow >> 2) * rowpitch + any_off + (x >> 3)];
+                        const uint32_t wm = bits[(brow >> 2) * rowpitch + any_off + (xm >> 3)];
+                        const bool any_n = __any_sync(0xffffffffu, live && ((wn >> ((brow & 3) * 8 + (x & 7))) & 1u));
+                        const bool any_m = MIRROR && __any_sync(0xffffffffu, live && ((wm >> ((brow & 3) * 8 + (xm & 7))) & 1u));
                         if (!any_n && !any_m) continue;
                         const uint2 pe = s_pal[cur >> 21];
                         const uint32_t lo1 = (pe.x & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
@@ -334,10 +334,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_band_kernel(cons
                         const int brow = (int) (cur.x >> 16) - y0;
                         const int xm = W - 1 - x;
                         const bool live = base + lane < seg1;
-                        const uint32_t wn = bits[brow * rowpitch + any_off + (x >> 5)];
-                        const uint32_t wm = bits[brow * rowpitch + any_off + (xm >> 5)];
-                        const bool any_n = __any_sync(0xffffffffu, live && ((wn >> (x & 31)) & 1u));
-                        const bool any_m = MIRROR && __any_sync(0xffffffffu, live && ((wm >> (xm & 31)) & 1u));
+                        const uint32_t wn = bits[(brow >> 2) * rowpitch + any_off + (x >> 3)];
+                        const uint32_t wm = bits[(brow >> 2) * rowpitch + any_off + (xm >> 3)];
+                        const bool any_n = __any_sync(0xffffffffu, live && ((wn >> ((brow & 3) * 8 + (x & 7))) & 1u));
+                        const bool any_m = MIRROR && __any_sync(0xffffffffu, live && ((wm >> ((brow & 3) * 8 + (xm & 7))) & 1u));
                         if (!any_n && !any_m) continue;
                         const uint32_t len1 = ((cur.w & 0xFFFFu) << CDS_CODE_SR_SHIFT) | 0xFFu;
                         const uint32_t len2 = ((cur.w >> 16) << CDS_CODE_SR_SHIFT) | 0xFFu;
@@ -394,18 +394,18 @@ struct BandConfig {
 template <int GROUP>
 BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
 {
-    const int bpitch = occupancy_pitch(g.W);
+    const int bpitch = occupancy_tile_pitch(g.W);
     BandConfig c{};
     const int S = xy_shift;
     const int NS = xy_shift == 0 ? 1 : (xy_shift == 2 ? 9 : 17);
     const int NV = mirror ? 2 * NS : NS;
     const size_t budget = 227 * 1024;
-    for (int R = g.H; R >= 1; R--) {
+    for (int R = (g.H + 3) / 4 * 4; R >= 4; R -= 4) {       // whole occupancy tiles per band
         int n_bands = (g.H + R - 1) / R;
         if (n_bands > kMaxBands) break;
         size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
         if (stage_words * 4 >= (1u << 20)) continue;
-        BandSmem<GROUP> L((int) stage_words, n_bands, NV, R * occupancy_row_pitch(bpitch));
+        BandSmem<GROUP> L((int) stage_words, n_bands, NV, (R / 4) * occupancy_row_pitch(bpitch));
         if (L.total <= budget) {
             c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = L.total; c.ok = true;
             return c;
@@ -472,7 +472,7 @@ int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *p
                            cudaStream_t s)
 {
     if (n_masks == 0 || n_targets == 0) return 0;
-    if (!occ || !groups || bpitch != occupancy_pitch(g.W)) return 0;
+    if (!occ || !groups || bpitch != occupancy_tile_pitch(g.W)) return 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 64) return 0;

@@ -28,7 +28,7 @@ namespace cds {
 namespace {
 
 constexpr int kStages = 2;
-constexpr int kMaxBands = 128;
+constexpr int kMaxBands = 256;
 constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy destination aligned)
 constexpr int kQueue = 64;          // candidate slots per warp (power of two, >= 2 * 32)
 constexpr int kWordQueue = 64;      // word slots per warp (power of two, >= 2 * 32)
@@ -45,9 +45,10 @@ struct CandParams {
     int n_bands;
     int stage_words;                // (R + 2s) * pitch
     int n_groups;
-    const uint32_t *occ;            // occupancy bitmaps [n_targets][H][occupancy_row_pitch(bpitch)]
+    const uint32_t *occ;            // occupancy bitmaps in 8 x 4 tiles, [n_targets][tile rows][sectors + 1][bpitch] (cds_kernels.cuh)
     int bpitch;
     const PaletteGroup *groups;
+    int *acc;                       // [grid][GROUP][2 * offsets] match counters, zero between work items
     int debug_skip;                 // profiling aid (CDSGPU_CAND_NULL): consumers skip the tickets, only the band pipeline runs
 };
 
@@ -67,23 +68,24 @@ __device__ __forceinline__ void offset_of(int v, int &dx, int &dy)
     dy = (k % 3 - 1) * 4;
 }
 
-// acc[OFF / 4] += 1 (shared memory, predicated reduction) when the code word c lies in [lo, lo + len].
-// Matches are rare (a few per hundred evaluations), so nearly all of these reductions are predicated off.
+// acc[OFF / 4] += 1 (a predicated reduction on this CTA's accumulators in global memory, performed in L2) when the code word c
+// lies in [lo, lo + len].  Matches are rare (a few per hundred evaluations), so nearly all of these reductions are predicated
+// off; keeping the accumulators out of shared memory leaves room for taller bands.
 template <int OFF>
-__device__ __forceinline__ void count_hit(uint32_t acc, uint32_t c, uint32_t lo, uint32_t len)
+__device__ __forceinline__ void count_hit(const int *acc, uint32_t c, uint32_t lo, uint32_t len)
 {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 a;\n\t"
                  "sub.u32 a, %1, %2;\n\t"
                  "setp.le.u32 p, a, %3;\n\t"
-                 "@p red.shared.add.u32 [%0+%4], 1;\n\t}"
-                 :: "r"(acc), "r"(c), "r"(lo), "r"(len), "n"(OFF));
+                 "@p red.global.add.u32 [%0+%4], 1;\n\t}"
+                 :: "l"(acc), "r"(c), "r"(lo), "r"(len), "n"(OFF));
     // no "memory" clobber on purpose: the band reads around it may be scheduled freely; the accumulators are only read after a
-    // named barrier (itself a volatile asm with a memory clobber), and volatile asms keep their order
+    // __threadfence() and a named barrier (a volatile asm with a memory clobber), and volatile asms keep their order
 }
 
 template <int GROUP>
 struct CandSmem {
-    size_t stage_off, bits_off, pal_off, acc_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, total;
+    size_t stage_off, bits_off, pal_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, total;
     __host__ __device__ CandSmem(int stage_words, int NS, int bits_words, int n_warps)
     {
         size_t o = 0;
@@ -96,7 +98,7 @@ struct CandSmem {
         item_off = o;  o += 16;
         next_off = o;  o += 16;
         band_off = o;  o += (size_t) kStages * 8;                               // per stage: {first, end} entry of the group's word list
-        acc_off = o;   o += (size_t) GROUP * 2 * NS * 4;
+        (void) NS;
         total = o;
     }
 };
@@ -113,7 +115,7 @@ struct EvalUnroll {
         cw[V] = pc[dy * pitch + dx];
         EvalUnroll<NRINGS, V + 1>::load(pc, pitch, cw);
     }
-    static __device__ __forceinline__ void count(const uint32_t (&cw)[Offsets<NRINGS>::N], uint32_t acc, uint32_t lo, uint32_t len)
+    static __device__ __forceinline__ void count(const uint32_t (&cw)[Offsets<NRINGS>::N], const int *acc, uint32_t lo, uint32_t len)
     {
         count_hit<4 * V>(acc, cw[V], lo, len);
         EvalUnroll<NRINGS, V + 1>::count(cw, acc, lo, len);
@@ -122,7 +124,7 @@ struct EvalUnroll {
 template <int NRINGS>
 struct EvalUnroll<NRINGS, Offsets<NRINGS>::N> {
     static __device__ __forceinline__ void load(const uint32_t *, int, uint32_t (&)[Offsets<NRINGS>::N]) {}
-    static __device__ __forceinline__ void count(const uint32_t (&)[Offsets<NRINGS>::N], uint32_t, uint32_t, uint32_t) {}
+    static __device__ __forceinline__ void count(const uint32_t (&)[Offsets<NRINGS>::N], const int *, uint32_t, uint32_t) {}
 };
 
 // First half of an evaluation: the candidate's palette reference (palette index | 0x8000 for the second interval), an L2
@@ -136,11 +138,11 @@ __device__ __forceinline__ uint32_t fetch_palette_ref(uint2 cand, bool live, con
 
 template <int NRINGS>
 __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const uint32_t *__restrict__ band, int y0, int pitch,
-                                                const uint2 *__restrict__ s_pal, uint32_t acc_base)
+                                                const uint2 *__restrict__ s_pal, const int *acc_base)
 {
     constexpr int NS = Offsets<NRINGS>::N;
     constexpr int S = 2 * NRINGS;
-    const uint32_t mi = (cand.x >> 22) & 255u;
+    const uint32_t mi = (cand.x >> 22) & 511u;
     const uint2 pe = s_pal[pr & (CDS_PALETTE_SIZE - 1)];
     const uint32_t iv = (pr & 0x8000u) ? pe.y : pe.x;                           // the interval that lives in this candidate's sector
     const uint32_t lo = (iv & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
@@ -150,7 +152,7 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const u
     const uint32_t orient = (cand.x >> 21) & 1u;
     const uint32_t *pc = band + (yrel + S) * pitch + x;
     // accumulators of this mask: [0, NS) unmirrored, [NS, 2 NS) mirrored
-    const uint32_t acc = acc_base + (mi * 2u * NS + orient * NS) * 4u;
+    const int *acc = acc_base + (mi * 2u * NS + orient * NS);
     uint32_t cw[NS];
     EvalUnroll<NRINGS, 0>::load(pc, pitch, cw);          // all shifted reads first, then the compares
     EvalUnroll<NRINGS, 0>::count(cw, acc, lo, len);
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int rowpitch = occupancy_row_pitch(p.bpitch);
-    const int bits_words = p.rows_per_band * rowpitch;
+    const int bits_words = (p.rows_per_band / 4) * rowpitch;       // rows_per_band is a multiple of the tile height
     const CandSmem<GROUP> L(p.stage_words, NS, bits_words, NCW);
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
     uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + L.queue_off);                  // [NCW][kQueue] candidates
     uint2 *s_wqueue = reinterpret_cast<uint2 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] {candidate bits, entry index} of words with candidates
-    int *s_acc = reinterpret_cast<int *>(smem_raw + L.acc_off);                         // [GROUP][NV]
+    int *s_acc = p.acc + (size_t) blockIdx.x * GROUP * NV;                              // this CTA's accumulators [GROUP][NV], global memory, zero on entry
     uint2 *s_band = reinterpret_cast<uint2 *>(smem_raw + L.band_off);                   // [kStages] range of the group's word list inside the staged band
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
     unsigned long long *s_empty = s_full + kStages;
@@ -193,7 +195,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < GROUP * NV; i += blockDim.x) s_acc[i] = 0;
     // never-matching words below each stage: a candidate in the first row of a band whose shifted column is -1..-4
     if (tid < kStages * kPrePad) s_stage[(tid / kPrePad) * stage_stride - kPrePad + (tid % kPrePad)] = CDS_CODE_PAD_WORD;
     __syncthreads();
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     const int y0 = b * R;
                     const int y1 = min(y0 + R, H);
                     uint2 range = make_uint2(0u, 0u);
-                    if (!done) range = make_uint2(__ldg(gstart + y0), __ldg(gstart + y1));     // issued before the wait below
+                    if (!done) range = make_uint2(__ldg(gstart + y0 / 4), __ldg(gstart + (y1 + 3) / 4));     // tile rows of the band; issued before the wait below
                     if (q >= kStages) mbar_wait(smem_u32(s_empty + stage), ((q >> 1) - 1) & 1);
                     s_next[stage] = 0;
                     s_band[stage] = range;
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     if (done) { mbar_arrive(bar); break; }
                     const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
                     const uint32_t *src = p.planes + p.g.row_offset(t, 0) + (long long) (y0 - S) * pitch;   // guard rows cover y0 - S < 0
-                    const uint32_t bbytes = (uint32_t) ((y1 - y0) * rowpitch) * 4u;
-                    const uint32_t *bsrc = p.occ + ((size_t) t * H + y0) * rowpitch;
+                    const uint32_t bbytes = (uint32_t) (((y1 - y0 + 3) / 4) * rowpitch) * 4u;
+                    const uint32_t *bsrc = p.occ + ((size_t) t * occupancy_tile_rows(H) + y0 / 4) * rowpitch;
                     mbar_expect_tx(bar, bytes + bbytes);
                     bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
                     bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint2 *mywq = s_wqueue + warp * kWordQueue;
     const uint32_t mywq_addr = smem_u32(mywq);
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t acc_base = smem_u32(s_acc);
+    const int *acc_base = s_acc;
     for (;;) {
         mbar_wait(smem_u32(s_full + (q & 1)), (q >> 1) & 1);
         const long long w = *reinterpret_cast<volatile long long *>(s_item + (iseq & 1));
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const int stage = q & 1;
             if (b > 0) mbar_wait(smem_u32(s_full + stage), (q >> 1) & 1);
             const uint32_t *band = s_stage + (size_t) stage * stage_stride;
-            const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - (size_t) (b * R) * rowpitch;   // indexed by the entries' absolute occupancy word index
+            const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - (size_t) (b * R / 4) * rowpitch;   // indexed by the entries' absolute occupancy word index
             const int y0 = b * R;
             const uint2 range = s_band[stage];                                   // the group's word-list entries of this band
             const int n_tickets = (int) ((range.y - range.x + kChunk - 1) / kChunk);
@@ -298,15 +299,16 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             // candidate queue, lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
             auto peel = [&](uint32_t c, uint4 e) {
                 const uint32_t wbits = e.x, lrec = e.z;
-                const uint32_t base = (((e.w >> kWordMetaYBits) & 63u) << 5) | ((e.w & ((1u << kWordMetaYBits) - 1)) << 11) |
-                                      (((e.w >> kWordMetaOrientBit) & 1u) << 21) | (e.w & (255u << kWordMetaMaskShift));
+                // position of the tile's first pixel | orientation | mask; a set bit adds (bit & 7) to x and (bit >> 3) to y
+                const uint32_t base = (((e.w >> kWordMetaColShift) & 255u) << 3) | ((e.w & 255u) << (11 + 2)) |
+                                      (((e.w >> kWordMetaOrientBit) & 1u) << 21) | (e.w & (511u << kWordMetaMaskShift));
                 unsigned bal = __ballot_sync(0xffffffffu, c != 0);
                 while (bal) {
                     if (c) {
                         const int bit = __ffs((int) c) - 1;
                         const uint32_t k = (uint32_t) __popc(wbits & ((1u << bit) - 1u));
                         uint2 cand;
-                        cand.x = base | (uint32_t) bit;
+                        cand.x = base | ((uint32_t) bit & 7u) | (((uint32_t) bit >> 3) << 11);
                         cand.y = lrec + k;
                         myq[(qt + (uint32_t) __popc(bal & lt_mask)) & (kQueue - 1)] = cand;
                         c &= c - 1;
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 // The scan reads only the first 8 bytes {bits, occupancy word index} of the 16-byte entries, three iterations
                 // ahead; lanes past the end carry an empty word on a valid address.
                 const uint4 *wl = gwords;
-                const uint2 idle = make_uint2(0u, (uint32_t) (y0 * rowpitch));
+                const uint2 idle = make_uint2(0u, (uint32_t) ((y0 / 4) * rowpitch));
                 auto load = [&](uint32_t i) -> uint2 {
                     uint2 w = idle;
                     if (i < seg1) w = __ldg(reinterpret_cast<const uint2 *>(wl + i));
@@ -398,18 +400,19 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
         }
 
         // item epilogue: max over variants per orientation; mirrored wins only when strictly greater
+        __threadfence();                    // this thread's reductions are performed before anybody reads the accumulators
         consumer_barrier<NCT>();
         for (int mi = tid; mi < mb; mi += NCT) {
             int best = 0, bestm = 0;
 #pragma unroll
-            for (int v = 0; v < NS; v++) best = max(best, s_acc[mi * NV + v]);
+            for (int v = 0; v < NS; v++) best = max(best, __ldcg(&s_acc[mi * NV + v]));
 #pragma unroll
-            for (int v = 0; v < NS; v++) bestm = max(bestm, s_acc[mi * NV + NS + v]);
+            for (int v = 0; v < NS; v++) bestm = max(bestm, __ldcg(&s_acc[mi * NV + NS + v]));
             int word = best;
             if (bestm > best) word = bestm | CDS_SCORE_MIRROR_BIT;          // no mirrored words in the lists -> bestm stays 0
             p.scores[(size_t) (m0 + mi) * p.n_targets + t] = word;
 #pragma unroll
-            for (int v = 0; v < NV; v++) s_acc[mi * NV + v] = 0;
+            for (int v = 0; v < NV; v++) __stcg(&s_acc[mi * NV + v], 0);
         }
         consumer_barrier<NCT>();
         iseq++;
@@ -425,17 +428,17 @@ struct CandConfig {
 template <int GROUP>
 CandConfig cand_config(int xy_shift, const PlaneGeom &g, int n_warps)
 {
-    const int bpitch = occupancy_pitch(g.W);
+    const int bpitch = occupancy_tile_pitch(g.W);
     CandConfig c{};
     const int S = xy_shift;
     const int NS = xy_shift == 0 ? 1 : (xy_shift == 2 ? 9 : 17);
     const size_t budget = 227 * 1024;
-    for (int R = g.H; R >= 1; R--) {
+    for (int R = (g.H + 3) / 4 * 4; R >= 4; R -= 4) {        // whole occupancy tiles per band
         int n_bands = (g.H + R - 1) / R;
         if (n_bands > kMaxBands) break;
         size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
         if (stage_words * 4 >= (1u << 20)) continue;
-        CandSmem<GROUP> L((int) stage_words, NS, R * occupancy_row_pitch(bpitch), n_warps);
+        CandSmem<GROUP> L((int) stage_words, NS, (R / 4) * occupancy_row_pitch(bpitch), n_warps);
         if (L.total <= budget) {
             c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = L.total; c.ok = true;
             return c;
@@ -446,6 +449,8 @@ CandConfig cand_config(int xy_shift, const PlaneGeom &g, int n_warps)
 }
 
 unsigned long long *g_cand_counter[64] = {nullptr};
+int *g_cand_acc[64] = {nullptr};                 // per device: [multiprocessors][CDS_PALETTE_GROUP][CDS_MAX_VARIANTS] match counters
+constexpr size_t kAccBytes = (size_t) 256 * CDS_PALETTE_GROUP * CDS_MAX_VARIANTS * sizeof(int);
 
 int env_int(const char *name, int dflt)
 {
@@ -463,6 +468,7 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     CandParams p;
     p.masks = masks; p.n_masks = n_masks; p.planes = planes; p.g = g; p.n_targets = n_targets; p.scores = scores;
     p.work_counter = g_cand_counter[dev];
+    p.acc = g_cand_acc[dev];
     p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
     p.n_groups = (n_masks + GROUP - 1) / GROUP;
     p.occ = occ; p.bpitch = bpitch; p.groups = groups;
@@ -471,7 +477,7 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     long long n_items = (long long) p.n_groups * n_targets;
-    int grid = (int) std::min<long long>(n_sm, n_items);
+    int grid = (int) std::min<long long>(std::min(n_sm, 256), n_items);
     void (*kern)(const CandParams) = nullptr;
     const int rings = xy_shift / 2;
     if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW, kChunk>;
@@ -486,63 +492,66 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
 // Word lists.  One warp per (mask, row): the row's records are scattered into two shared-memory bitmaps (unmirrored and
 // mirrored target coordinates), whose non-zero words become the entries.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kRowWords = 64;       // W <= 2048
-constexpr int kLists = 2 * CDS_NUM_SECTORS;      // (orientation, sector) bitmaps per mask row
+constexpr int kRowTiles = 256;      // W <= 2048: tile columns per tile row
+constexpr int kLists = 2 * CDS_NUM_SECTORS;      // (orientation, sector) bitmaps per mask tile row
 
-// Scatters the records of one mask row into the (orientation, sector) bitmaps.  A mask pixel goes into the list of the sector
-// of each of its non-empty rank intervals: its own sector (interval 1) and, near a sector boundary, one neighbouring sector
-// (interval 2).  `pix` (may be null) receives, per x, the pixel's palette index | own sector << 11.
-__device__ __forceinline__ void build_row_lists(const MaskDesc &md, int y, int W, bool mirror, const cds_class_interval *__restrict__ class_tab,
-                                                uint32_t (*bm)[kRowWords] /* [kLists] */, uint16_t *pix)
+// Scatters the records of one mask TILE ROW (4 image rows) into the (orientation, sector) tile bitmaps: pixel (x, y) is bit
+// (y % 4) * 8 + (x % 8) of tile word x / 8.  A mask pixel goes into the list of the sector of each of its non-empty rank
+// intervals: its own sector (interval 1) and, near a sector boundary, one neighbouring sector (interval 2).  `pix` (may be null)
+// receives, per (y % 4, x), the pixel's palette index | own sector << 11.
+__device__ __forceinline__ void build_tile_row_lists(const MaskDesc &md, int ty, int W, int H, bool mirror,
+                                                     const cds_class_interval *__restrict__ class_tab,
+                                                     uint32_t (*bm)[kRowTiles] /* [kLists] */, uint16_t *pix)
 {
     const int lane = threadIdx.x & 31;
-    for (int k = lane; k < kLists * kRowWords; k += 32) bm[0][k] = 0;
+    for (int k = lane; k < kLists * kRowTiles; k += 32) bm[0][k] = 0;
     __syncwarp();
-    const uint32_t r0 = __ldg(md.rowstart + y), r1 = __ldg(md.rowstart + y + 1);
+    const uint32_t r0 = __ldg(md.rowstart + 4 * ty), r1 = __ldg(md.rowstart + min(4 * ty + 4, H));
     for (uint32_t i = r0 + lane; i < r1; i += 32) {
         const uint32_t cls = __ldg(md.classes + i);
         if (cls >= (uint32_t) CDS_NUM_CLASSES) continue;                       // no colour sector: matches nothing
-        const int x = (int) (__ldg(&md.records[i].xy) & 0xFFFFu);
+        const uint32_t xy = __ldg(&md.records[i].xy);
+        const int x = (int) (xy & 0xFFFFu), yy = (int) (xy >> 16) & 3;
         const int xm = W - 1 - x;
         const int s1 = (int) (cls / CDS_NUM_RANKS);
         const cds_class_interval iv = class_tab[cls];
-        if (pix) pix[x] = (uint16_t) ((md.crec ? (__ldg(md.crec + i) >> 21) : 0u) | ((uint32_t) s1 << 11));
+        if (pix) pix[yy * (kRowTiles * 8) + x] = (uint16_t) ((md.crec ? (__ldg(md.crec + i) >> 21) : 0u) | ((uint32_t) s1 << 11));
+        const uint32_t bn = 1u << (yy * 8 + (x & 7)), bmr = 1u << (yy * 8 + (xm & 7));
         if (iv.lo1 != CDS_IV_EMPTY) {
-            atomicOr(&bm[s1][x >> 5], 1u << (x & 31));
-            if (mirror) atomicOr(&bm[CDS_NUM_SECTORS + s1][xm >> 5], 1u << (xm & 31));
+            atomicOr(&bm[s1][x >> 3], bn);
+            if (mirror) atomicOr(&bm[CDS_NUM_SECTORS + s1][xm >> 3], bmr);
         }
         if (iv.lo2 != CDS_IV_EMPTY) {
             const int s2 = (int) (iv.lo2 / CDS_SECTOR_STRIDE);
-            atomicOr(&bm[s2][x >> 5], 1u << (x & 31));
-            if (mirror) atomicOr(&bm[CDS_NUM_SECTORS + s2][xm >> 5], 1u << (xm & 31));
+            atomicOr(&bm[s2][x >> 3], bn);
+            if (mirror) atomicOr(&bm[CDS_NUM_SECTORS + s2][xm >> 3], bmr);
         }
     }
     __syncwarp();
 }
 
-// counts[m][y] = {word-list entries, set bits} of (mask m, row y)
-__global__ void __launch_bounds__(128) words_count_kernel(const MaskDesc *__restrict__ masks, int W, int H, bool mirror,
-                                                          const cds_class_interval *__restrict__ class_tab,
-                                                          uint32_t *__restrict__ wcount, uint32_t *__restrict__ bcount)
+// counts[m][ty] = {word-list entries, set bits} of (mask m, tile row ty); one warp per (mask, tile row)
+__global__ void __launch_bounds__(32) words_count_kernel(const MaskDesc *__restrict__ masks, int W, int H, bool mirror,
+                                                         const cds_class_interval *__restrict__ class_tab,
+                                                         uint32_t *__restrict__ wcount, uint32_t *__restrict__ bcount)
 {
-    __shared__ uint32_t s_bm[4][kLists][kRowWords];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int y = blockIdx.x * 4 + warp;
+    __shared__ uint32_t s_bm[kLists][kRowTiles];
+    const int lane = threadIdx.x;
+    const int ty = blockIdx.x, HT = gridDim.x;
     const int m = blockIdx.y;
-    if (y >= H) return;
     const MaskDesc md = masks[m];
-    build_row_lists(md, y, W, mirror, class_tab, s_bm[warp], nullptr);
+    build_tile_row_lists(md, ty, W, H, mirror, class_tab, s_bm, nullptr);
     int nw = 0, nb = 0;
-    for (int k = lane; k < kLists * kRowWords; k += 32) {
-        const uint32_t wbits = s_bm[warp][0][k];
+    for (int k = lane; k < kLists * kRowTiles; k += 32) {
+        const uint32_t wbits = s_bm[0][k];
         nw += wbits != 0;
         nb += __popc(wbits);
     }
     nw = __reduce_add_sync(0xffffffffu, nw);
     nb = __reduce_add_sync(0xffffffffu, nb);
     if (lane == 0) {
-        wcount[(size_t) m * (H + 1) + y] = (uint32_t) nw;
-        bcount[(size_t) m * (H + 1) + y] = (uint32_t) nb;
+        wcount[(size_t) m * (HT + 1) + ty] = (uint32_t) nw;
+        bcount[(size_t) m * (HT + 1) + ty] = (uint32_t) nb;
     }
 }
 
@@ -565,32 +574,32 @@ __global__ void __launch_bounds__(128) words_group_rows_kernel(uint32_t *__restr
     grow[(size_t) g * (H + 1) + y] = acc;
 }
 
-__global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restrict__ masks, int first_mask, int W, int H, bool mirror,
-                                                         const cds_class_interval *__restrict__ class_tab,
-                                                         const uint32_t *__restrict__ gstart /* [n_groups][H+1] entries */,
-                                                         const uint32_t *__restrict__ bstart /* [n_groups][H+1] bits */,
-                                                         const uint32_t *__restrict__ boff /* [M][H+1] */,
-                                                         uint4 *__restrict__ words, uint16_t *__restrict__ lpal)
+__global__ void __launch_bounds__(32) words_fill_kernel(const MaskDesc *__restrict__ masks, int first_mask, int W, int H, bool mirror,
+                                                        const cds_class_interval *__restrict__ class_tab,
+                                                        const uint32_t *__restrict__ gstart /* [n_groups][HT+1] entries */,
+                                                        const uint32_t *__restrict__ bstart /* [n_groups][HT+1] bits */,
+                                                        const uint32_t *__restrict__ boff /* [M][HT+1] */,
+                                                        uint4 *__restrict__ words, uint16_t *__restrict__ lpal)
 {
-    __shared__ uint32_t s_bm[4][kLists][kRowWords];
-    __shared__ uint16_t s_pix[4][kRowWords * 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int y = blockIdx.x * 4 + warp;
+    __shared__ uint32_t s_bm[kLists][kRowTiles];
+    __shared__ uint16_t s_pix[4 * kRowTiles * 8];
+    const int lane = threadIdx.x;
+    const int ty = blockIdx.x, HT = gridDim.x;
     const int m = first_mask + blockIdx.y;
-    if (y >= H) return;
     const MaskDesc md = masks[blockIdx.y];
-    build_row_lists(md, y, W, mirror, class_tab, s_bm[warp], s_pix[warp]);
+    build_tile_row_lists(md, ty, W, H, mirror, class_tab, s_bm, s_pix);
     const int g = m / CDS_PALETTE_GROUP;
     const uint32_t mtag = (uint32_t) (m % CDS_PALETTE_GROUP) << kWordMetaMaskShift;
-    uint32_t out_w = __ldg(gstart + (size_t) g * (H + 1) + y) + __ldg(md.wstart + y);       // start of the row's run + this mask's offset in it
-    uint32_t out_b = __ldg(bstart + (size_t) g * (H + 1) + y) + __ldg(boff + (size_t) m * (H + 1) + y);
+    uint32_t out_w = __ldg(gstart + (size_t) g * (HT + 1) + ty) + __ldg(md.wstart + ty);       // start of the tile row's run + this mask's offset in it
+    uint32_t out_b = __ldg(bstart + (size_t) g * (HT + 1) + ty) + __ldg(boff + (size_t) m * (HT + 1) + ty);
     const uint32_t lt = (1u << lane) - 1u;
-    const int bp = occupancy_pitch(W);
+    const int tp = occupancy_tile_pitch(W);
+    const int n_tiles = (W + 7) / 8;
     for (int list = 0; list < (mirror ? kLists : CDS_NUM_SECTORS); list++) {
         const int o = list / CDS_NUM_SECTORS, sec = list % CDS_NUM_SECTORS;
-        for (int k0 = 0; k0 < kRowWords; k0 += 32) {
+        for (int k0 = 0; k0 < n_tiles; k0 += 32) {
             const int k = k0 + lane;
-            uint32_t wbits = s_bm[warp][list][k];
+            uint32_t wbits = k < kRowTiles ? s_bm[list][k] : 0u;
             const unsigned bal = __ballot_sync(0xffffffffu, wbits != 0);
             if (bal == 0) continue;
             const uint32_t pc = (uint32_t) __popc(wbits);
@@ -603,15 +612,15 @@ __global__ void __launch_bounds__(128) words_fill_kernel(const MaskDesc *__restr
             if (wbits) {
                 const uint32_t pos = out_w + (uint32_t) __popc(bal & lt);
                 uint32_t lrec = out_b + incl - pc;
-                words[pos] = make_uint4(wbits, (uint32_t) ((y * occupancy_row_pitch(bp)) + sec * bp + k), lrec,
-                                        (uint32_t) y | ((uint32_t) k << kWordMetaYBits) | ((uint32_t) o << kWordMetaOrientBit) |
+                words[pos] = make_uint4(wbits, (uint32_t) (ty * occupancy_row_pitch(tp) + sec * tp + k), lrec,
+                                        (uint32_t) ty | ((uint32_t) k << kWordMetaColShift) | ((uint32_t) o << kWordMetaOrientBit) |
                                             ((uint32_t) sec << kWordMetaSectorShift) | mtag);
                 // palette references of the word's pixels, in bit order: index | (interval 2 ? 0x8000 : 0)
                 while (wbits) {
                     const int bit = __ffs((int) wbits) - 1;
                     wbits &= wbits - 1;
-                    const int xt = k * 32 + bit;
-                    const uint32_t pv = s_pix[warp][o ? W - 1 - xt : xt];
+                    const int xt = k * 8 + (bit & 7);
+                    const uint32_t pv = s_pix[(bit >> 3) * (kRowTiles * 8) + (o ? W - 1 - xt : xt)];
                     lpal[lrec++] = (uint16_t) ((pv & 0x7FFu) | (((pv >> 11) & 7u) != (uint32_t) sec ? 0x8000u : 0u));
                 }
             }
@@ -638,8 +647,9 @@ void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool m
 {
     for (int m0 = 0; m0 < n_masks; m0 += 32768) {
         int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
-        dim3 grid((H + 3) / 4, cnt);
-        words_count_kernel<<<grid, 128, 0, s>>>(masks + m0, W, H, mirror, class_tab, wcount + (size_t) m0 * (H + 1), bcount + (size_t) m0 * (H + 1));
+        const int HT = occupancy_tile_rows(H);
+        dim3 grid(HT, cnt);
+        words_count_kernel<<<grid, 32, 0, s>>>(masks + m0, W, H, mirror, class_tab, wcount + (size_t) m0 * (HT + 1), bcount + (size_t) m0 * (HT + 1));
     }
 }
 
@@ -656,8 +666,8 @@ void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mi
 {
     for (int m0 = 0; m0 < n_masks; m0 += 32768) {
         int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
-        dim3 grid((H + 3) / 4, cnt);
-        words_fill_kernel<<<grid, 128, 0, s>>>(masks + m0, m0, W, H, mirror, class_tab, gstart, bstart, boff, words, lpal);
+        dim3 grid(occupancy_tile_rows(H), cnt);
+        words_fill_kernel<<<grid, 32, 0, s>>>(masks + m0, m0, W, H, mirror, class_tab, gstart, bstart, boff, words, lpal);
     }
 }
 
@@ -667,14 +677,18 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
 {
     (void) mirror;      // the word lists already say which orientations exist
     if (n_masks == 0 || n_targets == 0) return 0;
-    if (!occ || !groups || bpitch != occupancy_pitch(g.W)) return 0;
+    if (!occ || !groups || bpitch != occupancy_tile_pitch(g.W)) return 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 64) return 0;
     if (!g_cand_counter[dev]) {
         if (cudaMalloc(&g_cand_counter[dev], sizeof(unsigned long long)) != cudaSuccess) return 0;
     }
+    if (!g_cand_acc[dev]) {
+        if (cudaMalloc(&g_cand_acc[dev], kAccBytes) != cudaSuccess) return 0;
+    }
     cudaMemsetAsync(g_cand_counter[dev], 0, sizeof(unsigned long long), s);
+    cudaMemsetAsync(g_cand_acc[dev], 0, kAccBytes, s);
     // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket.  More warps need more
     // shared memory for their queues; when the band stages no longer fit (xyShift 4: 34 accumulators per mask) fewer are used.
     static const int warps_env = env_int("CDSGPU_CAND_WARPS", 31);

@@ -9,21 +9,22 @@ namespace cds {
 // WORD LISTS of a mask group (built once per mask set, per device).
 // A mask pixel can only match target pixels whose colour sector is the sector of one of its (at most two) rank intervals: its
 // own sector (interval 1) and, near a sector boundary, one neighbouring sector (interval 2).  Per mask, orientation and
-// sector the kernel keeps a bitmap in TARGET coordinates (orientation 0: bit x of row y for a mask pixel (x, y); orientation 1,
-// only when the mask set mirrors: bit W-1-x) holding the pixels with an interval in that sector, stored as its non-zero 32-bit
-// words.  The words of the CDS_PALETTE_GROUP masks of a group form ONE list ordered by image row (then mask, orientation,
-// sector, column) with a row-start table gstart[H+1], so the entries that concern a band of rows are one contiguous range that
-// is cut into equal tickets regardless of mask boundaries.  One 16-byte entry per word:
-//     bits : the word
-//     occ  : index of the matching occupancy word inside a target's bitmaps: y * occupancy_row_pitch + sector * pitch + column
+// sector the kernel keeps a bitmap in TARGET coordinates (orientation 0: pixel (x, y); orientation 1, only when the mask set
+// mirrors: pixel (W-1-x, y)) of the pixels with an interval in that sector, cut into TILES of 8 x 4 pixels like the library's
+// occupancy bitmaps (bit (y % 4) * 8 + (x % 8) of tile (y / 4, x / 8)) and stored as its non-zero 32-bit tile words.  The
+// words of the CDS_PALETTE_GROUP masks of a group form ONE list ordered by tile row (then mask, orientation, sector, tile
+// column) with a row-start table gstart[tile rows + 1], so the entries that concern a band of image rows are one contiguous
+// range that is cut into equal tickets regardless of mask boundaries.  One 16-byte entry per word:
+//     bits : the tile word
+//     occ  : index of the matching occupancy word inside a target's bitmaps: tile row * occupancy_row_pitch + sector * pitch + tile column
 //     lrec : index into the group's `lpal` array of the palette reference of the word's LOWEST set bit; set bit b has
 //            lpal[lrec + popc(bits below b)] = palette index | 0x8000 when the pixel is in this list through its interval 2
-//     meta : y | word column << 10 | orientation << 16 | sector << 17 | mask index inside the group << 22 (8 bits)   (H <= 1024, W <= 2048)
+//     meta : tile row | tile column << 8 | orientation << 16 | sector << 17 | mask index inside the group << 22 (8 bits)   (H <= 1024, W <= 2048)
 // The scan touches only {bits, occ}; the second half is read for the words that have candidates.
-// ANDing `bits` with the library's occupancy word of the same (row, sector, column) leaves exactly the mask pixels that can
-// match in some shifted variant of that orientation -- 32 pixels per instruction -- and an evaluation tests ONE interval: the
-// two lists of a boundary pixel partition its matches by target sector, so nothing is counted twice.
-constexpr int kWordMetaYBits = 10;
+// ANDing `bits` with the library's occupancy word of the same (tile row, sector, tile column) leaves exactly the mask pixels
+// that can match in some shifted variant of that orientation -- 32 pixels per instruction -- and an evaluation tests ONE
+// interval: the two lists of a boundary pixel partition its matches by target sector, so nothing is counted twice.
+constexpr int kWordMetaColShift = 8;
 constexpr int kWordMetaOrientBit = 16;
 constexpr int kWordMetaSectorShift = 17;
 constexpr int kWordMetaMaskShift = 22;
@@ -31,8 +32,8 @@ constexpr int kWordMetaMaskShift = 22;
 bool cand_kernel_supported(int xy_shift, const PlaneGeom &g);
 
 // Construction, in this order (class_tab: the device interval table of the mask set's zTolerance):
-//   launch_words_count      wcount[m][y] / bcount[m][y] = entries / set bits of (mask m, row y)   (masks[m].records, classes, rowstart)
-//   launch_words_group_rows (once per array) count[m][y] -> offset of mask m inside its group's run of row y; grow[g][y] = run length
+//   launch_words_count      wcount[m][ty] / bcount[m][ty] = entries / set bits of (mask m, tile row ty); arrays are [.][tile rows + 1]
+//   launch_words_group_rows (once per array, H = tile rows) count[m][ty] -> offset of mask m inside its group's run; grow[g][ty] = run length
 //   (host) gstart / bstart = exclusive scans of the two grow arrays over (group, row), absolute indices; [g][H] = end of the group
 //   launch_words_fill       writes entries and palette references; masks[m].wstart must point at wcount[m], boff at bcount
 void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,

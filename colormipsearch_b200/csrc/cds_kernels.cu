@@ -133,16 +133,15 @@ void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_ta
 // threshold, in this sector"; pass 2: OR of the bits at the shift offsets, 32 pixels at a time with word shifts, plus the
 // OR over the sectors in slot CDS_NUM_SECTORS.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restrict__ planes, PlaneGeom g, int64_t t0, int bp,
-                                                         uint32_t *__restrict__ valid /* chunk-relative */)
+__global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restrict__ planes, PlaneGeom g, int64_t t0, int vp,
+                                                         uint32_t *__restrict__ valid /* chunk-relative [n][H][sectors][vp] */)
 {
     const int y = blockIdx.x;
     const int64_t t = t0 + blockIdx.y;
-    const int rowpitch = occupancy_row_pitch(bp);
     const uint32_t *row = planes + g.row_offset(t, y);
-    uint32_t *out = valid + ((size_t) blockIdx.y * g.H + y) * rowpitch;
+    uint32_t *out = valid + ((size_t) blockIdx.y * g.H + y) * CDS_NUM_SECTORS * vp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < bp; k += (int) (blockDim.x >> 5)) {
+    for (int k = warp; k < vp; k += (int) (blockDim.x >> 5)) {
         const int x = k * 32 + lane;
         int sector = -1;
         if (x < g.W) {
@@ -155,62 +154,71 @@ __global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restr
 #pragma unroll
         for (int s = 0; s < CDS_NUM_SECTORS; s++) {
             const unsigned bal = __ballot_sync(0xffffffffu, sector == s);
-            if (lane == 0) out[s * bp + k] = bal;
+            if (lane == 0) out[s * vp + k] = bal;
         }
     }
 }
 
-__device__ __forceinline__ uint32_t hspread(const uint32_t *__restrict__ vrow, int k, int bp, int s)
+__device__ __forceinline__ uint32_t hspread(const uint32_t *__restrict__ vrow, int k, int vp, int s)
 {
     // bit x of the result = valid(x - s) | valid(x) | valid(x + s)
     const uint32_t c = vrow[k];
     const uint32_t l = k > 0 ? vrow[k - 1] : 0u;
-    const uint32_t r = k + 1 < bp ? vrow[k + 1] : 0u;
+    const uint32_t r = k + 1 < vp ? vrow[k + 1] : 0u;
     return c | (c << s) | (l >> (32 - s)) | (c >> s) | (r << (32 - s));
 }
 
-__global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restrict__ valid /* chunk-relative */, int H, int bp, int64_t t0, int64_t n,
-                                                        int rings, uint32_t *__restrict__ occ)
+// One thread per 32-pixel strip of one image row: the dilated bits of every sector, scattered as bytes into the 8 x 4 tiles.
+__global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restrict__ valid /* chunk-relative */, int H, int vp, int tp,
+                                                        int64_t t0, int64_t n, int rings, uint32_t *__restrict__ occ)
 {
-    const int rowpitch = occupancy_row_pitch(bp);
-    const size_t total = (size_t) n * H * bp;
+    const int rowpitch = occupancy_row_pitch(tp);
+    const int HT = occupancy_tile_rows(H);
+    const int vrow_words = CDS_NUM_SECTORS * vp;
+    const size_t total = (size_t) n * H * vp;
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
-        const int k = (int) (i % bp);
-        const int y = (int) ((i / bp) % H);
-        const int64_t tl = (int64_t) (i / ((size_t) bp * H));
-        const uint32_t *vimg = valid + (size_t) tl * H * rowpitch;
-        uint32_t *orow = occ + ((size_t) (t0 + tl) * H + y) * rowpitch;
+        const int k = (int) (i % vp);
+        const int y = (int) ((i / vp) % H);
+        const int64_t tl = (int64_t) (i / ((size_t) vp * H));
+        const uint32_t *vimg = valid + (size_t) tl * H * vrow_words;
+        uint8_t *orow = reinterpret_cast<uint8_t *>(occ + ((size_t) (t0 + tl) * HT + (y >> 2)) * rowpitch) + (y & 3);
         uint32_t any = 0;
 #pragma unroll
-        for (int s = 0; s < CDS_NUM_SECTORS; s++) {
+        for (int s = 0; s <= CDS_NUM_SECTORS; s++) {
             uint32_t o;
-            if (rings == 0) {
-                o = vimg[(size_t) y * rowpitch + s * bp + k];
+            if (s == CDS_NUM_SECTORS) {
+                o = any;
+            } else if (rings == 0) {
+                o = vimg[(size_t) y * vrow_words + s * vp + k];
             } else {
                 o = 0;
                 for (int dy = -2; dy <= 2; dy += 2)
-                    if (y + dy >= 0 && y + dy < H) o |= hspread(vimg + (size_t) (y + dy) * rowpitch + s * bp, k, bp, 2);
+                    if (y + dy >= 0 && y + dy < H) o |= hspread(vimg + (size_t) (y + dy) * vrow_words + s * vp, k, vp, 2);
                 if (rings >= 2)
                     for (int dy = -4; dy <= 4; dy += 4)
-                        if (y + dy >= 0 && y + dy < H) o |= hspread(vimg + (size_t) (y + dy) * rowpitch + s * bp, k, bp, 4);
+                        if (y + dy >= 0 && y + dy < H) o |= hspread(vimg + (size_t) (y + dy) * vrow_words + s * vp, k, vp, 4);
             }
-            orow[s * bp + k] = o;
             any |= o;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int tx = 4 * k + j;
+                if (tx < tp) orow[((size_t) s * tp + tx) * 4] = (uint8_t) (o >> (8 * j));
+            }
         }
-        orow[CDS_NUM_SECTORS * bp + k] = any;
     }
 }
 
-void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int bp,
+void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int tp,
                       uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s)
 {
     if (n == 0) return;
+    const int vp = occupancy_valid_pitch(g.W);
     if (scratch_targets > 32768) scratch_targets = 32768;      // gridDim.y
     for (int64_t i0 = 0; i0 < n; i0 += scratch_targets) {
         const int64_t cnt = n - i0 < scratch_targets ? n - i0 : scratch_targets;
         dim3 grid(g.H, (unsigned) cnt);
-        valid_bits_kernel<<<grid, 256, 0, s>>>(planes, g, t0 + i0, bp, valid_scratch);
-        occupancy_kernel<<<148 * 8, 256, 0, s>>>(valid_scratch, g.H, bp, t0 + i0, cnt, rings, occ);
+        valid_bits_kernel<<<grid, 256, 0, s>>>(planes, g, t0 + i0, vp, valid_scratch);
+        occupancy_kernel<<<148 * 8, 256, 0, s>>>(valid_scratch, g.H, vp, tp, t0 + i0, cnt, rings, occ);
     }
 }
 

@@ -62,16 +62,22 @@ void launch_encode_rgb(const uint8_t *rgb, int64_t n, uint32_t *planes, PlaneGeo
 void launch_rebake(uint32_t *planes, size_t n_words, int data_threshold, cudaStream_t s);
 void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_tab, int data_threshold, uint32_t *codes, cudaStream_t s);
 
-// Occupancy bitmaps of the library.  Per target and image row there are CDS_NUM_SECTORS + 1 bit rows of `bp` 32-bit words
-// each (row pitch occupancy_row_pitch(bp)): bit (x, y) of sector row s is set when at least one of the pixels (x + dx, y + dy),
-// (dx, dy) in the shift set of `rings` (0: centre only, 1: {-2,0,2}^2, 2: additionally {-4,0,4}^2), is inside the image, above
-// the baked threshold and of colour sector s; the last bit row is the OR of the sector rows.  A mask pixel can only match
-// target pixels of the sector of one of its (at most two) rank intervals, so a clear bit in that sector's row means "cannot
-// match in any shifted variant"; the shift set being symmetric, the bit of the mirrored position covers the mirrored variants.
-// `valid_scratch` holds scratch_targets * H * occupancy_row_pitch(bp) words.
-__host__ __device__ inline int occupancy_pitch(int W) { return (((W + 31) / 32) + 3) / 4 * 4; }
-__host__ __device__ inline int occupancy_row_pitch(int bp) { return (CDS_NUM_SECTORS + 1) * bp; }
-void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int bp,
+// Occupancy bitmaps of the library, in TILES of 8 x 4 pixels: bit (y % 4) * 8 + (x % 8) of tile word (y / 4, x / 8).  Per target
+// and tile row there are CDS_NUM_SECTORS + 1 rows of `tp` tile words each (occupancy_row_pitch(tp) words per tile row): bit (x, y)
+// of sector row s is set when at least one of the pixels (x + dx, y + dy), (dx, dy) in the shift set of `rings` (0: centre only,
+// 1: {-2,0,2}^2, 2: additionally {-4,0,4}^2), is inside the image, above the baked threshold and of colour sector s; the last
+// row is the OR of the sector rows.  A mask pixel can only match target pixels of the sector of one of its (at most two) rank
+// intervals, so a clear bit in that sector's row means "cannot match in any shifted variant"; the shift set being symmetric, the
+// bit of the mirrored position covers the mirrored variants.  (Tiles rather than 32 x 1 strips because a neurite a few pixels
+// wide fills a compact tile much better than a strip: 1.8 x fewer non-empty mask words to scan, cds_cand.cuh.)
+// The bitmaps must be zero before the first launch_occupancy (bytes of rows beyond the image are never written).
+// `valid_scratch` holds scratch_targets * H * CDS_NUM_SECTORS * occupancy_valid_pitch(W) words (row layout, one bit per pixel).
+__host__ __device__ inline int occupancy_valid_pitch(int W) { return (((W + 31) / 32) + 3) / 4 * 4; }
+__host__ __device__ inline int occupancy_tile_pitch(int W) { return (((W + 7) / 8) + 3) / 4 * 4; }
+__host__ __device__ inline int occupancy_tile_rows(int H) { return (H + 3) / 4; }
+__host__ __device__ inline int occupancy_row_pitch(int tp) { return (CDS_NUM_SECTORS + 1) * tp; }
+__host__ __device__ inline size_t occupancy_target_words(int W, int H) { return (size_t) occupancy_tile_rows(H) * occupancy_row_pitch(occupancy_tile_pitch(W)); }
+void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int tp,
                       uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s);
 
 void launch_mask_count_rows(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,

@@ -98,7 +98,7 @@ struct cds_library {
     struct Shard {
         uint32_t *planes = nullptr;
         int64_t cap_local = 0;
-        uint32_t *occ = nullptr;        // occupancy bitmap [cap_local][H][bpitch] (cds_kernels.cuh), built on demand
+        uint32_t *occ = nullptr;        // occupancy bitmaps [cap_local][tile rows][sectors + 1][bpitch] (cds_kernels.cuh), built on demand
         uint32_t *valid = nullptr;      // its scratch
         int64_t occ_done = 0;           // local targets covered by `occ`
     };

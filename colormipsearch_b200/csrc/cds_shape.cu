@@ -413,7 +413,7 @@ extern "C" cds_status cds_shape_maskset_create(cds_ctx *ctx, int32_t width, int3
     if (width > 2048 || height > 1024) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_shape_maskset_create: images larger than 2048 x 1024 are not supported");
     if (border != 0) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_shape_maskset_create: only border = 0 is supported");
     auto sms = new cds_shape_maskset();
-    sms->ctx = ctx; sms->W = width; sms->H = height; sms->bpitch = occupancy_pitch(width);
+    sms->ctx = ctx; sms->W = width; sms->H = height; sms->bpitch = occupancy_valid_pitch(width);   // row-layout bitmaps: one bit per pixel, 32-pixel words
     sms->query_threshold = query_threshold; sms->mirror = mirror ? 1 : 0;
     sms->rects = to_rectset(rects, n_rects);
     DevState &d0 = ctx->devs[0];

@@ -65,10 +65,12 @@ cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, in
         if (sb.scores) { cudaFree(sb.scores); sb.scores = nullptr; }
         sb.chunk = 0; sb.m_cap = 0;
         const size_t words = g.total_words(chunk);
-        const size_t bm_words = (size_t) chunk * g.H * occupancy_row_pitch(bpitch);
-        (void) words;
+        const size_t bm_words = (size_t) chunk * occupancy_target_words(g.W, g.H);
+        const size_t valid_words = (size_t) chunk * g.H * CDS_NUM_SECTORS * occupancy_valid_pitch(g.W);
+        (void) words; (void) bpitch;
         CDS_CUDA(ctx, cudaMalloc(&sb.occ, bm_words * sizeof(uint32_t)));
-        CDS_CUDA(ctx, cudaMalloc(&sb.valid, bm_words * sizeof(uint32_t)));
+        CDS_CUDA(ctx, cudaMalloc(&sb.valid, valid_words * sizeof(uint32_t)));
+        CDS_CUDA(ctx, cudaMemsetAsync(sb.occ, 0, bm_words * sizeof(uint32_t), ds.stream));      // rows beyond the image stay clear
         sb.W = g.W; sb.H = g.H; sb.chunk = chunk;
     }
     if (upload && !sb.planes) {
@@ -146,7 +148,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     const int D = (int) ctx->devs.size();
     PlaneGeom g;
     g.W = ms->W; g.H = ms->H; g.pitch = choose_pitch(ms->W); g.guard = CDS_GUARD_ROWS;
-    const int bpitch = occupancy_pitch(g.W);
+    const int bpitch = occupancy_tile_pitch(g.W);
     const size_t img_bytes = (size_t) g.W * g.H * 3;
     if (resident) {
         if (resident->ctx != ctx) return ctx->fail(CDS_ERR_BAD_ARG, "library belongs to another context");
