@@ -458,7 +458,7 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": {1: "pixelmatch_cand_kernel<1,512,31,256>", 2: "pixelmatch_band_kernel<1,true,128,24>", 3: "pixelmatch_gather_kernel"}.get(kernel_used, "?"),
+                         "kernel": {1: "pixelmatch_cand_kernel<1,1024,31,256>", 2: "pixelmatch_band_kernel<1,true,128,24>", 3: "pixelmatch_gather_kernel"}.get(kernel_used, "?"),
                          "algorithmic_bytes_per_comparison": ALGO_BYTES_PER_COMPARISON,
                          "comparisons_per_launch": per_launch_cmp, "avg_launch_ms": avg_launch_s * 1e3,
                          "note": "algorithmic bytes = 3*W*H per comparison (SURVEY 8d); a mask group shares one pass over the "

@@ -142,7 +142,7 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const u
 {
     constexpr int NS = Offsets<NRINGS>::N;
     constexpr int S = 2 * NRINGS;
-    const uint32_t mi = (cand.x >> 22) & 511u;
+    const uint32_t mi = cand.x >> 22;
     const uint2 pe = s_pal[pr & (CDS_PALETTE_SIZE - 1)];
     const uint32_t iv = (pr & 0x8000u) ? pe.y : pe.x;                           // the interval that lives in this candidate's sector
     const uint32_t lo = (iv & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 const uint32_t wbits = e.x, lrec = e.z;
                 // position of the tile's first pixel | orientation | mask; a set bit adds (bit & 7) to x and (bit >> 3) to y
                 const uint32_t base = (((e.w >> kWordMetaColShift) & 255u) << 3) | ((e.w & 255u) << (11 + 2)) |
-                                      (((e.w >> kWordMetaOrientBit) & 1u) << 21) | (e.w & (511u << kWordMetaMaskShift));
+                                      (((e.w >> kWordMetaOrientBit) & 1u) << 21) | (e.w & (1023u << kWordMetaMaskShift));
                 unsigned bal = __ballot_sync(0xffffffffu, c != 0);
                 while (bal) {
                     if (c) {

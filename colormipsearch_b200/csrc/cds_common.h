@@ -61,7 +61,7 @@ struct cds_class_interval {
 //     palette = { lo1 | len1 << 18 , lo2 | len2 << 18 }         SR units, 18 + 14 bits; empty interval: lo = CDS_PAL_EMPTY_LO
 // Groups that do not fit (more classes, larger images, tolerances so wide that an interval spans >= 16384 ranks) use the
 // 16-byte records above.
-#define CDS_PALETTE_GROUP 512
+#define CDS_PALETTE_GROUP 1024
 #define CDS_PALETTE_SIZE 2048
 #define CDS_PAL_LO_BITS 18
 #define CDS_PAL_EMPTY_LO 0x3FFFFu     // an SR no code word has (> CDS_SR_NONE)
