@@ -116,6 +116,15 @@ cds_status cds_ctx::ensure_scratch(DevState &d, int slot, size_t bytes, void **o
     return CDS_OK;
 }
 
+cds_status cds_ctx::ensure_match_scratch(DevState &d)
+{
+    if (d.match_scratch.work_counter && d.match_scratch.acc) return CDS_OK;
+    CDS_CUDA(this, cudaSetDevice(d.dev));
+    if (!d.match_scratch.work_counter) CDS_CUDA(this, cudaMalloc(&d.match_scratch.work_counter, sizeof(unsigned long long)));
+    if (!d.match_scratch.acc) CDS_CUDA(this, cudaMalloc(&d.match_scratch.acc, kMatchAccBytes));
+    return CDS_OK;
+}
+
 cds_status cds_ctx::class_table_on(DevState &d, double tol, const cds_class_interval **out)
 {
     uint64_t key;
@@ -220,6 +229,8 @@ extern "C" void cds_ctx_destroy(cds_ctx *ctx)
         for (int i = 0; i < 4; i++) if (d.scratch[i]) cudaFree(d.scratch[i]);
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
         if (d.pair_plane) cudaFree(d.pair_plane);
+        if (d.match_scratch.work_counter) cudaFree(d.match_scratch.work_counter);
+        if (d.match_scratch.acc) cudaFree(d.match_scratch.acc);
         d.pool.release_all();
         d.sb.release();
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -880,18 +891,20 @@ cds_status launch_match_view(cds_ctx *ctx, const cds_maskset *ms, const TargetVi
     const bool batched_ok = mc >= band_min_masks() && tv.occ_ready && (m0 % CDS_PALETTE_GROUP) == 0;
     const bool cand_ok = batched_ok && (choice == 0 || choice == 1) && ms->d_words[d] && ms->words_built && cand_kernel_supported(ms->params.xy_shift, tv.g);
     const bool band_ok = batched_ok && choice != 3 && band_kernel_supported(ms->params.xy_shift, tv.g);
+    if (cand_ok || band_ok) CDS_TRY(ctx->ensure_match_scratch(ctx->devs[d]));
+    const MatchScratch &scratch = ctx->devs[d].match_scratch;
     if (ev0) cudaEventRecord(ev0, stream);
     if (cand_ok) {
         int launches = launch_pixelmatch_cand(ms->d_descs[d] + m0, mc, tv.planes, tv.g, tv.n, tv.occ, tv.bpitch,
                                               ms->d_groups[d] + m0 / CDS_PALETTE_GROUP, ms->params.xy_shift, ms->params.mirror != 0,
-                                              d_scores, stream);
+                                              d_scores, scratch, stream);
         ctx->stats.kernel_launches += launches;
         ctx->stats.match_kernel_launches += launches;
         ctx->stats.match_kernel = 1;
     } else if (band_ok) {
         int launches = launch_pixelmatch_band(ms->d_descs[d] + m0, mc, tv.planes, tv.g, tv.n, tv.occ, tv.bpitch,
                                               ms->d_groups[d] + m0 / CDS_PALETTE_GROUP, ms->params.xy_shift, ms->params.mirror != 0,
-                                              d_scores, stream);
+                                              d_scores, scratch, stream);
         ctx->stats.kernel_launches += launches;
         ctx->stats.match_kernel_launches += launches;
         ctx->stats.match_kernel = 2;

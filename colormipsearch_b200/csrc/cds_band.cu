@@ -415,7 +415,6 @@ BandConfig band_config(int xy_shift, bool mirror, const PlaneGeom &g)
     return c;
 }
 
-unsigned long long *g_work_counter[64] = {nullptr};
 
 int env_int(const char *name, int dflt)
 {
@@ -426,13 +425,13 @@ int env_int(const char *name, int dflt)
 template <int GROUP, int NCW>
 int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror, int32_t *scores,
-               cudaStream_t s, int dev)
+               const MatchScratch &scratch, cudaStream_t s, int dev)
 {
     BandConfig c = band_config<GROUP>(xy_shift, mirror, g);
     if (!c.ok) return 0;
     BandParams p;
     p.masks = masks; p.n_masks = n_masks; p.planes = planes; p.g = g; p.n_targets = n_targets; p.scores = scores;
-    p.work_counter = g_work_counter[dev];
+    p.work_counter = scratch.work_counter;
     p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
     p.n_groups = (n_masks + GROUP - 1) / GROUP;
     p.occ = occ; p.bpitch = bpitch; p.groups = groups;
@@ -469,27 +468,24 @@ int band_min_masks()
 
 int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                            const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror, int32_t *scores,
-                           cudaStream_t s)
+                           const MatchScratch &scratch, cudaStream_t s)
 {
     if (n_masks == 0 || n_targets == 0) return 0;
     if (!occ || !groups || bpitch != occupancy_tile_pitch(g.W)) return 0;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 64) return 0;
-    if (!g_work_counter[dev]) {
-        if (cudaMalloc(&g_work_counter[dev], sizeof(unsigned long long)) != cudaSuccess) return 0;
-    }
-    cudaMemsetAsync(g_work_counter[dev], 0, sizeof(unsigned long long), s);
+    if (!scratch.work_counter) return 0;
+    cudaMemsetAsync(scratch.work_counter, 0, sizeof(unsigned long long), s);
     // tuning knobs (defaults picked from profiles/): masks per work item, consumer warps per CTA
     static const int group_env = env_int("CDSGPU_BAND_GROUP", 0);
     static const int warps_env = env_int("CDSGPU_BAND_WARPS", 24);
     const int group = group_env ? group_env : (n_masks > 96 ? 128 : 64);
     if (group == 128) {
-        if (warps_env == 24) return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, s, dev);
-        return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, s, dev);
+        if (warps_env == 24) return launch_cfg<128, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, scratch, s, dev);
+        return launch_cfg<128, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, scratch, s, dev);
     }
-    if (warps_env == 24) return launch_cfg<64, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, s, dev);
-    return launch_cfg<64, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, s, dev);
+    if (warps_env == 24) return launch_cfg<64, 24>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, scratch, s, dev);
+    return launch_cfg<64, 16>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, mirror, scores, scratch, s, dev);
 }
 
 }  // namespace cds

@@ -19,7 +19,7 @@ int band_min_masks();
 // that group's descriptor.
 int launch_pixelmatch_band(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                            const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror,
-                           int32_t *scores, cudaStream_t s);
+                           int32_t *scores, const MatchScratch &scratch, cudaStream_t s);
 
 }  // namespace cds
 #endif

@@ -448,9 +448,6 @@ CandConfig cand_config(int xy_shift, const PlaneGeom &g, int n_warps)
     return c;
 }
 
-unsigned long long *g_cand_counter[64] = {nullptr};
-int *g_cand_acc[64] = {nullptr};                 // per device: [multiprocessors][CDS_PALETTE_GROUP][CDS_MAX_VARIANTS] match counters
-constexpr size_t kAccBytes = (size_t) 256 * CDS_PALETTE_GROUP * CDS_MAX_VARIANTS * sizeof(int);
 
 int env_int(const char *name, int dflt)
 {
@@ -461,14 +458,14 @@ int env_int(const char *name, int dflt)
 template <int GROUP, int NCW, int kChunk>
 int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, int32_t *scores,
-               cudaStream_t s, int dev)
+               const MatchScratch &scratch, cudaStream_t s, int dev)
 {
     CandConfig c = cand_config<GROUP>(xy_shift, g, NCW);
     if (!c.ok) return 0;
     CandParams p;
     p.masks = masks; p.n_masks = n_masks; p.planes = planes; p.g = g; p.n_targets = n_targets; p.scores = scores;
-    p.work_counter = g_cand_counter[dev];
-    p.acc = g_cand_acc[dev];
+    p.work_counter = scratch.work_counter;
+    p.acc = scratch.acc;
     p.rows_per_band = c.rows_per_band; p.n_bands = c.n_bands; p.stage_words = c.stage_words;
     p.n_groups = (n_masks + GROUP - 1) / GROUP;
     p.occ = occ; p.bpitch = bpitch; p.groups = groups;
@@ -673,22 +670,16 @@ void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mi
 
 int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                            const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror,
-                           int32_t *scores, cudaStream_t s)
+                           int32_t *scores, const MatchScratch &scratch, cudaStream_t s)
 {
     (void) mirror;      // the word lists already say which orientations exist
     if (n_masks == 0 || n_targets == 0) return 0;
     if (!occ || !groups || bpitch != occupancy_tile_pitch(g.W)) return 0;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 64) return 0;
-    if (!g_cand_counter[dev]) {
-        if (cudaMalloc(&g_cand_counter[dev], sizeof(unsigned long long)) != cudaSuccess) return 0;
-    }
-    if (!g_cand_acc[dev]) {
-        if (cudaMalloc(&g_cand_acc[dev], kAccBytes) != cudaSuccess) return 0;
-    }
-    cudaMemsetAsync(g_cand_counter[dev], 0, sizeof(unsigned long long), s);
-    cudaMemsetAsync(g_cand_acc[dev], 0, kAccBytes, s);
+    if (!scratch.work_counter || !scratch.acc) return 0;
+    cudaMemsetAsync(scratch.work_counter, 0, sizeof(unsigned long long), s);
+    cudaMemsetAsync(scratch.acc, 0, kMatchAccBytes, s);
     // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket.  More warps need more
     // shared memory for their queues; when the band stages no longer fit (xyShift 4: 34 accumulators per mask) fewer are used.
     static const int warps_env = env_int("CDSGPU_CAND_WARPS", 31);
@@ -697,7 +688,7 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     if (warps >= 31 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 31).ok) warps = 28;
     if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok) warps = 24;
     if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24).ok) warps = 16;
-#define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<CDS_PALETTE_GROUP, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, s, dev)
+#define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<CDS_PALETTE_GROUP, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, scratch, s, dev)
     if (chunk_env == 512) {
         if (warps >= 31) return CDS_CAND_LAUNCH(31, 512);
         return CDS_CAND_LAUNCH(28, 512);

@@ -53,6 +53,14 @@ struct ShiftSet {
     int8_t dy[CDS_MAX_SHIFT_OFFSETS];
 };
 
+// Device scratch of the batched match kernels, owned by one context's device state (two contexts on one device must not share it):
+// the work-item counter of the persistent grids and the candidate kernel's match counters.
+struct MatchScratch {
+    unsigned long long *work_counter = nullptr;
+    int *acc = nullptr;                       // kMatchAccBytes, zero between launches
+};
+constexpr size_t kMatchAccBytes = (size_t) 256 * CDS_PALETTE_GROUP * CDS_MAX_VARIANTS * sizeof(int);   // [<= 256 CTAs][masks of a group][variants]
+
 // score word written by the match kernels: matching pixels | mirrored << 30
 #define CDS_SCORE_MIRROR_BIT 0x40000000
 

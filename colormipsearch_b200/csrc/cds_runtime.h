@@ -64,6 +64,7 @@ struct DevState {
     size_t scratch_bytes[4] = {0, 0, 0, 0};
     StreamBufs sb;
     DevPool pool;
+    MatchScratch match_scratch;       // allocated on first use (cds_ctx::ensure_match_scratch)
     uint32_t *pair_plane = nullptr;   // one code plane + one score word for cds_score_pair_rgb
     int pair_W = 0, pair_H = 0;
 };
@@ -86,6 +87,7 @@ struct cds_ctx {
     cds_status ensure_staging(cds::DevState &d, size_t bytes);
     cds_status ensure_pinned(cds::DevState &d, size_t bytes);
     cds_status ensure_scratch(cds::DevState &d, int slot, size_t bytes, void **out);
+    cds_status ensure_match_scratch(cds::DevState &d);
     cds_status class_table_on(cds::DevState &d, double tol, const cds_class_interval **out);
 };
 

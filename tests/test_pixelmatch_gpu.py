@@ -395,6 +395,30 @@ def test_concurrent_callers_on_one_context(ctx, synth):
     ms.close()
 
 
+def test_two_contexts_on_one_device_run_concurrently(synth):
+    """Each context owns its streams and kernel scratch: searches of two contexts on the same GPU may overlap."""
+    from concurrent.futures import ThreadPoolExecutor
+    masks, targets, _ = synth
+    rects = O.label_rects(W, H)
+
+    def run(seed_offset):
+        c = capi.Context(n_dev=1)
+        lib = capi.Library(c, W, H, 70)
+        lib.add_rgb(targets[::-1] if seed_offset else targets)
+        ms = capi.MaskSet(c, W, H, 20, 20, 0.01, 2, True, rects)
+        ms.add_rgb(masks)
+        outs = [ms.search_dense(lib)[0] for _ in range(6)]
+        ms.close(); lib.close(); c.close()
+        return outs
+
+    with ThreadPoolExecutor(2) as ex:
+        a, b = ex.map(run, (0, 1))
+    for x in a[1:]:
+        assert np.array_equal(x, a[0])
+    for x in b:
+        assert np.array_equal(x[:, ::-1], a[0])
+
+
 def test_edge_cases_and_errors(ctx, fixtures):
     rects = O.label_rects(W, H)
     # odd xyShift -> IllegalArgumentException (ColorDepthSearchAlgorithmProviderFactory.java:57-60)
