@@ -295,32 +295,58 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 if (pend) run_pending();
                 pend_cand = cand; pend_pr = pr; pend = true;
             };
-            // Peels the candidate bits `c` of 32 queued words (one word per lane, `e` its list entry; c = 0 for idle lanes) into the
-            // candidate queue, lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
+            // Turns the candidate bits `c` of 32 queued words (one word per lane, `e` its list entry; c = 0 for idle lanes) into
+            // candidates, 32 per round, and evaluates them.
             auto peel = [&](uint32_t c, uint4 e) {
                 const uint32_t wbits = e.x, lrec = e.z;
                 // position of the tile's first pixel | orientation | mask; a set bit adds (bit & 7) to x and (bit >> 3) to y
                 const uint32_t base = (((e.w >> kWordMetaColShift) & 255u) << 3) | ((e.w & 255u) << (11 + 2)) |
                                       (((e.w >> kWordMetaOrientBit) & 1u) << 21) | (e.w & (1023u << kWordMetaMaskShift));
-                unsigned bal = __ballot_sync(0xffffffffu, c != 0);
-                while (bal) {
-                    if (c) {
-                        const int bit = __ffs((int) c) - 1;
-                        const uint32_t k = (uint32_t) __popc(wbits & ((1u << bit) - 1u));
-                        uint2 cand;
-                        cand.x = base | ((uint32_t) bit & 7u) | (((uint32_t) bit >> 3) << 11);
-                        cand.y = lrec + k;
-                        myq[(qt + (uint32_t) __popc(bal & lt_mask)) & (kQueue - 1)] = cand;
-                        c &= c - 1;
+                // Load-balanced expansion: the batch's T candidate bits are numbered word by word (prefix sums of the popcounts),
+                // and in every round lane j takes candidate number j0 + j -- whichever word it belongs to -- so a round costs the
+                // same whether the bits sit in one dense tile or are spread over all 32.
+                const uint32_t n = (uint32_t) __popc(c);
+                uint32_t incl = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t excl = incl - n;
+                for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                    const uint32_t j = j0 + (uint32_t) lane;
+                    // source word = number of words whose candidates all come before number j (binary search over the lanes)
+                    uint32_t src = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const uint32_t end = __shfl_sync(0xffffffffu, incl, (int) (src + step - 1) & 31);
+                        if (end <= j) src += step;
                     }
-                    qt += (uint32_t) __popc(bal);
-                    if (qt - qh >= 32) {
-                        __syncwarp();
-                        const uint2 cand = myq[(qh + lane) & (kQueue - 1)];
-                        qh += 32;
-                        submit(cand, true);
+                    const bool live = j < total;
+                    src &= 31u;
+                    const uint32_t cs = __shfl_sync(0xffffffffu, c, (int) src), es = __shfl_sync(0xffffffffu, excl, (int) src);
+                    const uint32_t bs = __shfl_sync(0xffffffffu, base, (int) src), ls = __shfl_sync(0xffffffffu, lrec, (int) src);
+                    const uint32_t ws = __shfl_sync(0xffffffffu, wbits, (int) src);
+                    uint2 cand = make_uint2((uint32_t) y0 << 11, 0u);
+                    if (live) {
+                        const uint32_t bit = __fns(cs, 0u, (int) (j - es) + 1);          // the (j - es)-th candidate bit of that word
+                        cand.x = bs | (bit & 7u) | ((bit >> 3) << 11);
+                        cand.y = ls + (uint32_t) __popc(ws & ((1u << bit) - 1u));
                     }
-                    bal = __ballot_sync(0xffffffffu, c != 0);
+                    if (j0 + 32 <= total) {
+                        submit(cand, true);                                             // a full round goes straight to evaluation
+                    } else {
+                        // the batch's last, partial round waits in the candidate queue for company
+                        if (live) myq[(qt + (uint32_t) lane) & (kQueue - 1)] = cand;
+                        qt += total - j0;
+                        if (qt - qh >= 32) {
+                            __syncwarp();
+                            const uint2 full = myq[(qh + lane) & (kQueue - 1)];
+                            qh += 32;
+                            submit(full, true);
+                        }
+                    }
                 }
             };
             // A full batch of words with candidates: re-read their list entries (the scan only carried bits and position), peel
