@@ -85,7 +85,7 @@ __device__ __forceinline__ void count_hit(const int *acc, uint32_t c, uint32_t l
 
 template <int GROUP>
 struct CandSmem {
-    size_t stage_off, bits_off, pal_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, total;
+    size_t stage_off, bits_off, pal_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, sel_off, total;
     __host__ __device__ CandSmem(int stage_words, int NS, int bits_words, int n_warps)
     {
         size_t o = 0;
@@ -98,6 +98,7 @@ struct CandSmem {
         item_off = o;  o += 16;
         next_off = o;  o += 16;
         band_off = o;  o += (size_t) kStages * 8;                               // per stage: {first, end} entry of the group's word list
+        sel_off = o;   o += 64;                                                 // position of the r-th set bit of a nibble
         (void) NS;
         total = o;
     }
@@ -126,6 +127,21 @@ struct EvalUnroll<NRINGS, Offsets<NRINGS>::N> {
     static __device__ __forceinline__ void load(const uint32_t *, int, uint32_t (&)[Offsets<NRINGS>::N]) {}
     static __device__ __forceinline__ void count(const uint32_t (&)[Offsets<NRINGS>::N], const int *, uint32_t, uint32_t) {}
 };
+
+// Position of the r-th (0-based) set bit of c, r < popc(c): the byte (= tile row) by three prefix popcounts, the nibble by one
+// more, the bit inside the nibble from a 64-byte table (sel[nibble * 4 + r]).  About half the instructions of __fns.
+__device__ __forceinline__ uint32_t select_bit(uint32_t c, uint32_t r, const uint8_t *__restrict__ sel)
+{
+    const uint32_t t0 = (uint32_t) __popc(c & 0xFFu), t1 = (uint32_t) __popc(c & 0xFFFFu), t2 = (uint32_t) __popc(c & 0xFFFFFFu);
+    uint32_t sh = 0, e = 0;
+    if (r >= t0) { sh = 8; e = t0; }
+    if (r >= t1) { sh = 16; e = t1; }
+    if (r >= t2) { sh = 24; e = t2; }
+    uint32_t b = (c >> sh) & 0xFFu, q = r - e;
+    const uint32_t h = (uint32_t) __popc(b & 0xFu);
+    if (q >= h) { b >>= 4; q -= h; sh += 4; }
+    return sh + sel[(b & 0xFu) * 4 + (q & 3u)];
+}
 
 // First half of an evaluation: the candidate's palette reference (palette index | 0x8000 for the second interval), an L2
 // access whose latency the caller hides behind the evaluation of the previous batch.
@@ -182,6 +198,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     unsigned long long *s_empty = s_full + kStages;
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
     long long *s_item = reinterpret_cast<long long *>(smem_raw + L.item_off);           // [2] published work items
+    uint8_t *s_sel = smem_raw + L.sel_off;                                               // [16][4] r-th set bit of a nibble
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pitch = p.g.pitch, H = p.g.H, R = p.rows_per_band, NB = p.n_bands;
@@ -194,6 +211,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             s_next[s] = 0;
         }
         mbar_fence_init();
+    }
+    if (tid < 64) {
+        int nib = tid >> 2, r = tid & 3, pos = 0;
+        for (int b = 0, seen = 0; b < 4; b++)
+            if (nib & (1 << b)) { if (seen == r) pos = b; seen++; }
+        s_sel[tid] = (uint8_t) pos;
     }
     // never-matching words below each stage: a candidate in the first row of a band whose shifted column is -1..-4
     if (tid < kStages * kPrePad) s_stage[(tid / kPrePad) * stage_stride - kPrePad + (tid % kPrePad)] = CDS_CODE_PAD_WORD;
@@ -330,7 +353,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     const uint32_t ws = __shfl_sync(0xffffffffu, wbits, (int) src);
                     uint2 cand = make_uint2((uint32_t) y0 << 11, 0u);
                     if (live) {
-                        const uint32_t bit = __fns(cs, 0u, (int) (j - es) + 1);          // the (j - es)-th candidate bit of that word
+                        const uint32_t bit = select_bit(cs, j - es, s_sel);              // the (j - es)-th candidate bit of that word
                         cand.x = bs | (bit & 7u) | ((bit >> 3) << 11);
                         cand.y = ls + (uint32_t) __popc(ws & ((1u << bit) - 1u));
                     }
