@@ -281,6 +281,8 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "cand", "band"], help="batched match kernel (auto = candidate kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-tiff", action="store_true", help="skip the TIFF-file variant of the end-to-end step")
+    ap.add_argument("--e2e-tiff", action="store_true", help="run the TIFF-file variant also when world > 1")
     ap.add_argument("--no-shape", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -435,6 +437,70 @@ def main():
                "what": "every step, from pinned HOST buffers through the C ABI: cds_maskset_create + cds_maskset_add_rgb (H2D + mask "
                        "preparation) + cds_search_stream_rgb (chunked H2D of the targets overlapping encode + match + top-K, "
                        "result D2H, host merge) + destroy"}
+        # ---- the same step with the targets as PackBits TIFF FILES in pinned host memory (how colour-depth MIP libraries are
+        # stored): the files cross PCIe as they are and are decoded on the device
+        if (world == 1 or args.e2e_tiff) and not args.no_e2e_tiff and pool_t >= Te:
+            from concurrent.futures import ThreadPoolExecutor
+            t_enc = time.perf_counter()
+            pool_img = pool_arr[:Te * img_bytes].reshape(Te, H, W, 3)
+            with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+                files = list(ex.map(lambda i: capi.tiff_encode_rgb(pool_img[i], 8, 32773), range(Te)))
+            offsets = np.zeros(Te + 1, np.int64)
+            np.cumsum([len(f) for f in files], out=offsets[1:])
+            blob_arr, blob_ptr = ctx.host_alloc(int(offsets[-1]) + 64)
+            for i, f in enumerate(files):
+                blob_arr[offsets[i]:offsets[i + 1]] = np.frombuffer(f, np.uint8)
+            del files
+            with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+                mfiles = list(ex.map(lambda i: capi.tiff_encode_rgb(masks_host[i], 8, 32773), range(M)))
+            moffsets = np.zeros(M + 1, np.int64)
+            np.cumsum([len(f) for f in mfiles], out=moffsets[1:])
+            mblob_arr, mblob_ptr = ctx.host_alloc(int(moffsets[-1]) + 64)
+            for i, f in enumerate(mfiles):
+                mblob_arr[moffsets[i]:moffsets[i + 1]] = np.frombuffer(f, np.uint8)
+            del mfiles
+            enc_s = time.perf_counter() - t_enc
+            tphases = {"masks_h2d_prepare": 0.0, "stream_search": 0.0, "destroy": 0.0}
+
+            def e2e_tiff_step():
+                ta = time.perf_counter()
+                ms_e = capi.MaskSet(ctx, W, H, PARAMS["mask_threshold"], PARAMS["data_threshold"], PARAMS["z_tolerance"],
+                                    PARAMS["xy_shift"], PARAMS["mirror"], rects)
+                ms_e.add_tiff((mblob_arr, moffsets), blob_ptr=mblob_ptr)
+                tb = time.perf_counter(); tphases["masks_h2d_prepare"] += tb - ta
+                r = ms_e.search_stream_tiff((blob_arr, offsets), TOPK, PCT_POSITIVE, blob_ptr=blob_ptr)
+                tc = time.perf_counter(); tphases["stream_search"] += tc - tb
+                ms_e.close()
+                tphases["destroy"] += time.perf_counter() - tc
+                return r
+
+            e2e_tiff_step()
+            for kph in tphases:
+                tphases[kph] = 0.0
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                rt = e2e_tiff_step()
+            barrier()
+            tiff_s = time.perf_counter() - t0
+            tt = torch.tensor([tiff_s], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tiff_s = float(tt.item())
+            same = bool(np.array_equal(rt[3], res[3]) and all(np.array_equal(rt[i][m, :rt[3][m]], res[i][m, :res[3][m]])
+                                                              for i in range(3) for m in range(0, M, max(1, M // 64))))
+            e2e["tiff"] = {"value": M * Te * world * e2e_steps / tiff_s, "unit": "comparisons/s",
+                           "h2d_bytes_per_step": (int(offsets[-1]) + int(moffsets[-1])) * world, "d2h_bytes_per_step": d2h * world,
+                           "ms_per_step": tiff_s / e2e_steps * 1e3, "file_bytes_mean": float(offsets[-1]) / Te,
+                           "compression_ratio": Te * img_bytes / float(offsets[-1]),
+                           "phase_ms_per_step": {k: v / e2e_steps * 1e3 for k, v in tphases.items()},
+                           "equals_rgb_search": same, "encode_setup_s": enc_s,
+                           "what": "the same step with masks and targets as PackBits RGB TIFF files (71 strips of 8 rows, written by "
+                                   "cds_tiff_encode_rgb outside the timed region) in pinned host memory: cds_maskset_add_tiff + "
+                                   "cds_search_stream_tiff parse the tags on the host, upload the files as stored and decode them on "
+                                   "the device"}
+            ctx.host_free(blob_ptr)
+            ctx.host_free(mblob_ptr)
         ctx.host_free(pool_ptr)
         ctx.host_free(mask_ptr)
 

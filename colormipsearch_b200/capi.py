@@ -49,6 +49,12 @@ class SearchStats(C.Structure):
                 ("match_kernel", C.c_int64), ("chunked", C.c_int64)]
 
 
+class TiffInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("compression", C.c_int32), ("samples_per_pixel", C.c_int32),
+                ("bits_per_sample", C.c_int32), ("photometric", C.c_int32), ("planar_config", C.c_int32), ("rows_per_strip", C.c_int32),
+                ("n_strips", C.c_int32), ("big_endian", C.c_int32), ("data_bytes", C.c_int64), ("decodable", C.c_int32), ("pad", C.c_int32)]
+
+
 _lib = None
 _vp = C.c_void_p
 _u8p = C.POINTER(C.c_uint8)
@@ -85,6 +91,14 @@ SIGNATURES = {
     "cds_search_stream_rgb": (C.c_int32, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_double, _i32p, _i64p, _u8p, _i32p]),
     "cds_search_stream_matches_rgb": (C.c_int32, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_int64, _i32p, _i64p, _i32p, _u8p, _i64p]),
     "cds_search_matches": (C.c_int32, [_vp, _vp, _vp, C.c_double, C.c_int64, _i32p, _i64p, _i32p, _u8p, _i64p]),
+    "cds_tiff_probe": (C.c_int32, [_vp, C.c_int64, C.POINTER(TiffInfo)]),
+    "cds_tiff_encode_bound": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "cds_tiff_encode_rgb": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int64, _i64p]),
+    "cds_tiff_decode_rgb": (C.c_int32, [_vp, _vp, _i64p, C.c_int64, C.c_int32, C.c_int32, _vp]),
+    "cds_maskset_add_tiff": (C.c_int32, [_vp, _vp, _i64p, C.c_int32, _i32p]),
+    "cds_library_add_tiff": (C.c_int32, [_vp, _vp, _i64p, C.c_int64, _i64p]),
+    "cds_search_stream_tiff": (C.c_int32, [_vp, _vp, _vp, _i64p, C.c_int64, C.c_int32, C.c_double, _i32p, _i64p, _u8p, _i32p]),
+    "cds_search_stream_matches_tiff": (C.c_int32, [_vp, _vp, _vp, _i64p, C.c_int64, C.c_double, C.c_int64, _i32p, _i64p, _i32p, _u8p, _i64p]),
     "cds_score_pair_rgb": (C.c_int32, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
     "cds_shape_maskset_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Rect), C.c_int32, _vp, C.POINTER(_vp)]),
     "cds_shape_maskset_destroy": (None, [_vp]),
@@ -269,6 +283,13 @@ class Library:
         _check(lib().cds_library_add_rgb(self.h, ptr, int(n), C.byref(first)), self.ctx.h)
         return first.value
 
+    def add_tiff(self, files):
+        """cds_library_add_tiff.  files: a list of bytes objects, or a (blob, offsets) pair (see pack_files)."""
+        blob, offsets = pack_files(files)
+        first = C.c_int64()
+        _check(lib().cds_library_add_tiff(self.h, _ptr(blob), offsets.ctypes.data_as(_i64p), len(offsets) - 1, C.byref(first)), self.ctx.h)
+        return first.value
+
     def generate_synthetic(self, seed, first_synth_index, n):
         first = C.c_int64()
         _check(lib().cds_library_generate_synthetic(self.h, int(seed), int(first_synth_index), int(n), C.byref(first)), self.ctx.h)
@@ -315,6 +336,15 @@ class MaskSet:
             raise CdsIllegalArgument(CDS_ERR_SIZE_MISMATCH, "mask shape %s does not match the mask set (%d, %d)" % (rgb.shape, self.H, self.W))
         sizes = np.zeros(rgb.shape[0], np.int32)
         _check(lib().cds_maskset_add_rgb(self.h, _ptr(rgb), rgb.shape[0], sizes.ctypes.data_as(_i32p)), self.ctx.h)
+        return sizes
+
+    def add_tiff(self, files, blob_ptr=None):
+        """cds_maskset_add_tiff.  files: a list of bytes objects or a (blob, offsets) pair -> mask sizes."""
+        blob, offsets = pack_files(files)
+        n = len(offsets) - 1
+        sizes = np.zeros(n, np.int32)
+        ptr = blob_ptr if blob_ptr is not None else _ptr(blob)
+        _check(lib().cds_maskset_add_tiff(self.h, ptr, offsets.ctypes.data_as(_i64p), n, sizes.ctypes.data_as(_i32p)), self.ctx.h)
         return sizes
 
     def add_rgb_ptr(self, ptr, n):
@@ -365,6 +395,41 @@ class MaskSet:
                                            score.ctypes.data_as(_i32p), target.ctypes.data_as(_i64p),
                                            mirrored.ctypes.data_as(_u8p), count.ctypes.data_as(_i32p)), self.ctx.h)
         return score, target, mirrored, count
+
+    def search_stream_tiff(self, files, k, pct_positive_pixels=0.0, blob_ptr=None):
+        """cds_search_stream_tiff.  files: a list of bytes objects or a (blob, offsets) pair; blob_ptr overrides the blob's address
+        (e.g. a pinned copy of it)."""
+        blob, offsets = pack_files(files)
+        n = len(offsets) - 1
+        M = len(self)
+        score = np.zeros((M, k), np.int32)
+        target = np.full((M, k), -1, np.int64)
+        mirrored = np.zeros((M, k), np.uint8)
+        count = np.zeros(M, np.int32)
+        ptr = blob_ptr if blob_ptr is not None else _ptr(blob)
+        _check(lib().cds_search_stream_tiff(self.ctx.h, self.h, ptr, offsets.ctypes.data_as(_i64p), int(n), int(k), float(pct_positive_pixels),
+                                            score.ctypes.data_as(_i32p), target.ctypes.data_as(_i64p),
+                                            mirrored.ctypes.data_as(_u8p), count.ctypes.data_as(_i32p)), self.ctx.h)
+        return score, target, mirrored, count
+
+    def search_stream_matches_tiff(self, files, pct_positive_pixels=0.0, capacity=None):
+        """cds_search_stream_matches_tiff: every pair that passes isMatch, targets given as TIFF files."""
+        blob, offsets = pack_files(files)
+        n = len(offsets) - 1
+        cap = int(capacity) if capacity is not None else max(1024, 4 * len(self))
+        for _ in range(2):
+            mask = np.zeros(cap, np.int32); target = np.zeros(cap, np.int64); score = np.zeros(cap, np.int32); mir = np.zeros(cap, np.uint8)
+            count = C.c_int64(0)
+            st = lib().cds_search_stream_matches_tiff(self.ctx.h, self.h, _ptr(blob), offsets.ctypes.data_as(_i64p), int(n),
+                                                      float(pct_positive_pixels), cap, mask.ctypes.data_as(_i32p), target.ctypes.data_as(_i64p),
+                                                      score.ctypes.data_as(_i32p), mir.ctypes.data_as(_u8p), C.byref(count))
+            if st == CDS_ERR_CAPACITY and capacity is None:
+                cap = int(count.value)
+                continue
+            _check(st, self.ctx.h)
+            c = int(count.value)
+            return mask[:c], target[:c], score[:c], mir[:c]
+        _check(st, self.ctx.h)
 
     def search_stream_matches(self, targets_rgb, pct_positive_pixels=0.0, capacity=None):
         """cds_search_stream_matches_rgb: every pair that passes isMatch -> (mask, target, score, mirrored) arrays.  With
@@ -485,6 +550,49 @@ def class_intervals(z_tolerance, sector, rank):
     lo1, len1, lo2, len2 = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     _check(lib().cds_debug_class_intervals(float(z_tolerance), int(sector), int(rank), C.byref(lo1), C.byref(len1), C.byref(lo2), C.byref(len2)))
     return lo1.value, len1.value, lo2.value, len2.value
+
+
+def pack_files(files):
+    """A list of bytes-like objects -> (uint8 blob, int64 offsets[n + 1]), the layout the *_tiff calls take.  A (blob, offsets) pair
+    passes through."""
+    if isinstance(files, tuple) and len(files) == 2 and isinstance(files[1], np.ndarray):
+        blob, offsets = files
+        return blob, np.ascontiguousarray(offsets, dtype=np.int64)
+    offsets = np.zeros(len(files) + 1, np.int64)
+    for i, f in enumerate(files):
+        offsets[i + 1] = offsets[i] + len(f)
+    blob = np.frombuffer(b"".join(bytes(f) for f in files), dtype=np.uint8) if len(files) else np.zeros(0, np.uint8)
+    if blob.size == 0:
+        blob = np.zeros(1, np.uint8)
+    return blob, offsets
+
+
+def tiff_probe(data):
+    """cds_tiff_probe -> dict of the TIFF's tags (host only)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    info = TiffInfo()
+    _check(lib().cds_tiff_probe(_ptr(buf) if buf.size else None, buf.size, C.byref(info)))
+    return {k: getattr(info, k) for k, _ in TiffInfo._fields_ if k != "pad"}
+
+
+def tiff_encode_rgb(rgb, rows_per_strip=8, compression=32773):
+    """cds_tiff_encode_rgb -> bytes of a little-endian RGB TIFF (host only)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    H, W = rgb.shape[:2]
+    cap = lib().cds_tiff_encode_bound(W, H, rows_per_strip)
+    out = np.empty(cap, np.uint8)
+    n = C.c_int64(0)
+    _check(lib().cds_tiff_encode_rgb(_ptr(rgb), W, H, rows_per_strip, compression, _ptr(out), cap, C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def tiff_decode_rgb(ctx, files, W, H):
+    """cds_tiff_decode_rgb: decodes TIFF files on the device -> uint8 [n][H][W][3]."""
+    blob, offsets = pack_files(files)
+    n = len(offsets) - 1
+    out = np.empty((n, H, W, 3), np.uint8)
+    _check(lib().cds_tiff_decode_rgb(ctx.h, _ptr(blob), offsets.ctypes.data_as(_i64p), n, W, H, _ptr(out)), ctx.h)
+    return out
 
 
 def java_string_hash(s):

@@ -286,6 +286,11 @@ extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t
         ctx->stream_chunk = value;
         return CDS_OK;
     }
+    if (std::strcmp(name, "stream_chunk_tiff") == 0) {
+        if (value < 1 || value > 32768) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk_tiff must be 1..32768");
+        ctx->stream_chunk_tiff = value;
+        return CDS_OK;
+    }
     return ctx->fail(CDS_ERR_BAD_ARG, std::string("cds_ctx_set_option: unknown option ") + name);
 }
 
@@ -627,13 +632,14 @@ static cds_status arena_reserve(cds_ctx *ctx, DevState &ds, cds_maskset::Arena &
     return CDS_OK;
 }
 
-extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, int32_t n, int32_t *mask_size_out)
+// Appends n masks whose RGB pixels `fill` puts into device staging memory: fill(i0, cnt, stage, stream) enqueues, on `stream`,
+// whatever produces the pixels of masks [i0, i0 + cnt) of the call at `stage` (an H2D copy, or an upload of TIFF files and
+// their decode).
+namespace cds {
+cds_status maskset_append(cds_maskset *ms, int32_t n, int32_t *mask_size_out,
+                          const std::function<cds_status(int i0, int cnt, uint8_t *stage, cudaStream_t stream)> &fill)
 {
-    if (!ms) { set_tls_error("cds_maskset_add_rgb: NULL mask set"); return CDS_ERR_BAD_ARG; }
     cds_ctx *ctx = ms->ctx;
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (n < 0 || (!rgb && n > 0)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_rgb: bad arguments");
-    if (n == 0) return CDS_OK;
     const int D = (int) ctx->devs.size();
     const size_t img_bytes = (size_t) ms->W * ms->H * 3;
     const int H = ms->H;
@@ -660,7 +666,7 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
         const int slot = (i0 / kChunk) & 1;
         uint8_t *stage = (uint8_t *) d0.staging + (size_t) slot * kChunk * img_bytes;
         if (i0 >= 2 * kChunk) CDS_CUDA(ctx, cudaStreamWaitEvent(up_stream, d0.up_free[slot], 0));
-        CDS_CUDA(ctx, cudaMemcpyAsync(stage, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, up_stream));
+        CDS_TRY(fill(i0, cnt, stage, up_stream));
         CDS_CUDA(ctx, cudaEventRecord(d0.up_done[slot], up_stream));
         return CDS_OK;
     };
@@ -672,7 +678,6 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
         uint8_t *stage = (uint8_t *) d0.staging + (size_t) slot * kChunk * img_bytes;
         if (i0 + kChunk < n) CDS_TRY(enqueue_upload(i0 + kChunk));
         CDS_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d0.up_done[slot], 0));
-        ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
         uint32_t *rowstart = (uint32_t *) ((uint8_t *) s0.rowstart.p + s0.rowstart.used);
         launch_mask_count_rows(stage, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, rowstart, d0.stream);
         launch_mask_scan_rows(rowstart, cnt, H, d_sizes, d0.stream);
@@ -731,6 +736,22 @@ extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, i
     (void) first_mask;
     ms->descs_dirty = true;
     return CDS_OK;
+}
+}  // namespace cds
+
+extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, int32_t n, int32_t *mask_size_out)
+{
+    if (!ms) { set_tls_error("cds_maskset_add_rgb: NULL mask set"); return CDS_ERR_BAD_ARG; }
+    cds_ctx *ctx = ms->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || (!rgb && n > 0)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_rgb: bad arguments");
+    if (n == 0) return CDS_OK;
+    const size_t img_bytes = (size_t) ms->W * ms->H * 3;
+    return maskset_append(ms, n, mask_size_out, [&](int i0, int cnt, uint8_t *stage, cudaStream_t stream) -> cds_status {
+        CDS_CUDA(ctx, cudaMemcpyAsync(stage, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, stream));
+        ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
+        return CDS_OK;
+    });
 }
 
 cds_status cds_maskset::sync_descs()

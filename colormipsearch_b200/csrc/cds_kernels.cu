@@ -52,40 +52,106 @@ void launch_fill_words(uint32_t *p, size_t n, uint32_t v, cudaStream_t s)
 }
 
 // One CTA per (image row, image).  The RGB row (3W bytes, arbitrary alignment) is staged through shared memory with
-// aligned 32-bit loads; each thread then encodes pixels and writes coalesced code words, pads included.
-__global__ void __launch_bounds__(256) encode_rgb_kernel(const uint8_t *__restrict__ rgb, uint32_t *__restrict__ planes, PlaneGeom g,
-                                                         int64_t first_slot, const uint16_t *__restrict__ rank_tab, int thr)
+// aligned 32-bit loads; each warp then encodes 32 consecutive pixels per iteration and writes coalesced code words, pads
+// included.  With VALID the kernel also emits the row's per-sector "can match" bits (what valid_bits_kernel derives from
+// the code words) while the pixels are in registers: six ballots per 32 pixels instead of a second pass over the planes.
+__device__ __forceinline__ int code_sector(uint32_t cw)
 {
-    extern __shared__ uint32_t srow[];
-    const int y = blockIdx.x;
+    // above the threshold, and in a colour sector: "no sector" pixels (ties for the maximum, e.g. grey) have pixel gap
+    // 10000 against everything (AbstractColorDepthSearchAlgorithm.java:182, 259-388), they can never match
+    const uint32_t sr = (cw >> CDS_CODE_SR_SHIFT) & 0x3FFFFu;
+    if ((cw & (CDS_CODE_BELOW_BIT | CDS_CODE_PAD_BIT)) == 0 && sr < (uint32_t) CDS_SR_NONE) return (int) (sr / CDS_SECTOR_STRIDE);
+    return -1;
+}
+
+constexpr int kEncodeRows = 4;      // image rows per CTA (fewer for very wide images): one staging round trip to DRAM per 4 rows
+
+template <bool VALID>
+__global__ void __launch_bounds__(256) encode_rgb_kernel(const uint8_t *__restrict__ rgb, uint32_t *__restrict__ planes, PlaneGeom g,
+                                                         int64_t first_slot, const uint16_t *__restrict__ rank_tab, int thr,
+                                                         int vp, uint32_t *__restrict__ valid /* chunk-relative [n][H][sectors][vp] */,
+                                                         int rows_per_cta)
+{
+    extern __shared__ uint4 srow4[];
+    const int y0 = blockIdx.x * rows_per_cta;
+    const int rows = min(rows_per_cta, g.H - y0);
     const int64_t img = blockIdx.y;
     const size_t row_bytes = (size_t) g.W * 3;
-    const uint8_t *src = rgb + ((size_t) img * g.H + y) * row_bytes;
+    // the rows are contiguous in the source: stage them with aligned 128-bit loads (the source has arbitrary alignment)
+    const uint8_t *src = rgb + ((size_t) img * g.H + y0) * row_bytes;
     const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-    const int off = (int) (a & 3);
-    const uint32_t *asrc = reinterpret_cast<const uint32_t *>(a - off);
-    const int n_words = (int) ((off + row_bytes + 3) / 4);
-    for (int k = threadIdx.x; k < n_words; k += blockDim.x) srow[k] = asrc[k];
+    const int off = (int) (a & 15);
+    const uint4 *asrc = reinterpret_cast<const uint4 *>(a - off);
+    const int n_vec = (int) ((off + rows * row_bytes + 15) / 16);
+    for (int k = threadIdx.x; k < n_vec; k += blockDim.x) srow4[k] = asrc[k];
     __syncthreads();
-    const uint8_t *sb = reinterpret_cast<const uint8_t *>(srow) + off;
-    uint32_t *dst = planes + g.row_offset(first_slot + img, y);
-    for (int x = threadIdx.x; x < g.pitch; x += blockDim.x) {
-        uint32_t code = CDS_CODE_PAD_WORD;
-        if (x < g.W) code = encode_color_dev(sb[3 * x], sb[3 * x + 1], sb[3 * x + 2], rank_tab, thr);
-        dst[x] = code;
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(srow4) + off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kmax = max((g.pitch + 31) >> 5, vp);
+    // the rows' valid words are collected behind the staged pixels and leave as one contiguous block: a lane writing single
+    // words at a stride of vp makes every store a partial-sector write that L2 has to merge
+    uint32_t *s_valid = reinterpret_cast<uint32_t *>(srow4 + (rows_per_cta * row_bytes + 15 + 15) / 16);
+    // Colour-depth MIPs are mostly black: a warp whose 32 pixels are all (0, 0, 0) writes the black code word and six empty
+    // valid words without running the encoder (the encoder is ~150 instructions per 32 pixels, this path ~15).
+    const uint32_t black = encode_color_dev(0, 0, 0, rank_tab, thr);
+    for (int r = 0; r < rows; r++) {
+        uint32_t *drow = planes + g.row_offset(first_slot + img, y0 + r);
+        const uint8_t *srow = sb + (size_t) r * row_bytes;
+        for (int k = warp; k < kmax; k += (int) (blockDim.x >> 5)) {
+            const int x = k * 32 + lane;
+            int pr = 0, pg = 0, pb = 0;
+            if (x < g.W) { pr = srow[3 * x]; pg = srow[3 * x + 1]; pb = srow[3 * x + 2]; }
+            uint32_t code = x < g.W ? black : CDS_CODE_PAD_WORD;
+            const bool lit = __any_sync(0xffffffffu, (pr | pg | pb) != 0);
+            if (lit && x < g.W) code = encode_color_dev(pr, pg, pb, rank_tab, thr);
+            if (x < g.pitch) drow[x] = code;
+            if (VALID) {
+                if (!lit) {
+                    if (lane < CDS_NUM_SECTORS && k < vp) s_valid[(r * CDS_NUM_SECTORS + lane) * vp + k] = 0u;
+                } else {
+                    const int sector = code_sector(code);
+#pragma unroll
+                    for (int s = 0; s < CDS_NUM_SECTORS; s++) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, sector == s);
+                        if (lane == 0 && k < vp) s_valid[(r * CDS_NUM_SECTORS + s) * vp + k] = bal;
+                    }
+                }
+            }
+        }
+    }
+    if (VALID) {
+        __syncthreads();
+        uint32_t *vout = valid + ((size_t) img * g.H + y0) * CDS_NUM_SECTORS * vp;
+        for (int k = threadIdx.x; k < rows * CDS_NUM_SECTORS * vp; k += blockDim.x) vout[k] = s_valid[k];
     }
 }
 
 void launch_encode_rgb(const uint8_t *rgb, int64_t n, uint32_t *planes, PlaneGeom g, int64_t first_slot,
-                       const uint16_t *rank_tab, int data_threshold, cudaStream_t s)
+                       const uint16_t *rank_tab, int data_threshold, cudaStream_t s, uint32_t *valid)
 {
     if (n == 0) return;
-    size_t smem = ((size_t) g.W * 3 + 8 + 3) / 4 * 4;
+    const int vp = occupancy_valid_pitch(g.W);
+    int rpc = kEncodeRows;
+    auto smem_for = [&](int r) { return ((size_t) r * g.W * 3 + 15 + 15) / 16 * 16 + (valid ? (size_t) r * CDS_NUM_SECTORS * vp * 4 : 0); };
+    while (rpc > 1 && smem_for(rpc) > 96 * 1024) rpc >>= 1;
+    const size_t smem = smem_for(rpc);
+    static bool attr_set = false;
+    if (!attr_set) {
+        // wide images need more than the default 48 kB of dynamic shared memory
+        cudaFuncSetAttribute(encode_rgb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(encode_rgb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
     // gridDim.y is limited to 65535: chunk
     for (int64_t i0 = 0; i0 < n; i0 += 32768) {
         int64_t cnt = n - i0 < 32768 ? n - i0 : 32768;
-        dim3 grid(g.H, (unsigned) cnt);
-        encode_rgb_kernel<<<grid, 256, smem, s>>>(rgb + (size_t) i0 * g.H * g.W * 3, planes, g, first_slot + i0, rank_tab, data_threshold);
+        dim3 grid((g.H + rpc - 1) / rpc, (unsigned) cnt);
+        const uint8_t *src = rgb + (size_t) i0 * g.H * g.W * 3;
+        if (valid)
+            encode_rgb_kernel<true><<<grid, 256, smem, s>>>(src, planes, g, first_slot + i0, rank_tab, data_threshold, vp,
+                                                            valid + (size_t) i0 * g.H * CDS_NUM_SECTORS * vp, rpc);
+        else
+            encode_rgb_kernel<false><<<grid, 256, smem, s>>>(src, planes, g, first_slot + i0, rank_tab, data_threshold, vp, nullptr, rpc);
     }
 }
 
@@ -136,6 +202,7 @@ void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_ta
 __global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restrict__ planes, PlaneGeom g, int64_t t0, int vp,
                                                          uint32_t *__restrict__ valid /* chunk-relative [n][H][sectors][vp] */)
 {
+    extern __shared__ uint32_t s_valid[];
     const int y = blockIdx.x;
     const int64_t t = t0 + blockIdx.y;
     const uint32_t *row = planes + g.row_offset(t, y);
@@ -143,20 +210,15 @@ __global__ void __launch_bounds__(256) valid_bits_kernel(const uint32_t *__restr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = warp; k < vp; k += (int) (blockDim.x >> 5)) {
         const int x = k * 32 + lane;
-        int sector = -1;
-        if (x < g.W) {
-            // above the threshold, and in a colour sector: "no sector" pixels (ties for the maximum, e.g. grey) have pixel gap
-            // 10000 against everything (AbstractColorDepthSearchAlgorithm.java:182, 259-388), they can never match
-            const uint32_t cw = row[x];
-            const uint32_t sr = (cw >> CDS_CODE_SR_SHIFT) & 0x3FFFFu;
-            if ((cw & (CDS_CODE_BELOW_BIT | CDS_CODE_PAD_BIT)) == 0 && sr < (uint32_t) CDS_SR_NONE) sector = (int) (sr / CDS_SECTOR_STRIDE);
-        }
+        const int sector = x < g.W ? code_sector(row[x]) : -1;
 #pragma unroll
         for (int s = 0; s < CDS_NUM_SECTORS; s++) {
             const unsigned bal = __ballot_sync(0xffffffffu, sector == s);
-            if (lane == 0) out[s * vp + k] = bal;
+            if (lane == 0) s_valid[s * vp + k] = bal;
         }
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < CDS_NUM_SECTORS * vp; k += blockDim.x) out[k] = s_valid[k];      // one contiguous block per row
 }
 
 __device__ __forceinline__ uint32_t hspread(const uint32_t *__restrict__ vrow, int k, int vp, int s)
@@ -168,57 +230,97 @@ __device__ __forceinline__ uint32_t hspread(const uint32_t *__restrict__ vrow, i
     return c | (c << s) | (l >> (32 - s)) | (c >> s) | (r << (32 - s));
 }
 
-// One thread per 32-pixel strip of one image row: the dilated bits of every sector, scattered as bytes into the 8 x 4 tiles.
+// One thread per 32-pixel strip of one TILE row (4 image rows): per sector the dilated bits of the four rows, transposed
+// into the strip's four 8 x 4 tile words and written as one 128-bit store -- consecutive threads write consecutive 16 bytes.
+template <int RINGS>
+__device__ __forceinline__ void occupancy_strip(const uint32_t *__restrict__ vsec /* sector's words of row 0 */, int vrow_words, int H,
+                                                int vp, int k, int y0, uint32_t o[4])
+{
+    if (RINGS == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) o[r] = y0 + r < H ? vsec[(size_t) (y0 + r) * vrow_words + k] : 0u;
+        return;
+    }
+    uint32_t h2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int y = y0 - 2 + j;
+        h2[j] = (y >= 0 && y < H) ? hspread(vsec + (size_t) y * vrow_words, k, vp, 2) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) o[r] = h2[r] | h2[r + 2] | h2[r + 4];
+    if (RINGS >= 2) {
+        uint32_t h4[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            const int y = y0 - 4 + j;
+            h4[j] = (y >= 0 && y < H) ? hspread(vsec + (size_t) y * vrow_words, k, vp, 4) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) o[r] |= h4[r] | h4[r + 4] | h4[r + 8];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) if (y0 + r >= H) o[r] = 0u;       // rows of the last tile row that lie below the image
+}
+
+// rows o[0..3] of a 32-pixel strip -> its four tile words (byte r of word j = byte j of row r)
+__device__ __forceinline__ uint4 strip_to_tiles(const uint32_t o[4])
+{
+    const uint32_t a = __byte_perm(o[0], o[1], 0x5140), b = __byte_perm(o[2], o[3], 0x5140);
+    const uint32_t c = __byte_perm(o[0], o[1], 0x7362), d = __byte_perm(o[2], o[3], 0x7362);
+    return make_uint4(__byte_perm(a, b, 0x5410), __byte_perm(a, b, 0x7632), __byte_perm(c, d, 0x5410), __byte_perm(c, d, 0x7632));
+}
+
+template <int RINGS>
 __global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restrict__ valid /* chunk-relative */, int H, int vp, int tp,
-                                                        int64_t t0, int64_t n, int rings, uint32_t *__restrict__ occ)
+                                                        int64_t t0, int64_t n, uint32_t *__restrict__ occ)
 {
     const int rowpitch = occupancy_row_pitch(tp);
     const int HT = occupancy_tile_rows(H);
     const int vrow_words = CDS_NUM_SECTORS * vp;
-    const size_t total = (size_t) n * H * vp;
+    const size_t total = (size_t) n * HT * vp;
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
         const int k = (int) (i % vp);
-        const int y = (int) ((i / vp) % H);
-        const int64_t tl = (int64_t) (i / ((size_t) vp * H));
+        const int ty = (int) ((i / vp) % HT);
+        const int64_t tl = (int64_t) (i / ((size_t) vp * HT));
+        if (4 * k >= tp) continue;                     // tp is a multiple of 4: a strip is four whole tile words or none
         const uint32_t *vimg = valid + (size_t) tl * H * vrow_words;
-        uint8_t *orow = reinterpret_cast<uint8_t *>(occ + ((size_t) (t0 + tl) * HT + (y >> 2)) * rowpitch) + (y & 3);
-        uint32_t any = 0;
+        uint4 *orow = reinterpret_cast<uint4 *>(occ + ((size_t) (t0 + tl) * HT + ty) * rowpitch) + k;
+        uint32_t any[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int s = 0; s <= CDS_NUM_SECTORS; s++) {
-            uint32_t o;
-            if (s == CDS_NUM_SECTORS) {
-                o = any;
-            } else if (rings == 0) {
-                o = vimg[(size_t) y * vrow_words + s * vp + k];
-            } else {
-                o = 0;
-                for (int dy = -2; dy <= 2; dy += 2)
-                    if (y + dy >= 0 && y + dy < H) o |= hspread(vimg + (size_t) (y + dy) * vrow_words + s * vp, k, vp, 2);
-                if (rings >= 2)
-                    for (int dy = -4; dy <= 4; dy += 4)
-                        if (y + dy >= 0 && y + dy < H) o |= hspread(vimg + (size_t) (y + dy) * vrow_words + s * vp, k, vp, 4);
-            }
-            any |= o;
+        for (int s = 0; s < CDS_NUM_SECTORS; s++) {
+            uint32_t o[4];
+            occupancy_strip<RINGS>(vimg + s * vp, vrow_words, H, vp, k, 4 * ty, o);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int tx = 4 * k + j;
-                if (tx < tp) orow[((size_t) s * tp + tx) * 4] = (uint8_t) (o >> (8 * j));
-            }
+            for (int r = 0; r < 4; r++) any[r] |= o[r];
+            orow[(size_t) s * (tp / 4)] = strip_to_tiles(o);
         }
+        orow[(size_t) CDS_NUM_SECTORS * (tp / 4)] = strip_to_tiles(any);
     }
 }
 
+static void launch_occupancy_kernel(const uint32_t *valid, int H, int vp, int tp, int64_t t0, int64_t n, int rings, uint32_t *occ, cudaStream_t s)
+{
+    if (rings == 0) occupancy_kernel<0><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
+    else if (rings == 1) occupancy_kernel<1><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
+    else occupancy_kernel<2><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
+}
+
 void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int tp,
-                      uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s)
+                      uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s, bool valid_ready)
 {
     if (n == 0) return;
     const int vp = occupancy_valid_pitch(g.W);
+    if (valid_ready) {      // the encoder already wrote the bits of targets [0, n) (launch_encode_rgb with `valid`)
+        launch_occupancy_kernel(valid_scratch, g.H, vp, tp, t0, n, rings, occ, s);
+        return;
+    }
     if (scratch_targets > 32768) scratch_targets = 32768;      // gridDim.y
     for (int64_t i0 = 0; i0 < n; i0 += scratch_targets) {
         const int64_t cnt = n - i0 < scratch_targets ? n - i0 : scratch_targets;
         dim3 grid(g.H, (unsigned) cnt);
-        valid_bits_kernel<<<grid, 256, 0, s>>>(planes, g, t0 + i0, vp, valid_scratch);
-        occupancy_kernel<<<148 * 8, 256, 0, s>>>(valid_scratch, g.H, vp, tp, t0 + i0, cnt, rings, occ);
+        valid_bits_kernel<<<grid, 256, (size_t) CDS_NUM_SECTORS * vp * 4, s>>>(planes, g, t0 + i0, vp, valid_scratch);
+        launch_occupancy_kernel(valid_scratch, g.H, vp, tp, t0 + i0, cnt, rings, occ, s);
     }
 }
 

@@ -65,8 +65,10 @@ constexpr size_t kMatchAccBytes = (size_t) 256 * CDS_PALETTE_GROUP * CDS_MAX_VAR
 #define CDS_SCORE_MIRROR_BIT 0x40000000
 
 void launch_fill_words(uint32_t *p, size_t n, uint32_t v, cudaStream_t s);
+// `valid` (optional): chunk-relative scratch [n][H][sectors][occupancy_valid_pitch(W)]; the encoder then also writes the per-sector
+// "can match" bits of every row, and launch_occupancy can be called with valid_ready = true (no second pass over the planes).
 void launch_encode_rgb(const uint8_t *rgb, int64_t n, uint32_t *planes, PlaneGeom g, int64_t first_slot,
-                       const uint16_t *rank_tab, int data_threshold, cudaStream_t s);
+                       const uint16_t *rank_tab, int data_threshold, cudaStream_t s, uint32_t *valid = nullptr);
 void launch_rebake(uint32_t *planes, size_t n_words, int data_threshold, cudaStream_t s);
 void launch_encode_colors(const uint8_t *rgb, int64_t n, const uint16_t *rank_tab, int data_threshold, uint32_t *codes, cudaStream_t s);
 
@@ -86,7 +88,7 @@ __host__ __device__ inline int occupancy_tile_rows(int H) { return (H + 3) / 4; 
 __host__ __device__ inline int occupancy_row_pitch(int tp) { return (CDS_NUM_SECTORS + 1) * tp; }
 __host__ __device__ inline size_t occupancy_target_words(int W, int H) { return (size_t) occupancy_tile_rows(H) * occupancy_row_pitch(occupancy_tile_pitch(W)); }
 void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int tp,
-                      uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s);
+                      uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s, bool valid_ready = false);
 
 void launch_mask_count_rows(const uint8_t *rgb, int n_masks, int W, int H, int threshold, RectSet rects,
                             uint32_t *rowcount, cudaStream_t s);

@@ -33,6 +33,10 @@ struct StreamBufs {
     int32_t *counts_chunk = nullptr, *counts_run = nullptr, *min_score = nullptr;
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, enc_done[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> timing;    // pairs around every chunk's match kernel
+    // targets that arrive as TIFF files (cds_search_stream_tiff): file bytes as uploaded + strip tables, double buffered
+    uint8_t *comp[2] = {nullptr, nullptr};
+    void *d_strips[2] = {nullptr, nullptr}, *h_strips[2] = {nullptr, nullptr};     // cds::TiffStrip[]; the host copies are pinned
+    size_t comp_cap = 0, strips_cap = 0;
     void release();
 };
 
@@ -81,6 +85,7 @@ struct cds_ctx {
     int match_kernel = 0;      // cds_ctx_set_option("match_kernel"): 0 automatic, 1 candidate, 2 band, 3 gather
     int resident_occupancy = 1;   // cds_ctx_set_option("resident_occupancy"): 0 = always build occupancy bitmaps per target chunk
     int64_t stream_chunk = 256;   // cds_ctx_set_option("stream_chunk"): targets per chunk of cds_search_stream_rgb
+    int64_t stream_chunk_tiff = 1024;   // cds_ctx_set_option("stream_chunk_tiff"): targets per chunk of cds_search_stream_tiff
 
     cds_status fail(cds_status code, const std::string &msg) const;
     cds_status check(cudaError_t e, const char *what) const;
@@ -177,6 +182,9 @@ cds_status search_library_chunked(cds_ctx *ctx, const cds_maskset *ms, cds_libra
 cds_status library_append(cds_library *lib, int64_t n,
                           const std::function<cds_status(DevState &, int64_t i0, int64_t cnt, uint8_t *d_rgb)> &src,
                           int64_t *first_index);
+// Appends n masks whose pixels `fill` puts into device staging memory (cds_api.cu).
+cds_status maskset_append(cds_maskset *ms, int32_t n, int32_t *mask_size_out,
+                          const std::function<cds_status(int i0, int cnt, uint8_t *stage, cudaStream_t stream)> &fill);
 }  // namespace cds
 
 #endif

@@ -16,6 +16,7 @@
 #include "cds_runtime.h"
 #include "cds_band.cuh"
 #include "cds_topk.cuh"
+#include "cds_tiff.h"
 
 using namespace cds;
 
@@ -34,6 +35,13 @@ void cds::StreamBufs::release()
     for (void *b : bufs) if (b) cudaFree(b);
     planes = occ = valid = nullptr; scores = nullptr; keys_chunk = keys_run = nullptr;
     counts_chunk = counts_run = min_score = nullptr;
+    for (int i = 0; i < 2; i++) {
+        if (comp[i]) cudaFree(comp[i]);
+        if (d_strips[i]) cudaFree(d_strips[i]);
+        if (h_strips[i]) cudaFreeHost(h_strips[i]);
+        comp[i] = nullptr; d_strips[i] = nullptr; h_strips[i] = nullptr;
+    }
+    comp_cap = strips_cap = 0;
     for (cudaEvent_t e : timing) cudaEventDestroy(e);
     timing.clear();
     if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -106,9 +114,43 @@ cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, in
     return CDS_OK;
 }
 
+// staging of the TIFF source: both streams are drained before anything is replaced
+cds_status ensure_tiff_bufs(cds_ctx *ctx, DevState &ds, size_t comp_bytes, size_t n_strips)
+{
+    StreamBufs &sb = ds.sb;
+    if (sb.comp_cap >= comp_bytes && sb.strips_cap >= n_strips) return CDS_OK;
+    CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+    CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+    CDS_CUDA(ctx, cudaStreamSynchronize(sb.copy_stream));
+    if (sb.comp_cap < comp_bytes) {
+        for (int i = 0; i < 2; i++) {
+            if (sb.comp[i]) { cudaFree(sb.comp[i]); sb.comp[i] = nullptr; }
+            CDS_CUDA(ctx, cudaMalloc(&sb.comp[i], comp_bytes));
+        }
+        sb.comp_cap = comp_bytes;
+    }
+    if (sb.strips_cap < n_strips) {
+        const size_t cap = std::max(n_strips, sb.strips_cap * 2);
+        for (int i = 0; i < 2; i++) {
+            if (sb.d_strips[i]) { cudaFree(sb.d_strips[i]); sb.d_strips[i] = nullptr; }
+            if (sb.h_strips[i]) { cudaFreeHost(sb.h_strips[i]); sb.h_strips[i] = nullptr; }
+            CDS_CUDA(ctx, cudaMalloc(&sb.d_strips[i], cap * sizeof(TiffStrip)));
+            CDS_CUDA(ctx, cudaMallocHost(&sb.h_strips[i], cap * sizeof(TiffStrip)));
+        }
+        sb.strips_cap = cap;
+    }
+    return CDS_OK;
+}
+
 }  // namespace
 
 namespace {
+
+// targets given as TIFF files stored back to back (cds_search_stream_tiff)
+struct TiffSource {
+    const uint8_t *blob;
+    const int64_t *offsets;
+};
 
 // `all` selects the second mode of the streaming search: instead of per-mask top-K lists, every pair that passes isMatch.
 struct AllMatchesOut {
@@ -123,7 +165,7 @@ struct AllMatchesOut {
 cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8_t *targets_rgb, int64_t n_targets,
                               int32_t k, double pct_positive_pixels,
                               int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count, const AllMatchesOut *all,
-                              cds_library *resident)
+                              cds_library *resident, const TiffSource *tiff = nullptr)
 {
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
@@ -131,7 +173,8 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     if (!all && (k <= 0 || k > topk_max_k())) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: k must be in 1..4096");
     if (all) k = 1;
     if (resident) n_targets = resident->size;
-    if (!resident && (n_targets < 0 || (n_targets > 0 && !targets_rgb))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: bad target array");
+    if (!resident && !tiff && (n_targets < 0 || (n_targets > 0 && !targets_rgb))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_rgb: bad target array");
+    if (tiff && (n_targets < 0 || (n_targets > 0 && (!tiff->blob || !tiff->offsets)))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_tiff: bad target array");
     const int M = (int) ms->sizes.size();
     if (all) {
         if (!all->count || all->capacity < 0 || (all->capacity > 0 && (!all->mask || !all->target || !all->score)))
@@ -155,7 +198,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         g = resident->g;
         CDS_TRY(resident->bake(ms->params.data_threshold));
     }
-    const int64_t chunk = std::min<int64_t>(ctx->stream_chunk, n_targets);
+    const int64_t chunk = std::min<int64_t>(tiff ? ctx->stream_chunk_tiff : ctx->stream_chunk, n_targets);
     // the chunk plan: (device, first target, count); host targets go round-robin over the devices, a resident library is
     // walked shard by shard (first = index LOCAL to the shard)
     struct Chunk { int d; int64_t first, cnt; };
@@ -173,6 +216,17 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     const int thr = ms->params.data_threshold;
     const int rings = ms->params.xy_shift / 2;
     const bool want_occ = batched_kernel_supported(ms->params.xy_shift, g) && M >= band_min_masks();
+
+    size_t tiff_comp_bytes = 0;
+    std::vector<TiffStrip> strips;
+    if (tiff) {
+        if ((uint64_t) chunk * img_bytes > 0xF0000000ull) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_search_stream_tiff: stream_chunk too large for this image size");
+        for (const Chunk &ch : plan) {
+            const int64_t a = tiff->offsets[ch.first], b = tiff->offsets[ch.first + ch.cnt];
+            if (a < 0 || b < a) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_tiff: offsets must be non-decreasing");
+            tiff_comp_bytes = std::max(tiff_comp_bytes, (size_t) (b - a) + 64);
+        }
+    }
 
     std::vector<int32_t> min_score(M);
     for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);
@@ -194,6 +248,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     for (int d = 0; d < used_devs; d++) {
         DevState &ds = ctx->devs[d];
         CDS_TRY(ensure_stream_bufs(ctx, ds, g, bpitch, chunk, M, k, resident == nullptr));
+        if (tiff) CDS_TRY(ensure_tiff_bufs(ctx, ds, tiff_comp_bytes, (size_t) chunk * 128));
         CDS_CUDA(ctx, cudaMemcpyAsync(ds.sb.min_score, min_score.data(), (size_t) M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaMemsetAsync(ds.sb.counts_run, 0, (size_t) M * sizeof(int32_t), ds.stream));
         if (all) {
@@ -225,6 +280,32 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         const uint32_t *planes = sb.planes;
         if (resident) {
             planes = resident->shards[d].planes + (size_t) first * g.plane_stride();      // the same geometry, starting at plane `first`
+        } else if (tiff) {
+            // host: the chunk's strip table from the files' tags (overlaps the device's work on earlier chunks)
+            strips.clear();
+            const int64_t base = tiff->offsets[first];
+            std::string err;
+            for (int64_t i = 0; i < cnt; i++) {
+                const int64_t a = tiff->offsets[first + i], b = tiff->offsets[first + i + 1];
+                if (b < a) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_tiff: offsets must be non-decreasing");
+                cds_status st = tiff_collect_strips(tiff->blob + a, (size_t) (b - a), g.W, g.H, (uint64_t) (a - base), (uint64_t) i * img_bytes, strips, err);
+                if (st != CDS_OK) return ctx->fail(st, "cds_search_stream_tiff: file " + std::to_string(first + i) + ": " + err);
+            }
+            CDS_TRY(ensure_tiff_bufs(ctx, ds, tiff_comp_bytes, strips.size()));
+            if (j >= 2) CDS_CUDA(ctx, cudaEventSynchronize(sb.h2d_done[slot]));        // the slot's previous table has left the host
+            memcpy(sb.h_strips[slot], strips.data(), strips.size() * sizeof(TiffStrip));
+            if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
+            const size_t bytes = (size_t) (tiff->offsets[first + cnt] - base);
+            CDS_CUDA(ctx, cudaMemcpyAsync(sb.comp[slot], tiff->blob + base, bytes, cudaMemcpyHostToDevice, sb.copy_stream));
+            CDS_CUDA(ctx, cudaMemcpyAsync(sb.d_strips[slot], sb.h_strips[slot], strips.size() * sizeof(TiffStrip), cudaMemcpyHostToDevice, sb.copy_stream));
+            ctx->stats.h2d_bytes += (int64_t) bytes + (int64_t) (strips.size() * sizeof(TiffStrip));
+            CDS_CUDA(ctx, cudaEventRecord(sb.h2d_done[slot], sb.copy_stream));
+            CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
+            // decode into one RGB area (stream order protects it), then the usual encoder
+            launch_tiff_decode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.staging[0], ds.stream);
+            launch_encode_rgb(sb.staging[0], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream, want_occ ? sb.valid : nullptr);
+            CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ds.stream));
+            ctx->stats.kernel_launches += 2;
         } else {
             if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
             CDS_CUDA(ctx, cudaMemcpyAsync(sb.staging[slot], targets_rgb + (size_t) first * img_bytes, (size_t) cnt * img_bytes,
@@ -232,15 +313,16 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
             CDS_CUDA(ctx, cudaEventRecord(sb.h2d_done[slot], sb.copy_stream));
             CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
-            launch_encode_rgb(sb.staging[slot], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream);
+            launch_encode_rgb(sb.staging[slot], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream, want_occ ? sb.valid : nullptr);
             CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ds.stream));
             ctx->stats.kernel_launches++;
         }
         TargetView tv;
         tv.planes = planes; tv.g = g; tv.bpitch = bpitch; tv.n = cnt; tv.occ = nullptr; tv.occ_ready = false;
         if (want_occ) {
-            launch_occupancy(planes, g, 0, cnt, rings, bpitch, sb.valid, sb.chunk, sb.occ, ds.stream);
-            ctx->stats.kernel_launches += 2;
+            // host targets: the encoder has just written the valid bits of this chunk
+            launch_occupancy(planes, g, 0, cnt, rings, bpitch, sb.valid, sb.chunk, sb.occ, ds.stream, resident == nullptr);
+            ctx->stats.kernel_launches += resident ? 2 : 1;
             tv.occ = sb.occ;
             tv.occ_ready = true;
         }
@@ -387,6 +469,26 @@ extern "C" cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_mask
     if (!ctx || !ms) { set_tls_error("cds_search_stream_matches_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
     const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
     return stream_search_impl(ctx, ms, targets_rgb, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, nullptr);
+}
+
+extern "C" cds_status cds_search_stream_tiff(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *blob, const int64_t *offsets, int64_t n_targets,
+                                             int32_t k, double pct_positive_pixels,
+                                             int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
+{
+    if (!ctx || !ms) { set_tls_error("cds_search_stream_tiff: NULL argument"); return CDS_ERR_BAD_ARG; }
+    const TiffSource src{blob, offsets};
+    return stream_search_impl(ctx, ms, nullptr, n_targets, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr, nullptr, &src);
+}
+
+extern "C" cds_status cds_search_stream_matches_tiff(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *blob, const int64_t *offsets, int64_t n_targets,
+                                                     double pct_positive_pixels, int64_t capacity,
+                                                     int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored,
+                                                     int64_t *out_count)
+{
+    if (!ctx || !ms) { set_tls_error("cds_search_stream_matches_tiff: NULL argument"); return CDS_ERR_BAD_ARG; }
+    const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
+    const TiffSource src{blob, offsets};
+    return stream_search_impl(ctx, ms, nullptr, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, nullptr, &src);
 }
 
 // The same chunked search over a device-resident library: occupancy bitmaps are built per chunk instead of being kept for

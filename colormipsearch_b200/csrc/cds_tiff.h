@@ -1,0 +1,41 @@
+// cds_tiff.h -- TIFF container parsing on the host and the strip table the device decoder consumes.
+#ifndef CDS_TIFF_H
+#define CDS_TIFF_H
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/cdsgpu.h"
+
+namespace cds {
+
+// One strip of one image, as the decode kernel sees it: `src` = first byte of the strip relative to the start of the uploaded
+// byte range, `dst` = first decoded byte relative to the start of the chunk's RGB area.  Bit 31 of dst_len: the strip is
+// PackBits-compressed (otherwise stored bytes are copied).
+struct TiffStrip {
+    uint32_t src, src_len, dst, dst_len;
+};
+constexpr uint32_t kTiffStripPacked = 0x80000000u;
+constexpr uint32_t kTiffStoredPiece = 8192;      // stored (uncompressed) strips are cut into pieces of this many bytes
+// most table entries one W x H image can need: a PackBits strip holds at least one row
+inline size_t tiff_strips_bound(int W, int H) { return (size_t) H + (size_t) W * H * 3 / kTiffStoredPiece + 2; }
+
+// Reads the header and the first IFD of `file` (classic TIFF, either byte order).  Fills `info`; when strip_off / strip_len are
+// given, also the strip table (file-relative offsets, byte counts).  Returns CDS_OK, or CDS_ERR_BAD_ARG with `err` set for a
+// buffer that is not a well-formed TIFF.  Whether the device decoder takes the file is info.decodable (`why` says why not).
+cds_status tiff_parse(const uint8_t *file, size_t len, cds_tiff_info &info, std::vector<uint64_t> *strip_off,
+                      std::vector<uint64_t> *strip_len, std::string &err, std::string *why = nullptr);
+
+// Appends the strips of file `file` (located `src_base` bytes into the uploaded range, decoding to `dst_base`) to `out`;
+// checks that the image is width x height and decodable.  On failure `err` describes the problem.
+cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int height, uint64_t src_base, uint64_t dst_base,
+                               std::vector<TiffStrip> &out, std::string &err);
+
+void launch_tiff_decode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint8_t *dst_rgb, cudaStream_t s);
+
+}  // namespace cds
+#endif

@@ -90,6 +90,8 @@ int32_t    cds_abi_version(void);
  * a kernel that does not support the search's parameters falls through to the next one.  All three compute the same
  * scores bit for bit (tests/test_pixelmatch_gpu.py cross-checks them).
  * "stream_chunk": targets per chunk of the chunked searches (default 256).
+ * "stream_chunk_tiff": targets per chunk of cds_search_stream_tiff (default 1024: compressed files upload fast, larger chunks
+ *   keep the match kernel's grid full).
  * "resident_occupancy": 1 (default) keeps a library's occupancy bitmaps on the device next to its code planes (+23 % memory) and
  * falls back to building them per target chunk inside cds_search_topk when they do not fit; 0 always builds them per chunk.
  * Unknown names: CDS_ERR_BAD_ARG. */
@@ -168,6 +170,63 @@ cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_maskset *ms, co
  * target = index in the library). */
 cds_status cds_search_matches(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, double pct_positive_pixels, int64_t capacity,
                               int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored, int64_t *out_count);
+
+/* ---------------------------------------------------------------- image ingest ------------------------------------------- */
+
+/* Colour-depth MIP libraries are stored as RGB TIFF files, normally PackBits-compressed (the reference's own fixtures: 1210x566,
+ * 71 strips of 8 rows, 65-255 kB per 2 MB image).  The reference decodes them on the JVM: ImageJ's Opener for whole files
+ * (API/imageprocessing/ImageArrayUtils.java:176-182) and its own strip loop + packBitsUncompress for PackBits files
+ * (ImageArrayUtils.java:184-258, LocalTiffDecoder.java).  Here the container is parsed on the host (tags only), the strips
+ * travel to the device AS STORED and are decoded there, so a search over host-resident files moves 8-30 x fewer bytes over PCIe.
+ * Supported: classic (non-Big) TIFF, either byte order, first image of the file, 8-bit RGB chunky (SamplesPerPixel 3,
+ * PlanarConfiguration 1), Compression 1 (none) or 32773 (PackBits), strips (no tiles).
+ * Anything else: CDS_ERR_UNSUPPORTED naming the file (LZW, which the reference hands to ImageJ, included). */
+typedef struct cds_tiff_info {
+    int32_t width, height;
+    int32_t compression;          /* tag 259: 1 none, 5 LZW, 32773 PackBits, ... */
+    int32_t samples_per_pixel;    /* tag 277 */
+    int32_t bits_per_sample;      /* tag 258 (first sample) */
+    int32_t photometric;          /* tag 262 */
+    int32_t planar_config;        /* tag 284 (1 when absent) */
+    int32_t rows_per_strip;       /* tag 278 (height when absent) */
+    int32_t n_strips;
+    int32_t big_endian;           /* 1 for "MM" files */
+    int64_t data_bytes;           /* sum of the strip byte counts */
+    int32_t decodable;            /* 1 when the device decoder takes this file */
+    int32_t pad;
+} cds_tiff_info;
+
+/* Host only (no device needed): reads the first IFD of a TIFF file held in memory. */
+cds_status cds_tiff_probe(const uint8_t *file, int64_t len, cds_tiff_info *info);
+
+/* Host only: writes an 8-bit RGB image as a little-endian TIFF with PackBits-compressed strips of rows_per_strip rows (every
+ * row packed on its own, as the TIFF specification asks).  compression = 32773 or 1.  cds_tiff_encode_bound gives a capacity
+ * that always suffices.  Used to build test and benchmark libraries; the reference only reads TIFFs. */
+int64_t    cds_tiff_encode_bound(int32_t width, int32_t height, int32_t rows_per_strip);
+cds_status cds_tiff_encode_rgb(const uint8_t *rgb, int32_t width, int32_t height, int32_t rows_per_strip, int32_t compression,
+                               uint8_t *out, int64_t capacity, int64_t *out_len);
+
+/* n TIFF files stored back to back in `blob`: file i is blob[offsets[i] .. offsets[i+1]) (offsets has n + 1 entries).
+ * Decodes them on device 0 of the context and returns the pixels: out_rgb is uint8[n][height][width][3].  A strip that decodes
+ * to fewer bytes than its rows need leaves the rest 0, like the zero-initialised array of ImageArrayUtils.java:198.
+ * CDS_ERR_SIZE_MISMATCH when a file's size is not width x height. */
+cds_status cds_tiff_decode_rgb(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n,
+                               int32_t width, int32_t height, uint8_t *out_rgb);
+
+/* cds_library_add_rgb / cds_maskset_add_rgb for TIFF files: compressed strips are uploaded and decoded on the devices. */
+cds_status cds_maskset_add_tiff(cds_maskset *ms, const uint8_t *blob, const int64_t *offsets, int32_t n, int32_t *mask_size_out /* [n], may be NULL */);
+cds_status cds_library_add_tiff(cds_library *lib, const uint8_t *blob, const int64_t *offsets, int64_t n, int64_t *first_index);
+
+/* cds_search_stream_rgb / cds_search_stream_matches_rgb for targets that are TIFF files in host memory (same results as decoding
+ * them first): per chunk the host parses the tags, the copy stream uploads the files' bytes as they are, and the compute stream
+ * decodes, encodes and matches them.  Pinned memory (cds_host_alloc) for `blob` gives full PCIe rate. */
+cds_status cds_search_stream_tiff(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *blob, const int64_t *offsets, int64_t n_targets,
+                                  int32_t k, double pct_positive_pixels,
+                                  int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count);
+cds_status cds_search_stream_matches_tiff(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *blob, const int64_t *offsets, int64_t n_targets,
+                                          double pct_positive_pixels, int64_t capacity,
+                                          int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored,
+                                          int64_t *out_count);
 
 /* One mask x one target held in host memory: the literal single-pair call of the Java API
  * (ColorDepthSearchAlgorithm.calculateMatchingScore, API/cds/ColorDepthSearchAlgorithm.java:60-61). */

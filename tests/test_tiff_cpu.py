@@ -1,0 +1,104 @@
+"""Image ingest, CPU side: the oracle's TIFF / PackBits restatement against the reference's own fixtures,
+and the host-only entry points of the C ABI (tag parsing, TIFF writer)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from colormipsearch_b200 import capi
+from oracle import tiff as OT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def tiffs():
+    with np.load(os.path.join(ROOT, "tests", "golden", "tiff_fixtures.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+DECODABLE = ["pack1", "pack2", "stored1", "em_12191", "em_LPLC2", "lm_GMR"]
+
+
+@pytest.mark.parametrize("name", DECODABLE)
+def test_oracle_decodes_reference_fixtures(tiffs, name):
+    """packBitsUncompress / readImageArrayRangeWithTiffReader restated == the pixels ImageJ (here: Pillow) reads."""
+    got = OT.read_tiff_rgb(tiffs["file_" + name].tobytes())
+    assert np.array_equal(got, tiffs["pixels_" + name])
+
+
+def test_oracle_matches_cdsearch_fixtures(tiffs, fixtures):
+    """The colour-depth MIPs decoded here are the images every scoring test of the reference uses."""
+    assert np.array_equal(OT.read_tiff_rgb(tiffs["file_em_12191"].tobytes()), fixtures["em_12191"])
+    assert np.array_equal(OT.read_tiff_rgb(tiffs["file_em_LPLC2"].tobytes()), fixtures["em_LPLC2"])
+
+
+@pytest.mark.parametrize("name", ["pack1", "pack2"])
+def test_oracle_range_read_like_reference_test(tiffs, name):
+    """ImageArrayUtilsTest.readImageRangeForPackBits (:19-44): reading the range of the image's bounding rows gives the image's
+    pixels inside those rows and black outside."""
+    px = tiffs["pixels_" + name]
+    Hh, Ww = px.shape[:2]
+    nz = np.argwhere(px.any(axis=2))
+    miny, maxy = nz[:, 0].min(), nz[:, 0].max() + 1
+    minx, maxx = nz[:, 1].min(), nz[:, 1].max() + 1
+    got = OT.read_tiff_rgb(tiffs["file_" + name].tobytes(), int(miny) * Ww, int(maxy) * Ww + int(maxx))
+    assert np.array_equal(got[miny:maxy + 1], px[miny:maxy + 1])       # the test's `y <= boundaries[3]` rows
+    assert not got[:miny].any()
+    assert not got[maxy + 1:].any()
+
+
+def test_probe_reads_the_tags(tiffs):
+    info = capi.tiff_probe(tiffs["file_em_12191"].tobytes())
+    assert (info["width"], info["height"], info["compression"], info["rows_per_strip"], info["n_strips"]) == (1210, 566, 32773, 8, 71)
+    assert info["big_endian"] == 1 and info["decodable"] == 1 and info["samples_per_pixel"] == 3
+    info = capi.tiff_probe(tiffs["file_pack1"].tobytes())
+    assert (info["width"], info["height"], info["compression"], info["n_strips"], info["big_endian"]) == (256, 256, 32773, 1, 0)
+    info = capi.tiff_probe(tiffs["file_lzw1"].tobytes())
+    assert info["compression"] == 5 and info["decodable"] == 0
+    info = capi.tiff_probe(tiffs["file_stored1"].tobytes())
+    assert info["compression"] == 1 and info["decodable"] == 1 and info["data_bytes"] == 256 * 256 * 3
+    # the oracle's tag reader agrees
+    for name in DECODABLE + ["lzw1"]:
+        a = capi.tiff_probe(tiffs["file_" + name].tobytes())
+        b = OT.tiff_info(tiffs["file_" + name].tobytes())
+        assert (a["width"], a["height"], a["compression"], a["n_strips"]) == (b["width"], b["height"], b["compression"], len(b["strip_offsets"]))
+        assert a["data_bytes"] == sum(b["strip_lengths"])
+
+
+def test_probe_rejects_what_is_not_a_tiff(tiffs):
+    for bad in (b"", b"II", b"XX*\0\0\0\0\0", b"II+\0\x08\0\0\0\0\0\0\0", b"II*\0\xff\xff\xff\x7f"):
+        with pytest.raises(capi.CdsError):
+            capi.tiff_probe(bad)
+    # a directory that runs past the end of the file
+    data = bytearray(tiffs["file_pack1"].tobytes())
+    (ifd,) = struct.unpack("<I", data[4:8])
+    with pytest.raises(capi.CdsError):
+        capi.tiff_probe(bytes(data[:ifd + 20]))
+
+
+@pytest.mark.parametrize("rows_per_strip,compression", [(8, 32773), (1, 32773), (566, 32773), (7, 32773), (8, 1), (0, 1)])
+def test_writer_round_trips_through_the_oracle(rows_per_strip, compression):
+    rng = np.random.default_rng(rows_per_strip * 7 + compression)
+    W, H = 301, 57
+    img = np.zeros((H, W, 3), np.uint8)
+    img[5:30, 40:200] = rng.integers(0, 256, (25, 160, 3))
+    img[33:35, :] = 9                       # long runs, longer than 128 bytes
+    img[40, 10:12] = 200                    # runs of two
+    img[41, 0:130] = rng.integers(0, 2, (130, 1)) * 255   # short runs of a three-byte pattern
+    data = capi.tiff_encode_rgb(img, rows_per_strip, compression)
+    info = capi.tiff_probe(data)
+    rps = rows_per_strip if 0 < rows_per_strip <= H else H
+    assert info["decodable"] == 1 and info["n_strips"] == -(-H // rps) and info["compression"] == compression
+    assert np.array_equal(OT.read_tiff_rgb(data), img)
+    if compression == 32773:
+        assert len(data) < img.size // 2
+
+
+def test_writer_worst_case_fits_the_bound():
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (33, 129, 3)).astype(np.uint8)       # incompressible
+    data = capi.tiff_encode_rgb(img, 4, 32773)
+    assert np.array_equal(OT.read_tiff_rgb(data), img)
+    assert len(data) <= capi.lib().cds_tiff_encode_bound(129, 33, 4)

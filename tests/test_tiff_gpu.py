@@ -1,0 +1,190 @@
+"""Image ingest on the device: TIFF strips decoded by tiff_decode_kernel == the oracle's restatement of the
+reference's reader, and searches over TIFF files == searches over the decoded pixels."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from colormipsearch_b200 import capi
+from oracle import oracle as O
+from oracle import tiff as OT
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+W, H = 1210, 566
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(n_dev=1)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def tiffs():
+    with np.load(os.path.join(ROOT, "tests", "golden", "tiff_fixtures.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("name", ["pack1", "pack2", "stored1", "em_12191", "em_LPLC2", "lm_GMR"])
+def test_device_decode_of_reference_fixtures(ctx, tiffs, name):
+    px = tiffs["pixels_" + name]
+    got = capi.tiff_decode_rgb(ctx, [tiffs["file_" + name].tobytes()], px.shape[1], px.shape[0])
+    assert np.array_equal(got[0], px)
+    assert np.array_equal(got[0], OT.read_tiff_rgb(tiffs["file_" + name].tobytes()))
+
+
+def test_device_decode_batch_and_layouts(ctx):
+    """Many files per call (more than one internal chunk), every strip layout the writer can produce, both compressions."""
+    rng = np.random.default_rng(11)
+    w, h = 333, 61
+    files, imgs = [], []
+    for i in range(150):
+        img = np.zeros((h, w, 3), np.uint8)
+        y0, x0 = rng.integers(0, h - 20), rng.integers(0, w - 90)
+        img[y0:y0 + 20, x0:x0 + 90] = rng.integers(0, 256, (20, 90, 3))
+        img[rng.integers(0, h)] = rng.integers(0, 256)
+        imgs.append(img)
+        files.append(capi.tiff_encode_rgb(img, [1, 3, 8, 61, 0][i % 5], 32773 if i % 7 else 1))
+    got = capi.tiff_decode_rgb(ctx, files, w, h)
+    assert np.array_equal(got, np.stack(imgs))
+    for i in (0, 6, 7, 149):
+        assert np.array_equal(got[i], OT.read_tiff_rgb(files[i]))
+    assert capi.tiff_decode_rgb(ctx, [], w, h).shape == (0, h, w, 3)
+
+
+def test_device_decode_errors(ctx, tiffs):
+    with pytest.raises(capi.CdsError) as e:                       # LZW goes to ImageJ in the reference; not decodable here
+        capi.tiff_decode_rgb(ctx, [tiffs["file_lzw1"].tobytes()], 256, 256)
+    assert e.value.status == capi.CDS_ERR_UNSUPPORTED and "compression 5" in str(e.value)
+    with pytest.raises(capi.CdsIllegalArgument) as e:             # wrong image size
+        capi.tiff_decode_rgb(ctx, [tiffs["file_pack1"].tobytes()], 1210, 566)
+    assert e.value.status == capi.CDS_ERR_SIZE_MISMATCH
+    with pytest.raises(capi.CdsIllegalArgument):                  # not a TIFF
+        capi.tiff_decode_rgb(ctx, [b"not a tiff at all"], 256, 256)
+    good = tiffs["file_pack1"].tobytes()
+    with pytest.raises(capi.CdsError) as e:                       # the second file is bad: the message names it
+        capi.tiff_decode_rgb(ctx, [good, good[:100]], 256, 256)
+    assert "file 1" in str(e.value)
+
+
+def test_truncated_strip_leaves_zeros(ctx, tiffs):
+    """A strip whose byte count stops early decodes as far as it goes; the rest of the image stays black, like the
+    zero-initialised array of the reference (ImageArrayUtils.java:198) -- checked against the oracle's run decoder."""
+    data = bytearray(tiffs["file_pack1"].tobytes())
+    info = OT.tiff_info(bytes(data))
+    (ifd,) = struct.unpack("<I", data[4:8])
+    (n,) = struct.unpack("<H", data[ifd:ifd + 2])
+    full = info["strip_lengths"][0]
+    # cut at a run boundary so that the reference's decoder ends cleanly too
+    strip = bytes(data[info["strip_offsets"][0]:info["strip_offsets"][0] + full])
+    idx, cut = 0, 0
+    while idx < full // 2:
+        c = strip[idx]
+        idx += (c + 2) if c < 128 else (2 if c != 128 else 1)
+        cut = idx
+    for i in range(n):
+        at = ifd + 2 + 12 * i
+        tag, typ, count = struct.unpack("<HHI", data[at:at + 8])
+        if tag == 279:
+            assert count == 1
+            data[at + 8:at + 12] = struct.pack("<I", cut) if typ == 4 else struct.pack("<HH", cut, 0)
+    exp = OT.read_tiff_rgb(bytes(data))
+    got = capi.tiff_decode_rgb(ctx, [bytes(data)], 256, 256)[0]
+    assert np.array_equal(got, exp)
+    assert exp.any() and not exp[-1].any()
+
+
+@pytest.fixture(scope="module")
+def synth_files(ctx):
+    masks = capi.synth_rgb_host(0, 0xC0FFEE, 0, 24, W, H)
+    targets = capi.synth_rgb_host(1, 0xC0FFEE, 0, 70, W, H)
+    files = [capi.tiff_encode_rgb(t, 8 if i % 3 else 566, 32773 if i % 5 else 1) for i, t in enumerate(targets)]
+    return masks, targets, files
+
+
+@pytest.mark.parametrize("chunk", [256, 16, 7])
+def test_stream_search_over_tiff_files_equals_rgb(ctx, synth_files, chunk):
+    masks, targets, files = synth_files
+    rects = O.label_rects(W, H)
+    ctx.set_option("stream_chunk", chunk)
+    ctx.set_option("stream_chunk_tiff", chunk)
+    try:
+        for n_masks, k, pct in ((24, 300, 0.0), (24, 5, 1.0), (3, 9, 0.0)):
+            ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+            ms.add_rgb(masks[:n_masks])
+            exp = ms.search_stream(targets, k, pct)
+            got = ms.search_stream_tiff(files, k, pct)
+            st = ctx.last_stats()
+            assert np.array_equal(got[3], exp[3])
+            for m in range(n_masks):
+                c = exp[3][m]
+                for a, b in zip(got[:3], exp[:3]):
+                    assert np.array_equal(a[m, :c], b[m, :c]), (chunk, n_masks, k, m)
+            assert st["h2d_bytes"] < targets.nbytes                # the files crossed PCIe, not the pixels
+            em = ms.search_stream_matches(targets, pct)
+            gm = ms.search_stream_matches_tiff(files, pct)
+            for a, b in zip(gm, em):
+                assert np.array_equal(a, b)
+            s, t, mir, cnt = ms.search_stream_tiff([], 4, 0.0)
+            assert cnt.tolist() == [0] * n_masks
+            ms.close()
+    finally:
+        ctx.set_option("stream_chunk", 256)
+        ctx.set_option("stream_chunk_tiff", 1024)
+
+
+def test_stream_search_reports_the_bad_file(ctx, synth_files, tiffs):
+    masks, targets, files = synth_files
+    ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, O.label_rects(W, H))
+    ms.add_rgb(masks[:3])
+    bad = list(files[:20]) + [tiffs["file_pack1"].tobytes()] + list(files[20:30])
+    with pytest.raises(capi.CdsIllegalArgument) as e:
+        ms.search_stream_tiff(bad, 4, 0.0)
+    assert "file 20" in str(e.value)
+    # the context is still usable afterwards
+    got = ms.search_stream_tiff(files[:10], 4, 0.0)
+    exp = ms.search_stream(targets[:10], 4, 0.0)
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b)
+    ms.close()
+
+
+def test_library_from_tiff_files(ctx, synth_files):
+    masks, targets, files = synth_files
+    rects = O.label_rects(W, H)
+    lib_rgb = capi.Library(ctx, W, H, 80)
+    lib_rgb.add_rgb(targets)
+    lib_tif = capi.Library(ctx, W, H, 80)
+    assert lib_tif.add_tiff(files[:10]) == 0
+    assert lib_tif.add_tiff(files[10:]) == 10                    # appends continue inside a block of 64
+    assert len(lib_tif) == len(lib_rgb) == 70
+    ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    ms.add_rgb(masks)
+    a, am = ms.search_dense(lib_rgb)
+    b, bm = ms.search_dense(lib_tif)
+    assert np.array_equal(a, b) and np.array_equal(am, bm)
+    ms.close(); lib_rgb.close(); lib_tif.close()
+
+
+def test_masks_from_tiff_files(ctx, synth_files, tiffs, fixtures):
+    """cds_maskset_add_tiff == cds_maskset_add_rgb of the decoded pixels; the reference's own EM mask file gives the mask size
+    the reference's tests pin (PixelMatchColorDepthSearchAlgorithmTest: 12191_JRC2018U, threshold 20)."""
+    masks, targets, files = synth_files
+    rects = O.label_rects(W, H)
+    mfiles = [capi.tiff_encode_rgb(m, 8, 32773) for m in masks] + [tiffs["file_em_12191"].tobytes()]
+    mrgb = np.concatenate([masks, fixtures["em_12191"][None]])
+    a = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    b = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    sa = a.add_rgb(mrgb)
+    sb = b.add_tiff(mfiles[:5])
+    sb = np.concatenate([sb, b.add_tiff(mfiles[5:])])
+    assert np.array_equal(sa, sb)
+    ra = a.search_stream(targets, 10, 0.0)
+    rb = b.search_stream_tiff(files, 10, 0.0)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    a.close(); b.close()
