@@ -399,6 +399,62 @@ public:
         cds_maskset_destroy(ms);
         return out;
     }
+
+    // The same search for masks and targets that are TIFF FILES (the bytes as stored: PackBits or uncompressed RGB): nothing is
+    // decoded on the host, the files are uploaded as they are and decoded on the devices (cds_maskset_add_tiff,
+    // cds_search_stream_matches_tiff / cds_search_stream_tiff).  Replaces NeuronMIPUtils.loadComputeFile + ImageArrayUtils.readImageArray
+    // (colormipsearch-api/.../mips/NeuronMIPUtils.java:62-103, imageprocessing/ImageArrayUtils.java:98-258) in front of the search.
+    std::vector<CDMatch> findAllColorDepthMatchesInFiles(int width, int height, const std::vector<std::vector<uint8_t>> &maskFiles,
+                                                         const std::vector<std::vector<uint8_t>> &targetFiles, int maxPerMask)
+    {
+        std::vector<CDMatch> out;
+        if (maskFiles.empty() || targetFiles.empty()) return out;
+        auto pack = [](const std::vector<std::vector<uint8_t>> &files, std::vector<uint8_t> &blob, std::vector<int64_t> &offsets) {
+            offsets.assign(1, 0);
+            for (const auto &f : files) offsets.push_back(offsets.back() + (int64_t) f.size());
+            blob.resize((size_t) offsets.back() + 64);
+            for (size_t i = 0; i < files.size(); i++) std::copy(files[i].begin(), files[i].end(), blob.begin() + offsets[i]);
+        };
+        std::vector<uint8_t> mblob, tblob;
+        std::vector<int64_t> moff, toff;
+        pack(maskFiles, mblob, moff);
+        pack(targetFiles, tblob, toff);
+        cds_maskset *ms = nullptr;
+        GpuContext::check(cds_maskset_create(gpu_->get(), width, height, &params_, &ms), gpu_->get());
+        try {
+            std::vector<int32_t> sizes(maskFiles.size());
+            GpuContext::check(cds_maskset_add_tiff(ms, mblob.data(), moff.data(), (int32_t) maskFiles.size(), sizes.data()), gpu_->get());
+            const int64_t T = (int64_t) targetFiles.size();
+            if (maxPerMask <= 0) {
+                int64_t cap = std::max<int64_t>(1024, 4 * (int64_t) maskFiles.size()), n = 0;
+                std::vector<int32_t> mk, sc; std::vector<int64_t> tg; std::vector<uint8_t> mir;
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    mk.resize(cap); sc.resize(cap); tg.resize(cap); mir.resize(cap);
+                    cds_status st = cds_search_stream_matches_tiff(gpu_->get(), ms, tblob.data(), toff.data(), T, pctPositivePixels_, cap,
+                                                                   mk.data(), tg.data(), sc.data(), mir.data(), &n);
+                    if (st == CDS_ERR_CAPACITY && attempt == 0) { cap = n; continue; }
+                    GpuContext::check(st, gpu_->get());
+                    break;
+                }
+                for (int64_t i = 0; i < n; i++)
+                    out.push_back({mk[i], tg[i], sc[i], (float) ((double) sc[i] / (double) sizes[mk[i]]), mir[i] != 0});
+            } else {
+                const int K = std::max(1, std::min<int>(maxPerMask, (int) T));
+                std::vector<int32_t> score(maskFiles.size() * K), count(maskFiles.size());
+                std::vector<int64_t> target(maskFiles.size() * K);
+                std::vector<uint8_t> mir(maskFiles.size() * K);
+                GpuContext::check(cds_search_stream_tiff(gpu_->get(), ms, tblob.data(), toff.data(), T, K, pctPositivePixels_,
+                                                         score.data(), target.data(), mir.data(), count.data()), gpu_->get());
+                for (size_t m = 0; m < maskFiles.size(); m++)
+                    for (int i = 0; i < count[m]; i++) {
+                        const size_t o = m * K + i;
+                        out.push_back({(int) m, target[o], score[o], (float) ((double) score[o] / (double) sizes[m]), mir[o] != 0});
+                    }
+            }
+        } catch (...) { cds_maskset_destroy(ms); throw; }
+        cds_maskset_destroy(ms);
+        return out;
+    }
 };
 
 }  // namespace colormipsearch

@@ -23,6 +23,9 @@ import org.janelia.colormipsearch.model.ProcessingType;
  * native search -- the same seam --use-spark already uses (ColorDepthSearchCmd.java:279-295).  Masks are prepared once on the
  * device; targets are decoded by the JVM (as today, through CachedMIPsUtils) into a pinned staging buffer and streamed to the
  * GPUs; only matches that pass ColorMIPSearch.isMatch come back (LocalColorMIPSearchProcessor.java:93-105 keeps exactly those).
+ * With -Dcdsgpu.ingest=tiff and targets that are plain .tif files the JVM does not decode at all: the files' bytes go into the
+ * pinned buffer as stored and cds_search_stream_*_tiff decodes them on the device (PackBits or uncompressed RGB; anything else
+ * makes the native call return CDS_ERR_UNSUPPORTED and the processor falls back to the decoded path).
  * UNVERIFIED (no JDK in the build image of the GPU library).
  */
 public class GpuColorMIPSearchProcessor<M extends AbstractNeuronEntity, T extends AbstractNeuronEntity> implements ColorMIPSearchProcessor<M, T> {
@@ -72,6 +75,10 @@ public class GpuColorMIPSearchProcessor<M extends AbstractNeuronEntity, T extend
                 CdsGpu.check((int) CdsGpu.masksetAddRgb.invokeExact(ms, CdsGpu.copyBytes(a, ImageArrayAccess.rgbBytes(masks.get(i).getImageArray())), 1, size));
                 maskSizes[i] = size.get(ValueLayout.JAVA_INT, 0);
             }
+            if ("tiff".equals(System.getProperty("cdsgpu.ingest")) && searchTiffFiles(a, ctx, ms, masks, targetMIPs, maskSizes, k, results)) {
+                CdsGpu.masksetDestroy.invokeExact(ms);
+                return results;
+            }
             // targets: one pinned buffer, filled by the JVM's decoders, streamed by the library (H2D of chunk i+1 overlaps the search of chunk i)
             CdsGpu.check((int) CdsGpu.hostAlloc.invokeExact(ctx, imgBytes * targets.size(), out));
             MemorySegment pinned = out.get(ValueLayout.ADDRESS, 0).reinterpret(imgBytes * targets.size());
@@ -109,6 +116,79 @@ public class GpuColorMIPSearchProcessor<M extends AbstractNeuronEntity, T extend
             CdsGpu.masksetDestroy.invokeExact(ms);
         } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
         return results;
+    }
+
+    /**
+     * Targets as TIFF files: raw bytes -> pinned blob -> cds_search_stream_matches_tiff / cds_search_stream_tiff.  Returns false
+     * (nothing added to `results`) when a target is not a plain .tif file or the library cannot decode one of them.
+     */
+    private boolean searchTiffFiles(Arena a, MemorySegment ctx, MemorySegment ms, List<NeuronMIP<M>> masks, List<T> targetMIPs, int[] maskSizes,
+                                    int k, List<CDMatchEntity<M, T>> results) throws Throwable {
+        List<T> kept = new ArrayList<>();
+        List<java.nio.file.Path> paths = new ArrayList<>();
+        long total = 0;
+        for (T t : targetMIPs) {
+            org.janelia.colormipsearch.model.FileData fd = t.getComputeFileData(ComputeFileType.InputColorDepthImage);
+            if (fd == null) continue;
+            String name = fd.getFileName() == null ? "" : fd.getFileName().toLowerCase();
+            if (fd.getDataType() != org.janelia.colormipsearch.model.FileData.FileDataType.file || !(name.endsWith(".tif") || name.endsWith(".tiff"))) return false;
+            java.nio.file.Path p = java.nio.file.Paths.get(fd.getFileName());
+            kept.add(t); paths.add(p);
+            total += java.nio.file.Files.size(p);
+        }
+        if (kept.isEmpty()) return true;
+        MemorySegment out = a.allocate(ValueLayout.ADDRESS);
+        CdsGpu.check((int) CdsGpu.hostAlloc.invokeExact(ctx, total + 64, out));
+        MemorySegment blob = out.get(ValueLayout.ADDRESS, 0).reinterpret(total + 64);
+        MemorySegment offsets = a.allocate(8L * (kept.size() + 1), 8);
+        long at = 0;
+        for (int i = 0; i < kept.size(); i++) {
+            offsets.set(ValueLayout.JAVA_LONG, 8L * i, at);
+            try (java.nio.channels.FileChannel ch = java.nio.channels.FileChannel.open(paths.get(i))) {
+                java.nio.ByteBuffer bb = blob.asSlice(at, ch.size()).asByteBuffer();
+                while (bb.hasRemaining() && ch.read(bb) >= 0) { }
+                at += ch.size();
+            }
+        }
+        offsets.set(ValueLayout.JAVA_LONG, 8L * kept.size(), at);
+        List<NeuronMIP<T>> targets = new ArrayList<>();
+        for (T t : kept) targets.add(new NeuronMIP<>(t, t.getComputeFileData(ComputeFileType.InputColorDepthImage), null));
+        boolean done = true;
+        if (maxMatchesPerMask <= 0) {
+            long cap = Math.max(1024L, 4L * masks.size());
+            MemorySegment count = a.allocate(ValueLayout.JAVA_LONG);
+            for (int attempt = 0; ; attempt++) {
+                MemorySegment mk = a.allocate(4 * cap, 4), tg = a.allocate(8 * cap, 8), sc = a.allocate(4 * cap, 4), mir = a.allocate(cap);
+                int st = (int) CdsGpu.searchStreamMatchesTiff.invokeExact(ctx, ms, blob, offsets, (long) kept.size(), pctPositivePixels, cap, mk, tg, sc, mir, count);
+                long n = count.get(ValueLayout.JAVA_LONG, 0);
+                if (st == CdsGpu.CDS_ERR_CAPACITY && attempt == 0) { cap = n; continue; }
+                if (st == CdsGpu.CDS_ERR_UNSUPPORTED) { done = false; break; }
+                CdsGpu.check(st);
+                for (long i = 0; i < n; i++)
+                    results.add(newMatch(masks, targets, maskSizes, mk.get(ValueLayout.JAVA_INT, 4 * i), (int) tg.get(ValueLayout.JAVA_LONG, 8 * i),
+                            sc.get(ValueLayout.JAVA_INT, 4 * i), mir.get(ValueLayout.JAVA_BYTE, i) != 0));
+                break;
+            }
+        } else {
+            int kk = Math.min(k, kept.size());
+            MemorySegment score = a.allocate(4L * masks.size() * kk, 4), target = a.allocate(8L * masks.size() * kk, 8);
+            MemorySegment mirrored = a.allocate((long) masks.size() * kk), count = a.allocate(4L * masks.size(), 4);
+            int st = (int) CdsGpu.searchStreamTiff.invokeExact(ctx, ms, blob, offsets, (long) kept.size(), kk, pctPositivePixels, score, target, mirrored, count);
+            if (st == CdsGpu.CDS_ERR_UNSUPPORTED) done = false;
+            else {
+                CdsGpu.check(st);
+                for (int m = 0; m < masks.size(); m++) {
+                    int n = count.get(ValueLayout.JAVA_INT, 4L * m);
+                    for (int i = 0; i < n; i++) {
+                        long o = (long) m * kk + i;
+                        results.add(newMatch(masks, targets, maskSizes, m, (int) target.get(ValueLayout.JAVA_LONG, 8 * o),
+                                score.get(ValueLayout.JAVA_INT, 4 * o), mirrored.get(ValueLayout.JAVA_BYTE, o) != 0));
+                    }
+                }
+            }
+        }
+        CdsGpu.check((int) CdsGpu.hostFree.invokeExact(ctx, blob));
+        return done;
     }
 
     @SuppressWarnings("unchecked")

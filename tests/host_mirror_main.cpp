@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <sstream>
 
 #include "../colormipsearch_b200/host/cds_host.hpp"
@@ -75,6 +76,23 @@ int main(int argc, char **argv)
             auto every = proc.findAllColorDepthMatches({&em1, &em2}, {&lmA, &lmB, &lmC}, 0);      // no limit: every isMatch pair
             for (const CDMatch &m : every)
                 std::printf("allpairs mask %d target %lld pixels %d mirrored %d\n", m.maskIndex, m.targetIndex, m.matchingPixels, m.mirrored ? 1 : 0);
+        }
+
+        // ---- the same seam fed with TIFF files (no decode on the host): <name>.tif next to the raw images
+        {
+            auto slurp = [&](const std::string &name) {
+                std::ifstream f(dir + "/" + name, std::ios::binary);
+                if (!f) throw std::runtime_error("cannot read " + name);
+                return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            };
+            GpuColorMIPSearchProcessor proc(gpu, true, 20, 20, 1.0, 2, 1.0, textLabelRegions()(em1));
+            auto every = proc.findAllColorDepthMatchesInFiles(W, H, {slurp("em_12191.tif"), slurp("em_12191_FL.tif")},
+                                                              {slurp("lm_VT033614.tif"), slurp("lm_BJD.tif"), slurp("lm_VT016795.tif")}, 0);
+            for (const CDMatch &m : every)
+                std::printf("tiffpairs mask %d target %lld pixels %d mirrored %d\n", m.maskIndex, m.targetIndex, m.matchingPixels, m.mirrored ? 1 : 0);
+            auto best = proc.findAllColorDepthMatchesInFiles(W, H, {slurp("em_12191.tif")}, {slurp("lm_VT033614.tif"), slurp("lm_BJD.tif"), slurp("lm_VT016795.tif")}, 1);
+            for (const CDMatch &m : best)
+                std::printf("tiffbest mask %d target %lld pixels %d mirrored %d\n", m.maskIndex, m.targetIndex, m.matchingPixels, m.mirrored ? 1 : 0);
         }
 
         // ---- Shape2DMatchColorDepthSearchAlgorithmTest: provider(mirror), thr 20; zgap = the on-disk file for BJD

@@ -34,6 +34,12 @@ def test_reference_scenarios_through_the_cpp_mirror(tmp_path, fixtures):
     for k in ("em_12191", "em_12191_FL", "lm_VT033614", "lm_BJD", "lm_VT016795", "zgap_BJD"):
         np.ascontiguousarray(fixtures[k], np.uint8).tofile(tmp_path / (k + ".rgb"))
     np.ascontiguousarray(fixtures["grad_BJD"], np.uint16).tofile(tmp_path / "grad_BJD.g16")
+    # the same images as TIFF files: the reference's own PackBits file for the EM mask, our writer (PackBits / stored) for the rest
+    from colormipsearch_b200 import capi
+    with np.load(os.path.join(ROOT, "tests", "golden", "tiff_fixtures.npz")) as z:
+        (tmp_path / "em_12191.tif").write_bytes(z["file_em_12191"].tobytes())
+    for k, (rps, comp) in {"em_12191_FL": (566, 1), "lm_VT033614": (8, 32773), "lm_BJD": (1, 32773), "lm_VT016795": (566, 32773)}.items():
+        (tmp_path / (k + ".tif")).write_bytes(capi.tiff_encode_rgb(fixtures[k], rps, comp))
     out = subprocess.run([exe, str(tmp_path)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
     lines = {" ".join(ln.split()[:2]): ln.split()[2:] for ln in out}
     # PixelMatchColorDepthSearchAlgorithmTest.java:72-103
@@ -54,6 +60,10 @@ def test_reference_scenarios_through_the_cpp_mirror(tmp_path, fixtures):
     assert (1, 0, 515, 0) in got and (1, 2, 483, 0) in got
     every = [ln.split() for ln in out if ln.startswith("allpairs")]
     assert [(int(b[2]), int(b[4]), int(b[6]), int(b[8])) for b in every] == got       # 3 targets, K = 3: the same six pairs
+    tiffp = [ln.split() for ln in out if ln.startswith("tiffpairs")]
+    assert [(int(b[2]), int(b[4]), int(b[6]), int(b[8])) for b in tiffp] == got       # TIFF files in, the same pairs out
+    tiffb = [ln.split() for ln in out if ln.startswith("tiffbest")]
+    assert [(int(b[2]), int(b[4]), int(b[6]), int(b[8])) for b in tiffb] == [(0, 0, 439, 0)]
     # Shape2DMatchColorDepthSearchAlgorithmTest.java:53-54, 230-291
     assert lines["shape_masks 17340"][:1] == ["70640"] and lines["shape_masks 17340"][2] == "2"
     assert lines["shape 12191xBJD_zgapfile"] == ["33884", "523", "34058", "0"]
