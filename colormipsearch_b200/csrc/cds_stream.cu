@@ -210,7 +210,16 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             for (int d = 0; d < D; d++)
                 if (f < resident->local_size(d)) plan.push_back({d, f, std::min<int64_t>(chunk, resident->local_size(d) - f)});
     } else {
-        for (int64_t c = 0, f = 0; f < n_targets; c++, f += chunk) plan.push_back({(int) (c % D), f, std::min<int64_t>(chunk, n_targets - f)});
+        // TIFF files: the first chunks of every device are short (256, 512, ...) so that the match kernel starts early -- a full
+        // chunk of 1 024 files needs ~10 ms of parsing, upload, decode and encode before its first comparison
+        int64_t f = 0;
+        for (int64_t c = 0; f < n_targets; c++) {
+            int64_t want = chunk;
+            if (tiff) want = std::min<int64_t>(chunk, (int64_t) 256 << std::min<int64_t>(c / D, 8));
+            const int64_t cnt = std::min<int64_t>(want, n_targets - f);
+            plan.push_back({(int) (c % D), f, cnt});
+            f += cnt;
+        }
     }
     const int64_t n_chunks = (int64_t) plan.size();
     const int thr = ms->params.data_threshold;
