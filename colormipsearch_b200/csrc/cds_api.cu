@@ -792,7 +792,7 @@ cds_status cds_maskset::sync_descs()
         if (d_words[d]) { ds.pool.free(d_words[d]); d_words[d] = nullptr; }
         if (d_wstart[d]) { ds.pool.free(d_wstart[d]); d_wstart[d] = nullptr; }
         std::vector<PaletteGroup> groups(std::max(n_groups, 1));
-        for (auto &g : groups) { g.palette = nullptr; g.words = nullptr; g.gstart = nullptr; g.lpal = nullptr; g.n_pal = 0; g.pad = 0; }
+        for (auto &g : groups) { g.palette = nullptr; g.words = nullptr; g.gstart = nullptr; g.lpal = nullptr; g.tocc = nullptr; g.n_pal = 0; g.pad = 0; }
         if (compact_ok) {
             // palettes of the compact records: mark classes per group, number them, pack intervals, rewrite records
             const size_t slots = (size_t) n_groups * (CDS_NUM_CLASSES + 1);
@@ -874,20 +874,48 @@ cds_status cds_maskset::sync_descs()
             if (total[0] < ((uint64_t) 1 << 32) && total[1] < ((uint64_t) 1 << 32)) {
                 uint32_t *d_gstart = d_wstart[d] + 2 * ms_n, *d_bstart = d_gstart + gs_n;
                 // d_words: the entries, then the palette references
-                CDS_CUDA(ctx, ds.pool.alloc((void **) &d_words[d], std::max<uint64_t>(total[0], 1) * sizeof(uint4) + std::max<uint64_t>(total[1], 1) * sizeof(uint16_t)));
+                // d_words: the entries, the ticket bounds, then the palette references
+                const size_t n_tocc = words_tocc_count((uint32_t) total[0]);
+                CDS_CUDA(ctx, ds.pool.alloc((void **) &d_words[d], std::max<uint64_t>(total[0], 1) * sizeof(uint4) + n_tocc * sizeof(uint32_t) +
+                                                                       std::max<uint64_t>(total[1], 1) * sizeof(uint16_t)));
                 uint4 *d_entries = reinterpret_cast<uint4 *>(d_words[d]);
-                uint16_t *d_lpal = reinterpret_cast<uint16_t *>(d_entries + std::max<uint64_t>(total[0], 1));
+                uint32_t *d_tocc = reinterpret_cast<uint32_t *>(d_entries + std::max<uint64_t>(total[0], 1));
+                uint16_t *d_lpal = reinterpret_cast<uint16_t *>(d_tocc + n_tocc);
                 CDS_CUDA(ctx, cudaMemcpyAsync(d_gstart, grow.data(), 2 * gs_n * sizeof(uint32_t), cudaMemcpyHostToDevice, ds.stream));
                 for (int m = 0; m < M; m++) h[m].wstart = d_wcount + (size_t) m * (HT + 1);
                 for (int g = 0; g < n_groups; g++) {
                     groups[g].words = d_entries;
                     groups[g].gstart = d_gstart + (size_t) g * (HT + 1);
                     groups[g].lpal = d_lpal;
+                    groups[g].tocc = d_tocc;
                 }
                 CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
                 launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, class_tab, d_gstart, d_bstart, d_bcount, d_entries, d_lpal, ds.stream);
                 ctx->stats.kernel_launches++;
                 CDS_CUDA(ctx, cudaGetLastError());
+                {
+                    // bucket order inside every tile row (cds_cand.cuh): sort into a scratch copy, copy back
+                    uint4 *d_sorted = nullptr;
+                    uint32_t *d_tables = nullptr;
+                    const size_t tbl = (size_t) 2 * n_groups * words_bucket_count(W, H) * sizeof(uint32_t);
+                    cds_status st2 = ctx->check(ds.pool.alloc((void **) &d_sorted, std::max<uint64_t>(total[0], 1) * sizeof(uint4)), "cudaMalloc(sorted words)");
+                    if (st2 == CDS_OK) st2 = ctx->check(ds.pool.alloc((void **) &d_tables, tbl), "cudaMalloc(bucket tables)");
+                    if (st2 == CDS_OK) {
+                        launch_words_bucket_sort(d_entries, d_gstart, n_groups, W, H, d_tables, d_sorted, ds.stream);
+                        ctx->stats.kernel_launches += 3;
+                        st2 = ctx->check(cudaGetLastError(), "bucket sort kernels");
+                    }
+                    if (st2 == CDS_OK) st2 = ctx->check(cudaMemcpyAsync(d_entries, d_sorted, total[0] * sizeof(uint4), cudaMemcpyDeviceToDevice, ds.stream), "sorted words copy");
+                    if (st2 == CDS_OK) {
+                        launch_words_tocc(d_entries, (uint32_t) total[0], d_tocc, ds.stream);
+                        ctx->stats.kernel_launches++;
+                        st2 = ctx->check(cudaGetLastError(), "ticket bounds kernel");
+                    }
+                    cudaStreamSynchronize(ds.stream);
+                    ds.pool.free(d_sorted);
+                    ds.pool.free(d_tables);
+                    if (st2 != CDS_OK) return st2;
+                }
                 CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));      // `grow` is pageable memory
             } else {
                 all_words = false;

@@ -50,6 +50,7 @@ struct CandParams {
     const PaletteGroup *groups;
     int *acc;                       // [grid][GROUP][2 * offsets] match counters, zero between work items
     int debug_skip;                 // profiling aid (CDSGPU_CAND_NULL): consumers skip the tickets, only the band pipeline runs
+    int ticket_skip;                // the lists are in bucket order: a ticket whose occupancy words are all empty is not scanned
 };
 
 template <int NRINGS> struct Offsets;
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     int cur_gi = -1;
     const uint4 *gwords = nullptr;                   // word list of the current group
     const uint16_t *glpal = nullptr;                 // palette references of its entries' set bits
+    const uint32_t *gtocc = nullptr;                 // occupancy word of the first entry of every ticket of 32 entries
     uint2 *myq = s_queue + warp * kQueue;
     uint2 *mywq = s_wqueue + warp * kWordQueue;
     const uint32_t mywq_addr = smem_u32(mywq);
@@ -286,6 +288,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const PaletteGroup pg = p.groups[m0 / CDS_PALETTE_GROUP];
             gwords = pg.words;
             glpal = pg.lpal;
+            gtocc = pg.tocc;
             for (int i = tid; i < pg.n_pal; i += NCT) s_pal[i] = pg.palette[i];
             if (tid == 0) s_pal[CDS_PALETTE_SIZE - 1] = make_uint2(CDS_PAL_EMPTY_LO, CDS_PAL_EMPTY_LO);   // idle lanes point here
             consumer_barrier<NCT>();
@@ -384,46 +387,85 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 wpend_c = live ? qe.x : 0u; wpend_e = e; wpend = true;
             };
 
+            // Tickets.  Inside a tile row the entries are ordered by occupancy word (sector, tile column), so the 32 entries of
+            // a ticket (entries 32 j .. 32 j + 31 of the list) concern the contiguous run of occupancy words between the first
+            // entry of this ticket and the first entry of the next one (pg.tocc, one word per ticket).  On colour-depth MIPs
+            // ~97 % of the entries sit on tiles where the target has nothing in that sector, so a warp first TESTS 32 tickets,
+            // one per lane -- is any occupancy word of the ticket's run set? -- and then scans only the tickets that passed.
+            // Tickets are dealt out strided (lane i of batch b gets ticket b + i * n_batches): neighbouring tickets, which tend
+            // to pass or fail together, go to different warps.
+            const uint32_t band_lo = (uint32_t) ((y0 / 4) * rowpitch);
+            const uint32_t band_hi = (uint32_t) (((min(y0 + R, H) + 3) / 4) * rowpitch) - 1u;
+            const uint32_t sec_words = (uint32_t) (CDS_NUM_SECTORS * p.bpitch);
+            const uint32_t j_first = range.x >> 5;
+            const uint32_t n_tk = range.y > range.x ? ((range.y - 1u) >> 5) - j_first + 1u : 0u;
+            // a multiple of the number of consumer warps, so that every warp gets the same number of (partly filled) batches
+            const uint32_t n_batches = (uint32_t) NCW * ((n_tk + 32u * NCW - 1u) / (32u * NCW));
+            const uint2 idle = make_uint2(0u, band_lo);
+            auto scan_one = [&](uint2 w, uint32_t entry) {
+                const uint32_t c = w.x & bits_y0[w.y];                  // mask pixels of this word that can match
+                // words with candidates are compacted first, so that the bit expansion runs on full warps
+                const unsigned has = __ballot_sync(0xffffffffu, c != 0);
+                if (c) {
+                    const uint32_t slot = (wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1);
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(mywq_addr + slot * 8u), "r"(c), "r"(entry) : "memory");
+                }
+                wt += (uint32_t) __popc(has);
+                if (wt - wh >= 32) {
+                    __syncwarp();
+                    const uint2 qe = mywq[(wh + lane) & (kWordQueue - 1)];
+                    wh += 32;
+                    submit_words(qe, true);
+                }
+            };
+            auto load = [&](uint32_t jt) -> uint2 {                     // this lane's entry of ticket jt: {bits, occupancy word index}
+                const uint32_t i = (jt << 5) + (uint32_t) lane;
+                uint2 w = idle;
+                if (i >= range.x && i < range.y) w = __ldg(reinterpret_cast<const uint2 *>(gwords + i));
+                return w;
+            };
             for (;;) {
-                int tk = 0;
-                if (lane == 0) tk = atomicAdd(&s_next[stage], 1);
-                tk = __shfl_sync(0xffffffffu, tk, 0);
-                if (tk >= n_tickets || p.debug_skip) break;
-                // a ticket = kChunk consecutive entries of the group's word list; entries carry their mask's index
-                const uint32_t seg0 = range.x + (uint32_t) tk * kChunk;
-                const uint32_t seg1 = min(seg0 + kChunk, range.y);
-                // The scan reads only the first 8 bytes {bits, occupancy word index} of the 16-byte entries, three iterations
-                // ahead; lanes past the end carry an empty word on a valid address.
-                const uint4 *wl = gwords;
-                const uint2 idle = make_uint2(0u, (uint32_t) ((y0 / 4) * rowpitch));
-                auto load = [&](uint32_t i) -> uint2 {
-                    uint2 w = idle;
-                    if (i < seg1) w = __ldg(reinterpret_cast<const uint2 *>(wl + i));
-                    return w;
-                };
-                auto scan_one = [&](uint2 w, uint32_t entry) {
-                    const uint32_t c = w.x & bits_y0[w.y];                  // mask pixels of this word that can match
-                    // words with candidates are compacted first, so that the bit peeling runs on full warps
-                    const unsigned has = __ballot_sync(0xffffffffu, c != 0);
-                    if (c) {
-                        const uint32_t slot = (wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1);
-                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(mywq_addr + slot * 8u), "r"(c), "r"(entry) : "memory");
+                uint32_t bt = 0;
+                if (lane == 0) bt = (uint32_t) atomicAdd(&s_next[stage], 1);
+                bt = __shfl_sync(0xffffffffu, bt, 0);
+                if (bt >= n_batches || p.debug_skip) break;
+                const uint32_t k = bt + (uint32_t) lane * n_batches;
+                const uint32_t jt = j_first + k;
+                bool pass = false;
+                if (k < n_tk) {
+                    // tickets cut by the band's ends take the band's bound (their neighbours belong to other tile rows)
+                    uint32_t o_lo = band_lo, o_hi = band_hi;
+                    if ((jt << 5) >= range.x) o_lo = max(band_lo, __ldg(gtocc + jt));
+                    if (((jt + 1u) << 5) < range.y) o_hi = min(band_hi, __ldg(gtocc + jt + 1u));
+                    if (!p.ticket_skip || o_hi - o_lo > 95u) {
+                        pass = true;                                    // a long run (few mask pixels there): not worth the test
+                    } else {
+                        uint32_t r = o_lo % (uint32_t) rowpitch;        // position inside the tile row: the OR-of-sectors part is left out
+                        for (uint32_t o = o_lo; o <= o_hi; o++) {
+                            pass |= r < sec_words && bits_y0[o] != 0u;
+                            if (++r == (uint32_t) rowpitch) r = 0;
+                        }
                     }
-                    wt += (uint32_t) __popc(has);
-                    if (wt - wh >= 32) {
-                        __syncwarp();
-                        const uint2 qe = mywq[(wh + lane) & (kWordQueue - 1)];
-                        wh += 32;
-                        submit_words(qe, true);
+                }
+                unsigned live = __ballot_sync(0xffffffffu, pass);
+                if (!live) continue;
+                // scan the tickets that passed; the next one's entries are requested before the current one is used
+                int src = __ffs((int) live) - 1;
+                live &= live - 1;
+                uint32_t jc = __shfl_sync(0xffffffffu, jt, src);
+                uint2 wn = load(jc);
+                for (;;) {
+                    const uint2 w = wn;
+                    const uint32_t entry = (jc << 5) + (uint32_t) lane;
+                    const bool more = live != 0;
+                    if (more) {
+                        src = __ffs((int) live) - 1;
+                        live &= live - 1;
+                        jc = __shfl_sync(0xffffffffu, jt, src);
+                        wn = load(jc);
                     }
-                };
-                uint2 w0 = load(seg0 + lane), w1 = load(seg0 + 32 + lane), w2 = load(seg0 + 64 + lane);
-                for (uint32_t base = seg0; base < seg1; base += 32) {
-                    const uint2 w = w0;
-                    w0 = w1;
-                    w1 = w2;
-                    w2 = load(base + 96 + lane);
-                    scan_one(w, base + lane);
+                    scan_one(w, entry);
+                    if (!more) break;
                 }
             }
             // the band's last, partly filled batches: everything queued reads this stage, so it is evaluated before the release
@@ -520,6 +562,8 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     p.occ = occ; p.bpitch = bpitch; p.groups = groups;
     static const int debug_skip = env_int("CDSGPU_CAND_NULL", 0);
     p.debug_skip = debug_skip;
+    static const int no_skip = env_int("CDSGPU_CAND_NOSKIP", 0);
+    p.ticket_skip = no_skip ? 0 : 1;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     long long n_items = (long long) p.n_groups * n_targets;
@@ -676,7 +720,85 @@ __global__ void __launch_bounds__(32) words_fill_kernel(const MaskDesc *__restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Bucket order.  words_fill_kernel writes a tile row's entries mask by mask; the kernel wants them ordered by occupancy word
+// (sector, tile column) so that the entries that meet one target tile are neighbours and whole tickets can be skipped.
+// A counting sort per group over the occupancy word index: count, exclusive scan, scatter (the order inside a bucket is
+// whatever the atomics give -- scores are sums, they do not depend on it).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) words_bucket_count_kernel(const uint4 *__restrict__ words, const uint32_t *__restrict__ gstart, int HT,
+                                                                 uint32_t n_buckets, uint32_t *__restrict__ counts)
+{
+    const int g = blockIdx.y;
+    const uint32_t e0 = gstart[(size_t) g * (HT + 1)], e1 = gstart[(size_t) g * (HT + 1) + HT];
+    for (uint32_t i = e0 + blockIdx.x * blockDim.x + threadIdx.x; i < e1; i += gridDim.x * blockDim.x)
+        atomicAdd(&counts[(size_t) g * n_buckets + words[i].y], 1u);
+}
+
+// one CTA per group: counts -> first entry of every bucket (absolute index), in place
+__global__ void __launch_bounds__(1024) words_bucket_scan_kernel(uint32_t *__restrict__ counts, const uint32_t *__restrict__ gstart, int HT, uint32_t n_buckets)
+{
+    __shared__ uint32_t s_sum[1024];
+    const int g = blockIdx.x;
+    uint32_t *c = counts + (size_t) g * n_buckets;
+    const uint32_t per = (n_buckets + 1023u) / 1024u;
+    const uint32_t b0 = min(threadIdx.x * per, n_buckets), b1 = min(b0 + per, n_buckets);
+    uint32_t sum = 0;
+    for (uint32_t b = b0; b < b1; b++) sum += c[b];
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const uint32_t v = threadIdx.x >= (unsigned) d ? s_sum[threadIdx.x - d] : 0u;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t acc = gstart[(size_t) g * (HT + 1)] + s_sum[threadIdx.x] - sum;
+    for (uint32_t b = b0; b < b1; b++) { const uint32_t n = c[b]; c[b] = acc; acc += n; }
+}
+
+__global__ void __launch_bounds__(256) words_bucket_scatter_kernel(const uint4 *__restrict__ words, const uint32_t *__restrict__ gstart, int HT,
+                                                                   uint32_t n_buckets, const uint32_t *__restrict__ first, uint32_t *__restrict__ cursor,
+                                                                   uint4 *__restrict__ sorted)
+{
+    const int g = blockIdx.y;
+    const uint32_t e0 = gstart[(size_t) g * (HT + 1)], e1 = gstart[(size_t) g * (HT + 1) + HT];
+    for (uint32_t i = e0 + blockIdx.x * blockDim.x + threadIdx.x; i < e1; i += gridDim.x * blockDim.x) {
+        const uint4 e = words[i];
+        const size_t b = (size_t) g * n_buckets + e.y;
+        sorted[first[b] + atomicAdd(&cursor[b], 1u)] = e;
+    }
+}
+
+// tocc[j] = occupancy word of entry 32 j (of the last entry beyond the end): the bounds of the tickets' occupancy runs
+__global__ void __launch_bounds__(256) words_tocc_kernel(const uint4 *__restrict__ words, uint32_t n_entries, uint32_t n_tocc, uint32_t *__restrict__ tocc)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_tocc) return;
+    tocc[j] = n_entries ? words[min(j << 5, n_entries - 1u)].y : 0u;
+}
+
 }  // namespace
+
+void launch_words_tocc(const uint4 *words, uint32_t n_entries, uint32_t *tocc, cudaStream_t s)
+{
+    const uint32_t n = words_tocc_count(n_entries);
+    words_tocc_kernel<<<(n + 255) / 256, 256, 0, s>>>(words, n_entries, n, tocc);
+}
+
+void launch_words_bucket_sort(const uint4 *words, const uint32_t *gstart, int n_groups, int W, int H, uint32_t *tables /* 2 * n_groups * buckets */,
+                              uint4 *sorted, cudaStream_t s)
+{
+    if (n_groups == 0) return;
+    const int HT = occupancy_tile_rows(H);
+    const uint32_t nb = (uint32_t) words_bucket_count(W, H);
+    uint32_t *first = tables, *cursor = tables + (size_t) n_groups * nb;
+    cudaMemsetAsync(tables, 0, (size_t) 2 * n_groups * nb * sizeof(uint32_t), s);
+    dim3 grid(148 * 4, n_groups);
+    words_bucket_count_kernel<<<grid, 256, 0, s>>>(words, gstart, HT, nb, first);
+    words_bucket_scan_kernel<<<n_groups, 1024, 0, s>>>(first, gstart, HT, nb);
+    words_bucket_scatter_kernel<<<grid, 256, 0, s>>>(words, gstart, HT, nb, first, cursor, sorted);
+}
 
 bool cand_kernel_supported(int xy_shift, const PlaneGeom &g)
 {
@@ -738,13 +860,13 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok) warps = 24;
     if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24).ok) warps = 16;
 #define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<CDS_PALETTE_GROUP, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, scratch, s, dev)
-    if (chunk_env == 512) {
-        if (warps >= 31) return CDS_CAND_LAUNCH(31, 512);
-        return CDS_CAND_LAUNCH(28, 512);
+    if (chunk_env == 64) {
+        if (warps >= 31) return CDS_CAND_LAUNCH(31, 64);
+        return CDS_CAND_LAUNCH(28, 64);
     }
     if (chunk_env == 128) {
-        if (warps >= 28) return CDS_CAND_LAUNCH(28, 128);
-        return CDS_CAND_LAUNCH(24, 128);
+        if (warps >= 31) return CDS_CAND_LAUNCH(31, 128);
+        return CDS_CAND_LAUNCH(28, 128);
     }
     if (warps >= 31) return CDS_CAND_LAUNCH(31, 256);
     if (warps >= 28) return CDS_CAND_LAUNCH(28, 256);

@@ -12,8 +12,8 @@ namespace cds {
 // sector the kernel keeps a bitmap in TARGET coordinates (orientation 0: pixel (x, y); orientation 1, only when the mask set
 // mirrors: pixel (W-1-x, y)) of the pixels with an interval in that sector, cut into TILES of 8 x 4 pixels like the library's
 // occupancy bitmaps (bit (y % 4) * 8 + (x % 8) of tile (y / 4, x / 8)) and stored as its non-zero 32-bit tile words.  The
-// words of the CDS_PALETTE_GROUP masks of a group form ONE list ordered by tile row (then mask, orientation, sector, tile
-// column) with a row-start table gstart[tile rows + 1], so the entries that concern a band of image rows are one contiguous
+// words of the CDS_PALETTE_GROUP masks of a group form ONE list ordered by tile row (then sector, tile column -- the order of the
+// occupancy words --, then whatever) with a row-start table gstart[tile rows + 1], so the entries that concern a band of image rows are one contiguous
 // range that is cut into equal tickets regardless of mask boundaries.  One 16-byte entry per word:
 //     bits : the tile word
 //     occ  : index of the matching occupancy word inside a target's bitmaps: tile row * occupancy_row_pitch + sector * pitch + tile column
@@ -41,6 +41,15 @@ void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool m
 void launch_words_group_rows(uint32_t *count, int n_masks, int H, uint32_t *grow, cudaStream_t s);
 void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,
                        const uint32_t *gstart, const uint32_t *bstart, const uint32_t *boff, uint4 *words, uint16_t *lpal, cudaStream_t s);
+
+// Reorders every tile row's entries by occupancy word (`occ`), i.e. by (sector, tile column): afterwards the entries that meet one
+// target tile are neighbours, and the kernel skips the tickets whose occupancy words are all empty.  `tables` = scratch of
+// 2 * n_groups * words_bucket_count(W, H) words; `sorted` receives the entries (same size as `words`, must not alias it).
+inline size_t words_bucket_count(int W, int H) { return (size_t) occupancy_tile_rows(H) * occupancy_row_pitch(occupancy_tile_pitch(W)); }
+void launch_words_bucket_sort(const uint4 *words, const uint32_t *gstart, int n_groups, int W, int H, uint32_t *tables, uint4 *sorted, cudaStream_t s);
+// PaletteGroup::tocc of the SORTED list: the occupancy word of every 32nd entry, words_tocc_count(n_entries) words.
+inline uint32_t words_tocc_count(uint32_t n_entries) { return n_entries / 32 + 2; }
+void launch_words_tocc(const uint4 *words, uint32_t n_entries, uint32_t *tocc, cudaStream_t s);
 
 // Same contract as launch_pixelmatch_band (cds_band.cuh); every group needs a palette and its word lists
 // (PaletteGroup::palette / words / gstart / lpal).

@@ -42,6 +42,7 @@ struct PaletteGroup {
     const uint4 *words;               // base of the word lists of the candidate kernel (cds_cand.cuh), or nullptr
     const uint32_t *gstart;           // H + 1 entries: this group's entries of image row y are words[gstart[y] .. gstart[y+1])
     const uint16_t *lpal;             // palette references of the entries' set bits (cds_cand.cuh)
+    const uint32_t *tocc;             // occupancy word of every 32nd entry of `words` (cds_cand.cuh)
     int n_pal;
     int pad;
 };
