@@ -524,11 +524,15 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": {1: "pixelmatch_cand_kernel<1,1024,31,256>", 2: "pixelmatch_band_kernel<1,true,128,24>", 3: "pixelmatch_gather_kernel"}.get(kernel_used, "?"),
+                         "kernel": {1: "pixelmatch_cand_kernel<1,1024,31>", 2: "pixelmatch_band_kernel<1,true,128,24>", 3: "pixelmatch_gather_kernel"}.get(kernel_used, "?"),
                          "algorithmic_bytes_per_comparison": ALGO_BYTES_PER_COMPARISON,
                          "comparisons_per_launch": per_launch_cmp, "avg_launch_ms": avg_launch_s * 1e3,
+                         "physical_dram_gbs": (traffic / avg_launch_s / 1e9) if traffic else None,
+                         "physical_dram_frac": (traffic / avg_launch_s / 1e9 / peak) if traffic else None,
                          "note": "algorithmic bytes = 3*W*H per comparison (SURVEY 8d); a mask group shares one pass over the "
-                                 "target, so frac can exceed 1 -- physical DRAM traffic is in `traffic` / profiles/"},
+                                 "target, so frac can exceed 1 -- physical DRAM traffic (ncu dram bytes per comparison x this "
+                                 "launch's comparisons) is in `traffic`, its rate in physical_dram_*; the kernel is bound by "
+                                 "instruction issue (profiles/r01_v18_cand_ncu_summary.txt), not by HBM"},
             "e2e": e2e,
             "mask_pixels_mean": float(np.mean(mask_sizes)), "setup_s": setup_s,
             "matches_returned": int(merged[3].sum()) if merged is not None else None,

@@ -175,7 +175,7 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const u
     EvalUnroll<NRINGS, 0>::count(cw, acc, lo, len);
 }
 
-template <int NRINGS, int GROUP, int NCW, int kChunk>
+template <int NRINGS, int GROUP, int NCW>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(const CandParams p)
 {
     constexpr int NS = Offsets<NRINGS>::N;            // shift offsets = variants per orientation
@@ -302,7 +302,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - (size_t) (b * R / 4) * rowpitch;   // indexed by the entries' absolute occupancy word index
             const int y0 = b * R;
             const uint2 range = s_band[stage];                                   // the group's word-list entries of this band
-            const int n_tickets = (int) ((range.y - range.x + kChunk - 1) / kChunk);
 
             uint32_t qh = 0, qt = 0;            // candidate queue head / tail (free running, slot = index & (kQueue - 1))
             uint32_t wh = 0, wt = 0;            // word queue head / tail
@@ -546,7 +545,7 @@ int env_int(const char *name, int dflt)
     return e ? std::atoi(e) : dflt;
 }
 
-template <int GROUP, int NCW, int kChunk>
+template <int GROUP, int NCW>
 int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, int32_t *scores,
                const MatchScratch &scratch, cudaStream_t s, int dev)
@@ -570,9 +569,9 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     int grid = (int) std::min<long long>(std::min(n_sm, 256), n_items);
     void (*kern)(const CandParams) = nullptr;
     const int rings = xy_shift / 2;
-    if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW, kChunk>;
-    else if (rings == 1) kern = pixelmatch_cand_kernel<1, GROUP, NCW, kChunk>;
-    else kern = pixelmatch_cand_kernel<2, GROUP, NCW, kChunk>;
+    if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW>;
+    else if (rings == 1) kern = pixelmatch_cand_kernel<1, GROUP, NCW>;
+    else kern = pixelmatch_cand_kernel<2, GROUP, NCW>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem_bytes);
     kern<<<grid, (NCW + 1) * 32, c.smem_bytes, s>>>(p);
     return 1;
@@ -851,27 +850,18 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     if (!scratch.work_counter || !scratch.acc) return 0;
     cudaMemsetAsync(scratch.work_counter, 0, sizeof(unsigned long long), s);
     cudaMemsetAsync(scratch.acc, 0, kMatchAccBytes, s);
-    // tuning knobs (defaults picked from profiles/): consumer warps per CTA, word-list entries per ticket.  More warps need more
+    // tuning knob (default picked from profiles/): consumer warps per CTA.  More warps need more
     // shared memory for their queues; when the band stages no longer fit (xyShift 4: 34 accumulators per mask) fewer are used.
     static const int warps_env = env_int("CDSGPU_CAND_WARPS", 31);
-    static const int chunk_env = env_int("CDSGPU_CAND_CHUNK", 256);
     int warps = warps_env;
     if (warps >= 31 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 31).ok) warps = 28;
     if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok) warps = 24;
     if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24).ok) warps = 16;
-#define CDS_CAND_LAUNCH(NCW, CH) launch_cfg<CDS_PALETTE_GROUP, NCW, CH>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, scratch, s, dev)
-    if (chunk_env == 64) {
-        if (warps >= 31) return CDS_CAND_LAUNCH(31, 64);
-        return CDS_CAND_LAUNCH(28, 64);
-    }
-    if (chunk_env == 128) {
-        if (warps >= 31) return CDS_CAND_LAUNCH(31, 128);
-        return CDS_CAND_LAUNCH(28, 128);
-    }
-    if (warps >= 31) return CDS_CAND_LAUNCH(31, 256);
-    if (warps >= 28) return CDS_CAND_LAUNCH(28, 256);
-    if (warps >= 24) return CDS_CAND_LAUNCH(24, 256);
-    return CDS_CAND_LAUNCH(16, 256);
+#define CDS_CAND_LAUNCH(NCW) launch_cfg<CDS_PALETTE_GROUP, NCW>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, scratch, s, dev)
+    if (warps >= 31) return CDS_CAND_LAUNCH(31);
+    if (warps >= 28) return CDS_CAND_LAUNCH(28);
+    if (warps >= 24) return CDS_CAND_LAUNCH(24);
+    return CDS_CAND_LAUNCH(16);
 #undef CDS_CAND_LAUNCH
 }
 
