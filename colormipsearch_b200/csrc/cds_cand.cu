@@ -396,6 +396,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const uint32_t band_lo = (uint32_t) ((y0 / 4) * rowpitch);
             const uint32_t band_hi = (uint32_t) (((min(y0 + R, H) + 3) / 4) * rowpitch) - 1u;
             const uint32_t sec_words = (uint32_t) (CDS_NUM_SECTORS * p.bpitch);
+            const uint32_t nz_off = (uint32_t) ((CDS_NUM_SECTORS + 1) * p.bpitch);    // the non-empty bits of a tile row, behind its OR row
             const uint32_t j_first = range.x >> 5;
             const uint32_t n_tk = range.y > range.x ? ((range.y - 1u) >> 5) - j_first + 1u : 0u;
             // a multiple of the number of consumer warps, so that every warp gets the same number of (partly filled) batches
@@ -436,13 +437,27 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     uint32_t o_lo = band_lo, o_hi = band_hi;
                     if ((jt << 5) >= range.x) o_lo = max(band_lo, __ldg(gtocc + jt));
                     if (((jt + 1u) << 5) < range.y) o_hi = min(band_hi, __ldg(gtocc + jt + 1u));
-                    if (!p.ticket_skip || o_hi - o_lo > 95u) {
-                        pass = true;                                    // a long run (few mask pixels there): not worth the test
+                    if (!p.ticket_skip) {
+                        pass = true;
                     } else {
-                        uint32_t r = o_lo % (uint32_t) rowpitch;        // position inside the tile row: the OR-of-sectors part is left out
-                        for (uint32_t o = o_lo; o <= o_hi; o++) {
-                            pass |= r < sec_words && bits_y0[o] != 0u;
-                            if (++r == (uint32_t) rowpitch) r = 0;
+                        // the run [o_lo, o_hi], tile row by tile row, against the rows' non-empty bits (one bit per sector word,
+                        // cds_kernels.cuh): a few masked words instead of a walk over the occupancy words themselves
+                        uint32_t ra = o_lo - band_lo, base = band_lo;
+                        while (ra >= (uint32_t) rowpitch) { ra -= (uint32_t) rowpitch; base += (uint32_t) rowpitch; }
+                        uint32_t re = o_hi - base;                       // may lie in a later tile row
+                        for (;;) {
+                            const uint32_t hi = min(re, sec_words - 1u);
+                            if (ra <= hi) {
+                                const uint32_t *nz = bits_y0 + base + nz_off;
+                                for (uint32_t wd = ra >> 5; wd <= (hi >> 5); wd++) {
+                                    uint32_t m = nz[wd];
+                                    if (wd == (ra >> 5)) m &= 0xffffffffu << (ra & 31u);
+                                    if (wd == (hi >> 5)) m &= 0xffffffffu >> (31u - (hi & 31u));
+                                    pass |= m != 0u;
+                                }
+                            }
+                            if (re < (uint32_t) rowpitch) break;
+                            re -= (uint32_t) rowpitch; base += (uint32_t) rowpitch; ra = 0;
                         }
                     }
                 }

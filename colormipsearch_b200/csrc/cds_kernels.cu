@@ -299,11 +299,31 @@ __global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restri
     }
 }
 
+// One warp per (target, tile row): the non-empty bits of the row's sector words (cds_kernels.cuh), read back from the tile
+// words the kernel above has just written.
+__global__ void __launch_bounds__(256) occupancy_nz_kernel(int H, int tp, int64_t t0, int64_t n, uint32_t *__restrict__ occ)
+{
+    const int rowpitch = occupancy_row_pitch(tp);
+    const int HT = occupancy_tile_rows(H);
+    const int lane = threadIdx.x & 31;
+    const int sec_words = CDS_NUM_SECTORS * tp;
+    const int64_t total = n * HT;
+    for (int64_t r = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < total; r += (int64_t) gridDim.x * (blockDim.x >> 5)) {
+        uint32_t *row = occ + ((size_t) t0 * HT + (size_t) r) * rowpitch;
+        for (int i0 = 0; i0 < occupancy_nz_words(tp) * 32; i0 += 32) {
+            const int i = i0 + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, i < sec_words && row[i] != 0u);
+            if (lane == 0) row[(CDS_NUM_SECTORS + 1) * tp + (i0 >> 5)] = m;
+        }
+    }
+}
+
 static void launch_occupancy_kernel(const uint32_t *valid, int H, int vp, int tp, int64_t t0, int64_t n, int rings, uint32_t *occ, cudaStream_t s)
 {
     if (rings == 0) occupancy_kernel<0><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
     else if (rings == 1) occupancy_kernel<1><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
     else occupancy_kernel<2><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
+    occupancy_nz_kernel<<<148 * 8, 256, 0, s>>>(H, tp, t0, n, occ);
 }
 
 void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int tp,
