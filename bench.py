@@ -532,7 +532,7 @@ def main():
                          "note": "algorithmic bytes = 3*W*H per comparison (SURVEY 8d); a mask group shares one pass over the "
                                  "target, so frac can exceed 1 -- physical DRAM traffic (ncu dram bytes per comparison x this "
                                  "launch's comparisons) is in `traffic`, its rate in physical_dram_*; the kernel is bound by "
-                                 "instruction issue (profiles/r01_v18_cand_ncu_summary.txt), not by HBM"},
+                                 "instruction issue (profiles/r01_v19_cand_ncu_summary.txt), not by HBM"},
             "e2e": e2e,
             "mask_pixels_mean": float(np.mean(mask_sizes)), "setup_s": setup_s,
             "matches_returned": int(merged[3].sum()) if merged is not None else None,
