@@ -276,6 +276,19 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         }
     }
 
+    // whatever way this call ends (a bad file in chunk 5, a CUDA error), nothing of it is still in flight afterwards: the next
+    // call reuses the staging buffers from chunk 0 without waiting for anybody
+    struct Drain {
+        cds_ctx *ctx; int n;
+        ~Drain() {
+            for (int d = 0; d < n; d++) {
+                cudaSetDevice(ctx->devs[d].dev);
+                if (ctx->devs[d].sb.copy_stream) cudaStreamSynchronize(ctx->devs[d].sb.copy_stream);
+                cudaStreamSynchronize(ctx->devs[d].stream);
+            }
+        }
+    } drain{ctx, used_devs};
+
     // enqueue every chunk; nothing below blocks the host when the source is pinned memory
     std::vector<int64_t> per_dev(D, 0);
     for (const Chunk &ch : plan) {
