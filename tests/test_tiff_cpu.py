@@ -102,3 +102,28 @@ def test_writer_worst_case_fits_the_bound():
     data = capi.tiff_encode_rgb(img, 4, 32773)
     assert np.array_equal(OT.read_tiff_rgb(data), img)
     assert len(data) <= capi.lib().cds_tiff_encode_bound(129, 33, 4)
+
+
+def test_probe_survives_corrupted_files(tiffs):
+    """The tag parser reads files that come from outside: random corruption of valid files must end in a clean status (OK or an
+    error), never in a crash, and whatever is reported as decodable must have its strips inside the file."""
+    rng = np.random.default_rng(20241018)
+    seeds = [tiffs["file_pack1"].tobytes(), tiffs["file_em_12191"].tobytes(), tiffs["file_stored1"].tobytes()[:4096] + b"\0" * 64,
+             capi.tiff_encode_rgb(np.zeros((9, 17, 3), np.uint8), 2, 32773)]
+    for it in range(3000):
+        data = bytearray(seeds[it % len(seeds)])
+        n = len(data)
+        (ifd,) = struct.unpack("<I" if data[:2] == b"II" else ">I", data[4:8])
+        for _ in range(int(rng.integers(1, 6))):
+            # most flips inside the header / directory, where they matter
+            pos = int(rng.integers(0, 8)) if rng.random() < 0.2 else int(min(n - 1, ifd + rng.integers(0, 200))) if rng.random() < 0.8 else int(rng.integers(0, n))
+            data[pos] = int(rng.integers(0, 256))
+        if rng.random() < 0.2:
+            data = data[:int(rng.integers(0, n))]
+        try:
+            info = capi.tiff_probe(bytes(data))
+        except capi.CdsError:
+            continue
+        assert info["width"] > 0 and info["height"] > 0
+        if info["decodable"]:
+            assert 0 <= info["data_bytes"] <= len(data) * max(1, info["n_strips"])

@@ -188,3 +188,53 @@ def test_masks_from_tiff_files(ctx, synth_files, tiffs, fixtures):
     for x, y in zip(ra, rb):
         assert np.array_equal(x, y)
     a.close(); b.close()
+
+
+def _clamped_packbits(strip, out_len):
+    """The decoder's documented behaviour for ANY input (include/cdsgpu.h): the reference's run loop, stopping at the end of the
+    strip's input or of its rows; bytes a literal is missing, and everything that was not produced, are 0."""
+    out = np.zeros(out_len, np.uint8)
+    idx = pos = 0
+    n = len(strip)
+    while idx < n and pos < out_len:
+        c = strip[idx]
+        if c < 128:
+            cnt = c + 1
+            lit = strip[idx + 1:idx + 1 + cnt]
+            lim = min(cnt, out_len - pos)
+            out[pos:pos + min(lim, len(lit))] = np.frombuffer(bytes(lit[:lim]), np.uint8)
+            idx += 1 + cnt
+            pos += cnt
+        elif c != 128:
+            cnt = 257 - c
+            v = strip[idx + 1] if idx + 1 < n else 0
+            out[pos:min(out_len, pos + cnt)] = v
+            idx += 2
+            pos += cnt
+        else:
+            idx += 1
+    return out
+
+
+def test_device_decode_of_garbage_strips(ctx):
+    """Random bytes inside a well-formed container: the decoder neither hangs nor writes outside the image, and produces what the
+    clamped run loop produces."""
+    rng = np.random.default_rng(99)
+    w, h, rps = 67, 23, 5
+    files, expect = [], []
+    for i in range(40):
+        img = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+        data = bytearray(capi.tiff_encode_rgb(img, rps, 32773))
+        info = OT.tiff_info(bytes(data))
+        exp = np.zeros(h * w * 3, np.uint8)
+        for s, (off, ln) in enumerate(zip(info["strip_offsets"], info["strip_lengths"])):
+            garbage = rng.integers(0, 256, ln).astype(np.uint8)
+            if i % 4 == 0:
+                garbage[:] = rng.choice([0x81, 0x00, 0x80, 0x7f, 0xff], ln)      # long runs, no-ops, maximal literals
+            data[off:off + ln] = garbage.tobytes()
+            rows = min(rps, h - s * rps)
+            exp[s * rps * w * 3:(s * rps + rows) * w * 3] = _clamped_packbits(bytes(garbage), rows * w * 3)
+        files.append(bytes(data))
+        expect.append(exp.reshape(h, w, 3))
+    got = capi.tiff_decode_rgb(ctx, files, w, h)
+    assert np.array_equal(got, np.stack(expect))
