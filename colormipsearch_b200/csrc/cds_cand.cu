@@ -9,15 +9,17 @@
 //     pixels has its occupancy bit set.  On colour-depth MIPs ~8 % of the (pixel, orientation) tests can match but ~34 % of
 //     the 32-pixel warp iterations contain at least one, so most evaluated lanes are dead weight and the per-pixel
 //     bookkeeping (record decode, two bitmap reads, two votes) is paid for every pixel.
-//   * here a lane owns one 32-pixel WORD of the mask bitmap per iteration (cds_cand.cuh): candidates = word & occupancy word.
-//     Set bits are peeled off with warp-aggregated pushes into a per-warp shared-memory queue; whenever 32 candidates are
-//     queued the warp evaluates them: palette lookup, 9 (17) shifted reads of the band, predicated adds into per-lane
-//     counters.  Work is proportional to the candidates, not to the mask size.
+//   * here a lane owns one 32-pixel tile WORD of the mask bitmaps per iteration (cds_cand.cuh): candidates = word & occupancy
+//     word.  The words of a mask group are ordered by occupancy word, so that tickets of 32 words can be tested against the
+//     target ("does it have anything on these tiles, in this sector?") before they are read: ~97 % of them are never scanned.
+//     The candidate bits of the words that remain are expanded, load-balanced over the lanes, and evaluated 32 at a time:
+//     palette lookup, 9 (17) shifted reads of the band, predicated reductions into per-(mask, variant) counters in global
+//     memory.  Work is proportional to the candidates, not to the mask size.
 //
 // Mirrored variants need no separate code: orientation-1 words are stored in target coordinates (bit W-1-x), and the 3x3
 // (5x5) shift pattern is symmetric, so both orientations read the same neighbourhood offsets of their centre; only the
 // variant LABEL differs (offset (dx,dy) of a mirrored pixel is the reference's variant (-dx,dy)), and the score is a max
-// over labels.  A candidate's orientation just selects the half (low / high 16 bits) of the packed counters it increments.
+// over labels.  A candidate's orientation just selects the half of the mask's counters it increments.
 #include "cds_cand.cuh"
 #include "cds_ptx.cuh"
 
