@@ -65,6 +65,7 @@ __device__ __forceinline__ int code_sector(uint32_t cw)
 }
 
 constexpr int kEncodeRows = 4;      // image rows per CTA (fewer for very wide images): one staging round trip to DRAM per 4 rows
+constexpr int kEncodeQueue = 64;    // per-warp queue of non-black pixels waiting for the colour classifier (power of two, >= 2 * 32)
 
 template <bool VALID>
 __global__ void __launch_bounds__(256) encode_rgb_kernel(const uint8_t *__restrict__ rgb, uint32_t *__restrict__ planes, PlaneGeom g,
@@ -84,41 +85,60 @@ __global__ void __launch_bounds__(256) encode_rgb_kernel(const uint8_t *__restri
     const uint4 *asrc = reinterpret_cast<const uint4 *>(a - off);
     const int n_vec = (int) ((off + rows * row_bytes + 15) / 16);
     for (int k = threadIdx.x; k < n_vec; k += blockDim.x) srow4[k] = asrc[k];
-    __syncthreads();
     const uint8_t *sb = reinterpret_cast<const uint8_t *>(srow4) + off;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kmax = max((g.pitch + 31) >> 5, vp);
+    const int kmax = (g.pitch + 31) >> 5;
     // the rows' valid words are collected behind the staged pixels and leave as one contiguous block: a lane writing single
     // words at a stride of vp makes every store a partial-sector write that L2 has to merge
     uint32_t *s_valid = reinterpret_cast<uint32_t *>(srow4 + (rows_per_cta * row_bytes + 15 + 15) / 16);
-    // Colour-depth MIPs are mostly black: a warp whose 32 pixels are all (0, 0, 0) writes the black code word and six empty
-    // valid words without running the encoder (the encoder is ~150 instructions per 32 pixels, this path ~15).
+    uint32_t *s_queue = s_valid + (VALID ? rows_per_cta * CDS_NUM_SECTORS * vp : 0);       // [warps][kEncodeQueue] pixels to encode
+    if (VALID)
+        for (int k = threadIdx.x; k < rows * CDS_NUM_SECTORS * vp; k += blockDim.x) s_valid[k] = 0u;
+    __syncthreads();
+    // Colour-depth MIPs are mostly black (~94 % of the pixels): black pixels get the black code word straight away, and only the
+    // others run the colour classifier (~150 instructions) -- compacted warp-wide into a small queue so that the classifier always
+    // runs on full warps.  Work is proportional to the non-black pixels, not to the 32-pixel groups that contain one.
     const uint32_t black = encode_color_dev(0, 0, 0, rank_tab, thr);
+    uint32_t *prow0 = planes + g.row_offset(first_slot + img, y0);
+    uint32_t *myq = s_queue + warp * kEncodeQueue;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t qh = 0, qt = 0;
+    auto drain = [&](bool all) {
+        while (qt - qh >= 32u || (all && qt != qh)) {
+            const uint32_t n = min(32u, qt - qh);
+            if ((uint32_t) lane < n) {
+                const uint32_t e = myq[(qh + lane) & (kEncodeQueue - 1)];
+                const int x = (int) (e & 0xFFFFu), r = (int) (e >> 16);
+                const uint8_t *px = sb + (size_t) r * row_bytes + 3 * x;
+                const uint32_t code = encode_color_dev(px[0], px[1], px[2], rank_tab, thr);
+                prow0[(size_t) r * g.pitch + x] = code;
+                if (VALID) {
+                    const int sector = code_sector(code);
+                    if (sector >= 0) atomicOr(&s_valid[(r * CDS_NUM_SECTORS + sector) * vp + (x >> 5)], 1u << (x & 31));
+                }
+            }
+            qh += n;
+            __syncwarp();
+        }
+    };
     for (int r = 0; r < rows; r++) {
-        uint32_t *drow = planes + g.row_offset(first_slot + img, y0 + r);
+        uint32_t *drow = prow0 + (size_t) r * g.pitch;
         const uint8_t *srow = sb + (size_t) r * row_bytes;
         for (int k = warp; k < kmax; k += (int) (blockDim.x >> 5)) {
             const int x = k * 32 + lane;
-            int pr = 0, pg = 0, pb = 0;
-            if (x < g.W) { pr = srow[3 * x]; pg = srow[3 * x + 1]; pb = srow[3 * x + 2]; }
-            uint32_t code = x < g.W ? black : CDS_CODE_PAD_WORD;
-            const bool lit = __any_sync(0xffffffffu, (pr | pg | pb) != 0);
-            if (lit && x < g.W) code = encode_color_dev(pr, pg, pb, rank_tab, thr);
-            if (x < g.pitch) drow[x] = code;
-            if (VALID) {
-                if (!lit) {
-                    if (lane < CDS_NUM_SECTORS && k < vp) s_valid[(r * CDS_NUM_SECTORS + lane) * vp + k] = 0u;
-                } else {
-                    const int sector = code_sector(code);
-#pragma unroll
-                    for (int s = 0; s < CDS_NUM_SECTORS; s++) {
-                        const unsigned bal = __ballot_sync(0xffffffffu, sector == s);
-                        if (lane == 0 && k < vp) s_valid[(r * CDS_NUM_SECTORS + s) * vp + k] = bal;
-                    }
-                }
+            bool lit = false;
+            if (x < g.W) lit = (srow[3 * x] | srow[3 * x + 1] | srow[3 * x + 2]) != 0;
+            if (x < g.pitch && !lit) drow[x] = x < g.W ? black : CDS_CODE_PAD_WORD;
+            const unsigned m = __ballot_sync(0xffffffffu, lit);
+            if (m) {
+                if (lit) myq[(qt + (uint32_t) __popc(m & lt)) & (kEncodeQueue - 1)] = (uint32_t) x | ((uint32_t) r << 16);
+                qt += (uint32_t) __popc(m);
+                __syncwarp();
+                drain(false);
             }
         }
     }
+    drain(true);
     if (VALID) {
         __syncthreads();
         uint32_t *vout = valid + ((size_t) img * g.H + y0) * CDS_NUM_SECTORS * vp;
@@ -132,7 +152,7 @@ void launch_encode_rgb(const uint8_t *rgb, int64_t n, uint32_t *planes, PlaneGeo
     if (n == 0) return;
     const int vp = occupancy_valid_pitch(g.W);
     int rpc = kEncodeRows;
-    auto smem_for = [&](int r) { return ((size_t) r * g.W * 3 + 15 + 15) / 16 * 16 + (valid ? (size_t) r * CDS_NUM_SECTORS * vp * 4 : 0); };
+    auto smem_for = [&](int r) { return ((size_t) r * g.W * 3 + 15 + 15) / 16 * 16 + (valid ? (size_t) r * CDS_NUM_SECTORS * vp * 4 : 0) + (size_t) 8 * kEncodeQueue * 4; };
     while (rpc > 1 && smem_for(rpc) > 96 * 1024) rpc >>= 1;
     const size_t smem = smem_for(rpc);
     static bool attr_set = false;
