@@ -167,10 +167,13 @@ def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
     prep_s = time.perf_counter() - t0
     pm = np.repeat(np.arange(n_masks, dtype=np.int32), per_mask)
     pt = ((pm.astype(np.int64) * 7) + np.tile(np.arange(per_mask, dtype=np.int64) * 2, n_masks)) % n_targets
-    sms.score_pairs(targets[:8], grads[:8], None, pm[:16] % 1, pt[:16] % 8)      # warm-up
-    t0 = time.perf_counter()
-    gap, he, mir = sms.score_pairs(targets, grads, None, pm, pt)
-    e2e_s = time.perf_counter() - t0
+    sms.score_pairs(targets, grads, None, pm, pt)                                # warm-up: first-use allocations of the pooled buffers
+    e2e_s = None
+    for _ in range(2):                                                           # the better of two calls (each one complete: H2D .. D2H)
+        t0 = time.perf_counter()
+        gap, he, mir = sms.score_pairs(targets, grads, None, pm, pt)
+        dt = time.perf_counter() - t0
+        e2e_s = dt if e2e_s is None else min(e2e_s, dt)
     st = ctx.last_stats()
     n_pairs = len(pm)
     bytes_per_pair = 3 * W * H + 2 * W * H + 3 * W * H          # target RGB + gradient + zgap RGB
