@@ -175,6 +175,25 @@ def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
         dt = time.perf_counter() - t0
         e2e_s = dt if e2e_s is None else min(e2e_s, dt)
     st = ctx.last_stats()
+    # the same call with the targets as PackBits TIFF files (decoded on the device); gradients stay pixels (PNG in the reference)
+    from concurrent.futures import ThreadPoolExecutor as _TPE
+    with _TPE(max_workers=host_threads()) as ex:
+        files = list(ex.map(lambda i: capi.tiff_encode_rgb(targets[i], 8, 32773), range(n_targets)))
+    foff = np.zeros(n_targets + 1, np.int64)
+    np.cumsum([len(f) for f in files], out=foff[1:])
+    f_arr, f_ptr = ctx.host_alloc(int(foff[-1]) + 64)
+    for i, f in enumerate(files):
+        f_arr[foff[i]:foff[i + 1]] = np.frombuffer(f, np.uint8)
+    del files
+    sms.score_pairs_tiff((f_arr, foff), grads, None, pm, pt, blob_ptr=f_ptr)
+    tiff_s = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        gap2, he2, mir2 = sms.score_pairs_tiff((f_arr, foff), grads, None, pm, pt, blob_ptr=f_ptr)
+        dt = time.perf_counter() - t0
+        tiff_s = dt if tiff_s is None else min(tiff_s, dt)
+    tiff_same = bool(np.array_equal(gap2, gap) and np.array_equal(he2, he) and np.array_equal(mir2, mir))
+    ctx.host_free(f_ptr)
     n_pairs = len(pm)
     bytes_per_pair = 3 * W * H + 2 * W * H + 3 * W * H          # target RGB + gradient + zgap RGB
     peak, peak_src = measured_peak()
@@ -184,6 +203,9 @@ def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
            "e2e": {"value": n_pairs / e2e_s, "unit": "pairs/s", "ms": e2e_s * 1e3,
                    "h2d_bytes": int(n_targets * (3 * W * H + 2 * W * H)), "what": "cds_shape_score_pairs: H2D of targets + gradients, "
                    "zgap = maxFilter(10) on device, slice planes, pair kernel, D2H"},
+           "e2e_tiff": {"value": n_pairs / tiff_s, "unit": "pairs/s", "ms": tiff_s * 1e3,
+                        "h2d_bytes": int(foff[-1]) + int(n_targets * 2 * W * H), "equals_pixel_call": tiff_same,
+                        "what": "cds_shape_score_pairs_tiff: targets as PackBits TIFF files decoded on the device, gradients as pixels"},
            "mask_prep_ms_per_mask": prep_s / n_masks * 1e3,
            "roofline": {"bound": "hbm", "achieved": kernel_pairs_s * bytes_per_pair / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": kernel_pairs_s * bytes_per_pair / 1e9 / peak, "algorithmic_bytes_per_pair": bytes_per_pair,

@@ -105,6 +105,7 @@ SIGNATURES = {
     "cds_shape_maskset_add_rgb": (C.c_int32, [_vp, _vp, C.c_int32, _i64p, _i64p]),
     "cds_shape_maskset_size": (C.c_int32, [_vp]),
     "cds_shape_score_pairs": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i32p, _i64p, C.c_int64, _i64p, _i64p, _u8p]),
+    "cds_shape_score_pairs_tiff": (C.c_int32, [_vp, _vp, _vp, _i64p, _vp, _vp, _vp, C.c_int64, _i32p, _i64p, C.c_int64, _i64p, _i64p, _u8p]),
     "cds_make_zgap": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.POINTER(Rect), C.c_int32, _vp]),
     "cds_shape_score_2d": (C.c_int64, [C.c_int64, C.c_int64]),
     "cds_normalized_score": (C.c_double, [C.c_int32, C.c_int64, C.c_int64, C.c_int64]),
@@ -525,6 +526,26 @@ class ShapeMaskSet:
         _check(lib().cds_shape_score_pairs(self.ctx.h, self.h, _ptr(target_rgb), _ptr(gradient), _ptr(zgap_rgb), _ptr(has_variants),
                                            n_targets, pair_mask.ctypes.data_as(_i32p), pair_target.ctypes.data_as(_i64p), n,
                                            gap.ctypes.data_as(_i64p), he.ctypes.data_as(_i64p), mir.ctypes.data_as(_u8p)), self.ctx.h)
+        return gap, he, mir.astype(bool)
+
+    def score_pairs_tiff(self, files, gradient, zgap_rgb, pair_mask, pair_target, has_variants=None, blob_ptr=None):
+        """cds_shape_score_pairs_tiff: targets as TIFF files (a list of bytes objects or a (blob, offsets) pair)."""
+        blob, offsets = pack_files(files)
+        n_targets = len(offsets) - 1
+        gradient = None if gradient is None else np.ascontiguousarray(gradient, dtype=np.uint16)
+        zgap_rgb = None if zgap_rgb is None else np.ascontiguousarray(zgap_rgb, dtype=np.uint8)
+        has_variants = None if has_variants is None else np.ascontiguousarray(has_variants, dtype=np.uint8)
+        pair_mask = np.ascontiguousarray(pair_mask, dtype=np.int32)
+        pair_target = np.ascontiguousarray(pair_target, dtype=np.int64)
+        n = len(pair_mask)
+        gap = np.zeros(n, np.int64)
+        he = np.zeros(n, np.int64)
+        mir = np.zeros(n, np.uint8)
+        ptr = blob_ptr if blob_ptr is not None else _ptr(blob)
+        _check(lib().cds_shape_score_pairs_tiff(self.ctx.h, self.h, ptr, offsets.ctypes.data_as(_i64p), _ptr(gradient), _ptr(zgap_rgb),
+                                                _ptr(has_variants), n_targets, pair_mask.ctypes.data_as(_i32p),
+                                                pair_target.ctypes.data_as(_i64p), n, gap.ctypes.data_as(_i64p), he.ctypes.data_as(_i64p),
+                                                mir.ctypes.data_as(_u8p)), self.ctx.h)
         return gap, he, mir.astype(bool)
 
 

@@ -20,6 +20,7 @@
 
 #include "cds_lut.h"
 #include "cds_runtime.h"
+#include "cds_tiff.h"
 
 using namespace cds;
 
@@ -555,10 +556,12 @@ extern "C" cds_status cds_make_zgap(cds_ctx *ctx, const uint8_t *rgb, int64_t n,
     return st;
 }
 
-extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskset *sms_c, const uint8_t *target_rgb, const uint16_t *gradient,
-                                            const uint8_t *zgap_rgb, const uint8_t *has_variants, int64_t n_targets,
-                                            const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
-                                            int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
+// Targets either as pixels (target_rgb) or as TIFF files stored back to back (blob + offsets, decoded on the device).
+static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *sms_c, const uint8_t *target_rgb,
+                                         const uint8_t *blob, const int64_t *offsets, const uint16_t *gradient,
+                                         const uint8_t *zgap_rgb, const uint8_t *has_variants, int64_t n_targets,
+                                         const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
+                                         int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
 {
     if (!ctx || !sms_c) { set_tls_error("cds_shape_score_pairs: NULL argument"); return CDS_ERR_BAD_ARG; }
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -575,7 +578,8 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
         if (!has_variants || has_variants[pair_target[i]]) any_scored = true;
     }
     // a missing gradient can only be expressed through has_variants; a NULL gradient array with scorable pairs is an error
-    if (any_scored && (!target_rgb || !gradient)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs: target / gradient images are NULL");
+    const bool from_files = blob != nullptr && offsets != nullptr;
+    if (any_scored && ((!target_rgb && !from_files) || !gradient)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs: target / gradient images are NULL");
     ctx->stats = cds_search_stats{};
     DevState &d0 = ctx->devs[0];
     SH_CUDA(ctx, cudaSetDevice(d0.dev));
@@ -598,7 +602,10 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
 
     uint16_t *d_zslice = nullptr, *d_grad = nullptr;
     uint32_t *d_tsig = nullptr;
-    uint8_t *d_t = nullptr, *d_z = nullptr, *d_tmp = nullptr, *d_has = nullptr;
+    uint8_t *d_t = nullptr, *d_z = nullptr, *d_tmp = nullptr, *d_has = nullptr, *d_comp = nullptr;
+    TiffStrip *d_strips = nullptr;
+    size_t comp_cap = 0, strips_cap = 0;
+    std::vector<TiffStrip> strips;
     int32_t *d_pm = nullptr;
     int64_t *d_pt = nullptr;
     long long *d_gap = nullptr, *d_he = nullptr;
@@ -613,6 +620,15 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
     if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_t, 2 * chunk * bytes), "cudaMalloc");          // two upload halves
     if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_z, 2 * chunk * bytes), "cudaMalloc");
     if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_tmp, chunk * bytes), "cudaMalloc");
+    if (st == CDS_OK && from_files && n_targets > 0) {
+        for (int64_t i = 0; i <= n_targets; i++)
+            if (offsets[i] < 0 || (i > 0 && offsets[i] < offsets[i - 1])) st = ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs_tiff: offsets must be non-decreasing");
+        if (st == CDS_OK) {
+            ingest_bounds(offsets, n_targets, chunk, W, H, comp_cap, strips_cap);
+            st = ctx->check(pool.alloc((void **) &d_comp, comp_cap), "cudaMalloc(files)");
+            if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_strips, strips_cap * sizeof(TiffStrip)), "cudaMalloc(strips)");
+        }
+    }
     if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_pm, n_pairs * sizeof(int32_t)), "cudaMalloc");
     if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_pt, n_pairs * sizeof(int64_t)), "cudaMalloc");
     if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_gap, n_pairs * sizeof(long long)), "cudaMalloc");
@@ -631,9 +647,16 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
             const int slot = (int) ((i0 / chunk) & 1);
             cds_status s2 = CDS_OK;
             if (i0 >= 2 * chunk) s2 = ctx->check(cudaStreamWaitEvent(d0.copy_stream, d0.up_free[slot], 0), "wait");
-            if (s2 == CDS_OK) s2 = ctx->check(cudaMemcpyAsync(d_t + (size_t) slot * chunk * bytes, target_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.copy_stream), "target H2D");
+            if (s2 == CDS_OK && from_files) {
+                // the files as stored, decoded on the copy stream (one buffer: uploads and decodes of consecutive chunks are ordered)
+                s2 = ingest_chunk(ctx, "cds_shape_score_pairs_tiff", blob, offsets, i0, cnt, W, H, d_comp, comp_cap, d_strips, strips_cap,
+                                  d_t + (size_t) slot * chunk * bytes, d0.copy_stream, strips);
+            } else if (s2 == CDS_OK) {
+                s2 = ctx->check(cudaMemcpyAsync(d_t + (size_t) slot * chunk * bytes, target_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.copy_stream), "target H2D");
+                ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
+            }
             if (s2 == CDS_OK) s2 = ctx->check(cudaMemcpyAsync(d_grad + (size_t) i0 * px, gradient + (size_t) i0 * px, (size_t) cnt * px * sizeof(uint16_t), cudaMemcpyHostToDevice, d0.copy_stream), "gradient H2D");
-            ctx->stats.h2d_bytes += (int64_t) (cnt * bytes) + (int64_t) (cnt * px * sizeof(uint16_t));
+            ctx->stats.h2d_bytes += (int64_t) (cnt * px * sizeof(uint16_t));
             if (s2 == CDS_OK && zgap_rgb) {
                 s2 = ctx->check(cudaMemcpyAsync(d_z + (size_t) slot * chunk * bytes, zgap_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.copy_stream), "zgap H2D");
                 ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
@@ -692,7 +715,26 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
     }
     if (st != CDS_OK) { cudaStreamSynchronize(d0.copy_stream); cudaStreamSynchronize(d0.stream); cudaGetLastError(); }
     for (void *p : {(void *) d_zslice, (void *) d_grad, (void *) d_tsig, (void *) d_t, (void *) d_z, (void *) d_tmp, (void *) d_has, (void *) d_pm,
-                    (void *) d_pt, (void *) d_gap, (void *) d_he, (void *) d_mir})
+                    (void *) d_pt, (void *) d_gap, (void *) d_he, (void *) d_mir, (void *) d_comp, (void *) d_strips})
         pool.free(p);
     return st;
+}
+
+extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskset *sms, const uint8_t *target_rgb, const uint16_t *gradient,
+                                            const uint8_t *zgap_rgb, const uint8_t *has_variants, int64_t n_targets,
+                                            const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
+                                            int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
+{
+    return shape_score_pairs_impl(ctx, sms, target_rgb, nullptr, nullptr, gradient, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
+                                  gap_out, high_expr_out, mirrored_out);
+}
+
+extern "C" cds_status cds_shape_score_pairs_tiff(cds_ctx *ctx, const cds_shape_maskset *sms, const uint8_t *blob, const int64_t *offsets,
+                                                 const uint16_t *gradient, const uint8_t *zgap_rgb, const uint8_t *has_variants, int64_t n_targets,
+                                                 const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
+                                                 int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
+{
+    if (n_targets > 0 && (!blob || !offsets)) { set_tls_error("cds_shape_score_pairs_tiff: NULL files"); return CDS_ERR_BAD_ARG; }
+    return shape_score_pairs_impl(ctx, sms, nullptr, blob, offsets, gradient, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
+                                  gap_out, high_expr_out, mirrored_out);
 }

@@ -35,6 +35,16 @@ cds_status tiff_parse(const uint8_t *file, size_t len, cds_tiff_info &info, std:
 cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int height, uint64_t src_base, uint64_t dst_base,
                                std::vector<TiffStrip> &out, std::string &err);
 
+}  // namespace cds
+struct cds_ctx;
+namespace cds {
+// Uploads files [i0, i0 + cnt) of the blob and decodes them into d_rgb, everything on stream `s` (cds_ingest.cu); d_comp / d_strips
+// must hold the chunk (ingest_bounds gives sizes that suffice for any `cnt` consecutive files).  `strips` is host scratch.
+cds_status ingest_chunk(cds_ctx *ctx, const char *who, const uint8_t *blob, const int64_t *offsets, int64_t i0, int64_t cnt, int W, int H,
+                        uint8_t *d_comp, size_t comp_cap, TiffStrip *d_strips, size_t strips_cap, uint8_t *d_rgb, cudaStream_t s,
+                        std::vector<TiffStrip> &strips);
+void ingest_bounds(const int64_t *offsets, int64_t n, int64_t cnt, int W, int H, size_t &comp_cap, size_t &strips_cap);
+
 void launch_tiff_decode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint8_t *dst_rgb, cudaStream_t s);
 
 }  // namespace cds

@@ -266,6 +266,14 @@ cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskset *sms,
                                  const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
                                  int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out);
 
+/* The same scoring for targets that are TIFF files in host memory (blob / offsets as in cds_search_stream_tiff): the files are
+ * uploaded as stored and decoded on the device, the gradient (and optional zgap) images are passed as pixels as above -- the
+ * reference keeps gradients as 16-bit PNG, which it decodes on the JVM (API/imageprocessing/ImageArrayUtils.java:98-121). */
+cds_status cds_shape_score_pairs_tiff(cds_ctx *ctx, const cds_shape_maskset *sms, const uint8_t *blob, const int64_t *offsets,
+                                      const uint16_t *gradient, const uint8_t *zgap_rgb, const uint8_t *has_variants, int64_t n_targets,
+                                      const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
+                                      int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out);
+
 /* The zgap image alone (f3 in SURVEY.md section 8f): maxFilter(radius)(mask(threshold)(clearLabels(rgb))) for n images. */
 cds_status cds_make_zgap(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t width, int32_t height, int32_t threshold,
                          double radius, const cds_rect *rects, int32_t n_rects, uint8_t *zgap_out);

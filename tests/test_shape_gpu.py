@@ -104,7 +104,39 @@ def test_synthetic_pairs_match_oracle(ctx):
         for i, (m, t) in enumerate(zip(pm, pt)):
             z = O.make_zgap(targets[t], 20, rects)
             assert (int(gap[i]), int(hexp[i]), bool(mir[i])) == oms[m].score(targets[t], grads[t], z), (mirror, m, t)
+        # the same pairs with the targets as TIFF files (PackBits and stored, several strip layouts), decoded on the device
+        files = [capi.tiff_encode_rgb(t, (8, 566, 1)[i % 3], 32773 if i % 2 else 1) for i, t in enumerate(targets)]
+        gap2, hexp2, mir2 = sms.score_pairs_tiff(files, grads, None, pm, pt)
+        assert np.array_equal(gap2, gap) and np.array_equal(hexp2, hexp) and np.array_equal(mir2, mir)
         sms.close()
+
+
+def test_shape_pairs_over_many_tiff_files(ctx):
+    """More targets than one upload chunk (32), a has_variants mask, and a bad file that must be named in the error."""
+    rects = O.label_rects(W, H)
+    masks = capi.synth_rgb_host(0, 77, 0, 3, W, H)
+    targets = capi.synth_rgb_host(1, 77, 0, 40, W, H)
+    grads = capi.synth_gradient_host(77, 0, 40, W, H)
+    files = [capi.tiff_encode_rgb(t, 8, 32773) for t in targets]
+    sms = capi.ShapeMaskSet(ctx, W, H, 20, True, rects)
+    sms.add_rgb(masks)
+    rng = np.random.default_rng(5)
+    pm = rng.integers(0, 3, 200)
+    pt = rng.integers(0, 40, 200)
+    has = (np.arange(40) % 7 != 3).astype(np.uint8)
+    a = sms.score_pairs(targets, grads, None, pm, pt, has)
+    b = sms.score_pairs_tiff(files, grads, None, pm, pt, has)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    bad = list(files)
+    bad[33] = b"II*\0" + b"\0" * 60
+    with pytest.raises(capi.CdsError) as e:
+        sms.score_pairs_tiff(bad, grads, None, pm, pt, has)
+    assert "file 33" in str(e.value)
+    c = sms.score_pairs_tiff(files, grads, None, pm, pt, has)            # the context still works
+    for x, y in zip(a, c):
+        assert np.array_equal(x, y)
+    sms.close()
 
 
 def test_roi_mask_matches_oracle(ctx, fixtures):
