@@ -156,6 +156,54 @@ def group_matches_by_mask(matches):
     return groups
 
 
+def group_matches_by_target(matches):
+    """MatchEntitiesGrouping.groupByTargetFields (MatchEntitiesGrouping.java:118-150) with the writer's arguments: the roles are
+    swapped -- the matched image becomes the group's key ("inputImage"), the original mask becomes every result's "image", and
+    the match compute files are taken from the MATCHED image's compute files."""
+    swapped = []
+    for m in matches:
+        tgt = m.get("image")
+        if tgt is None:
+            continue
+        r = OrderedDict((k, v) for k, v in m.items() if k not in ("maskImage", "image", "matchComputeFiles"))
+        r["maskImage"] = tgt
+        r["image"] = m.get("maskImage")
+        swapped.append(_ordered(r))
+    return group_matches_by_mask(swapped)
+
+
+def expand_results_by_mask(group):
+    """MatchEntitiesGrouping.expandResultsByMask (:152-175), the reader's inverse of the grouping: every result gets the group's
+    mask back, with the three compute files restored from its matchComputeFiles, which are then dropped."""
+    out = []
+    for r in group["results"]:
+        mask = OrderedDict(group["inputImage"])
+        cf = OrderedDict(mask.get("computeFiles", {}))
+        for src, dst in MASK_COMPUTE_TO_MATCH:
+            v = r.get("matchComputeFiles", {}).get(dst)
+            if v is not None:
+                cf[src] = v
+        if cf:
+            mask["computeFiles"] = cf
+        m = OrderedDict((k, v) for k, v in r.items() if k != "matchComputeFiles")
+        m["maskImage"] = mask
+        out.append(_ordered(m))
+    return out
+
+
+def write_matches_by_target(matches, out_dir):
+    """JSONNeuronMatchesWriter.writeMatchesByTarget: one <matched mipId>.json per matched image."""
+    os.makedirs(out_dir, exist_ok=True)
+    groups = group_matches_by_target(matches)
+    for key, g in groups.items():
+        if not key or not str(key).strip():
+            continue
+        doc = OrderedDict((("inputImage", g["inputImage"]), ("results", g["results"])))
+        with open(os.path.join(out_dir, "%s.json" % key), "w", encoding="utf-8") as f:
+            f.write(jackson_pretty(doc))
+    return len(groups)
+
+
 def write_matches_by_mask(matches, out_dir):
     """JSONNeuronMatchesWriter.writeMatchesByMask: one <mipId>.json per mask.  Returns the number of files written."""
     os.makedirs(out_dir, exist_ok=True)

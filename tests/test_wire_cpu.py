@@ -101,3 +101,50 @@ def test_matches_from_search_arrays():
     assert [r["mirrored"] for r in g["m0"]["results"]] == [False, True, False]
     assert wire.java_float_str(g["m1"]["results"][0]["matchingPixelsRatio"]) == "0.1"
     assert g["m0"]["results"][0]["matchingPixelsRatio"] == np.float32(50 / 200)
+
+
+def _plain(v):
+    """order-insensitive view of a JSON value"""
+    if isinstance(v, dict):
+        return {k: _plain(x) for k, x in v.items()}
+    if isinstance(v, list):
+        return [_plain(x) for x in v]
+    return float(v) if isinstance(v, float) else v
+
+
+def test_expand_is_the_inverse_of_grouping(sample):
+    """MatchEntitiesGrouping.expandResultsByMask undoes groupByMaskFields: the mask gets its three compute files back, the match
+    compute files disappear -- on the reference's sample every match comes back as it was."""
+    _, matches = sample
+    groups = wire.group_matches_by_mask(matches)
+    back = [m for g in groups.values() for m in wire.expand_results_by_mask(g)]
+    assert len(back) == len(matches)
+    def key(m):
+        return (m["maskImage"]["mipId"], m["image"]["mipId"], m["matchingPixels"], m["maskImage"]["computeFiles"]["InputColorDepthImage"])
+    want = {key(m): m for m in matches}
+    for m in back:
+        o = want[key(m)]
+        # everything but the mask is the match as it was; the mask is the GROUP's key (the first match's mask, ItemsHandling.java:57)
+        # with this match's own three compute files restored
+        assert _plain({k: v for k, v in m.items() if k != "maskImage"}) == _plain({k: v for k, v in o.items() if k not in ("maskImage", "matchComputeFiles")})
+        assert m["maskImage"]["mipId"] == o["maskImage"]["mipId"]
+        for f in ("InputColorDepthImage", "GradientImage", "ZGapImage"):
+            assert m["maskImage"]["computeFiles"][f] == o["maskImage"]["computeFiles"][f]
+
+
+def test_grouping_by_target(sample, tmp_path):
+    _, matches = sample
+    groups = wire.group_matches_by_target(matches)
+    assert set(groups) == {m["image"]["mipId"] for m in matches}
+    for key, g in groups.items():
+        assert g["inputImage"]["mipId"] == key
+        for gone in ("InputColorDepthImage", "GradientImage", "ZGapImage"):
+            assert gone not in g["inputImage"].get("computeFiles", {})
+        px = [r["matchingPixels"] for r in g["results"]]
+        assert px == sorted(px, reverse=True)
+        for r in g["results"]:
+            assert "maskImage" not in r
+            assert r["image"]["class"].endswith("EMNeuronEntity")           # the original mask is now the result's image
+            src = [m for m in matches if m["image"]["mipId"] == key][0]["image"]["computeFiles"]
+            assert r["matchComputeFiles"]["MaskColorDepthImage"] == src["InputColorDepthImage"]
+    assert wire.write_matches_by_target(matches, str(tmp_path)) == len(groups) == len(os.listdir(tmp_path))
