@@ -117,6 +117,7 @@ SIGNATURES = {
     "cds_get_last_stats": (C.c_int32, [_vp, C.POINTER(SearchStats)]),
     "cds_debug_encode_colors": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, _u32p]),
     "cds_debug_class_intervals": (C.c_int32, [C.c_double, C.c_int32, C.c_int32, _u32p, _u32p, _u32p, _u32p]),
+    "cds_debug_slice_numbers": (C.c_int32, [_vp, _vp, C.c_int64, _u16p]),
 }
 
 
@@ -227,6 +228,12 @@ class Context:
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
         out = np.empty(len(rgb), np.uint32)
         _check(lib().cds_debug_encode_colors(self.h, _ptr(rgb), len(rgb), int(data_threshold), out.ctypes.data_as(_u32p)), self.h)
+        return out
+
+    def debug_slice_numbers(self, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+        out = np.empty(len(rgb), np.uint16)
+        _check(lib().cds_debug_slice_numbers(self.h, _ptr(rgb), len(rgb), out.ctypes.data_as(_u16p)), self.h)
         return out
 
     def make_zgap(self, rgb, threshold, radius, rects):

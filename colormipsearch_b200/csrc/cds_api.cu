@@ -157,64 +157,66 @@ extern "C" const char *cds_last_error(const cds_ctx *ctx)
 
 extern "C" cds_status cds_ctx_create(const int32_t *device_ids, int32_t n_dev, cds_ctx **out)
 {
-    if (!out) { set_tls_error("cds_ctx_create: out is NULL"); return CDS_ERR_BAD_ARG; }
-    *out = nullptr;
-    int visible = 0;
-    cudaError_t e = cudaGetDeviceCount(&visible);
-    if (e != cudaSuccess || visible == 0) {
-        cudaGetLastError();
-        set_tls_error(std::string("cds_ctx_create: no CUDA device (") + (e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)) +
-                      "); libcdsgpu has no CPU fallback");
-        return CDS_ERR_NO_DEVICE;
-    }
-    if (n_dev < 0) { set_tls_error("cds_ctx_create: n_dev < 0"); return CDS_ERR_BAD_ARG; }
-    if (n_dev == 0) { n_dev = visible; device_ids = nullptr; }
-    auto ctx = new cds_ctx();
-    for (int i = 0; i < n_dev; i++) {
-        int id = device_ids ? device_ids[i] : i;
-        if (id < 0 || id >= visible) {
-            set_tls_error("cds_ctx_create: device id out of range");
-            cds_ctx_destroy(ctx);
+    return cds::abi_guard("cds_ctx_create", [&]() -> cds_status {
+        if (!out) { set_tls_error("cds_ctx_create: out is NULL"); return CDS_ERR_BAD_ARG; }
+        *out = nullptr;
+        int visible = 0;
+        cudaError_t e = cudaGetDeviceCount(&visible);
+        if (e != cudaSuccess || visible == 0) {
+            cudaGetLastError();
+            set_tls_error(std::string("cds_ctx_create: no CUDA device (") + (e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)) +
+                          "); libcdsgpu has no CPU fallback");
             return CDS_ERR_NO_DEVICE;
         }
-        DevState d;
-        d.dev = id;
-        ctx->devs.push_back(d);
-    }
-    const RatioTable &rt = ratio_table();
-    if ((int) rt.ratios.size() != CDS_NUM_RANKS) {
-        set_tls_error("cds_ctx_create: ratio table self-check failed");
-        cds_ctx_destroy(ctx);
-        return CDS_ERR_UNSUPPORTED;
-    }
-    for (DevState &d : ctx->devs) {
-        cds_status s = ctx->check(cudaSetDevice(d.dev), "cudaSetDevice");
-        if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        for (int i = 0; i < 2 && s == CDS_OK; i++) {
-            s = ctx->check(cudaEventCreateWithFlags(&d.up_done[i], cudaEventDisableTiming), "cudaEventCreate");
-            if (s == CDS_OK) s = ctx->check(cudaEventCreateWithFlags(&d.up_free[i], cudaEventDisableTiming), "cudaEventCreate");
-        }
-        if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev0), "cudaEventCreate");
-        if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev1), "cudaEventCreate");
-        if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev2), "cudaEventCreate");
-        if (s == CDS_OK) s = ctx->check(cudaMalloc(&d.d_rank_tab, rt.rank.size() * sizeof(uint16_t)), "cudaMalloc(rank table)");
-        if (s == CDS_OK) s = ctx->check(cudaMemcpy(d.d_rank_tab, rt.rank.data(), rt.rank.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "cudaMemcpy(rank table)");
-        if (s != CDS_OK) { cds_ctx_destroy(ctx); return s; }
-    }
-    // peer access between the context's devices (mask replication); failure is not fatal
-    for (DevState &a : ctx->devs)
-        for (DevState &b : ctx->devs) {
-            if (a.dev == b.dev) continue;
-            int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, a.dev, b.dev) == cudaSuccess && can) {
-                cudaSetDevice(a.dev);
-                cudaDeviceEnablePeerAccess(b.dev, 0);
-                cudaGetLastError();
+        if (n_dev < 0) { set_tls_error("cds_ctx_create: n_dev < 0"); return CDS_ERR_BAD_ARG; }
+        if (n_dev == 0) { n_dev = visible; device_ids = nullptr; }
+        auto ctx = new cds_ctx();
+        for (int i = 0; i < n_dev; i++) {
+            int id = device_ids ? device_ids[i] : i;
+            if (id < 0 || id >= visible) {
+                set_tls_error("cds_ctx_create: device id out of range");
+                cds_ctx_destroy(ctx);
+                return CDS_ERR_NO_DEVICE;
             }
+            DevState d;
+            d.dev = id;
+            ctx->devs.push_back(d);
         }
-    *out = ctx;
-    return CDS_OK;
+        const RatioTable &rt = ratio_table();
+        if ((int) rt.ratios.size() != CDS_NUM_RANKS) {
+            set_tls_error("cds_ctx_create: ratio table self-check failed");
+            cds_ctx_destroy(ctx);
+            return CDS_ERR_UNSUPPORTED;
+        }
+        for (DevState &d : ctx->devs) {
+            cds_status s = ctx->check(cudaSetDevice(d.dev), "cudaSetDevice");
+            if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            for (int i = 0; i < 2 && s == CDS_OK; i++) {
+                s = ctx->check(cudaEventCreateWithFlags(&d.up_done[i], cudaEventDisableTiming), "cudaEventCreate");
+                if (s == CDS_OK) s = ctx->check(cudaEventCreateWithFlags(&d.up_free[i], cudaEventDisableTiming), "cudaEventCreate");
+            }
+            if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev0), "cudaEventCreate");
+            if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev1), "cudaEventCreate");
+            if (s == CDS_OK) s = ctx->check(cudaEventCreate(&d.ev2), "cudaEventCreate");
+            if (s == CDS_OK) s = ctx->check(cudaMalloc(&d.d_rank_tab, rt.rank.size() * sizeof(uint16_t)), "cudaMalloc(rank table)");
+            if (s == CDS_OK) s = ctx->check(cudaMemcpy(d.d_rank_tab, rt.rank.data(), rt.rank.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "cudaMemcpy(rank table)");
+            if (s != CDS_OK) { cds_ctx_destroy(ctx); return s; }
+        }
+        // peer access between the context's devices (mask replication); failure is not fatal
+        for (DevState &a : ctx->devs)
+            for (DevState &b : ctx->devs) {
+                if (a.dev == b.dev) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, a.dev, b.dev) == cudaSuccess && can) {
+                    cudaSetDevice(a.dev);
+                    cudaDeviceEnablePeerAccess(b.dev, 0);
+                    cudaGetLastError();
+                }
+            }
+        *out = ctx;
+        return CDS_OK;
+    });
 }
 
 extern "C" void cds_ctx_destroy(cds_ctx *ctx)
@@ -233,6 +235,7 @@ extern "C" void cds_ctx_destroy(cds_ctx *ctx)
         if (d.match_scratch.acc) cudaFree(d.match_scratch.acc);
         d.pool.release_all();
         d.sb.release();
+        shape_release_dev(d);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev2) cudaEventDestroy(d.ev2);
@@ -251,55 +254,63 @@ extern "C" int32_t cds_ctx_num_devices(const cds_ctx *ctx) { return ctx ? (int32
 
 extern "C" cds_status cds_host_alloc(cds_ctx *ctx, uint64_t bytes, void **out)
 {
-    if (!ctx || !out) { set_tls_error("cds_host_alloc: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    *out = nullptr;
-    CDS_CUDA(ctx, cudaSetDevice(ctx->devs[0].dev));
-    CDS_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
-    return CDS_OK;
+    return cds::abi_guard("cds_host_alloc", [&]() -> cds_status {
+        if (!ctx || !out) { set_tls_error("cds_host_alloc: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        *out = nullptr;
+        CDS_CUDA(ctx, cudaSetDevice(ctx->devs[0].dev));
+        CDS_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+        return CDS_OK;
+    });
 }
 
 extern "C" cds_status cds_host_free(cds_ctx *ctx, void *p)
 {
-    if (!ctx) { set_tls_error("cds_host_free: NULL ctx"); return CDS_ERR_BAD_ARG; }
-    if (!p) return CDS_OK;
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    CDS_CUDA(ctx, cudaFreeHost(p));
-    return CDS_OK;
+    return cds::abi_guard("cds_host_free", [&]() -> cds_status {
+        if (!ctx) { set_tls_error("cds_host_free: NULL ctx"); return CDS_ERR_BAD_ARG; }
+        if (!p) return CDS_OK;
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        CDS_CUDA(ctx, cudaFreeHost(p));
+        return CDS_OK;
+    });
 }
 
 extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t value)
 {
-    if (!ctx || !name) { set_tls_error("cds_ctx_set_option: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (std::strcmp(name, "match_kernel") == 0) {
-        if (value < 0 || value > 3) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: match_kernel must be 0..3");
-        ctx->match_kernel = (int) value;
-        return CDS_OK;
-    }
-    if (std::strcmp(name, "resident_occupancy") == 0) {
-        ctx->resident_occupancy = value != 0;
-        return CDS_OK;
-    }
-    if (std::strcmp(name, "stream_chunk") == 0) {
-        if (value < 1 || value > 65536) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk must be 1..65536");
-        ctx->stream_chunk = value;
-        return CDS_OK;
-    }
-    if (std::strcmp(name, "stream_chunk_tiff") == 0) {
-        if (value < 1 || value > 32768) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk_tiff must be 1..32768");
-        ctx->stream_chunk_tiff = value;
-        return CDS_OK;
-    }
-    return ctx->fail(CDS_ERR_BAD_ARG, std::string("cds_ctx_set_option: unknown option ") + name);
+    return cds::abi_guard("cds_ctx_set_option", [&]() -> cds_status {
+        if (!ctx || !name) { set_tls_error("cds_ctx_set_option: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (std::strcmp(name, "match_kernel") == 0) {
+            if (value < 0 || value > 3) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: match_kernel must be 0..3");
+            ctx->match_kernel = (int) value;
+            return CDS_OK;
+        }
+        if (std::strcmp(name, "resident_occupancy") == 0) {
+            ctx->resident_occupancy = value != 0;
+            return CDS_OK;
+        }
+        if (std::strcmp(name, "stream_chunk") == 0) {
+            if (value < 1 || value > 65536) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk must be 1..65536");
+            ctx->stream_chunk = value;
+            return CDS_OK;
+        }
+        if (std::strcmp(name, "stream_chunk_tiff") == 0) {
+            if (value < 1 || value > 32768) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk_tiff must be 1..32768");
+            ctx->stream_chunk_tiff = value;
+            return CDS_OK;
+        }
+        return ctx->fail(CDS_ERR_BAD_ARG, std::string("cds_ctx_set_option: unknown option ") + name);
+    });
 }
 
 extern "C" cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out)
 {
-    if (!ctx || !out) { set_tls_error("cds_get_last_stats: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    *out = ctx->stats;
-    return CDS_OK;
+    return cds::abi_guard("cds_get_last_stats", [&]() -> cds_status {
+        if (!ctx || !out) { set_tls_error("cds_get_last_stats: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        *out = ctx->stats;
+        return CDS_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------------ library
@@ -397,45 +408,47 @@ cds_status cds_library::ensure_occupancy(int rings)
 
 extern "C" cds_status cds_library_create(cds_ctx *ctx, int32_t width, int32_t height, int64_t capacity, cds_library **out)
 {
-    if (!ctx || !out) { set_tls_error("cds_library_create: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    *out = nullptr;
-    if (width <= 0 || height <= 0 || width > 16384 || height > 16384 || capacity <= 0)
-        return ctx->fail(CDS_ERR_BAD_ARG, "cds_library_create: width/height must be in 1..16384 and capacity > 0");
-    auto lib = new cds_library();
-    lib->ctx = ctx;
-    lib->g.W = width;
-    lib->g.H = height;
-    lib->g.pitch = choose_pitch(width);
-    lib->g.guard = CDS_GUARD_ROWS;
-    lib->bpitch = occupancy_tile_pitch(width);
-    lib->capacity = capacity;
-    lib->baked_threshold = 20;
-    int D = (int) ctx->devs.size();
-    lib->shards.resize(D);
-    int64_t blocks = (capacity + kLibBlock - 1) / kLibBlock;
-    int64_t blocks_per_dev = (blocks + D - 1) / D;
-    for (int d = 0; d < D; d++) {
-        DevState &ds = ctx->devs[d];
-        cds_status s = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
-        int64_t cap_local = blocks_per_dev * kLibBlock;
-        if (cap_local > capacity && D == 1) cap_local = capacity;
-        size_t words = lib->g.total_words(cap_local);
-        if (s == CDS_OK) s = ctx->check(cudaMalloc(&lib->shards[d].planes, words * sizeof(uint32_t)), "cudaMalloc(library planes)");
-        if (s == CDS_OK) {
-            lib->shards[d].cap_local = cap_local;
-            launch_fill_words(lib->shards[d].planes, words, CDS_CODE_PAD_WORD, ds.stream);
-            s = ctx->check(cudaGetLastError(), "fill_words_kernel");
+    return cds::abi_guard("cds_library_create", [&]() -> cds_status {
+        if (!ctx || !out) { set_tls_error("cds_library_create: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        *out = nullptr;
+        if (width <= 0 || height <= 0 || width > 16384 || height > 16384 || capacity <= 0)
+            return ctx->fail(CDS_ERR_BAD_ARG, "cds_library_create: width/height must be in 1..16384 and capacity > 0");
+        auto lib = new cds_library();
+        lib->ctx = ctx;
+        lib->g.W = width;
+        lib->g.H = height;
+        lib->g.pitch = choose_pitch(width);
+        lib->g.guard = CDS_GUARD_ROWS;
+        lib->bpitch = occupancy_tile_pitch(width);
+        lib->capacity = capacity;
+        lib->baked_threshold = 20;
+        int D = (int) ctx->devs.size();
+        lib->shards.resize(D);
+        int64_t blocks = (capacity + kLibBlock - 1) / kLibBlock;
+        int64_t blocks_per_dev = (blocks + D - 1) / D;
+        for (int d = 0; d < D; d++) {
+            DevState &ds = ctx->devs[d];
+            cds_status s = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+            int64_t cap_local = blocks_per_dev * kLibBlock;
+            if (cap_local > capacity && D == 1) cap_local = capacity;
+            size_t words = lib->g.total_words(cap_local);
+            if (s == CDS_OK) s = ctx->check(cudaMalloc(&lib->shards[d].planes, words * sizeof(uint32_t)), "cudaMalloc(library planes)");
+            if (s == CDS_OK) {
+                lib->shards[d].cap_local = cap_local;
+                launch_fill_words(lib->shards[d].planes, words, CDS_CODE_PAD_WORD, ds.stream);
+                s = ctx->check(cudaGetLastError(), "fill_words_kernel");
+            }
+            if (s != CDS_OK) { cds_library_destroy(lib); return s; }
         }
-        if (s != CDS_OK) { cds_library_destroy(lib); return s; }
-    }
-    for (int d = 0; d < D; d++) {
-        cudaSetDevice(ctx->devs[d].dev);
-        cds_status s = ctx->check(cudaStreamSynchronize(ctx->devs[d].stream), "library init");
-        if (s != CDS_OK) { cds_library_destroy(lib); return s; }
-    }
-    *out = lib;
-    return CDS_OK;
+        for (int d = 0; d < D; d++) {
+            cudaSetDevice(ctx->devs[d].dev);
+            cds_status s = ctx->check(cudaStreamSynchronize(ctx->devs[d].stream), "library init");
+            if (s != CDS_OK) { cds_library_destroy(lib); return s; }
+        }
+        *out = lib;
+        return CDS_OK;
+    });
 }
 
 extern "C" void cds_library_destroy(cds_library *lib)
@@ -458,11 +471,13 @@ extern "C" int64_t cds_library_size(const cds_library *lib) { return lib ? lib->
 
 extern "C" cds_status cds_library_clear(cds_library *lib)
 {
-    if (!lib) { set_tls_error("cds_library_clear: NULL library"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(lib->ctx->mu);
-    lib->size = 0;
-    for (auto &sh : lib->shards) sh.occ_done = 0;
-    return CDS_OK;
+    return cds::abi_guard("cds_library_clear", [&]() -> cds_status {
+        if (!lib) { set_tls_error("cds_library_clear: NULL library"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(lib->ctx->mu);
+        lib->size = 0;
+        for (auto &sh : lib->shards) sh.occ_done = 0;
+        return CDS_OK;
+    });
 }
 
 // Upload `n` RGB images that occupy consecutive global indices starting at lib->size.  `src` supplies the pixels of a run
@@ -507,16 +522,18 @@ cds_status library_append(cds_library *lib, int64_t n,
 
 extern "C" cds_status cds_library_add_rgb(cds_library *lib, const uint8_t *rgb, int64_t n, int64_t *first_index)
 {
-    if (!lib) { set_tls_error("cds_library_add_rgb: NULL library"); return CDS_ERR_BAD_ARG; }
-    cds_ctx *ctx = lib->ctx;
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (!rgb && n > 0) return ctx->fail(CDS_ERR_BAD_ARG, "cds_library_add_rgb: rgb is NULL");
-    const size_t img_bytes = (size_t) lib->g.W * lib->g.H * 3;
-    return library_append(lib, n, [&](DevState &ds, int64_t i0, int64_t cnt, uint8_t *d_rgb) -> cds_status {
-        CDS_CUDA(ctx, cudaMemcpyAsync(d_rgb, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, ds.stream));
-        ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
-        return CDS_OK;
-    }, first_index);
+    return cds::abi_guard("cds_library_add_rgb", [&]() -> cds_status {
+        if (!lib) { set_tls_error("cds_library_add_rgb: NULL library"); return CDS_ERR_BAD_ARG; }
+        cds_ctx *ctx = lib->ctx;
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (!rgb && n > 0) return ctx->fail(CDS_ERR_BAD_ARG, "cds_library_add_rgb: rgb is NULL");
+        const size_t img_bytes = (size_t) lib->g.W * lib->g.H * 3;
+        return library_append(lib, n, [&](DevState &ds, int64_t i0, int64_t cnt, uint8_t *d_rgb) -> cds_status {
+            CDS_CUDA(ctx, cudaMemcpyAsync(d_rgb, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, ds.stream));
+            ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
+            return CDS_OK;
+        }, first_index);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------------ mask sets
@@ -541,45 +558,47 @@ static cds_status make_shift_set(int xy_shift, int mirror, ShiftSet &out)
 
 extern "C" cds_status cds_maskset_create(cds_ctx *ctx, int32_t width, int32_t height, const cds_pixparams *params, cds_maskset **out)
 {
-    if (!ctx || !out || !params) { set_tls_error("cds_maskset_create: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    *out = nullptr;
-    if (width <= 0 || height <= 0 || width > 16384 || height > 16384)
-        return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: width/height must be in 1..16384");
-    if (params->xy_shift & 1) return ctx->fail(CDS_ERR_BAD_ARG, "XY shift parameter must be an even number.");
-    if (params->xy_shift < 0) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: xy_shift < 0");
-    if (params->xy_shift > CDS_MAX_XY_SHIFT) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: xy_shift > CDS_MAX_XY_SHIFT");
-    if (params->n_rects < 0 || params->n_rects > CDS_MAX_RECTS) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: n_rects out of range");
-    if (!(params->z_tolerance < 1000.0) && !std::isnan(params->z_tolerance))
-        return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: z_tolerance >= 1000 is not supported");
-    auto ms = new cds_maskset();
-    ms->ctx = ctx;
-    ms->W = width;
-    ms->H = height;
-    ms->params = *params;
-    if (make_shift_set(params->xy_shift, params->mirror, ms->shifts) != CDS_OK) {
-        delete ms;
-        return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: too many shift offsets");
-    }
-    ms->rects.n = params->n_rects;
-    for (int i = 0; i < params->n_rects; i++) {
-        ms->rects.x0[i] = params->rects[i].x0; ms->rects.y0[i] = params->rects[i].y0;
-        ms->rects.x1[i] = params->rects[i].x1; ms->rects.y1[i] = params->rects[i].y1;
-    }
-    ms->d_descs.assign(ctx->devs.size(), nullptr);
-    ms->d_groups.assign(ctx->devs.size(), nullptr);
-    ms->d_palettes.assign(ctx->devs.size(), nullptr);
-    ms->d_words.assign(ctx->devs.size(), nullptr);
-    ms->d_wstart.assign(ctx->devs.size(), nullptr);
-    ms->store.resize(ctx->devs.size());
-    // build (or fetch) the interval table now so that a bad tolerance fails here
-    for (DevState &ds : ctx->devs) {
-        const cds_class_interval *tab;
-        cds_status s = ctx->class_table_on(ds, params->z_tolerance, &tab);
-        if (s != CDS_OK) { delete ms; return s; }
-    }
-    *out = ms;
-    return CDS_OK;
+    return cds::abi_guard("cds_maskset_create", [&]() -> cds_status {
+        if (!ctx || !out || !params) { set_tls_error("cds_maskset_create: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        *out = nullptr;
+        if (width <= 0 || height <= 0 || width > 16384 || height > 16384)
+            return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: width/height must be in 1..16384");
+        if (params->xy_shift & 1) return ctx->fail(CDS_ERR_BAD_ARG, "XY shift parameter must be an even number.");
+        if (params->xy_shift < 0) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: xy_shift < 0");
+        if (params->xy_shift > CDS_MAX_XY_SHIFT) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: xy_shift > CDS_MAX_XY_SHIFT");
+        if (params->n_rects < 0 || params->n_rects > CDS_MAX_RECTS) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_create: n_rects out of range");
+        if (!(params->z_tolerance < 1000.0) && !std::isnan(params->z_tolerance))
+            return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: z_tolerance >= 1000 is not supported");
+        auto ms = new cds_maskset();
+        ms->ctx = ctx;
+        ms->W = width;
+        ms->H = height;
+        ms->params = *params;
+        if (make_shift_set(params->xy_shift, params->mirror, ms->shifts) != CDS_OK) {
+            delete ms;
+            return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_maskset_create: too many shift offsets");
+        }
+        ms->rects.n = params->n_rects;
+        for (int i = 0; i < params->n_rects; i++) {
+            ms->rects.x0[i] = params->rects[i].x0; ms->rects.y0[i] = params->rects[i].y0;
+            ms->rects.x1[i] = params->rects[i].x1; ms->rects.y1[i] = params->rects[i].y1;
+        }
+        ms->d_descs.assign(ctx->devs.size(), nullptr);
+        ms->d_groups.assign(ctx->devs.size(), nullptr);
+        ms->d_palettes.assign(ctx->devs.size(), nullptr);
+        ms->d_words.assign(ctx->devs.size(), nullptr);
+        ms->d_wstart.assign(ctx->devs.size(), nullptr);
+        ms->store.resize(ctx->devs.size());
+        // build (or fetch) the interval table now so that a bad tolerance fails here
+        for (DevState &ds : ctx->devs) {
+            const cds_class_interval *tab;
+            cds_status s = ctx->class_table_on(ds, params->z_tolerance, &tab);
+            if (s != CDS_OK) { delete ms; return s; }
+        }
+        *out = ms;
+        return CDS_OK;
+    });
 }
 
 extern "C" void cds_maskset_destroy(cds_maskset *ms)
@@ -608,10 +627,12 @@ extern "C" int32_t cds_maskset_size(const cds_maskset *ms) { return ms ? (int32_
 
 extern "C" cds_status cds_maskset_get_mask_sizes(const cds_maskset *ms, int32_t *sizes_out)
 {
-    if (!ms || !sizes_out) { set_tls_error("cds_maskset_get_mask_sizes: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ms->ctx->mu);
-    std::copy(ms->sizes.begin(), ms->sizes.end(), sizes_out);
-    return CDS_OK;
+    return cds::abi_guard("cds_maskset_get_mask_sizes", [&]() -> cds_status {
+        if (!ms || !sizes_out) { set_tls_error("cds_maskset_get_mask_sizes: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ms->ctx->mu);
+        std::copy(ms->sizes.begin(), ms->sizes.end(), sizes_out);
+        return CDS_OK;
+    });
 }
 
 // Makes room for `used + more` bytes in a device arena; contents are preserved (device-to-device copy on growth).
@@ -636,8 +657,43 @@ static cds_status arena_reserve(cds_ctx *ctx, DevState &ds, cds_maskset::Arena &
 // whatever produces the pixels of masks [i0, i0 + cnt) of the call at `stage` (an H2D copy, or an upload of TIFF files and
 // their decode).
 namespace cds {
+static cds_status maskset_append_body(cds_maskset *ms, int32_t n, int32_t *mask_size_out,
+                                      const std::function<cds_status(int i0, int cnt, uint8_t *stage, cudaStream_t stream)> &fill);
+
+// All or nothing: when the append fails half way (an undecodable file in a later chunk, an allocation failure), everything that
+// is still in flight is drained and the mask set is rolled back to what it held before the call -- sizes, record offsets and the
+// arenas of every device -- so that the next search never meets descriptors that disagree with the arenas.
 cds_status maskset_append(cds_maskset *ms, int32_t n, int32_t *mask_size_out,
                           const std::function<cds_status(int i0, int cnt, uint8_t *stage, cudaStream_t stream)> &fill)
+{
+    cds_ctx *ctx = ms->ctx;
+    const size_t first_mask = ms->sizes.size();
+    const cds_maskset::DevStore &s0 = ms->store[0];
+    const size_t used0[4] = {s0.records.used, s0.classes.used, s0.crec.used, s0.rowstart.used};
+    const cds_status st = maskset_append_body(ms, n, mask_size_out, fill);
+    if (st == CDS_OK) return CDS_OK;
+    const std::string msg = ctx->err;
+    for (DevState &ds : ctx->devs) {
+        if (cudaSetDevice(ds.dev) != cudaSuccess) continue;
+        cudaStreamSynchronize(ds.copy_stream);
+        cudaStreamSynchronize(ds.stream);
+    }
+    cudaGetLastError();
+    ms->sizes.resize(first_mask);
+    ms->rec_offset.resize(first_mask);
+    for (cds_maskset::DevStore &sd : ms->store) {
+        sd.records.used = std::min(sd.records.used, used0[0]);
+        sd.classes.used = std::min(sd.classes.used, used0[1]);
+        sd.crec.used = std::min(sd.crec.used, used0[2]);
+        sd.rowstart.used = std::min(sd.rowstart.used, used0[3]);
+    }
+    ms->descs_dirty = true;
+    cudaSetDevice(ctx->devs[0].dev);
+    return ctx->fail(st, msg);
+}
+
+static cds_status maskset_append_body(cds_maskset *ms, int32_t n, int32_t *mask_size_out,
+                                      const std::function<cds_status(int i0, int cnt, uint8_t *stage, cudaStream_t stream)> &fill)
 {
     cds_ctx *ctx = ms->ctx;
     const int D = (int) ctx->devs.size();
@@ -741,16 +797,18 @@ cds_status maskset_append(cds_maskset *ms, int32_t n, int32_t *mask_size_out,
 
 extern "C" cds_status cds_maskset_add_rgb(cds_maskset *ms, const uint8_t *rgb, int32_t n, int32_t *mask_size_out)
 {
-    if (!ms) { set_tls_error("cds_maskset_add_rgb: NULL mask set"); return CDS_ERR_BAD_ARG; }
-    cds_ctx *ctx = ms->ctx;
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (n < 0 || (!rgb && n > 0)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_rgb: bad arguments");
-    if (n == 0) return CDS_OK;
-    const size_t img_bytes = (size_t) ms->W * ms->H * 3;
-    return maskset_append(ms, n, mask_size_out, [&](int i0, int cnt, uint8_t *stage, cudaStream_t stream) -> cds_status {
-        CDS_CUDA(ctx, cudaMemcpyAsync(stage, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, stream));
-        ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
-        return CDS_OK;
+    return cds::abi_guard("cds_maskset_add_rgb", [&]() -> cds_status {
+        if (!ms) { set_tls_error("cds_maskset_add_rgb: NULL mask set"); return CDS_ERR_BAD_ARG; }
+        cds_ctx *ctx = ms->ctx;
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || (!rgb && n > 0)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_rgb: bad arguments");
+        if (n == 0) return CDS_OK;
+        const size_t img_bytes = (size_t) ms->W * ms->H * 3;
+        return maskset_append(ms, n, mask_size_out, [&](int i0, int cnt, uint8_t *stage, cudaStream_t stream) -> cds_status {
+            CDS_CUDA(ctx, cudaMemcpyAsync(stage, rgb + (size_t) i0 * img_bytes, (size_t) cnt * img_bytes, cudaMemcpyHostToDevice, stream));
+            ctx->stats.h2d_bytes += (int64_t) cnt * (int64_t) img_bytes;
+            return CDS_OK;
+        });
     });
 }
 
@@ -1014,69 +1072,71 @@ void reset_stats(cds_ctx *ctx)
 
 extern "C" cds_status cds_search_dense(cds_ctx *ctx, const cds_maskset *ms_c, cds_library *lib, int32_t *scores, uint8_t *mirrored)
 {
-    if (!ctx || !ms_c || !lib) { set_tls_error("cds_search_dense: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
-    CDS_TRY(check_search_args(ctx, ms, lib));
-    const int M = (int) ms->sizes.size();
-    const int64_t T = lib->size;
-    if (M == 0 || T == 0) return CDS_OK;
-    if (!scores) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_dense: scores is NULL");
-    reset_stats(ctx);
-    CDS_TRY(ms->sync_descs());
-    CDS_TRY(lib->bake(ms->params.data_threshold));
-    if (batched_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
-    const int D = lib->n_dev();
-    // mask chunking bounds the per-device score buffer to ~256 MiB
-    std::vector<int32_t *> d_scores(D, nullptr);
-    cds_status st = CDS_OK;
-    int64_t max_local = 0;
-    for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
-    int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 64 << 20) / std::max<int64_t>(max_local, 1)));
-    if (mchunk < M && mchunk > CDS_PALETTE_GROUP) mchunk -= mchunk % CDS_PALETTE_GROUP;   // keep chunks aligned to palette groups
-    for (int d = 0; d < D && st == CDS_OK; d++) {
-        st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
-        if (st == CDS_OK) st = ctx->ensure_scratch(ctx->devs[d], 0, (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t), (void **) &d_scores[d]);
-        if (st == CDS_OK) st = ctx->ensure_pinned(ctx->devs[d], (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t));
-    }
-    double match_ms = 0;
-    for (int m0 = 0; m0 < M && st == CDS_OK; m0 += mchunk) {
-        const int mc = std::min(mchunk, M - m0);
+    return cds::abi_guard("cds_search_dense", [&]() -> cds_status {
+        if (!ctx || !ms_c || !lib) { set_tls_error("cds_search_dense: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
+        CDS_TRY(check_search_args(ctx, ms, lib));
+        const int M = (int) ms->sizes.size();
+        const int64_t T = lib->size;
+        if (M == 0 || T == 0) return CDS_OK;
+        if (!scores) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_dense: scores is NULL");
+        reset_stats(ctx);
+        CDS_TRY(ms->sync_descs());
+        CDS_TRY(lib->bake(ms->params.data_threshold));
+        if (batched_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks()) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
+        const int D = lib->n_dev();
+        // mask chunking bounds the per-device score buffer to ~256 MiB
+        std::vector<int32_t *> d_scores(D, nullptr);
+        cds_status st = CDS_OK;
+        int64_t max_local = 0;
+        for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
+        int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 64 << 20) / std::max<int64_t>(max_local, 1)));
+        if (mchunk < M && mchunk > CDS_PALETTE_GROUP) mchunk -= mchunk % CDS_PALETTE_GROUP;   // keep chunks aligned to palette groups
         for (int d = 0; d < D && st == CDS_OK; d++) {
-            const int64_t nl = lib->local_size(d);
-            if (nl == 0) continue;
-            DevState &ds = ctx->devs[d];
-            st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
-            if (st == CDS_OK) st = launch_match(ctx, ms, lib, d, m0, mc, nl, d_scores[d]);
-            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(ds.h_pinned, d_scores[d], (size_t) mc * nl * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "scores D2H");
-            ctx->stats.d2h_bytes += (int64_t) mc * nl * (int64_t) sizeof(int32_t);
+            st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
+            if (st == CDS_OK) st = ctx->ensure_scratch(ctx->devs[d], 0, (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t), (void **) &d_scores[d]);
+            if (st == CDS_OK) st = ctx->ensure_pinned(ctx->devs[d], (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t));
         }
-        double chunk_ms = 0;
-        for (int d = 0; d < D && st == CDS_OK; d++) {
-            const int64_t nl = lib->local_size(d);
-            if (nl == 0) continue;
-            DevState &ds = ctx->devs[d];
-            cudaSetDevice(ds.dev);
-            st = ctx->check(cudaStreamSynchronize(ds.stream), "pixel match");
-            if (st != CDS_OK) break;
-            float ms_f = 0;
-            cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev1);
-            chunk_ms = std::max(chunk_ms, (double) ms_f);
-            const int32_t *h = (const int32_t *) ds.h_pinned;
-            for (int mi = 0; mi < mc; mi++)
-                for (int64_t l = 0; l < nl; l++) {
-                    int32_t w = h[(size_t) mi * nl + l];
-                    size_t o = (size_t) (m0 + mi) * T + lib->global_of(d, l);
-                    scores[o] = w & ~CDS_SCORE_MIRROR_BIT;
-                    if (mirrored) mirrored[o] = (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0;
-                }
+        double match_ms = 0;
+        for (int m0 = 0; m0 < M && st == CDS_OK; m0 += mchunk) {
+            const int mc = std::min(mchunk, M - m0);
+            for (int d = 0; d < D && st == CDS_OK; d++) {
+                const int64_t nl = lib->local_size(d);
+                if (nl == 0) continue;
+                DevState &ds = ctx->devs[d];
+                st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+                if (st == CDS_OK) st = launch_match(ctx, ms, lib, d, m0, mc, nl, d_scores[d]);
+                if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(ds.h_pinned, d_scores[d], (size_t) mc * nl * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "scores D2H");
+                ctx->stats.d2h_bytes += (int64_t) mc * nl * (int64_t) sizeof(int32_t);
+            }
+            double chunk_ms = 0;
+            for (int d = 0; d < D && st == CDS_OK; d++) {
+                const int64_t nl = lib->local_size(d);
+                if (nl == 0) continue;
+                DevState &ds = ctx->devs[d];
+                cudaSetDevice(ds.dev);
+                st = ctx->check(cudaStreamSynchronize(ds.stream), "pixel match");
+                if (st != CDS_OK) break;
+                float ms_f = 0;
+                cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev1);
+                chunk_ms = std::max(chunk_ms, (double) ms_f);
+                const int32_t *h = (const int32_t *) ds.h_pinned;
+                for (int mi = 0; mi < mc; mi++)
+                    for (int64_t l = 0; l < nl; l++) {
+                        int32_t w = h[(size_t) mi * nl + l];
+                        size_t o = (size_t) (m0 + mi) * T + lib->global_of(d, l);
+                        scores[o] = w & ~CDS_SCORE_MIRROR_BIT;
+                        if (mirrored) mirrored[o] = (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0;
+                    }
+            }
+            match_ms += chunk_ms;
         }
-        match_ms += chunk_ms;
-    }
-    ctx->stats.match_kernel_ms = match_ms;
-    ctx->stats.total_device_ms = match_ms;
-    ctx->stats.comparisons = (int64_t) M * T;
-    return st;
+        ctx->stats.match_kernel_ms = match_ms;
+        ctx->stats.total_device_ms = match_ms;
+        ctx->stats.comparisons = (int64_t) M * T;
+        return st;
+    });
 }
 
 // smallest score s in [1, P] with ColorMIPSearch.isMatch true (API/cds/ColorMIPSearch.java:42-45); P+1 when none.
@@ -1096,187 +1156,191 @@ int32_t min_matching_score(int32_t P, double pct_positive_pixels)
 extern "C" cds_status cds_search_topk(cds_ctx *ctx, const cds_maskset *ms_c, cds_library *lib, int32_t k, double pct_positive_pixels,
                                       int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
 {
-    if (!ctx || !ms_c || !lib) { set_tls_error("cds_search_topk: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
-    CDS_TRY(check_search_args(ctx, ms, lib));
-    if (k <= 0 || k > topk_max_k()) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_topk: k must be in 1..4096");
-    const int M = (int) ms->sizes.size();
-    const int64_t T = lib->size;
-    if (M == 0) return CDS_OK;
-    if (!out_score || !out_target || !out_count) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_topk: NULL output");
-    reset_stats(ctx);
-    for (int m = 0; m < M; m++) out_count[m] = 0;
-    if (T == 0) return CDS_OK;
-    CDS_TRY(ms->sync_descs());
-    CDS_TRY(lib->bake(ms->params.data_threshold));
-    const bool batched = batched_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks();
-    if (batched && ctx->resident_occupancy) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
-    if (batched && (lib->occ_on_the_fly || !ctx->resident_occupancy))
-        return search_library_chunked(ctx, ms, lib, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count);
-    const int D = lib->n_dev();
-    std::vector<int32_t> min_score(M);
-    for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);
+    return cds::abi_guard("cds_search_topk", [&]() -> cds_status {
+        if (!ctx || !ms_c || !lib) { set_tls_error("cds_search_topk: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        cds_maskset *ms = const_cast<cds_maskset *>(ms_c);
+        CDS_TRY(check_search_args(ctx, ms, lib));
+        if (k <= 0 || k > topk_max_k()) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_topk: k must be in 1..4096");
+        const int M = (int) ms->sizes.size();
+        const int64_t T = lib->size;
+        if (M == 0) return CDS_OK;
+        if (!out_score || !out_target || !out_count) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_topk: NULL output");
+        reset_stats(ctx);
+        for (int m = 0; m < M; m++) out_count[m] = 0;
+        if (T == 0) return CDS_OK;
+        CDS_TRY(ms->sync_descs());
+        CDS_TRY(lib->bake(ms->params.data_threshold));
+        const bool batched = batched_kernel_supported(ms->params.xy_shift, lib->g) && M >= band_min_masks();
+        if (batched && ctx->resident_occupancy) CDS_TRY(lib->ensure_occupancy(ms->params.xy_shift / 2));
+        if (batched && (lib->occ_on_the_fly || !ctx->resident_occupancy))
+            return search_library_chunked(ctx, ms, lib, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count);
+        const int D = lib->n_dev();
+        std::vector<int32_t> min_score(M);
+        for (int m = 0; m < M; m++) min_score[m] = min_matching_score(ms->sizes[m], pct_positive_pixels);
 
-    int64_t max_local = 0;
-    for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
-    int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 512 << 20) / std::max<int64_t>(max_local, 1)));
-    if (mchunk < M && mchunk > CDS_PALETTE_GROUP) mchunk -= mchunk % CDS_PALETTE_GROUP;   // keep chunks aligned to palette groups
-    std::vector<int32_t *> d_scores(D, nullptr);
-    std::vector<int32_t *> d_min(D, nullptr);
-    std::vector<uint64_t *> d_keys(D, nullptr);
-    std::vector<int32_t *> d_counts(D, nullptr);
-    cds_status st = CDS_OK;
-    const size_t keys_bytes = (size_t) M * k * sizeof(uint64_t);
-    for (int d = 0; d < D && st == CDS_OK; d++) {
-        DevState &ds = ctx->devs[d];
-        st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
-        if (st == CDS_OK) st = ctx->ensure_scratch(ds, 0, (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t), (void **) &d_scores[d]);
-        if (st == CDS_OK) st = ctx->ensure_scratch(ds, 1, M * sizeof(int32_t), (void **) &d_min[d]);
-        if (st == CDS_OK) st = ctx->ensure_scratch(ds, 2, keys_bytes, (void **) &d_keys[d]);
-        if (st == CDS_OK) st = ctx->ensure_scratch(ds, 3, M * sizeof(int32_t), (void **) &d_counts[d]);
-        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_min[d], min_score.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream), "min scores H2D");
-        if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_counts[d], 0, M * sizeof(int32_t), ds.stream), "memset");
-        if (st == CDS_OK) st = ctx->ensure_pinned(ds, keys_bytes + M * sizeof(int32_t));
-    }
-    double match_ms = 0, total_ms = 0;
-    for (int m0 = 0; m0 < M && st == CDS_OK; m0 += mchunk) {
-        const int mc = std::min(mchunk, M - m0);
+        int64_t max_local = 0;
+        for (int d = 0; d < D; d++) max_local = std::max(max_local, lib->local_size(d));
+        int mchunk = (int) std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t) 512 << 20) / std::max<int64_t>(max_local, 1)));
+        if (mchunk < M && mchunk > CDS_PALETTE_GROUP) mchunk -= mchunk % CDS_PALETTE_GROUP;   // keep chunks aligned to palette groups
+        std::vector<int32_t *> d_scores(D, nullptr);
+        std::vector<int32_t *> d_min(D, nullptr);
+        std::vector<uint64_t *> d_keys(D, nullptr);
+        std::vector<int32_t *> d_counts(D, nullptr);
+        cds_status st = CDS_OK;
+        const size_t keys_bytes = (size_t) M * k * sizeof(uint64_t);
         for (int d = 0; d < D && st == CDS_OK; d++) {
-            const int64_t nl = lib->local_size(d);
-            if (nl == 0) continue;
             DevState &ds = ctx->devs[d];
             st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
-            if (st == CDS_OK) st = launch_match(ctx, ms, lib, d, m0, mc, nl, d_scores[d]);
-            if (st == CDS_OK) {
-                launch_topk(d_scores[d], mc, nl, d_min[d] + m0, k, 0, d_keys[d] + (size_t) m0 * k, d_counts[d] + m0, ds.stream);
-                ctx->stats.kernel_launches++;
-                cudaEventRecord(ds.ev2, ds.stream);
-                st = ctx->check(cudaGetLastError(), "topk kernel");
-            }
+            if (st == CDS_OK) st = ctx->ensure_scratch(ds, 0, (size_t) mchunk * std::max<int64_t>(lib->local_size(d), 1) * sizeof(int32_t), (void **) &d_scores[d]);
+            if (st == CDS_OK) st = ctx->ensure_scratch(ds, 1, M * sizeof(int32_t), (void **) &d_min[d]);
+            if (st == CDS_OK) st = ctx->ensure_scratch(ds, 2, keys_bytes, (void **) &d_keys[d]);
+            if (st == CDS_OK) st = ctx->ensure_scratch(ds, 3, M * sizeof(int32_t), (void **) &d_counts[d]);
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_min[d], min_score.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream), "min scores H2D");
+            if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_counts[d], 0, M * sizeof(int32_t), ds.stream), "memset");
+            if (st == CDS_OK) st = ctx->ensure_pinned(ds, keys_bytes + M * sizeof(int32_t));
         }
-        double chunk_ms = 0, chunk_total_ms = 0;
+        double match_ms = 0, total_ms = 0;
+        for (int m0 = 0; m0 < M && st == CDS_OK; m0 += mchunk) {
+            const int mc = std::min(mchunk, M - m0);
+            for (int d = 0; d < D && st == CDS_OK; d++) {
+                const int64_t nl = lib->local_size(d);
+                if (nl == 0) continue;
+                DevState &ds = ctx->devs[d];
+                st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+                if (st == CDS_OK) st = launch_match(ctx, ms, lib, d, m0, mc, nl, d_scores[d]);
+                if (st == CDS_OK) {
+                    launch_topk(d_scores[d], mc, nl, d_min[d] + m0, k, 0, d_keys[d] + (size_t) m0 * k, d_counts[d] + m0, ds.stream);
+                    ctx->stats.kernel_launches++;
+                    cudaEventRecord(ds.ev2, ds.stream);
+                    st = ctx->check(cudaGetLastError(), "topk kernel");
+                }
+            }
+            double chunk_ms = 0, chunk_total_ms = 0;
+            for (int d = 0; d < D && st == CDS_OK; d++) {
+                if (lib->local_size(d) == 0) continue;
+                DevState &ds = ctx->devs[d];
+                cudaSetDevice(ds.dev);
+                st = ctx->check(cudaStreamSynchronize(ds.stream), "pixel match + topk");
+                if (st != CDS_OK) break;
+                float ms_f = 0;
+                cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev1);
+                chunk_ms = std::max(chunk_ms, (double) ms_f);
+                cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev2);
+                chunk_total_ms = std::max(chunk_total_ms, (double) ms_f);
+            }
+            match_ms += chunk_ms;
+            total_ms += chunk_total_ms;
+        }
+        // read back per-device lists and merge on the host (no collective: nothing is reduced across devices)
+        std::vector<std::vector<uint64_t>> h_keys(D);
+        std::vector<std::vector<int32_t>> h_counts(D);
         for (int d = 0; d < D && st == CDS_OK; d++) {
             if (lib->local_size(d) == 0) continue;
             DevState &ds = ctx->devs[d];
             cudaSetDevice(ds.dev);
-            st = ctx->check(cudaStreamSynchronize(ds.stream), "pixel match + topk");
-            if (st != CDS_OK) break;
-            float ms_f = 0;
-            cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev1);
-            chunk_ms = std::max(chunk_ms, (double) ms_f);
-            cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev2);
-            chunk_total_ms = std::max(chunk_total_ms, (double) ms_f);
+            uint8_t *hp = (uint8_t *) ds.h_pinned;
+            st = ctx->check(cudaMemcpyAsync(hp, d_keys[d], keys_bytes, cudaMemcpyDeviceToHost, ds.stream), "keys D2H");
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(hp + keys_bytes, d_counts[d], M * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "counts D2H");
+            ctx->stats.d2h_bytes += (int64_t) keys_bytes + (int64_t) M * 4;
         }
-        match_ms += chunk_ms;
-        total_ms += chunk_total_ms;
-    }
-    // read back per-device lists and merge on the host (no collective: nothing is reduced across devices)
-    std::vector<std::vector<uint64_t>> h_keys(D);
-    std::vector<std::vector<int32_t>> h_counts(D);
-    for (int d = 0; d < D && st == CDS_OK; d++) {
-        if (lib->local_size(d) == 0) continue;
-        DevState &ds = ctx->devs[d];
-        cudaSetDevice(ds.dev);
-        uint8_t *hp = (uint8_t *) ds.h_pinned;
-        st = ctx->check(cudaMemcpyAsync(hp, d_keys[d], keys_bytes, cudaMemcpyDeviceToHost, ds.stream), "keys D2H");
-        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(hp + keys_bytes, d_counts[d], M * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream), "counts D2H");
-        ctx->stats.d2h_bytes += (int64_t) keys_bytes + (int64_t) M * 4;
-    }
-    for (int d = 0; d < D && st == CDS_OK; d++) {
-        if (lib->local_size(d) == 0) continue;
-        DevState &ds = ctx->devs[d];
-        cudaSetDevice(ds.dev);
-        st = ctx->check(cudaStreamSynchronize(ds.stream), "topk D2H");
-        if (st != CDS_OK) break;
-        const uint8_t *hp = (const uint8_t *) ds.h_pinned;
-        h_keys[d].assign((const uint64_t *) hp, (const uint64_t *) hp + (size_t) M * k);
-        h_counts[d].assign((const int32_t *) (hp + keys_bytes), (const int32_t *) (hp + keys_bytes) + M);
-    }
-    if (st == CDS_OK) {
-        struct Item { int32_t score; int64_t target; uint8_t mir; };
-        std::vector<Item> items;
-        for (int m = 0; m < M; m++) {
-            items.clear();
-            for (int d = 0; d < D; d++) {
-                if (h_counts[d].empty()) continue;
-                int c = std::min(h_counts[d][m], k);
+        for (int d = 0; d < D && st == CDS_OK; d++) {
+            if (lib->local_size(d) == 0) continue;
+            DevState &ds = ctx->devs[d];
+            cudaSetDevice(ds.dev);
+            st = ctx->check(cudaStreamSynchronize(ds.stream), "topk D2H");
+            if (st != CDS_OK) break;
+            const uint8_t *hp = (const uint8_t *) ds.h_pinned;
+            h_keys[d].assign((const uint64_t *) hp, (const uint64_t *) hp + (size_t) M * k);
+            h_counts[d].assign((const int32_t *) (hp + keys_bytes), (const int32_t *) (hp + keys_bytes) + M);
+        }
+        if (st == CDS_OK) {
+            struct Item { int32_t score; int64_t target; uint8_t mir; };
+            std::vector<Item> items;
+            for (int m = 0; m < M; m++) {
+                items.clear();
+                for (int d = 0; d < D; d++) {
+                    if (h_counts[d].empty()) continue;
+                    int c = std::min(h_counts[d][m], k);
+                    for (int i = 0; i < c; i++) {
+                        uint64_t key = h_keys[d][(size_t) m * k + i];
+                        Item it;
+                        topk_decode_key(key, it.score, it.target, it.mir);
+                        it.target = lib->global_of(d, it.target);
+                        items.push_back(it);
+                    }
+                }
+                std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+                    if (a.score != b.score) return a.score > b.score;
+                    return a.target < b.target;
+                });
+                int c = (int) std::min<size_t>(items.size(), (size_t) k);
+                out_count[m] = c;
                 for (int i = 0; i < c; i++) {
-                    uint64_t key = h_keys[d][(size_t) m * k + i];
-                    Item it;
-                    topk_decode_key(key, it.score, it.target, it.mir);
-                    it.target = lib->global_of(d, it.target);
-                    items.push_back(it);
+                    out_score[(size_t) m * k + i] = items[i].score;
+                    out_target[(size_t) m * k + i] = items[i].target;
+                    if (out_mirrored) out_mirrored[(size_t) m * k + i] = items[i].mir;
                 }
             }
-            std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-                if (a.score != b.score) return a.score > b.score;
-                return a.target < b.target;
-            });
-            int c = (int) std::min<size_t>(items.size(), (size_t) k);
-            out_count[m] = c;
-            for (int i = 0; i < c; i++) {
-                out_score[(size_t) m * k + i] = items[i].score;
-                out_target[(size_t) m * k + i] = items[i].target;
-                if (out_mirrored) out_mirrored[(size_t) m * k + i] = items[i].mir;
-            }
         }
-    }
-    ctx->stats.match_kernel_ms = match_ms;
-    ctx->stats.total_device_ms = total_ms;
-    ctx->stats.comparisons = (int64_t) M * T;
-    return st;
+        ctx->stats.match_kernel_ms = match_ms;
+        ctx->stats.total_device_ms = total_ms;
+        ctx->stats.comparisons = (int64_t) M * T;
+        return st;
+    });
 }
 
 extern "C" cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, int32_t mask_index, const uint8_t *target_rgb,
                                          int32_t target_width, int32_t target_height,
                                          int32_t *score_out, double *ratio_out, int32_t *mirrored_out)
 {
-    if (!ctx || !ms || !score_out || !ratio_out || !mirrored_out) { set_tls_error("cds_score_pair_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (mask_index < 0 || mask_index >= (int) ms->sizes.size()) return ctx->fail(CDS_ERR_BAD_ARG, "cds_score_pair_rgb: mask index out of range");
-    const int P = ms->sizes[mask_index];
-    if (P == 0) { *score_out = 0; *ratio_out = 0; *mirrored_out = 0; return CDS_OK; }   // PixelMatch...:169-170 (before the size check)
-    if (target_width != ms->W || target_height != ms->H) {
-        char buf[200];
-        snprintf(buf, sizeof buf, "Invalid image size - target's image size (%d, %d) must match query's image size: (%d, %d)",
-                 ms->W, ms->H, target_width, target_height);
-        return ctx->fail(CDS_ERR_SIZE_MISMATCH, buf);
-    }
-    if (!target_rgb) return ctx->fail(CDS_ERR_BAD_ARG, "cds_score_pair_rgb: target is NULL");
-    // a one-slot library on device 0, kept between calls (this is the call the reference's thread pool makes per pair)
-    cds_ctx *c = ctx;
-    cds_maskset *msm = const_cast<cds_maskset *>(ms);
-    CDS_TRY(msm->sync_descs());
-    DevState &d0 = c->devs[0];
-    CDS_CUDA(c, cudaSetDevice(d0.dev));
-    PlaneGeom g;
-    g.W = ms->W; g.H = ms->H; g.pitch = choose_pitch(ms->W); g.guard = CDS_GUARD_ROWS;
-    const size_t words = g.total_words(1);
-    const size_t img_bytes = (size_t) g.W * g.H * 3;
-    CDS_TRY(c->ensure_staging(d0, (size_t) kLibBlock * img_bytes));
-    if (d0.pair_W != g.W || d0.pair_H != g.H) {
-        if (d0.pair_plane) { CDS_CUDA(c, cudaStreamSynchronize(d0.stream)); cudaFree(d0.pair_plane); d0.pair_plane = nullptr; }
-        CDS_CUDA(c, cudaMalloc(&d0.pair_plane, words * sizeof(uint32_t) + sizeof(int32_t)));
-        launch_fill_words(d0.pair_plane, words, CDS_CODE_PAD_WORD, d0.stream);     // guard rows / pad columns stay pad words
-        d0.pair_W = g.W; d0.pair_H = g.H;
-    }
-    uint32_t *plane = d0.pair_plane;
-    int32_t *d_score = (int32_t *) (plane + words);
-    cds_status st = c->check(cudaMemcpyAsync(d0.staging, target_rgb, img_bytes, cudaMemcpyHostToDevice, d0.stream), "pair H2D");
-    if (st == CDS_OK) {
-        launch_encode_rgb((const uint8_t *) d0.staging, 1, plane, g, 0, d0.d_rank_tab, ms->params.data_threshold, d0.stream);
-        launch_pixelmatch_gather(msm->d_descs[0] + mask_index, 1, plane, g, 1, ms->shifts, d_score, d0.stream);
-        st = c->check(cudaGetLastError(), "pair kernels");
-    }
-    int32_t w = 0;
-    if (st == CDS_OK) st = c->check(cudaMemcpyAsync(&w, d_score, sizeof w, cudaMemcpyDeviceToHost, d0.stream), "pair D2H");
-    if (st == CDS_OK) st = c->check(cudaStreamSynchronize(d0.stream), "pair sync");
-    if (st != CDS_OK) return st;
-    *score_out = w & ~CDS_SCORE_MIRROR_BIT;
-    *mirrored_out = (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0;
-    *ratio_out = (double) *score_out / (double) P;     // :194
-    return CDS_OK;
+    return cds::abi_guard("cds_score_pair_rgb", [&]() -> cds_status {
+        if (!ctx || !ms || !score_out || !ratio_out || !mirrored_out) { set_tls_error("cds_score_pair_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (mask_index < 0 || mask_index >= (int) ms->sizes.size()) return ctx->fail(CDS_ERR_BAD_ARG, "cds_score_pair_rgb: mask index out of range");
+        const int P = ms->sizes[mask_index];
+        if (P == 0) { *score_out = 0; *ratio_out = 0; *mirrored_out = 0; return CDS_OK; }   // PixelMatch...:169-170 (before the size check)
+        if (target_width != ms->W || target_height != ms->H) {
+            char buf[200];
+            snprintf(buf, sizeof buf, "Invalid image size - target's image size (%d, %d) must match query's image size: (%d, %d)",
+                     ms->W, ms->H, target_width, target_height);
+            return ctx->fail(CDS_ERR_SIZE_MISMATCH, buf);
+        }
+        if (!target_rgb) return ctx->fail(CDS_ERR_BAD_ARG, "cds_score_pair_rgb: target is NULL");
+        // a one-slot library on device 0, kept between calls (this is the call the reference's thread pool makes per pair)
+        cds_ctx *c = ctx;
+        cds_maskset *msm = const_cast<cds_maskset *>(ms);
+        CDS_TRY(msm->sync_descs());
+        DevState &d0 = c->devs[0];
+        CDS_CUDA(c, cudaSetDevice(d0.dev));
+        PlaneGeom g;
+        g.W = ms->W; g.H = ms->H; g.pitch = choose_pitch(ms->W); g.guard = CDS_GUARD_ROWS;
+        const size_t words = g.total_words(1);
+        const size_t img_bytes = (size_t) g.W * g.H * 3;
+        CDS_TRY(c->ensure_staging(d0, (size_t) kLibBlock * img_bytes));
+        if (d0.pair_W != g.W || d0.pair_H != g.H) {
+            if (d0.pair_plane) { CDS_CUDA(c, cudaStreamSynchronize(d0.stream)); cudaFree(d0.pair_plane); d0.pair_plane = nullptr; }
+            CDS_CUDA(c, cudaMalloc(&d0.pair_plane, words * sizeof(uint32_t) + sizeof(int32_t)));
+            launch_fill_words(d0.pair_plane, words, CDS_CODE_PAD_WORD, d0.stream);     // guard rows / pad columns stay pad words
+            d0.pair_W = g.W; d0.pair_H = g.H;
+        }
+        uint32_t *plane = d0.pair_plane;
+        int32_t *d_score = (int32_t *) (plane + words);
+        cds_status st = c->check(cudaMemcpyAsync(d0.staging, target_rgb, img_bytes, cudaMemcpyHostToDevice, d0.stream), "pair H2D");
+        if (st == CDS_OK) {
+            launch_encode_rgb((const uint8_t *) d0.staging, 1, plane, g, 0, d0.d_rank_tab, ms->params.data_threshold, d0.stream);
+            launch_pixelmatch_gather(msm->d_descs[0] + mask_index, 1, plane, g, 1, ms->shifts, d_score, d0.stream);
+            st = c->check(cudaGetLastError(), "pair kernels");
+        }
+        int32_t w = 0;
+        if (st == CDS_OK) st = c->check(cudaMemcpyAsync(&w, d_score, sizeof w, cudaMemcpyDeviceToHost, d0.stream), "pair D2H");
+        if (st == CDS_OK) st = c->check(cudaStreamSynchronize(d0.stream), "pair sync");
+        if (st != CDS_OK) return st;
+        *score_out = w & ~CDS_SCORE_MIRROR_BIT;
+        *mirrored_out = (w & CDS_SCORE_MIRROR_BIT) ? 1 : 0;
+        *ratio_out = (double) *score_out / (double) P;     // :194
+        return CDS_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------------ post-processing
@@ -1300,58 +1364,64 @@ extern "C" double cds_normalized_score(int32_t pixel_match_score, int64_t shape_
 extern "C" cds_status cds_normalize_scores(const int32_t *pixel_scores, const int64_t *gaps, const int64_t *high_exprs, int64_t n,
                                            float *normalized_out)
 {
-    // CalculateGradientScoresCmd.normalizeScores, TOOLS/CalculateGradientScoresCmd.java:616-645: the maxima run over the
-    // mask's matches, the normalised score is stored as float
-    if (n < 0 || (n > 0 && (!pixel_scores || !gaps || !high_exprs || !normalized_out))) {
-        set_tls_error("cds_normalize_scores: bad arguments");
-        return CDS_ERR_BAD_ARG;
-    }
-    int64_t max_pix = 0, max_shape = -1;
-    bool any = false;
-    for (int64_t i = 0; i < n; i++) {
-        max_pix = std::max<int64_t>(max_pix, pixel_scores[i]);
-        int64_t s = cds_shape_score_2d(gaps[i], high_exprs[i]);
-        if (!any || s > max_shape) { max_shape = s; any = true; }
-    }
-    for (int64_t i = 0; i < n; i++) {
-        int64_t s = cds_shape_score_2d(gaps[i], high_exprs[i]);
-        normalized_out[i] = (float) cds_normalized_score(pixel_scores[i], s, max_pix, max_shape);
-    }
-    return CDS_OK;
+    return cds::abi_guard("cds_normalize_scores", [&]() -> cds_status {
+        // CalculateGradientScoresCmd.normalizeScores, TOOLS/CalculateGradientScoresCmd.java:616-645: the maxima run over the
+        // mask's matches, the normalised score is stored as float
+        if (n < 0 || (n > 0 && (!pixel_scores || !gaps || !high_exprs || !normalized_out))) {
+            set_tls_error("cds_normalize_scores: bad arguments");
+            return CDS_ERR_BAD_ARG;
+        }
+        int64_t max_pix = 0, max_shape = -1;
+        bool any = false;
+        for (int64_t i = 0; i < n; i++) {
+            max_pix = std::max<int64_t>(max_pix, pixel_scores[i]);
+            int64_t s = cds_shape_score_2d(gaps[i], high_exprs[i]);
+            if (!any || s > max_shape) { max_shape = s; any = true; }
+        }
+        for (int64_t i = 0; i < n; i++) {
+            int64_t s = cds_shape_score_2d(gaps[i], high_exprs[i]);
+            normalized_out[i] = (float) cds_normalized_score(pixel_scores[i], s, max_pix, max_shape);
+        }
+        return CDS_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------------ test hooks
 extern "C" cds_status cds_debug_encode_colors(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t data_threshold, uint32_t *codes_out)
 {
-    if (!ctx || (n > 0 && (!rgb || !codes_out))) { set_tls_error("cds_debug_encode_colors: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (n <= 0) return CDS_OK;
-    DevState &d0 = ctx->devs[0];
-    CDS_CUDA(ctx, cudaSetDevice(d0.dev));
-    uint8_t *d_rgb = nullptr;
-    uint32_t *d_codes = nullptr;
-    cds_status st = ctx->check(cudaMalloc(&d_rgb, (size_t) n * 3), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_codes, (size_t) n * 4), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_rgb, rgb, (size_t) n * 3, cudaMemcpyHostToDevice, d0.stream), "H2D");
-    if (st == CDS_OK) {
-        launch_encode_colors(d_rgb, n, d0.d_rank_tab, data_threshold, d_codes, d0.stream);
-        st = ctx->check(cudaGetLastError(), "encode_colors_kernel");
-    }
-    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(codes_out, d_codes, (size_t) n * 4, cudaMemcpyDeviceToHost, d0.stream), "D2H");
-    if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "sync");
-    if (d_rgb) cudaFree(d_rgb);
-    if (d_codes) cudaFree(d_codes);
-    return st;
+    return cds::abi_guard("cds_debug_encode_colors", [&]() -> cds_status {
+        if (!ctx || (n > 0 && (!rgb || !codes_out))) { set_tls_error("cds_debug_encode_colors: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n <= 0) return CDS_OK;
+        DevState &d0 = ctx->devs[0];
+        CDS_CUDA(ctx, cudaSetDevice(d0.dev));
+        uint8_t *d_rgb = nullptr;
+        uint32_t *d_codes = nullptr;
+        cds_status st = ctx->check(cudaMalloc(&d_rgb, (size_t) n * 3), "cudaMalloc");
+        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_codes, (size_t) n * 4), "cudaMalloc");
+        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_rgb, rgb, (size_t) n * 3, cudaMemcpyHostToDevice, d0.stream), "H2D");
+        if (st == CDS_OK) {
+            launch_encode_colors(d_rgb, n, d0.d_rank_tab, data_threshold, d_codes, d0.stream);
+            st = ctx->check(cudaGetLastError(), "encode_colors_kernel");
+        }
+        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(codes_out, d_codes, (size_t) n * 4, cudaMemcpyDeviceToHost, d0.stream), "D2H");
+        if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "sync");
+        if (d_rgb) cudaFree(d_rgb);
+        if (d_codes) cudaFree(d_codes);
+        return st;
+    });
 }
 
 extern "C" cds_status cds_debug_class_intervals(double z_tolerance, int32_t sector, int32_t rank,
                                                 uint32_t *lo1, uint32_t *len1, uint32_t *lo2, uint32_t *len2)
 {
-    if (sector < 0 || sector >= CDS_NUM_SECTORS || rank < 0 || rank >= CDS_NUM_RANKS || !lo1 || !len1 || !lo2 || !len2) {
-        set_tls_error("cds_debug_class_intervals: bad arguments");
-        return CDS_ERR_BAD_ARG;
-    }
-    cds_class_interval iv = class_interval(z_tolerance, sector, rank);
-    *lo1 = iv.lo1; *len1 = iv.len1; *lo2 = iv.lo2; *len2 = iv.len2;
-    return CDS_OK;
+    return cds::abi_guard("cds_debug_class_intervals", [&]() -> cds_status {
+        if (sector < 0 || sector >= CDS_NUM_SECTORS || rank < 0 || rank >= CDS_NUM_RANKS || !lo1 || !len1 || !lo2 || !len2) {
+            set_tls_error("cds_debug_class_intervals: bad arguments");
+            return CDS_ERR_BAD_ARG;
+        }
+        cds_class_interval iv = class_interval(z_tolerance, sector, rank);
+        *lo1 = iv.lo1; *len1 = iv.len1; *lo2 = iv.lo2; *len2 = iv.len2;
+        return CDS_OK;
+    });
 }

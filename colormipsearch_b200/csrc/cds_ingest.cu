@@ -206,98 +206,104 @@ void ingest_bounds(const int64_t *offsets, int64_t n, int64_t cnt, int W, int H,
 extern "C" cds_status cds_tiff_decode_rgb(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n,
                                           int32_t width, int32_t height, uint8_t *out_rgb)
 {
-    if (!ctx) { set_tls_error("cds_tiff_decode_rgb: NULL context"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (n < 0 || width <= 0 || height <= 0 || width > 16384 || height > 16384) return ctx->fail(CDS_ERR_BAD_ARG, "cds_tiff_decode_rgb: bad size");
-    if (n == 0) return CDS_OK;
-    if (!blob || !offsets || !out_rgb) return ctx->fail(CDS_ERR_BAD_ARG, "cds_tiff_decode_rgb: NULL argument");
-    DevState &ds = ctx->devs[0];
-    CDS_CUDA(ctx, cudaSetDevice(ds.dev));
-    const size_t img_bytes = (size_t) width * height * 3;
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(64, (int64_t) ((size_t) 1 << 30) / (int64_t) img_bytes));
-    size_t comp_cap, strips_cap;
-    ingest_bounds(offsets, n, chunk, width, height, comp_cap, strips_cap);
-    uint8_t *d_comp = nullptr, *d_rgb = nullptr;
-    TiffStrip *d_strips = nullptr;
-    auto release = [&]() { cudaStreamSynchronize(ds.stream); ds.pool.free(d_comp); ds.pool.free(d_rgb); ds.pool.free(d_strips); };
-    struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
-    CDS_CUDA(ctx, ds.pool.alloc((void **) &d_comp, comp_cap));
-    CDS_CUDA(ctx, ds.pool.alloc((void **) &d_strips, strips_cap * sizeof(TiffStrip)));
-    CDS_CUDA(ctx, ds.pool.alloc((void **) &d_rgb, (size_t) chunk * img_bytes));
-    std::vector<TiffStrip> strips;
-    for (int64_t i0 = 0; i0 < n; i0 += chunk) {
-        const int64_t cnt = std::min(chunk, n - i0);
-        CDS_TRY(ingest_chunk(ctx, "cds_tiff_decode_rgb", blob, offsets, i0, cnt, width, height, d_comp, comp_cap, d_strips, strips_cap, d_rgb, ds.stream, strips));
-        CDS_CUDA(ctx, cudaMemcpyAsync(out_rgb + (size_t) i0 * img_bytes, d_rgb, (size_t) cnt * img_bytes, cudaMemcpyDeviceToHost, ds.stream));
-        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
-        ctx->stats.d2h_bytes += (int64_t) cnt * (int64_t) img_bytes;
-    }
-    return CDS_OK;
+    return cds::abi_guard("cds_tiff_decode_rgb", [&]() -> cds_status {
+        if (!ctx) { set_tls_error("cds_tiff_decode_rgb: NULL context"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || width <= 0 || height <= 0 || width > 16384 || height > 16384) return ctx->fail(CDS_ERR_BAD_ARG, "cds_tiff_decode_rgb: bad size");
+        if (n == 0) return CDS_OK;
+        if (!blob || !offsets || !out_rgb) return ctx->fail(CDS_ERR_BAD_ARG, "cds_tiff_decode_rgb: NULL argument");
+        DevState &ds = ctx->devs[0];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        const size_t img_bytes = (size_t) width * height * 3;
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(64, (int64_t) ((size_t) 1 << 30) / (int64_t) img_bytes));
+        size_t comp_cap, strips_cap;
+        ingest_bounds(offsets, n, chunk, width, height, comp_cap, strips_cap);
+        uint8_t *d_comp = nullptr, *d_rgb = nullptr;
+        TiffStrip *d_strips = nullptr;
+        auto release = [&]() { cudaStreamSynchronize(ds.stream); ds.pool.free(d_comp); ds.pool.free(d_rgb); ds.pool.free(d_strips); };
+        struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_comp, comp_cap));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_strips, strips_cap * sizeof(TiffStrip)));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_rgb, (size_t) chunk * img_bytes));
+        std::vector<TiffStrip> strips;
+        for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+            const int64_t cnt = std::min(chunk, n - i0);
+            CDS_TRY(ingest_chunk(ctx, "cds_tiff_decode_rgb", blob, offsets, i0, cnt, width, height, d_comp, comp_cap, d_strips, strips_cap, d_rgb, ds.stream, strips));
+            CDS_CUDA(ctx, cudaMemcpyAsync(out_rgb + (size_t) i0 * img_bytes, d_rgb, (size_t) cnt * img_bytes, cudaMemcpyDeviceToHost, ds.stream));
+            CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+            ctx->stats.d2h_bytes += (int64_t) cnt * (int64_t) img_bytes;
+        }
+        return CDS_OK;
+    });
 }
 
 extern "C" cds_status cds_library_add_tiff(cds_library *lib, const uint8_t *blob, const int64_t *offsets, int64_t n, int64_t *first_index)
 {
-    if (!lib) { set_tls_error("cds_library_add_tiff: NULL library"); return CDS_ERR_BAD_ARG; }
-    cds_ctx *ctx = lib->ctx;
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (n < 0) return ctx->fail(CDS_ERR_BAD_ARG, "negative image count");
-    if (n > 0 && (!blob || !offsets)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_library_add_tiff: NULL argument");
-    if (n == 0) return library_append(lib, 0, nullptr, first_index);
-    const int W = lib->g.W, H = lib->g.H;
-    // library_append hands out runs of at most kLibBlock images; bound the staging by any kLibBlock consecutive files
-    size_t comp_cap = 0, strips_cap = 0;
-    {
-        int64_t worst = 0;
-        for (int64_t i = 0; i < n; i++) worst = std::max(worst, offsets[std::min(n, i + kLibBlock)] - offsets[i]);
-        comp_cap = (size_t) std::max<int64_t>(worst, 0) + 64;
-        strips_cap = (size_t) kLibBlock * tiff_strips_bound(W, H);
-    }
-    const size_t D = ctx->devs.size();
-    std::vector<uint8_t *> d_comp(D, nullptr);
-    std::vector<TiffStrip *> d_strips(D, nullptr);
-    auto release = [&]() {
-        for (size_t d = 0; d < D; d++) {
-            if (!d_comp[d] && !d_strips[d]) continue;
-            cudaSetDevice(ctx->devs[d].dev);
-            cudaStreamSynchronize(ctx->devs[d].stream);
-            ctx->devs[d].pool.free(d_comp[d]);
-            ctx->devs[d].pool.free(d_strips[d]);
+    return cds::abi_guard("cds_library_add_tiff", [&]() -> cds_status {
+        if (!lib) { set_tls_error("cds_library_add_tiff: NULL library"); return CDS_ERR_BAD_ARG; }
+        cds_ctx *ctx = lib->ctx;
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0) return ctx->fail(CDS_ERR_BAD_ARG, "negative image count");
+        if (n > 0 && (!blob || !offsets)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_library_add_tiff: NULL argument");
+        if (n == 0) return library_append(lib, 0, nullptr, first_index);
+        const int W = lib->g.W, H = lib->g.H;
+        // library_append hands out runs of at most kLibBlock images; bound the staging by any kLibBlock consecutive files
+        size_t comp_cap = 0, strips_cap = 0;
+        {
+            int64_t worst = 0;
+            for (int64_t i = 0; i < n; i++) worst = std::max(worst, offsets[std::min(n, i + kLibBlock)] - offsets[i]);
+            comp_cap = (size_t) std::max<int64_t>(worst, 0) + 64;
+            strips_cap = (size_t) kLibBlock * tiff_strips_bound(W, H);
         }
-    };
-    struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
-    std::vector<TiffStrip> strips;
-    return library_append(lib, n, [&](DevState &ds, int64_t i0, int64_t cnt, uint8_t *d_rgb) -> cds_status {
-        const size_t d = (size_t) (&ds - ctx->devs.data());
-        if (!d_comp[d]) {
-            CDS_CUDA(ctx, ds.pool.alloc((void **) &d_comp[d], comp_cap));
-            CDS_CUDA(ctx, ds.pool.alloc((void **) &d_strips[d], strips_cap * sizeof(TiffStrip)));
-        }
-        return ingest_chunk(ctx, "cds_library_add_tiff", blob, offsets, i0, cnt, W, H, d_comp[d], comp_cap, d_strips[d], strips_cap, d_rgb, ds.stream, strips);
-    }, first_index);
+        const size_t D = ctx->devs.size();
+        std::vector<uint8_t *> d_comp(D, nullptr);
+        std::vector<TiffStrip *> d_strips(D, nullptr);
+        auto release = [&]() {
+            for (size_t d = 0; d < D; d++) {
+                if (!d_comp[d] && !d_strips[d]) continue;
+                cudaSetDevice(ctx->devs[d].dev);
+                cudaStreamSynchronize(ctx->devs[d].stream);
+                ctx->devs[d].pool.free(d_comp[d]);
+                ctx->devs[d].pool.free(d_strips[d]);
+            }
+        };
+        struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
+        std::vector<TiffStrip> strips;
+        return library_append(lib, n, [&](DevState &ds, int64_t i0, int64_t cnt, uint8_t *d_rgb) -> cds_status {
+            const size_t d = (size_t) (&ds - ctx->devs.data());
+            if (!d_comp[d]) {
+                CDS_CUDA(ctx, ds.pool.alloc((void **) &d_comp[d], comp_cap));
+                CDS_CUDA(ctx, ds.pool.alloc((void **) &d_strips[d], strips_cap * sizeof(TiffStrip)));
+            }
+            return ingest_chunk(ctx, "cds_library_add_tiff", blob, offsets, i0, cnt, W, H, d_comp[d], comp_cap, d_strips[d], strips_cap, d_rgb, ds.stream, strips);
+        }, first_index);
+    });
 }
 
 extern "C" cds_status cds_maskset_add_tiff(cds_maskset *ms, const uint8_t *blob, const int64_t *offsets, int32_t n, int32_t *mask_size_out)
 {
-    if (!ms) { set_tls_error("cds_maskset_add_tiff: NULL mask set"); return CDS_ERR_BAD_ARG; }
-    cds_ctx *ctx = ms->ctx;
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (n < 0 || (n > 0 && (!blob || !offsets))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_tiff: bad arguments");
-    if (n == 0) return CDS_OK;
-    const int W = ms->W, H = ms->H;
-    // maskset_append asks for runs of at most 64 masks; uploads and decodes are ordered on one stream, so one buffer does
-    size_t comp_cap = 0, strips_cap = 0;
-    ingest_bounds(offsets, n, 64, W, H, comp_cap, strips_cap);
-    for (int64_t i = 0; i < n; i++) comp_cap = std::max(comp_cap, (size_t) std::max<int64_t>(offsets[std::min<int64_t>(n, i + 64)] - offsets[i], 0) + 64);
-    DevState &d0 = ctx->devs[0];
-    CDS_CUDA(ctx, cudaSetDevice(d0.dev));
-    uint8_t *d_comp = nullptr;
-    TiffStrip *d_strips = nullptr;
-    auto release = [&]() { cudaStreamSynchronize(d0.copy_stream); cudaStreamSynchronize(d0.stream); d0.pool.free(d_comp); d0.pool.free(d_strips); };
-    struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
-    CDS_CUDA(ctx, d0.pool.alloc((void **) &d_comp, comp_cap));
-    CDS_CUDA(ctx, d0.pool.alloc((void **) &d_strips, strips_cap * sizeof(TiffStrip)));
-    std::vector<TiffStrip> strips;
-    return maskset_append(ms, n, mask_size_out, [&](int i0, int cnt, uint8_t *stage, cudaStream_t stream) -> cds_status {
-        return ingest_chunk(ctx, "cds_maskset_add_tiff", blob, offsets, i0, cnt, W, H, d_comp, comp_cap, d_strips, strips_cap, stage, stream, strips);
+    return cds::abi_guard("cds_maskset_add_tiff", [&]() -> cds_status {
+        if (!ms) { set_tls_error("cds_maskset_add_tiff: NULL mask set"); return CDS_ERR_BAD_ARG; }
+        cds_ctx *ctx = ms->ctx;
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || (n > 0 && (!blob || !offsets))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_tiff: bad arguments");
+        if (n == 0) return CDS_OK;
+        const int W = ms->W, H = ms->H;
+        // maskset_append asks for runs of at most 64 masks; uploads and decodes are ordered on one stream, so one buffer does
+        size_t comp_cap = 0, strips_cap = 0;
+        ingest_bounds(offsets, n, 64, W, H, comp_cap, strips_cap);
+        for (int64_t i = 0; i < n; i++) comp_cap = std::max(comp_cap, (size_t) std::max<int64_t>(offsets[std::min<int64_t>(n, i + 64)] - offsets[i], 0) + 64);
+        DevState &d0 = ctx->devs[0];
+        CDS_CUDA(ctx, cudaSetDevice(d0.dev));
+        uint8_t *d_comp = nullptr;
+        TiffStrip *d_strips = nullptr;
+        auto release = [&]() { cudaStreamSynchronize(d0.copy_stream); cudaStreamSynchronize(d0.stream); d0.pool.free(d_comp); d0.pool.free(d_strips); };
+        struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
+        CDS_CUDA(ctx, d0.pool.alloc((void **) &d_comp, comp_cap));
+        CDS_CUDA(ctx, d0.pool.alloc((void **) &d_strips, strips_cap * sizeof(TiffStrip)));
+        std::vector<TiffStrip> strips;
+        return maskset_append(ms, n, mask_size_out, [&](int i0, int cnt, uint8_t *stage, cudaStream_t stream) -> cds_status {
+            return ingest_chunk(ctx, "cds_maskset_add_tiff", blob, offsets, i0, cnt, W, H, d_comp, comp_cap, d_strips, strips_cap, stage, stream, strips);
+        });
     });
 }

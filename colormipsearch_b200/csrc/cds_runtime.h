@@ -8,6 +8,8 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -71,9 +73,32 @@ struct DevState {
     MatchScratch match_scratch;       // allocated on first use (cds_ctx::ensure_match_scratch)
     uint32_t *pair_plane = nullptr;   // one code plane + one score word for cds_score_pair_rgb
     int pair_W = 0, pair_H = 0;
+    uint16_t *d_slice_tab = nullptr;  // shape path: slice number of every (channel pair, max, second) (cds_shape.cu), built on first use
+    std::vector<cudaEvent_t> shape_timing;   // pairs around every window's pair kernel
 };
+void shape_release_dev(DevState &ds);
 
 void set_tls_error(const std::string &msg);
+
+// Every exported function runs its body through this: "nothing aborts or throws across the ABI" (include/cdsgpu.h).  A C++
+// exception (std::bad_alloc from a vector sized by caller input, std::length_error, ...) would otherwise unwind through the C
+// boundary and, in the Java binding, through FFM / JNI frames.  Locks taken inside the body are released by the unwinding.
+template <class F>
+inline cds_status abi_guard(const char *name, F &&body) noexcept
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        try { set_tls_error(std::string(name) + ": out of host memory"); } catch (...) {}
+        return CDS_ERR_OOM;
+    } catch (const std::exception &e) {
+        try { set_tls_error(std::string(name) + ": " + e.what()); } catch (...) {}
+        return CDS_ERR_CUDA;
+    } catch (...) {
+        try { set_tls_error(std::string(name) + ": unknown C++ exception"); } catch (...) {}
+        return CDS_ERR_CUDA;
+    }
+}
 
 }  // namespace cds
 

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/cdsgpu.h"
+#include "cds_runtime.h"
 
 namespace cds { void set_tls_error(const std::string &msg); }
 
@@ -78,24 +79,26 @@ extern "C" cds_status cds_select_best_matches(const int32_t *line, const int32_t
                                               int32_t top_lines, int32_t top_samples_per_line, int32_t top_matches_per_sample,
                                               int64_t *selected, int64_t *n_selected)
 {
-    if (n < 0 || n_lines < 0 || n_samples < 0 || !n_selected || (n > 0 && (!line || !sample || !score || !line_hash || !sample_hash || !selected))) {
-        cds::set_tls_error("cds_select_best_matches: bad arguments");
-        return CDS_ERR_BAD_ARG;
-    }
-    for (int64_t i = 0; i < n; i++)
-        if (line[i] < 0 || line[i] >= n_lines || sample[i] < 0 || sample[i] >= n_samples) {
-            cds::set_tls_error("cds_select_best_matches: group id out of range");
+    return cds::abi_guard("cds_select_best_matches", [&]() -> cds_status {
+        if (n < 0 || n_lines < 0 || n_samples < 0 || !n_selected || (n > 0 && (!line || !sample || !score || !line_hash || !sample_hash || !selected))) {
+            cds::set_tls_error("cds_select_best_matches: bad arguments");
             return CDS_ERR_BAD_ARG;
         }
-    std::vector<int64_t> all(n);
-    std::iota(all.begin(), all.end(), 0);
-    std::vector<int32_t> line_slot(n_lines, -1), sample_slot(n_samples, -1);
-    int64_t out = 0;
-    for (const Group &ln : select_top_ranked(all, line, line_hash, n_lines, score, top_lines, -1, line_slot))
-        for (const Group &sm : select_top_ranked(ln.items, sample, sample_hash, n_samples, score, top_samples_per_line, top_matches_per_sample, sample_slot))
-            for (int64_t it : sm.items) selected[out++] = it;
-    *n_selected = out;
-    return CDS_OK;
+        for (int64_t i = 0; i < n; i++)
+            if (line[i] < 0 || line[i] >= n_lines || sample[i] < 0 || sample[i] >= n_samples) {
+                cds::set_tls_error("cds_select_best_matches: group id out of range");
+                return CDS_ERR_BAD_ARG;
+            }
+        std::vector<int64_t> all(n);
+        std::iota(all.begin(), all.end(), 0);
+        std::vector<int32_t> line_slot(n_lines, -1), sample_slot(n_samples, -1);
+        int64_t out = 0;
+        for (const Group &ln : select_top_ranked(all, line, line_hash, n_lines, score, top_lines, -1, line_slot))
+            for (const Group &sm : select_top_ranked(ln.items, sample, sample_hash, n_samples, score, top_samples_per_line, top_matches_per_sample, sample_slot))
+                for (int64_t it : sm.items) selected[out++] = it;
+        *n_selected = out;
+        return CDS_OK;
+    });
 }
 
 // String.hashCode() of a UTF-16 string given as UTF-8 restricted to the Basic Multilingual Plane subset the names use (ASCII):

@@ -10,12 +10,28 @@
 //
 // B200 formulation.  PIXEL_GAP_OP is zero wherever the (label-cleared, ROI-masked) query pixel is black -- its "queryMask * gradient"
 // term needs gray(query) > 2 -- so the gradient-area gap is a sum over the query's NON-BLACK pixels only (~1-3 % of the image).
-// Per mask the device keeps (a) that pixel list with the query's slice number folded in, (b) the high-expression mask and its
-// row-mirrored copy as bitmaps.  Per target it keeps the slice-number plane of the thresholded zgap image, the gradient plane and
-// the "above threshold outside labels" bitmap.  One CTA scores one (mask, target) pair in both orientations: a gather over the
-// pixel list for the gaps, and an AND + POPC sweep over the bitmaps for the high-expression area.
+// Per mask the devices keep (a) that pixel list with the query's slice number folded in, (b) the high-expression mask and its
+// row-mirrored copy as bitmaps.  Per target a device keeps, for as long as the target's window is being scored, the slice-number
+// plane of the thresholded zgap image, the gradient plane and the "above threshold outside labels" bitmap.  One CTA scores one
+// (mask, target) pair in both orientations: a gather over the pixel list for the gaps, and an AND + POPC sweep over the bitmaps for
+// the high-expression area.
+//
+// What is new against the first version of this file (profiles/r01_shape_launches.csv: the u8 disc max filter took 65 % of the
+// device time at 1.8 % of the HBM peak, the slice planes 23 %, the pair kernel 3 %):
+//   * the zgap image is never materialised.  shape_target_derive_kernel stages a tile of the thresholded, label-cleared target as
+//     16-bit lanes (two pixels per 32-bit word), dilates it with the ImageJ disc by a nested-rectangle (Horner) scheme whose only
+//     arithmetic is the 3-input packed maximum VIMNMX3.U16x2, and turns the three channel maxima straight into a slice number.
+//   * slice numbers come from a table [max/second channel pair][max][second] built once per device by the reference's own double
+//     arithmetic (findSliceNumberInLUT), not from up to 56 double divisions per pixel.
+//   * the mask side only ever needs ZERO / NON-ZERO facts about the r = 60 and r = 20 dilations, so it is binary morphology on
+//     bitmaps (64 pixels per lane and instruction) instead of two u8 disc filters; masks are prepared in batches with one
+//     device round trip per batch instead of two per mask.
+//   * targets are processed in windows (device memory does not grow with the call) that are dealt out over ALL devices of the
+//     context; the shape mask data is replicated like the pixel-match masks (pairs go to the device that holds the target).
 #include <algorithm>
 #include <cmath>
+#include <memory>
+#include <numeric>
 #include <vector>
 
 #include "cds_lut.h"
@@ -28,15 +44,6 @@ namespace cds {
 
 // ------------------------------------------------------------------------------------------------------------------ slice numbers
 __constant__ uint8_t c_shape_lut[256 * 3];
-static bool g_shape_lut_uploaded[64] = {false};
-
-static cudaError_t ensure_shape_lut(int dev)
-{
-    if (dev < 64 && g_shape_lut_uploaded[dev]) return cudaSuccess;
-    cudaError_t e = cudaMemcpyToSymbol(c_shape_lut, kColorDepthLut, sizeof(kColorDepthLut));
-    if (e == cudaSuccess && dev < 64) g_shape_lut_uploaded[dev] = true;
-    return e;
-}
 
 // findSliceNumberInLUT, API/cds/GradientAreaGapUtils.java:131-197 (IEEE double, no contraction: the file is built with --fmad=false)
 __device__ int find_slice_in_lut(int lo, int hi, double colorRatio)
@@ -63,22 +70,44 @@ __device__ int find_slice_in_lut(int lo, int hi, double colorRatio)
     return sliceNumber;
 }
 
-// the slice of one colour: first half of calculateSliceGap (:18-99) + findSliceNumber (:107-129).  0 for black.
-__device__ int slice_number(int red, int green, int blue)
+// The slice of a colour is a function of (which channel is the maximum, which is the second -- ties resolved by the >= order of
+// calculateSliceGap :31-93 --, the two values): 6 x 256 x 256 entries, built once per device with the arithmetic above.
+//   pair 0: R max, G second (LUT 171..212)   1: R, B (213..255)   2: G, R (128..170)   3: G, B (86..127)   4: B, R (0..29)   5: B, G (30..85)
+constexpr int kSliceTabEntries = 6 * 65536;
+
+__global__ void build_slice_table_kernel(uint16_t *__restrict__ tab)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kSliceTabEntries) return;
+    const int pair = i >> 16, max1 = (i >> 8) & 255, max2 = i & 255;
+    const int lo[6] = {171, 213, 128, 86, 0, 30}, hi[6] = {212, 255, 170, 127, 29, 85};
+    int s = 0;
+    if (max1 > 0 && max2 <= max1) s = find_slice_in_lut(lo[pair], hi[pair], (double) max2 / (double) max1);
+    tab[i] = (uint16_t) s;
+}
+
+// first half of calculateSliceGap (:18-99) + findSliceNumber (:107-129).  0 for black.
+__device__ __forceinline__ int slice_of(const uint16_t *__restrict__ tab, int red, int green, int blue)
 {
     if ((red | green | blue) == 0) return 0;
-    int max1, max2, lo, hi;
+    int max1, max2, pair;
     if (red >= green && red >= blue) {
         max1 = red;
-        if (green >= blue) { max2 = green; lo = 171; hi = 212; } else { max2 = blue; lo = 213; hi = 255; }
+        if (green >= blue) { max2 = green; pair = 0; } else { max2 = blue; pair = 1; }
     } else if (green >= red && green >= blue) {
         max1 = green;
-        if (red >= blue) { max2 = red; lo = 128; hi = 170; } else { max2 = blue; lo = 86; hi = 127; }
+        if (red >= blue) { max2 = red; pair = 2; } else { max2 = blue; pair = 3; }
     } else {
         max1 = blue;
-        if (red >= green) { max2 = red; lo = 0; hi = 29; } else { max2 = green; lo = 30; hi = 85; }
+        if (red >= green) { max2 = red; pair = 4; } else { max2 = green; pair = 5; }
     }
-    return find_slice_in_lut(lo, hi, (double) max2 / (double) max1);
+    return (int) __ldg(tab + ((pair << 16) | (max1 << 8) | max2));
+}
+
+__global__ void slice_numbers_kernel(const uint8_t *__restrict__ rgb, int64_t n, const uint16_t *__restrict__ tab, uint16_t *__restrict__ out)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        out[i] = (uint16_t) slice_of(tab, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
 }
 
 __device__ __forceinline__ bool shape_in_rects(const RectSet &r, int x, int y)
@@ -91,21 +120,68 @@ __device__ __forceinline__ bool shape_in_rects(const RectSet &r, int x, int y)
 }
 
 // rgbToGrayNoGammaCorrection with maxGrayValue 255 (ColorTransformation.java:40-54, :103) in its exact integer form
-// floor((2 (r + g + b) + 3) / 6): the double expression is never within 1/6 of an integer boundary (checked over all 2^24 colours
-// against the oracle, tests/test_oracle_golden.py::test_gray_integer_form)
+// floor((2 (r + g + b) + 3) / 6): the double expression is never within 1/6 of an integer boundary (checked over ALL 2^24 colours
+// against the oracle's double expression, tests/test_oracle_golden.py::test_gray_integer_form)
 __device__ __forceinline__ int gray_of(int r, int g, int b) { return (r | g | b) == 0 ? 0 : (2 * (r + g + b) + 3) / 6; }
 
-// ------------------------------------------------------------------------------------------------------------------ max filter
-// Disc dilation with ImageJ's RankFilters disc (makeLineRadii): dst(x,y,c) = max over dy in [-k,k], |dx| <= dxs[dy+k] of
-// src(x+dx, y+dy, c), pixels outside the image ignored.  One CTA produces a TR x TC tile of one channel: the tile plus a k-wide
-// halo is loaded into shared memory, a sparse table of horizontal running maxima over windows 1,2,4,.. is built next to it, and
-// every disc row then costs two table reads.  Tiles whose halo is entirely zero (most of a colour-depth MIP) are written as zeros.
-constexpr int kMfTR = 16, kMfTC = 64;
-
+// ------------------------------------------------------------------------------------------------------------------ the ImageJ disc
+// makeLineRadii, API/imageprocessing/ImageTransformation.java:549-572: rows dy = -k..k with half widths dxs[dy + k].
 struct DiscSpec {
     int k;
     int dxs[121];      // half widths for dy = -k..k (k <= 60)
 };
+
+static DiscSpec make_disc(double radiusArg)
+{
+    DiscSpec d{};
+    double radius;
+    if (radiusArg >= 1.5 && radiusArg < 1.75) radius = 1.75;
+    else if (radiusArg >= 2.5 && radiusArg < 2.85) radius = 2.85;
+    else radius = radiusArg;
+    const int r2 = (int) (radius * radius) + 1;
+    const int k = (int) (std::sqrt(r2 + 1e-10));
+    d.k = k;
+    if (k > 60) return d;
+    for (int y = -k; y <= k; y++) d.dxs[y + k] = (y == 0) ? k : (int) (std::sqrt(r2 - y * y + 1e-10));
+    return d;
+}
+
+// The disc as a union of nested rectangles.  Its half widths never grow with |dy|, so with w_1 > w_2 > .. > w_n the distinct
+// half widths and h_i the largest |dy| whose row is at least w_i wide, disc = U_i [-w_i, w_i] x [-h_i, h_i] (h grows as w shrinks).
+// A max (or OR) over a rectangle is a horizontal max of half width w_i of the vertical max over |dy| <= h_i, and because both
+// families are nested the whole union evaluates Horner-style:
+//     X = 0;  for i = 1..n:  X = max(X, rows h_(i-1) < |dy| <= h_i);  X = hmax_(w_i - w_(i+1))(X)        (w_(n+1) = 0)
+// i.e. every row of the window is read once (2k + 1 reads) and the horizontal work is w_1 = k single-pixel steps in total,
+// whatever the number of rectangles.
+struct DiscRings {
+    int k, n;
+    int8_t h[64];      // last |dy| of ring i
+    int8_t d[64];      // horizontal steps after ring i
+};
+
+static DiscRings make_rings(const DiscSpec &disc)
+{
+    DiscRings r{};
+    r.k = disc.k;
+    int i = 0;
+    for (int dy = 0; dy <= disc.k;) {
+        const int w = disc.dxs[disc.k + dy];
+        int last = dy;
+        while (last + 1 <= disc.k && disc.dxs[disc.k + last + 1] == w) last++;
+        const int wn = last + 1 <= disc.k ? disc.dxs[disc.k + last + 1] : 0;
+        r.h[i] = (int8_t) last;
+        r.d[i] = (int8_t) (w - wn);
+        i++;
+        dy = last + 1;
+    }
+    r.n = i;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ u8 max filter (generic radii)
+// Kept for cds_make_zgap with radii beyond the fused kernel's halo (k > 16): one CTA produces a TR x TC tile of one channel from a
+// sparse table of horizontal running maxima.  Not on the scoring path.
+constexpr int kMfTR = 16, kMfTC = 64;
 
 __global__ void __launch_bounds__(256) max_filter_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int W, int H, int nch,
                                                          DiscSpec disc, int nlev)
@@ -170,26 +246,8 @@ __global__ void __launch_bounds__(256) max_filter_kernel(const uint8_t *__restri
     }
 }
 
-static DiscSpec make_disc(double radiusArg)
+static bool launch_max_filter(const uint8_t *src, uint8_t *dst, int64_t n, int W, int H, int nch, const DiscSpec &disc, cudaStream_t s)
 {
-    // makeLineRadii, API/imageprocessing/ImageTransformation.java:549-572
-    DiscSpec d{};
-    double radius;
-    if (radiusArg >= 1.5 && radiusArg < 1.75) radius = 1.75;
-    else if (radiusArg >= 2.5 && radiusArg < 2.85) radius = 2.85;
-    else radius = radiusArg;
-    const int r2 = (int) (radius * radius) + 1;
-    const int k = (int) (std::sqrt(r2 + 1e-10));
-    d.k = k;
-    if (k > 60) return d;
-    for (int y = -k; y <= k; y++) d.dxs[y + k] = (y == 0) ? k : (int) (std::sqrt(r2 - y * y + 1e-10));
-    return d;
-}
-
-// dilates n images of nch interleaved channels; returns false when the radius is not supported
-static bool launch_max_filter(const uint8_t *src, uint8_t *dst, int64_t n, int W, int H, int nch, double radius, cudaStream_t s)
-{
-    DiscSpec disc = make_disc(radius);
     if (disc.k > 60 || disc.k < 0) return false;
     int nlev = 1;
     while ((1 << nlev) <= 2 * disc.k + 1) nlev++;
@@ -203,7 +261,6 @@ static bool launch_max_filter(const uint8_t *src, uint8_t *dst, int64_t n, int W
     return true;
 }
 
-// ------------------------------------------------------------------------------------------------------------------ image transforms
 // dst = clearRegion(src) then optionally mask(threshold): black inside label rectangles, black where every channel <= threshold
 __global__ void clear_and_mask_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int64_t n, int W, int H, RectSet rects,
                                       int threshold, int apply_mask)
@@ -219,10 +276,169 @@ __global__ void clear_and_mask_kernel(const uint8_t *__restrict__ src, uint8_t *
     }
 }
 
-// target side of a pair: zslice = slice number of mask(threshold)(zgap) (0 = black), tsig bit = clearLabels(target) above threshold
+// ------------------------------------------------------------------------------------------------------------------ target side, fused
+// zslice(x, y) = slice number of mask(threshold)(maxFilter_r(mask(threshold)(clearLabels(target))))(x, y), tsig bit = clearLabels(target)
+// above threshold -- Shape2DMatchColorDepthSearchAlgorithm.java:159-161 with the zgap image the reference's tests derive
+// (Shape2DMatchColorDepthSearchAlgorithmTest.java:171-174) -- in one pass over the target's RGB bytes.
+//
+// A CTA produces kZgTH rows x kZgStrip columns.  The strip plus kZgHalo columns on either side (128 pixels) and the rows plus k
+// above and below are staged per channel as u16 lanes, two pixels per word (pixel 2j in the low half of word j).  A warp then
+// owns one output row at a time; lane l holds pixels 4l..4l+3 of the strip as two words, reads the 2k + 1 window rows ring by
+// ring (LDS.64 + VIMNMX3.U16x2) and after each ring widens the running maximum by single-pixel steps: the neighbours' edge
+// pixels arrive by two shuffles, PRMT lines the three shifted pairs up, VIMNMX3 takes the maximum.  Garbage creeps in from the
+// strip's ends one pixel per step, k <= kZgHalo pixels in all, so the strip's own columns are exact.  Rows whose whole window is
+// black (most of a colour-depth MIP) are skipped.
+constexpr int kZgTH = 32;
+constexpr int kZgStrip = 96;
+constexpr int kZgHalo = 16;
+constexpr int kZgWords = (kZgStrip + 2 * kZgHalo) / 2;      // 64 words = 128 pixels per staged row
+
+__device__ __forceinline__ uint32_t vmax3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+
+template <bool OUT_RGB>
+__global__ void __launch_bounds__(256) shape_target_derive_kernel(const uint8_t *__restrict__ target, int W, int H, RectSet rects, int threshold,
+                                                                  DiscRings rings, const uint16_t *__restrict__ slice_tab,
+                                                                  uint16_t *__restrict__ zslice, uint32_t *__restrict__ tsig, int bpitch,
+                                                                  uint8_t *__restrict__ rgb_out)
+{
+    extern __shared__ uint32_t s_in[];                         // [3][rows][kZgWords]
+    __shared__ uint32_t s_sig[kZgTH][4];
+    __shared__ int s_rowpre[kZgTH + 2 * kZgHalo + 2];          // prefix sums of "row has a non-black pixel"
+    const int k = rings.k;
+    const int rows = kZgTH + 2 * k;
+    const int64_t img = blockIdx.z;
+    const int x0 = blockIdx.x * kZgStrip, y0 = blockIdx.y * kZgTH;
+    const int xin = x0 - kZgHalo, yin = y0 - k;
+    const uint8_t *src = target + (size_t) img * W * H * 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid < kZgTH * 4) s_sig[0][tid] = 0;
+    if (tid <= rows) s_rowpre[tid] = 0;
+    __syncthreads();
+
+    // ---- stage: one pixel pair per thread and step
+    int any = 0;
+    for (int i = tid; i < rows * kZgWords; i += 256) {
+        const int row = i / kZgWords, j = i % kZgWords;
+        const int y = yin + row, x = xin + 2 * j;
+        uint32_t wr = 0, wg = 0, wb = 0;
+        if (y >= 0 && y < H) {
+            const uint8_t *p = src + ((size_t) y * W + x) * 3;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int xx = x + e;
+                if (xx < 0 || xx >= W) continue;
+                const int r = p[3 * e], g = p[3 * e + 1], b = p[3 * e + 2];
+                const bool keep = !shape_in_rects(rects, xx, y) && (r > threshold || g > threshold || b > threshold);
+                if (!keep) continue;
+                wr |= (uint32_t) r << (16 * e); wg |= (uint32_t) g << (16 * e); wb |= (uint32_t) b << (16 * e);
+                const int sx = xx - x0, sy = y - y0;
+                if (!OUT_RGB && sx >= 0 && sx < kZgStrip && sy >= 0 && sy < kZgTH) atomicOr(&s_sig[sy][sx >> 5], 1u << (sx & 31));
+            }
+        }
+        s_in[(0 * rows + row) * kZgWords + j] = wr;
+        s_in[(1 * rows + row) * kZgWords + j] = wg;
+        s_in[(2 * rows + row) * kZgWords + j] = wb;
+        if (wr | wg | wb) { any = 1; s_rowpre[row + 1] = 1; }       // benign race: every writer stores 1
+    }
+    any = __syncthreads_or(any);
+
+    if (!OUT_RGB) {
+        // the target's signal bitmap of this tile (row layout, 32 pixels per word; x0 is a multiple of 32)
+        // (the last strip also clears the row's pad words)
+        const int nw = blockIdx.x + 1 == gridDim.x ? bpitch - (x0 >> 5) : 3;
+        for (int i = tid; i < kZgTH * nw; i += 256) {
+            const int sy = i / nw, wi = i % nw;
+            const int y = y0 + sy, wcol = (x0 >> 5) + wi;
+            if (y < H && wcol < bpitch) tsig[((size_t) img * H + y) * bpitch + wcol] = wi < 3 ? s_sig[sy][wi] : 0u;
+        }
+    }
+    if (!any) {
+        // nothing above the threshold anywhere near: the tile's output is black
+        for (int i = tid; i < kZgTH * kZgStrip; i += 256) {
+            const int y = y0 + i / kZgStrip, x = x0 + i % kZgStrip;
+            if (y >= H || x >= W) continue;
+            if (OUT_RGB) { uint8_t *o = rgb_out + (((size_t) img * H + y) * W + x) * 3; o[0] = o[1] = o[2] = 0; }
+            else zslice[((size_t) img * H + y) * W + x] = 0;
+        }
+        return;
+    }
+    if (tid == 0) {
+        int acc = 0;
+        for (int r = 0; r < rows; r++) { acc += s_rowpre[r + 1]; s_rowpre[r + 1] = acc; }
+    }
+    __syncthreads();
+
+    for (int ro = warp; ro < kZgTH; ro += 8) {
+        const int y = y0 + ro;
+        if (y >= H) break;
+        uint32_t res[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
+        if (s_rowpre[ro + 2 * k + 1] - s_rowpre[ro] > 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const uint32_t *base = s_in + ((size_t) c * rows + ro + k) * kZgWords + 2 * lane;      // the window's centre row, this lane's words
+                uint32_t X0 = 0, X1 = 0;
+                int dy = 0;
+                for (int i = 0; i < rings.n; i++) {
+                    const int h = rings.h[i];
+                    for (; dy <= h; dy++) {
+                        const uint2 a = *reinterpret_cast<const uint2 *>(base - dy * kZgWords);
+                        const uint2 b = *reinterpret_cast<const uint2 *>(base + dy * kZgWords);
+                        X0 = vmax3_u16x2(X0, a.x, b.x);
+                        X1 = vmax3_u16x2(X1, a.y, b.y);
+                    }
+                    for (int s = rings.d[i]; s > 0; s--) {
+                        uint32_t left = __shfl_up_sync(0xffffffffu, X1, 1), right = __shfl_down_sync(0xffffffffu, X0, 1);
+                        if (lane == 0) left = 0;
+                        if (lane == 31) right = 0;
+                        const uint32_t A0 = __byte_perm(left, X0, 0x5432);      // pixels (4l - 1, 4l)
+                        const uint32_t B0 = __byte_perm(X0, X1, 0x5432);        // pixels (4l + 1, 4l + 2)
+                        const uint32_t B1 = __byte_perm(X1, right, 0x5432);     // pixels (4l + 3, 4l + 4)
+                        X0 = vmax3_u16x2(A0, X0, B0);
+                        X1 = vmax3_u16x2(B0, X1, B1);
+                    }
+                }
+                res[c][0] = X0; res[c][1] = X1;
+            }
+        }
+        // this lane's four pixels: strip columns 4l - kZgHalo .. + 3
+        const int sx = 4 * lane - kZgHalo;
+        if (sx < 0 || sx >= kZgStrip) continue;
+        const int x = x0 + sx;
+        if (OUT_RGB) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (x + e >= W) break;
+                uint8_t *o = rgb_out + (((size_t) img * H + y) * W + x + e) * 3;
+                o[0] = (uint8_t) ((res[0][e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+                o[1] = (uint8_t) ((res[1][e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+                o[2] = (uint8_t) ((res[2][e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+            }
+        } else {
+            uint32_t sl[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int r = (int) ((res[0][e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+                const int g = (int) ((res[1][e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+                const int b = (int) ((res[2][e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+                sl[e] = (r > threshold || g > threshold || b > threshold) ? (uint32_t) slice_of(slice_tab, r, g, b) : 0u;   // mask(threshold) then slice
+            }
+            uint16_t *o = zslice + ((size_t) img * H + y) * W + x;
+            if ((W & 1) == 0 && x + 3 < W) {
+                *reinterpret_cast<uint32_t *>(o) = sl[0] | (sl[1] << 16);
+                *reinterpret_cast<uint32_t *>(o + 2) = sl[2] | (sl[3] << 16);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) if (x + e < W) o[e] = (uint16_t) sl[e];
+            }
+        }
+    }
+}
+
+// target side of a pair when the caller supplies the zgap image: zslice = slice number of mask(threshold)(zgap), tsig as above
 __global__ void __launch_bounds__(256) target_planes_kernel(const uint8_t *__restrict__ target, const uint8_t *__restrict__ zgap, int W, int H,
-                                                            RectSet rects, int threshold, int bpitch, uint16_t *__restrict__ zslice,
-                                                            uint32_t *__restrict__ tsig)
+                                                            RectSet rects, int threshold, int bpitch, const uint16_t *__restrict__ slice_tab,
+                                                            uint16_t *__restrict__ zslice, uint32_t *__restrict__ tsig)
 {
     const int y = blockIdx.x;
     const int64_t img = blockIdx.y;
@@ -239,7 +455,7 @@ __global__ void __launch_bounds__(256) target_planes_kernel(const uint8_t *__res
             sig = !shape_in_rects(rects, x, y) && (r > threshold || g > threshold || b > threshold);
             const int zr = zrow[3 * x], zg = zrow[3 * x + 1], zb = zrow[3 * x + 2];
             int sl = 0;
-            if (zr > threshold || zg > threshold || zb > threshold) sl = slice_number(zr, zg, zb);   // mask(threshold) then slice
+            if (zr > threshold || zg > threshold || zb > threshold) sl = slice_of(slice_tab, zr, zg, zb);   // mask(threshold) then slice
             zs[x] = (uint16_t) sl;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, sig);
@@ -247,56 +463,173 @@ __global__ void __launch_bounds__(256) target_planes_kernel(const uint8_t *__res
     }
 }
 
-// mask side: from Q (label-cleared query), max60(Q), max20(Q) and the label-cleared ROI (or NULL):
-//   QM = gray(Q) > 2, HE = max20 == black && gray(max60) > 0            (ProviderFactory :105-111)
-//   gap list entry for every pixel with Q != black that the ROI keeps in at least one orientation:
-//       x | y << 11 | (slice(Q) - 1) << 21 | QM << 29 | keep_normal << 30 | keep_mirrored << 31
-//   bitmaps he_n = HE & ROI, he_m = mirror(HE) & ROI;  counters[0] += sum QM, counters[1] += sum HE, counters[2] = list length
-__global__ void __launch_bounds__(256) mask_planes_kernel(const uint8_t *__restrict__ q, const uint8_t *__restrict__ m60, const uint8_t *__restrict__ m20,
-                                                          const uint8_t *__restrict__ roi, int W, int H, int bpitch,
-                                                          uint32_t *__restrict__ he_n, uint32_t *__restrict__ he_m,
-                                                          uint32_t *__restrict__ gap_list, unsigned long long *__restrict__ counters)
+// ------------------------------------------------------------------------------------------------------------------ mask side
+// createShapeMatchCDSAlgorithmProvider :96-111 needs of the two dilations of Q (the label-cleared query) only
+//     max20(Q) == black            <=>  no non-black pixel of Q inside the r = 20 disc                              = !dil20(N)
+//     gray(max60(Q)) > 0           <=>  the three channel maxima over the r = 60 disc add up to >= 2 (gray_of above)
+//                                  <=>  dil60(B2) | at least two of dil60(A_r), dil60(A_g), dil60(A_b)
+// with the bitmaps N = "some channel > 0", B2 = "some channel >= 2", A_c = "channel c >= 1" -- binary dilations, 64 pixels per
+// lane.  Scratch bitmaps are [which][mask][H][bpitch] with which = 0 (N, r = 20) and 1..4 (B2, A_r, A_g, A_b, r = 60).
+constexpr int kMaskBitmaps = 5;
+
+// per (mask, row): the five bitmaps, QM = gray(Q) > 2 count (counters[m][0]), gap-list length (counters[m][2]), row flags
+__global__ void __launch_bounds__(256) shape_mask_bits_kernel(const uint8_t *__restrict__ rgb, int n_masks, int W, int H, int bpitch, RectSet rects,
+                                                              const uint32_t *__restrict__ roi_bits, uint32_t *__restrict__ bits,
+                                                              uint8_t *__restrict__ rowany, unsigned long long *__restrict__ counters)
 {
-    const int y = blockIdx.x;
-    const uint8_t *qrow = q + (size_t) y * W * 3;
-    const uint8_t *arow = m60 + (size_t) y * W * 3;
-    const uint8_t *brow = m20 + (size_t) y * W * 3;
-    const uint8_t *rrow = roi ? roi + (size_t) y * W * 3 : nullptr;
+    const int y = blockIdx.x, m = blockIdx.y;
+    const uint8_t *row = rgb + ((size_t) m * H + y) * W * 3;
+    const size_t plane = (size_t) n_masks * H * bpitch;
+    uint32_t *out = bits + ((size_t) m * H + y) * bpitch;
     const int lane = threadIdx.x & 31;
-    int qm_cnt = 0, he_cnt = 0;
+    int qm_cnt = 0, list_cnt = 0, nz = 0;
     for (int x0 = (threadIdx.x >> 5) * 32; x0 < bpitch * 32; x0 += (int) blockDim.x) {
-        const int x = x0 + lane;          // normal orientation: output pixel x takes HE(x)
-        const int xs = W - 1 - x;         // mirrored orientation: output pixel x takes HE(W-1-x)
-        bool hn = false, hm = false;
-        if (x < W) {
-            const bool keep = !rrow || (rrow[3 * x] | rrow[3 * x + 1] | rrow[3 * x + 2]) != 0;
-            const bool he_here = (brow[3 * x] | brow[3 * x + 1] | brow[3 * x + 2]) == 0 && gray_of(arow[3 * x], arow[3 * x + 1], arow[3 * x + 2]) > 0;
-            const bool he_mir = (brow[3 * xs] | brow[3 * xs + 1] | brow[3 * xs + 2]) == 0 && gray_of(arow[3 * xs], arow[3 * xs + 1], arow[3 * xs + 2]) > 0;
-            hn = he_here && keep;
-            hm = he_mir && keep;
-            he_cnt += he_here ? 1 : 0;
-            const int r = qrow[3 * x], g = qrow[3 * x + 1], b = qrow[3 * x + 2];
-            if ((r | g | b) != 0) {
-                const int qm = gray_of(r, g, b) > 2 ? 1 : 0;
-                qm_cnt += qm;
-                // this query pixel lands on output x (normal) and on output W-1-x (mirrored); the ROI is tested at the output
-                const bool keep_m = !rrow || (rrow[3 * xs] | rrow[3 * xs + 1] | rrow[3 * xs + 2]) != 0;
-                if (keep || keep_m) {
-                    const uint32_t e = (uint32_t) x | ((uint32_t) y << 11) | ((uint32_t) (slice_number(r, g, b) - 1) << 21) |
-                                       ((uint32_t) qm << 29) | ((uint32_t) keep << 30) | ((uint32_t) keep_m << 31);
-                    const unsigned long long slot = atomicAdd(&counters[2], 1ull);
-                    gap_list[slot] = e;
-                }
+        const int x = x0 + lane;
+        bool n = false, b2 = false, ar = false, ag = false, ab = false;
+        if (x < W && !shape_in_rects(rects, x, y)) {
+            const int r = row[3 * x], g = row[3 * x + 1], b = row[3 * x + 2];
+            n = (r | g | b) != 0; b2 = r >= 2 || g >= 2 || b >= 2; ar = r >= 1; ag = g >= 1; ab = b >= 1;
+            if (n) {
+                qm_cnt += gray_of(r, g, b) > 2 ? 1 : 0;
+                const int xs = W - 1 - x;
+                const bool keep = !roi_bits || ((roi_bits[(size_t) y * bpitch + (x >> 5)] >> (x & 31)) & 1u);
+                const bool keep_m = !roi_bits || ((roi_bits[(size_t) y * bpitch + (xs >> 5)] >> (xs & 31)) & 1u);
+                list_cnt += (keep || keep_m) ? 1 : 0;
             }
         }
-        const unsigned bn = __ballot_sync(0xffffffffu, hn), bm = __ballot_sync(0xffffffffu, hm);
-        if (lane == 0) { he_n[(size_t) y * bpitch + (x0 >> 5)] = bn; he_m[(size_t) y * bpitch + (x0 >> 5)] = bm; }
+        const unsigned wn = __ballot_sync(0xffffffffu, n), w2 = __ballot_sync(0xffffffffu, b2);
+        const unsigned wr = __ballot_sync(0xffffffffu, ar), wg = __ballot_sync(0xffffffffu, ag), wb = __ballot_sync(0xffffffffu, ab);
+        if (lane == 0) {
+            const int j = x0 >> 5;
+            out[j] = wn; out[plane + j] = w2; out[2 * plane + j] = wr; out[3 * plane + j] = wg; out[4 * plane + j] = wb;
+        }
+        nz |= wn != 0;
     }
     qm_cnt = __reduce_add_sync(0xffffffffu, qm_cnt);
-    he_cnt = __reduce_add_sync(0xffffffffu, he_cnt);
+    list_cnt = __reduce_add_sync(0xffffffffu, list_cnt);
     if (lane == 0) {
-        if (qm_cnt) atomicAdd(&counters[0], (unsigned long long) qm_cnt);
-        if (he_cnt) atomicAdd(&counters[1], (unsigned long long) he_cnt);
+        if (qm_cnt) atomicAdd(&counters[4 * m + 0], (unsigned long long) qm_cnt);
+        if (list_cnt) atomicAdd(&counters[4 * m + 2], (unsigned long long) list_cnt);
+    }
+    const int any = __syncthreads_or(nz);
+    if (threadIdx.x == 0) rowany[(size_t) m * H + y] = (uint8_t) (any != 0);
+}
+
+// binary disc dilation of bitmap `which` of every mask: one warp per output row, lane j = pixels 64j..64j+63 (two words).
+__global__ void __launch_bounds__(256) shape_mask_dilate_kernel(const uint32_t *__restrict__ bits, const uint8_t *__restrict__ rowany, int n_masks, int H,
+                                                                int bpitch, DiscRings rings20, DiscRings rings60, uint32_t *__restrict__ dil)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y = blockIdx.x * 8 + warp;
+    const int which = blockIdx.y % kMaskBitmaps, m = blockIdx.y / kMaskBitmaps;
+    if (y >= H) return;
+    const DiscRings &rings = which == 0 ? rings20 : rings60;
+    const int k = rings.k;
+    const size_t plane = (size_t) n_masks * H * bpitch;
+    const uint32_t *in = bits + which * plane + (size_t) m * H * bpitch;
+    uint32_t *out = dil + which * plane + ((size_t) m * H + y) * bpitch;
+    const int np = bpitch / 2;
+    // rows of the window that hold anything at all
+    bool some = false;
+    for (int r = y - k + lane; r <= y + k; r += 32)
+        if (r >= 0 && r < H && rowany[(size_t) m * H + r]) some = true;
+    if (!__any_sync(0xffffffffu, some)) {
+        if (lane < np) *reinterpret_cast<uint2 *>(out + 2 * lane) = make_uint2(0u, 0u);
+        return;
+    }
+    uint32_t lo = 0, hi = 0;
+    int dy = 0;
+    for (int i = 0; i < rings.n; i++) {
+        const int h = rings.h[i];
+        for (; dy <= h; dy++) {
+            if (lane < np) {
+                if (y - dy >= 0) { const uint2 a = __ldg(reinterpret_cast<const uint2 *>(in + (size_t) (y - dy) * bpitch) + lane); lo |= a.x; hi |= a.y; }
+                if (dy > 0 && y + dy < H) { const uint2 b = __ldg(reinterpret_cast<const uint2 *>(in + (size_t) (y + dy) * bpitch) + lane); lo |= b.x; hi |= b.y; }
+            }
+        }
+        for (int s = rings.d[i]; s > 0; s--) {
+            uint32_t lefthi = __shfl_up_sync(0xffffffffu, hi, 1), rightlo = __shfl_down_sync(0xffffffffu, lo, 1);
+            if (lane == 0) lefthi = 0;
+            if (lane == 31) rightlo = 0;
+            const uint32_t nlo = lo | __funnelshift_l(lefthi, lo, 1) | __funnelshift_r(lo, hi, 1);
+            const uint32_t nhi = hi | __funnelshift_l(lo, hi, 1) | __funnelshift_r(hi, rightlo, 1);
+            lo = nlo; hi = nhi;
+        }
+    }
+    if (lane < np) *reinterpret_cast<uint2 *>(out + 2 * lane) = make_uint2(lo, hi);
+}
+
+// HE = !dil20(N) & (dil60(B2) | majority(dil60(A_r), dil60(A_g), dil60(A_b))) inside the image; he_n = HE & ROI,
+// he_m = mirror(HE) & ROI (the ROI is not mirrored with the query, Shape2DMatch...:205-218); counters[m][1] += |HE|.
+__global__ void __launch_bounds__(64) shape_mask_finish_kernel(const uint32_t *__restrict__ dil, int n_masks, int W, int H, int bpitch,
+                                                               const uint32_t *__restrict__ roi_bits, uint32_t *const *__restrict__ he_n_ptrs,
+                                                               uint32_t *const *__restrict__ he_m_ptrs, unsigned long long *__restrict__ counters)
+{
+    __shared__ uint32_t s_he[66];
+    const int y = blockIdx.x, m = blockIdx.y, j = threadIdx.x;
+    const size_t plane = (size_t) n_masks * H * bpitch;
+    const uint32_t *d = dil + ((size_t) m * H + y) * bpitch;
+    uint32_t he = 0;
+    if (j < bpitch) {
+        const uint32_t dn = d[j], d2 = d[plane + j], dr = d[2 * plane + j], dg = d[3 * plane + j], db = d[4 * plane + j];
+        he = ~dn & (d2 | (dr & dg) | (dr & db) | (dg & db));
+        const int rem = W - 32 * j;                                           // pixels of this word that are inside the image
+        if (rem <= 0) he = 0;
+        else if (rem < 32) he &= (1u << rem) - 1u;
+    }
+    s_he[j + 1] = he;
+    if (j == 0) { s_he[0] = 0; s_he[65] = 0; }
+    int cnt = __popc(he);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((j & 31) == 0 && cnt) atomicAdd(&counters[4 * m + 1], (unsigned long long) cnt);
+    __syncthreads();
+    if (j >= bpitch) return;
+    const uint32_t roi = roi_bits ? roi_bits[(size_t) y * bpitch + j] : 0xffffffffu;
+    he_n_ptrs[m][(size_t) y * bpitch + j] = he & roi;
+    // mirrored word j: output pixel x = 32 j + b takes HE(W - 1 - x); the 32 source pixels start at lo = W - 32 - 32 j
+    const int lo = W - 32 - 32 * j;
+    const int idx = lo >> 5, off = lo & 31;                                   // floor division: lo may be negative
+    const uint32_t w0 = (idx >= 0 && idx < 64) ? s_he[idx + 1] : 0u, w1 = (idx + 1 >= 0 && idx + 1 < 64) ? s_he[idx + 2] : 0u;
+    const uint32_t v = __funnelshift_r(w0, w1, off);
+    he_m_ptrs[m][(size_t) y * bpitch + j] = __brev(v) & roi;
+}
+
+// gap list entry for every pixel with Q != black that the ROI keeps in at least one orientation:
+//     x | y << 11 | (slice(Q) - 1) << 21 | QM << 29 | keep_normal << 30 | keep_mirrored << 31
+__global__ void __launch_bounds__(256) shape_mask_list_kernel(const uint8_t *__restrict__ rgb, int W, int H, int bpitch, RectSet rects,
+                                                              const uint32_t *__restrict__ roi_bits, const uint16_t *__restrict__ slice_tab,
+                                                              uint32_t *const *__restrict__ list_ptrs, unsigned long long *__restrict__ counters)
+{
+    const int y = blockIdx.x, m = blockIdx.y;
+    const uint8_t *row = rgb + ((size_t) m * H + y) * W * 3;
+    uint32_t *list = list_ptrs[m];
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        if (shape_in_rects(rects, x, y)) continue;
+        const int r = row[3 * x], g = row[3 * x + 1], b = row[3 * x + 2];
+        if ((r | g | b) == 0) continue;
+        const int xs = W - 1 - x;
+        const bool keep = !roi_bits || ((roi_bits[(size_t) y * bpitch + (x >> 5)] >> (x & 31)) & 1u);
+        const bool keep_m = !roi_bits || ((roi_bits[(size_t) y * bpitch + (xs >> 5)] >> (xs & 31)) & 1u);
+        if (!keep && !keep_m) continue;
+        const uint32_t qm = gray_of(r, g, b) > 2 ? 1u : 0u;
+        const uint32_t e = (uint32_t) x | ((uint32_t) y << 11) | ((uint32_t) (slice_of(slice_tab, r, g, b) - 1) << 21) | (qm << 29) |
+                           ((uint32_t) keep << 30) | ((uint32_t) keep_m << 31);
+        const unsigned long long slot = atomicAdd(&counters[4 * m + 3], 1ull);
+        list[slot] = e;
+    }
+}
+
+// the label-cleared ROI as a bitmap: bit set where the ROI pixel is not black (ColorTransformation.mask(pt, p, m) :134-143)
+__global__ void __launch_bounds__(256) shape_roi_bits_kernel(const uint8_t *__restrict__ roi, int W, int H, int bpitch, RectSet rects, uint32_t *__restrict__ bits)
+{
+    const int y = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    for (int x0 = (threadIdx.x >> 5) * 32; x0 < bpitch * 32; x0 += (int) blockDim.x) {
+        const int x = x0 + lane;
+        bool keep = false;
+        if (x < W && !shape_in_rects(rects, x, y)) keep = (roi[((size_t) y * W + x) * 3] | roi[((size_t) y * W + x) * 3 + 1] | roi[((size_t) y * W + x) * 3 + 2]) != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) bits[(size_t) y * bpitch + (x0 >> 5)] = bal;
     }
 }
 
@@ -308,19 +641,16 @@ struct ShapeMaskDesc {
     int pad;
 };
 
+// pair_slot = index of the pair's target inside the window's planes
 __global__ void __launch_bounds__(256) shape_pair_kernel(const ShapeMaskDesc *__restrict__ masks, const int32_t *__restrict__ pair_mask,
-                                                         const int64_t *__restrict__ pair_target, const uint8_t *__restrict__ has_variants,
+                                                         const int32_t *__restrict__ pair_slot,
                                                          const uint16_t *__restrict__ zslice, const uint16_t *__restrict__ grad,
                                                          const uint32_t *__restrict__ tsig, int W, int H, int bpitch, int mirror,
                                                          long long *__restrict__ gap_out, long long *__restrict__ he_out, uint8_t *__restrict__ mir_out)
 {
     __shared__ long long s_red[4][8];
     const int64_t pr = blockIdx.x;
-    const int64_t t = pair_target[pr];
-    if (has_variants && !has_variants[t]) {                      // missing gradient / zgap supplier: (-1, -1, not mirrored), Shape2DMatch...:155-158
-        if (threadIdx.x == 0) { gap_out[pr] = -1; he_out[pr] = -1; mir_out[pr] = 0; }
-        return;
-    }
+    const int64_t t = pair_slot[pr];
     const ShapeMaskDesc md = masks[pair_mask[pr]];
     const uint16_t *zs = zslice + (size_t) t * W * H;
     const uint16_t *gr = grad + (size_t) t * W * H;
@@ -376,6 +706,52 @@ __global__ void __launch_bounds__(256) shape_pair_kernel(const ShapeMaskDesc *__
     }
 }
 
+// per-device constants of the shape path: the colour LUT in constant memory and the slice table
+static cds_status ensure_shape_tables(cds_ctx *ctx, DevState &ds)
+{
+    if (ds.d_slice_tab) return CDS_OK;
+    cds_status st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+    if (st == CDS_OK) st = ctx->check(cudaMemcpyToSymbol(c_shape_lut, kColorDepthLut, sizeof(kColorDepthLut)), "lut upload");
+    uint16_t *tab = nullptr;
+    if (st == CDS_OK) st = ctx->check(cudaMalloc(&tab, kSliceTabEntries * sizeof(uint16_t)), "cudaMalloc(slice table)");
+    if (st == CDS_OK) {
+        build_slice_table_kernel<<<(kSliceTabEntries + 255) / 256, 256, 0, ds.stream>>>(tab);
+        st = ctx->check(cudaGetLastError(), "build_slice_table_kernel");
+    }
+    if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "slice table");
+    if (st != CDS_OK) { if (tab) cudaFree(tab); return st; }
+    ds.d_slice_tab = tab;
+    return CDS_OK;
+}
+
+void shape_release_dev(DevState &ds)
+{
+    if (ds.d_slice_tab) cudaFree(ds.d_slice_tab);
+    ds.d_slice_tab = nullptr;
+    for (cudaEvent_t e : ds.shape_timing) cudaEventDestroy(e);
+    ds.shape_timing.clear();
+}
+
+// launches the fused derive kernel for n images; false when the disc is outside its envelope
+template <bool OUT_RGB>
+static bool launch_target_derive(const uint8_t *target, int64_t n, int W, int H, const RectSet &rects, int threshold, const DiscSpec &disc,
+                                 const uint16_t *slice_tab, uint16_t *zslice, uint32_t *tsig, int bpitch, uint8_t *rgb_out, cudaStream_t s)
+{
+    if (disc.k > kZgHalo || disc.k < 0) return false;
+    const DiscRings rings = make_rings(disc);
+    const size_t smem = (size_t) 3 * (kZgTH + 2 * disc.k) * kZgWords * sizeof(uint32_t);
+    auto kern = shape_target_derive_kernel<OUT_RGB>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    for (int64_t i0 = 0; i0 < n; i0 += 32768) {
+        const int64_t cnt = std::min<int64_t>(32768, n - i0);
+        dim3 grid((W + kZgStrip - 1) / kZgStrip, (H + kZgTH - 1) / kZgTH, (unsigned) cnt);
+        kern<<<grid, 256, smem, s>>>(target + (size_t) i0 * W * H * 3, W, H, rects, threshold, rings, slice_tab,
+                                     zslice ? zslice + (size_t) i0 * W * H : nullptr, tsig ? tsig + (size_t) i0 * H * bpitch : nullptr, bpitch,
+                                     rgb_out ? rgb_out + (size_t) i0 * W * H * 3 : nullptr);
+    }
+    return true;
+}
+
 }  // namespace cds
 
 // ------------------------------------------------------------------------------------------------------------------ C ABI
@@ -384,11 +760,17 @@ struct cds_shape_maskset {
     int W = 0, H = 0, bpitch = 0;
     int query_threshold = 0, mirror = 0;
     RectSet rects{};
-    uint8_t *d_roi = nullptr;                        // label-cleared ROI on device 0, or nullptr
-    struct Mask { uint32_t *gap_list = nullptr; uint32_t *he_n = nullptr; uint32_t *he_m = nullptr; int n_gap = 0; };
-    std::vector<Mask> masks;
-    ShapeMaskDesc *d_descs = nullptr;
-    bool descs_dirty = true;
+    uint32_t *d_roi_bits = nullptr;                  // label-cleared ROI bitmap on device 0 (where masks are prepared), or nullptr
+    int n_masks = 0;
+    // per device: the masks' descriptors (device-local pointers), the blocks that hold their lists and bitmaps
+    struct Dev {
+        std::vector<ShapeMaskDesc> h_descs;
+        std::vector<void *> blocks;
+        ShapeMaskDesc *d_descs = nullptr;
+        size_t d_descs_cap = 0;
+        bool dirty = true;
+    };
+    std::vector<Dev> dev;
 };
 
 #define SH_TRY(expr) do { cds_status _s = (expr); if (_s != CDS_OK) return _s; } while (0)
@@ -402,40 +784,62 @@ static RectSet to_rectset(const cds_rect *rects, int n)
     return r;
 }
 
+namespace {
+// frees pooled blocks on scope exit, after the device's streams have drained
+struct PoolGuard {
+    DevState *ds;
+    std::vector<void *> ptrs;
+    explicit PoolGuard(DevState *d) : ds(d) {}
+    cudaError_t alloc(void **p, size_t bytes) { cudaError_t e = ds->pool.alloc(p, bytes); if (e == cudaSuccess) ptrs.push_back(*p); return e; }
+    ~PoolGuard()
+    {
+        if (ptrs.empty()) return;
+        cudaSetDevice(ds->dev);
+        cudaStreamSynchronize(ds->copy_stream);
+        cudaStreamSynchronize(ds->stream);
+        for (void *p : ptrs) ds->pool.free(p);
+    }
+};
+}  // namespace
+
 extern "C" cds_status cds_shape_maskset_create(cds_ctx *ctx, int32_t width, int32_t height, int32_t query_threshold, int32_t border,
                                                int32_t mirror, const cds_rect *rects, int32_t n_rects, const uint8_t *roi_rgb,
                                                cds_shape_maskset **out)
 {
-    if (!ctx || !out) { set_tls_error("cds_shape_maskset_create: NULL argument"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    *out = nullptr;
-    if (width <= 0 || height <= 0 || n_rects < 0 || n_rects > CDS_MAX_RECTS || (n_rects > 0 && !rects))
-        return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_maskset_create: bad arguments");
-    if (width > 2048 || height > 1024) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_shape_maskset_create: images larger than 2048 x 1024 are not supported");
-    if (border != 0) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_shape_maskset_create: only border = 0 is supported");
-    auto sms = new cds_shape_maskset();
-    sms->ctx = ctx; sms->W = width; sms->H = height; sms->bpitch = occupancy_valid_pitch(width);   // row-layout bitmaps: one bit per pixel, 32-pixel words
-    sms->query_threshold = query_threshold; sms->mirror = mirror ? 1 : 0;
-    sms->rects = to_rectset(rects, n_rects);
-    DevState &d0 = ctx->devs[0];
-    cds_status st = ctx->check(cudaSetDevice(d0.dev), "cudaSetDevice");
-    if (st == CDS_OK) st = ctx->check(ensure_shape_lut(d0.dev), "lut upload");
-    if (st == CDS_OK && roi_rgb) {
-        const size_t bytes = (size_t) width * height * 3;
-        uint8_t *tmp = nullptr;
-        st = ctx->check(cudaMalloc(&sms->d_roi, bytes), "cudaMalloc(roi)");
-        if (st == CDS_OK) st = ctx->check(cudaMalloc(&tmp, bytes), "cudaMalloc(roi tmp)");
-        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(tmp, roi_rgb, bytes, cudaMemcpyHostToDevice, d0.stream), "roi H2D");
-        if (st == CDS_OK) {
-            clear_and_mask_kernel<<<148 * 4, 256, 0, d0.stream>>>(tmp, sms->d_roi, 1, width, height, sms->rects, 0, 0);   // ROI is label-cleared too (:97-101)
-            st = ctx->check(cudaGetLastError(), "clear_and_mask_kernel");
+    return cds::abi_guard("cds_shape_maskset_create", [&]() -> cds_status {
+        if (!ctx || !out) { set_tls_error("cds_shape_maskset_create: NULL argument"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        *out = nullptr;
+        if (width <= 0 || height <= 0 || n_rects < 0 || n_rects > CDS_MAX_RECTS || (n_rects > 0 && !rects))
+            return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_maskset_create: bad arguments");
+        if (width > 2048 || height > 1024) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_shape_maskset_create: images larger than 2048 x 1024 are not supported");
+        if (border != 0) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_shape_maskset_create: only border = 0 is supported");
+        auto sms = new cds_shape_maskset();
+        sms->ctx = ctx; sms->W = width; sms->H = height; sms->bpitch = occupancy_valid_pitch(width);   // row-layout bitmaps: one bit per pixel, 32-pixel words
+        sms->query_threshold = query_threshold; sms->mirror = mirror ? 1 : 0;
+        sms->rects = to_rectset(rects, n_rects);
+        sms->dev.resize(ctx->devs.size());
+        DevState &d0 = ctx->devs[0];
+        cds_status st = CDS_OK;
+        for (DevState &ds : ctx->devs) if (st == CDS_OK) st = ensure_shape_tables(ctx, ds);
+        if (st == CDS_OK) st = ctx->check(cudaSetDevice(d0.dev), "cudaSetDevice");
+        if (st == CDS_OK && roi_rgb) {
+            const size_t bytes = (size_t) width * height * 3;
+            uint8_t *tmp = nullptr;
+            st = ctx->check(cudaMalloc(&sms->d_roi_bits, (size_t) height * sms->bpitch * sizeof(uint32_t)), "cudaMalloc(roi)");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&tmp, bytes), "cudaMalloc(roi tmp)");
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(tmp, roi_rgb, bytes, cudaMemcpyHostToDevice, d0.stream), "roi H2D");
+            if (st == CDS_OK) {
+                shape_roi_bits_kernel<<<height, 256, 0, d0.stream>>>(tmp, width, height, sms->bpitch, sms->rects, sms->d_roi_bits);   // the ROI is label-cleared too (:97-101)
+                st = ctx->check(cudaGetLastError(), "shape_roi_bits_kernel");
+            }
+            if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "roi");
+            if (tmp) cudaFree(tmp);
         }
-        if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "roi");
-        if (tmp) cudaFree(tmp);
-    }
-    if (st != CDS_OK) { cds_shape_maskset_destroy(sms); return st; }
-    *out = sms;
-    return CDS_OK;
+        if (st != CDS_OK) { cds_shape_maskset_destroy(sms); return st; }
+        *out = sms;
+        return CDS_OK;
+    });
 }
 
 extern "C" void cds_shape_maskset_destroy(cds_shape_maskset *sms)
@@ -443,118 +847,202 @@ extern "C" void cds_shape_maskset_destroy(cds_shape_maskset *sms)
     if (!sms) return;
     cds_ctx *ctx = sms->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    cudaSetDevice(ctx->devs[0].dev);
-    cudaStreamSynchronize(ctx->devs[0].stream);
-    DevPool &pool = ctx->devs[0].pool;
-    for (auto &m : sms->masks) {
-        pool.free(m.gap_list);
-        pool.free(m.he_n);
-        pool.free(m.he_m);
+    for (size_t d = 0; d < sms->dev.size(); d++) {
+        DevState &ds = ctx->devs[d];
+        cudaSetDevice(ds.dev);
+        cudaStreamSynchronize(ds.copy_stream);
+        cudaStreamSynchronize(ds.stream);
+        for (void *p : sms->dev[d].blocks) ds.pool.free(p);
+        if (sms->dev[d].d_descs) cudaFree(sms->dev[d].d_descs);
     }
-    if (sms->d_roi) cudaFree(sms->d_roi);
-    if (sms->d_descs) cudaFree(sms->d_descs);
+    if (sms->d_roi_bits) { cudaSetDevice(ctx->devs[0].dev); cudaFree(sms->d_roi_bits); }
     cudaGetLastError();
     delete sms;
 }
 
-extern "C" int32_t cds_shape_maskset_size(const cds_shape_maskset *sms) { return sms ? (int32_t) sms->masks.size() : 0; }
+extern "C" int32_t cds_shape_maskset_size(const cds_shape_maskset *sms) { return sms ? sms->n_masks : 0; }
 
+// Masks are prepared on device 0 in batches: upload, bitmaps + counts (one read-back: the gap lists' lengths size the batch's block),
+// the five binary dilations, HE bitmaps, gap lists; the finished block is then copied to the other devices.
 extern "C" cds_status cds_shape_maskset_add_rgb(cds_shape_maskset *sms, const uint8_t *rgb, int32_t n, int64_t *qm_size_out, int64_t *he_size_out)
 {
-    if (!sms) { set_tls_error("cds_shape_maskset_add_rgb: NULL mask set"); return CDS_ERR_BAD_ARG; }
-    cds_ctx *ctx = sms->ctx;
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (n < 0 || (n > 0 && !rgb)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_maskset_add_rgb: bad arguments");
-    DevState &d0 = ctx->devs[0];
-    SH_CUDA(ctx, cudaSetDevice(d0.dev));
-    const int W = sms->W, H = sms->H;
-    const size_t px = (size_t) W * H, bytes = px * 3;
-    const size_t bm_words = (size_t) H * sms->bpitch;
-    uint8_t *d_raw = nullptr, *d_q = nullptr, *d_m60 = nullptr, *d_m20 = nullptr;
-    uint32_t *d_list = nullptr;
-    unsigned long long *d_cnt = nullptr;
-    DevPool &pool = d0.pool;
-    cds_status st = ctx->check(pool.alloc((void **) &d_raw, bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_q, bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_m60, bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_m20, bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_list, px * sizeof(uint32_t)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_cnt, 4 * sizeof(unsigned long long)), "cudaMalloc");
-    for (int i = 0; i < n && st == CDS_OK; i++) {
-        cds_shape_maskset::Mask m;
-        st = ctx->check(pool.alloc((void **) &m.he_n, bm_words * sizeof(uint32_t)), "cudaMalloc(he bitmap)");
-        if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &m.he_m, bm_words * sizeof(uint32_t)), "cudaMalloc(he bitmap)");
-        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_raw, rgb + (size_t) i * bytes, bytes, cudaMemcpyHostToDevice, d0.stream), "mask H2D");
-        if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), d0.stream), "memset");
-        if (st == CDS_OK) {
-            clear_and_mask_kernel<<<148 * 4, 256, 0, d0.stream>>>(d_raw, d_q, 1, W, H, sms->rects, 0, 0);
-            launch_max_filter(d_q, d_m60, 1, W, H, 3, 60, d0.stream);
-            launch_max_filter(d_q, d_m20, 1, W, H, 3, 20, d0.stream);
-            mask_planes_kernel<<<H, 256, 0, d0.stream>>>(d_q, d_m60, d_m20, sms->d_roi, W, H, sms->bpitch, m.he_n, m.he_m, d_list, d_cnt);
+    return cds::abi_guard("cds_shape_maskset_add_rgb", [&]() -> cds_status {
+        if (!sms) { set_tls_error("cds_shape_maskset_add_rgb: NULL mask set"); return CDS_ERR_BAD_ARG; }
+        cds_ctx *ctx = sms->ctx;
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || (n > 0 && !rgb)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_maskset_add_rgb: bad arguments");
+        if (n == 0) return CDS_OK;
+        const int D = (int) ctx->devs.size();
+        DevState &d0 = ctx->devs[0];
+        SH_CUDA(ctx, cudaSetDevice(d0.dev));
+        const int W = sms->W, H = sms->H, bpitch = sms->bpitch;
+        const size_t px = (size_t) W * H, bytes = px * 3;
+        const size_t bm_words = (size_t) H * bpitch;
+        const int batch = std::min<int>(n, 64);
+        const DiscRings rings20 = make_rings(make_disc(20)), rings60 = make_rings(make_disc(60));
+
+        PoolGuard g0(&d0);
+        uint8_t *d_raw = nullptr, *d_rowany = nullptr;
+        uint32_t *d_bits = nullptr, *d_dil = nullptr;
+        unsigned long long *d_cnt = nullptr;
+        uint32_t **d_ptrs = nullptr;                        // [3][batch]: list, he_n, he_m pointers of the batch's masks
+        SH_CUDA(ctx, g0.alloc((void **) &d_raw, (size_t) batch * bytes));
+        SH_CUDA(ctx, g0.alloc((void **) &d_bits, (size_t) kMaskBitmaps * batch * bm_words * sizeof(uint32_t)));
+        SH_CUDA(ctx, g0.alloc((void **) &d_dil, (size_t) kMaskBitmaps * batch * bm_words * sizeof(uint32_t)));
+        SH_CUDA(ctx, g0.alloc((void **) &d_rowany, (size_t) batch * H));
+        SH_CUDA(ctx, g0.alloc((void **) &d_cnt, (size_t) batch * 4 * sizeof(unsigned long long)));
+        SH_CUDA(ctx, g0.alloc((void **) &d_ptrs, (size_t) 3 * batch * sizeof(uint32_t *)));
+        std::vector<unsigned long long> cnt((size_t) batch * 4);
+        std::vector<uint32_t *> h_ptrs((size_t) 3 * batch);
+
+        for (int i0 = 0; i0 < n; i0 += batch) {
+            const int nb = std::min(batch, n - i0);
+            SH_CUDA(ctx, cudaSetDevice(d0.dev));
+            SH_CUDA(ctx, cudaMemcpyAsync(d_raw, rgb + (size_t) i0 * bytes, (size_t) nb * bytes, cudaMemcpyHostToDevice, d0.stream));
+            SH_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, (size_t) nb * 4 * sizeof(unsigned long long), d0.stream));
+            shape_mask_bits_kernel<<<dim3(H, nb), 256, 0, d0.stream>>>(d_raw, nb, W, H, bpitch, sms->rects, sms->d_roi_bits, d_bits, d_rowany, d_cnt);
+            SH_CUDA(ctx, cudaGetLastError());
+            SH_CUDA(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t) nb * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d0.stream));
+            shape_mask_dilate_kernel<<<dim3((H + 7) / 8, nb * kMaskBitmaps), 256, 0, d0.stream>>>(d_bits, d_rowany, nb, H, bpitch, rings20, rings60, d_dil);
+            SH_CUDA(ctx, cudaGetLastError());
+            SH_CUDA(ctx, cudaStreamSynchronize(d0.stream));         // the list lengths (the dilation above is already running)
+            // one block per batch and device: [he_n | he_m] per mask, then the gap lists
+            size_t list_words = 0;
+            for (int i = 0; i < nb; i++) list_words += (size_t) ((cnt[4 * i + 2] + 3) / 4 * 4);
+            const size_t block_words = (size_t) nb * 2 * bm_words + std::max<size_t>(list_words, 4);
+            std::vector<uint32_t *> block(D, nullptr);
+            for (int d = 0; d < D; d++) {
+                SH_CUDA(ctx, cudaSetDevice(ctx->devs[d].dev));
+                void *p = nullptr;
+                SH_CUDA(ctx, ctx->devs[d].pool.alloc(&p, block_words * sizeof(uint32_t)));
+                sms->dev[d].blocks.push_back(p);
+                block[d] = (uint32_t *) p;
+            }
+            SH_CUDA(ctx, cudaSetDevice(d0.dev));
+            size_t lo = (size_t) nb * 2 * bm_words;
+            std::vector<size_t> list_off(nb);
+            for (int i = 0; i < nb; i++) {
+                list_off[i] = lo;
+                h_ptrs[i] = block[0] + lo;
+                h_ptrs[batch + i] = block[0] + (size_t) i * 2 * bm_words;
+                h_ptrs[2 * batch + i] = block[0] + (size_t) i * 2 * bm_words + bm_words;
+                lo += (size_t) ((cnt[4 * i + 2] + 3) / 4 * 4);
+            }
+            SH_CUDA(ctx, cudaMemcpyAsync(d_ptrs, h_ptrs.data(), (size_t) 3 * batch * sizeof(uint32_t *), cudaMemcpyHostToDevice, d0.stream));
+            shape_mask_finish_kernel<<<dim3(H, nb), 64, 0, d0.stream>>>(d_dil, nb, W, H, bpitch, sms->d_roi_bits, d_ptrs + batch, d_ptrs + 2 * batch, d_cnt);
+            shape_mask_list_kernel<<<dim3(H, nb), 256, 0, d0.stream>>>(d_raw, W, H, bpitch, sms->rects, sms->d_roi_bits, d0.d_slice_tab, d_ptrs, d_cnt);
+            SH_CUDA(ctx, cudaGetLastError());
             ctx->stats.kernel_launches += 4;
-            st = ctx->check(cudaGetLastError(), "shape mask kernels");
+            SH_CUDA(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t) nb * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d0.stream));
+            for (int d = 1; d < D; d++)
+                SH_CUDA(ctx, cudaMemcpyPeerAsync(block[d], ctx->devs[d].dev, block[0], d0.dev, block_words * sizeof(uint32_t), d0.stream));
+            SH_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+            for (int i = 0; i < nb; i++) {
+                if (qm_size_out) qm_size_out[i0 + i] = (int64_t) cnt[4 * i + 0];
+                if (he_size_out) he_size_out[i0 + i] = (int64_t) cnt[4 * i + 1];
+                for (int d = 0; d < D; d++) {
+                    ShapeMaskDesc md;
+                    md.gap_list = block[d] + list_off[i];
+                    md.he_n = block[d] + (size_t) i * 2 * bm_words;
+                    md.he_m = md.he_n + bm_words;
+                    md.n_gap = (int) cnt[4 * i + 2];
+                    md.pad = 0;
+                    sms->dev[d].h_descs.push_back(md);
+                    sms->dev[d].dirty = true;
+                }
+            }
+            sms->n_masks += nb;
         }
-        unsigned long long cnt[4] = {0, 0, 0, 0};
-        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, d0.stream), "counters D2H");
-        if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "shape mask");
-        if (st == CDS_OK) {
-            m.n_gap = (int) cnt[2];
-            st = ctx->check(pool.alloc((void **) &m.gap_list, std::max<size_t>(1, (size_t) m.n_gap) * sizeof(uint32_t)), "cudaMalloc(gap list)");
-            if (st == CDS_OK && m.n_gap) st = ctx->check(cudaMemcpyAsync(m.gap_list, d_list, (size_t) m.n_gap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d0.stream), "gap list copy");
-            if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "gap list");
-        }
-        if (st != CDS_OK) {
-            pool.free(m.he_n);
-            pool.free(m.he_m);
-            pool.free(m.gap_list);
-            break;
-        }
-        if (qm_size_out) qm_size_out[i] = (int64_t) cnt[0];
-        if (he_size_out) he_size_out[i] = (int64_t) cnt[1];
-        sms->masks.push_back(m);
-        sms->descs_dirty = true;
-    }
-    cudaStreamSynchronize(d0.stream);
-    pool.free(d_raw);
-    pool.free(d_q);
-    pool.free(d_m60);
-    pool.free(d_m20);
-    pool.free(d_list);
-    pool.free(d_cnt);
-    return st;
+        return CDS_OK;
+    });
 }
 
 extern "C" cds_status cds_make_zgap(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t width, int32_t height, int32_t threshold,
                                     double radius, const cds_rect *rects, int32_t n_rects, uint8_t *zgap_out)
 {
-    if (!ctx) { set_tls_error("cds_make_zgap: NULL ctx"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (n < 0 || (n > 0 && (!rgb || !zgap_out)) || width <= 0 || height <= 0 || n_rects < 0 || n_rects > CDS_MAX_RECTS || (n_rects > 0 && !rects))
-        return ctx->fail(CDS_ERR_BAD_ARG, "cds_make_zgap: bad arguments");
-    if (make_disc(radius).k > 60) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_make_zgap: radius > 60 is not supported");
-    DevState &d0 = ctx->devs[0];
-    SH_CUDA(ctx, cudaSetDevice(d0.dev));
-    const RectSet rs = to_rectset(rects, n_rects);
-    const size_t bytes = (size_t) width * height * 3;
-    const int64_t chunk = 32;
-    uint8_t *d_a = nullptr, *d_b = nullptr;
-    cds_status st = ctx->check(cudaMalloc(&d_a, chunk * bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_b, chunk * bytes), "cudaMalloc");
-    for (int64_t i0 = 0; i0 < n && st == CDS_OK; i0 += chunk) {
-        const int64_t cnt = std::min<int64_t>(chunk, n - i0);
-        st = ctx->check(cudaMemcpyAsync(d_a, rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.stream), "zgap H2D");
-        if (st != CDS_OK) break;
-        clear_and_mask_kernel<<<148 * 4, 256, 0, d0.stream>>>(d_a, d_b, cnt, width, height, rs, threshold, 1);
-        launch_max_filter(d_b, d_a, cnt, width, height, 3, radius, d0.stream);
-        ctx->stats.kernel_launches += 2;
-        st = ctx->check(cudaGetLastError(), "zgap kernels");
-        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(zgap_out + (size_t) i0 * bytes, d_a, (size_t) cnt * bytes, cudaMemcpyDeviceToHost, d0.stream), "zgap D2H");
-        if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "zgap");
-    }
-    if (d_a) cudaFree(d_a);
-    if (d_b) cudaFree(d_b);
-    return st;
+    return cds::abi_guard("cds_make_zgap", [&]() -> cds_status {
+        if (!ctx) { set_tls_error("cds_make_zgap: NULL ctx"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || (n > 0 && (!rgb || !zgap_out)) || width <= 0 || height <= 0 || n_rects < 0 || n_rects > CDS_MAX_RECTS || (n_rects > 0 && !rects))
+            return ctx->fail(CDS_ERR_BAD_ARG, "cds_make_zgap: bad arguments");
+        const DiscSpec disc = make_disc(radius);
+        if (disc.k > 60) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_make_zgap: radius > 60 is not supported");
+        DevState &d0 = ctx->devs[0];
+        SH_CUDA(ctx, cudaSetDevice(d0.dev));
+        const RectSet rs = to_rectset(rects, n_rects);
+        const size_t bytes = (size_t) width * height * 3;
+        const int64_t chunk = 32;
+        PoolGuard g0(&d0);
+        uint8_t *d_a = nullptr, *d_b = nullptr;
+        SH_CUDA(ctx, g0.alloc((void **) &d_a, chunk * bytes));
+        SH_CUDA(ctx, g0.alloc((void **) &d_b, chunk * bytes));
+        for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+            const int64_t cnt = std::min<int64_t>(chunk, n - i0);
+            SH_CUDA(ctx, cudaMemcpyAsync(d_a, rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.stream));
+            uint8_t *res = d_b;
+            if (launch_target_derive<true>(d_a, cnt, width, height, rs, threshold, disc, nullptr, nullptr, nullptr, 0, d_b, d0.stream)) {
+                ctx->stats.kernel_launches += 1;
+            } else {
+                clear_and_mask_kernel<<<148 * 4, 256, 0, d0.stream>>>(d_a, d_b, cnt, width, height, rs, threshold, 1);
+                launch_max_filter(d_b, d_a, cnt, width, height, 3, disc, d0.stream);
+                ctx->stats.kernel_launches += 2;
+                res = d_a;
+            }
+            SH_CUDA(ctx, cudaGetLastError());
+            SH_CUDA(ctx, cudaMemcpyAsync(zgap_out + (size_t) i0 * bytes, res, (size_t) cnt * bytes, cudaMemcpyDeviceToHost, d0.stream));
+            SH_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+        }
+        return CDS_OK;
+    });
 }
+
+extern "C" cds_status cds_debug_slice_numbers(cds_ctx *ctx, const uint8_t *rgb, int64_t n, uint16_t *slices_out)
+{
+    return cds::abi_guard("cds_debug_slice_numbers", [&]() -> cds_status {
+        if (!ctx) { set_tls_error("cds_debug_slice_numbers: NULL ctx"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || (n > 0 && (!rgb || !slices_out))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_debug_slice_numbers: bad arguments");
+        if (n == 0) return CDS_OK;
+        DevState &d0 = ctx->devs[0];
+        SH_TRY(ensure_shape_tables(ctx, d0));
+        SH_CUDA(ctx, cudaSetDevice(d0.dev));
+        PoolGuard g0(&d0);
+        uint8_t *d_rgb = nullptr;
+        uint16_t *d_out = nullptr;
+        SH_CUDA(ctx, g0.alloc((void **) &d_rgb, (size_t) n * 3));
+        SH_CUDA(ctx, g0.alloc((void **) &d_out, (size_t) n * sizeof(uint16_t)));
+        SH_CUDA(ctx, cudaMemcpyAsync(d_rgb, rgb, (size_t) n * 3, cudaMemcpyHostToDevice, d0.stream));
+        slice_numbers_kernel<<<148 * 8, 256, 0, d0.stream>>>(d_rgb, n, d0.d_slice_tab, d_out);
+        SH_CUDA(ctx, cudaGetLastError());
+        SH_CUDA(ctx, cudaMemcpyAsync(slices_out, d_out, (size_t) n * sizeof(uint16_t), cudaMemcpyDeviceToHost, d0.stream));
+        SH_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+        return CDS_OK;
+    });
+}
+
+namespace {
+
+constexpr int64_t kShapeWindow = 32;      // targets per window
+
+// What one device holds while it works through its windows.
+struct ShapeDevWork {
+    uint8_t *d_t[2] = {nullptr, nullptr}, *d_z[2] = {nullptr, nullptr};
+    uint16_t *d_grad[2] = {nullptr, nullptr};
+    uint16_t *d_zslice = nullptr;
+    uint32_t *d_tsig = nullptr;
+    uint8_t *d_comp = nullptr;
+    TiffStrip *d_strips = nullptr;
+    int32_t *d_pm = nullptr, *d_ps = nullptr;
+    long long *d_gap = nullptr, *d_he = nullptr;
+    uint8_t *d_mir = nullptr;
+    std::vector<int32_t> pm, ps;            // this device's pairs in window order
+    std::vector<int64_t> where;             // their positions in the caller's arrays
+    std::vector<long long> h_gap, h_he;
+    std::vector<uint8_t> h_mir;
+    int64_t windows = 0;
+};
+
+}  // namespace
 
 // Targets either as pixels (target_rgb) or as TIFF files stored back to back (blob + offsets, decoded on the device).
 static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *sms_c, const uint8_t *target_rgb,
@@ -570,154 +1058,222 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
     if (n_pairs < 0 || n_targets < 0) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs: negative count");
     if (n_pairs == 0) return CDS_OK;
     if (!pair_mask || !pair_target || !gap_out || !high_expr_out || !mirrored_out) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs: NULL pair arrays");
-    const int M = (int) sms->masks.size();
+    const int M = sms->n_masks;
+    // pairs per target (counting sort by target keeps the caller's order inside a target)
+    std::vector<int64_t> tstart((size_t) n_targets + 1, 0);
     bool any_scored = false;
     for (int64_t i = 0; i < n_pairs; i++) {
         if (pair_mask[i] < 0 || pair_mask[i] >= M || pair_target[i] < 0 || pair_target[i] >= n_targets)
             return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs: pair index out of range");
-        if (!has_variants || has_variants[pair_target[i]]) any_scored = true;
+        if (!has_variants || has_variants[pair_target[i]]) { any_scored = true; tstart[pair_target[i] + 1]++; }
+        else { gap_out[i] = -1; high_expr_out[i] = -1; mirrored_out[i] = 0; }      // missing gradient / zgap supplier: (-1, -1, not mirrored), Shape2DMatch...:155-158
     }
     // a missing gradient can only be expressed through has_variants; a NULL gradient array with scorable pairs is an error
     const bool from_files = blob != nullptr && offsets != nullptr;
     if (any_scored && ((!target_rgb && !from_files) || !gradient)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs: target / gradient images are NULL");
     ctx->stats = cds_search_stats{};
-    DevState &d0 = ctx->devs[0];
-    SH_CUDA(ctx, cudaSetDevice(d0.dev));
-    SH_CUDA(ctx, ensure_shape_lut(d0.dev));
+    if (!any_scored) return CDS_OK;
+    if (from_files)
+        for (int64_t i = 0; i <= n_targets; i++)
+            if (offsets[i] < 0 || (i > 0 && offsets[i] < offsets[i - 1])) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs_tiff: offsets must be non-decreasing");
+    for (int64_t t = 0; t < n_targets; t++) tstart[t + 1] += tstart[t];
+    const int64_t n_scored = tstart[n_targets];
+    std::vector<int64_t> order((size_t) n_scored);
+    {
+        std::vector<int64_t> cur(tstart.begin(), tstart.end() - 1);
+        for (int64_t i = 0; i < n_pairs; i++)
+            if (!has_variants || has_variants[pair_target[i]]) order[cur[pair_target[i]]++] = i;
+    }
+    std::vector<int64_t> active;                    // targets that are scored at all, ascending
+    for (int64_t t = 0; t < n_targets; t++) if (tstart[t + 1] > tstart[t]) active.push_back(t);
+
     const int W = sms->W, H = sms->H, bpitch = sms->bpitch;
     const size_t px = (size_t) W * H, bytes = px * 3;
     const size_t bm_words = (size_t) H * bpitch;
+    const int D = (int) ctx->devs.size();
+    const int64_t win = kShapeWindow;
+    const int64_t n_windows = ((int64_t) active.size() + win - 1) / win;
+    const int used = (int) std::min<int64_t>(D, n_windows);
+    const DiscSpec disc10 = make_disc(10);
 
-    if (sms->descs_dirty) {
-        std::vector<ShapeMaskDesc> h(std::max(M, 1));
-        for (int i = 0; i < M; i++) {
-            h[i].gap_list = sms->masks[i].gap_list; h[i].he_n = sms->masks[i].he_n; h[i].he_m = sms->masks[i].he_m;
-            h[i].n_gap = sms->masks[i].n_gap; h[i].pad = 0;
-        }
-        if (sms->d_descs) { cudaFree(sms->d_descs); sms->d_descs = nullptr; }
-        SH_CUDA(ctx, cudaMalloc(&sms->d_descs, h.size() * sizeof(ShapeMaskDesc)));
-        SH_CUDA(ctx, cudaMemcpy(sms->d_descs, h.data(), h.size() * sizeof(ShapeMaskDesc), cudaMemcpyHostToDevice));
-        sms->descs_dirty = false;
+    // window w -> device w % used; per device the pairs of its windows in window order
+    std::vector<ShapeDevWork> work(used);
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> win_pairs(used);      // per device and window: [first, end) into its pair arrays
+    for (int64_t w = 0; w < n_windows; w++) {
+        ShapeDevWork &wk = work[w % used];
+        const int64_t a0 = w * win, a1 = std::min<int64_t>((int64_t) active.size(), a0 + win);
+        const int64_t first = (int64_t) wk.pm.size();
+        for (int64_t a = a0; a < a1; a++)
+            for (int64_t q = tstart[active[a]]; q < tstart[active[a] + 1]; q++) {
+                wk.pm.push_back(pair_mask[order[q]]);
+                wk.ps.push_back((int32_t) (a - a0));
+                wk.where.push_back(order[q]);
+            }
+        win_pairs[w % used].push_back({first, (int64_t) wk.pm.size()});
+        wk.windows++;
     }
 
-    uint16_t *d_zslice = nullptr, *d_grad = nullptr;
-    uint32_t *d_tsig = nullptr;
-    uint8_t *d_t = nullptr, *d_z = nullptr, *d_tmp = nullptr, *d_has = nullptr, *d_comp = nullptr;
-    TiffStrip *d_strips = nullptr;
+    std::vector<std::unique_ptr<PoolGuard>> guards;
     size_t comp_cap = 0, strips_cap = 0;
+    if (from_files) ingest_bounds(offsets, n_targets, win, W, H, comp_cap, strips_cap);
+    for (int d = 0; d < used; d++) {
+        DevState &ds = ctx->devs[d];
+        ShapeDevWork &wk = work[d];
+        SH_CUDA(ctx, cudaSetDevice(ds.dev));
+        SH_TRY(ensure_shape_tables(ctx, ds));
+        cds_shape_maskset::Dev &sd = sms->dev[d];
+        if (sd.dirty) {
+            if (sd.d_descs_cap < sd.h_descs.size()) {
+                SH_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+                if (sd.d_descs) { cudaFree(sd.d_descs); sd.d_descs = nullptr; sd.d_descs_cap = 0; }
+                const size_t cap = std::max<size_t>(sd.h_descs.size() * 2, 64);
+                SH_CUDA(ctx, cudaMalloc(&sd.d_descs, cap * sizeof(ShapeMaskDesc)));
+                sd.d_descs_cap = cap;
+            }
+            SH_CUDA(ctx, cudaMemcpy(sd.d_descs, sd.h_descs.data(), sd.h_descs.size() * sizeof(ShapeMaskDesc), cudaMemcpyHostToDevice));
+            sd.dirty = false;
+        }
+        guards.emplace_back(new PoolGuard(&ds));
+        PoolGuard &g = *guards.back();
+        // buffers come from the device's caching pool: consecutive calls (one per mask batch in gradientScores) reuse them
+        for (int s = 0; s < 2; s++) {
+            SH_CUDA(ctx, g.alloc((void **) &wk.d_t[s], win * bytes));
+            SH_CUDA(ctx, g.alloc((void **) &wk.d_grad[s], win * px * sizeof(uint16_t)));
+            if (zgap_rgb) SH_CUDA(ctx, g.alloc((void **) &wk.d_z[s], win * bytes));
+        }
+        SH_CUDA(ctx, g.alloc((void **) &wk.d_zslice, win * px * sizeof(uint16_t)));
+        SH_CUDA(ctx, g.alloc((void **) &wk.d_tsig, win * bm_words * sizeof(uint32_t)));
+        if (from_files) {
+            SH_CUDA(ctx, g.alloc((void **) &wk.d_comp, comp_cap));
+            SH_CUDA(ctx, g.alloc((void **) &wk.d_strips, strips_cap * sizeof(TiffStrip)));
+        }
+        const size_t np = wk.pm.size();
+        SH_CUDA(ctx, g.alloc((void **) &wk.d_pm, np * sizeof(int32_t)));
+        SH_CUDA(ctx, g.alloc((void **) &wk.d_ps, np * sizeof(int32_t)));
+        SH_CUDA(ctx, g.alloc((void **) &wk.d_gap, np * sizeof(long long)));
+        SH_CUDA(ctx, g.alloc((void **) &wk.d_he, np * sizeof(long long)));
+        SH_CUDA(ctx, g.alloc((void **) &wk.d_mir, np));
+        wk.h_gap.resize(np); wk.h_he.resize(np); wk.h_mir.resize(np);
+        SH_CUDA(ctx, cudaStreamSynchronize(ds.stream));     // pooled buffers may still be in use by an earlier call
+        SH_CUDA(ctx, cudaMemcpyAsync(wk.d_pm, wk.pm.data(), np * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream));
+        SH_CUDA(ctx, cudaMemcpyAsync(wk.d_ps, wk.ps.data(), np * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream));
+        while (ds.shape_timing.size() < (size_t) 2 * wk.windows) {
+            cudaEvent_t e;
+            SH_CUDA(ctx, cudaEventCreate(&e));
+            ds.shape_timing.push_back(e);
+        }
+    }
+
+    // Uploads (target, its gradient, its zgap image when given) of window j + 1 run on the copy stream while the main stream turns
+    // window j into slice / signal planes and scores its pairs.  Runs of consecutive targets travel as one copy.
     std::vector<TiffStrip> strips;
-    int32_t *d_pm = nullptr;
-    int64_t *d_pt = nullptr;
-    long long *d_gap = nullptr, *d_he = nullptr;
-    uint8_t *d_mir = nullptr;
-    const int64_t chunk = 32;
-    const int64_t nt = std::max<int64_t>(n_targets, 1);
-    // buffers come from the device's caching pool: consecutive calls (one per mask batch in gradientScores) reuse them
-    DevPool &pool = d0.pool;
-    cds_status st = ctx->check(pool.alloc((void **) &d_zslice, nt * px * sizeof(uint16_t)), "cudaMalloc(zslice)");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_grad, nt * px * sizeof(uint16_t)), "cudaMalloc(gradient)");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_tsig, nt * bm_words * sizeof(uint32_t)), "cudaMalloc(tsig)");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_t, 2 * chunk * bytes), "cudaMalloc");          // two upload halves
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_z, 2 * chunk * bytes), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_tmp, chunk * bytes), "cudaMalloc");
-    if (st == CDS_OK && from_files && n_targets > 0) {
-        for (int64_t i = 0; i <= n_targets; i++)
-            if (offsets[i] < 0 || (i > 0 && offsets[i] < offsets[i - 1])) st = ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs_tiff: offsets must be non-decreasing");
-        if (st == CDS_OK) {
-            ingest_bounds(offsets, n_targets, chunk, W, H, comp_cap, strips_cap);
-            st = ctx->check(pool.alloc((void **) &d_comp, comp_cap), "cudaMalloc(files)");
-            if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_strips, strips_cap * sizeof(TiffStrip)), "cudaMalloc(strips)");
-        }
-    }
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_pm, n_pairs * sizeof(int32_t)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_pt, n_pairs * sizeof(int64_t)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_gap, n_pairs * sizeof(long long)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_he, n_pairs * sizeof(long long)), "cudaMalloc");
-    if (st == CDS_OK) st = ctx->check(pool.alloc((void **) &d_mir, n_pairs), "cudaMalloc");
-    if (st == CDS_OK && has_variants) {
-        st = ctx->check(pool.alloc((void **) &d_has, nt), "cudaMalloc");
-        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_has, has_variants, n_targets, cudaMemcpyHostToDevice, d0.stream), "has_variants H2D");
-    }
-    if (st == CDS_OK && any_scored) {
-        // Uploads (target, its gradient, its zgap image when given) run on the copy stream one chunk ahead of the kernels that
-        // turn chunk i into slice / signal planes on the main stream.
-        if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "shape pairs");     // pooled buffers may still be in use by an earlier call
-        auto enqueue_upload = [&](int64_t i0) -> cds_status {
-            const int64_t cnt = std::min<int64_t>(chunk, n_targets - i0);
-            const int slot = (int) ((i0 / chunk) & 1);
-            cds_status s2 = CDS_OK;
-            if (i0 >= 2 * chunk) s2 = ctx->check(cudaStreamWaitEvent(d0.copy_stream, d0.up_free[slot], 0), "wait");
-            if (s2 == CDS_OK && from_files) {
-                // the files as stored, decoded on the copy stream (one buffer: uploads and decodes of consecutive chunks are ordered)
-                s2 = ingest_chunk(ctx, "cds_shape_score_pairs_tiff", blob, offsets, i0, cnt, W, H, d_comp, comp_cap, d_strips, strips_cap,
-                                  d_t + (size_t) slot * chunk * bytes, d0.copy_stream, strips);
-            } else if (s2 == CDS_OK) {
-                s2 = ctx->check(cudaMemcpyAsync(d_t + (size_t) slot * chunk * bytes, target_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.copy_stream), "target H2D");
+    auto upload_window = [&](int d, int64_t j) -> cds_status {
+        DevState &ds = ctx->devs[d];
+        ShapeDevWork &wk = work[d];
+        const int64_t w = j * used + d;
+        const int slot = (int) (j & 1);
+        const int64_t a0 = w * win, a1 = std::min<int64_t>((int64_t) active.size(), a0 + win);
+        SH_CUDA(ctx, cudaSetDevice(ds.dev));
+        if (j >= 2) SH_CUDA(ctx, cudaStreamWaitEvent(ds.copy_stream, ds.up_free[slot], 0));
+        for (int64_t a = a0; a < a1;) {
+            int64_t e = a + 1;
+            while (e < a1 && active[e] == active[e - 1] + 1) e++;
+            const int64_t t0 = active[a], cnt = e - a, s0 = a - a0;
+            if (from_files) {
+                SH_TRY(ingest_chunk(ctx, "cds_shape_score_pairs_tiff", blob, offsets, t0, cnt, W, H, wk.d_comp, comp_cap, wk.d_strips, strips_cap,
+                                    wk.d_t[slot] + (size_t) s0 * bytes, ds.copy_stream, strips));
+            } else {
+                SH_CUDA(ctx, cudaMemcpyAsync(wk.d_t[slot] + (size_t) s0 * bytes, target_rgb + (size_t) t0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, ds.copy_stream));
                 ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
             }
-            if (s2 == CDS_OK) s2 = ctx->check(cudaMemcpyAsync(d_grad + (size_t) i0 * px, gradient + (size_t) i0 * px, (size_t) cnt * px * sizeof(uint16_t), cudaMemcpyHostToDevice, d0.copy_stream), "gradient H2D");
+            SH_CUDA(ctx, cudaMemcpyAsync(wk.d_grad[slot] + (size_t) s0 * px, gradient + (size_t) t0 * px, (size_t) cnt * px * sizeof(uint16_t), cudaMemcpyHostToDevice, ds.copy_stream));
             ctx->stats.h2d_bytes += (int64_t) (cnt * px * sizeof(uint16_t));
-            if (s2 == CDS_OK && zgap_rgb) {
-                s2 = ctx->check(cudaMemcpyAsync(d_z + (size_t) slot * chunk * bytes, zgap_rgb + (size_t) i0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, d0.copy_stream), "zgap H2D");
+            if (zgap_rgb) {
+                SH_CUDA(ctx, cudaMemcpyAsync(wk.d_z[slot] + (size_t) s0 * bytes, zgap_rgb + (size_t) t0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, ds.copy_stream));
                 ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
             }
-            if (s2 == CDS_OK) s2 = ctx->check(cudaEventRecord(d0.up_done[slot], d0.copy_stream), "record");
-            return s2;
-        };
-        if (st == CDS_OK && n_targets > 0) st = enqueue_upload(0);
-        for (int64_t i0 = 0; i0 < n_targets && st == CDS_OK; i0 += chunk) {
-            const int64_t cnt = std::min<int64_t>(chunk, n_targets - i0);
-            const int slot = (int) ((i0 / chunk) & 1);
-            uint8_t *ct = d_t + (size_t) slot * chunk * bytes, *cz = d_z + (size_t) slot * chunk * bytes;
-            if (i0 + chunk < n_targets) st = enqueue_upload(i0 + chunk);
+            a = e;
+        }
+        SH_CUDA(ctx, cudaEventRecord(ds.up_done[slot], ds.copy_stream));
+        return CDS_OK;
+    };
+
+    cds_status st = CDS_OK;
+    for (int d = 0; d < used && st == CDS_OK; d++) st = upload_window(d, 0);
+    int64_t max_windows = 0;
+    for (int d = 0; d < used; d++) max_windows = std::max(max_windows, work[d].windows);
+    for (int64_t j = 0; j < max_windows && st == CDS_OK; j++) {
+        for (int d = 0; d < used && st == CDS_OK; d++) {
+            ShapeDevWork &wk = work[d];
+            if (j >= wk.windows) continue;
+            DevState &ds = ctx->devs[d];
+            if (j + 1 < wk.windows) st = upload_window(d, j + 1);
             if (st != CDS_OK) break;
-            st = ctx->check(cudaStreamWaitEvent(d0.stream, d0.up_done[slot], 0), "wait");
+            const int slot = (int) (j & 1);
+            const int64_t w = j * used + d;
+            const int64_t cnt = std::min<int64_t>((int64_t) active.size(), (w + 1) * win) - w * win;
+            st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+            if (st == CDS_OK) st = ctx->check(cudaStreamWaitEvent(ds.stream, ds.up_done[slot], 0), "wait");
             if (st != CDS_OK) break;
-            if (!zgap_rgb) {
-                // the zgap image the reference's tests derive: maxFilter(10)(mask(threshold)(clearLabels(target)))
-                clear_and_mask_kernel<<<148 * 4, 256, 0, d0.stream>>>(ct, d_tmp, cnt, W, H, sms->rects, sms->query_threshold, 1);
-                launch_max_filter(d_tmp, cz, cnt, W, H, 3, 10, d0.stream);
-                ctx->stats.kernel_launches += 2;
+            if (zgap_rgb) {
+                target_planes_kernel<<<dim3(H, (unsigned) cnt), 256, 0, ds.stream>>>(wk.d_t[slot], wk.d_z[slot], W, H, sms->rects, sms->query_threshold, bpitch,
+                                                                                    ds.d_slice_tab, wk.d_zslice, wk.d_tsig);
+            } else {
+                // the zgap image the reference's tests derive: maxFilter(10)(mask(threshold)(clearLabels(target))), never materialised
+                launch_target_derive<false>(wk.d_t[slot], cnt, W, H, sms->rects, sms->query_threshold, disc10, ds.d_slice_tab, wk.d_zslice, wk.d_tsig, bpitch,
+                                            nullptr, ds.stream);
             }
-            dim3 grid(H, (unsigned) cnt);
-            target_planes_kernel<<<grid, 256, 0, d0.stream>>>(ct, cz, W, H, sms->rects, sms->query_threshold, bpitch,
-                                                              d_zslice + (size_t) i0 * px, d_tsig + (size_t) i0 * bm_words);
             ctx->stats.kernel_launches++;
-            st = ctx->check(cudaGetLastError(), "target planes");
-            if (st == CDS_OK) st = ctx->check(cudaEventRecord(d0.up_free[slot], d0.stream), "record");
+            const auto pr = win_pairs[d][j];
+            cudaEventRecord(ds.shape_timing[2 * j], ds.stream);
+            if (pr.second > pr.first) {
+                shape_pair_kernel<<<(unsigned) (pr.second - pr.first), 256, 0, ds.stream>>>(sms->dev[d].d_descs, wk.d_pm + pr.first, wk.d_ps + pr.first,
+                                                                                            wk.d_zslice, wk.d_grad[slot], wk.d_tsig, W, H, bpitch, sms->mirror,
+                                                                                            wk.d_gap + pr.first, wk.d_he + pr.first, wk.d_mir + pr.first);
+                ctx->stats.kernel_launches++;
+                ctx->stats.match_kernel_launches++;
+            }
+            cudaEventRecord(ds.shape_timing[2 * j + 1], ds.stream);
+            st = ctx->check(cudaGetLastError(), "shape kernels");
+            if (st == CDS_OK) st = ctx->check(cudaEventRecord(ds.up_free[slot], ds.stream), "record");
         }
     }
-    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_pm, pair_mask, n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, d0.stream), "pairs H2D");
-    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(d_pt, pair_target, n_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, d0.stream), "pairs H2D");
-    if (st == CDS_OK) {
-        cudaEventRecord(d0.ev0, d0.stream);
-        for (int64_t p0 = 0; p0 < n_pairs; p0 += (1 << 30)) {
-            const int64_t cnt = std::min<int64_t>(1 << 30, n_pairs - p0);
-            shape_pair_kernel<<<(unsigned) cnt, 256, 0, d0.stream>>>(sms->d_descs, d_pm + p0, d_pt + p0, d_has, d_zslice, d_grad, d_tsig, W, H, bpitch,
-                                                                      sms->mirror, d_gap + p0, d_he + p0, d_mir + p0);
-            ctx->stats.kernel_launches++;
-            ctx->stats.match_kernel_launches++;
-        }
-        cudaEventRecord(d0.ev1, d0.stream);
-        st = ctx->check(cudaGetLastError(), "shape_pair_kernel");
+    for (int d = 0; d < used && st == CDS_OK; d++) {
+        DevState &ds = ctx->devs[d];
+        ShapeDevWork &wk = work[d];
+        const size_t np = wk.pm.size();
+        st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(wk.h_gap.data(), wk.d_gap, np * sizeof(long long), cudaMemcpyDeviceToHost, ds.stream), "gap D2H");
+        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(wk.h_he.data(), wk.d_he, np * sizeof(long long), cudaMemcpyDeviceToHost, ds.stream), "he D2H");
+        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(wk.h_mir.data(), wk.d_mir, np, cudaMemcpyDeviceToHost, ds.stream), "mirrored D2H");
     }
-    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(gap_out, d_gap, n_pairs * sizeof(long long), cudaMemcpyDeviceToHost, d0.stream), "gap D2H");
-    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(high_expr_out, d_he, n_pairs * sizeof(long long), cudaMemcpyDeviceToHost, d0.stream), "he D2H");
-    if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(mirrored_out, d_mir, n_pairs, cudaMemcpyDeviceToHost, d0.stream), "mirrored D2H");
-    if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "shape pairs");
+    double kernel_ms = 0;
+    for (int d = 0; d < used && st == CDS_OK; d++) {
+        DevState &ds = ctx->devs[d];
+        ShapeDevWork &wk = work[d];
+        st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
+        if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "shape pairs");
+        if (st != CDS_OK) break;
+        double dev_ms = 0;
+        for (int64_t j = 0; j < wk.windows; j++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ds.shape_timing[2 * j], ds.shape_timing[2 * j + 1]);
+            dev_ms += ms;
+        }
+        kernel_ms = std::max(kernel_ms, dev_ms);
+        for (size_t i = 0; i < wk.where.size(); i++) {
+            gap_out[wk.where[i]] = wk.h_gap[i];
+            high_expr_out[wk.where[i]] = wk.h_he[i];
+            mirrored_out[wk.where[i]] = wk.h_mir[i];
+        }
+    }
     if (st == CDS_OK) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, d0.ev0, d0.ev1);
-        ctx->stats.match_kernel_ms = ms;
-        ctx->stats.total_device_ms = ms;
+        ctx->stats.match_kernel_ms = kernel_ms;
+        ctx->stats.total_device_ms = kernel_ms;
         ctx->stats.comparisons = n_pairs;
-        ctx->stats.d2h_bytes = n_pairs * 17;
+        ctx->stats.d2h_bytes = n_scored * 17;
     }
-    if (st != CDS_OK) { cudaStreamSynchronize(d0.copy_stream); cudaStreamSynchronize(d0.stream); cudaGetLastError(); }
-    for (void *p : {(void *) d_zslice, (void *) d_grad, (void *) d_tsig, (void *) d_t, (void *) d_z, (void *) d_tmp, (void *) d_has, (void *) d_pm,
-                    (void *) d_pt, (void *) d_gap, (void *) d_he, (void *) d_mir, (void *) d_comp, (void *) d_strips})
-        pool.free(p);
-    return st;
+    return st;      // the guards drain both streams of every device before the pooled buffers go back
 }
 
 extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskset *sms, const uint8_t *target_rgb, const uint16_t *gradient,
@@ -725,8 +1281,10 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
                                             const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
                                             int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
 {
-    return shape_score_pairs_impl(ctx, sms, target_rgb, nullptr, nullptr, gradient, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
-                                  gap_out, high_expr_out, mirrored_out);
+    return cds::abi_guard("cds_shape_score_pairs", [&]() -> cds_status {
+        return shape_score_pairs_impl(ctx, sms, target_rgb, nullptr, nullptr, gradient, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
+                                      gap_out, high_expr_out, mirrored_out);
+    });
 }
 
 extern "C" cds_status cds_shape_score_pairs_tiff(cds_ctx *ctx, const cds_shape_maskset *sms, const uint8_t *blob, const int64_t *offsets,
@@ -734,7 +1292,9 @@ extern "C" cds_status cds_shape_score_pairs_tiff(cds_ctx *ctx, const cds_shape_m
                                                  const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
                                                  int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
 {
-    if (n_targets > 0 && (!blob || !offsets)) { set_tls_error("cds_shape_score_pairs_tiff: NULL files"); return CDS_ERR_BAD_ARG; }
-    return shape_score_pairs_impl(ctx, sms, nullptr, blob, offsets, gradient, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
-                                  gap_out, high_expr_out, mirrored_out);
+    return cds::abi_guard("cds_shape_score_pairs_tiff", [&]() -> cds_status {
+        if (n_targets > 0 && (!blob || !offsets)) { set_tls_error("cds_shape_score_pairs_tiff: NULL files"); return CDS_ERR_BAD_ARG; }
+        return shape_score_pairs_impl(ctx, sms, nullptr, blob, offsets, gradient, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
+                                      gap_out, high_expr_out, mirrored_out);
+    });
 }

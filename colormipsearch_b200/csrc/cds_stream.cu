@@ -479,8 +479,10 @@ extern "C" cds_status cds_search_stream_rgb(cds_ctx *ctx, const cds_maskset *ms,
                                             int32_t k, double pct_positive_pixels,
                                             int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
 {
-    if (!ctx || !ms) { set_tls_error("cds_search_stream_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
-    return stream_search_impl(ctx, ms, targets_rgb, n_targets, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr, nullptr);
+    return cds::abi_guard("cds_search_stream_rgb", [&]() -> cds_status {
+        if (!ctx || !ms) { set_tls_error("cds_search_stream_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
+        return stream_search_impl(ctx, ms, targets_rgb, n_targets, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr, nullptr);
+    });
 }
 
 extern "C" cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *targets_rgb, int64_t n_targets,
@@ -488,18 +490,22 @@ extern "C" cds_status cds_search_stream_matches_rgb(cds_ctx *ctx, const cds_mask
                                                     int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored,
                                                     int64_t *out_count)
 {
-    if (!ctx || !ms) { set_tls_error("cds_search_stream_matches_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
-    const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
-    return stream_search_impl(ctx, ms, targets_rgb, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, nullptr);
+    return cds::abi_guard("cds_search_stream_matches_rgb", [&]() -> cds_status {
+        if (!ctx || !ms) { set_tls_error("cds_search_stream_matches_rgb: NULL argument"); return CDS_ERR_BAD_ARG; }
+        const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
+        return stream_search_impl(ctx, ms, targets_rgb, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, nullptr);
+    });
 }
 
 extern "C" cds_status cds_search_stream_tiff(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *blob, const int64_t *offsets, int64_t n_targets,
                                              int32_t k, double pct_positive_pixels,
                                              int32_t *out_score, int64_t *out_target, uint8_t *out_mirrored, int32_t *out_count)
 {
-    if (!ctx || !ms) { set_tls_error("cds_search_stream_tiff: NULL argument"); return CDS_ERR_BAD_ARG; }
-    const TiffSource src{blob, offsets};
-    return stream_search_impl(ctx, ms, nullptr, n_targets, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr, nullptr, &src);
+    return cds::abi_guard("cds_search_stream_tiff", [&]() -> cds_status {
+        if (!ctx || !ms) { set_tls_error("cds_search_stream_tiff: NULL argument"); return CDS_ERR_BAD_ARG; }
+        const TiffSource src{blob, offsets};
+        return stream_search_impl(ctx, ms, nullptr, n_targets, k, pct_positive_pixels, out_score, out_target, out_mirrored, out_count, nullptr, nullptr, &src);
+    });
 }
 
 extern "C" cds_status cds_search_stream_matches_tiff(cds_ctx *ctx, const cds_maskset *ms, const uint8_t *blob, const int64_t *offsets, int64_t n_targets,
@@ -507,10 +513,12 @@ extern "C" cds_status cds_search_stream_matches_tiff(cds_ctx *ctx, const cds_mas
                                                      int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored,
                                                      int64_t *out_count)
 {
-    if (!ctx || !ms) { set_tls_error("cds_search_stream_matches_tiff: NULL argument"); return CDS_ERR_BAD_ARG; }
-    const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
-    const TiffSource src{blob, offsets};
-    return stream_search_impl(ctx, ms, nullptr, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, nullptr, &src);
+    return cds::abi_guard("cds_search_stream_matches_tiff", [&]() -> cds_status {
+        if (!ctx || !ms) { set_tls_error("cds_search_stream_matches_tiff: NULL argument"); return CDS_ERR_BAD_ARG; }
+        const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
+        const TiffSource src{blob, offsets};
+        return stream_search_impl(ctx, ms, nullptr, n_targets, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, nullptr, &src);
+    });
 }
 
 // The same chunked search over a device-resident library: occupancy bitmaps are built per chunk instead of being kept for
@@ -526,13 +534,15 @@ cds_status search_library_chunked(cds_ctx *ctx, const cds_maskset *ms, cds_libra
 extern "C" cds_status cds_search_matches(cds_ctx *ctx, const cds_maskset *ms, cds_library *lib, double pct_positive_pixels, int64_t capacity,
                                          int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored, int64_t *out_count)
 {
-    if (!ctx || !ms || !lib) { set_tls_error("cds_search_matches: NULL argument"); return CDS_ERR_BAD_ARG; }
-    if (ms->W != lib->g.W || ms->H != lib->g.H) {
-        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-        char buf[200];
-        snprintf(buf, sizeof buf, "Invalid image size - target's image size (%d, %d) must match query's image size: (%d, %d)", ms->W, ms->H, lib->g.W, lib->g.H);
-        return ctx->fail(CDS_ERR_SIZE_MISMATCH, buf);
-    }
-    const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
-    return stream_search_impl(ctx, ms, nullptr, 0, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, lib);
+    return cds::abi_guard("cds_search_matches", [&]() -> cds_status {
+        if (!ctx || !ms || !lib) { set_tls_error("cds_search_matches: NULL argument"); return CDS_ERR_BAD_ARG; }
+        if (ms->W != lib->g.W || ms->H != lib->g.H) {
+            std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+            char buf[200];
+            snprintf(buf, sizeof buf, "Invalid image size - target's image size (%d, %d) must match query's image size: (%d, %d)", ms->W, ms->H, lib->g.W, lib->g.H);
+            return ctx->fail(CDS_ERR_SIZE_MISMATCH, buf);
+        }
+        const AllMatchesOut all{capacity, out_mask, out_target, out_score, out_mirrored, out_count};
+        return stream_search_impl(ctx, ms, nullptr, 0, 1, pct_positive_pixels, nullptr, nullptr, nullptr, nullptr, &all, lib);
+    });
 }

@@ -99,102 +99,108 @@ cds_status synth_render_device(cds_ctx *ctx, DevState &ds, int kind, uint64_t se
 
 extern "C" cds_status cds_library_generate_synthetic(cds_library *lib, uint64_t seed, int64_t first_synth_index, int64_t n, int64_t *first_index)
 {
-    if (!lib) { set_tls_error("cds_library_generate_synthetic: NULL library"); return CDS_ERR_BAD_ARG; }
-    cds_ctx *ctx = lib->ctx;
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (lib->g.W > 16000 || lib->g.H > 16000) return ctx->fail(CDS_ERR_UNSUPPORTED, "synthetic images are limited to 16000 x 16000");
-    const int D = lib->n_dev();
-    std::vector<SynthSpec *> d_specs(D, nullptr);
-    cds_status st = CDS_OK;
-    for (int d = 0; d < D && st == CDS_OK; d++) {
-        st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
-        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_specs[d], (size_t) kLibBlock * sizeof(SynthSpec)), "cudaMalloc(specs)");
-    }
-    if (st == CDS_OK) {
-        st = library_append(lib, n, [&](DevState &ds, int64_t i0, int64_t cnt, uint8_t *d_rgb) -> cds_status {
-            int di = 0;
-            for (int d = 0; d < D; d++) if (ctx->devs[d].dev == ds.dev) di = d;
-            return synth_render_device(ctx, ds, 1, seed, first_synth_index + i0, cnt, lib->g.W, lib->g.H, d_specs[di], d_rgb);
-        }, first_index);
-    }
-    for (int d = 0; d < D; d++) if (d_specs[d]) { cudaSetDevice(ctx->devs[d].dev); cudaFree(d_specs[d]); }
-    return st;
+    return cds::abi_guard("cds_library_generate_synthetic", [&]() -> cds_status {
+        if (!lib) { set_tls_error("cds_library_generate_synthetic: NULL library"); return CDS_ERR_BAD_ARG; }
+        cds_ctx *ctx = lib->ctx;
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (lib->g.W > 16000 || lib->g.H > 16000) return ctx->fail(CDS_ERR_UNSUPPORTED, "synthetic images are limited to 16000 x 16000");
+        const int D = lib->n_dev();
+        std::vector<SynthSpec *> d_specs(D, nullptr);
+        cds_status st = CDS_OK;
+        for (int d = 0; d < D && st == CDS_OK; d++) {
+            st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_specs[d], (size_t) kLibBlock * sizeof(SynthSpec)), "cudaMalloc(specs)");
+        }
+        if (st == CDS_OK) {
+            st = library_append(lib, n, [&](DevState &ds, int64_t i0, int64_t cnt, uint8_t *d_rgb) -> cds_status {
+                int di = 0;
+                for (int d = 0; d < D; d++) if (ctx->devs[d].dev == ds.dev) di = d;
+                return synth_render_device(ctx, ds, 1, seed, first_synth_index + i0, cnt, lib->g.W, lib->g.H, d_specs[di], d_rgb);
+            }, first_index);
+        }
+        for (int d = 0; d < D; d++) if (d_specs[d]) { cudaSetDevice(ctx->devs[d].dev); cudaFree(d_specs[d]); }
+        return st;
+    });
 }
 
 extern "C" cds_status cds_synth_rgb(cds_ctx *ctx, int32_t kind, uint64_t seed, int64_t first_index, int64_t n,
                                     int32_t width, int32_t height, int32_t on_device, uint8_t *rgb_out)
 {
-    if (n < 0 || (n > 0 && !rgb_out) || width <= 0 || height <= 0 || width > 16000 || height > 16000 || (kind != 0 && kind != 1)) {
-        set_tls_error("cds_synth_rgb: bad arguments");
-        return CDS_ERR_BAD_ARG;
-    }
-    const size_t img_bytes = (size_t) width * height * 3;
-    if (!on_device) {
-        std::vector<SynthSpec> spec(1);
-        for (int64_t i = 0; i < n; i++) {
-            synth_make_spec(kind, seed, first_index + i, width, height, spec[0]);
-            synth_render_host(spec[0], rgb_out + (size_t) i * img_bytes);
+    return cds::abi_guard("cds_synth_rgb", [&]() -> cds_status {
+        if (n < 0 || (n > 0 && !rgb_out) || width <= 0 || height <= 0 || width > 16000 || height > 16000 || (kind != 0 && kind != 1)) {
+            set_tls_error("cds_synth_rgb: bad arguments");
+            return CDS_ERR_BAD_ARG;
         }
-        return CDS_OK;
-    }
-    if (!ctx) { set_tls_error("cds_synth_rgb: device generation needs a context"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    DevState &d0 = ctx->devs[0];
-    {
-        cds_status st = ctx->check(cudaSetDevice(d0.dev), "cudaSetDevice");
-        if (st != CDS_OK) return st;
-        SynthSpec *d_specs = nullptr;
-        st = ctx->check(cudaMalloc(&d_specs, (size_t) kLibBlock * sizeof(SynthSpec)), "cudaMalloc(specs)");
-        if (st != CDS_OK) return st;
-        st = ctx->ensure_staging(d0, (size_t) kLibBlock * img_bytes);
-        for (int64_t i0 = 0; i0 < n && st == CDS_OK; i0 += kLibBlock) {
-            int64_t cnt = std::min<int64_t>(kLibBlock, n - i0);
-            st = synth_render_device(ctx, d0, kind, seed, first_index + i0, cnt, width, height, d_specs, (uint8_t *) d0.staging);
-            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(rgb_out + (size_t) i0 * img_bytes, d0.staging, (size_t) cnt * img_bytes, cudaMemcpyDeviceToHost, d0.stream), "synth D2H");
-            if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "synth sync");
+        const size_t img_bytes = (size_t) width * height * 3;
+        if (!on_device) {
+            std::vector<SynthSpec> spec(1);
+            for (int64_t i = 0; i < n; i++) {
+                synth_make_spec(kind, seed, first_index + i, width, height, spec[0]);
+                synth_render_host(spec[0], rgb_out + (size_t) i * img_bytes);
+            }
+            return CDS_OK;
         }
-        cudaFree(d_specs);
-        return st;
-    }
+        if (!ctx) { set_tls_error("cds_synth_rgb: device generation needs a context"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        DevState &d0 = ctx->devs[0];
+        {
+            cds_status st = ctx->check(cudaSetDevice(d0.dev), "cudaSetDevice");
+            if (st != CDS_OK) return st;
+            SynthSpec *d_specs = nullptr;
+            st = ctx->check(cudaMalloc(&d_specs, (size_t) kLibBlock * sizeof(SynthSpec)), "cudaMalloc(specs)");
+            if (st != CDS_OK) return st;
+            st = ctx->ensure_staging(d0, (size_t) kLibBlock * img_bytes);
+            for (int64_t i0 = 0; i0 < n && st == CDS_OK; i0 += kLibBlock) {
+                int64_t cnt = std::min<int64_t>(kLibBlock, n - i0);
+                st = synth_render_device(ctx, d0, kind, seed, first_index + i0, cnt, width, height, d_specs, (uint8_t *) d0.staging);
+                if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(rgb_out + (size_t) i0 * img_bytes, d0.staging, (size_t) cnt * img_bytes, cudaMemcpyDeviceToHost, d0.stream), "synth D2H");
+                if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "synth sync");
+            }
+            cudaFree(d_specs);
+            return st;
+        }
+    });
 }
 
 extern "C" cds_status cds_synth_gradient(cds_ctx *ctx, uint64_t seed, int64_t first_index, int64_t n,
                                          int32_t width, int32_t height, int32_t on_device, uint16_t *grad_out)
 {
-    if (n < 0 || (n > 0 && !grad_out) || width <= 0 || height <= 0 || width > 16000 || height > 16000) {
-        set_tls_error("cds_synth_gradient: bad arguments");
-        return CDS_ERR_BAD_ARG;
-    }
-    const size_t img_px = (size_t) width * height;
-    std::vector<SynthSpec> spec(1);
-    if (!on_device) {
-        for (int64_t i = 0; i < n; i++) {
-            synth_make_spec(1, seed, first_index + i, width, height, spec[0]);
-            synth_gradient_host(spec[0], grad_out + (size_t) i * img_px);
+    return cds::abi_guard("cds_synth_gradient", [&]() -> cds_status {
+        if (n < 0 || (n > 0 && !grad_out) || width <= 0 || height <= 0 || width > 16000 || height > 16000) {
+            set_tls_error("cds_synth_gradient: bad arguments");
+            return CDS_ERR_BAD_ARG;
         }
-        return CDS_OK;
-    }
-    if (!ctx) { set_tls_error("cds_synth_gradient: device generation needs a context"); return CDS_ERR_BAD_ARG; }
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    DevState &d0 = ctx->devs[0];
-    cds_status st = ctx->check(cudaSetDevice(d0.dev), "cudaSetDevice");
-    if (st != CDS_OK) return st;
-    SynthSpec *d_spec = nullptr;
-    uint16_t *d_grad = nullptr;
-    st = ctx->check(cudaMalloc(&d_spec, sizeof(SynthSpec)), "cudaMalloc(spec)");
-    if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_grad, img_px * sizeof(uint16_t)), "cudaMalloc(grad)");
-    for (int64_t i = 0; i < n && st == CDS_OK; i++) {
-        synth_make_spec(1, seed, first_index + i, width, height, spec[0]);
-        st = ctx->check(cudaMemcpyAsync(d_spec, spec.data(), sizeof(SynthSpec), cudaMemcpyHostToDevice, d0.stream), "spec H2D");
-        if (st != CDS_OK) break;
-        dim3 grid(height, 1);
-        synth_gradient_kernel<<<grid, 256, 0, d0.stream>>>(d_spec, d_grad);
-        ctx->stats.kernel_launches++;
-        st = ctx->check(cudaGetLastError(), "synth_gradient_kernel");
-        if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(grad_out + (size_t) i * img_px, d_grad, img_px * sizeof(uint16_t), cudaMemcpyDeviceToHost, d0.stream), "grad D2H");
-        if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "grad sync");
-    }
-    if (d_spec) cudaFree(d_spec);
-    if (d_grad) cudaFree(d_grad);
-    return st;
+        const size_t img_px = (size_t) width * height;
+        std::vector<SynthSpec> spec(1);
+        if (!on_device) {
+            for (int64_t i = 0; i < n; i++) {
+                synth_make_spec(1, seed, first_index + i, width, height, spec[0]);
+                synth_gradient_host(spec[0], grad_out + (size_t) i * img_px);
+            }
+            return CDS_OK;
+        }
+        if (!ctx) { set_tls_error("cds_synth_gradient: device generation needs a context"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        DevState &d0 = ctx->devs[0];
+        cds_status st = ctx->check(cudaSetDevice(d0.dev), "cudaSetDevice");
+        if (st != CDS_OK) return st;
+        SynthSpec *d_spec = nullptr;
+        uint16_t *d_grad = nullptr;
+        st = ctx->check(cudaMalloc(&d_spec, sizeof(SynthSpec)), "cudaMalloc(spec)");
+        if (st == CDS_OK) st = ctx->check(cudaMalloc(&d_grad, img_px * sizeof(uint16_t)), "cudaMalloc(grad)");
+        for (int64_t i = 0; i < n && st == CDS_OK; i++) {
+            synth_make_spec(1, seed, first_index + i, width, height, spec[0]);
+            st = ctx->check(cudaMemcpyAsync(d_spec, spec.data(), sizeof(SynthSpec), cudaMemcpyHostToDevice, d0.stream), "spec H2D");
+            if (st != CDS_OK) break;
+            dim3 grid(height, 1);
+            synth_gradient_kernel<<<grid, 256, 0, d0.stream>>>(d_spec, d_grad);
+            ctx->stats.kernel_launches++;
+            st = ctx->check(cudaGetLastError(), "synth_gradient_kernel");
+            if (st == CDS_OK) st = ctx->check(cudaMemcpyAsync(grad_out + (size_t) i * img_px, d_grad, img_px * sizeof(uint16_t), cudaMemcpyDeviceToHost, d0.stream), "grad D2H");
+            if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(d0.stream), "grad sync");
+        }
+        if (d_spec) cudaFree(d_spec);
+        if (d_grad) cudaFree(d_grad);
+        return st;
+    });
 }

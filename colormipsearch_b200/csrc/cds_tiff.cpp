@@ -117,7 +117,10 @@ cds_status tiff_parse(const uint8_t *file, size_t len, cds_tiff_info &info, std:
         const uint64_t want = (uint64_t) info.width * info.height * info.samples_per_pixel * ((info.bits_per_sample + 7) / 8);
         lens.push_back(offs[0] <= len ? std::min<uint64_t>(want, len - offs[0]) : 0);
     }
-    if (lens.size() != offs.size() && !tiled) { err = "TIFF: strip offsets and byte counts differ in number"; return CDS_ERR_BAD_ARG; }
+    // a tiled file is reported (decodable = 0) but its strip tags, if it carries any, mean nothing: they are dropped, so nothing
+    // below (or in a caller) ever indexes one table with the other's length
+    if (tiled) { offs.clear(); lens.clear(); }
+    if (lens.size() != offs.size()) { err = "TIFF: strip offsets and byte counts differ in number"; return CDS_ERR_BAD_ARG; }
     info.n_strips = (int32_t) offs.size();
     for (size_t i = 0; i < offs.size(); i++) {
         if (!r.ok(offs[i], lens[i])) { err = "TIFF: strip outside the file"; return CDS_ERR_BAD_ARG; }
@@ -179,11 +182,13 @@ cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int h
 
 extern "C" cds_status cds_tiff_probe(const uint8_t *file, int64_t len, cds_tiff_info *info)
 {
-    if (!file || !info || len < 0) { cds::set_tls_error("cds_tiff_probe: bad argument"); return CDS_ERR_BAD_ARG; }
-    std::string err;
-    cds_status s = cds::tiff_parse(file, (size_t) len, *info, nullptr, nullptr, err);
-    if (s != CDS_OK) cds::set_tls_error("cds_tiff_probe: " + err);
-    return s;
+    return cds::abi_guard("cds_tiff_probe", [&]() -> cds_status {
+        if (!file || !info || len < 0) { cds::set_tls_error("cds_tiff_probe: bad argument"); return CDS_ERR_BAD_ARG; }
+        std::string err;
+        cds_status s = cds::tiff_parse(file, (size_t) len, *info, nullptr, nullptr, err);
+        if (s != CDS_OK) cds::set_tls_error("cds_tiff_probe: " + err);
+        return s;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------------ writer
@@ -235,52 +240,54 @@ extern "C" int64_t cds_tiff_encode_bound(int32_t width, int32_t height, int32_t 
 extern "C" cds_status cds_tiff_encode_rgb(const uint8_t *rgb, int32_t width, int32_t height, int32_t rows_per_strip, int32_t compression,
                                           uint8_t *out, int64_t capacity, int64_t *out_len)
 {
-    if (!rgb || !out || !out_len || width <= 0 || height <= 0) { cds::set_tls_error("cds_tiff_encode_rgb: bad argument"); return CDS_ERR_BAD_ARG; }
-    if (compression != 1 && compression != 32773) { cds::set_tls_error("cds_tiff_encode_rgb: compression must be 1 or 32773"); return CDS_ERR_UNSUPPORTED; }
-    if (rows_per_strip <= 0 || rows_per_strip > height) rows_per_strip = height;
-    if (capacity < cds_tiff_encode_bound(width, height, rows_per_strip)) { cds::set_tls_error("cds_tiff_encode_rgb: capacity below cds_tiff_encode_bound"); return CDS_ERR_CAPACITY; }
-    const size_t row = (size_t) width * 3;
-    const int strips = (height + rows_per_strip - 1) / rows_per_strip;
-    std::vector<uint32_t> offs(strips), lens(strips);
-    size_t o = 8;
-    for (int s = 0; s < strips; s++) {
-        offs[s] = (uint32_t) o;
-        const int y1 = std::min(height, (s + 1) * rows_per_strip);
-        for (int y = s * rows_per_strip; y < y1; y++) {
-            if (compression == 1) { memcpy(out + o, rgb + (size_t) y * row, row); o += row; }
-            else o += packbits_row(rgb + (size_t) y * row, row, out + o);
+    return cds::abi_guard("cds_tiff_encode_rgb", [&]() -> cds_status {
+        if (!rgb || !out || !out_len || width <= 0 || height <= 0) { cds::set_tls_error("cds_tiff_encode_rgb: bad argument"); return CDS_ERR_BAD_ARG; }
+        if (compression != 1 && compression != 32773) { cds::set_tls_error("cds_tiff_encode_rgb: compression must be 1 or 32773"); return CDS_ERR_UNSUPPORTED; }
+        if (rows_per_strip <= 0 || rows_per_strip > height) rows_per_strip = height;
+        if (capacity < cds_tiff_encode_bound(width, height, rows_per_strip)) { cds::set_tls_error("cds_tiff_encode_rgb: capacity below cds_tiff_encode_bound"); return CDS_ERR_CAPACITY; }
+        const size_t row = (size_t) width * 3;
+        const int strips = (height + rows_per_strip - 1) / rows_per_strip;
+        std::vector<uint32_t> offs(strips), lens(strips);
+        size_t o = 8;
+        for (int s = 0; s < strips; s++) {
+            offs[s] = (uint32_t) o;
+            const int y1 = std::min(height, (s + 1) * rows_per_strip);
+            for (int y = s * rows_per_strip; y < y1; y++) {
+                if (compression == 1) { memcpy(out + o, rgb + (size_t) y * row, row); o += row; }
+                else o += packbits_row(rgb + (size_t) y * row, row, out + o);
+            }
+            lens[s] = (uint32_t) (o - offs[s]);
         }
-        lens[s] = (uint32_t) (o - offs[s]);
-    }
-    if (o & 1) out[o++] = 0;
-    // out-of-line values: BitsPerSample, then the two strip tables when there is more than one strip
-    const size_t bits_at = o;
-    put16(out + o, 8); put16(out + o + 2, 8); put16(out + o + 4, 8); o += 6;
-    size_t offs_at = 0, lens_at = 0;
-    if (strips > 1) {
-        offs_at = o;
-        for (int s = 0; s < strips; s++, o += 4) put32(out + o, offs[s]);
-        lens_at = o;
-        for (int s = 0; s < strips; s++, o += 4) put32(out + o, lens[s]);
-    }
-    const size_t ifd = o;
-    struct Entry { uint16_t tag, type; uint32_t count, value; };
-    const Entry entries[] = {
-        {256, 4, 1, (uint32_t) width}, {257, 4, 1, (uint32_t) height}, {258, 3, 3, (uint32_t) bits_at},
-        {259, 3, 1, (uint32_t) compression}, {262, 3, 1, 2}, {273, 4, (uint32_t) strips, strips > 1 ? (uint32_t) offs_at : offs[0]},
-        {277, 3, 1, 3}, {278, 4, 1, (uint32_t) rows_per_strip}, {279, 4, (uint32_t) strips, strips > 1 ? (uint32_t) lens_at : lens[0]},
-        {284, 3, 1, 1},
-    };
-    const int n_entries = (int) (sizeof entries / sizeof entries[0]);
-    put16(out + o, n_entries); o += 2;
-    for (const Entry &e : entries) {
-        put16(out + o, e.tag); put16(out + o + 2, e.type); put32(out + o + 4, e.count);
-        if (e.type == 3 && e.count == 1) { put16(out + o + 8, e.value); put16(out + o + 10, 0); }
-        else put32(out + o + 8, e.value);
-        o += 12;
-    }
-    put32(out + o, 0); o += 4;
-    out[0] = 'I'; out[1] = 'I'; put16(out + 2, 42); put32(out + 4, (uint32_t) ifd);
-    *out_len = (int64_t) o;
-    return CDS_OK;
+        if (o & 1) out[o++] = 0;
+        // out-of-line values: BitsPerSample, then the two strip tables when there is more than one strip
+        const size_t bits_at = o;
+        put16(out + o, 8); put16(out + o + 2, 8); put16(out + o + 4, 8); o += 6;
+        size_t offs_at = 0, lens_at = 0;
+        if (strips > 1) {
+            offs_at = o;
+            for (int s = 0; s < strips; s++, o += 4) put32(out + o, offs[s]);
+            lens_at = o;
+            for (int s = 0; s < strips; s++, o += 4) put32(out + o, lens[s]);
+        }
+        const size_t ifd = o;
+        struct Entry { uint16_t tag, type; uint32_t count, value; };
+        const Entry entries[] = {
+            {256, 4, 1, (uint32_t) width}, {257, 4, 1, (uint32_t) height}, {258, 3, 3, (uint32_t) bits_at},
+            {259, 3, 1, (uint32_t) compression}, {262, 3, 1, 2}, {273, 4, (uint32_t) strips, strips > 1 ? (uint32_t) offs_at : offs[0]},
+            {277, 3, 1, 3}, {278, 4, 1, (uint32_t) rows_per_strip}, {279, 4, (uint32_t) strips, strips > 1 ? (uint32_t) lens_at : lens[0]},
+            {284, 3, 1, 1},
+        };
+        const int n_entries = (int) (sizeof entries / sizeof entries[0]);
+        put16(out + o, n_entries); o += 2;
+        for (const Entry &e : entries) {
+            put16(out + o, e.tag); put16(out + o + 2, e.type); put32(out + o + 4, e.count);
+            if (e.type == 3 && e.count == 1) { put16(out + o + 8, e.value); put16(out + o + 10, 0); }
+            else put32(out + o + 8, e.value);
+            o += 12;
+        }
+        put32(out + o, 0); o += 4;
+        out[0] = 'I'; out[1] = 'I'; put16(out + 2, 42); put32(out + 4, (uint32_t) ifd);
+        *out_len = (int64_t) o;
+        return CDS_OK;
+    });
 }

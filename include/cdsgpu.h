@@ -336,6 +336,10 @@ cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out);
 cds_status cds_debug_encode_colors(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t data_threshold, uint32_t *codes_out);
 cds_status cds_debug_class_intervals(double z_tolerance, int32_t sector, int32_t rank,
                                      uint32_t *lo1, uint32_t *len1, uint32_t *lo2, uint32_t *len2);
+/* Slice numbers (1..256, 0 = black) of n RGB colours as the shape path computes them on the device -- a table built per device
+ * with the double arithmetic of GradientAreaGapUtils.findSliceNumberInLUT (API/cds/GradientAreaGapUtils.java:18-197) -- so that the
+ * table can be checked against the oracle over all 2^24 colours. */
+cds_status cds_debug_slice_numbers(cds_ctx *ctx, const uint8_t *rgb, int64_t n, uint16_t *slices_out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -539,6 +539,15 @@ CDSO_API int cdso_slice_number(int red, int green, int blue)
     return cdso_find_slice_number(c1, c2, ratio);
 }
 
+/* Batch forms for the exhaustive tests (all 2^24 colours): out[i] = slice number / gray of colour rgb[3i..3i+2]. */
+CDSO_API void cdso_slice_numbers(const uint8_t *rgb, int64_t n, uint16_t *out)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < n; i++) out[i] = (uint16_t) cdso_slice_number(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+}
+
 /* calculateSliceGap :18-105; rgb ints are 0xAARRGGBB */
 CDSO_API int cdso_slice_gap(int rgb1, int rgb2)
 {
@@ -578,6 +587,14 @@ CDSO_API int cdso_rgb_to_gray(int r, int g, int b)     /* rgbToGrayNoGammaCorrec
     double gw = 1 / 3.;
     double bw = 1 / 3.;
     return (int) ((maxGrayValue / 255) * (r * rw + g * gw + b * bw + 0.5));
+}
+
+CDSO_API void cdso_rgb_to_gray_batch(const uint8_t *rgb, int64_t n, uint8_t *out)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < n; i++) out[i] = (uint8_t) cdso_rgb_to_gray(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
 }
 
 /* ColorTransformation.mask(threshold) on RGB (:29-38, :114-132): black when every channel <= threshold */

@@ -73,6 +73,8 @@ def lib():
         L.cdso_lut.argtypes = [i32p]
         L.cdso_slice_number.restype = C.c_int
         L.cdso_slice_number.argtypes = [C.c_int] * 3
+        L.cdso_slice_numbers.argtypes = [u8p, C.c_int64, u16p]
+        L.cdso_rgb_to_gray_batch.argtypes = [u8p, C.c_int64, u8p]
         L.cdso_slice_gap.restype = C.c_int
         L.cdso_slice_gap.argtypes = [C.c_int, C.c_int]
         L.cdso_shape_score_2d.restype = C.c_int64
@@ -202,6 +204,21 @@ def lut():
 
 def slice_number(r, g, b):
     return lib().cdso_slice_number(int(r), int(g), int(b))
+
+
+def slice_numbers(rgb):
+    """slice number of every colour of rgb[n][3] (uint16[n])"""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+    out = np.empty(len(rgb), np.uint16)
+    lib().cdso_slice_numbers(_u8(rgb), len(rgb), _u16(out))
+    return out
+
+
+def rgb_to_gray_batch(rgb):
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+    out = np.empty(len(rgb), np.uint8)
+    lib().cdso_rgb_to_gray_batch(_u8(rgb), len(rgb), _u8(out))
+    return out
 
 
 def slice_gap(rgb1, rgb2):

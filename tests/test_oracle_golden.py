@@ -91,13 +91,31 @@ def test_line_radii_r10():
     assert dx.tolist() == [1, 4, 6, 7, 8, 8, 9, 9, 9, 10, 10, 10, 9, 9, 9, 8, 8, 7, 6, 4, 1]
 
 
+def _all_colours():
+    v = np.arange(1 << 24, dtype=np.uint32)
+    return np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=1).astype(np.uint8)
+
+
 def test_gray_integer_form():
-    # gray == floor((2(r+g+b)+3)/6) for every colour (spot check a lattice + random)
-    rng = np.random.default_rng(3)
-    cols = rng.integers(0, 256, (20000, 3))
-    for r, g, b in cols:
-        exp = 0 if (r | g | b) == 0 else (2 * (int(r) + int(g) + int(b)) + 3) // 6
-        assert O.rgb_to_gray(r, g, b) == exp
+    # gray == floor((2(r+g+b)+3)/6) for EVERY colour (all 2^24): the integer form the device uses
+    # (csrc/cds_shape.cu gray_of) against the oracle's double expression (ColorTransformation.java:40-54)
+    cols = _all_colours()
+    s = cols.astype(np.int64).sum(axis=1)
+    exp = np.where(s == 0, 0, (2 * s + 3) // 6).astype(np.uint8)
+    assert np.array_equal(O.rgb_to_gray_batch(cols), exp)
+
+
+def test_slice_numbers_of_the_lut():
+    # GradientAreaGapUtils.java:131-197: a LUT colour is found by exact ratio equality -> its own 1-based index,
+    # unless an earlier entry of the same sub-range has the same ratio (none has); black -> 0
+    lut = O.lut()
+    got = O.slice_numbers(lut.astype(np.uint8))
+    assert got.tolist() == list(range(1, 257))
+    assert O.slice_number(0, 0, 0) == 0
+    # the batch form is the scalar form
+    rng = np.random.default_rng(11)
+    cols = rng.integers(0, 256, (5000, 3)).astype(np.uint8)
+    assert O.slice_numbers(cols).tolist() == [O.slice_number(*c) for c in cols]
 
 
 def test_is_match():

@@ -18,6 +18,17 @@ def ctx():
     c.close()
 
 
+def test_slice_numbers_all_colours(ctx):
+    """The device's slice table (csrc/cds_shape.cu slice_of) against GradientAreaGapUtils.calculateSliceGap's slice numbers
+    (oracle cdso_slice_number, API/cds/GradientAreaGapUtils.java:18-197) for ALL 2^24 colours."""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    cols = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=1).astype(np.uint8)
+    got = ctx.debug_slice_numbers(cols)
+    want = O.slice_numbers(cols)
+    assert np.array_equal(got, want)
+    assert got.max() == 256 and got[0] == 0
+
+
 def test_mask_sizes_golden(ctx, fixtures):
     # Shape2DMatchColorDepthSearchAlgorithmTest.java:53-54
     for mask, thr, exp_qm, exp_he in GV.SHAPE_MASK_SIZES:
@@ -152,3 +163,44 @@ def test_roi_mask_matches_oracle(ctx, fixtures):
         gap, he, mir = sms.score_pairs(t[None], fixtures[gkey][None], z[None], [0], [0])
         assert (int(gap[0]), int(he[0]), bool(mir[0])) == om.score(t, fixtures[gkey], z)
     sms.close()
+
+
+@pytest.mark.parametrize("size", [(333, 151), (96, 64), (1025, 70)], ids=["odd", "one_strip", "wide"])
+def test_small_and_odd_image_sizes_match_oracle(ctx, size):
+    """Image sizes that are not the library's: odd widths (unaligned slice-plane rows), a single strip, partly filled last tiles;
+    random sparse colours next to the borders and inside a label rectangle, derived and given zgap images, with and without ROI."""
+    Ws, Hs = size
+    rng = np.random.default_rng(Ws * 1000 + Hs)
+    rects = np.array([[0, 0, min(40, Ws // 3), 12], [Ws - 17, Hs - 9, Ws, Hs]], np.int32)
+
+    def sparse(n, lo=1):
+        img = np.zeros((Hs, Ws, 3), np.uint8)
+        idx = rng.integers(0, Hs * Ws, n)
+        img.reshape(-1, 3)[idx] = rng.integers(lo, 256, (n, 3))
+        img[0, :5] = 200; img[-1, -5:] = 90; img[:4, -1] = 33          # pixels on the borders
+        return img
+
+    dim = np.zeros((Hs, Ws, 3), np.uint8)               # channel values 0..2: the gray(max60) > 0 test is "channel maxima add up to >= 2"
+    idx = rng.integers(0, Hs * Ws, 40)
+    dim.reshape(-1, 3)[idx] = rng.integers(0, 3, (40, 3))
+    masks = np.stack([sparse(60 + 40 * i, 0) for i in range(3)] + [dim])
+    targets = np.stack([sparse(150 + 100 * i) for i in range(5)])
+    grads = rng.integers(0, 700, (5, Hs, Ws)).astype(np.uint16)
+    roi = np.zeros((Hs, Ws, 3), np.uint8)
+    roi[Hs // 5: Hs - 3, Ws // 7: Ws - Ws // 9] = 255
+    for r in (None, roi):
+        sms = capi.ShapeMaskSet(ctx, Ws, Hs, 20, True, rects, roi=r)
+        qm, he = sms.add_rgb(masks)
+        oms = [O.ShapeMask(m, 20, True, rects, roi=r) for m in masks]
+        assert qm.tolist() == [int(o.qm.sum()) for o in oms]
+        assert he.tolist() == [int(o.he.sum()) for o in oms]
+        pm = [m for m in range(4) for _ in range(5)]
+        pt = [t for _ in range(4) for t in range(5)]
+        zg = np.stack([O.make_zgap(t, 20, rects) for t in targets])
+        got_z = ctx.make_zgap(targets, 20, 10, rects)
+        assert np.array_equal(got_z, zg)
+        for z in (None, zg):
+            gap, hexp, mir = sms.score_pairs(targets, grads, z, pm, pt)
+            for i, (m, t) in enumerate(zip(pm, pt)):
+                assert (int(gap[i]), int(hexp[i]), bool(mir[i])) == oms[m].score(targets[t], grads[t], zg[t]), (size, r is not None, z is not None, m, t)
+        sms.close()

@@ -127,3 +127,30 @@ def test_probe_survives_corrupted_files(tiffs):
         assert info["width"] > 0 and info["height"] > 0
         if info["decodable"]:
             assert 0 <= info["data_bytes"] <= len(data) * max(1, info["n_strips"])
+
+
+def _ifd_file(entries, extra=b""):
+    """A little-endian TIFF whose IFD (at offset 8) holds `entries` = [(tag, type, count, value)], followed by `extra` bytes."""
+    out = b"II" + struct.pack("<HI", 42, 8) + struct.pack("<H", len(entries))
+    for tag, typ, count, value in entries:
+        out += struct.pack("<HHII", tag, typ, count, value)
+    return out + struct.pack("<I", 0) + extra
+
+
+def test_probe_tiled_file_with_strip_tags_and_mismatched_strip_tables():
+    """A tile tag next to StripOffsets without (or with fewer) StripByteCounts used to index the byte-count table out of bounds
+    (a crash inside cds_tiff_probe, i.e. inside the JVM); strip tables of different lengths are a malformed file either way."""
+    end = 8 + 2 + 4 * 12 + 4
+    # width, height, 3 strip offsets (out of line), TileWidth -- no StripByteCounts at all
+    tiled = _ifd_file([(256, 4, 1, 64), (257, 4, 1, 64), (273, 4, 3, end), (322, 4, 1, 16)], struct.pack("<III", 8, 8, 8))
+    info = capi.tiff_probe(tiled)
+    assert info["decodable"] == 0 and info["n_strips"] == 0
+    # not tiled: 3 offsets, 2 byte counts
+    end = 8 + 2 + 4 * 12 + 4
+    bad = _ifd_file([(256, 4, 1, 64), (257, 4, 1, 64), (273, 4, 3, end), (279, 4, 2, end + 12)], struct.pack("<IIIII", 8, 8, 8, 1, 1))
+    with pytest.raises(capi.CdsIllegalArgument):
+        capi.tiff_probe(bad)
+    # tiled with both tables present but of different lengths: still only reported as not decodable
+    both = _ifd_file([(256, 4, 1, 64), (257, 4, 1, 64), (273, 4, 3, end + 12), (279, 4, 2, end + 24), (322, 4, 1, 16)],
+                     struct.pack("<IIIIIIII", 0, 0, 0, 8, 8, 8, 1, 1))
+    assert capi.tiff_probe(both)["decodable"] == 0

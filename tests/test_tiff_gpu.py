@@ -238,3 +238,29 @@ def test_device_decode_of_garbage_strips(ctx):
         expect.append(exp.reshape(h, w, 3))
     got = capi.tiff_decode_rgb(ctx, files, w, h)
     assert np.array_equal(got, np.stack(expect))
+
+
+def test_failed_mask_append_leaves_the_mask_set_unchanged(ctx, synth_files):
+    """cds_maskset_add_tiff with an undecodable file in its SECOND chunk of 64: the call fails naming the file, and the mask set
+    is exactly what it was before the call (all or nothing) -- the next append and search behave like a fresh mask set's."""
+    masks, targets, files = synth_files
+    rects = O.label_rects(W, H)
+    mfiles = [capi.tiff_encode_rgb(m, 8, 32773) for m in masks]
+    many = [mfiles[i % len(mfiles)] for i in range(80)]
+    bad = list(many)
+    bad[70] = b"II*\0" + b"\0" * 60
+    a = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    first = a.add_tiff(mfiles[:3])
+    with pytest.raises(capi.CdsError) as e:
+        a.add_tiff(bad)
+    assert "file 70" in str(e.value)
+    assert len(a) == 3 and np.array_equal(a.sizes(), first)
+    more = a.add_tiff(many[:70])
+    b = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    sb = np.concatenate([b.add_tiff(mfiles[:3]), b.add_tiff(many[:70])])
+    assert np.array_equal(np.concatenate([first, more]), sb) and len(a) == len(b) == 73
+    ra = a.search_stream_tiff(files, 10, 0.0)
+    rb = b.search_stream_tiff(files, 10, 0.0)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    a.close(); b.close()
