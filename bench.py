@@ -105,17 +105,6 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def synth_host_parallel(kind, first, n):
-    """Host build of the synthetic generator, one chunk per host thread (ctypes releases the GIL)."""
-    from concurrent.futures import ThreadPoolExecutor
-    from colormipsearch_b200 import capi
-    nt = host_threads()
-    chunks = [(first + i, min(8, n - i)) for i in range(0, n, 8)]
-    with ThreadPoolExecutor(nt) as ex:
-        parts = list(ex.map(lambda c: capi.synth_rgb_host(kind, SEED, c[0], c[1], W, H), chunks))
-    return np.concatenate(parts)
-
-
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -244,20 +233,109 @@ def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
     return out
 
 
+def data_dependence(ctx, masks_synth, n_masks=1000, n_targets=1024, reps=3):
+    """The candidate kernel's speed depends on the data (its ticket tests skip mask tiles where the target has nothing in that
+    colour sector), so the headline workload is not the whole story.  Two more settings at reduced size, each with its own
+    comparisons/s (device time of cds_search_topk over a resident library) and an oracle check of sampled cells:
+      real_fixture     masks = the reference's three EM fixtures, targets = its four LM fixtures, label regions cleared, replicated
+                       with translation (and brightness scaling for the targets) jitter
+      dense_synthetic  the synthetic masks against targets that overlay six synthetic targets each (~20-30 % of the pixels lit)"""
+    from colormipsearch_b200 import capi
+    from oracle import oracle as O
+    rects = label_rects()
+    p = PARAMS
+    rng = np.random.default_rng(7)
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "cdsearch_fixtures.npz"))
+
+    def clear(img):
+        img = img.copy()
+        for x0, y0, x1, y1 in rects:
+            img[y0:y1, x0:x1] = 0
+        return img
+
+    def jitter(img, scale):
+        out = np.roll(img, (int(rng.integers(-40, 41)), int(rng.integers(-60, 61))), axis=(0, 1))
+        if scale < 1.0:
+            out = ((out.astype(np.uint16) * int(scale * 256)) >> 8).astype(np.uint8)
+        return out
+
+    def leg(masks, targets, what):
+        lib = capi.Library(ctx, W, H, len(targets))
+        for i in range(0, len(targets), 256):
+            lib.add_rgb(targets[i:i + 256])
+        ms = capi.MaskSet(ctx, W, H, p["mask_threshold"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], p["mirror"], rects)
+        sizes = np.concatenate([ms.add_rgb(masks[i:i + 64]) for i in range(0, len(masks), 64)])
+        ms.search_topk(lib, TOPK, PCT_POSITIVE)
+        dev_ms, kern = 0.0, 0
+        for _ in range(reps):
+            res = ms.search_topk(lib, TOPK, PCT_POSITIVE)
+            st = ctx.last_stats()
+            dev_ms += st["total_device_ms"]
+            kern = st["match_kernel"]
+        # oracle: 4 masks x 8 targets, every cell
+        pm = np.sort(rng.choice(len(masks), 4, replace=False))
+        pt = np.sort(rng.choice(len(targets), 8, replace=False))
+        sub = capi.MaskSet(ctx, W, H, p["mask_threshold"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], p["mirror"], rects)
+        sub.add_rgb(masks[pm])
+        dense, dmir = sub.search_dense(lib)
+        sub.close()
+        oms = [O.PixelMatchMask(masks[i], p["mask_threshold"], p["mirror"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], rects) for i in pm]
+        es, em, _ = O.search_dense(oms, targets[pt])
+        ok = bool(np.array_equal(dense[:, pt], es) and np.array_equal(dmir[:, pt], em))
+        lit = float(np.mean([(t.max(axis=2) > p["data_threshold"]).mean() for t in targets[:: max(1, len(targets) // 32)]]))
+        out = {"value": len(masks) * len(targets) * reps / (dev_ms * 1e-3), "unit": "comparisons/s", "masks": len(masks), "targets": len(targets),
+               "ms_per_search": dev_ms / reps, "match_kernel": {1: "candidate", 2: "band", 3: "gather"}.get(kern, "?"),
+               "target_pixels_above_threshold": lit, "mask_pixels_mean": float(np.mean(sizes)),
+               "matches_returned": int(res[3].sum()), "equals_oracle_on_sampled_cells": ok, "what": what}
+        ms.close()
+        lib.close()
+        return out
+
+    legs = {}
+    em = [clear(fx[k]) for k in ("em_12191", "em_12191_FL", "em_LPLC2")]
+    lm = [clear(fx[k]) for k in ("lm_BJD", "lm_GMR", "lm_VT016795", "lm_VT033614")]
+    masks = np.stack([jitter(em[i % 3], 1.0) for i in range(n_masks)])
+    targets = np.stack([jitter(lm[i % 4], float(rng.uniform(0.5, 1.0))) for i in range(n_targets)])
+    legs["real_fixture"] = leg(masks, targets, "the reference's EM / LM fixture images (labels cleared), replicated with jitter")
+    del masks, targets
+    base = np.concatenate([ctx.synth_rgb(1, SEED, 100000 + i, min(64, 6 * 128 - i), W, H, on_device=True) for i in range(0, 6 * 128, 64)])
+    pool = []
+    for i in range(128):
+        out = base[6 * i].copy()
+        for k in range(1, 6):
+            nxt = base[6 * i + k]
+            empty = ~out.any(axis=2)
+            out[empty] = nxt[empty]
+        pool.append(out)
+    del base
+    targets = np.stack([jitter(pool[i % 128], 1.0) for i in range(n_targets)])
+    legs["dense_synthetic"] = leg(masks_synth[:n_masks], targets, "synthetic masks x overlays of six synthetic targets each, replicated with jitter")
+    return legs
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is Java and there is no JVM on
     this image, so this is the oracle port (oracle/cds_oracle.c, pinned on the reference's golden vectors) on all host
-    cores; each step is a bounded sample of the workload."""
+    cores; each step is a bounded sample of the workload.  Nothing here maps the GPU library: the synthetic inputs come from
+    the host-only build of the generator (oracle/synth_host.cpp)."""
     rank, local_rank, world = dist_env()
     if rank != 0:
         return
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as O
+    from oracle import synth as S
     rects = label_rects()
     cores = host_threads()
     p = PARAMS
     n_m, n_t = args.ref_masks, max(args.ref_targets, cores)
-    masks = synth_host_parallel(0, 0, n_m)
-    targets = synth_host_parallel(1, 0, n_t)
+
+    def gen(kind, n):
+        chunks = [(i, min(8, n - i)) for i in range(0, n, 8)]
+        with ThreadPoolExecutor(cores) as ex:
+            return np.concatenate(list(ex.map(lambda c: S.synth_rgb(kind, SEED, c[0], c[1], W, H), chunks)))
+
+    masks = gen(0, n_m)
+    targets = gen(1, n_t)
     oms = [O.PixelMatchMask(m, p["mask_threshold"], p["mirror"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], rects)
            for m in masks]
     for _ in range(args.warmup):
@@ -268,13 +346,17 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = n_m * n_t * args.steps / dt
     sample = "%d masks x %d targets per step (bounded sample of the workload), OpenMP over targets" % (n_m, n_t)
+    cfg = workload_config(args, world)
+    cfg["workload"] += "; THIS ARM: CPU port timed on a bounded sample of it, %d masks x %d targets per step" % (n_m, n_t)
+    cfg["sample"] = {"masks": n_m, "targets": n_t}
     line = {
         "impl": "reference", "metric": "mask x target CDS comparisons/sec", "value": value, "unit": "comparisons/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": workload_config(args, world),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "comparisons/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "comparisons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_library_mapped": "libcdsgpu" in open("/proc/self/maps").read(),
         "note": "Java reference cannot run here (no JVM); this is the C port of its algorithm pinned on its golden vectors",
     }
     print(json.dumps(line), flush=True)
@@ -307,8 +389,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-tiff", action="store_true", help="skip the TIFF-file variant of the end-to-end step")
-    ap.add_argument("--e2e-tiff", action="store_true", help="run the TIFF-file variant also when world > 1")
+    ap.add_argument("--e2e-tiff", action="store_true", help="(default now) the TIFF-file variant of the end-to-end step runs at every N")
     ap.add_argument("--no-shape", action="store_true")
+    ap.add_argument("--no-data-dependence", action="store_true", help="skip the real-fixture / dense-target legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -464,7 +547,7 @@ def main():
                        "result D2H, host merge) + destroy"}
         # ---- the same step with the targets as PackBits TIFF FILES in pinned host memory (how colour-depth MIP libraries are
         # stored): the files cross PCIe as they are and are decoded on the device
-        if (world == 1 or args.e2e_tiff) and not args.no_e2e_tiff and pool_t >= Te:
+        if not args.no_e2e_tiff and pool_t >= Te:
             from concurrent.futures import ThreadPoolExecutor
             t_enc = time.perf_counter()
             pool_img = pool_arr[:Te * img_bytes].reshape(Te, H, W, 3)
@@ -533,37 +616,65 @@ def main():
         peak, peak_src = measured_peak()
         per_launch_cmp = M * T / max(match_launches / args.steps, 1)
         avg_launch_s = match_ms * 1e-3 / max(match_launches, 1)
-        achieved = per_launch_cmp * ALGO_BYTES_PER_COMPARISON / avg_launch_s / 1e9
-        traffic = None
+        cmp_per_s_kernel = per_launch_cmp / avg_launch_s
+        achieved_algo = cmp_per_s_kernel * ALGO_BYTES_PER_COMPARISON / 1e9
+        # counters of the dominant kernel from one `ncu --set full` capture of this command at reduced size (profiles/ncu_traffic.json
+        # names the capture): DRAM bytes and executed warp instructions per comparison scale with the launch
+        nc = {}
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp))["dram_bytes_per_comparison"] * per_launch_cmp   # ncu capture scaled to this launch
+                nc = json.load(open(tp))
             except Exception:
-                traffic = None
+                nc = {}
+        traffic = nc["dram_bytes_per_comparison"] * per_launch_cmp if "dram_bytes_per_comparison" in nc else None
+        n_groups = -(-M // 1024)
+        # what ONE pass of the kernel's own layout over the resident shard costs: code plane + occupancy bitmaps of every target, per mask group
+        plane_bytes = (H + 4) * 1224 * 4 + 142 * (7 * 152 + 32) * 4
+        pass_floor = float(plane_bytes) * T * n_groups
+        clocks = sampler.summary()
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = 148 * 4 * sm_hz                    # warp instructions / s: 148 SMs x 4 schedulers x clock
+        wipc = nc.get("warp_inst_per_comparison")
         line = {
             "metric": "mask x target CDS comparisons/sec", "value": value, "unit": "comparisons/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
-            "clocks": sampler.summary(), "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm",
+                         # frac = PHYSICAL DRAM traffic of the dominant kernel (ncu dram__bytes_read + write, per launch) / its launch time / HBM copy peak
+                         "achieved": (traffic / avg_launch_s / 1e9) if traffic else None, "peak": peak, "unit": "GB/s",
+                         "frac": (traffic / avg_launch_s / 1e9 / peak) if traffic else None,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": {1: "pixelmatch_cand_kernel<1,1024,31>", 2: "pixelmatch_band_kernel<1,true,128,24>", 3: "pixelmatch_gather_kernel"}.get(kernel_used, "?"),
-                         "algorithmic_bytes_per_comparison": ALGO_BYTES_PER_COMPARISON,
                          "comparisons_per_launch": per_launch_cmp, "avg_launch_ms": avg_launch_s * 1e3,
-                         "physical_dram_gbs": (traffic / avg_launch_s / 1e9) if traffic else None,
-                         "physical_dram_frac": (traffic / avg_launch_s / 1e9 / peak) if traffic else None,
-                         "note": "algorithmic bytes = 3*W*H per comparison (SURVEY 8d); a mask group shares one pass over the "
-                                 "target, so frac can exceed 1 -- physical DRAM traffic (ncu dram bytes per comparison x this "
-                                 "launch's comparisons) is in `traffic`, its rate in physical_dram_*; the kernel is bound by "
-                                 "instruction issue (profiles/r01_v19_cand_ncu_summary.txt), not by HBM"},
+                         # SURVEY 8(d)'s accounting: 3*W*H bytes per comparison, as if every mask re-read every target
+                         "algorithmic_bytes_per_comparison": ALGO_BYTES_PER_COMPARISON,
+                         "achieved_algorithmic": achieved_algo, "frac_algorithmic": achieved_algo / peak,
+                         # the kernel's own layout read exactly once per mask group: the HBM floor of this formulation
+                         "pass_floor_bytes": pass_floor, "pass_floor_frac": pass_floor / avg_launch_s / 1e9 / peak,
+                         # the ceiling that binds: issue slots
+                         "warp_inst_per_comparison": wipc,
+                         "issue_frac": (wipc * cmp_per_s_kernel / issue_peak) if wipc else None,
+                         "issue_peak_warp_inst_per_s": issue_peak,
+                         "spin_share_of_instructions": nc.get("spin_share_of_instructions"),
+                         "counters_source": nc.get("source"),
+                         "note": "frac is physical (ncu DRAM bytes per comparison x this launch's comparisons / launch time / measured "
+                                 "HBM copy peak).  frac_algorithmic follows SURVEY 8(d) (3*W*H bytes per comparison) and exceeds 1 because "
+                                 "up to 1024 masks share one pass over a target.  The kernel is bound by instruction issue: issue_frac = "
+                                 "warp instructions per comparison x comparisons/s / (148 SMs x 4 schedulers x SM clock)"},
             "e2e": e2e,
             "mask_pixels_mean": float(np.mean(mask_sizes)), "setup_s": setup_s,
             "matches_returned": int(merged[3].sum()) if merged is not None else None,
         }
         if not args.no_shape and world == 1:
             line["shape"] = shape_bench(ctx)
+        if not args.no_data_dependence and world == 1:
+            try:
+                line["data_dependence"] = data_dependence(ctx, masks_host)
+            except Exception as e:      # reporting only
+                line["data_dependence"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             def targets_fn(n):
                 return np.concatenate([ctx.synth_rgb(1, SEED, i, min(64, n - i), W, H, on_device=True) for i in range(0, n, 64)])
