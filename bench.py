@@ -233,6 +233,81 @@ def shape_bench(ctx, n_masks=64, n_targets=600, per_mask=300, cpu_pairs=48):
     return out
 
 
+def shape_config2_mix(ctx, topk, n_masks, t_first, t_limit=4096):
+    """BASELINE configs[2] with its REAL pair mix: the pairs are the top-300 isMatch targets of every mask from the pixel-match
+    step this bench has just run (about 8 pairs per target, not 32), restricted to the first `t_limit` targets of the shard so
+    that targets + gradients fit comfortably in pinned host memory.  End to end through cds_shape_score_pairs(_tiff) with host buffers."""
+    from concurrent.futures import ThreadPoolExecutor
+    from colormipsearch_b200 import capi
+    rects = label_rects()
+    score, target, mirrored, count = topk
+    pm = np.repeat(np.arange(n_masks, dtype=np.int32), count[:n_masks])
+    pt = np.concatenate([target[m, :count[m]] for m in range(n_masks)]).astype(np.int64)
+    keep = pt < t_limit
+    pm, pt = pm[keep], pt[keep]
+    n_pairs, n_t = len(pm), t_limit
+    if n_pairs == 0:
+        return {"error": "no pairs"}
+    masks = np.concatenate([ctx.synth_rgb(0, SEED, i, min(64, n_masks - i), W, H, on_device=True) for i in range(0, n_masks, 64)])
+    t_arr, t_ptr = ctx.host_alloc(n_t * 3 * W * H)
+    g_arr, g_ptr = ctx.host_alloc(n_t * 2 * W * H)
+    targets = t_arr.reshape(n_t, H, W, 3)
+    grads = g_arr.view(np.uint16).reshape(n_t, H, W)
+    for i in range(0, n_t, 64):
+        n = min(64, n_t - i)
+        targets[i:i + n] = ctx.synth_rgb(1, SEED, t_first + i, n, W, H, on_device=True)
+        grads[i:i + n] = ctx.synth_gradient(SEED, t_first + i, n, W, H, on_device=True)
+    m_arr, m_ptr = ctx.host_alloc(n_masks * 3 * W * H)
+    np.copyto(m_arr, masks.reshape(-1))
+    sms = capi.ShapeMaskSet(ctx, W, H, 20, True, rects)
+    sms.add_rgb(masks[:64])                                                       # warm-up: pooled buffers
+    sms.close()
+    t0 = time.perf_counter()
+    sms = capi.ShapeMaskSet(ctx, W, H, 20, True, rects)
+    sms.add_rgb_ptr(m_ptr, n_masks)
+    prep_s = time.perf_counter() - t0
+    sms.score_pairs(targets[:64], grads[:64], None, pm[:8] * 0, pt[:8] % 64)      # warm-up
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        gap, he, mir = sms.score_pairs(targets, grads, None, pm, pt)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    st = ctx.last_stats()
+    with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+        files = list(ex.map(lambda i: capi.tiff_encode_rgb(targets[i], 8, 32773), range(n_t)))
+    foff = np.zeros(n_t + 1, np.int64)
+    np.cumsum([len(f) for f in files], out=foff[1:])
+    f_arr, f_ptr = ctx.host_alloc(int(foff[-1]) + 64)
+    for i, f in enumerate(files):
+        f_arr[foff[i]:foff[i + 1]] = np.frombuffer(f, np.uint8)
+    del files
+    sms.score_pairs_tiff((f_arr, foff), grads, None, pm[:64], pt[:64], blob_ptr=f_ptr)
+    best_t = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        gap2, he2, mir2 = sms.score_pairs_tiff((f_arr, foff), grads, None, pm, pt, blob_ptr=f_ptr)
+        dt = time.perf_counter() - t0
+        best_t = dt if best_t is None else min(best_t, dt)
+    st_t = ctx.last_stats()
+    same = bool(np.array_equal(gap2, gap) and np.array_equal(he2, he) and np.array_equal(mir2, mir))
+    n_active = int(len(np.unique(pt)))
+    out = {"pairs": int(n_pairs), "distinct_targets": n_active, "masks": n_masks,
+           "e2e": {"value": n_pairs / best, "unit": "pairs/s", "ms": best * 1e3, "h2d_bytes": int(st["h2d_bytes"]),
+                   "h2d_gbs": st["h2d_bytes"] / best / 1e9},
+           "e2e_tiff": {"value": n_pairs / best_t, "unit": "pairs/s", "ms": best_t * 1e3, "h2d_bytes": int(st_t["h2d_bytes"]),
+                        "h2d_gbs": st_t["h2d_bytes"] / best_t / 1e9, "equals_pixel_call": same},
+           "pair_kernel_ms": st["match_kernel_ms"], "pair_kernel_pairs_per_s": n_pairs / (st["match_kernel_ms"] * 1e-3),
+           "mask_prep_ms_per_mask": prep_s / n_masks * 1e3, "mask_prep_h2d_bytes_per_mask": 3 * W * H,
+           "what": "pairs = top-300 isMatch targets per mask from this run's pixel-match search, targets < %d; only targets with pairs are "
+                   "uploaded (RGB or TIFF file + gray16 gradient), zgap dilation + slice planes + pair kernel per window of 32 targets" % t_limit}
+    sms.close()
+    del targets, grads
+    for q in (t_ptr, g_ptr, m_ptr, f_ptr):
+        ctx.host_free(q)
+    return out
+
+
 def data_dependence(ctx, masks_synth, n_masks=1000, n_targets=1024, reps=3):
     """The candidate kernel's speed depends on the data (its ticket tests skip mask tiles where the target has nothing in that
     colour sector), so the headline workload is not the whole story.  Two more settings at reduced size, each with its own
@@ -670,6 +745,10 @@ def main():
         }
         if not args.no_shape and world == 1:
             line["shape"] = shape_bench(ctx)
+            try:
+                line["shape"]["config2_mix"] = shape_config2_mix(ctx, last, M, t_first, min(T, 4096))
+            except Exception as e:      # reporting only
+                line["shape"]["config2_mix"] = {"error": repr(e)}
         if not args.no_data_dependence and world == 1:
             try:
                 line["data_dependence"] = data_dependence(ctx, masks_host)

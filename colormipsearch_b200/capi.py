@@ -515,6 +515,13 @@ class ShapeMaskSet:
         _check(lib().cds_shape_maskset_add_rgb(self.h, _ptr(rgb), n, qm.ctypes.data_as(_i64p), he.ctypes.data_as(_i64p)), self.ctx.h)
         return qm, he
 
+    def add_rgb_ptr(self, ptr, n):
+        """masks already laid out as uint8[n][H][W][3] at a raw host address (e.g. pinned memory from Context.host_alloc)"""
+        qm = np.zeros(n, np.int64)
+        he = np.zeros(n, np.int64)
+        _check(lib().cds_shape_maskset_add_rgb(self.h, ptr, int(n), qm.ctypes.data_as(_i64p), he.ctypes.data_as(_i64p)), self.ctx.h)
+        return qm, he
+
     def __len__(self):
         return lib().cds_shape_maskset_size(self.h)
 

@@ -23,7 +23,9 @@
 #include "cds_cand.cuh"
 #include "cds_ptx.cuh"
 
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 namespace cds {
 
@@ -53,7 +55,10 @@ struct CandParams {
     int *acc;                       // [grid][GROUP][2 * offsets] match counters, zero between work items
     int debug_skip;                 // profiling aid (CDSGPU_CAND_NULL): consumers skip the tickets, only the band pipeline runs
     int ticket_skip;                // the lists are in bucket order: a ticket whose occupancy words are all empty is not scanned
+    int wait_mode;                  // how a warp waits for a band: 0 polls try_wait, 1 try_wait with a suspend-time hint, 2 test_wait + nanosleep
+    long long *trace;               // profiling aid (CDSGPU_CAND_TRACE): SM clock of CTA 0's first items, [item][band][32 warps][2] (+ producer in slot 31)
 };
+constexpr int kTraceItems = 8;
 
 template <int NRINGS> struct Offsets;
 template <> struct Offsets<0> { static constexpr int N = 1; };
@@ -148,10 +153,10 @@ __device__ __forceinline__ uint32_t select_bit(uint32_t c, uint32_t r, const uin
 
 // First half of an evaluation: the candidate's palette reference (palette index | 0x8000 for the second interval), an L2
 // access whose latency the caller hides behind the evaluation of the previous batch.
-__device__ __forceinline__ uint32_t fetch_palette_ref(uint2 cand, bool live, const uint16_t *__restrict__ lpal)
+__device__ __forceinline__ uint32_t fetch_palette_ref(uint2 cand, bool live, const uint16_t *__restrict__ lpal, uint64_t policy)
 {
     uint32_t pr = CDS_PALETTE_SIZE - 1;                                         // the never-matching entry
-    if (live) pr = __ldg(lpal + cand.y);
+    if (live) pr = policy ? ldg_hint_u16(lpal + cand.y, policy) : (uint32_t) __ldg(lpal + cand.y);
     return pr;
 }
 
@@ -177,7 +182,7 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const u
     EvalUnroll<NRINGS, 0>::count(cw, acc, lo, len);
 }
 
-template <int NRINGS, int GROUP, int NCW>
+template <int NRINGS, int GROUP, int NCW, bool HINT>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(const CandParams p)
 {
     constexpr int NS = Offsets<NRINGS>::N;            // shift offsets = variants per orientation
@@ -206,6 +211,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pitch = p.g.pitch, H = p.g.H, R = p.rows_per_band, NB = p.n_bands;
     const long long n_items = (long long) p.n_groups * p.n_targets;
+    const uint64_t pol_stream = HINT ? l2_policy_evict_first() : 0ull, pol_keep = HINT ? l2_policy_evict_last() : 0ull;
+    long long *const trace = blockIdx.x == 0 ? p.trace : nullptr;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) {
@@ -245,6 +252,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     uint2 range = make_uint2(0u, 0u);
                     if (!done) range = make_uint2(__ldg(gstart + y0 / 4), __ldg(gstart + (y1 + 3) / 4));     // tile rows of the band; issued before the wait below
                     if (q >= kStages) mbar_wait(smem_u32(s_empty + stage), ((q >> 1) - 1) & 1);
+                    if (trace && iseq < (uint32_t) kTraceItems) trace[(((size_t) iseq * kMaxBands + b) * 32 + 31) * 2] = clock64();
                     s_next[stage] = 0;
                     s_band[stage] = range;
                     if (b == 0) s_item[iseq & 1] = done ? -1 : w;
@@ -255,8 +263,13 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     const uint32_t bbytes = (uint32_t) (((y1 - y0 + 3) / 4) * rowpitch) * 4u;
                     const uint32_t *bsrc = p.occ + ((size_t) t * occupancy_tile_rows(H) + y0 / 4) * rowpitch;
                     mbar_expect_tx(bar, bytes + bbytes);
-                    bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
-                    bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
+                    if (HINT) {
+                        bulk_load_hint(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar, pol_stream);
+                        bulk_load_hint(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar, pol_stream);
+                    } else {
+                        bulk_load(smem_u32(s_stage + (size_t) stage * stage_stride), src, bytes, bar);
+                        bulk_load(smem_u32(s_bits + (size_t) stage * bits_words), bsrc, bbytes, bar);
+                    }
                 }
                 if (done) break;
                 iseq++;
@@ -276,8 +289,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const uint32_t mywq_addr = smem_u32(mywq);
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int *acc_base = s_acc;
+    auto wait_full = [&](uint32_t qq) {
+        if (p.wait_mode == 0) mbar_wait(smem_u32(s_full + (qq & 1)), (qq >> 1) & 1);
+        else mbar_wait_parked(smem_u32(s_full + (qq & 1)), (qq >> 1) & 1, p.wait_mode);
+    };
     for (;;) {
-        mbar_wait(smem_u32(s_full + (q & 1)), (q >> 1) & 1);
+        wait_full(q);
         const long long w = *reinterpret_cast<volatile long long *>(s_item + (iseq & 1));
         if (w < 0) break;
         const int gi = (int) (w / p.n_targets);
@@ -299,7 +316,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
 
         for (int b = 0; b < NB; b++, q++) {
             const int stage = q & 1;
-            if (b > 0) mbar_wait(smem_u32(s_full + stage), (q >> 1) & 1);
+            if (b > 0) wait_full(q);
+            if (trace && iseq < (uint32_t) kTraceItems && lane == 0) trace[(((size_t) iseq * kMaxBands + b) * 32 + warp) * 2] = clock64();
             const uint32_t *band = s_stage + (size_t) stage * stage_stride;
             const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - (size_t) (b * R / 4) * rowpitch;   // indexed by the entries' absolute occupancy word index
             const int y0 = b * R;
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             bool pend = false;
             auto run_pending = [&]() { eval_candidates<NRINGS>(pend_cand, pend_pr, band, y0, pitch, s_pal, acc_base); };
             auto submit = [&](uint2 cand, bool live) {
-                const uint32_t pr = fetch_palette_ref(cand, live, glpal);
+                const uint32_t pr = fetch_palette_ref(cand, live, glpal, pol_keep);
                 if (pend) run_pending();
                 pend_cand = cand; pend_pr = pr; pend = true;
             };
@@ -383,7 +401,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             bool wpend = false;
             auto submit_words = [&](uint2 qe, bool live) {
                 uint4 e = make_uint4(0u, 0u, 0u, 0u);
-                if (live) e = __ldg(gwords + qe.y);
+                if (live) e = HINT ? ldg_hint_v4(gwords + qe.y, pol_keep) : __ldg(gwords + qe.y);
                 if (wpend) peel(wpend_c, wpend_e);
                 wpend_c = live ? qe.x : 0u; wpend_e = e; wpend = true;
             };
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             auto load = [&](uint32_t jt) -> uint2 {                     // this lane's entry of ticket jt: {bits, occupancy word index}
                 const uint32_t i = (jt << 5) + (uint32_t) lane;
                 uint2 w = idle;
-                if (i >= range.x && i < range.y) w = __ldg(reinterpret_cast<const uint2 *>(gwords + i));
+                if (i >= range.x && i < range.y) w = HINT ? ldg_hint_v2(gwords + i, pol_keep) : __ldg(reinterpret_cast<const uint2 *>(gwords + i));
                 return w;
             };
             for (;;) {
@@ -437,8 +455,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 if (k < n_tk) {
                     // tickets cut by the band's ends take the band's bound (their neighbours belong to other tile rows)
                     uint32_t o_lo = band_lo, o_hi = band_hi;
-                    if ((jt << 5) >= range.x) o_lo = max(band_lo, __ldg(gtocc + jt));
-                    if (((jt + 1u) << 5) < range.y) o_hi = min(band_hi, __ldg(gtocc + jt + 1u));
+                    if ((jt << 5) >= range.x) o_lo = max(band_lo, HINT ? ldg_hint_u32(gtocc + jt, pol_keep) : __ldg(gtocc + jt));
+                    if (((jt + 1u) << 5) < range.y) o_hi = min(band_hi, HINT ? ldg_hint_u32(gtocc + jt + 1u, pol_keep) : __ldg(gtocc + jt + 1u));
                     if (!p.ticket_skip) {
                         pass = true;
                     } else {
@@ -503,6 +521,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             if (pend) run_pending();
             // this warp is done with the stage: let the producer refill it
             __syncwarp();
+            if (trace && iseq < (uint32_t) kTraceItems && lane == 0) trace[(((size_t) iseq * kMaxBands + b) * 32 + warp) * 2 + 1] = clock64();
             if (lane == 0) mbar_arrive(smem_u32(s_empty + stage));
         }
 
@@ -580,17 +599,39 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     p.debug_skip = debug_skip;
     static const int no_skip = env_int("CDSGPU_CAND_NOSKIP", 0);
     p.ticket_skip = no_skip ? 0 : 1;
+    p.wait_mode = cand_tuning().wait_mode;
+    const int hint = cand_tuning().l2_hint;
+    static const char *trace_path = std::getenv("CDSGPU_CAND_TRACE");
+    p.trace = nullptr;
+    const size_t trace_bytes = (size_t) kTraceItems * kMaxBands * 32 * 2 * sizeof(long long);
+    if (trace_path) {
+        cudaMalloc(&p.trace, trace_bytes);
+        cudaMemsetAsync(p.trace, 0, trace_bytes, s);
+    }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     long long n_items = (long long) p.n_groups * n_targets;
     int grid = (int) std::min<long long>(std::min(n_sm, 256), n_items);
     void (*kern)(const CandParams) = nullptr;
     const int rings = xy_shift / 2;
-    if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW>;
-    else if (rings == 1) kern = pixelmatch_cand_kernel<1, GROUP, NCW>;
-    else kern = pixelmatch_cand_kernel<2, GROUP, NCW>;
+    if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW, false>;
+    else if (rings == 1) kern = hint ? pixelmatch_cand_kernel<1, GROUP, NCW, true> : pixelmatch_cand_kernel<1, GROUP, NCW, false>;
+    else kern = pixelmatch_cand_kernel<2, GROUP, NCW, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem_bytes);
     kern<<<grid, (NCW + 1) * 32, c.smem_bytes, s>>>(p);
+    if (p.trace) {
+        // profiling aid: dump the clocks (this synchronises the stream)
+        std::vector<long long> h(trace_bytes / sizeof(long long));
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h.data(), p.trace, trace_bytes, cudaMemcpyDeviceToHost);
+        cudaFree(p.trace);
+        if (FILE *f = std::fopen(trace_path, "wb")) {
+            const int hdr[4] = {kTraceItems, kMaxBands, c.n_bands, NCW};
+            std::fwrite(hdr, sizeof hdr, 1, f);
+            std::fwrite(h.data(), 1, trace_bytes, f);
+            std::fclose(f);
+        }
+    }
     return 1;
 }
 
@@ -796,6 +837,12 @@ __global__ void __launch_bounds__(256) words_tocc_kernel(const uint4 *__restrict
 
 }  // namespace
 
+CandTuning &cand_tuning()
+{
+    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 0), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31)};
+    return t;
+}
+
 void launch_words_tocc(const uint4 *words, uint32_t n_entries, uint32_t *tocc, cudaStream_t s)
 {
     const uint32_t n = words_tocc_count(n_entries);
@@ -869,8 +916,7 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     cudaMemsetAsync(scratch.acc, 0, kMatchAccBytes, s);
     // tuning knob (default picked from profiles/): consumer warps per CTA.  More warps need more
     // shared memory for their queues; when the band stages no longer fit (xyShift 4: 34 accumulators per mask) fewer are used.
-    static const int warps_env = env_int("CDSGPU_CAND_WARPS", 31);
-    int warps = warps_env;
+    int warps = cand_tuning().warps;
     if (warps >= 31 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 31).ok) warps = 28;
     if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok) warps = 24;
     if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24).ok) warps = 16;

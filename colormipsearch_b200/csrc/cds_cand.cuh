@@ -31,6 +31,15 @@ constexpr int kWordMetaMaskShift = 22;
 
 bool cand_kernel_supported(int xy_shift, const PlaneGeom &g);
 
+// Tuning knobs of the candidate kernel (process-wide; defaults from the environment, changed through cds_ctx_set_option
+// "cand_wait_mode" / "cand_l2_hint" / "cand_warps" so that one process can sweep them).
+struct CandTuning {
+    int wait_mode;      // how a consumer warp waits for a band: 0 polls try_wait, 1 try_wait with a suspend-time hint, 2 test_wait + nanosleep
+    int l2_hint;        // 1: bulk copies of the streamed planes are evict-first, loads of the group's lists evict-last
+    int warps;          // consumer warps per CTA (31, 28, 24 or 16)
+};
+CandTuning &cand_tuning();
+
 // Construction, in this order (class_tab: the device interval table of the mask set's zTolerance):
 //   launch_words_count      wcount[m][ty] / bcount[m][ty] = entries / set bits of (mask m, tile row ty); arrays are [.][tile rows + 1]
 //   launch_words_group_rows (once per array, H = tile rows) count[m][ty] -> offset of mask m inside its group's run; grow[g][ty] = run length
