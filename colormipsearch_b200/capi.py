@@ -118,6 +118,7 @@ SIGNATURES = {
     "cds_debug_encode_colors": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, _u32p]),
     "cds_debug_class_intervals": (C.c_int32, [C.c_double, C.c_int32, C.c_int32, _u32p, _u32p, _u32p, _u32p]),
     "cds_debug_slice_numbers": (C.c_int32, [_vp, _vp, C.c_int64, _u16p]),
+    "cds_debug_tiff_codes": (C.c_int32, [_vp, _vp, _i64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _u32p, _u32p]),
 }
 
 
@@ -229,6 +230,17 @@ class Context:
         out = np.empty(len(rgb), np.uint32)
         _check(lib().cds_debug_encode_colors(self.h, _ptr(rgb), len(rgb), int(data_threshold), out.ctypes.data_as(_u32p)), self.h)
         return out
+
+    def debug_tiff_codes(self, files, W, H, data_threshold, fused):
+        """-> (codes uint32[n][H][W], valid uint32[n][H][6][vp]) of the TIFF files through the fused or the two-kernel ingest path"""
+        blob, offsets = pack_files(files)
+        n = len(offsets) - 1
+        vp = (((W + 31) // 32) + 3) // 4 * 4
+        codes = np.zeros((n, H, W), np.uint32)
+        valid = np.zeros((n, H, 6, vp), np.uint32)
+        _check(lib().cds_debug_tiff_codes(self.h, _ptr(blob), offsets.ctypes.data_as(_i64p), n, W, H, int(data_threshold), int(bool(fused)),
+                                          codes.ctypes.data_as(_u32p), valid.ctypes.data_as(_u32p)), self.h)
+        return codes, valid
 
     def debug_slice_numbers(self, rgb):
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)

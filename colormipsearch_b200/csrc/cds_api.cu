@@ -299,6 +299,7 @@ extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t
             ctx->stream_chunk_tiff = value;
             return CDS_OK;
         }
+        if (std::strcmp(name, "fused_ingest") == 0) { ctx->fused_ingest = value != 0; return CDS_OK; }
         if (std::strcmp(name, "cand_wait_mode") == 0) { cand_tuning().wait_mode = (int) value; return CDS_OK; }
         if (std::strcmp(name, "cand_l2_hint") == 0) { cand_tuning().l2_hint = value != 0; return CDS_OK; }
         if (std::strcmp(name, "cand_warps") == 0) { cand_tuning().warps = (int) value; return CDS_OK; }

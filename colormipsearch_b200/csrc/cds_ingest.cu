@@ -143,6 +143,223 @@ tiff_decode_kernel(const uint8_t *__restrict__ src, const TiffStrip *__restrict_
 
 }  // namespace
 
+namespace {
+// ------------------------------------------------------------------------------------------------------------------
+// Fused ingest: PackBits / stored strips -> the library's code words and per-sector "can match" bits, with no RGB image in HBM in
+// between (the streaming search's chunks used to be decoded to RGB, written out, and read back by encode_rgb_kernel).
+//
+// One warp per strip again -- PackBits is serial in its control bytes -- but the warp owns ONE IMAGE ROW of decoded bytes in
+// shared memory instead of a window of the output image.  A colour-depth MIP is mostly black, and a black stretch is a chain of
+// zero fills: those only advance the output position (the row buffer starts out, and is left, all zero).  Literal runs and
+// non-zero fills are written into the row buffer and mark the 32-pixel chunks they touch.  When the position passes the end of
+// the row the row is emitted: the whole row of code words is written as the black code word with 128-bit stores (pad columns
+// included), then only the marked chunks are looked at -- their non-black pixels are compacted into a small queue so that the
+// colour classifier (~150 instructions) runs on full warps, and their code words and sector bits patch the row.  Work is
+// proportional to the image's content, not to its area.  Same decoding rules as tiff_decode_kernel (and the reference's
+// packBitsUncompress, ImageArrayUtils.java:229-258): decoding stops at the end of the strip's input or of its rows, whatever was
+// not produced stays black.
+__device__ __forceinline__ int fuse_classify(int r, int g, int b, int &second, int &maxv)
+{
+    if (b > r && b > g) { maxv = b; if (r > g) { second = r; return 0; } second = g; return 1; }
+    if (g > b && g > r) { maxv = g; if (b > r) { second = b; return 2; } second = r; return 3; }
+    if (r > b && r > g) { maxv = r; if (g > b) { second = g; return 4; } second = b; return 5; }
+    maxv = max(r, max(g, b));
+    second = 0;
+    return -1;
+}
+
+// the code word of cds_common.h (the same arithmetic as encode_color_dev in cds_kernels.cu; test_encode_all_16M_colours pins both
+// through searches over files == searches over pixels)
+__device__ __forceinline__ uint32_t fuse_encode(int r, int g, int b, const uint16_t *__restrict__ rank_tab, int thr, int &sector)
+{
+    int second, maxv;
+    sector = fuse_classify(r, g, b, second, maxv);
+    const uint32_t sr = sector < 0 ? (uint32_t) CDS_SR_NONE : (uint32_t) sector * CDS_SECTOR_STRIDE + __ldg(rank_tab + second * 256 + maxv);
+    uint32_t code = (sr << CDS_CODE_SR_SHIFT) | (uint32_t) maxv;
+    if (!(maxv > thr)) { code |= CDS_CODE_BELOW_BIT; sector = -1; }
+    return code;
+}
+
+constexpr int kFuseWarps = 8;
+constexpr int kFuseQueue = 64;
+
+__global__ void __launch_bounds__(kFuseWarps * 32)
+tiff_encode_kernel(const uint8_t *__restrict__ src, const TiffStrip *__restrict__ strips, int64_t n_strips, uint32_t *__restrict__ planes,
+                   PlaneGeom g, int64_t first_slot, const uint16_t *__restrict__ rank_tab, int thr, int vp,
+                   uint32_t *__restrict__ valid /* chunk-relative [n][H][sectors][vp], or nullptr */, int row_buf_bytes)
+{
+    extern __shared__ uint4 s_fuse4[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w = (int64_t) blockIdx.x * kFuseWarps + warp;
+    if (w >= n_strips) return;
+    const int valid_words = CDS_NUM_SECTORS * vp;
+    const int per_warp = row_buf_bytes + valid_words * 4 + kFuseQueue * 4;           // multiples of 16
+    uint8_t *rowbuf = reinterpret_cast<uint8_t *>(s_fuse4) + (size_t) warp * per_warp;
+    uint32_t *s_valid = reinterpret_cast<uint32_t *>(rowbuf + row_buf_bytes);
+    uint32_t *s_queue = s_valid + valid_words;
+    const uint32_t rowbuf_a = (uint32_t) __cvta_generic_to_shared(rowbuf);
+
+    const TiffStrip st = strips[w];
+    const uint8_t *__restrict__ in = src + st.src;
+    const uint32_t in_len = st.src_len, out_len = st.dst_len & ~kTiffStripPacked;
+    const bool packed = (st.dst_len & kTiffStripPacked) != 0;
+    const uint32_t row_bytes = (uint32_t) g.W * 3u;
+    const uint32_t img_bytes = row_bytes * (uint32_t) g.H;
+    const int64_t img = st.dst / img_bytes;
+    int y = (int) ((st.dst % img_bytes) / row_bytes);                                 // strips and stored pieces are whole rows
+    const int y_end = y + (int) (out_len / row_bytes);
+    const uint32_t black = (uint32_t) CDS_SR_NONE << CDS_CODE_SR_SHIFT | (0 > thr ? 0u : CDS_CODE_BELOW_BIT);
+
+    for (int k = lane; k < (row_buf_bytes + valid_words * 4) / 16; k += 32) reinterpret_cast<uint4 *>(rowbuf)[k] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+
+    uint32_t dirty_lo = 0, dirty_hi = 0;           // 32-pixel chunks of the current row that hold decoded non-zero bytes (uniform)
+    uint32_t row_start = 0;                        // strip-relative output position of the current row's first byte
+    const uint32_t lt = (1u << lane) - 1u;
+
+    // One loop, one site per step (the steps are long; several inlined copies of them would not fit the instruction cache):
+    //   (1) take the next run from the input -> a span [a, a + n) of decoded bytes to write (n = 0 for zero fills and no-ops),
+    //   (2) emit the rows that end at or before a (all remaining rows once the input or the strip's rows are used up),
+    //   (3) write the span into the row buffer, piece by piece where it crosses rows.
+    uint32_t pos = 0, idx = 0;
+    bool done = false;
+    while (!done) {
+        uint32_t a = pos, n = 0, from = 0, fill = 0;
+        bool literal = false;
+        if (pos < out_len && idx < in_len) {
+            if (!packed) {
+                n = min(min(in_len - idx, out_len - pos), 4096u);
+                literal = true; from = idx;
+                pos += n; idx += n;
+            } else {
+                // lane i looks at the pair (control, value) that starts at idx + 2 i
+                const uint32_t q = idx + 2 * lane;
+                const uint32_t c = q < in_len ? (uint32_t) in[q] : 0u;
+                const uint32_t v = q + 1 < in_len ? (uint32_t) in[q + 1] : 0u;
+                const uint32_t c0 = __shfl_sync(0xffffffffu, c, 0);
+                if (c0 < 128u) {
+                    const uint32_t cnt = c0 + 1u;
+                    n = min(cnt, out_len - pos);
+                    literal = true; from = idx + 1u;
+                    pos += cnt; idx += 1u + cnt;
+                } else if (c0 == 128u) {
+                    idx += 1u;
+                } else {
+                    // as many consecutive fill runs of the first pair's value as the warp can see at once
+                    const uint32_t v0 = __shfl_sync(0xffffffffu, v, 0);
+                    const uint32_t same = __ballot_sync(0xffffffffu, c > 128u && v == v0 && q + 1 < in_len);
+                    const uint32_t k = same == 0xffffffffu ? 32u : (uint32_t) __ffs((int) ~same) - 1u;
+                    uint32_t cnt;
+                    fill = v0;
+                    if (k == 0u) { cnt = 257u - c0; fill = 0u; idx += 2u; }                            // a fill whose value byte lies beyond the input
+                    else { cnt = __reduce_add_sync(0xffffffffu, lane < k ? 257u - c : 0u); idx += 2u * k; }
+                    if (fill != 0u) n = min(cnt, out_len - pos);
+                    pos += cnt;
+                }
+            }
+        } else {
+            done = true;
+        }
+        for (;;) {
+            const bool emit = done ? y < y_end : (n != 0u && a >= row_start + row_bytes);
+            if (emit) {
+                // ------------------------------------------------------------------ emit the current row
+                uint32_t *drow = planes + g.row_offset(first_slot + img, y);
+                // the whole row black, pad columns as pad words (the row is 16-byte aligned and a multiple of four words long)
+                for (int v4 = (int) lane; v4 < g.pitch / 4; v4 += 32) {
+                    const int x = 4 * v4;
+                    uint4 w4;
+                    w4.x = x < g.W ? black : CDS_CODE_PAD_WORD; w4.y = x + 1 < g.W ? black : CDS_CODE_PAD_WORD;
+                    w4.z = x + 2 < g.W ? black : CDS_CODE_PAD_WORD; w4.w = x + 3 < g.W ? black : CDS_CODE_PAD_WORD;
+                    reinterpret_cast<uint4 *>(drow)[v4] = w4;
+                }
+                const bool dirty = (dirty_lo | dirty_hi) != 0u;
+                if (dirty) {
+                    __syncwarp();                  // the black words above are ordered before the patches below
+                    // non-black pixels of the marked chunks -> queue -> colour classifier on full warps
+                    uint32_t qh = 0, qt = 0;
+                    uint32_t m = dirty_lo;
+                    int cbase = 0;
+                    for (;;) {
+                        bool more = true;
+                        if (m == 0u) {
+                            if (cbase == 0) { m = dirty_hi; cbase = 32; }
+                            if (m == 0u) more = false;
+                        }
+                        if (more) {
+                            const int c = (__ffs((int) m) - 1) + cbase;
+                            m &= m - 1;
+                            const int x = 32 * c + (int) lane;
+                            bool lit = false;
+                            if (x < g.W) lit = (rowbuf[3 * x] | rowbuf[3 * x + 1] | rowbuf[3 * x + 2]) != 0;
+                            const unsigned bal = __ballot_sync(0xffffffffu, lit);
+                            if (lit) s_queue[(qt + (uint32_t) __popc(bal & lt)) & (kFuseQueue - 1)] = (uint32_t) x;
+                            qt += (uint32_t) __popc(bal);
+                            __syncwarp();
+                        }
+                        // classify when 32 pixels wait (or, after the last chunk, whatever is left)
+                        while (qt - qh >= 32u || (!more && qt != qh)) {
+                            const uint32_t nq = min(32u, qt - qh);
+                            if (lane < nq) {
+                                const int x = (int) s_queue[(qh + lane) & (kFuseQueue - 1)];
+                                const uint8_t *px = rowbuf + 3 * x;
+                                int sector;
+                                const uint32_t code = fuse_encode(px[0], px[1], px[2], rank_tab, thr, sector);
+                                drow[x] = code;
+                                if (valid && sector >= 0) atomicOr(&s_valid[sector * vp + (x >> 5)], 1u << (x & 31));
+                            }
+                            qh += nq;
+                            __syncwarp();
+                        }
+                        if (!more) break;
+                    }
+                }
+                if (valid) {
+                    uint4 *vout = reinterpret_cast<uint4 *>(valid + ((size_t) img * g.H + y) * valid_words);
+                    for (int k = (int) lane; k < valid_words / 4; k += 32) vout[k] = reinterpret_cast<const uint4 *>(s_valid)[k];
+                }
+                if (dirty) {
+                    __syncwarp();
+                    for (int k = (int) lane; k < (row_buf_bytes + valid_words * 4) / 16; k += 32) reinterpret_cast<uint4 *>(rowbuf)[k] = make_uint4(0u, 0u, 0u, 0u);
+                    __syncwarp();
+                }
+                dirty_lo = dirty_hi = 0u;
+                y++;
+                row_start += row_bytes;
+                continue;
+            }
+            if (n == 0u) break;
+            // ---------------------------------------------------------------------- write the piece of the span inside this row
+            const uint32_t off = a - row_start;
+            const uint32_t take = min(n, row_bytes - off);
+            for (uint32_t i = lane; i < take; i += 32) {
+                uint32_t b = fill;
+                if (literal) b = from + i < in_len ? (uint32_t) in[from + i] : 0u;
+                asm volatile("st.shared.u8 [%0], %1;" :: "r"(rowbuf_a + off + i), "r"(b) : "memory");
+            }
+            const uint32_t c0 = off / 96u, c1 = (off + take - 1u) / 96u;                 // chunk = 32 pixels = 96 bytes
+            for (uint32_t c = c0; c <= c1; c++) { if (c < 32u) dirty_lo |= 1u << c; else dirty_hi |= 1u << (c - 32u); }
+            a += take; n -= take; from += take;
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace
+
+void cds::launch_tiff_encode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint32_t *planes, PlaneGeom g, int64_t first_slot,
+                             const uint16_t *rank_tab, int data_threshold, uint32_t *valid, cudaStream_t s)
+{
+    if (n_strips <= 0) return;
+    const int vp = occupancy_valid_pitch(g.W);
+    const int row_buf = (g.W * 3 + 15) / 16 * 16;
+    const size_t smem = (size_t) kFuseWarps * (row_buf + CDS_NUM_SECTORS * vp * 4 + kFuseQueue * 4);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(tiff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    const int64_t blocks = (n_strips + kFuseWarps - 1) / kFuseWarps;
+    tiff_encode_kernel<<<(unsigned) blocks, kFuseWarps * 32, smem, s>>>(src, strips, n_strips, planes, g, first_slot, rank_tab, data_threshold, vp, valid, row_buf);
+}
+
 void cds::launch_tiff_decode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint8_t *dst_rgb, cudaStream_t s)
 {
     if (n_strips <= 0) return;
@@ -305,5 +522,63 @@ extern "C" cds_status cds_maskset_add_tiff(cds_maskset *ms, const uint8_t *blob,
         return maskset_append(ms, n, mask_size_out, [&](int i0, int cnt, uint8_t *stage, cudaStream_t stream) -> cds_status {
             return ingest_chunk(ctx, "cds_maskset_add_tiff", blob, offsets, i0, cnt, W, H, d_comp, comp_cap, d_strips, strips_cap, stage, stream, strips);
         });
+    });
+}
+
+
+// Test hook: n TIFF files -> the code planes (and per-sector valid bits) a streaming search would build from them, through either
+// ingest path, so that the fused kernel can be compared word for word with decode + encode and with the encoder's colour table.
+extern "C" cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n, int32_t width, int32_t height,
+                                           int32_t data_threshold, int32_t fused, uint32_t *codes_out, uint32_t *valid_out)
+{
+    return cds::abi_guard("cds_debug_tiff_codes", [&]() -> cds_status {
+        if (!ctx) { set_tls_error("cds_debug_tiff_codes: NULL context"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || width <= 0 || height <= 0 || width > 2048 || height > 16384) return ctx->fail(CDS_ERR_BAD_ARG, "cds_debug_tiff_codes: bad size");
+        if (n == 0) return CDS_OK;
+        if (!blob || !offsets || !codes_out) return ctx->fail(CDS_ERR_BAD_ARG, "cds_debug_tiff_codes: NULL argument");
+        DevState &ds = ctx->devs[0];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        PlaneGeom g;
+        g.W = width; g.H = height; g.pitch = choose_pitch(width); g.guard = CDS_GUARD_ROWS;
+        const int vp = occupancy_valid_pitch(width);
+        const size_t img_bytes = (size_t) width * height * 3;
+        const size_t valid_words = (size_t) height * CDS_NUM_SECTORS * vp;
+        uint8_t *d_comp = nullptr, *d_rgb = nullptr;
+        TiffStrip *d_strips = nullptr;
+        uint32_t *d_planes = nullptr, *d_valid = nullptr;
+        auto release = [&]() { cudaStreamSynchronize(ds.stream); for (void *p : {(void *) d_comp, (void *) d_rgb, (void *) d_strips, (void *) d_planes, (void *) d_valid}) ds.pool.free(p); };
+        struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
+        std::vector<TiffStrip> strips;
+        std::string err;
+        for (int64_t i = 0; i < n; i++) {
+            const int64_t a = offsets[i], b = offsets[i + 1];
+            if (a < 0 || b < a) return ctx->fail(CDS_ERR_BAD_ARG, "cds_debug_tiff_codes: offsets must be non-decreasing");
+            cds_status st = tiff_collect_strips(blob + a, (size_t) (b - a), width, height, (uint64_t) (a - offsets[0]), (uint64_t) i * img_bytes, strips, err, fused != 0);
+            if (st != CDS_OK) return ctx->fail(st, "cds_debug_tiff_codes: file " + std::to_string(i) + ": " + err);
+        }
+        const size_t comp_bytes = (size_t) (offsets[n] - offsets[0]);
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_comp, comp_bytes + 64));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_strips, strips.size() * sizeof(TiffStrip) + 16));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_planes, g.total_words(n) * sizeof(uint32_t)));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_valid, (size_t) n * valid_words * sizeof(uint32_t)));
+        if (!fused) CDS_CUDA(ctx, ds.pool.alloc((void **) &d_rgb, (size_t) n * img_bytes + 64));
+        CDS_CUDA(ctx, cudaMemcpyAsync(d_comp, blob + offsets[0], comp_bytes, cudaMemcpyHostToDevice, ds.stream));
+        CDS_CUDA(ctx, cudaMemcpyAsync(d_strips, strips.data(), strips.size() * sizeof(TiffStrip), cudaMemcpyHostToDevice, ds.stream));
+        launch_fill_words(d_planes, g.total_words(n), CDS_CODE_PAD_WORD, ds.stream);
+        if (fused) {
+            launch_tiff_encode(d_comp, d_strips, (int64_t) strips.size(), d_planes, g, 0, ds.d_rank_tab, data_threshold, d_valid, ds.stream);
+        } else {
+            CDS_CUDA(ctx, cudaMemsetAsync(d_rgb, 0, (size_t) n * img_bytes, ds.stream));
+            launch_tiff_decode(d_comp, d_strips, (int64_t) strips.size(), d_rgb, ds.stream);
+            launch_encode_rgb(d_rgb, n, d_planes, g, 0, ds.d_rank_tab, data_threshold, ds.stream, d_valid);
+        }
+        CDS_CUDA(ctx, cudaGetLastError());
+        for (int64_t i = 0; i < n; i++)
+            CDS_CUDA(ctx, cudaMemcpy2DAsync(codes_out + (size_t) i * width * height, (size_t) width * 4, d_planes + g.row_offset(i, 0), (size_t) g.pitch * 4,
+                                           (size_t) width * 4, (size_t) height, cudaMemcpyDeviceToHost, ds.stream));
+        if (valid_out) CDS_CUDA(ctx, cudaMemcpyAsync(valid_out, d_valid, (size_t) n * valid_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds.stream));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        return CDS_OK;
     });
 }

@@ -110,6 +110,7 @@ struct cds_ctx {
     int match_kernel = 0;      // cds_ctx_set_option("match_kernel"): 0 automatic, 1 candidate, 2 band, 3 gather
     int resident_occupancy = 1;   // cds_ctx_set_option("resident_occupancy"): 0 = always build occupancy bitmaps per target chunk
     int64_t stream_chunk = 256;   // cds_ctx_set_option("stream_chunk"): targets per chunk of cds_search_stream_rgb
+    int fused_ingest = 1;         // cds_ctx_set_option("fused_ingest"): 1 = TIFF strips go straight to code words (tiff_encode_kernel), 0 = decode to RGB, then encode
     int64_t stream_chunk_tiff = 1024;   // cds_ctx_set_option("stream_chunk_tiff"): targets per chunk of cds_search_stream_tiff
 
     cds_status fail(cds_status code, const std::string &msg) const;

@@ -30,6 +30,7 @@
 //     context; the shape mask data is replicated like the pixel-match masks (pairs go to the device that holds the target).
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <memory>
 #include <numeric>
 #include <vector>
@@ -316,7 +317,10 @@ __global__ void __launch_bounds__(256) shape_target_derive_kernel(const uint8_t 
     if (tid <= rows) s_rowpre[tid] = 0;
     __syncthreads();
 
-    // ---- stage: one pixel pair per thread and step
+    // ---- stage: one pixel pair per thread and step (only tiles that touch a label rectangle test their pixels against them)
+    bool near_rects = false;
+    for (int i = 0; i < rects.n; i++)
+        near_rects |= rects.x0[i] < xin + 2 * kZgWords && rects.x1[i] > xin && rects.y0[i] < yin + rows && rects.y1[i] > yin;
     int any = 0;
     for (int i = tid; i < rows * kZgWords; i += 256) {
         const int row = i / kZgWords, j = i % kZgWords;
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(256) shape_target_derive_kernel(const uint8_t 
                 const int xx = x + e;
                 if (xx < 0 || xx >= W) continue;
                 const int r = p[3 * e], g = p[3 * e + 1], b = p[3 * e + 2];
-                const bool keep = !shape_in_rects(rects, xx, y) && (r > threshold || g > threshold || b > threshold);
+                const bool keep = (r > threshold || g > threshold || b > threshold) && !(near_rects && shape_in_rects(rects, xx, y));
                 if (!keep) continue;
                 wr |= (uint32_t) r << (16 * e); wg |= (uint32_t) g << (16 * e); wb |= (uint32_t) b << (16 * e);
                 const int sx = xx - x0, sy = y - y0;
@@ -1022,7 +1026,7 @@ extern "C" cds_status cds_debug_slice_numbers(cds_ctx *ctx, const uint8_t *rgb, 
 
 namespace {
 
-constexpr int64_t kShapeWindow = 32;      // targets per window
+constexpr int64_t kShapeWindowSmall = 32, kShapeWindowLarge = 128;      // targets per window: large calls use large windows (pair-kernel launches that fill the GPU)
 
 // What one device holds while it works through its windows.
 struct ShapeDevWork {
@@ -1091,7 +1095,7 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
     const size_t px = (size_t) W * H, bytes = px * 3;
     const size_t bm_words = (size_t) H * bpitch;
     const int D = (int) ctx->devs.size();
-    const int64_t win = kShapeWindow;
+    const int64_t win = (int64_t) active.size() >= 4 * kShapeWindowLarge * D ? kShapeWindowLarge : kShapeWindowSmall;
     const int64_t n_windows = ((int64_t) active.size() + win - 1) / win;
     const int used = (int) std::min<int64_t>(D, n_windows);
     const DiscSpec disc10 = make_disc(10);
@@ -1114,8 +1118,17 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
     }
 
     std::vector<std::unique_ptr<PoolGuard>> guards;
+    // files: one upload of the window's file bytes (run by run), ONE strip table and ONE decode launch per window; the tables go
+    // through two pinned host slots per device
     size_t comp_cap = 0, strips_cap = 0;
-    if (from_files) ingest_bounds(offsets, n_targets, win, W, H, comp_cap, strips_cap);
+    if (from_files) {
+        for (int64_t w = 0; w < n_windows; w++) {
+            size_t sum = 0;
+            for (int64_t a = w * win; a < std::min<int64_t>((int64_t) active.size(), (w + 1) * win); a++) sum += (size_t) (offsets[active[a] + 1] - offsets[active[a]]);
+            comp_cap = std::max(comp_cap, sum + 64);
+        }
+        strips_cap = (size_t) win * tiff_strips_bound(W, H);
+    }
     for (int d = 0; d < used; d++) {
         DevState &ds = ctx->devs[d];
         ShapeDevWork &wk = work[d];
@@ -1146,6 +1159,7 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
         if (from_files) {
             SH_CUDA(ctx, g.alloc((void **) &wk.d_comp, comp_cap));
             SH_CUDA(ctx, g.alloc((void **) &wk.d_strips, strips_cap * sizeof(TiffStrip)));
+            SH_TRY(ctx->ensure_pinned(ds, 2 * strips_cap * sizeof(TiffStrip)));
         }
         const size_t np = wk.pm.size();
         SH_CUDA(ctx, g.alloc((void **) &wk.d_pm, np * sizeof(int32_t)));
@@ -1175,13 +1189,25 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
         const int64_t a0 = w * win, a1 = std::min<int64_t>((int64_t) active.size(), a0 + win);
         SH_CUDA(ctx, cudaSetDevice(ds.dev));
         if (j >= 2) SH_CUDA(ctx, cudaStreamWaitEvent(ds.copy_stream, ds.up_free[slot], 0));
+        strips.clear();
+        size_t comp_off = 0;
         for (int64_t a = a0; a < a1;) {
             int64_t e = a + 1;
             while (e < a1 && active[e] == active[e - 1] + 1) e++;
             const int64_t t0 = active[a], cnt = e - a, s0 = a - a0;
             if (from_files) {
-                SH_TRY(ingest_chunk(ctx, "cds_shape_score_pairs_tiff", blob, offsets, t0, cnt, W, H, wk.d_comp, comp_cap, wk.d_strips, strips_cap,
-                                    wk.d_t[slot] + (size_t) s0 * bytes, ds.copy_stream, strips));
+                std::string err;
+                for (int64_t i = 0; i < cnt; i++) {
+                    const int64_t fa = offsets[t0 + i], fb = offsets[t0 + i + 1];
+                    cds_status fs = tiff_collect_strips(blob + fa, (size_t) (fb - fa), W, H, (uint64_t) (comp_off + (size_t) (fa - offsets[t0])),
+                                                        (uint64_t) (s0 + i) * bytes, strips, err);
+                    if (fs != CDS_OK) return ctx->fail(fs, "cds_shape_score_pairs_tiff: file " + std::to_string(t0 + i) + ": " + err);
+                }
+                const size_t run_bytes = (size_t) (offsets[t0 + cnt] - offsets[t0]);
+                if (comp_off + run_bytes > comp_cap || strips.size() > strips_cap) return ctx->fail(CDS_ERR_CAPACITY, "cds_shape_score_pairs_tiff: internal staging too small");
+                SH_CUDA(ctx, cudaMemcpyAsync(wk.d_comp + comp_off, blob + offsets[t0], run_bytes, cudaMemcpyHostToDevice, ds.copy_stream));
+                ctx->stats.h2d_bytes += (int64_t) run_bytes;
+                comp_off += run_bytes;
             } else {
                 SH_CUDA(ctx, cudaMemcpyAsync(wk.d_t[slot] + (size_t) s0 * bytes, target_rgb + (size_t) t0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, ds.copy_stream));
                 ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
@@ -1193,6 +1219,16 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
                 ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
             }
             a = e;
+        }
+        if (from_files) {
+            TiffStrip *h_tab = (TiffStrip *) ds.h_pinned + (size_t) slot * strips_cap;
+            if (j >= 2) SH_CUDA(ctx, cudaEventSynchronize(ds.up_done[slot]));      // the slot's previous table has left the host
+            memcpy(h_tab, strips.data(), strips.size() * sizeof(TiffStrip));
+            SH_CUDA(ctx, cudaMemcpyAsync(wk.d_strips, h_tab, strips.size() * sizeof(TiffStrip), cudaMemcpyHostToDevice, ds.copy_stream));
+            ctx->stats.h2d_bytes += (int64_t) (strips.size() * sizeof(TiffStrip));
+            launch_tiff_decode(wk.d_comp, wk.d_strips, (int64_t) strips.size(), wk.d_t[slot], ds.copy_stream);
+            ctx->stats.kernel_launches++;
+            SH_CUDA(ctx, cudaGetLastError());
         }
         SH_CUDA(ctx, cudaEventRecord(ds.up_done[slot], ds.copy_stream));
         return CDS_OK;

@@ -228,6 +228,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
 
     size_t tiff_comp_bytes = 0;
     std::vector<TiffStrip> strips;
+    const bool fused_ingest = ctx->fused_ingest != 0 && g.W <= 2048;      // the fused kernel marks 32-pixel chunks in a 64-bit mask
     if (tiff) {
         if ((uint64_t) chunk * img_bytes > 0xF0000000ull) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_search_stream_tiff: stream_chunk too large for this image size");
         for (const Chunk &ch : plan) {
@@ -310,7 +311,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             for (int64_t i = 0; i < cnt; i++) {
                 const int64_t a = tiff->offsets[first + i], b = tiff->offsets[first + i + 1];
                 if (b < a) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_tiff: offsets must be non-decreasing");
-                cds_status st = tiff_collect_strips(tiff->blob + a, (size_t) (b - a), g.W, g.H, (uint64_t) (a - base), (uint64_t) i * img_bytes, strips, err);
+                cds_status st = tiff_collect_strips(tiff->blob + a, (size_t) (b - a), g.W, g.H, (uint64_t) (a - base), (uint64_t) i * img_bytes, strips, err, fused_ingest);
                 if (st != CDS_OK) return ctx->fail(st, "cds_search_stream_tiff: file " + std::to_string(first + i) + ": " + err);
             }
             CDS_TRY(ensure_tiff_bufs(ctx, ds, tiff_comp_bytes, strips.size()));
@@ -323,11 +324,18 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             ctx->stats.h2d_bytes += (int64_t) bytes + (int64_t) (strips.size() * sizeof(TiffStrip));
             CDS_CUDA(ctx, cudaEventRecord(sb.h2d_done[slot], sb.copy_stream));
             CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
-            // decode into one RGB area (stream order protects it), then the usual encoder
-            launch_tiff_decode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.staging[0], ds.stream);
-            launch_encode_rgb(sb.staging[0], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream, want_occ ? sb.valid : nullptr);
+            if (fused_ingest) {
+                // strips -> code words + per-sector valid bits in one kernel, no RGB image in HBM in between
+                launch_tiff_encode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.planes, g, 0, ds.d_rank_tab, thr,
+                                   want_occ ? sb.valid : nullptr, ds.stream);
+                ctx->stats.kernel_launches += 1;
+            } else {
+                // decode into one RGB area (stream order protects it), then the usual encoder
+                launch_tiff_decode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.staging[0], ds.stream);
+                launch_encode_rgb(sb.staging[0], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream, want_occ ? sb.valid : nullptr);
+                ctx->stats.kernel_launches += 2;
+            }
             CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ds.stream));
-            ctx->stats.kernel_launches += 2;
         } else {
             if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
             CDS_CUDA(ctx, cudaMemcpyAsync(sb.staging[slot], targets_rgb + (size_t) first * img_bytes, (size_t) cnt * img_bytes,

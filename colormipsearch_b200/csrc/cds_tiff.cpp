@@ -142,7 +142,7 @@ cds_status tiff_parse(const uint8_t *file, size_t len, cds_tiff_info &info, std:
 }
 
 cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int height, uint64_t src_base, uint64_t dst_base,
-                               std::vector<TiffStrip> &out, std::string &err)
+                               std::vector<TiffStrip> &out, std::string &err, bool whole_rows)
 {
     cds_tiff_info info;
     std::vector<uint64_t> offs, lens;
@@ -169,8 +169,9 @@ cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int h
         if (flag) { out.push_back(TiffStrip{(uint32_t) src, (uint32_t) lens[i], (uint32_t) dst, (uint32_t) dlen | flag}); continue; }
         // stored bytes need no order: cut them into pieces so that one-strip files still spread over many warps
         const uint64_t have = std::min<uint64_t>(lens[i], dlen);
-        for (uint64_t o = 0; o < dlen; o += kTiffStoredPiece) {
-            const uint64_t piece = std::min<uint64_t>(kTiffStoredPiece, dlen - o);
+        const uint64_t step = whole_rows ? std::max<uint64_t>(1, kTiffStoredPiece / row_bytes) * row_bytes : kTiffStoredPiece;
+        for (uint64_t o = 0; o < dlen; o += step) {
+            const uint64_t piece = std::min<uint64_t>(step, dlen - o);
             const uint64_t avail = o < have ? std::min<uint64_t>(piece, have - o) : 0;
             out.push_back(TiffStrip{(uint32_t) (src + o), (uint32_t) avail, (uint32_t) (dst + o), (uint32_t) piece});
         }

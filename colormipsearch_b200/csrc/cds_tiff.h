@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/cdsgpu.h"
+#include "cds_kernels.cuh"
 
 namespace cds {
 
@@ -32,8 +33,9 @@ cds_status tiff_parse(const uint8_t *file, size_t len, cds_tiff_info &info, std:
 
 // Appends the strips of file `file` (located `src_base` bytes into the uploaded range, decoding to `dst_base`) to `out`;
 // checks that the image is width x height and decodable.  On failure `err` describes the problem.
+// whole_rows: stored (uncompressed) strips are cut into pieces of whole rows instead of kTiffStoredPiece bytes.
 cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int height, uint64_t src_base, uint64_t dst_base,
-                               std::vector<TiffStrip> &out, std::string &err);
+                               std::vector<TiffStrip> &out, std::string &err, bool whole_rows = false);
 
 }  // namespace cds
 struct cds_ctx;
@@ -46,6 +48,11 @@ cds_status ingest_chunk(cds_ctx *ctx, const char *who, const uint8_t *blob, cons
 void ingest_bounds(const int64_t *offsets, int64_t n, int64_t cnt, int W, int H, size_t &comp_cap, size_t &strips_cap);
 
 void launch_tiff_decode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint8_t *dst_rgb, cudaStream_t s);
+// Fused ingest (cds_ingest.cu): the same strips straight to code words (planes, slot first_slot + image) and, when `valid` is
+// given, the per-sector "can match" bits of every row (launch_occupancy with valid_ready).  Needs a strip table whose stored
+// pieces are whole rows (tiff_collect_strips with whole_rows = true); every row of every image must be covered by a strip.
+void launch_tiff_encode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint32_t *planes, PlaneGeom g, int64_t first_slot,
+                        const uint16_t *rank_tab, int data_threshold, uint32_t *valid, cudaStream_t s);
 
 }  // namespace cds
 #endif

@@ -94,6 +94,9 @@ int32_t    cds_abi_version(void);
  *   keep the match kernel's grid full).
  * "resident_occupancy": 1 (default) keeps a library's occupancy bitmaps on the device next to its code planes (+23 % memory) and
  * falls back to building them per target chunk inside cds_search_topk when they do not fit; 0 always builds them per chunk.
+ * "fused_ingest": 1 (default) = the streaming searches over TIFF files turn the strips straight into the library's code words;
+ * 0 = decode to RGB pixels first, then encode (the two-kernel path, kept as a cross-check).
+ * "cand_wait_mode", "cand_l2_hint", "cand_warps": tuning knobs of the candidate kernel (csrc/cds_cand.cuh), process-wide.
  * Unknown names: CDS_ERR_BAD_ARG. */
 cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t value);
 
@@ -336,6 +339,11 @@ cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out);
 cds_status cds_debug_encode_colors(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t data_threshold, uint32_t *codes_out);
 cds_status cds_debug_class_intervals(double z_tolerance, int32_t sector, int32_t rank,
                                      uint32_t *lo1, uint32_t *len1, uint32_t *lo2, uint32_t *len2);
+/* n TIFF files (blob / offsets as in cds_search_stream_tiff) -> the code words a streaming search builds from them, uint32[n][H][W]
+ * (cds_common.h), and optionally the per-sector "can match" bits uint32[n][H][6][ceil32(W) rounded up to 4 words]; fused != 0 runs
+ * the fused strip -> code-word kernel, 0 the decode + encode pair.  Lets tests compare the two ingest paths word for word. */
+cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n, int32_t width, int32_t height,
+                                int32_t data_threshold, int32_t fused, uint32_t *codes_out, uint32_t *valid_out);
 /* Slice numbers (1..256, 0 = black) of n RGB colours as the shape path computes them on the device -- a table built per device
  * with the double arithmetic of GradientAreaGapUtils.findSliceNumberInLUT (API/cds/GradientAreaGapUtils.java:18-197) -- so that the
  * table can be checked against the oracle over all 2^24 colours. */

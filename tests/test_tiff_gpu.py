@@ -264,3 +264,95 @@ def test_failed_mask_append_leaves_the_mask_set_unchanged(ctx, synth_files):
     for x, y in zip(ra, rb):
         assert np.array_equal(x, y)
     a.close(); b.close()
+
+
+def _expected_codes_and_valid(ctx, pixels, thr):
+    """Code words of decoded pixels through the colour encoder (checked against the oracle's double predicate over all 2^24
+    colours elsewhere), and the per-sector "can match" bits derived from them (cds_common.h: sector = SR / 32768 when the pixel is
+    above the threshold and has a sector)."""
+    n, Hh, Ww, _ = pixels.shape
+    codes = ctx.debug_encode_colors(pixels.reshape(-1, 3), thr).reshape(n, Hh, Ww)
+    vp = (((Ww + 31) // 32) + 3) // 4 * 4
+    sr = (codes >> 8) & 0x3FFFF
+    ok = ((codes & 0xC0000000) == 0) & (sr < 6 * 32768)
+    valid = np.zeros((n, Hh, 6, vp), np.uint32)
+    xs = np.arange(Ww)
+    for s in range(6):
+        bits = (ok & (sr // 32768 == s)).astype(np.uint32) << (xs % 32).astype(np.uint32)
+        np.add.at(valid[:, :, s, :], (slice(None), slice(None), xs // 32), bits)       # distinct bits: add == or
+    return codes, valid
+
+
+def test_fused_ingest_equals_decode_then_encode(ctx, tiffs, synth_files):
+    """tiff_encode_kernel (strips -> code words + valid bits, no RGB image in between) against decode + encode and against the
+    colour encoder applied to the oracle-decoded pixels: the reference's own files, synthetic MIPs in several strip layouts
+    (PackBits and stored), truncated and garbage strips."""
+    # the reference's colour-depth MIP files (1210 x 566, 71 PackBits strips)
+    names = ["em_12191", "em_LPLC2", "lm_GMR"]
+    files = [tiffs["file_" + k].tobytes() for k in names]
+    px = np.stack([tiffs["pixels_" + k] for k in names])
+    for thr in (20, 100, 0):
+        exp_c, exp_v = _expected_codes_and_valid(ctx, px, thr)
+        for fused in (1, 0):
+            c, v = ctx.debug_tiff_codes(files, W, H, thr, fused)
+            assert np.array_equal(c, exp_c), (thr, fused)
+            assert np.array_equal(v, exp_v), (thr, fused)
+    # synthetic MIPs: rows per strip 8 / 566 / 1 / 7, PackBits and stored
+    masks, targets, _ = synth_files
+    imgs = np.concatenate([targets[:10], masks[:2]])
+    layouts = [(8, 32773), (566, 32773), (1, 32773), (7, 32773), (8, 1), (566, 1), (3, 1)]
+    sfiles = [capi.tiff_encode_rgb(im, *layouts[i % len(layouts)]) for i, im in enumerate(imgs)]
+    exp_c, exp_v = _expected_codes_and_valid(ctx, imgs, 20)
+    for fused in (1, 0):
+        c, v = ctx.debug_tiff_codes(sfiles, W, H, 20, fused)
+        assert np.array_equal(c, exp_c) and np.array_equal(v, exp_v), fused
+    # small odd-sized images with noise (literal-heavy strips, runs that cross rows when the whole image is one strip)
+    rng = np.random.default_rng(12)
+    Ws, Hs = 333, 41
+    small = np.zeros((4, Hs, Ws, 3), np.uint8)
+    small[0] = rng.integers(0, 256, (Hs, Ws, 3))
+    small[1, 5:30, 40:200] = rng.integers(0, 256, (25, 160, 3))
+    small[2, :, ::7] = 77
+    small[3, 11] = 255
+    sf = [capi.tiff_encode_rgb(im, rps, comp) for im, (rps, comp) in zip(small, [(8, 32773), (Hs, 32773), (5, 1), (1, 32773)])]
+    exp_c, exp_v = _expected_codes_and_valid(ctx, small, 20)
+    for fused in (1, 0):
+        c, v = ctx.debug_tiff_codes(sf, Ws, Hs, 20, fused)
+        assert np.array_equal(c, exp_c) and np.array_equal(v, exp_v), fused
+
+
+def test_fused_ingest_of_truncated_and_garbage_strips(ctx):
+    """Malformed strips: both ingest paths follow the documented clamped PackBits rules (include/cdsgpu.h) and agree word for word."""
+    rng = np.random.default_rng(99)
+    Ws, Hs = 200, 24
+    files, pixels = [], []
+    for case in range(12):
+        row = Ws * 3
+        strips = []
+        for s in range(3):                       # 3 strips of 8 rows
+            n = int(rng.integers(1, 900))
+            strips.append(bytes(rng.integers(0, 256, n).astype(np.uint8)))
+        pixels.append(np.concatenate([_clamped_packbits(st, 8 * row) for st in strips]).reshape(Hs, Ws, 3))
+        # a little-endian TIFF around the strips
+        data = b"".join(strips)
+        offs, o = [], 8
+        for st in strips:
+            offs.append(o); o += len(st)
+        body = data + (b"\0" if len(data) & 1 else b"")
+        p0 = 8 + len(body)
+        extra = struct.pack("<HHH", 8, 8, 8) + struct.pack("<III", *offs) + struct.pack("<III", *[len(st) for st in strips])
+        ifd = p0 + len(extra)
+        ent = [(256, 4, 1, Ws), (257, 4, 1, Hs), (258, 3, 3, p0), (259, 3, 1, 32773), (262, 3, 1, 2), (273, 4, 3, p0 + 6), (277, 3, 1, 3),
+               (278, 4, 1, 8), (279, 4, 3, p0 + 18), (284, 3, 1, 1)]
+        d = b"II" + struct.pack("<HI", 42, ifd) + body + extra + struct.pack("<H", len(ent))
+        for tag, typ, cnt, val in ent:
+            d += struct.pack("<HHI", tag, typ, cnt) + (struct.pack("<HH", val, 0) if typ == 3 and cnt == 1 else struct.pack("<I", val))
+        d += struct.pack("<I", 0)
+        files.append(d)
+    px = np.stack(pixels)
+    got = capi.tiff_decode_rgb(ctx, files, Ws, Hs)
+    assert np.array_equal(got, px)
+    exp_c, exp_v = _expected_codes_and_valid(ctx, px, 20)
+    for fused in (1, 0):
+        c, v = ctx.debug_tiff_codes(files, Ws, Hs, 20, fused)
+        assert np.array_equal(c, exp_c) and np.array_equal(v, exp_v), fused
