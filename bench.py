@@ -105,6 +105,37 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu(gpu_index):
+    """Moves this rank onto the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE it allocates and
+    first-touches its pinned buffers, so that host->device uploads of N ranks do not all pull from one NUMA node.  Returns what
+    was found, for the JSON line.  Best effort."""
+    info = {"bound": False}
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        dev = "/sys/bus/pci/devices/%s:%s" % (dom[-4:], rest)
+        info["pci"] = dev.rsplit("/", 1)[1]
+        info["numa_node"] = int(open(dev + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or allowed
+        info["local_cpus"] = len(cpus)
+        info["host_cpus_allowed"] = len(allowed)
+        if use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+        info["cpus_used"] = len(use)
+    except Exception as e:
+        info["error"] = repr(e)
+    return info
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -466,6 +497,7 @@ def main():
     ap.add_argument("--no-e2e-tiff", action="store_true", help="skip the TIFF-file variant of the end-to-end step")
     ap.add_argument("--e2e-tiff", action="store_true", help="(default now) the TIFF-file variant of the end-to-end step runs at every N")
     ap.add_argument("--no-shape", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not move the rank onto the CPUs next to its GPU")
     ap.add_argument("--no-data-dependence", action="store_true", help="skip the real-fixture / dense-target legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -488,6 +520,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    binding = bind_to_gpu(local_rank) if not args.no_bind else {"bound": False, "disabled": True}
     from colormipsearch_b200 import capi
     ctx = capi.Context(device_ids=[local_rank])
     ctx.set_match_kernel(args.kernel)
@@ -687,6 +720,17 @@ def main():
         ctx.host_free(pool_ptr)
         ctx.host_free(mask_ptr)
 
+    # The headline end-to-end number is the step fed with the library AS THE REFERENCE STORES IT: PackBits RGB TIFF files held in
+    # (pinned) host memory, uploaded as they are and decoded on the device.  The same step fed with decoded pixels is kept next to
+    # it as e2e.rgb_pixels: it moves 16 x the bytes over PCIe and is bound by the link, not by anything this library does.
+    e2e_line = e2e
+    if e2e and "tiff" in e2e:
+        rgb = dict(e2e)
+        e2e_line = rgb.pop("tiff")
+        e2e_line["steps"] = rgb.get("steps")
+        e2e_line["targets_per_gpu"] = rgb.get("targets_per_gpu")
+        e2e_line["input"] = "masks and targets as PackBits RGB TIFF files in pinned host memory (the reference's storage format)"
+        e2e_line["rgb_pixels"] = rgb
     if rank == 0:
         peak, peak_src = measured_peak()
         per_launch_cmp = M * T / max(match_launches / args.steps, 1)
@@ -739,7 +783,7 @@ def main():
                                  "HBM copy peak).  frac_algorithmic follows SURVEY 8(d) (3*W*H bytes per comparison) and exceeds 1 because "
                                  "up to 1024 masks share one pass over a target.  The kernel is bound by instruction issue: issue_frac = "
                                  "warp instructions per comparison x comparisons/s / (148 SMs x 4 schedulers x SM clock)"},
-            "e2e": e2e,
+            "e2e": e2e_line, "host_binding": binding,
             "mask_pixels_mean": float(np.mean(mask_sizes)), "setup_s": setup_s,
             "matches_returned": int(merged[3].sum()) if merged is not None else None,
         }

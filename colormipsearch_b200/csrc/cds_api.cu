@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cctype>
+
+#include <sched.h>
 
 #include "cds_runtime.h"
 #include "cds_band.cuh"
@@ -252,6 +255,33 @@ extern "C" void cds_ctx_destroy(cds_ctx *ctx)
 
 extern "C" int32_t cds_ctx_num_devices(const cds_ctx *ctx) { return ctx ? (int32_t) ctx->devs.size() : 0; }
 
+// CPUs next to a CUDA device: /sys/bus/pci/devices/<domain:bus:device.function>/local_cpulist, e.g. "0-31,64-95"
+static bool device_local_cpus(int dev, cpu_set_t &set)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (char *c = bus; *c; c++) *c = (char) std::tolower((unsigned char) *c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE *f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    char line[1024] = {0};
+    const bool got = std::fgets(line, sizeof line, f) != nullptr;
+    std::fclose(f);
+    if (!got) return false;
+    CPU_ZERO(&set);
+    int n = 0;
+    for (const char *p = line; *p && *p != '\n';) {
+        char *end = nullptr;
+        long a = std::strtol(p, &end, 10), b = a;
+        if (end == p) break;
+        p = end;
+        if (*p == '-') { b = std::strtol(p + 1, &end, 10); p = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int) c, &set); n++; }
+        if (*p == ',') p++;
+    }
+    return n > 0;
+}
+
 extern "C" cds_status cds_host_alloc(cds_ctx *ctx, uint64_t bytes, void **out)
 {
     return cds::abi_guard("cds_host_alloc", [&]() -> cds_status {
@@ -259,7 +289,15 @@ extern "C" cds_status cds_host_alloc(cds_ctx *ctx, uint64_t bytes, void **out)
         std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         *out = nullptr;
         CDS_CUDA(ctx, cudaSetDevice(ctx->devs[0].dev));
-        CDS_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+        // Pinned pages land on the NUMA node of the allocating thread.  For the length of the allocation the thread is moved onto
+        // the CPUs next to the context's first device (sysfs local_cpulist of its PCI function), so that uploads from this buffer
+        // do not cross the socket interconnect; the previous affinity is restored afterwards.  Best effort: no sysfs entry, no move.
+        cpu_set_t before, local;
+        const bool have_before = sched_getaffinity(0, sizeof before, &before) == 0;
+        const bool moved = have_before && device_local_cpus(ctx->devs[0].dev, local) && sched_setaffinity(0, sizeof local, &local) == 0;
+        const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+        if (moved) sched_setaffinity(0, sizeof before, &before);
+        CDS_CUDA(ctx, e);
         return CDS_OK;
     });
 }
