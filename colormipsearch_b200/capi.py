@@ -117,6 +117,11 @@ SIGNATURES = {
     "cds_get_last_stats": (C.c_int32, [_vp, C.POINTER(SearchStats)]),
     "cds_debug_encode_colors": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, _u32p]),
     "cds_debug_class_intervals": (C.c_int32, [C.c_double, C.c_int32, C.c_int32, _u32p, _u32p, _u32p, _u32p]),
+    "cds_pairq_create": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "cds_pairq_destroy": (None, [_vp]),
+    "cds_pairq_score": (C.c_int32, [_vp, C.c_int32, C.c_uint64, _vp, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
+    "cds_pairq_get_stats": (C.c_int32, [_vp, _i64p, _i64p, _i64p]),
+    "cds_debug_pairq_drive": (C.c_int32, [_vp, _vp, C.c_int64, C.POINTER(C.c_uint64), _i32p, _i64p, C.c_int64, C.c_int32, _i32p, _u8p, _f64p]),
     "cds_debug_slice_numbers": (C.c_int32, [_vp, _vp, C.c_int64, _u16p]),
     "cds_debug_tiff_codes": (C.c_int32, [_vp, _vp, _i64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _u32p, _u32p]),
 }
@@ -495,6 +500,52 @@ class MaskSet:
         _check(lib().cds_score_pair_rgb(self.ctx.h, self.h, int(mask_index), _ptr(target_rgb), target_rgb.shape[1], target_rgb.shape[0],
                                         C.byref(s), C.byref(r), C.byref(m)), self.ctx.h)
         return s.value, r.value, bool(m.value)
+
+
+class PairQueue:
+    """cds_pairq_*: the reference's single-pair call (calculateMatchingScore) behind a micro-batching queue with a device-side
+    target cache.  score() blocks and may be called from many threads."""
+
+    def __init__(self, ctx, maskset, max_batch=64, max_wait_us=50, cache_targets=256):
+        self.ctx, self.ms = ctx, maskset
+        h = _vp()
+        _check(lib().cds_pairq_create(ctx.h, maskset.h, int(max_batch), int(max_wait_us), int(cache_targets), C.byref(h)), ctx.h)
+        self.h = h
+        ctx._children.add(self)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().cds_pairq_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def score(self, mask_index, target_rgb, key=0):
+        target_rgb = np.ascontiguousarray(target_rgb, dtype=np.uint8)
+        s, r, m = C.c_int32(), C.c_double(), C.c_int32()
+        _check(lib().cds_pairq_score(self.h, int(mask_index), int(key), _ptr(target_rgb), target_rgb.shape[1], target_rgb.shape[0],
+                                     C.byref(s), C.byref(r), C.byref(m)), None)
+        return s.value, r.value, bool(m.value)
+
+    def stats(self):
+        r, b, u = C.c_int64(), C.c_int64(), C.c_int64()
+        _check(lib().cds_pairq_get_stats(self.h, C.byref(r), C.byref(b), C.byref(u)), None)
+        return {"requests": r.value, "batches": b.value, "uploads": u.value}
+
+    def drive(self, targets_rgb, keys, pair_mask, pair_target, n_threads):
+        """n_threads native threads call cds_pairq_score over the pair list -> (scores, mirrored, seconds)"""
+        targets_rgb = np.ascontiguousarray(targets_rgb, dtype=np.uint8)
+        keys = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
+        pair_mask = np.ascontiguousarray(pair_mask, dtype=np.int32)
+        pair_target = np.ascontiguousarray(pair_target, dtype=np.int64)
+        n = len(pair_mask)
+        scores = np.zeros(n, np.int32)
+        mir = np.zeros(n, np.uint8)
+        secs = C.c_double()
+        _check(lib().cds_debug_pairq_drive(self.h, _ptr(targets_rgb), targets_rgb.shape[0], None if keys is None else keys.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           pair_mask.ctypes.data_as(_i32p), pair_target.ctypes.data_as(_i64p), n, int(n_threads),
+                                           scores.ctypes.data_as(_i32p), mir.ctypes.data_as(_u8p), C.byref(secs)), None)
+        return scores, mir.astype(bool), secs.value
 
 
 class ShapeMaskSet:

@@ -237,6 +237,28 @@ cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, int32_t mask_
                               int32_t target_width, int32_t target_height,
                               int32_t *score_out, double *ratio_out, int32_t *mirrored_out);
 
+/* The single-pair call at scale: a micro-batching scorer with a device-side target cache.
+ * The reference makes one calculateMatchingScore call per (mask, target) pair from ~40 pool threads at once, on one algorithm
+ * instance per mask (TOOLS/cdsprocess/LocalColorMIPSearchProcessor.java:93-105), and the SAME target image recurs across masks
+ * because targets come out of a cache (TOOLS/CachedMIPsUtils.java:60-110).  cds_pairq_score is that call: it blocks its caller
+ * until the score is known and may be called from any number of threads at once (it does not take the context's lock).  Calls
+ * that arrive together are scored by one kernel launch; a target whose key is already in the device cache is not uploaded again.
+ *   max_batch     most requests per launch (<= 0: 64)
+ *   max_wait_us   how long the dispatcher waits for company before it launches a partly filled batch
+ *   cache_targets code planes kept on every device (2.8 MB each for 1210 x 566); least recently used are replaced
+ *   target_key    the caller's identity of the image (the Java side passes the cache key / System.identityHashCode of the
+ *                 ImageArray); equal keys MUST mean equal pixels; 0 = do not cache
+ * Scores, ratio and mirrored flag are exactly cds_score_pair_rgb's.  The mask set must not be modified or destroyed while the
+ * queue exists.  Errors as cds_score_pair_rgb (CDS_ERR_SIZE_MISMATCH for a target of another size). */
+typedef struct cds_pairq cds_pairq;
+cds_status cds_pairq_create(cds_ctx *ctx, const cds_maskset *ms, int32_t max_batch, int32_t max_wait_us, int32_t cache_targets, cds_pairq **out);
+void       cds_pairq_destroy(cds_pairq *q);
+cds_status cds_pairq_score(cds_pairq *q, int32_t mask_index, uint64_t target_key, const uint8_t *target_rgb,
+                           int32_t target_width, int32_t target_height,
+                           int32_t *score_out, double *ratio_out, int32_t *mirrored_out);
+/* requests served, kernel launches (batches) and target uploads so far (any pointer may be NULL) */
+cds_status cds_pairq_get_stats(const cds_pairq *q, int64_t *requests, int64_t *batches, int64_t *uploads);
+
 /* ---------------------------------------------------------------- shape score ------------------------------------------------------------ */
 
 /* Prepared queries of the shape score.  Replaces createShapeMatchCDSAlgorithmProvider + its per-mask
@@ -344,6 +366,11 @@ cds_status cds_debug_class_intervals(double z_tolerance, int32_t sector, int32_t
  * the fused strip -> code-word kernel, 0 the decode + encode pair.  Lets tests compare the two ingest paths word for word. */
 cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n, int32_t width, int32_t height,
                                 int32_t data_threshold, int32_t fused, uint32_t *codes_out, uint32_t *valid_out);
+/* Drives cds_pairq_score from n_threads native threads over a list of pairs, the way the reference's thread pool drives
+ * calculateMatchingScore: thread-safety tests and the throughput number of the single-pair entry point (bench.py). */
+cds_status cds_debug_pairq_drive(cds_pairq *q, const uint8_t *targets_rgb, int64_t n_targets, const uint64_t *keys,
+                                 const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs, int32_t n_threads,
+                                 int32_t *scores_out, uint8_t *mirrored_out, double *seconds_out);
 /* Slice numbers (1..256, 0 = black) of n RGB colours as the shape path computes them on the device -- a table built per device
  * with the double arithmetic of GradientAreaGapUtils.findSliceNumberInLUT (API/cds/GradientAreaGapUtils.java:18-197) -- so that the
  * table can be checked against the oracle over all 2^24 colours. */
