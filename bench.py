@@ -419,6 +419,43 @@ def data_dependence(ctx, masks_synth, n_masks=1000, n_targets=1024, reps=3):
     return legs
 
 
+def pair_provider_bench(ctx, masks_host, n_masks=64, n_targets=256, threads=40):
+    """The reference's own calling convention: ColorDepthSearchAlgorithm.calculateMatchingScore, one (mask, target) pair per call,
+    from a pool of ~40 threads (LocalColorMIPSearchProcessor.java:93-105; 2 x cores - 1 = 39 workers in submitCDSJob.sh), the same
+    target images recurring across masks.  Here: cds_pairq_score driven by `threads` native threads (cds_debug_pairq_drive), mask by
+    mask over all targets like the reference's loop.  `cold` includes uploading + encoding every target once; `warm` finds them all
+    in the device cache (the reference keeps its targets in a 100 000-image cache)."""
+    from colormipsearch_b200 import capi
+    rects = label_rects()
+    p = PARAMS
+    ms = capi.MaskSet(ctx, W, H, p["mask_threshold"], p["data_threshold"], p["z_tolerance"], p["xy_shift"], p["mirror"], rects)
+    ms.add_rgb(masks_host[:n_masks])
+    targets = np.concatenate([ctx.synth_rgb(1, SEED, i, min(64, n_targets - i), W, H, on_device=True) for i in range(0, n_targets, 64)])
+    lib = capi.Library(ctx, W, H, n_targets)
+    lib.add_rgb(targets)
+    dense, dmir = ms.search_dense(lib)
+    lib.close()
+    pm = np.repeat(np.arange(n_masks, dtype=np.int32), n_targets)
+    pt = np.tile(np.arange(n_targets, dtype=np.int64), n_masks)
+    keys = np.arange(n_targets, dtype=np.uint64) + 1
+    q = capi.PairQueue(ctx, ms, max_batch=64, max_wait_us=60, cache_targets=max(512, 2 * n_targets))
+    sc, mir, cold_s = q.drive(targets, keys, pm, pt, threads)
+    st_cold = q.stats()
+    sc2, mir2, warm_s = q.drive(targets, keys, pm, pt, threads)
+    st = q.stats()
+    ok = bool(np.array_equal(sc, dense[pm, pt]) and np.array_equal(sc2, dense[pm, pt]) and np.array_equal(mir2, dmir[pm, pt].astype(bool)))
+    q.close()
+    ms.close()
+    n = len(pm)
+    return {"metric": "single-pair calls/sec through cds_pairq_score", "threads": threads, "masks": n_masks, "targets": n_targets, "pairs": n,
+            "cold": {"value": n / cold_s, "unit": "pairs/s", "uploads": st_cold["uploads"], "batches": st_cold["batches"]},
+            "warm": {"value": n / warm_s, "unit": "pairs/s", "uploads": st["uploads"] - st_cold["uploads"], "batches": st["batches"] - st_cold["batches"],
+                     "mean_batch": n / max(1, st["batches"] - st_cold["batches"])},
+            "equals_dense_search": ok,
+            "what": "blocking single-pair calls from %d native threads, micro-batched into one kernel launch per batch; targets keyed like the "
+                    "reference's image cache" % threads}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is Java and there is no JVM on
     this image, so this is the oracle port (oracle/cds_oracle.c, pinned on the reference's golden vectors) on all host
@@ -497,6 +534,7 @@ def main():
     ap.add_argument("--no-e2e-tiff", action="store_true", help="skip the TIFF-file variant of the end-to-end step")
     ap.add_argument("--e2e-tiff", action="store_true", help="(default now) the TIFF-file variant of the end-to-end step runs at every N")
     ap.add_argument("--no-shape", action="store_true")
+    ap.add_argument("--no-pair-provider", action="store_true", help="skip the single-pair (micro-batching queue) leg")
     ap.add_argument("--no-bind", action="store_true", help="do not move the rank onto the CPUs next to its GPU")
     ap.add_argument("--no-data-dependence", action="store_true", help="skip the real-fixture / dense-target legs")
     args = ap.parse_args()
@@ -793,6 +831,11 @@ def main():
                 line["shape"]["config2_mix"] = shape_config2_mix(ctx, last, M, t_first, min(T, 4096))
             except Exception as e:      # reporting only
                 line["shape"]["config2_mix"] = {"error": repr(e)}
+        if not args.no_pair_provider and world == 1:
+            try:
+                line["pair_provider"] = pair_provider_bench(ctx, masks_host)
+            except Exception as e:      # reporting only
+                line["pair_provider"] = {"error": repr(e)}
         if not args.no_data_dependence and world == 1:
             try:
                 line["data_dependence"] = data_dependence(ctx, masks_host)

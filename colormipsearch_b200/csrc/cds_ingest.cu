@@ -217,131 +217,225 @@ tiff_encode_kernel(const uint8_t *__restrict__ src, const TiffStrip *__restrict_
     uint32_t row_start = 0;                        // strip-relative output position of the current row's first byte
     const uint32_t lt = (1u << lane) - 1u;
 
-    // One loop, one site per step (the steps are long; several inlined copies of them would not fit the instruction cache):
-    //   (1) take the next run from the input -> a span [a, a + n) of decoded bytes to write (n = 0 for zero fills and no-ops),
-    //   (2) emit the rows that end at or before a (all remaining rows once the input or the strip's rows are used up),
-    //   (3) write the span into the row buffer, piece by piece where it crosses rows.
+    // The decoder.  PackBits is a chain of runs, but the chain can be followed 32 input bytes at a time: every lane takes one byte
+    // of the window, works out where the NEXT control byte would be if its byte were one, pointer doubling (four shuffles) and five
+    // OR-reductions mark the bytes that really are control bytes, and a warp scan over the runs' lengths gives every run its place
+    // in the output.  Zero fills -- most runs of a mostly black image -- then cost nothing more; literal bytes that lie inside the
+    // window are stored by the lanes that hold them, in one step for all literal runs of the window; non-zero fills and the tail
+    // of a literal that leaves the window are short cooperative loops.  (The first version took one run, or one stretch of equal
+    // fills, per iteration: ~16 500 iterations of ~130 instructions per image, profiles/r02_fuse_v1_ncu_summary.txt.)
+    // A window whose writes would cross the end of the current row falls back to a generic one-run-at-a-time step (`span`), which
+    // also serves stored strips.  One loop with one site per step: the steps are long, several inlined copies would not fit the
+    // instruction cache.
     uint32_t pos = 0, idx = 0;
+    uint32_t span_a = 0, span_n = 0, span_from = 0, span_fill = 0;     // generic step: decoded bytes [span_a, span_a + span_n) still to write
+    bool span_lit = false;
+    uint32_t emit_to = 0;                          // rows that end at or before this position are complete: emit them before the next write
     bool done = false;
-    while (!done) {
-        uint32_t a = pos, n = 0, from = 0, fill = 0;
-        bool literal = false;
-        if (pos < out_len && idx < in_len) {
-            if (!packed) {
-                n = min(min(in_len - idx, out_len - pos), 4096u);
-                literal = true; from = idx;
-                pos += n; idx += n;
-            } else {
-                // lane i looks at the pair (control, value) that starts at idx + 2 i
-                const uint32_t q = idx + 2 * lane;
-                const uint32_t c = q < in_len ? (uint32_t) in[q] : 0u;
-                const uint32_t v = q + 1 < in_len ? (uint32_t) in[q + 1] : 0u;
-                const uint32_t c0 = __shfl_sync(0xffffffffu, c, 0);
-                if (c0 < 128u) {
-                    const uint32_t cnt = c0 + 1u;
-                    n = min(cnt, out_len - pos);
-                    literal = true; from = idx + 1u;
-                    pos += cnt; idx += 1u + cnt;
-                } else if (c0 == 128u) {
-                    idx += 1u;
-                } else {
-                    // as many consecutive fill runs of the first pair's value as the warp can see at once
-                    const uint32_t v0 = __shfl_sync(0xffffffffu, v, 0);
-                    const uint32_t same = __ballot_sync(0xffffffffu, c > 128u && v == v0 && q + 1 < in_len);
-                    const uint32_t k = same == 0xffffffffu ? 32u : (uint32_t) __ffs((int) ~same) - 1u;
-                    uint32_t cnt;
-                    fill = v0;
-                    if (k == 0u) { cnt = 257u - c0; fill = 0u; idx += 2u; }                            // a fill whose value byte lies beyond the input
-                    else { cnt = __reduce_add_sync(0xffffffffu, lane < k ? 257u - c : 0u); idx += 2u * k; }
-                    if (fill != 0u) n = min(cnt, out_len - pos);
-                    pos += cnt;
-                }
+    for (;;) {
+        const uint32_t row_end = row_start + row_bytes;
+        if (done ? y < y_end : row_end <= emit_to) {
+            // ------------------------------------------------------------------ emit the current row
+            uint32_t *drow = planes + g.row_offset(first_slot + img, y);
+            // the whole row black, pad columns as pad words (the row is 16-byte aligned and a multiple of four words long)
+            for (int v4 = (int) lane; v4 < g.pitch / 4; v4 += 32) {
+                const int x = 4 * v4;
+                uint4 w4;
+                w4.x = x < g.W ? black : CDS_CODE_PAD_WORD; w4.y = x + 1 < g.W ? black : CDS_CODE_PAD_WORD;
+                w4.z = x + 2 < g.W ? black : CDS_CODE_PAD_WORD; w4.w = x + 3 < g.W ? black : CDS_CODE_PAD_WORD;
+                reinterpret_cast<uint4 *>(drow)[v4] = w4;
             }
-        } else {
-            done = true;
-        }
-        for (;;) {
-            const bool emit = done ? y < y_end : (n != 0u && a >= row_start + row_bytes);
-            if (emit) {
-                // ------------------------------------------------------------------ emit the current row
-                uint32_t *drow = planes + g.row_offset(first_slot + img, y);
-                // the whole row black, pad columns as pad words (the row is 16-byte aligned and a multiple of four words long)
-                for (int v4 = (int) lane; v4 < g.pitch / 4; v4 += 32) {
-                    const int x = 4 * v4;
-                    uint4 w4;
-                    w4.x = x < g.W ? black : CDS_CODE_PAD_WORD; w4.y = x + 1 < g.W ? black : CDS_CODE_PAD_WORD;
-                    w4.z = x + 2 < g.W ? black : CDS_CODE_PAD_WORD; w4.w = x + 3 < g.W ? black : CDS_CODE_PAD_WORD;
-                    reinterpret_cast<uint4 *>(drow)[v4] = w4;
-                }
-                const bool dirty = (dirty_lo | dirty_hi) != 0u;
-                if (dirty) {
-                    __syncwarp();                  // the black words above are ordered before the patches below
-                    // non-black pixels of the marked chunks -> queue -> colour classifier on full warps
-                    uint32_t qh = 0, qt = 0;
-                    uint32_t m = dirty_lo;
-                    int cbase = 0;
-                    for (;;) {
-                        bool more = true;
-                        if (m == 0u) {
-                            if (cbase == 0) { m = dirty_hi; cbase = 32; }
-                            if (m == 0u) more = false;
-                        }
-                        if (more) {
-                            const int c = (__ffs((int) m) - 1) + cbase;
-                            m &= m - 1;
-                            const int x = 32 * c + (int) lane;
-                            bool lit = false;
-                            if (x < g.W) lit = (rowbuf[3 * x] | rowbuf[3 * x + 1] | rowbuf[3 * x + 2]) != 0;
-                            const unsigned bal = __ballot_sync(0xffffffffu, lit);
-                            if (lit) s_queue[(qt + (uint32_t) __popc(bal & lt)) & (kFuseQueue - 1)] = (uint32_t) x;
-                            qt += (uint32_t) __popc(bal);
-                            __syncwarp();
-                        }
-                        // classify when 32 pixels wait (or, after the last chunk, whatever is left)
-                        while (qt - qh >= 32u || (!more && qt != qh)) {
-                            const uint32_t nq = min(32u, qt - qh);
-                            if (lane < nq) {
-                                const int x = (int) s_queue[(qh + lane) & (kFuseQueue - 1)];
-                                const uint8_t *px = rowbuf + 3 * x;
-                                int sector;
-                                const uint32_t code = fuse_encode(px[0], px[1], px[2], rank_tab, thr, sector);
-                                drow[x] = code;
-                                if (valid && sector >= 0) atomicOr(&s_valid[sector * vp + (x >> 5)], 1u << (x & 31));
-                            }
-                            qh += nq;
-                            __syncwarp();
-                        }
-                        if (!more) break;
+            const bool dirty = (dirty_lo | dirty_hi) != 0u;
+            if (dirty) {
+                __syncwarp();                  // the black words above are ordered before the patches below
+                // non-black pixels of the marked chunks -> queue -> colour classifier on full warps
+                uint32_t qh = 0, qt = 0;
+                uint32_t m = dirty_lo;
+                int cbase = 0;
+                for (;;) {
+                    bool more = true;
+                    if (m == 0u) {
+                        if (cbase == 0) { m = dirty_hi; cbase = 32; }
+                        if (m == 0u) more = false;
                     }
+                    if (more) {
+                        const int c = (__ffs((int) m) - 1) + cbase;
+                        m &= m - 1;
+                        const int x = 32 * c + (int) lane;
+                        bool lit = false;
+                        if (x < g.W) lit = (rowbuf[3 * x] | rowbuf[3 * x + 1] | rowbuf[3 * x + 2]) != 0;
+                        const unsigned bal = __ballot_sync(0xffffffffu, lit);
+                        if (lit) s_queue[(qt + (uint32_t) __popc(bal & lt)) & (kFuseQueue - 1)] = (uint32_t) x;
+                        qt += (uint32_t) __popc(bal);
+                        __syncwarp();
+                    }
+                    // classify when 32 pixels wait (or, after the last chunk, whatever is left)
+                    while (qt - qh >= 32u || (!more && qt != qh)) {
+                        const uint32_t nq = min(32u, qt - qh);
+                        if (lane < nq) {
+                            const int x = (int) s_queue[(qh + lane) & (kFuseQueue - 1)];
+                            const uint8_t *px = rowbuf + 3 * x;
+                            int sector;
+                            const uint32_t code = fuse_encode(px[0], px[1], px[2], rank_tab, thr, sector);
+                            drow[x] = code;
+                            if (valid && sector >= 0) atomicOr(&s_valid[sector * vp + (x >> 5)], 1u << (x & 31));
+                        }
+                        qh += nq;
+                        __syncwarp();
+                    }
+                    if (!more) break;
                 }
-                if (valid) {
-                    uint4 *vout = reinterpret_cast<uint4 *>(valid + ((size_t) img * g.H + y) * valid_words);
-                    for (int k = (int) lane; k < valid_words / 4; k += 32) vout[k] = reinterpret_cast<const uint4 *>(s_valid)[k];
-                }
-                if (dirty) {
-                    __syncwarp();
-                    for (int k = (int) lane; k < (row_buf_bytes + valid_words * 4) / 16; k += 32) reinterpret_cast<uint4 *>(rowbuf)[k] = make_uint4(0u, 0u, 0u, 0u);
-                    __syncwarp();
-                }
-                dirty_lo = dirty_hi = 0u;
-                y++;
-                row_start += row_bytes;
-                continue;
             }
-            if (n == 0u) break;
-            // ---------------------------------------------------------------------- write the piece of the span inside this row
-            const uint32_t off = a - row_start;
-            const uint32_t take = min(n, row_bytes - off);
+            if (valid) {
+                uint4 *vout = reinterpret_cast<uint4 *>(valid + ((size_t) img * g.H + y) * valid_words);
+                for (int k = (int) lane; k < valid_words / 4; k += 32) vout[k] = reinterpret_cast<const uint4 *>(s_valid)[k];
+            }
+            if (dirty) {
+                __syncwarp();
+                for (int k = (int) lane; k < (row_buf_bytes + valid_words * 4) / 16; k += 32) reinterpret_cast<uint4 *>(rowbuf)[k] = make_uint4(0u, 0u, 0u, 0u);
+                __syncwarp();
+            }
+            dirty_lo = dirty_hi = 0u;
+            y++;
+            row_start += row_bytes;
+            continue;
+        }
+        if (done) break;
+        if (span_n) {
+            // ---------------------------------------------------------------------- generic step: the piece of the span inside this row
+            if (span_a >= row_end) { emit_to = span_a; continue; }
+            const uint32_t off = span_a - row_start;
+            const uint32_t take = min(span_n, row_bytes - off);
             for (uint32_t i = lane; i < take; i += 32) {
-                uint32_t b = fill;
-                if (literal) b = from + i < in_len ? (uint32_t) in[from + i] : 0u;
+                uint32_t b = span_fill;
+                if (span_lit) b = span_from + i < in_len ? (uint32_t) in[span_from + i] : 0u;
                 asm volatile("st.shared.u8 [%0], %1;" :: "r"(rowbuf_a + off + i), "r"(b) : "memory");
             }
             const uint32_t c0 = off / 96u, c1 = (off + take - 1u) / 96u;                 // chunk = 32 pixels = 96 bytes
             for (uint32_t c = c0; c <= c1; c++) { if (c < 32u) dirty_lo |= 1u << c; else dirty_hi |= 1u << (c - 32u); }
-            a += take; n -= take; from += take;
+            span_a += take; span_n -= take; span_from += take;
             __syncwarp();
+            continue;
         }
+        if (!(pos < out_len && idx < in_len)) { done = true; continue; }
+        if (!packed) {
+            span_n = min(min(in_len - idx, out_len - pos), 4096u);
+            span_a = pos; span_lit = true; span_from = idx;
+            pos += span_n; idx += span_n;
+            continue;
+        }
+        // -------------------------------------------------------------------------- a window of 32 input bytes
+        const uint32_t p = idx + lane;
+        const uint32_t c = p < in_len ? (uint32_t) in[p] : 128u;
+        uint32_t v = __shfl_down_sync(0xffffffffu, c, 1);
+        const bool v_missing = p + 1 >= in_len;                        // a fill whose value byte lies beyond the input fills with 0
+        if (v_missing) v = 0u;
+        const bool is_lit = c < 128u, is_fill = c > 128u;
+        const uint32_t consumed = is_lit ? c + 2u : (is_fill ? 2u : 1u);
+        const uint32_t len = is_lit ? c + 1u : (is_fill ? 257u - c : 0u);
+        // a control byte can be taken in this window when its header is here: a fill needs its value byte (lane 31 only has it when the input ends)
+        const bool takeable = p < in_len && (!is_fill || lane < 31u || v_missing);
+        const uint32_t nxt = lane + consumed;
+        uint32_t j1 = (takeable && nxt < 32u && idx + nxt < in_len) ? nxt : 32u;     // 32 = the chain leaves the window
+        uint32_t t2 = __shfl_sync(0xffffffffu, j1, (int) (j1 & 31u));
+        const uint32_t j2 = j1 < 32u ? t2 : 32u;
+        t2 = __shfl_sync(0xffffffffu, j2, (int) (j2 & 31u));
+        const uint32_t j4 = j2 < 32u ? t2 : 32u;
+        t2 = __shfl_sync(0xffffffffu, j4, (int) (j4 & 31u));
+        const uint32_t j8 = j4 < 32u ? t2 : 32u;
+        t2 = __shfl_sync(0xffffffffu, j8, (int) (j8 & 31u));
+        const uint32_t j16 = j8 < 32u ? t2 : 32u;
+        uint32_t T = 1u;                                               // the control bytes of the window: byte 0 and everything the chain reaches
+        T |= __reduce_or_sync(0xffffffffu, ((T >> lane) & 1u) && j16 < 32u ? 1u << j16 : 0u);
+        T |= __reduce_or_sync(0xffffffffu, ((T >> lane) & 1u) && j8 < 32u ? 1u << j8 : 0u);
+        T |= __reduce_or_sync(0xffffffffu, ((T >> lane) & 1u) && j4 < 32u ? 1u << j4 : 0u);
+        T |= __reduce_or_sync(0xffffffffu, ((T >> lane) & 1u) && j2 < 32u ? 1u << j2 : 0u);
+        T |= __reduce_or_sync(0xffffffffu, ((T >> lane) & 1u) && j1 < 32u ? 1u << j1 : 0u);
+        const bool run = ((T >> lane) & 1u) && takeable;               // this lane's byte starts a run that this window decodes
+        // (the last control byte of the chain may be a fill cut off by the window's end: it starts the next window)
+        const uint32_t last = 31u - (uint32_t) __clz((int) T);
+        const bool last_taken = __shfl_sync(0xffffffffu, (int) takeable, (int) last) != 0;
+        const uint32_t last_next = __shfl_sync(0xffffffffu, nxt, (int) last);
+        const uint32_t new_idx = idx + (last_taken ? last_next : last);
+        // where every run starts in the output
+        const uint32_t mylen = run ? len : 0u;
+        uint32_t incl = mylen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int) lane >= d) incl += u;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t start = pos + incl - mylen;
+        const bool writes = run && start < out_len && (is_lit || (is_fill && v != 0u));
+        const uint32_t wend = min(start + len, out_len);
+        const uint32_t w_min = __reduce_min_sync(0xffffffffu, writes ? start : 0xffffffffu);
+        if (w_min == 0xffffffffu) { pos += total; idx = new_idx; continue; }          // nothing but zero fills and no-ops
+        if (w_min >= row_end) { emit_to = w_min; continue; }                           // finish the rows in between, then look at this window again
+        const uint32_t w_max = __reduce_max_sync(0xffffffffu, writes ? wend : 0u);
+        if (w_max > row_end) {
+            // the window's writes cross the end of the row: take its first run alone, generically
+            const uint32_t c0 = __shfl_sync(0xffffffffu, c, 0), v0 = __shfl_sync(0xffffffffu, v, 0);
+            const uint32_t len0 = c0 < 128u ? c0 + 1u : (c0 > 128u ? 257u - c0 : 0u);
+            span_a = pos; span_lit = c0 < 128u; span_from = idx + 1u; span_fill = v0;
+            span_n = (c0 < 128u || (c0 > 128u && v0 != 0u)) ? min(len0, out_len - pos) : 0u;
+            pos += len0;
+            idx += c0 < 128u ? c0 + 2u : (c0 > 128u ? 2u : 1u);
+            continue;
+        }
+        // ------------------------------------------------------------------------------ all writes of the window land in the current row
+        const uint32_t base = rowbuf_a - row_start;                    // row buffer address of output position 0 (wraps; only sums are used)
+        uint32_t d_lo = 0u, d_hi = 0u;
+        // literal bytes inside the window: the lane that holds the byte stores it
+        const uint32_t lit_runs = __ballot_sync(0xffffffffu, run && is_lit);
+        {
+            const uint32_t below = lit_runs & lt;
+            const int owner = below ? 31 - __clz((int) below) : 0;
+            const uint32_t oc = __shfl_sync(0xffffffffu, c, owner), ostart = __shfl_sync(0xffffffffu, start, owner);
+            const uint32_t d = lane - (uint32_t) owner - 1u;
+            if (below && d <= oc) {
+                const uint32_t o = ostart + d;
+                if (o < out_len) {
+                    const uint32_t b = p < in_len ? c : 0u;
+                    asm volatile("st.shared.u8 [%0], %1;" :: "r"(base + o), "r"(b) : "memory");
+                    const uint32_t ch = (o - row_start) / 96u;
+                    if (ch < 32u) d_lo |= 1u << ch; else d_hi |= 1u << (ch - 32u);
+                }
+            }
+        }
+        // the tail of a literal that leaves the window (only the last run can)
+        if (last_taken && last_next > 32u && ((lit_runs >> last) & 1u)) {
+            const uint32_t lstart = __shfl_sync(0xffffffffu, start, (int) last);
+            const uint32_t done_bytes = 31u - last;                    // data bytes of the run that were inside the window
+            const uint32_t extra = last_next - 32u;
+            for (uint32_t e = lane; e < extra; e += 32) {
+                const uint32_t o = lstart + done_bytes + e;
+                if (o < out_len) {
+                    const uint32_t src_i = idx + 32u + e;
+                    const uint32_t b = src_i < in_len ? (uint32_t) in[src_i] : 0u;
+                    asm volatile("st.shared.u8 [%0], %1;" :: "r"(base + o), "r"(b) : "memory");
+                    const uint32_t ch = (o - row_start) / 96u;
+                    if (ch < 32u) d_lo |= 1u << ch; else d_hi |= 1u << (ch - 32u);
+                }
+            }
+        }
+        // non-zero fills, one after the other
+        uint32_t fills = __ballot_sync(0xffffffffu, writes && is_fill);
+        while (fills) {
+            const int f = __ffs((int) fills) - 1;
+            fills &= fills - 1;
+            const uint32_t fs = __shfl_sync(0xffffffffu, start, f), fe = __shfl_sync(0xffffffffu, wend, f), fv = __shfl_sync(0xffffffffu, v, f);
+            for (uint32_t o = fs + lane; o < fe; o += 32) {
+                asm volatile("st.shared.u8 [%0], %1;" :: "r"(base + o), "r"(fv) : "memory");
+                const uint32_t ch = (o - row_start) / 96u;
+                if (ch < 32u) d_lo |= 1u << ch; else d_hi |= 1u << (ch - 32u);
+            }
+        }
+        dirty_lo |= __reduce_or_sync(0xffffffffu, d_lo);
+        dirty_hi |= __reduce_or_sync(0xffffffffu, d_hi);
+        pos += total;
+        idx = new_idx;
+        __syncwarp();
     }
 }
 
