@@ -15,7 +15,7 @@ SO = os.path.join(LIBDIR, "libcdsgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU_SOURCES = ["cds_api.cu", "cds_stream.cu", "cds_kernels.cu", "cds_band.cu", "cds_cand.cu", "cds_topk.cu", "cds_synth.cu", "cds_shape.cu", "cds_ingest.cu", "cds_pairq.cu"]
-CPP_SOURCES = ["cds_tables.cpp", "cds_select.cpp", "cds_tiff.cpp"]
+CPP_SOURCES = ["cds_tables.cpp", "cds_select.cpp", "cds_tiff.cpp", "cds_formats.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libcdsgpu build failed")
     cmd = [NVCC, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",
-                                              "-Xcompiler", "-fPIC", "-cudart", "shared"]
+                                              "-Xcompiler", "-fPIC", "-cudart", "shared", "-lz"]
     subprocess.run(cmd, check=True)
     return SO
 

@@ -65,6 +65,16 @@ _i64p = C.POINTER(C.c_int64)
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
 
+class PngInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32), ("color_type", C.c_int32), ("interlace", C.c_int32),
+                ("decodable", C.c_int32), ("data_bytes", C.c_int64)]
+
+
+class ZipEntry(C.Structure):
+    _fields_ = [("name_offset", C.c_int64), ("name_len", C.c_int32), ("method", C.c_int32), ("data_offset", C.c_int64),
+                ("compressed_size", C.c_int64), ("size", C.c_int64), ("crc32", C.c_uint32), ("is_directory", C.c_int32)]
+
+
 # name -> (restype, argtypes); the single source of truth for the Python side of the ABI
 SIGNATURES = {
     "cds_abi_version": (C.c_int32, []),
@@ -117,6 +127,16 @@ SIGNATURES = {
     "cds_get_last_stats": (C.c_int32, [_vp, C.POINTER(SearchStats)]),
     "cds_debug_encode_colors": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, _u32p]),
     "cds_debug_class_intervals": (C.c_int32, [C.c_double, C.c_int32, C.c_int32, _u32p, _u32p, _u32p, _u32p]),
+    "cds_tiff_decode_rgb_host": (C.c_int32, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp]),
+    "cds_tiff_to_packbits": (C.c_int32, [_vp, C.c_int64, _vp, C.c_int64, _i64p]),
+    "cds_png_probe": (C.c_int32, [_vp, C.c_int64, C.POINTER(PngInfo)]),
+    "cds_png_decode_gray16": (C.c_int32, [_vp, _vp, _i64p, C.c_int64, C.c_int32, C.c_int32, _vp]),
+    "cds_png_encode_bound": (C.c_int64, [C.c_int32, C.c_int32]),
+    "cds_png_encode_gray16": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int64, _i64p]),
+    "cds_zip_index": (C.c_int32, [_vp, C.c_int64, C.POINTER(ZipEntry), C.c_int64, _i64p]),
+    "cds_zip_find": (C.c_int64, [_vp, C.POINTER(ZipEntry), C.c_int64, C.c_char_p]),
+    "cds_zip_read": (C.c_int32, [_vp, C.c_int64, C.POINTER(ZipEntry), _vp, C.c_int64]),
+    "cds_shape_score_pairs_files": (C.c_int32, [_vp, _vp, _vp, _i64p, _vp, _i64p, _vp, _vp, C.c_int64, _i32p, _i64p, C.c_int64, _i64p, _i64p, _u8p]),
     "cds_pairq_create": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
     "cds_pairq_destroy": (None, [_vp]),
     "cds_pairq_score": (C.c_int32, [_vp, C.c_int32, C.c_uint64, _vp, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
@@ -605,6 +625,26 @@ class ShapeMaskSet:
                                            gap.ctypes.data_as(_i64p), he.ctypes.data_as(_i64p), mir.ctypes.data_as(_u8p)), self.ctx.h)
         return gap, he, mir.astype(bool)
 
+    def score_pairs_files(self, tiff_files, png_files, zgap_rgb, pair_mask, pair_target, has_variants=None):
+        """cds_shape_score_pairs_files: targets as TIFF files, gradient images as PNG files"""
+        tblob, toff = pack_files(tiff_files)
+        pblob, poff = pack_files(png_files)
+        n_targets = len(toff) - 1
+        assert len(poff) - 1 == n_targets
+        zgap_rgb = None if zgap_rgb is None else np.ascontiguousarray(zgap_rgb, dtype=np.uint8)
+        has_variants = None if has_variants is None else np.ascontiguousarray(has_variants, dtype=np.uint8)
+        pair_mask = np.ascontiguousarray(pair_mask, dtype=np.int32)
+        pair_target = np.ascontiguousarray(pair_target, dtype=np.int64)
+        n = len(pair_mask)
+        gap = np.zeros(n, np.int64)
+        he = np.zeros(n, np.int64)
+        mir = np.zeros(n, np.uint8)
+        _check(lib().cds_shape_score_pairs_files(self.ctx.h, self.h, _ptr(tblob), toff.ctypes.data_as(_i64p), _ptr(pblob), poff.ctypes.data_as(_i64p),
+                                                 _ptr(zgap_rgb), _ptr(has_variants), n_targets, pair_mask.ctypes.data_as(_i32p),
+                                                 pair_target.ctypes.data_as(_i64p), n, gap.ctypes.data_as(_i64p), he.ctypes.data_as(_i64p),
+                                                 mir.ctypes.data_as(_u8p)), self.ctx.h)
+        return gap, he, mir.astype(bool)
+
     def score_pairs_tiff(self, files, gradient, zgap_rgb, pair_mask, pair_target, has_variants=None, blob_ptr=None):
         """cds_shape_score_pairs_tiff: targets as TIFF files (a list of bytes objects or a (blob, offsets) pair)."""
         blob, offsets = pack_files(files)
@@ -691,6 +731,79 @@ def tiff_decode_rgb(ctx, files, W, H):
     out = np.empty((n, H, W, 3), np.uint8)
     _check(lib().cds_tiff_decode_rgb(ctx.h, _ptr(blob), offsets.ctypes.data_as(_i64p), n, W, H, _ptr(out)), ctx.h)
     return out
+
+
+def tiff_decode_rgb_host(data, W, H):
+    """cds_tiff_decode_rgb_host: any supported TIFF (none / PackBits / LZW) decoded on the host -> uint8 [H][W][3]"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    out = np.empty((H, W, 3), np.uint8)
+    _check(lib().cds_tiff_decode_rgb_host(_ptr(buf), len(buf), W, H, _ptr(out)))
+    return out
+
+
+def tiff_to_packbits(data):
+    buf = np.frombuffer(bytes(data), np.uint8)
+    info = tiff_probe(bytes(data))
+    cap = lib().cds_tiff_encode_bound(info["width"], info["height"], 8)
+    out = np.empty(cap, np.uint8)
+    n = C.c_int64()
+    _check(lib().cds_tiff_to_packbits(_ptr(buf), len(buf), _ptr(out), cap, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def png_probe(data):
+    buf = np.frombuffer(bytes(data), np.uint8)
+    info = PngInfo()
+    _check(lib().cds_png_probe(_ptr(buf), len(buf), C.byref(info)))
+    return {f: getattr(info, f) for f, _ in PngInfo._fields_}
+
+
+def png_encode_gray16(pixels, filter_mode=-1):
+    pixels = np.ascontiguousarray(pixels, dtype=np.uint16)
+    H, W = pixels.shape
+    cap = lib().cds_png_encode_bound(W, H)
+    out = np.empty(cap, np.uint8)
+    n = C.c_int64()
+    _check(lib().cds_png_encode_gray16(_ptr(pixels), W, H, int(filter_mode), _ptr(out), cap, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def png_decode_gray16(ctx, files, W, H):
+    """cds_png_decode_gray16: PNG files (host inflate, device unfilter) -> uint16 [n][H][W]"""
+    blob, offsets = pack_files(files)
+    n = len(offsets) - 1
+    out = np.empty((n, H, W), np.uint16)
+    _check(lib().cds_png_decode_gray16(ctx.h, _ptr(blob), offsets.ctypes.data_as(_i64p), n, W, H, _ptr(out)), ctx.h)
+    return out
+
+
+class ZipArchive:
+    """cds_zip_index / cds_zip_find / cds_zip_read over an archive held in memory."""
+
+    def __init__(self, data):
+        self.buf = np.frombuffer(bytes(data), np.uint8)
+        n = C.c_int64()
+        _check(lib().cds_zip_index(_ptr(self.buf), len(self.buf), None, 0, C.byref(n)))
+        self.entries = (ZipEntry * max(1, n.value))()
+        _check(lib().cds_zip_index(_ptr(self.buf), len(self.buf), self.entries, n.value, C.byref(n)))
+        self.n = n.value
+
+    def names(self):
+        return [bytes(self.buf[e.name_offset:e.name_offset + e.name_len]).decode() for e in self.entries[: self.n]]
+
+    def find(self, name):
+        return int(lib().cds_zip_find(_ptr(self.buf), self.entries, self.n, name.encode()))
+
+    def read(self, index):
+        e = self.entries[index]
+        out = np.empty(max(1, e.size), np.uint8)
+        _check(lib().cds_zip_read(_ptr(self.buf), len(self.buf), C.byref(e), _ptr(out), e.size))
+        return out[: e.size].tobytes()
+
+    def stored_span(self, index):
+        """(offset, size) of a stored entry inside the archive: usable in place, no copy"""
+        e = self.entries[index]
+        return (int(e.data_offset), int(e.size)) if e.method == 0 else None
 
 
 def java_string_hash(s):

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 
 #include "cds_runtime.h"
 #include "cds_tiff.h"
@@ -673,6 +674,163 @@ extern "C" cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, co
                                            (size_t) width * 4, (size_t) height, cudaMemcpyDeviceToHost, ds.stream));
         if (valid_out) CDS_CUDA(ctx, cudaMemcpyAsync(valid_out, d_valid, (size_t) n * valid_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds.stream));
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        return CDS_OK;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------------------------ PNG scanlines
+// The device side of the PNG ingest: the host has inflated the zlib stream (cds_formats.cpp); what is left per image is
+// height scanlines of [filter type][width * bps bytes], each filtered against the reconstructed bytes to the left and above
+// (PNG specification, section 9: None, Sub, Up, Average, Paeth), samples big-endian.  One warp per image walks the rows in order
+// with the previous reconstructed row in shared memory: None and Up are plain parallel passes, Sub is a prefix sum per byte lane
+// (segments per lane + a warp scan), Average and Paeth are serial in x but independent per byte lane, so bps lanes run them.
+// The reference's gradient files use filter None on every row (ImageJ's writer); the others are here for completeness.
+namespace {
+
+constexpr int kPngWarps = 4;
+
+__global__ void __launch_bounds__(kPngWarps * 32)
+png_unfilter_kernel(const uint8_t *__restrict__ filtered, size_t stride, const uint8_t *__restrict__ bytes_per_sample, int64_t n, int W, int H,
+                    uint16_t *__restrict__ out, int row_buf)
+{
+    extern __shared__ uint8_t s_png[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t img = (int64_t) blockIdx.x * kPngWarps + warp;
+    if (img >= n) return;
+    uint8_t *cur = s_png + (size_t) warp * 2 * row_buf, *prev = cur + row_buf;
+    const int bps = bytes_per_sample[img];
+    const int rb = W * bps;
+    const uint8_t *src = filtered + (size_t) img * stride;
+    uint16_t *dst = out + (size_t) img * W * H;
+    for (int i = lane; i < rb; i += 32) prev[i] = 0;
+    __syncwarp();
+    for (int y = 0; y < H; y++) {
+        const uint8_t *line = src + (size_t) y * (1 + rb);
+        const int f = line[0];
+        const uint8_t *x = line + 1;
+        if (f == 0) {
+            for (int i = lane; i < rb; i += 32) cur[i] = x[i];
+        } else if (f == 2) {
+            for (int i = lane; i < rb; i += 32) cur[i] = (uint8_t) (x[i] + prev[i]);
+        } else if (f == 1) {
+            // Sub: recon[i] = x[i] + recon[i - bps]: a running sum per byte lane.  Lane l owns pixels [l * seg, (l + 1) * seg).
+            const int seg = (W + 31) / 32;
+            const int p0 = min(lane * seg, W), p1 = min(p0 + seg, W);
+            uint32_t tot[2] = {0u, 0u};
+            for (int px = p0; px < p1; px++)
+                for (int b = 0; b < bps; b++) { tot[b] = (tot[b] + x[px * bps + b]) & 0xFFu; cur[px * bps + b] = (uint8_t) tot[b]; }
+            uint32_t off[2];
+            for (int b = 0; b < 2; b++) {
+                uint32_t incl = tot[b];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                off[b] = (incl - tot[b]) & 0xFFu;
+            }
+            for (int px = p0; px < p1; px++)
+                for (int b = 0; b < bps; b++) cur[px * bps + b] = (uint8_t) (cur[px * bps + b] + off[b]);
+        } else if (f == 3 || f == 4) {
+            if (lane < bps) {
+                int a = 0, c = 0;                                   // reconstructed byte to the left, and above-left
+                for (int i = lane; i < rb; i += bps) {
+                    const int b = prev[i];
+                    int pred;
+                    if (f == 3) pred = (a + b) >> 1;
+                    else { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+                    a = (x[i] + pred) & 0xFF;
+                    cur[i] = (uint8_t) a;
+                    c = b;
+                }
+            }
+        } else {
+            for (int i = lane; i < rb; i += 32) cur[i] = 0;         // not a PNG filter type: the row stays black
+        }
+        __syncwarp();
+        uint16_t *orow = dst + (size_t) y * W;
+        if (bps == 2) for (int px = lane; px < W; px += 32) orow[px] = (uint16_t) ((uint32_t) cur[2 * px] << 8 | cur[2 * px + 1]);
+        else for (int px = lane; px < W; px += 32) orow[px] = cur[px];
+        uint8_t *t = cur; cur = prev; prev = t;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+void cds::launch_png_unfilter(const uint8_t *filtered, size_t stride, const uint8_t *bytes_per_sample, int64_t n, int width, int height,
+                              uint16_t *out, cudaStream_t s)
+{
+    if (n <= 0) return;
+    const int row_buf = (width * 2 + 15) / 16 * 16;
+    const size_t smem = (size_t) kPngWarps * 2 * row_buf;
+    png_unfilter_kernel<<<(unsigned) ((n + kPngWarps - 1) / kPngWarps), kPngWarps * 32, smem, s>>>(filtered, stride, bytes_per_sample, n, width, height, out, row_buf);
+}
+
+namespace cds {
+// Inflates PNG files [first, first + cnt) of the blob into `h_filtered` (image i at i * stride, pinned or not) on up to `threads` host
+// threads; bps[i] = bytes per sample.  The first failure is reported with its file number.
+cds_status png_inflate_many(cds_ctx *ctx, const char *who, const uint8_t *blob, const int64_t *offsets, const int64_t *which, int64_t cnt,
+                            int W, int H, uint8_t *h_filtered, size_t stride, uint8_t *bps)
+{
+    const int threads = (int) std::max<int64_t>(1, std::min<int64_t>(cnt, std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()))));
+    std::vector<cds_status> st(threads, CDS_OK);
+    std::vector<std::string> errs(threads);
+    std::vector<int64_t> bad(threads, -1);
+    auto body = [&](int t) {
+        for (int64_t i = t; i < cnt; i += threads) {
+            const int64_t f = which ? which[i] : i;
+            const int64_t a = offsets[f], b = offsets[f + 1];
+            int depth = 16;
+            std::string err;
+            cds_status s = (a < 0 || b < a) ? CDS_ERR_BAD_ARG : png_inflate(blob + a, (size_t) (b - a), W, H, &depth, h_filtered + (size_t) i * stride, stride, err);
+            if (s != CDS_OK) { if (st[t] == CDS_OK) { st[t] = s; errs[t] = err.empty() ? "offsets must be non-decreasing" : err; bad[t] = f; } continue; }
+            bps[i] = (uint8_t) (depth / 8);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(body, t);
+    body(0);
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < threads; t++)
+        if (st[t] != CDS_OK) return ctx->fail(st[t], std::string(who) + ": file " + std::to_string(bad[t]) + ": " + errs[t]);
+    return CDS_OK;
+}
+}  // namespace cds
+
+extern "C" cds_status cds_png_decode_gray16(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n, int32_t width, int32_t height, uint16_t *out)
+{
+    return cds::abi_guard("cds_png_decode_gray16", [&]() -> cds_status {
+        if (!ctx) { set_tls_error("cds_png_decode_gray16: NULL context"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || width <= 0 || height <= 0 || width > 16384 || height > 16384) return ctx->fail(CDS_ERR_BAD_ARG, "cds_png_decode_gray16: bad size");
+        if (n == 0) return CDS_OK;
+        if (!blob || !offsets || !out) return ctx->fail(CDS_ERR_BAD_ARG, "cds_png_decode_gray16: NULL argument");
+        DevState &ds = ctx->devs[0];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        const size_t stride = ((size_t) height * (1 + (size_t) width * 2) + 15) / 16 * 16;
+        const size_t px = (size_t) width * height;
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(64, (int64_t) (((size_t) 256 << 20) / stride)));
+        CDS_TRY(ctx->ensure_pinned(ds, (size_t) chunk * (stride + 16)));
+        uint8_t *h_f = (uint8_t *) ds.h_pinned, *h_bps = h_f + (size_t) chunk * stride;
+        uint8_t *d_f = nullptr, *d_bps = nullptr;
+        uint16_t *d_out = nullptr;
+        auto release = [&]() { cudaStreamSynchronize(ds.stream); ds.pool.free(d_f); ds.pool.free(d_bps); ds.pool.free(d_out); };
+        struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_f, (size_t) chunk * stride));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_bps, (size_t) chunk));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_out, (size_t) chunk * px * sizeof(uint16_t)));
+        for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+            const int64_t cnt = std::min(chunk, n - i0);
+            CDS_TRY(png_inflate_many(ctx, "cds_png_decode_gray16", blob, offsets + i0, nullptr, cnt, width, height, h_f, stride, h_bps));
+            CDS_CUDA(ctx, cudaMemcpyAsync(d_f, h_f, (size_t) cnt * stride, cudaMemcpyHostToDevice, ds.stream));
+            CDS_CUDA(ctx, cudaMemcpyAsync(d_bps, h_bps, (size_t) cnt, cudaMemcpyHostToDevice, ds.stream));
+            launch_png_unfilter(d_f, stride, d_bps, cnt, width, height, d_out, ds.stream);
+            CDS_CUDA(ctx, cudaGetLastError());
+            CDS_CUDA(ctx, cudaMemcpyAsync(out + (size_t) i0 * px, d_out, (size_t) cnt * px * sizeof(uint16_t), cudaMemcpyDeviceToHost, ds.stream));
+            CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+            ctx->stats.kernel_launches++;
+        }
         return CDS_OK;
     });
 }

@@ -40,17 +40,26 @@ __device__ __forceinline__ bool pair_code_matches(uint32_t c, uint32_t lo1, uint
     return (c - lo1 <= len1) | (c - lo2 <= len2);
 }
 
-// acc: [n_pairs][2 * shifts.n + 1] zero on entry (the last word counts the pair's finished CTAs); scores[pair] = score word
+// The pairs of a launch travel in the kernel's parameter space (no copy to enqueue), the score words are written straight into
+// pinned host memory the dispatcher reads after the stream has drained (no copy back), and the last CTA of a pair leaves the
+// pair's accumulators zero for the next launch (no memset): a batch is ONE launch and one synchronisation.
+constexpr int kPairsPerLaunch = 128;
+struct PairList {
+    int32_t mask[kPairsPerLaunch];
+    int32_t slot[kPairsPerLaunch];
+};
+
+// acc: [kPairsPerLaunch][2 * NV + 1], zero on entry and on exit (the last word counts the pair's finished CTAs); scores[pair] = score word
 template <int NV>
-__global__ void __launch_bounds__(kPairThreads) pair_gather_kernel(const MaskDesc *__restrict__ masks, const int32_t *__restrict__ pair_mask,
-                                                                   const int32_t *__restrict__ pair_slot, const uint32_t *__restrict__ planes,
+__global__ void __launch_bounds__(kPairThreads) pair_gather_kernel(const MaskDesc *__restrict__ masks, const PairList pairs,
+                                                                   const uint32_t *__restrict__ planes,
                                                                    PlaneGeom g, ShiftSet shifts, int *__restrict__ acc, int32_t *__restrict__ scores)
 {
     __shared__ int s_cnt[2 * NV];
     __shared__ int s_last;
     const int pr = blockIdx.x, part = blockIdx.y;
-    const MaskDesc md = masks[pair_mask[pr]];
-    const uint32_t *plane = planes + g.row_offset(pair_slot[pr], 0);
+    const MaskDesc md = masks[pairs.mask[pr]];
+    const uint32_t *plane = planes + g.row_offset(pairs.slot[pr], 0);
     const int n_orient = shifts.mirror ? 2 : 1;
     int cnt[2 * NV];
 #pragma unroll
@@ -95,6 +104,7 @@ __global__ void __launch_bounds__(kPairThreads) pair_gather_kernel(const MaskDes
     int word = best;
     if (n_orient == 2 && bestm > best) word = bestm | CDS_SCORE_MIRROR_BIT;            // strict :189
     scores[pr] = word;
+    for (int v = 0; v <= 2 * NV; v++) __stcg(&pacc[v], 0);
 }
 
 struct PairRequest {
@@ -130,7 +140,7 @@ struct PairDev {
     struct Lane { cudaStream_t stream = nullptr; uint8_t *d_rgb = nullptr; uint8_t *h_rgb = nullptr; bool busy = false; };
     std::vector<Lane> lanes;
     // batch buffers
-    int32_t *d_pm = nullptr, *d_ps = nullptr, *d_scores = nullptr, *h_pm = nullptr, *h_ps = nullptr, *h_scores = nullptr;
+    int32_t *h_scores = nullptr, *d_scores_alias = nullptr;      // pinned + mapped: the kernel writes, the dispatcher reads
     int *d_acc = nullptr;
     int64_t batches = 0, requests = 0, uploads = 0;
 };
@@ -150,17 +160,17 @@ struct cds_pairq {
 
 namespace {
 
-void launch_pair_gather(const cds_pairq *q, PairDev &pd, int n, const MaskDesc *descs)
+// pairs [first, first + n) of the batch (n <= kPairsPerLaunch); consecutive launches of a batch share the accumulators in stream order
+void launch_pair_gather(const cds_pairq *q, PairDev &pd, const PairList &pl, int first, int n, const MaskDesc *descs)
 {
     const ShiftSet &sh = q->ms->shifts;
     const dim3 grid((unsigned) n, kPairSplit);
     const int nv = sh.n <= 1 ? 1 : (sh.n <= 9 ? 9 : (sh.n <= 17 ? 17 : CDS_MAX_SHIFT_OFFSETS));
-    const size_t acc_bytes = (size_t) n * (2 * nv + 1) * sizeof(int);
-    cudaMemsetAsync(pd.d_acc, 0, acc_bytes, pd.stream);
-    if (nv == 1) pair_gather_kernel<1><<<grid, kPairThreads, 0, pd.stream>>>(descs, pd.d_pm, pd.d_ps, pd.planes, q->g, sh, pd.d_acc, pd.d_scores);
-    else if (nv == 9) pair_gather_kernel<9><<<grid, kPairThreads, 0, pd.stream>>>(descs, pd.d_pm, pd.d_ps, pd.planes, q->g, sh, pd.d_acc, pd.d_scores);
-    else if (nv == 17) pair_gather_kernel<17><<<grid, kPairThreads, 0, pd.stream>>>(descs, pd.d_pm, pd.d_ps, pd.planes, q->g, sh, pd.d_acc, pd.d_scores);
-    else pair_gather_kernel<CDS_MAX_SHIFT_OFFSETS><<<grid, kPairThreads, 0, pd.stream>>>(descs, pd.d_pm, pd.d_ps, pd.planes, q->g, sh, pd.d_acc, pd.d_scores);
+    int32_t *out = pd.d_scores_alias + first;
+    if (nv == 1) pair_gather_kernel<1><<<grid, kPairThreads, 0, pd.stream>>>(descs, pl, pd.planes, q->g, sh, pd.d_acc, out);
+    else if (nv == 9) pair_gather_kernel<9><<<grid, kPairThreads, 0, pd.stream>>>(descs, pl, pd.planes, q->g, sh, pd.d_acc, out);
+    else if (nv == 17) pair_gather_kernel<17><<<grid, kPairThreads, 0, pd.stream>>>(descs, pl, pd.planes, q->g, sh, pd.d_acc, out);
+    else pair_gather_kernel<CDS_MAX_SHIFT_OFFSETS><<<grid, kPairThreads, 0, pd.stream>>>(descs, pl, pd.planes, q->g, sh, pd.d_acc, out);
 }
 
 void dispatcher(cds_pairq *q, PairDev *pdp)
@@ -189,18 +199,16 @@ void dispatcher(cds_pairq *q, PairDev *pdp)
         if (n == 0) continue;
         last_n = n;
         cudaError_t e = cudaSuccess;
-        for (int i = 0; i < n; i++) {
-            pd.h_pm[i] = batch[i]->mask;
-            pd.h_ps[i] = batch[i]->slot;
+        for (int i = 0; i < n; i++)
             if (batch[i]->ready && e == cudaSuccess) e = cudaStreamWaitEvent(pd.stream, batch[i]->ready, 0);
-        }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(pd.d_pm, pd.h_pm, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, pd.stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(pd.d_ps, pd.h_ps, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, pd.stream);
-        if (e == cudaSuccess) {
-            launch_pair_gather(q, pd, n, q->ms->d_descs[pd.d]);
+        for (int first = 0; first < n && e == cudaSuccess; first += kPairsPerLaunch) {
+            const int cnt = std::min(kPairsPerLaunch, n - first);
+            PairList pl;
+            for (int i = 0; i < cnt; i++) { pl.mask[i] = batch[first + i]->mask; pl.slot[i] = batch[first + i]->slot; }
+            for (int i = cnt; i < kPairsPerLaunch; i++) { pl.mask[i] = 0; pl.slot[i] = 0; }
+            launch_pair_gather(q, pd, pl, first, cnt, q->ms->d_descs[pd.d]);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(pd.h_scores, pd.d_scores, (size_t) n * sizeof(int32_t), cudaMemcpyDeviceToHost, pd.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(pd.stream);
         if (e != cudaSuccess) cudaGetLastError();
         {
@@ -263,12 +271,10 @@ extern "C" cds_status cds_pairq_create(cds_ctx *ctx, const cds_maskset *ms, int3
                 if (st == CDS_OK) st = ctx->check(cudaMalloc(&pd->lanes[l].d_rgb, img_bytes + 64), "cudaMalloc(pair staging)");
                 if (st == CDS_OK) st = ctx->check(cudaHostAlloc(&pd->lanes[l].h_rgb, img_bytes, cudaHostAllocDefault), "cudaHostAlloc(pair staging)");
             }
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&pd->d_pm, (size_t) max_batch * sizeof(int32_t)), "cudaMalloc");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&pd->d_ps, (size_t) max_batch * sizeof(int32_t)), "cudaMalloc");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&pd->d_scores, (size_t) max_batch * sizeof(int32_t)), "cudaMalloc");
-            if (st == CDS_OK) st = ctx->check(cudaMalloc(&pd->d_acc, (size_t) max_batch * nv_max * sizeof(int)), "cudaMalloc");
-            if (st == CDS_OK) st = ctx->check(cudaHostAlloc(&pd->h_pm, (size_t) 3 * max_batch * sizeof(int32_t), cudaHostAllocDefault), "cudaHostAlloc");
-            if (st == CDS_OK) { pd->h_ps = pd->h_pm + max_batch; pd->h_scores = pd->h_ps + max_batch; }
+            if (st == CDS_OK) st = ctx->check(cudaMalloc(&pd->d_acc, (size_t) kPairsPerLaunch * nv_max * sizeof(int)), "cudaMalloc");
+            if (st == CDS_OK) st = ctx->check(cudaMemsetAsync(pd->d_acc, 0, (size_t) kPairsPerLaunch * nv_max * sizeof(int), pd->stream), "memset");
+            if (st == CDS_OK) st = ctx->check(cudaHostAlloc(&pd->h_scores, (size_t) max_batch * sizeof(int32_t), cudaHostAllocMapped), "cudaHostAlloc");
+            if (st == CDS_OK) st = ctx->check(cudaHostGetDevicePointer((void **) &pd->d_scores_alias, pd->h_scores, 0), "cudaHostGetDevicePointer");
             if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(pd->stream), "pair cache");
             q->devs.push_back(std::move(pd));
         }
@@ -295,8 +301,8 @@ extern "C" void cds_pairq_destroy(cds_pairq *q)
             if (l.h_rgb) cudaFreeHost(l.h_rgb);
         }
         for (auto &s : pd->slots) if (s.ready) cudaEventDestroy(s.ready);
-        for (void *p : {(void *) pd->planes, (void *) pd->d_pm, (void *) pd->d_ps, (void *) pd->d_scores, (void *) pd->d_acc}) if (p) cudaFree(p);
-        if (pd->h_pm) cudaFreeHost(pd->h_pm);
+        for (void *p : {(void *) pd->planes, (void *) pd->d_acc}) if (p) cudaFree(p);
+        if (pd->h_scores) cudaFreeHost(pd->h_scores);
     }
     cudaGetLastError();
     delete q;

@@ -75,6 +75,8 @@ struct DevState {
     int pair_W = 0, pair_H = 0;
     uint16_t *d_slice_tab = nullptr;  // shape path: slice number of every (channel pair, max, second) (cds_shape.cu), built on first use
     std::vector<cudaEvent_t> shape_timing;   // pairs around every window's pair kernel
+    void *h_pinned2 = nullptr;               // shape path: pinned host slots for inflated PNG scanlines
+    size_t h_pinned2_bytes = 0;
 };
 void shape_release_dev(DevState &ds);
 

@@ -734,6 +734,9 @@ void shape_release_dev(DevState &ds)
     ds.d_slice_tab = nullptr;
     for (cudaEvent_t e : ds.shape_timing) cudaEventDestroy(e);
     ds.shape_timing.clear();
+    if (ds.h_pinned2) cudaFreeHost(ds.h_pinned2);
+    ds.h_pinned2 = nullptr;
+    ds.h_pinned2_bytes = 0;
 }
 
 // launches the fused derive kernel for n images; false when the disc is outside its envelope
@@ -1036,6 +1039,7 @@ struct ShapeDevWork {
     uint32_t *d_tsig = nullptr;
     uint8_t *d_comp = nullptr;
     TiffStrip *d_strips = nullptr;
+    uint8_t *d_pngraw = nullptr, *d_bps = nullptr;
     int32_t *d_pm = nullptr, *d_ps = nullptr;
     long long *d_gap = nullptr, *d_he = nullptr;
     uint8_t *d_mir = nullptr;
@@ -1051,6 +1055,7 @@ struct ShapeDevWork {
 // Targets either as pixels (target_rgb) or as TIFF files stored back to back (blob + offsets, decoded on the device).
 static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *sms_c, const uint8_t *target_rgb,
                                          const uint8_t *blob, const int64_t *offsets, const uint16_t *gradient,
+                                         const uint8_t *png_blob, const int64_t *png_offsets,
                                          const uint8_t *zgap_rgb, const uint8_t *has_variants, int64_t n_targets,
                                          const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
                                          int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
@@ -1074,7 +1079,8 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
     }
     // a missing gradient can only be expressed through has_variants; a NULL gradient array with scorable pairs is an error
     const bool from_files = blob != nullptr && offsets != nullptr;
-    if (any_scored && ((!target_rgb && !from_files) || !gradient)) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs: target / gradient images are NULL");
+    const bool from_png = png_blob != nullptr && png_offsets != nullptr;
+    if (any_scored && ((!target_rgb && !from_files) || (!gradient && !from_png))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs: target / gradient images are NULL");
     ctx->stats = cds_search_stats{};
     if (!any_scored) return CDS_OK;
     if (from_files)
@@ -1129,6 +1135,9 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
         }
         strips_cap = (size_t) win * tiff_strips_bound(W, H);
     }
+    // gradient images as PNG files: inflated scanlines of a window go through two pinned host slots per device
+    const size_t png_stride = ((size_t) H * (1 + (size_t) W * 2) + 15) / 16 * 16;
+    const size_t png_slot_bytes = (size_t) win * png_stride + (size_t) win;
     for (int d = 0; d < used; d++) {
         DevState &ds = ctx->devs[d];
         ShapeDevWork &wk = work[d];
@@ -1160,6 +1169,16 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
             SH_CUDA(ctx, g.alloc((void **) &wk.d_comp, comp_cap));
             SH_CUDA(ctx, g.alloc((void **) &wk.d_strips, strips_cap * sizeof(TiffStrip)));
             SH_TRY(ctx->ensure_pinned(ds, 2 * strips_cap * sizeof(TiffStrip)));
+        }
+        if (from_png) {
+            SH_CUDA(ctx, g.alloc((void **) &wk.d_pngraw, (size_t) win * png_stride));
+            SH_CUDA(ctx, g.alloc((void **) &wk.d_bps, (size_t) win));
+            if (ds.h_pinned2_bytes < 2 * png_slot_bytes) {
+                SH_CUDA(ctx, cudaStreamSynchronize(ds.copy_stream));
+                if (ds.h_pinned2) { cudaFreeHost(ds.h_pinned2); ds.h_pinned2 = nullptr; ds.h_pinned2_bytes = 0; }
+                SH_CUDA(ctx, cudaHostAlloc(&ds.h_pinned2, 2 * png_slot_bytes, cudaHostAllocDefault));
+                ds.h_pinned2_bytes = 2 * png_slot_bytes;
+            }
         }
         const size_t np = wk.pm.size();
         SH_CUDA(ctx, g.alloc((void **) &wk.d_pm, np * sizeof(int32_t)));
@@ -1212,17 +1231,31 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
                 SH_CUDA(ctx, cudaMemcpyAsync(wk.d_t[slot] + (size_t) s0 * bytes, target_rgb + (size_t) t0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, ds.copy_stream));
                 ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
             }
-            SH_CUDA(ctx, cudaMemcpyAsync(wk.d_grad[slot] + (size_t) s0 * px, gradient + (size_t) t0 * px, (size_t) cnt * px * sizeof(uint16_t), cudaMemcpyHostToDevice, ds.copy_stream));
-            ctx->stats.h2d_bytes += (int64_t) (cnt * px * sizeof(uint16_t));
+            if (!from_png) {
+                SH_CUDA(ctx, cudaMemcpyAsync(wk.d_grad[slot] + (size_t) s0 * px, gradient + (size_t) t0 * px, (size_t) cnt * px * sizeof(uint16_t), cudaMemcpyHostToDevice, ds.copy_stream));
+                ctx->stats.h2d_bytes += (int64_t) (cnt * px * sizeof(uint16_t));
+            }
             if (zgap_rgb) {
                 SH_CUDA(ctx, cudaMemcpyAsync(wk.d_z[slot] + (size_t) s0 * bytes, zgap_rgb + (size_t) t0 * bytes, (size_t) cnt * bytes, cudaMemcpyHostToDevice, ds.copy_stream));
                 ctx->stats.h2d_bytes += (int64_t) (cnt * bytes);
             }
             a = e;
         }
+        if (j >= 2 && (from_files || from_png)) SH_CUDA(ctx, cudaEventSynchronize(ds.up_done[slot]));      // the slot's previous tables / scanlines have left the host
+        if (from_png) {
+            // inflate this window's gradient files on host threads (the devices are busy with earlier windows meanwhile)
+            uint8_t *h_f = (uint8_t *) ds.h_pinned2 + (size_t) slot * png_slot_bytes, *h_bps = h_f + (size_t) win * png_stride;
+            const int64_t cnt = a1 - a0;
+            SH_TRY(png_inflate_many(ctx, "cds_shape_score_pairs_files", png_blob, png_offsets, active.data() + a0, cnt, W, H, h_f, png_stride, h_bps));
+            SH_CUDA(ctx, cudaMemcpyAsync(wk.d_pngraw, h_f, (size_t) cnt * png_stride, cudaMemcpyHostToDevice, ds.copy_stream));
+            SH_CUDA(ctx, cudaMemcpyAsync(wk.d_bps, h_bps, (size_t) cnt, cudaMemcpyHostToDevice, ds.copy_stream));
+            ctx->stats.h2d_bytes += (int64_t) (cnt * png_stride + cnt);
+            launch_png_unfilter(wk.d_pngraw, png_stride, wk.d_bps, cnt, W, H, wk.d_grad[slot], ds.copy_stream);
+            ctx->stats.kernel_launches++;
+            SH_CUDA(ctx, cudaGetLastError());
+        }
         if (from_files) {
             TiffStrip *h_tab = (TiffStrip *) ds.h_pinned + (size_t) slot * strips_cap;
-            if (j >= 2) SH_CUDA(ctx, cudaEventSynchronize(ds.up_done[slot]));      // the slot's previous table has left the host
             memcpy(h_tab, strips.data(), strips.size() * sizeof(TiffStrip));
             SH_CUDA(ctx, cudaMemcpyAsync(wk.d_strips, h_tab, strips.size() * sizeof(TiffStrip), cudaMemcpyHostToDevice, ds.copy_stream));
             ctx->stats.h2d_bytes += (int64_t) (strips.size() * sizeof(TiffStrip));
@@ -1318,7 +1351,7 @@ extern "C" cds_status cds_shape_score_pairs(cds_ctx *ctx, const cds_shape_maskse
                                             int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
 {
     return cds::abi_guard("cds_shape_score_pairs", [&]() -> cds_status {
-        return shape_score_pairs_impl(ctx, sms, target_rgb, nullptr, nullptr, gradient, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
+        return shape_score_pairs_impl(ctx, sms, target_rgb, nullptr, nullptr, gradient, nullptr, nullptr, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
                                       gap_out, high_expr_out, mirrored_out);
     });
 }
@@ -1330,7 +1363,20 @@ extern "C" cds_status cds_shape_score_pairs_tiff(cds_ctx *ctx, const cds_shape_m
 {
     return cds::abi_guard("cds_shape_score_pairs_tiff", [&]() -> cds_status {
         if (n_targets > 0 && (!blob || !offsets)) { set_tls_error("cds_shape_score_pairs_tiff: NULL files"); return CDS_ERR_BAD_ARG; }
-        return shape_score_pairs_impl(ctx, sms, nullptr, blob, offsets, gradient, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
+        return shape_score_pairs_impl(ctx, sms, nullptr, blob, offsets, gradient, nullptr, nullptr, zgap_rgb, has_variants, n_targets, pair_mask, pair_target, n_pairs,
                                       gap_out, high_expr_out, mirrored_out);
+    });
+}
+
+extern "C" cds_status cds_shape_score_pairs_files(cds_ctx *ctx, const cds_shape_maskset *sms, const uint8_t *tiff_blob, const int64_t *tiff_offsets,
+                                                  const uint8_t *png_blob, const int64_t *png_offsets, const uint8_t *zgap_rgb,
+                                                  const uint8_t *has_variants, int64_t n_targets,
+                                                  const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
+                                                  int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out)
+{
+    return cds::abi_guard("cds_shape_score_pairs_files", [&]() -> cds_status {
+        if (n_targets > 0 && (!tiff_blob || !tiff_offsets || !png_blob || !png_offsets)) { set_tls_error("cds_shape_score_pairs_files: NULL files"); return CDS_ERR_BAD_ARG; }
+        return shape_score_pairs_impl(ctx, sms, nullptr, tiff_blob, tiff_offsets, nullptr, png_blob, png_offsets, zgap_rgb, has_variants, n_targets,
+                                      pair_mask, pair_target, n_pairs, gap_out, high_expr_out, mirrored_out);
     });
 }

@@ -40,6 +40,16 @@ cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int h
 }  // namespace cds
 struct cds_ctx;
 namespace cds {
+// host decoders (cds_formats.cpp)
+cds_status tiff_decode_host(const uint8_t *file, size_t len, int width, int height, uint8_t *out_rgb, std::string &err);
+cds_status png_inflate(const uint8_t *file, size_t len, int width, int height, int *bit_depth_out, uint8_t *out, size_t out_cap, std::string &err);
+// PNG scanline filters undone on the device: image i's inflated stream at filtered + i * stride, bytes_per_sample[i] in {1, 2};
+// out = uint16[n][height][width]
+cds_status png_inflate_many(cds_ctx *ctx, const char *who, const uint8_t *blob, const int64_t *offsets, const int64_t *which, int64_t cnt,
+                            int W, int H, uint8_t *h_filtered, size_t stride, uint8_t *bps);
+void launch_png_unfilter(const uint8_t *filtered, size_t stride, const uint8_t *bytes_per_sample, int64_t n, int width, int height,
+                         uint16_t *out, cudaStream_t s);
+
 // Uploads files [i0, i0 + cnt) of the blob and decodes them into d_rgb, everything on stream `s` (cds_ingest.cu); d_comp / d_strips
 // must hold the chunk (ingest_bounds gives sizes that suffice for any `cnt` consecutive files).  `strips` is host scratch.
 cds_status ingest_chunk(cds_ctx *ctx, const char *who, const uint8_t *blob, const int64_t *offsets, int64_t i0, int64_t cnt, int W, int H,

@@ -231,6 +231,56 @@ cds_status cds_search_stream_matches_tiff(cds_ctx *ctx, const cds_maskset *ms, c
                                           int32_t *out_mask, int64_t *out_target, int32_t *out_score, uint8_t *out_mirrored,
                                           int64_t *out_count);
 
+/* ---- what the reference reads that is not a PackBits / stored RGB TIFF (csrc/cds_formats.cpp) ---- */
+
+/* Host only.  Decodes the first image of any 8-bit RGB strip TIFF the tag parser understands -- uncompressed, PackBits, or LZW with or
+ * without the horizontal predictor (tag 317) -- into out_rgb = uint8[height][width][3].  LZW files are what the reference hands to
+ * ImageJ's Opener (API/imageprocessing/ImageArrayUtils.java:176-182, 196-198: every TIFF whose compression is not PackBits). */
+cds_status cds_tiff_decode_rgb_host(const uint8_t *file, int64_t len, int32_t width, int32_t height, uint8_t *out_rgb);
+/* Host only.  Rewrites such a file as the PackBits TIFF (strips of 8 rows) the device ingest takes, so that an LZW library can be fed
+ * to cds_search_stream_tiff / cds_library_add_tiff after one pass on the host.  capacity >= cds_tiff_encode_bound(width, height, 8). */
+cds_status cds_tiff_to_packbits(const uint8_t *file, int64_t len, uint8_t *out, int64_t capacity, int64_t *out_len);
+
+/* PNG: the gradient images of gradientScores are 16-bit grayscale PNG files, which the reference reads through ImageIO.read
+ * (API/imageprocessing/ImageArrayUtils.java:98-121, 176-178).  Supported: grayscale, 8 or 16 bits, not interlaced. */
+typedef struct cds_png_info {
+    int32_t width, height;
+    int32_t bit_depth;            /* 8 or 16 for decodable files */
+    int32_t color_type;           /* 0 = grayscale */
+    int32_t interlace;
+    int32_t decodable;
+    int64_t data_bytes;           /* sum of the IDAT chunk lengths */
+} cds_png_info;
+cds_status cds_png_probe(const uint8_t *file, int64_t len, cds_png_info *info);      /* host only */
+/* n PNG files stored back to back (blob / offsets as for the TIFF calls) -> out = uint16[n][height][width] (8-bit files are widened,
+ * like ImageArray.get on a ByteImageArray).  The zlib streams are inflated on host threads, the scanline filters (None, Sub, Up,
+ * Average, Paeth) are undone and the samples byte-swapped on device 0. */
+cds_status cds_png_decode_gray16(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n, int32_t width, int32_t height, uint16_t *out);
+/* Host only: a 16-bit grayscale PNG writer for tests and the bench (filter_mode 0..4 = that filter on every row, -1 = per row the
+ * filter with the smallest sum of absolute differences).  cds_png_encode_bound gives a capacity that suffices. */
+int64_t    cds_png_encode_bound(int32_t width, int32_t height);
+cds_status cds_png_encode_gray16(const uint16_t *pixels, int32_t width, int32_t height, int32_t filter_mode,
+                                 uint8_t *out, int64_t capacity, int64_t *out_len);
+
+/* zip archives: libraries are routinely zip files whose entries are the MIPs (API/mips/NeuronMIPUtils.java:124-129, 177-227).
+ * cds_zip_index reads the central directory (entries may be NULL with capacity 0 to count); a stored entry (method 0) IS the file:
+ * archive + data_offset, `size` bytes -- a (blob, offsets) pair for the TIFF calls can point straight into the mapped archive when
+ * the wanted entries are stored and consecutive; cds_zip_read copies (stored) or inflates (deflate) an entry and checks its CRC.
+ * cds_zip_find looks an entry up like the reference: the exact name, else the first non-directory entry with the same file name
+ * (NeuronMIPUtils.openZipEntryStream :193-208); -1 when there is none.  zip64 is not supported. */
+typedef struct cds_zip_entry {
+    int64_t name_offset;          /* the entry's name inside the archive (not NUL-terminated) */
+    int32_t name_len;
+    int32_t method;               /* 0 stored, 8 deflate */
+    int64_t data_offset;
+    int64_t compressed_size, size;
+    uint32_t crc32;
+    int32_t is_directory;
+} cds_zip_entry;
+cds_status cds_zip_index(const uint8_t *archive, int64_t len, cds_zip_entry *entries, int64_t capacity, int64_t *n_entries);
+int64_t    cds_zip_find(const uint8_t *archive, const cds_zip_entry *entries, int64_t n_entries, const char *name);
+cds_status cds_zip_read(const uint8_t *archive, int64_t len, const cds_zip_entry *entry, uint8_t *out, int64_t capacity);
+
 /* One mask x one target held in host memory: the literal single-pair call of the Java API
  * (ColorDepthSearchAlgorithm.calculateMatchingScore, API/cds/ColorDepthSearchAlgorithm.java:60-61). */
 cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, int32_t mask_index, const uint8_t *target_rgb,
@@ -298,6 +348,16 @@ cds_status cds_shape_score_pairs_tiff(cds_ctx *ctx, const cds_shape_maskset *sms
                                       const uint16_t *gradient, const uint8_t *zgap_rgb, const uint8_t *has_variants, int64_t n_targets,
                                       const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
                                       int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out);
+
+/* The same scoring with BOTH inputs as files in host memory, the way gradientScores finds them: targets as PackBits / stored RGB
+ * TIFF files, gradient images as 16-bit (or 8-bit) grayscale PNG files (png_blob / png_offsets, n_targets + 1 offsets).  The PNG
+ * streams of a window of targets are inflated on host threads while the device works on the previous window; filters and byte
+ * order are undone on the device. */
+cds_status cds_shape_score_pairs_files(cds_ctx *ctx, const cds_shape_maskset *sms, const uint8_t *tiff_blob, const int64_t *tiff_offsets,
+                                       const uint8_t *png_blob, const int64_t *png_offsets, const uint8_t *zgap_rgb,
+                                       const uint8_t *has_variants, int64_t n_targets,
+                                       const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs,
+                                       int64_t *gap_out, int64_t *high_expr_out, uint8_t *mirrored_out);
 
 /* The zgap image alone (f3 in SURVEY.md section 8f): maxFilter(radius)(mask(threshold)(clearLabels(rgb))) for n images. */
 cds_status cds_make_zgap(cds_ctx *ctx, const uint8_t *rgb, int64_t n, int32_t width, int32_t height, int32_t threshold,
