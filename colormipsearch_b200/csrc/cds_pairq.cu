@@ -26,6 +26,11 @@
 #include <thread>
 #include <unordered_map>
 
+#include <climits>
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "cds_runtime.h"
 
 using namespace cds;
@@ -112,8 +117,20 @@ struct PairRequest {
     cudaEvent_t ready = nullptr;         // the slot's upload + encode (nullptr: already resident)
     int32_t word = 0;
     cds_status status = CDS_OK;
-    bool done = false;
+    std::atomic<bool> done{false};
 };
+
+// Callers sleep on the device's batch counter (a futex word) instead of a condition variable: one FUTEX_WAKE releases all callers
+// of a batch at once and none of them has to take a mutex on the way out (40 threads re-acquiring one mutex one after the other
+// were half of a batch's latency).
+inline void futex_wait_u32(std::atomic<uint32_t> *addr, uint32_t expected)
+{
+    syscall(SYS_futex, reinterpret_cast<uint32_t *>(addr), FUTEX_WAIT_PRIVATE, expected, nullptr, nullptr, 0);
+}
+inline void futex_wake_all(std::atomic<uint32_t> *addr)
+{
+    syscall(SYS_futex, reinterpret_cast<uint32_t *>(addr), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
+}
 
 struct CacheSlot {
     uint64_t key = 0;
@@ -134,7 +151,8 @@ struct PairDev {
     std::unordered_map<uint64_t, int> by_key;
     std::deque<PairRequest *> queue;
     std::mutex mu;
-    std::condition_variable cv_work, cv_done, cv_slot;
+    std::condition_variable cv_work, cv_slot;
+    std::atomic<uint32_t> generation{0};  // batches completed: what callers sleep on
     std::thread worker;
     // upload staging: one device buffer + stream + pinned host buffer per upload lane (callers take a lane for the length of an upload)
     struct Lane { cudaStream_t stream = nullptr; uint8_t *d_rgb = nullptr; uint8_t *h_rgb = nullptr; bool busy = false; };
@@ -222,10 +240,11 @@ void dispatcher(cds_pairq *q, PairDev *pdp)
                 CacheSlot &cs = pd.slots[r->slot];
                 cs.ready_pending = false;            // the batch ran behind the slot's event
                 if (--cs.refs == 0) pd.cv_slot.notify_all();
-                r->done = true;
             }
         }
-        pd.cv_done.notify_all();
+        for (int i = 0; i < n; i++) batch[i]->done.store(true, std::memory_order_release);      // (the request lives on its caller's stack: not touched after this)
+        pd.generation.fetch_add(1, std::memory_order_release);
+        futex_wake_all(&pd.generation);
     }
 }
 
@@ -404,10 +423,14 @@ extern "C" cds_status cds_pairq_score(cds_pairq *q, int32_t mask_index, uint64_t
         }
         if (st != CDS_OK) return st;
         {
-            std::unique_lock<std::mutex> lk(pd.mu);
+            std::lock_guard<std::mutex> lk(pd.mu);
             pd.queue.push_back(&req);
-            pd.cv_work.notify_one();
-            pd.cv_done.wait(lk, [&] { return req.done; });
+        }
+        pd.cv_work.notify_one();
+        for (;;) {
+            const uint32_t g = pd.generation.load(std::memory_order_acquire);
+            if (req.done.load(std::memory_order_acquire)) break;
+            futex_wait_u32(&pd.generation, g);
         }
         if (req.status != CDS_OK) { set_tls_error("cds_pairq_score: the batch's kernel failed"); return req.status; }
         *score_out = req.word & ~CDS_SCORE_MIRROR_BIT;
