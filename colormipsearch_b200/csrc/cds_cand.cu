@@ -37,7 +37,8 @@ constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy dest
 constexpr int kQueue = 64;          // candidate slots per warp (power of two, >= 2 * 32)
 constexpr int kWordQueue = 64;      // word slots per warp (power of two, >= 2 * 32)
 constexpr int kTicketQueue = 256;   // passing tickets of a band that wait in the CTA-wide queue (16-bit slots; what is left of the 227 kB)
-constexpr uint32_t kTicketFree = 0xFFFFu;
+constexpr uint32_t kTicketFree = 0xFFFFu;     // slot reserved or unused, not written yet
+constexpr uint32_t kTicketSkip = 0xFFFEu;     // slot written, holds no ticket (its batch did not fit and is scanned by its own warp)
 
 struct CandParams {
     const MaskDesc *masks;
@@ -503,11 +504,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                         int base = 0;
                         if (lane == 0) base = atomicAdd(&s_tqc[4 * stage], cnt);
                         base = __shfl_sync(0xffffffffu, base, 0);
-                        const bool fits = base + cnt <= kTicketQueue && __all_sync(0xffffffffu, !pass || k < kTicketFree);
-                        if (fits) {
-                            if (pass) s_tq[stage * kTicketQueue + base + __popc(live & lt_mask)] = (uint16_t) k;
-                            queued = true;
-                        }
+                        const bool fits = base + cnt <= kTicketQueue && __all_sync(0xffffffffu, !pass || k < kTicketSkip);
+                        // every reserved slot inside the queue is written -- with the ticket, or with "nothing here" when the batch
+                        // does not fit as a whole: a popper that has taken a slot waits for its value
+                        const int slot = base + __popc(live & lt_mask);
+                        if (pass && slot < kTicketQueue) s_tq[stage * kTicketQueue + slot] = (uint16_t) (fits ? k : kTicketSkip);
+                        queued = fits;
                     }
                     __syncwarp();
                     if (lane == 0) { __threadfence_block(); atomicAdd(&s_tqc[4 * stage + 2], 1); }
@@ -548,6 +550,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                                     uint32_t v;
                                     while ((v = tq[h]) == kTicketFree) {}          // its pusher has reserved the slot and is about to write it
                                     tq[h] = (uint16_t) kTicketFree;
+                                    if (v == kTicketSkip) continue;
                                     kk = (int) v;
                                     break;
                                 }

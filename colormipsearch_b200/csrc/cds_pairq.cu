@@ -154,6 +154,8 @@ struct PairDev {
     std::condition_variable cv_work, cv_slot;
     std::atomic<uint32_t> generation{0};  // batches completed: what callers sleep on
     std::thread worker;
+    bool busy = false;                   // the dispatcher is between taking a batch and finishing it
+    std::condition_variable cv_idle;
     // upload staging: one device buffer + stream + pinned host buffer per upload lane (callers take a lane for the length of an upload)
     struct Lane { cudaStream_t stream = nullptr; uint8_t *d_rgb = nullptr; uint8_t *h_rgb = nullptr; bool busy = false; };
     std::vector<Lane> lanes;
@@ -174,6 +176,11 @@ struct cds_pairq {
     std::vector<std::unique_ptr<PairDev>> devs;
     std::atomic<bool> stop{false};
     std::atomic<uint64_t> anon{0};
+    // masks may be added to the mask set while the queue exists (one provider, one queue, an algorithm per mask): a call that names a
+    // mask the queue has not seen quiesces the dispatchers, rebuilds the device descriptors and goes on
+    std::atomic<int> n_masks{0};
+    std::vector<int32_t> sizes;          // getQuerySize() of the masks the queue knows (a private copy: the mask set's vector may grow)
+    std::mutex refresh_mu;
 };
 
 namespace {
@@ -212,6 +219,7 @@ void dispatcher(cds_pairq *q, PairDev *pdp)
                 pd.cv_work.wait_until(lk, deadline, [&] { return q->stop.load() || (int) pd.queue.size() >= expect; });
             }
             while (!pd.queue.empty() && (int) batch.size() < q->max_batch) { batch.push_back(pd.queue.front()); pd.queue.pop_front(); }
+            pd.busy = !batch.empty();
         }
         const int n = (int) batch.size();
         if (n == 0) continue;
@@ -241,7 +249,9 @@ void dispatcher(cds_pairq *q, PairDev *pdp)
                 cs.ready_pending = false;            // the batch ran behind the slot's event
                 if (--cs.refs == 0) pd.cv_slot.notify_all();
             }
+            pd.busy = false;
         }
+        pd.cv_idle.notify_all();
         for (int i = 0; i < n; i++) batch[i]->done.store(true, std::memory_order_release);      // (the request lives on its caller's stack: not touched after this)
         pd.generation.fetch_add(1, std::memory_order_release);
         futex_wake_all(&pd.generation);
@@ -267,6 +277,8 @@ extern "C" cds_status cds_pairq_create(cds_ctx *ctx, const cds_maskset *ms, int3
         std::unique_ptr<cds_pairq> q(new cds_pairq());
         q->ctx = ctx; q->ms = ms; q->max_batch = max_batch; q->max_wait_us = max_wait_us;
         q->g.W = ms->W; q->g.H = ms->H; q->g.pitch = choose_pitch(ms->W); q->g.guard = CDS_GUARD_ROWS;
+        q->sizes = ms->sizes;
+        q->n_masks.store((int) ms->sizes.size());
         const size_t img_bytes = (size_t) ms->W * ms->H * 3;
         const int n_lanes = 8;
         const int nv_max = 2 * CDS_MAX_SHIFT_OFFSETS + 1;
@@ -334,8 +346,30 @@ extern "C" cds_status cds_pairq_score(cds_pairq *q, int32_t mask_index, uint64_t
     return cds::abi_guard("cds_pairq_score", [&]() -> cds_status {
         if (!q || !score_out || !ratio_out || !mirrored_out) { set_tls_error("cds_pairq_score: NULL argument"); return CDS_ERR_BAD_ARG; }
         const cds_maskset *ms = q->ms;
-        if (mask_index < 0 || mask_index >= (int) ms->sizes.size()) { set_tls_error("cds_pairq_score: mask index out of range"); return CDS_ERR_BAD_ARG; }
-        const int P = ms->sizes[mask_index];
+        if (mask_index >= q->n_masks.load(std::memory_order_acquire) && mask_index >= 0) {
+            // a mask added after the queue was created: stop the dispatchers between two batches, rebuild the descriptors, go on
+            std::lock_guard<std::mutex> rl(q->refresh_mu);
+            if (mask_index >= q->n_masks.load()) {
+                std::lock_guard<std::recursive_mutex> cl(q->ctx->mu);
+                if (mask_index < (int) ms->sizes.size()) {
+                    std::vector<std::unique_lock<std::mutex>> held;
+                    for (auto &pd : q->devs) {
+                        held.emplace_back(pd->mu);
+                        pd->cv_idle.wait(held.back(), [&] { return !pd->busy; });
+                    }
+                    const cds_status rs = const_cast<cds_maskset *>(ms)->sync_descs();
+                    if (rs != CDS_OK) return rs;
+                    q->sizes = ms->sizes;                      // (callers read q->sizes only below n_masks, and never while it is replaced: see below)
+                    q->n_masks.store((int) ms->sizes.size(), std::memory_order_release);
+                }
+            }
+        }
+        if (mask_index < 0 || mask_index >= q->n_masks.load(std::memory_order_acquire)) { set_tls_error("cds_pairq_score: mask index out of range"); return CDS_ERR_BAD_ARG; }
+        int P;
+        {
+            std::lock_guard<std::mutex> rl(q->refresh_mu);     // short: guards the vector against a concurrent refresh
+            P = q->sizes[mask_index];
+        }
         if (P == 0) { *score_out = 0; *ratio_out = 0; *mirrored_out = 0; return CDS_OK; }   // PixelMatch...:169-170 (before the size check)
         if (target_width != ms->W || target_height != ms->H) {
             char buf[200];

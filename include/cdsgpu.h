@@ -298,8 +298,9 @@ cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, int32_t mask_
  *   cache_targets code planes kept on every device (2.8 MB each for 1210 x 566); least recently used are replaced
  *   target_key    the caller's identity of the image (the Java side passes the cache key / System.identityHashCode of the
  *                 ImageArray); equal keys MUST mean equal pixels; 0 = do not cache
- * Scores, ratio and mirrored flag are exactly cds_score_pair_rgb's.  The mask set must not be modified or destroyed while the
- * queue exists.  Errors as cds_score_pair_rgb (CDS_ERR_SIZE_MISMATCH for a target of another size). */
+ * Scores, ratio and mirrored flag are exactly cds_score_pair_rgb's.  Masks may be ADDED to the mask set while the queue exists (one
+ * provider = one mask set + one queue, one algorithm object per mask): the first call that names a new mask pauses the dispatchers
+ * between two batches and picks the new masks up.  The mask set must not be destroyed before the queue.  Errors as cds_score_pair_rgb (CDS_ERR_SIZE_MISMATCH for a target of another size). */
 typedef struct cds_pairq cds_pairq;
 cds_status cds_pairq_create(cds_ctx *ctx, const cds_maskset *ms, int32_t max_batch, int32_t max_wait_us, int32_t cache_targets, cds_pairq **out);
 void       cds_pairq_destroy(cds_pairq *q);

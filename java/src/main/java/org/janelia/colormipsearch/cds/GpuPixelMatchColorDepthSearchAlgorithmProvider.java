@@ -24,7 +24,12 @@ import org.janelia.colormipsearch.model.ComputeFileType;
  * (ColorDepthSearchAlgorithmProviderFactory.java:30-74): same parameters, same per-mask overrides, same exceptions; the
  * scoring runs in libcdsgpu (no JVM-side compute).  Selected with `--cds-provider gpu` (INTEGRATION.md).
  *
- * This class serves the literal single-pair API (one native call per calculateMatchingScore); throughput comes from
+ * This class serves the literal single-pair API: every calculateMatchingScore is one blocking cds_pairq_score call.  The calls of
+ * the processor's ~40 pool threads (LocalColorMIPSearchProcessor.java:93-105) meet in the library's micro-batching queue and are
+ * scored by one kernel launch per batch; a target that was scored before is found in the device-side cache by its identity (the
+ * reference serves the same ImageArray object to every mask out of its Guava cache, CachedMIPsUtils.java:60-110), so it crosses
+ * PCIe once.  All algorithms of one parameter set share ONE native mask set and ONE queue (masks are appended as algorithms are
+ * created); raise --task-concurrency to a few hundred threads to fill the batches.  Bulk throughput still comes from
  * GpuColorMIPSearchProcessor, which hands whole mask / target lists to one native search.
  *
  * UNVERIFIED (no JDK in the build image of the GPU library).
@@ -44,16 +49,57 @@ public class GpuPixelMatchColorDepthSearchAlgorithmProvider implements ColorDept
     @Override
     public ColorDepthSearchParams getDefaultCDSParams() { return defaults; }
 
+    /** One native mask set + pair queue per (image size, parameter set). */
+    private static final class Shared {
+        MemorySegment maskSet, queue;
+        int nMasks;
+    }
+    private final Map<String, Shared> shared = new java.util.HashMap<>();
+
+    /** A unique id per target ImageArray OBJECT (System.identityHashCode can collide; equal keys must mean equal pixels). */
+    private static final Map<ImageArray<?>, Long> TARGET_IDS = Collections.synchronizedMap(new java.util.WeakHashMap<>());
+    private static final java.util.concurrent.atomic.AtomicLong NEXT_ID = new java.util.concurrent.atomic.AtomicLong();
+    static long targetKey(ImageArray<?> target) { return TARGET_IDS.computeIfAbsent(target, t -> NEXT_ID.incrementAndGet()); }
+
+    private synchronized int addMask(String key, ImageArray<?> queryImage, int queryThreshold, boolean mirror, int dataThreshold, double zTolerance,
+                                     int xyShift, int[][] rects, Shared[] out, int[] sizeOut) {
+        Shared sh = shared.get(key);
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment o = a.allocate(ValueLayout.ADDRESS), size = a.allocate(ValueLayout.JAVA_INT);
+            if (sh == null) {
+                sh = new Shared();
+                MemorySegment p = CdsGpu.pixParams(a, queryThreshold, dataThreshold, zTolerance, xyShift, mirror, rects);
+                CdsGpu.check((int) CdsGpu.masksetCreate.invokeExact(CdsGpu.context(), queryImage.getWidth(), queryImage.getHeight(), p, o));
+                sh.maskSet = o.get(ValueLayout.ADDRESS, 0);
+                shared.put(key, sh);
+            }
+            CdsGpu.check((int) CdsGpu.masksetAddRgb.invokeExact(sh.maskSet, CdsGpu.copyBytes(a, ImageArrayAccess.rgbBytes(queryImage)), 1, size));
+            sizeOut[0] = size.get(ValueLayout.JAVA_INT, 0);
+            if (sh.queue == null) {
+                // max batch 256, wait at most 60 us for company, 4096 cached targets per device (11 GB of code planes for 1210 x 566)
+                CdsGpu.check((int) CdsGpu.pairqCreate.invokeExact(CdsGpu.context(), sh.maskSet, 256, 60, Integer.getInteger("cdsgpu.cachedTargets", 4096), o));
+                sh.queue = o.get(ValueLayout.ADDRESS, 0);
+            }
+            out[0] = sh;
+            return sh.nMasks++;
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+    }
+
     @Override
     public ColorDepthSearchAlgorithm<PixelMatchScore> createColorDepthSearchAlgorithm(ImageArray<?> queryImage, int queryThreshold,
                                                                                       int queryBorderSize, ColorDepthSearchParams cdsParams) {
         double fluct = cdsParams.getDoubleParam("pixColorFluctuation", defaults.getDoubleParam("pixColorFluctuation", 2.0));
         int xyShift = cdsParams.getIntParam("xyShift", defaults.getIntParam("xyShift", 0));
         if ((xyShift & 0x1) == 1) throw new IllegalArgumentException("XY shift parameter must be an even number.");   // :57-60
-        return new Algorithm(queryImage, queryThreshold,
-                cdsParams.getBoolParam("mirrorMask", defaults.getBoolParam("mirrorMask", false)),
-                cdsParams.getIntParam("dataThreshold", defaults.getIntParam("dataThreshold", 100)),
-                fluct / 100, xyShift, rectanglesOf(ignoredRegionsProvider, queryImage));
+        boolean mirror = cdsParams.getBoolParam("mirrorMask", defaults.getBoolParam("mirrorMask", false));
+        int dataThreshold = cdsParams.getIntParam("dataThreshold", defaults.getIntParam("dataThreshold", 100));
+        int[][] rects = rectanglesOf(ignoredRegionsProvider, queryImage);
+        String key = queryImage.getWidth() + "x" + queryImage.getHeight() + ":" + queryThreshold + ":" + mirror + ":" + dataThreshold + ":" + fluct + ":" + xyShift
+                + ":" + java.util.Arrays.deepToString(rects);
+        Shared[] sh = new Shared[1];
+        int[] size = new int[1];
+        int index = addMask(key, queryImage, queryThreshold, mirror, dataThreshold, fluct / 100, xyShift, rects, sh, size);
+        return new Algorithm(queryImage, sh[0].queue, index, size[0]);
     }
 
     /**
@@ -89,19 +135,11 @@ public class GpuPixelMatchColorDepthSearchAlgorithmProvider implements ColorDept
 
     static final class Algorithm implements ColorDepthSearchAlgorithm<PixelMatchScore> {
         private final ImageArray<?> queryImage;
-        private final transient MemorySegment maskSet;   // native handle: not serialisable, Spark mode is unsupported on this provider
-        private final int querySize;
+        private final transient MemorySegment queue;   // native handle: not serialisable, Spark mode is unsupported on this provider
+        private final int maskIndex, querySize;
 
-        Algorithm(ImageArray<?> queryImage, int queryThreshold, boolean mirror, int dataThreshold, double zTolerance, int xyShift, int[][] rects) {
-            this.queryImage = queryImage;
-            try (Arena a = Arena.ofConfined()) {
-                MemorySegment out = a.allocate(ValueLayout.ADDRESS), size = a.allocate(ValueLayout.JAVA_INT);
-                MemorySegment p = CdsGpu.pixParams(a, queryThreshold, dataThreshold, zTolerance, xyShift, mirror, rects);
-                CdsGpu.check((int) CdsGpu.masksetCreate.invokeExact(CdsGpu.context(), queryImage.getWidth(), queryImage.getHeight(), p, out));
-                maskSet = out.get(ValueLayout.ADDRESS, 0);
-                CdsGpu.check((int) CdsGpu.masksetAddRgb.invokeExact(maskSet, CdsGpu.copyBytes(a, ImageArrayAccess.rgbBytes(queryImage)), 1, size));
-                querySize = size.get(ValueLayout.JAVA_INT, 0);
-            } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+        Algorithm(ImageArray<?> queryImage, MemorySegment queue, int maskIndex, int querySize) {
+            this.queryImage = queryImage; this.queue = queue; this.maskIndex = maskIndex; this.querySize = querySize;
         }
 
         @Override public ImageArray<?> getQueryImage() { return queryImage; }
@@ -110,19 +148,17 @@ public class GpuPixelMatchColorDepthSearchAlgorithmProvider implements ColorDept
         @Override public int getQueryLastPixelIndex() { return queryImage.getPixelCount() - 1; }
         @Override public Set<ComputeFileType> getRequiredTargetVariantTypes() { return Collections.emptySet(); }
 
-        /** Thread-safe: calls on one context are serialised inside the library. */
+        /** Thread-safe and re-entrant: cds_pairq_score takes no context-wide lock; calls that arrive together share a kernel launch. */
         @Override
         public PixelMatchScore calculateMatchingScore(@Nonnull ImageArray<?> target, Map<ComputeFileType, Supplier<ImageArray<?>>> variants) {
             try (Arena a = Arena.ofConfined()) {
                 MemorySegment score = a.allocate(ValueLayout.JAVA_INT), ratio = a.allocate(ValueLayout.JAVA_DOUBLE), mir = a.allocate(ValueLayout.JAVA_INT);
-                CdsGpu.check((int) CdsGpu.scorePairRgb.invokeExact(CdsGpu.context(), maskSet, 0, CdsGpu.copyBytes(a, ImageArrayAccess.rgbBytes(target)),
+                // the pixels are only read when the key is not in the device cache; a heap array has to be copied off-heap to be passed at all
+                // (FFM cannot pin byte[]), a JNI shim would use GetPrimitiveArrayCritical instead
+                CdsGpu.check((int) CdsGpu.pairqScore.invokeExact(queue, maskIndex, targetKey(target), CdsGpu.copyBytes(a, ImageArrayAccess.rgbBytes(target)),
                         target.getWidth(), target.getHeight(), score, ratio, mir));
                 return new PixelMatchScore(score.get(ValueLayout.JAVA_INT, 0), ratio.get(ValueLayout.JAVA_DOUBLE, 0), mir.get(ValueLayout.JAVA_INT, 0) != 0);
             } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
-        }
-
-        public void close() {
-            try { CdsGpu.masksetDestroy.invokeExact(maskSet); } catch (Throwable ignored) { }
         }
     }
 }

@@ -64,6 +64,14 @@ public final class CdsGpu {
     public static final MethodHandle searchStreamMatchesTiff = h("cds_search_stream_matches_tiff", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_DOUBLE, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     public static final MethodHandle shapeScorePairsTiff = h("cds_shape_score_pairs_tiff", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
     public static final MethodHandle tiffProbe = h("cds_tiff_probe", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
+    // the single-pair call behind a micro-batching queue with a device-side target cache (include/cdsgpu.h, cds_pairq_*)
+    public static final MethodHandle pairqCreate = h("cds_pairq_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS));
+    public static final MethodHandle pairqDestroy = h("cds_pairq_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    public static final MethodHandle pairqScore = h("cds_pairq_score", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    // gradient images as PNG files, targets as TIFF files
+    public static final MethodHandle shapeScorePairsFiles = h("cds_shape_score_pairs_files", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
+    public static final MethodHandle tiffToPackbits = h("cds_tiff_to_packbits", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS));
+    public static final MethodHandle tiffEncodeBound = h("cds_tiff_encode_bound", FunctionDescriptor.of(JAVA_LONG, JAVA_INT, JAVA_INT, JAVA_INT));
     public static final MethodHandle scorePairRgb = h("cds_score_pair_rgb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     public static final MethodHandle shapeMasksetCreate = h("cds_shape_maskset_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     public static final MethodHandle shapeMasksetDestroy = h("cds_shape_maskset_destroy", FunctionDescriptor.ofVoid(ADDRESS));

@@ -22,7 +22,8 @@ import org.janelia.colormipsearch.model.ProcessingType;
  * The batched seam: ColorMIPSearchProcessor.findAllColorDepthMatches (ColorMIPSearchProcessor.java:8-12) as ONE streaming
  * native search -- the same seam --use-spark already uses (ColorDepthSearchCmd.java:279-295).  Masks are prepared once on the
  * device; targets are decoded by the JVM (as today, through CachedMIPsUtils) into a pinned staging buffer and streamed to the
- * GPUs; only matches that pass ColorMIPSearch.isMatch come back (LocalColorMIPSearchProcessor.java:93-105 keeps exactly those).
+ * GPUs in chunks of cdsgpu.targetChunk images (one pinned staging buffer, whatever the size of the library; masks are grouped by
+ * image size); only matches that pass ColorMIPSearch.isMatch come back (LocalColorMIPSearchProcessor.java:93-105 keeps exactly those).
  * With -Dcdsgpu.ingest=tiff and targets that are plain .tif files the JVM does not decode at all: the files' bytes go into the
  * pinned buffer as stored and cds_search_stream_*_tiff decodes them on the device (PackBits or uncompressed RGB; anything else
  * makes the native call return CDS_ERR_UNSUPPORTED and the processor falls back to the decoded path).
@@ -45,24 +46,28 @@ public class GpuColorMIPSearchProcessor<M extends AbstractNeuronEntity, T extend
         this.maxMatchesPerMask = maxMatchesPerMask; this.tags = tags;
     }
 
+    /** Targets per native call on the decoded path: bounds the pinned staging buffer (2 GB for 1210 x 566 images) whatever the library's size. */
+    private static final int TARGET_CHUNK = Integer.getInteger("cdsgpu.targetChunk", 1024);
+
     @Override
-    @SuppressWarnings("unchecked")
     public List<CDMatchEntity<M, T>> findAllColorDepthMatches(List<M> queryMIPs, List<T> targetMIPs) {
         List<CDMatchEntity<M, T>> results = new ArrayList<>();
-        List<NeuronMIP<M>> masks = new ArrayList<>();
+        // masks grouped by image size: a mask set holds images of one size, and the reference compares a mask only with targets of
+        // its own size (PixelMatchColorDepthSearchAlgorithm.java:171-175 throws otherwise)
+        java.util.Map<Long, List<NeuronMIP<M>>> bySize = new java.util.LinkedHashMap<>();
         for (M q : queryMIPs) {
             NeuronMIP<M> m = NeuronMIPUtils.loadComputeFile(q, ComputeFileType.InputColorDepthImage);
-            if (m != null && !m.hasNoImageArray()) masks.add(m);
+            if (m == null || m.hasNoImageArray()) continue;
+            long key = ((long) m.getImageArray().getWidth() << 32) | m.getImageArray().getHeight();
+            bySize.computeIfAbsent(key, x -> new ArrayList<>()).add(m);
         }
-        List<NeuronMIP<T>> targets = new ArrayList<>();
-        for (T t : targetMIPs) {
-            NeuronMIP<T> tm = CachedMIPsUtils.loadMIP(t, ComputeFileType.InputColorDepthImage);
-            if (NeuronMIPUtils.hasImageArray(tm)) targets.add(tm);
-        }
-        if (masks.isEmpty() || targets.isEmpty()) return results;
+        for (List<NeuronMIP<M>> masks : bySize.values()) searchOneSize(masks, targetMIPs, results);
+        return results;
+    }
+
+    private void searchOneSize(List<NeuronMIP<M>> masks, List<T> targetMIPs, List<CDMatchEntity<M, T>> results) {
         int w = masks.get(0).getImageArray().getWidth(), h = masks.get(0).getImageArray().getHeight();
         long imgBytes = 3L * w * h;
-        int k = Math.min(maxMatchesPerMask > 0 ? maxMatchesPerMask : targets.size(), targets.size());
         try (Arena a = Arena.ofConfined()) {
             MemorySegment ctx = CdsGpu.context();
             MemorySegment out = a.allocate(ValueLayout.ADDRESS);
@@ -72,50 +77,62 @@ public class GpuColorMIPSearchProcessor<M extends AbstractNeuronEntity, T extend
             int[] maskSizes = new int[masks.size()];
             MemorySegment size = a.allocate(ValueLayout.JAVA_INT);
             for (int i = 0; i < masks.size(); i++) {
-                CdsGpu.check((int) CdsGpu.masksetAddRgb.invokeExact(ms, CdsGpu.copyBytes(a, ImageArrayAccess.rgbBytes(masks.get(i).getImageArray())), 1, size));
+                try (Arena one = Arena.ofConfined()) {
+                    CdsGpu.check((int) CdsGpu.masksetAddRgb.invokeExact(ms, CdsGpu.copyBytes(one, ImageArrayAccess.rgbBytes(masks.get(i).getImageArray())), 1, size));
+                }
                 maskSizes[i] = size.get(ValueLayout.JAVA_INT, 0);
             }
-            if ("tiff".equals(System.getProperty("cdsgpu.ingest")) && searchTiffFiles(a, ctx, ms, masks, targetMIPs, maskSizes, k, results)) {
+            if ("tiff".equals(System.getProperty("cdsgpu.ingest")) && searchTiffFiles(a, ctx, ms, masks, targetMIPs, maskSizes,
+                    maxMatchesPerMask > 0 ? maxMatchesPerMask : targetMIPs.size(), results)) {
                 CdsGpu.masksetDestroy.invokeExact(ms);
-                return results;
+                return;
             }
-            // targets: one pinned buffer, filled by the JVM's decoders, streamed by the library (H2D of chunk i+1 overlaps the search of chunk i)
-            CdsGpu.check((int) CdsGpu.hostAlloc.invokeExact(ctx, imgBytes * targets.size(), out));
-            MemorySegment pinned = out.get(ValueLayout.ADDRESS, 0).reinterpret(imgBytes * targets.size());
-            for (int i = 0; i < targets.size(); i++)
-                MemorySegment.copy(ImageArrayAccess.rgbBytes(targets.get(i).getImageArray()), 0, pinned, ValueLayout.JAVA_BYTE, imgBytes * i, (int) imgBytes);
-            if (maxMatchesPerMask <= 0) {
-                // like LocalColorMIPSearchProcessor: every pair that passes ColorMIPSearch.isMatch
-                long cap = Math.max(1024L, 4L * masks.size());
-                MemorySegment count = a.allocate(ValueLayout.JAVA_LONG);
-                for (int attempt = 0; ; attempt++) {
-                    MemorySegment mk = a.allocate(4 * cap, 4), tg = a.allocate(8 * cap, 8), sc = a.allocate(4 * cap, 4), mir = a.allocate(cap);
-                    int st = (int) CdsGpu.searchStreamMatches.invokeExact(ctx, ms, pinned, (long) targets.size(), pctPositivePixels, cap, mk, tg, sc, mir, count);
-                    long n = count.get(ValueLayout.JAVA_LONG, 0);
-                    if (st == CdsGpu.CDS_ERR_CAPACITY && attempt == 0) { cap = n; continue; }
-                    CdsGpu.check(st);
-                    for (long i = 0; i < n; i++)
-                        results.add(newMatch(masks, targets, maskSizes, mk.get(ValueLayout.JAVA_INT, 4 * i), (int) tg.get(ValueLayout.JAVA_LONG, 8 * i),
-                                sc.get(ValueLayout.JAVA_INT, 4 * i), mir.get(ValueLayout.JAVA_BYTE, i) != 0));
-                    break;
+            // Decoded targets: ONE pinned staging buffer of TARGET_CHUNK images, refilled by the JVM's decoders chunk after chunk; inside a
+            // chunk the library overlaps the upload with the search.  Targets of another size are skipped for this mask group.
+            CdsGpu.check((int) CdsGpu.hostAlloc.invokeExact(ctx, imgBytes * TARGET_CHUNK, out));
+            MemorySegment pinned = out.get(ValueLayout.ADDRESS, 0).reinterpret(imgBytes * TARGET_CHUNK);
+            List<List<CDMatchEntity<M, T>>> perMask = new ArrayList<>();
+            for (int m = 0; m < masks.size(); m++) perMask.add(new ArrayList<>());
+            List<NeuronMIP<T>> chunk = new ArrayList<>();
+            for (int t0 = 0; t0 <= targetMIPs.size(); t0++) {
+                if (t0 < targetMIPs.size()) {
+                    NeuronMIP<T> tm = CachedMIPsUtils.loadMIP(targetMIPs.get(t0), ComputeFileType.InputColorDepthImage);
+                    if (NeuronMIPUtils.hasImageArray(tm) && tm.getImageArray().getWidth() == w && tm.getImageArray().getHeight() == h) {
+                        MemorySegment.copy(ImageArrayAccess.rgbBytes(tm.getImageArray()), 0, pinned, ValueLayout.JAVA_BYTE, imgBytes * chunk.size(), (int) imgBytes);
+                        chunk.add(tm);
+                    }
+                    if (chunk.size() < TARGET_CHUNK) continue;
                 }
-            } else {
-                MemorySegment score = a.allocate(4L * masks.size() * k, 4), target = a.allocate(8L * masks.size() * k, 8);
-                MemorySegment mirrored = a.allocate((long) masks.size() * k), count = a.allocate(4L * masks.size(), 4);
-                CdsGpu.check((int) CdsGpu.searchStream.invokeExact(ctx, ms, pinned, (long) targets.size(), k, pctPositivePixels, score, target, mirrored, count));
-                for (int m = 0; m < masks.size(); m++) {
-                    int n = count.get(ValueLayout.JAVA_INT, 4L * m);
-                    for (int i = 0; i < n; i++) {
-                        long o = (long) m * k + i;
-                        results.add(newMatch(masks, targets, maskSizes, m, (int) target.get(ValueLayout.JAVA_LONG, 8 * o),
-                                score.get(ValueLayout.JAVA_INT, 4 * o), mirrored.get(ValueLayout.JAVA_BYTE, o) != 0));
+                if (chunk.isEmpty()) continue;
+                // every pair of the chunk that passes ColorMIPSearch.isMatch, like LocalColorMIPSearchProcessor.java:93-105
+                long cap = Math.max(1024L, 4L * masks.size());
+                try (Arena ca = Arena.ofConfined()) {
+                    MemorySegment count = ca.allocate(ValueLayout.JAVA_LONG);
+                    for (int attempt = 0; ; attempt++) {
+                        MemorySegment mk = ca.allocate(4 * cap, 4), tg = ca.allocate(8 * cap, 8), sc = ca.allocate(4 * cap, 4), mir = ca.allocate(cap);
+                        int st = (int) CdsGpu.searchStreamMatches.invokeExact(ctx, ms, pinned, (long) chunk.size(), pctPositivePixels, cap, mk, tg, sc, mir, count);
+                        long n = count.get(ValueLayout.JAVA_LONG, 0);
+                        if (st == CdsGpu.CDS_ERR_CAPACITY && attempt == 0) { cap = n; continue; }
+                        CdsGpu.check(st);
+                        for (long i = 0; i < n; i++) {
+                            int m = mk.get(ValueLayout.JAVA_INT, 4 * i);
+                            perMask.get(m).add(newMatch(masks, chunk, maskSizes, m, (int) tg.get(ValueLayout.JAVA_LONG, 8 * i),
+                                    sc.get(ValueLayout.JAVA_INT, 4 * i), mir.get(ValueLayout.JAVA_BYTE, i) != 0));
+                        }
+                        break;
                     }
                 }
+                chunk = new ArrayList<>();
+            }
+            for (List<CDMatchEntity<M, T>> l : perMask) {
+                // chunks arrive in target order and every chunk's list is sorted by descending matchingPixels: a stable sort restores the
+                // per-mask order of a single search; the optional cap keeps the best maxMatchesPerMask
+                l.sort((x, y) -> Integer.compare(y.getMatchingPixels(), x.getMatchingPixels()));
+                results.addAll(maxMatchesPerMask > 0 && l.size() > maxMatchesPerMask ? l.subList(0, maxMatchesPerMask) : l);
             }
             CdsGpu.check((int) CdsGpu.hostFree.invokeExact(ctx, pinned));
             CdsGpu.masksetDestroy.invokeExact(ms);
         } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
-        return results;
     }
 
     /**

@@ -103,3 +103,28 @@ def test_queue_from_python_threads_and_errors(ctx, data):
     assert (a[0], b[0]) == (int(dense[0, 5]), int(dense[0, 6]))
     q.close()
     ms.close()
+
+
+def test_masks_added_after_the_queue_was_created(ctx, data):
+    """One provider = one mask set + one queue, an algorithm per mask: masks keep arriving while pairs are being scored."""
+    masks, targets = data
+    rects = O.label_rects(W, H)
+    ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    ms.add_rgb(masks[:2])
+    q = capi.PairQueue(ctx, ms, max_batch=8, max_wait_us=100, cache_targets=32)
+    first = [q.score(m, targets[t], key=t + 1) for m in range(2) for t in range(4)]
+    with pytest.raises(capi.CdsIllegalArgument):
+        q.score(2, targets[0], key=1)                      # not there yet
+    ms.add_rgb(masks[2:6])
+    keys = (np.arange(12) + 1).astype(np.uint64)
+    pm = np.repeat(np.arange(6), 12).astype(np.int32)
+    pt = np.tile(np.arange(12), 6).astype(np.int64)
+    sc, mir, _ = q.drive(targets, keys, pm, pt, 12)
+    lib = capi.Library(ctx, W, H, 16)
+    lib.add_rgb(targets)
+    dense, dmir = ms.search_dense(lib)
+    lib.close()
+    assert np.array_equal(sc, dense[pm, pt]) and np.array_equal(mir, dmir[pm, pt].astype(bool))
+    assert [f[0] for f in first] == [int(dense[m, t]) for m in range(2) for t in range(4)]
+    q.close()
+    ms.close()
