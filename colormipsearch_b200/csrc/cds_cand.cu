@@ -36,9 +36,6 @@ constexpr int kMaxBands = 256;
 constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy destination aligned)
 constexpr int kQueue = 64;          // candidate slots per warp (power of two, >= 2 * 32)
 constexpr int kWordQueue = 64;      // word slots per warp (power of two, >= 2 * 32)
-constexpr int kTicketQueue = 256;   // passing tickets of a band that wait in the CTA-wide queue (16-bit slots; what is left of the 227 kB)
-constexpr uint32_t kTicketFree = 0xFFFFu;     // slot reserved or unused, not written yet
-constexpr uint32_t kTicketSkip = 0xFFFEu;     // slot written, holds no ticket (its batch did not fit and is scanned by its own warp)
 
 struct CandParams {
     const MaskDesc *masks;
@@ -58,7 +55,6 @@ struct CandParams {
     int *acc;                       // [grid][GROUP][2 * offsets] match counters, zero between work items
     int debug_skip;                 // profiling aid (CDSGPU_CAND_NULL): consumers skip the tickets, only the band pipeline runs
     int ticket_skip;                // the lists are in bucket order: a ticket whose occupancy words are all empty is not scanned
-    int shared_tickets;             // 1: tickets that pass the occupancy test go through a CTA-wide queue and are scanned by whichever warp is free
     int wait_mode;                  // how a warp waits for a band: 0 polls try_wait, 1 try_wait with a suspend-time hint, 2 test_wait + nanosleep
     long long *trace;               // profiling aid (CDSGPU_CAND_TRACE): SM clock of CTA 0's first items, [item][band][32 warps][2] (+ producer in slot 31)
 };
@@ -97,7 +93,7 @@ __device__ __forceinline__ void count_hit(const int *acc, uint32_t c, uint32_t l
 
 template <int GROUP>
 struct CandSmem {
-    size_t stage_off, bits_off, pal_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, sel_off, tq_off, tqc_off, total;
+    size_t stage_off, bits_off, pal_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, sel_off, total;
     __host__ __device__ CandSmem(int stage_words, int NS, int bits_words, int n_warps)
     {
         size_t o = 0;
@@ -111,8 +107,6 @@ struct CandSmem {
         next_off = o;  o += 16;
         band_off = o;  o += (size_t) kStages * 8;                               // per stage: {first, end} entry of the group's word list
         sel_off = o;   o += 64;                                                 // position of the r-th set bit of a nibble
-        tq_off = o;    o += (size_t) kStages * kTicketQueue * 2;                // per stage: the CTA-wide queue of passing tickets
-        tqc_off = o;   o += (size_t) kStages * 16;                              // per stage: {tail, head, test batches done, -}
         (void) NS;
         total = o;
     }
@@ -213,8 +207,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
     long long *s_item = reinterpret_cast<long long *>(smem_raw + L.item_off);           // [2] published work items
     uint8_t *s_sel = smem_raw + L.sel_off;                                               // [16][4] r-th set bit of a nibble
-    uint16_t *s_tq = reinterpret_cast<uint16_t *>(smem_raw + L.tq_off);                  // [kStages][kTicketQueue] ticket numbers inside the band, kTicketFree = empty
-    int *s_tqc = reinterpret_cast<int *>(smem_raw + L.tqc_off);                          // [kStages][4] {tail, head, test batches done, -}
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pitch = p.g.pitch, H = p.g.H, R = p.rows_per_band, NB = p.n_bands;
@@ -227,11 +219,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             mbar_init(smem_u32(s_full + s), 1);
             mbar_init(smem_u32(s_empty + s), NCW);
             s_next[s] = 0;
-            s_tqc[4 * s] = 0; s_tqc[4 * s + 1] = 0; s_tqc[4 * s + 2] = 0;
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < kStages * kTicketQueue; i += (NCW + 1) * 32) s_tq[i] = (uint16_t) kTicketFree;
     if (tid < 64) {
         int nib = tid >> 2, r = tid & 3, pos = 0;
         for (int b = 0, seen = 0; b < 4; b++)
@@ -264,7 +254,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     if (q >= kStages) mbar_wait(smem_u32(s_empty + stage), ((q >> 1) - 1) & 1);
                     if (trace && iseq < (uint32_t) kTraceItems) trace[(((size_t) iseq * kMaxBands + b) * 32 + 31) * 2] = clock64();
                     s_next[stage] = 0;
-                    s_tqc[4 * stage] = 0; s_tqc[4 * stage + 1] = 0; s_tqc[4 * stage + 2] = 0;      // the queue's slots are all free again (poppers free them)
                     s_band[stage] = range;
                     if (b == 0) s_item[iseq & 1] = done ? -1 : w;
                     const uint32_t bar = smem_u32(s_full + stage);
@@ -493,28 +482,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     }
                 }
                 unsigned live = __ballot_sync(0xffffffffu, pass);
-                if (p.shared_tickets) {
-                    // Passing tickets go into the CTA-wide queue: whichever warp is free scans them, one ticket at a time, so a band
-                    // ends when its work is done and not when the warp with the heaviest batch is (profiles/r02_cand_trace.txt: the
-                    // slowest warp of a band was busy twice as long as the average one).  No room (or a ticket number that does
-                    // not fit 16 bits): the warp scans its own tickets as before.
-                    bool queued = false;
-                    if (live) {
-                        const int cnt = __popc(live);
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&s_tqc[4 * stage], cnt);
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        const bool fits = base + cnt <= kTicketQueue && __all_sync(0xffffffffu, !pass || k < kTicketSkip);
-                        // every reserved slot inside the queue is written -- with the ticket, or with "nothing here" when the batch
-                        // does not fit as a whole: a popper that has taken a slot waits for its value
-                        const int slot = base + __popc(live & lt_mask);
-                        if (pass && slot < kTicketQueue) s_tq[stage * kTicketQueue + slot] = (uint16_t) (fits ? k : kTicketSkip);
-                        queued = fits;
-                    }
-                    __syncwarp();
-                    if (lane == 0) { __threadfence_block(); atomicAdd(&s_tqc[4 * stage + 2], 1); }
-                    if (queued) continue;
-                }
                 if (!live) continue;
                 // scan the tickets that passed; the next one's entries are requested before the current one is used
                 int src = __ffs((int) live) - 1;
@@ -533,47 +500,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     }
                     scan_one(w, entry);
                     if (!more) break;
-                }
-            }
-            if (p.shared_tickets && !p.debug_skip) {
-                // take tickets from the CTA-wide queue until every test batch is in and the queue is empty
-                volatile int *tqc = s_tqc + 4 * stage;
-                volatile uint16_t *tq = s_tq + stage * kTicketQueue;
-                auto pop = [&]() -> int {
-                    int kk = -1;
-                    if (lane == 0) {
-                        for (;;) {
-                            const int h = tqc[1];
-                            const int t = min((int) tqc[0], kTicketQueue);
-                            if (h < t) {
-                                if (atomicCAS(&s_tqc[4 * stage + 1], h, h + 1) == h) {
-                                    uint32_t v;
-                                    while ((v = tq[h]) == kTicketFree) {}          // its pusher has reserved the slot and is about to write it
-                                    tq[h] = (uint16_t) kTicketFree;
-                                    if (v == kTicketSkip) continue;
-                                    kk = (int) v;
-                                    break;
-                                }
-                            } else if (tqc[2] >= (int) n_batches) {
-                                // every test batch is in: the tail is final
-                                if (tqc[1] >= min((int) tqc[0], kTicketQueue)) break;
-                            }
-                        }
-                    }
-                    return __shfl_sync(0xffffffffu, kk, 0);
-                };
-                int kc = pop();
-                if (kc >= 0) {
-                    uint32_t jc = j_first + (uint32_t) kc;
-                    uint2 wn = load(jc);
-                    for (;;) {
-                        const uint2 w = wn;
-                        const uint32_t entry = (jc << 5) + (uint32_t) lane;
-                        const int kn = pop();
-                        if (kn >= 0) { jc = j_first + (uint32_t) kn; wn = load(jc); }
-                        scan_one(w, entry);
-                        if (kn < 0) break;
-                    }
                 }
             }
             // the band's last, partly filled batches: everything queued reads this stage, so it is evaluated before the release
@@ -674,7 +600,6 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     static const int no_skip = env_int("CDSGPU_CAND_NOSKIP", 0);
     p.ticket_skip = no_skip ? 0 : 1;
     p.wait_mode = cand_tuning().wait_mode;
-    p.shared_tickets = cand_tuning().shared_tickets;
     const int hint = cand_tuning().l2_hint;
     static const char *trace_path = std::getenv("CDSGPU_CAND_TRACE");
     p.trace = nullptr;
@@ -914,7 +839,9 @@ __global__ void __launch_bounds__(256) words_tocc_kernel(const uint4 *__restrict
 
 CandTuning &cand_tuning()
 {
-    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 0), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31), env_int("CDSGPU_CAND_SHARED_TICKETS", 0)};
+    // wait mode 1 by default: the same throughput as the polling loop (tools/cand_sweep.py: 288.66 vs 288.70 M comparisons/s) without its
+    // instructions -- the polling loop was 24 % of everything the kernel executed
+    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 1), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31)};
     return t;
 }
 

@@ -37,7 +37,6 @@ struct CandTuning {
     int wait_mode;      // how a consumer warp waits for a band: 0 polls try_wait, 1 try_wait with a suspend-time hint, 2 test_wait + nanosleep
     int l2_hint;        // 1: bulk copies of the streamed planes are evict-first, loads of the group's lists evict-last
     int warps;          // consumer warps per CTA (31, 28, 24 or 16)
-    int shared_tickets; // 1: passing tickets go through a CTA-wide queue and are scanned by whichever warp is free (finer load balance inside a band)
 };
 CandTuning &cand_tuning();
 

@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--masks", type=int, default=1000)
 ap.add_argument("--targets", type=int, default=4096)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--settings", default="tq=0;tq=1;tq=1,wait=2;tq=0,warps=28;tq=1,warps=28")
+ap.add_argument("--settings", default="wait=0,hint=0;wait=1,hint=0;wait=2,hint=0;wait=0,hint=1")
 a = ap.parse_args()
 rects = O.label_rects(W, H)
 ctx = capi.Context(device_ids=[0])
@@ -29,7 +29,6 @@ for setting in a.settings.split(";"):
     ctx.set_option("cand_wait_mode", int(kv.get("wait", 0)))
     ctx.set_option("cand_l2_hint", int(kv.get("hint", 0)))
     ctx.set_option("cand_warps", int(kv.get("warps", 31)))
-    ctx.set_option("cand_shared_tickets", int(kv.get("tq", 0)))
     res = ms.search_topk(lib, 300, 1.0)
     ms_total = 0.0
     for _ in range(a.reps):
