@@ -109,7 +109,7 @@ def test_shape_scores_from_files_golden(ctx, fixtures, fmt):
     # more targets than a window, a target without pairs in the middle, has_variants, and the pixel call as the checker
     rng = np.random.default_rng(8)
     targets = capi.synth_rgb_host(1, 55, 0, 40, W, H)
-    grads = capi.synth_gradient_host(55, 0, 40, W, H)
+    grads = ctx.synth_gradient(55, 0, 40, W, H, on_device=True)
     tf = [capi.tiff_encode_rgb(t, 8, 32773) for t in targets]
     pf = [capi.png_encode_gray16(g, -1 if i % 2 else 0) for i, g in enumerate(grads)]
     pm = rng.integers(0, 2, 150)

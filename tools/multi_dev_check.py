@@ -9,6 +9,13 @@ masks = capi.synth_rgb_host(0, 0xC0FFEE, 0, 24, W, H)
 targets = capi.synth_rgb_host(1, 0xC0FFEE, 0, 200, W, H)
 rects = O.label_rects(W, H)
 files = [capi.tiff_encode_rgb(t, 8 if i % 3 else 566, 32773 if i % 5 else 1) for i, t in enumerate(targets)]
+NS = 72                                   # targets of the shape part: three windows of 32, so both devices get work
+grads = np.stack([capi.synth_gradient_host(0xC0FFEE, i, 1, W, H)[0] if i < 6 else np.roll(capi.synth_gradient_host(0xC0FFEE, i % 6, 1, W, H)[0], i, axis=1) for i in range(NS)])
+rng = np.random.default_rng(3)
+pm = rng.integers(0, 6, 600); pt = rng.integers(0, NS, 600)
+has = (np.arange(NS) % 11 != 5).astype(np.uint8)
+pfiles = [capi.png_encode_gray16(g, -1 if i % 2 else 0) for i, g in enumerate(grads)]
+tfiles = [capi.tiff_encode_rgb(t, 8, 32773) for t in targets[:NS]]
 res = {}
 for nd in (1, 0):
     ctx = capi.Context(n_dev=nd)
@@ -21,15 +28,9 @@ for nd in (1, 0):
     res[nd] = (ms.search_dense(lib), ms.search_topk(lib, 50, 0.0), ms.search_stream(targets, 50, 0.0), ms.search_stream_tiff(files, 50, 0.0),
                ms.search_topk(lib2, 50, 0.0), ms.search_stream_matches_tiff(files, 1.0), ms.search_matches(lib, 1.0))
     # shape score across the context's devices (windows of targets dealt out over the devices, masks replicated), pixels / TIFF / TIFF + PNG
-    grads = capi.synth_gradient_host(0xC0FFEE, 0, 200, W, H)
     sms = capi.ShapeMaskSet(ctx, W, H, 20, True, rects)
     qm, he = sms.add_rgb(masks[:6])
-    rng = np.random.default_rng(3)
-    pm = rng.integers(0, 6, 900); pt = rng.integers(0, 200, 900)
-    has = (np.arange(200) % 11 != 5).astype(np.uint8)
-    pfiles = [capi.png_encode_gray16(g, -1 if i % 2 else 0) for i, g in enumerate(grads)]
-    tfiles = [capi.tiff_encode_rgb(t, 8, 32773) for t in targets]
-    shape_res = (qm, he, sms.score_pairs(targets, grads, None, pm, pt, has), sms.score_pairs_tiff(tfiles, grads, None, pm, pt, has),
+    shape_res = (qm, he, sms.score_pairs(targets[:NS], grads, None, pm, pt, has), sms.score_pairs_tiff(tfiles, grads, None, pm, pt, has),
                  sms.score_pairs_files(tfiles, pfiles, None, pm, pt, has))
     sms.close()
     # the single-pair queue: one dispatcher per device, targets spread by key
