@@ -726,12 +726,20 @@ def main():
                        "result D2H, host merge) + destroy"}
         # ---- the same step with the targets as PackBits TIFF FILES in pinned host memory (how colour-depth MIP libraries are
         # stored): the files cross PCIe as they are and are decoded on the device
-        if not args.no_e2e_tiff and pool_t >= Te:
+        if not args.no_e2e_tiff:
             from concurrent.futures import ThreadPoolExecutor
             t_enc = time.perf_counter()
-            pool_img = pool_arr[:Te * img_bytes].reshape(Te, H, W, 3)
+            # the files are written from the pinned pool where it holds the whole step, otherwise chunk by chunk from the generator: the
+            # TIFF leg needs 1.7 GB of host memory per rank, whatever the pixel leg could get
+            files = []
             with ThreadPoolExecutor(max_workers=host_threads()) as ex:
-                files = list(ex.map(lambda i: capi.tiff_encode_rgb(pool_img[i], 8, 32773), range(Te)))
+                if pool_t >= Te:
+                    pool_img = pool_arr[:Te * img_bytes].reshape(Te, H, W, 3)
+                    files = list(ex.map(lambda i: capi.tiff_encode_rgb(pool_img[i], 8, 32773), range(Te)))
+                else:
+                    for i in range(0, Te, 64):
+                        blk = ctx.synth_rgb(1, SEED, t_first + i, min(64, Te - i), W, H, on_device=True)
+                        files += list(ex.map(lambda im: capi.tiff_encode_rgb(im, 8, 32773), blk))
             offsets = np.zeros(Te + 1, np.int64)
             np.cumsum([len(f) for f in files], out=offsets[1:])
             blob_arr, blob_ptr = ctx.host_alloc(int(offsets[-1]) + 64)
