@@ -741,7 +741,7 @@ static cds_status maskset_append_body(cds_maskset *ms, int32_t n, int32_t *mask_
     const int D = (int) ctx->devs.size();
     const size_t img_bytes = (size_t) ms->W * ms->H * 3;
     const int H = ms->H;
-    const int kChunk = 64;
+    const int kChunk = maskset_append_chunk(n);     // masks per staging half: every chunk costs one host round trip (the masks' sizes)
     DevState &d0 = ctx->devs[0];
     cds_maskset::DevStore &s0 = ms->store[0];
     CDS_CUDA(ctx, cudaSetDevice(d0.dev));

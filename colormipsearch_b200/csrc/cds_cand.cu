@@ -839,9 +839,9 @@ __global__ void __launch_bounds__(256) words_tocc_kernel(const uint4 *__restrict
 
 CandTuning &cand_tuning()
 {
-    // wait mode 1 by default: the same throughput as the polling loop (tools/cand_sweep.py: 288.66 vs 288.70 M comparisons/s) without its
-    // instructions -- the polling loop was 24 % of everything the kernel executed
-    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 1), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31)};
+    // sleeping waits by default (test_wait + nanosleep of that many ns): within 1 % of the polling loop's throughput (tools/cand_sweep.py)
+    // without its instructions -- the polling loop was 24 % of everything the kernel executed, in issue slots nobody else wanted
+    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 100), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31)};
     return t;
 }
 

@@ -34,7 +34,7 @@ bool cand_kernel_supported(int xy_shift, const PlaneGeom &g);
 // Tuning knobs of the candidate kernel (process-wide; defaults from the environment, changed through cds_ctx_set_option
 // "cand_wait_mode" / "cand_l2_hint" / "cand_warps" so that one process can sweep them).
 struct CandTuning {
-    int wait_mode;      // how a consumer warp waits for a band: 0 polls try_wait, 1 try_wait with a suspend-time hint, 2 test_wait + nanosleep
+    int wait_mode;      // how a consumer warp waits for a band: 0 polls try_wait, 1 try_wait with a suspend-time hint, n >= 2 test_wait + nanosleep(n ns)
     int l2_hint;        // 1: bulk copies of the streamed planes are evict-first, loads of the group's lists evict-last
     int warps;          // consumer warps per CTA (31, 28, 24 or 16)
 };

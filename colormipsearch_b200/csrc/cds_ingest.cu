@@ -601,10 +601,11 @@ extern "C" cds_status cds_maskset_add_tiff(cds_maskset *ms, const uint8_t *blob,
         if (n < 0 || (n > 0 && (!blob || !offsets))) return ctx->fail(CDS_ERR_BAD_ARG, "cds_maskset_add_tiff: bad arguments");
         if (n == 0) return CDS_OK;
         const int W = ms->W, H = ms->H;
-        // maskset_append asks for runs of at most 64 masks; uploads and decodes are ordered on one stream, so one buffer does
+        // maskset_append asks for runs of at most `chunk` masks; uploads and decodes are ordered on one stream, so one buffer does
+        const int64_t chunk = maskset_append_chunk(n);
         size_t comp_cap = 0, strips_cap = 0;
-        ingest_bounds(offsets, n, 64, W, H, comp_cap, strips_cap);
-        for (int64_t i = 0; i < n; i++) comp_cap = std::max(comp_cap, (size_t) std::max<int64_t>(offsets[std::min<int64_t>(n, i + 64)] - offsets[i], 0) + 64);
+        ingest_bounds(offsets, n, chunk, W, H, comp_cap, strips_cap);
+        for (int64_t i = 0; i < n; i++) comp_cap = std::max(comp_cap, (size_t) std::max<int64_t>(offsets[std::min<int64_t>(n, i + chunk)] - offsets[i], 0) + 64);
         DevState &d0 = ctx->devs[0];
         CDS_CUDA(ctx, cudaSetDevice(d0.dev));
         uint8_t *d_comp = nullptr;

@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restri
         const int64_t tl = (int64_t) (i / ((size_t) vp * HT));
         if (4 * k >= tp) continue;                     // tp is a multiple of 4: a strip is four whole tile words or none
         const uint32_t *vimg = valid + (size_t) tl * H * vrow_words;
-        uint4 *orow = reinterpret_cast<uint4 *>(occ + ((size_t) (t0 + tl) * HT + ty) * rowpitch) + k;
+        uint32_t *trow = occ + ((size_t) (t0 + tl) * HT + ty) * rowpitch;
+        uint4 *orow = reinterpret_cast<uint4 *>(trow) + k;
+        uint32_t *nz = trow + (CDS_NUM_SECTORS + 1) * tp;          // the row's non-empty bits: zero on entry (launch_occupancy_kernel clears them)
         uint32_t any[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int s = 0; s < CDS_NUM_SECTORS; s++) {
@@ -313,37 +315,31 @@ __global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restri
             occupancy_strip<RINGS>(vimg + s * vp, vrow_words, H, vp, k, 4 * ty, o);
 #pragma unroll
             for (int r = 0; r < 4; r++) any[r] |= o[r];
-            orow[(size_t) s * (tp / 4)] = strip_to_tiles(o);
+            const uint4 t = strip_to_tiles(o);
+            orow[(size_t) s * (tp / 4)] = t;
+            // one bit per sector tile word, "this word is not empty": bit s * tp + 4 k + j for the strip's four words (the four bits never
+            // straddle a 32-bit word: tp and 4 k are multiples of 4).  Occupied tiles are few, so this is a rare atomic, not a second pass.
+            const uint32_t nib = (t.x != 0u ? 1u : 0u) | (t.y != 0u ? 2u : 0u) | (t.z != 0u ? 4u : 0u) | (t.w != 0u ? 8u : 0u);
+            if (nib) {
+                const int bit = s * tp + 4 * k;
+                atomicOr(&nz[bit >> 5], nib << (bit & 31));
+            }
         }
         orow[(size_t) CDS_NUM_SECTORS * (tp / 4)] = strip_to_tiles(any);
     }
 }
 
-// One warp per (target, tile row): the non-empty bits of the row's sector words (cds_kernels.cuh), read back from the tile
-// words the kernel above has just written.
-__global__ void __launch_bounds__(256) occupancy_nz_kernel(int H, int tp, int64_t t0, int64_t n, uint32_t *__restrict__ occ)
-{
-    const int rowpitch = occupancy_row_pitch(tp);
-    const int HT = occupancy_tile_rows(H);
-    const int lane = threadIdx.x & 31;
-    const int sec_words = CDS_NUM_SECTORS * tp;
-    const int64_t total = n * HT;
-    for (int64_t r = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < total; r += (int64_t) gridDim.x * (blockDim.x >> 5)) {
-        uint32_t *row = occ + ((size_t) t0 * HT + (size_t) r) * rowpitch;
-        for (int i0 = 0; i0 < occupancy_nz_words(tp) * 32; i0 += 32) {
-            const int i = i0 + lane;
-            const unsigned m = __ballot_sync(0xffffffffu, i < sec_words && row[i] != 0u);
-            if (lane == 0) row[(CDS_NUM_SECTORS + 1) * tp + (i0 >> 5)] = m;
-        }
-    }
-}
-
 static void launch_occupancy_kernel(const uint32_t *valid, int H, int vp, int tp, int64_t t0, int64_t n, int rings, uint32_t *occ, cudaStream_t s)
 {
+    // the non-empty bits behind every tile row start from zero: one strided clear instead of the separate pass that used to read every
+    // tile word back (occupancy_nz_kernel, 0.26 ms per 1 024 targets)
+    const int rowpitch = occupancy_row_pitch(tp);
+    const int HT = occupancy_tile_rows(H);
+    cudaMemset2DAsync(occ + (size_t) t0 * HT * rowpitch + (size_t) (CDS_NUM_SECTORS + 1) * tp, (size_t) rowpitch * sizeof(uint32_t), 0,
+                      (size_t) occupancy_nz_words(tp) * sizeof(uint32_t), (size_t) n * HT, s);
     if (rings == 0) occupancy_kernel<0><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
     else if (rings == 1) occupancy_kernel<1><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
     else occupancy_kernel<2><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
-    occupancy_nz_kernel<<<148 * 8, 256, 0, s>>>(H, tp, t0, n, occ);
 }
 
 void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int tp,

@@ -34,9 +34,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
-// The same wait with the waiting warp kept out of the issue slots: mode 1 passes a suspend-time hint (ns) to try_wait, so the
-// hardware parks the warp instead of returning at once; mode 2 polls and sleeps in between.  (The plain loop above is 24 % of
-// all instructions the v19 candidate kernel executes, profiles/r01_v19_cand_source_hotspots.txt.)
+// The same wait with the waiting warp kept out of the issue slots: mode 1 passes a suspend-time hint (ns) to try_wait (measured: the
+// hardware still returns at once, the loop executes as many instructions as the plain one); mode >= 2 polls with test_wait and sleeps
+// `mode` nanoseconds in between.  (The plain loop above is 24 % of all instructions the v19 candidate kernel executes,
+// profiles/r01_v19_cand_source_hotspots.txt -- and none of its time: the slots it takes are idle anyway.)
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, int mode)
 {
     uint32_t ok;
@@ -51,7 +52,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, 
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) break;
-        __nanosleep(200);
+        __nanosleep((unsigned) mode);
     }
 }
 // L2 eviction policies for the bulk copies and the list loads: the streamed target planes should not push the mask group's word

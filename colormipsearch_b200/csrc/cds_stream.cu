@@ -352,7 +352,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         if (want_occ) {
             // host targets: the encoder has just written the valid bits of this chunk
             launch_occupancy(planes, g, 0, cnt, rings, bpitch, sb.valid, sb.chunk, sb.occ, ds.stream, resident == nullptr);
-            ctx->stats.kernel_launches += resident ? 3 : 2;
+            ctx->stats.kernel_launches += resident ? 2 : 1;      // (valid bits,) occupancy incl. the non-empty bits
             tv.occ = sb.occ;
             tv.occ_ready = true;
         }

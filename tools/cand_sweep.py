@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--masks", type=int, default=1000)
 ap.add_argument("--targets", type=int, default=4096)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--settings", default="wait=0,hint=0;wait=1,hint=0;wait=2,hint=0;wait=0,hint=1")
+ap.add_argument("--settings", default="wait=0;wait=1;wait=32;wait=64;wait=100;wait=200;wait=400;wait=0,hint=1")
 a = ap.parse_args()
 rects = O.label_rects(W, H)
 ctx = capi.Context(device_ids=[0])
