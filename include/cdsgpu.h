@@ -20,7 +20,10 @@
  *   - there is NO CPU fallback: without a CUDA device cds_ctx_create fails with CDS_ERR_NO_DEVICE.
  *   - images: RGB = uint8[H][W][3] in R,G,B order (API/imageprocessing/ColorImageArray.java:6-31),
  *     gray16 = uint16[H][W] (ShortImageArray.java:4-16), gray8 = uint8[H][W] (ByteImageArray.java:3-16).
- *   - a cds_ctx may be used from several host threads; calls on one ctx are serialised internally.
+ *   - a cds_ctx may be used from several host threads; calls on one ctx are serialised internally (cds_pairq_score is the exception:
+ *     it takes no context-wide lock).  Searches, library / mask-set construction, the shape score and the pair queue use every device
+ *     of the context; the one-shot utilities (cds_make_zgap, cds_tiff_decode_rgb, cds_png_decode_gray16, the cds_debug_* hooks) run on
+ *     its first device.
  */
 #ifndef CDSGPU_H
 #define CDSGPU_H

@@ -155,3 +155,12 @@ def test_synth_host_generator_properties():
     for r in rects:
         inside[r[1]:r[3], r[0]:r[2]] = False
     assert g[sig & inside].max() == 0 and g.max() <= 650 and g.max() > 50
+
+
+def test_host_only_generator_equals_the_library_generator():
+    """oracle/libcdssynth.so (the reference arm's input generator, built from the same header without CUDA) renders the images the
+    GPU library renders."""
+    from oracle import synth as S
+    for kind, idx in ((0, 3), (1, 11), (1, 20)):
+        assert np.array_equal(S.synth_rgb(kind, 0xC0FFEE, idx, 1, 1210, 566), capi.synth_rgb_host(kind, 0xC0FFEE, idx, 1, 1210, 566))
+    assert np.array_equal(S.synth_gradient(0xC0FFEE, 5, 1, 301, 97), capi.synth_gradient_host(0xC0FFEE, 5, 1, 301, 97))

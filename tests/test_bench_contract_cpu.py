@@ -18,7 +18,8 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "comparisons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and "2 masks x 8 targets" in d["config"]["workload"]      # the arm says what it actually timed
+    assert d["gpu_library_mapped"] is False        # the CPU arm takes its inputs from the host-only generator: libcdsgpu.so is not mapped
 
 
 def test_reference_arm_under_torchrun_prints_once():
