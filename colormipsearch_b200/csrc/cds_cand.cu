@@ -839,9 +839,10 @@ __global__ void __launch_bounds__(256) words_tocc_kernel(const uint4 *__restrict
 
 CandTuning &cand_tuning()
 {
-    // sleeping waits by default (test_wait + nanosleep of that many ns): within 1 % of the polling loop's throughput (tools/cand_sweep.py)
-    // without its instructions -- the polling loop was 24 % of everything the kernel executed, in issue slots nobody else wanted
-    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 100), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31)};
+    // Waits poll try_wait by default.  Measured (profiles/r02_cand_trace.txt, tools/cand_sweep.py): a suspend-time hint does not stop the
+    // hardware from returning at once, and sleeping between polls (32..400 ns) costs 1-3 % of the throughput without lowering the
+    // instruction count -- the polling loop runs in issue slots that are idle anyway.
+    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 0), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31)};
     return t;
 }
 
