@@ -31,11 +31,13 @@ namespace cds {
 
 namespace {
 
-constexpr int kStages = 2;
+constexpr int kMaxStages = 4;     // band stages of the pipeline: CandParams::n_stages of them are used
 constexpr int kMaxBands = 256;
 constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy destination aligned)
 constexpr int kQueue = 64;          // candidate slots per warp (power of two, >= 2 * 32)
 constexpr int kWordQueue = 64;      // word slots per warp (power of two, >= 2 * 32)
+constexpr int kCandOffsetBits = 15; // a staged band has fewer than 2^15 words (227 kB of shared memory hold 2 of them)
+constexpr uint32_t kCandOffsetMask = (1u << kCandOffsetBits) - 1u;
 
 struct CandParams {
     const MaskDesc *masks;
@@ -55,6 +57,7 @@ struct CandParams {
     int *acc;                       // [grid][GROUP][2 * offsets] match counters, zero between work items
     int debug_skip;                 // profiling aid (CDSGPU_CAND_NULL): consumers skip the tickets, only the band pipeline runs
     int ticket_skip;                // the lists are in bucket order: a ticket whose occupancy words are all empty is not scanned
+    int n_stages;                   // band stages in flight (2 .. kMaxStages)
     int wait_mode;                  // how a warp waits for a band: 0 polls try_wait, 1 try_wait with a suspend-time hint, 2 test_wait + nanosleep
     long long *trace;               // profiling aid (CDSGPU_CAND_TRACE): SM clock of CTA 0's first items, [item][band][32 warps][2] (+ producer in slot 31)
 };
@@ -94,18 +97,18 @@ __device__ __forceinline__ void count_hit(const int *acc, uint32_t c, uint32_t l
 template <int GROUP>
 struct CandSmem {
     size_t stage_off, bits_off, pal_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, sel_off, total;
-    __host__ __device__ CandSmem(int stage_words, int NS, int bits_words, int n_warps)
+    __host__ __device__ CandSmem(int stage_words, int NS, int bits_words, int n_warps, int n_stages)
     {
         size_t o = 0;
-        stage_off = o; o += (size_t) kStages * (stage_words + kPrePad) * 4;
-        bits_off = o;  o += (size_t) kStages * bits_words * 4;
+        stage_off = o; o += (size_t) n_stages * (stage_words + kPrePad) * 4;
+        bits_off = o;  o += (size_t) n_stages * bits_words * 4;
         pal_off = o;   o += (size_t) CDS_PALETTE_SIZE * 8;
         wqueue_off = o; o += (size_t) n_warps * kWordQueue * 8;
         queue_off = o; o += (size_t) n_warps * kQueue * 8;
-        bar_off = o;   o += 2 * kStages * 8;
+        bar_off = o;   o += 2 * kMaxStages * 8;
         item_off = o;  o += 16;
         next_off = o;  o += 16;
-        band_off = o;  o += (size_t) kStages * 8;                               // per stage: {first, end} entry of the group's word list
+        band_off = o;  o += (size_t) kMaxStages * 8;                               // per stage: {first, end} entry of the group's word list
         sel_off = o;   o += 64;                                                 // position of the r-th set bit of a nibble
         (void) NS;
         total = o;
@@ -113,7 +116,9 @@ struct CandSmem {
 };
 
 // The evaluations of 32 queued candidates: one per lane.
-// cand.x = x | y << 11 | orientation << 21 | mask (inside the group) << 22, in target coordinates; cand.y = index of the
+// cand.x = word offset of the candidate's pixel inside the staged band (halo rows included; < 2^15) | (mask inside the group * 2 +
+// orientation) << 15 -- everything the evaluation needs as two ready-made offsets, worked out once per WORD by the expansion;
+// cand.y = index of the
 // candidate's palette reference in the group's lpal array.
 template <int NRINGS, int V>
 struct EvalUnroll {
@@ -161,22 +166,17 @@ __device__ __forceinline__ uint32_t fetch_palette_ref(uint2 cand, bool live, con
 }
 
 template <int NRINGS>
-__device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const uint32_t *__restrict__ band, int y0, int pitch,
+__device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const uint32_t *__restrict__ band, int pitch,
                                                 const uint2 *__restrict__ s_pal, const int *acc_base)
 {
     constexpr int NS = Offsets<NRINGS>::N;
-    constexpr int S = 2 * NRINGS;
-    const uint32_t mi = cand.x >> 22;
     const uint2 pe = s_pal[pr & (CDS_PALETTE_SIZE - 1)];
     const uint32_t iv = (pr & 0x8000u) ? pe.y : pe.x;                           // the interval that lives in this candidate's sector
     const uint32_t lo = (iv & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
     const uint32_t len = ((iv >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
-    const int x = (int) (cand.x & 0x7FFu);
-    const int yrel = (int) ((cand.x >> 11) & 0x3FFu) - y0;
-    const uint32_t orient = (cand.x >> 21) & 1u;
-    const uint32_t *pc = band + (yrel + S) * pitch + x;
+    const uint32_t *pc = band + (cand.x & (kCandOffsetMask));
     // accumulators of this mask: [0, NS) unmirrored, [NS, 2 NS) mirrored
-    const int *acc = acc_base + (mi * 2u * NS + orient * NS);
+    const int *acc = acc_base + (cand.x >> kCandOffsetBits) * (uint32_t) NS;
     uint32_t cw[NS];
     EvalUnroll<NRINGS, 0>::load(pc, pitch, cw);          // all shifted reads first, then the compares
     EvalUnroll<NRINGS, 0>::count(cw, acc, lo, len);
@@ -193,7 +193,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int rowpitch = occupancy_row_pitch(p.bpitch);
     const int bits_words = (p.rows_per_band / 4) * rowpitch;       // rows_per_band is a multiple of the tile height
-    const CandSmem<GROUP> L(p.stage_words, NS, bits_words, NCW);
+    const int NSTG = p.n_stages;
+    const CandSmem<GROUP> L(p.stage_words, NS, bits_words, NCW, NSTG);
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
     const uint32_t *s_bits = reinterpret_cast<const uint32_t *>(smem_raw + L.bits_off);  // [kStages][R * bpitch]
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     int *s_acc = p.acc + (size_t) blockIdx.x * GROUP * NV;                              // this CTA's accumulators [GROUP][NV], global memory, zero on entry
     uint2 *s_band = reinterpret_cast<uint2 *>(smem_raw + L.band_off);                   // [kStages] range of the group's word list inside the staged band
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
-    unsigned long long *s_empty = s_full + kStages;
+    unsigned long long *s_empty = s_full + kMaxStages;
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
     long long *s_item = reinterpret_cast<long long *>(smem_raw + L.item_off);           // [2] published work items
     uint8_t *s_sel = smem_raw + L.sel_off;                                               // [16][4] r-th set bit of a nibble
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     long long *const trace = blockIdx.x == 0 ? p.trace : nullptr;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < kMaxStages; s++) {
             mbar_init(smem_u32(s_full + s), 1);
             mbar_init(smem_u32(s_empty + s), NCW);
             s_next[s] = 0;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
         s_sel[tid] = (uint8_t) pos;
     }
     // never-matching words below each stage: a candidate in the first row of a band whose shifted column is -1..-4
-    if (tid < kStages * kPrePad) s_stage[(tid / kPrePad) * stage_stride - kPrePad + (tid % kPrePad)] = CDS_CODE_PAD_WORD;
+    if (tid < NSTG * kPrePad) s_stage[(tid / kPrePad) * stage_stride - kPrePad + (tid % kPrePad)] = CDS_CODE_PAD_WORD;
     __syncthreads();
 
     if (warp == NCW) {
@@ -237,7 +238,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
         // Drives the barriers and the bulk copies, and publishes with every stage the range of the group's word list that falls
         // into the band's rows (two reads of the group's row-start table), so consumers never meet at a CTA-wide barrier.
         if (lane == 0) {
-            uint32_t q = 0;                 // running band number across items: stage = q & 1, use = q >> 1
+            uint32_t q = 0;                 // running band number across items: stage = q % NSTG, use = q / NSTG
+            int stage = 0;
+            uint32_t use = 0;
             uint32_t iseq = 0;
             for (;;) {
                 const long long w = (long long) atomicAdd(p.work_counter, 1ull);
@@ -245,13 +248,13 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 const int nb = done ? 1 : NB;
                 const int64_t t = done ? 0 : w % p.n_targets;
                 const uint32_t *gstart = done ? nullptr : p.groups[w / p.n_targets].gstart;
-                for (int b = 0; b < nb; b++, q++) {
-                    const int stage = q & 1;
+                for (int b = 0; b < nb; b++, q++, stage++) {
+                    if (stage == NSTG) { stage = 0; use++; }
                     const int y0 = b * R;
                     const int y1 = min(y0 + R, H);
                     uint2 range = make_uint2(0u, 0u);
                     if (!done) range = make_uint2(__ldg(gstart + y0 / 4), __ldg(gstart + (y1 + 3) / 4));     // tile rows of the band; issued before the wait below
-                    if (q >= kStages) mbar_wait(smem_u32(s_empty + stage), ((q >> 1) - 1) & 1);
+                    if (use > 0) mbar_wait(smem_u32(s_empty + stage), (use - 1) & 1);
                     if (trace && iseq < (uint32_t) kTraceItems) trace[(((size_t) iseq * kMaxBands + b) * 32 + 31) * 2] = clock64();
                     s_next[stage] = 0;
                     s_band[stage] = range;
@@ -279,7 +282,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     }
 
     // ---------------------------------------------------------------------- consumers
-    uint32_t q = 0, iseq = 0;
+    uint32_t iseq = 0;
+    int stage = 0;                                   // stage and use count of the band this warp is at
+    uint32_t use = 0;
     int cur_gi = -1;
     const uint4 *gwords = nullptr;                   // word list of the current group
     const uint16_t *glpal = nullptr;                 // palette references of its entries' set bits
@@ -289,12 +294,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const uint32_t mywq_addr = smem_u32(mywq);
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int *acc_base = s_acc;
-    auto wait_full = [&](uint32_t qq) {
-        if (p.wait_mode == 0) mbar_wait(smem_u32(s_full + (qq & 1)), (qq >> 1) & 1);
-        else mbar_wait_parked(smem_u32(s_full + (qq & 1)), (qq >> 1) & 1, p.wait_mode);
+    auto wait_full = [&]() {
+        if (p.wait_mode == 0) mbar_wait(smem_u32(s_full + stage), use & 1);
+        else mbar_wait_parked(smem_u32(s_full + stage), use & 1, p.wait_mode);
     };
     for (;;) {
-        wait_full(q);
+        wait_full();
         const long long w = *reinterpret_cast<volatile long long *>(s_item + (iseq & 1));
         if (w < 0) break;
         const int gi = (int) (w / p.n_targets);
@@ -314,9 +319,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             cur_gi = gi;
         }
 
-        for (int b = 0; b < NB; b++, q++) {
-            const int stage = q & 1;
-            if (b > 0) wait_full(q);
+        for (int b = 0; b < NB; b++) {
+            if (b > 0) wait_full();
             if (trace && iseq < (uint32_t) kTraceItems && lane == 0) trace[(((size_t) iseq * kMaxBands + b) * 32 + warp) * 2] = clock64();
             const uint32_t *band = s_stage + (size_t) stage * stage_stride;
             const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - (size_t) (b * R / 4) * rowpitch;   // indexed by the entries' absolute occupancy word index
@@ -331,10 +335,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             // Peels the set bits of 32 queued words (one word per lane; `c` = 0 for idle lanes) into the candidate queue,
             // lowest bit first, one bit per lane per round, and evaluates whenever 32 candidates are waiting.
             // A full batch of candidates: start its palette-index loads, evaluate the batch submitted before it.
-            uint2 pend_cand = make_uint2(0u, 0u);
+            const uint2 idle_cand = make_uint2((uint32_t) (S * pitch), 0u);      // an idle lane reads the band's first pixel and matches nothing
+            uint2 pend_cand = idle_cand;
             uint32_t pend_pr = 0;
             bool pend = false;
-            auto run_pending = [&]() { eval_candidates<NRINGS>(pend_cand, pend_pr, band, y0, pitch, s_pal, acc_base); };
+            auto run_pending = [&]() { eval_candidates<NRINGS>(pend_cand, pend_pr, band, pitch, s_pal, acc_base); };
             auto submit = [&](uint2 cand, bool live) {
                 const uint32_t pr = fetch_palette_ref(cand, live, glpal, pol_keep);
                 if (pend) run_pending();
@@ -344,9 +349,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             // candidates, 32 per round, and evaluates them.
             auto peel = [&](uint32_t c, uint4 e) {
                 const uint32_t wbits = e.x, lrec = e.z;
-                // position of the tile's first pixel | orientation | mask; a set bit adds (bit & 7) to x and (bit >> 3) to y
-                const uint32_t base = (((e.w >> kWordMetaColShift) & 255u) << 3) | ((e.w & 255u) << (11 + 2)) |
-                                      (((e.w >> kWordMetaOrientBit) & 1u) << 21) | (e.w & (1023u << kWordMetaMaskShift));
+                // offset of the tile's first pixel inside the staged band | (mask * 2 + orientation) << 15; a set bit adds
+                // (bit & 7) + (bit >> 3) * pitch
+                const uint32_t base = (uint32_t) (((int) (e.w & 255u) * 4 - y0 + S) * pitch) + (((e.w >> kWordMetaColShift) & 255u) << 3) +
+                                      ((((e.w >> kWordMetaMaskShift) << 1) | ((e.w >> kWordMetaOrientBit) & 1u)) << kCandOffsetBits);
                 // Load-balanced expansion: the batch's T candidate bits are numbered word by word (prefix sums of the popcounts),
                 // and in every round lane j takes candidate number j0 + j -- whichever word it belongs to -- so a round costs the
                 // same whether the bits sit in one dense tile or are spread over all 32.
@@ -361,22 +367,22 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 const uint32_t excl = incl - n;
                 for (uint32_t j0 = 0; j0 < total; j0 += 32) {
                     const uint32_t j = j0 + (uint32_t) lane;
-                    // source word = number of words whose candidates all come before number j (binary search over the lanes)
-                    uint32_t src = 0;
-#pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) {
-                        const uint32_t end = __shfl_sync(0xffffffffu, incl, (int) (src + step - 1) & 31);
-                        if (end <= j) src += step;
-                    }
+                    // source word of candidate j = (number of words that start at or before j) - 1.  Every queued word has at
+                    // least one candidate, so the words that START inside this round mark distinct bits of one 32-bit word
+                    // (one OR-reduction), and a lane counts the marks at or below its own position.
+                    const uint32_t rel = excl - j0;
+                    const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+                    const uint32_t w_first = (uint32_t) __popc(__ballot_sync(0xffffffffu, excl < j0));     // words that started in earlier rounds
+                    uint32_t src = w_first + (uint32_t) __popc(starts & (lt_mask + lt_mask + 1u)) - 1u;
                     const bool live = j < total;
                     src &= 31u;
                     const uint32_t cs = __shfl_sync(0xffffffffu, c, (int) src), es = __shfl_sync(0xffffffffu, excl, (int) src);
                     const uint32_t bs = __shfl_sync(0xffffffffu, base, (int) src), ls = __shfl_sync(0xffffffffu, lrec, (int) src);
                     const uint32_t ws = __shfl_sync(0xffffffffu, wbits, (int) src);
-                    uint2 cand = make_uint2((uint32_t) y0 << 11, 0u);
+                    uint2 cand = idle_cand;
                     if (live) {
                         const uint32_t bit = select_bit(cs, j - es, s_sel);              // the (j - es)-th candidate bit of that word
-                        cand.x = bs | (bit & 7u) | ((bit >> 3) << 11);
+                        cand.x = bs + (bit & 7u) + (bit >> 3) * (uint32_t) pitch;
                         cand.y = ls + (uint32_t) __popc(ws & ((1u << bit) - 1u));
                     }
                     if (j0 + 32 <= total) {
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             if (qt != qh) {
                 __syncwarp();
                 const bool live = lane < (int) (qt - qh);
-                uint2 cand = make_uint2((uint32_t) y0 << 11, 0u);
+                uint2 cand = idle_cand;
                 if (live) cand = myq[(qh + lane) & (kQueue - 1)];
                 submit(cand, live);
             }
@@ -523,6 +529,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             __syncwarp();
             if (trace && iseq < (uint32_t) kTraceItems && lane == 0) trace[(((size_t) iseq * kMaxBands + b) * 32 + warp) * 2 + 1] = clock64();
             if (lane == 0) mbar_arrive(smem_u32(s_empty + stage));
+            if (++stage == NSTG) { stage = 0; use++; }
         }
 
         // item epilogue: max over variants per orientation; mirrored wins only when strictly greater
@@ -552,19 +559,21 @@ struct CandConfig {
 };
 
 template <int GROUP>
-CandConfig cand_config(int xy_shift, const PlaneGeom &g, int n_warps)
+CandConfig cand_config(int xy_shift, const PlaneGeom &g, int n_warps, int n_stages, int max_rows)
 {
     const int bpitch = occupancy_tile_pitch(g.W);
     CandConfig c{};
     const int S = xy_shift;
     const int NS = xy_shift == 0 ? 1 : (xy_shift == 2 ? 9 : 17);
     const size_t budget = 227 * 1024;
-    for (int R = (g.H + 3) / 4 * 4; R >= 4; R -= 4) {        // whole occupancy tiles per band
+    int R_top = (g.H + 3) / 4 * 4;
+    if (max_rows >= 4) R_top = std::min(R_top, max_rows / 4 * 4);
+    for (int R = R_top; R >= 4; R -= 4) {        // whole occupancy tiles per band
         int n_bands = (g.H + R - 1) / R;
         if (n_bands > kMaxBands) break;
         size_t stage_words = (size_t) (R + 2 * S) * g.pitch;
-        if (stage_words * 4 >= (1u << 20)) continue;
-        CandSmem<GROUP> L((int) stage_words, NS, (R / 4) * occupancy_row_pitch(bpitch), n_warps);
+        if (stage_words >= (1u << kCandOffsetBits)) continue;       // candidates address the band with kCandOffsetBits bits (and a bulk copy stays below 1 MB)
+        CandSmem<GROUP> L((int) stage_words, NS, (R / 4) * occupancy_row_pitch(bpitch), n_warps, n_stages);
         if (L.total <= budget) {
             c.rows_per_band = R; c.n_bands = n_bands; c.stage_words = (int) stage_words; c.smem_bytes = L.total; c.ok = true;
             return c;
@@ -586,7 +595,8 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
                const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, int32_t *scores,
                const MatchScratch &scratch, cudaStream_t s, int dev)
 {
-    CandConfig c = cand_config<GROUP>(xy_shift, g, NCW);
+    const int n_stages = std::max(2, std::min(kMaxStages, cand_tuning().stages));
+    CandConfig c = cand_config<GROUP>(xy_shift, g, NCW, n_stages, cand_tuning().max_rows);
     if (!c.ok) return 0;
     CandParams p;
     p.masks = masks; p.n_masks = n_masks; p.planes = planes; p.g = g; p.n_targets = n_targets; p.scores = scores;
@@ -600,6 +610,7 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     static const int no_skip = env_int("CDSGPU_CAND_NOSKIP", 0);
     p.ticket_skip = no_skip ? 0 : 1;
     p.wait_mode = cand_tuning().wait_mode;
+    p.n_stages = n_stages;
     const int hint = cand_tuning().l2_hint;
     static const char *trace_path = std::getenv("CDSGPU_CAND_TRACE");
     p.trace = nullptr;
@@ -842,7 +853,8 @@ CandTuning &cand_tuning()
     // Waits poll try_wait by default.  Measured (profiles/r02_cand_trace.txt, tools/cand_sweep.py): a suspend-time hint does not stop the
     // hardware from returning at once, and sleeping between polls (32..400 ns) costs 1-3 % of the throughput without lowering the
     // instruction count -- the polling loop runs in issue slots that are idle anyway.
-    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 0), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31)};
+    static CandTuning t{env_int("CDSGPU_CAND_WAIT", 0), env_int("CDSGPU_CAND_L2HINT", 0), env_int("CDSGPU_CAND_WARPS", 31),
+                        env_int("CDSGPU_CAND_STAGES", 2), env_int("CDSGPU_CAND_ROWS", 0)};
     return t;
 }
 
@@ -873,7 +885,7 @@ bool cand_kernel_supported(int xy_shift, const PlaneGeom &g)
     if (!(xy_shift == 0 || xy_shift == 2 || xy_shift == 4)) return false;
     if (xy_shift > g.guard || xy_shift > g.pitch - g.W || xy_shift > kPrePad) return false;
     if (g.W > 2048 || g.H > 1024) return false;
-    return cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 16).ok;
+    return cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 16, 2, 0).ok;
 }
 
 void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,
@@ -920,9 +932,10 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     // tuning knob (default picked from profiles/): consumer warps per CTA.  More warps need more
     // shared memory for their queues; when the band stages no longer fit (xyShift 4: 34 accumulators per mask) fewer are used.
     int warps = cand_tuning().warps;
-    if (warps >= 31 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 31).ok) warps = 28;
-    if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28).ok) warps = 24;
-    if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24).ok) warps = 16;
+    const int n_stages = std::max(2, std::min(kMaxStages, cand_tuning().stages));
+    if (warps >= 31 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 31, n_stages, cand_tuning().max_rows).ok) warps = 28;
+    if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28, n_stages, cand_tuning().max_rows).ok) warps = 24;
+    if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24, n_stages, cand_tuning().max_rows).ok) warps = 16;
 #define CDS_CAND_LAUNCH(NCW) launch_cfg<CDS_PALETTE_GROUP, NCW>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, scratch, s, dev)
     if (warps >= 31) return CDS_CAND_LAUNCH(31);
     if (warps >= 28) return CDS_CAND_LAUNCH(28);

@@ -37,6 +37,8 @@ struct CandTuning {
     int wait_mode;      // how a consumer warp waits for a band: 0 polls try_wait, 1 try_wait with a suspend-time hint, n >= 2 test_wait + nanosleep(n ns)
     int l2_hint;        // 1: bulk copies of the streamed planes are evict-first, loads of the group's lists evict-last
     int warps;          // consumer warps per CTA (31, 28, 24 or 16)
+    int stages;         // band stages in flight (2 .. 4); more stages mean shorter bands
+    int max_rows;       // upper bound of the band height (0: as tall as shared memory allows)
 };
 CandTuning &cand_tuning();
 

@@ -9,13 +9,16 @@ sys.path.insert(0, ".")
 from colormipsearch_b200 import capi
 from oracle import oracle as O
 
-W, H, SEED = 1210, 566, 0xC0FFEE
+SEED = 0xC0FFEE
 ap = argparse.ArgumentParser()
 ap.add_argument("--masks", type=int, default=1000)
 ap.add_argument("--targets", type=int, default=4096)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--width", type=int, default=1210)
+ap.add_argument("--height", type=int, default=566)
 ap.add_argument("--settings", default="wait=0;wait=1;wait=32;wait=64;wait=100;wait=200;wait=400;wait=0,hint=1")
 a = ap.parse_args()
+W, H = a.width, a.height
 rects = O.label_rects(W, H)
 ctx = capi.Context(device_ids=[0])
 lib = capi.Library(ctx, W, H, a.targets)
@@ -29,6 +32,8 @@ for setting in a.settings.split(";"):
     ctx.set_option("cand_wait_mode", int(kv.get("wait", 0)))
     ctx.set_option("cand_l2_hint", int(kv.get("hint", 0)))
     ctx.set_option("cand_warps", int(kv.get("warps", 31)))
+    ctx.set_option("cand_stages", int(kv.get("stages", 2)))
+    ctx.set_option("cand_max_rows", int(kv.get("rows", 0)))
     res = ms.search_topk(lib, 300, 1.0)
     ms_total = 0.0
     for _ in range(a.reps):
