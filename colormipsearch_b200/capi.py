@@ -143,6 +143,7 @@ SIGNATURES = {
     "cds_pairq_get_stats": (C.c_int32, [_vp, _i64p, _i64p, _i64p]),
     "cds_debug_pairq_drive": (C.c_int32, [_vp, _vp, C.c_int64, C.POINTER(C.c_uint64), _i32p, _i64p, C.c_int64, C.c_int32, _i32p, _u8p, _f64p]),
     "cds_debug_slice_numbers": (C.c_int32, [_vp, _vp, C.c_int64, _u16p]),
+    "cds_debug_occupancy": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "cds_debug_tiff_codes": (C.c_int32, [_vp, _vp, _i64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _u32p, _u32p]),
 }
 
@@ -266,6 +267,16 @@ class Context:
         _check(lib().cds_debug_tiff_codes(self.h, _ptr(blob), offsets.ctypes.data_as(_i64p), n, W, H, int(data_threshold), int(bool(fused)),
                                           codes.ctypes.data_as(_u32p), valid.ctypes.data_as(_u32p)), self.h)
         return codes, valid
+
+    def debug_occupancy(self, valid, W, H, xy_shift):
+        """valid bits [n][H][6][vp] (uint32) -> occupancy tile rows [n][(H + 3) // 4][row pitch] (cds_debug_occupancy)."""
+        valid = np.ascontiguousarray(valid, dtype=np.uint32)
+        n = valid.shape[0]
+        tp = ((W + 7) // 8 + 3) // 4 * 4
+        nzw = ((6 * tp + 31) // 32 + 3) // 4 * 4
+        out = np.empty((n, (H + 3) // 4, 7 * tp + nzw), np.uint32)
+        _check(lib().cds_debug_occupancy(self.h, valid.ctypes.data_as(_vp), n, W, H, xy_shift, out.ctypes.data_as(_vp)), self.h)
+        return out
 
     def debug_slice_numbers(self, rgb):
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)

@@ -341,6 +341,7 @@ extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t
         if (std::strcmp(name, "cand_wait_mode") == 0) { cand_tuning().wait_mode = (int) value; return CDS_OK; }
         if (std::strcmp(name, "cand_l2_hint") == 0) { cand_tuning().l2_hint = value != 0; return CDS_OK; }
         if (std::strcmp(name, "cand_warps") == 0) { cand_tuning().warps = (int) value; return CDS_OK; }
+        if (std::strcmp(name, "occupancy_kernel") == 0) { occupancy_kernel_version() = value != 0; return CDS_OK; }
         if (std::strcmp(name, "cand_stages") == 0) { cand_tuning().stages = (int) value; return CDS_OK; }
         if (std::strcmp(name, "cand_max_rows") == 0) { cand_tuning().max_rows = (int) value; return CDS_OK; }
         return ctx->fail(CDS_ERR_BAD_ARG, std::string("cds_ctx_set_option: unknown option ") + name);

@@ -679,6 +679,41 @@ extern "C" cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, co
     });
 }
 
+// Test hook: per-sector valid bits [n][height][sectors][occupancy_valid_pitch(width)] -> the occupancy tile rows a search builds from
+// them, [n][tile rows][occupancy_row_pitch] (sector rows, OR row, non-empty bits), so that the occupancy kernels can be compared
+// with each other (cds_ctx_set_option "occupancy_kernel") and with the definition.
+extern "C" cds_status cds_debug_occupancy(cds_ctx *ctx, const uint32_t *valid, int64_t n, int32_t width, int32_t height, int32_t xy_shift,
+                                          uint32_t *occ_out)
+{
+    return cds::abi_guard("cds_debug_occupancy", [&]() -> cds_status {
+        if (!ctx) { set_tls_error("cds_debug_occupancy: NULL context"); return CDS_ERR_BAD_ARG; }
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (n < 0 || width <= 0 || height <= 0 || width > 16384 || height > 16384 || xy_shift < 0 || xy_shift > 4 || (xy_shift & 1))
+            return ctx->fail(CDS_ERR_BAD_ARG, "cds_debug_occupancy: bad size or xy_shift");
+        if (n == 0) return CDS_OK;
+        if (!valid || !occ_out) return ctx->fail(CDS_ERR_BAD_ARG, "cds_debug_occupancy: NULL argument");
+        DevState &ds = ctx->devs[0];
+        CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+        PlaneGeom g;
+        g.W = width; g.H = height; g.pitch = choose_pitch(width); g.guard = CDS_GUARD_ROWS;
+        const int vp = occupancy_valid_pitch(width), tp = occupancy_tile_pitch(width);
+        const size_t valid_words = (size_t) n * height * CDS_NUM_SECTORS * vp;
+        const size_t occ_words = (size_t) n * occupancy_target_words(width, height);
+        uint32_t *d_valid = nullptr, *d_occ = nullptr;
+        auto release = [&]() { cudaStreamSynchronize(ds.stream); ds.pool.free(d_valid); ds.pool.free(d_occ); };
+        struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_valid, valid_words * sizeof(uint32_t)));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_occ, occ_words * sizeof(uint32_t)));
+        CDS_CUDA(ctx, cudaMemcpyAsync(d_valid, valid, valid_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ds.stream));
+        CDS_CUDA(ctx, cudaMemsetAsync(d_occ, 0xA5, occ_words * sizeof(uint32_t), ds.stream));      // every word must be written by the kernels
+        launch_occupancy(nullptr, g, 0, n, xy_shift / 2, tp, d_valid, n, d_occ, ds.stream, true);
+        CDS_CUDA(ctx, cudaGetLastError());
+        CDS_CUDA(ctx, cudaMemcpyAsync(occ_out, d_occ, occ_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds.stream));
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        return CDS_OK;
+    });
+}
+
 // ------------------------------------------------------------------------------------------------------------------ PNG scanlines
 // The device side of the PNG ingest: the host has inflated the zlib stream (cds_formats.cpp); what is left per image is
 // height scanlines of [filter type][width * bps bytes], each filtered against the reconstructed bytes to the left and above

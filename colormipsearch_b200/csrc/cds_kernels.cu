@@ -329,6 +329,93 @@ __global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restri
     }
 }
 
+// The same for xyShift 2 (the production setting), every valid word read ONCE: a thread owns one 32-pixel column of one target and
+// walks down a segment of kOccSegRows tile rows with the last four image rows of every sector in registers, so a tile row costs four
+// new rows per sector instead of eight, and the vertical OR (rows y - 2, y, y + 2) is done on the raw words BEFORE the horizontal
+// spread (both are ORs of shifted copies, so they commute) -- four spreads per sector instead of eight.  The spread needs the
+// neighbouring columns' words: the threads of a block exchange them through shared memory (zero columns on both sides).
+constexpr int kOccThreads = 256;
+constexpr int kOccSegRows = 12;
+
+__global__ void __launch_bounds__(kOccThreads) occupancy_ring1_kernel(const uint32_t *__restrict__ valid /* chunk-relative */, int H, int vp, int tp,
+                                                                      int64_t t0, uint32_t *__restrict__ occ, int segs, int blocks_per_target)
+{
+    extern __shared__ uint32_t s_v[];                     // [sector][row of the tile][segment][kc + 2]
+    const int kc = tp / 4;                                // 32-pixel columns that hold tile words
+    const int cw = kc + 2;
+    const int seg = (int) threadIdx.x / kc, k = (int) threadIdx.x - seg * kc;
+    const int rowpitch = occupancy_row_pitch(tp);
+    const int HT = occupancy_tile_rows(H);
+    const int vrow_words = CDS_NUM_SECTORS * vp;
+    const int64_t tl = blockIdx.x / blocks_per_target;
+    const int ty0 = ((int) (blockIdx.x % blocks_per_target) * segs + seg) * kOccSegRows;
+    const bool active = seg < segs && ty0 < HT;
+    const uint32_t *vimg = valid + (size_t) tl * H * vrow_words + k;
+    auto sv = [&](int s, int r) -> uint32_t * { return s_v + ((s * 4 + r) * segs + seg) * cw; };
+    if (seg < segs && (k == 0 || k == kc - 1))
+        for (int i = 0; i < CDS_NUM_SECTORS * 4; i++) (s_v + (i * segs + seg) * cw)[k == 0 ? 0 : kc + 1] = 0u;
+    if (seg < segs && kc == 1)
+        for (int i = 0; i < CDS_NUM_SECTORS * 4; i++) (s_v + (i * segs + seg) * cw)[0] = 0u;
+    auto raw = [&](int s, int y) -> uint32_t { return (active && y >= 0 && y < H) ? __ldg(vimg + (size_t) y * vrow_words + s * vp) : 0u; };
+    uint32_t carry[CDS_NUM_SECTORS][4];                   // image rows y0 - 2 .. y0 + 1 of the coming tile row
+#pragma unroll
+    for (int s = 0; s < CDS_NUM_SECTORS; s++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) carry[s][j] = raw(s, 4 * ty0 - 2 + j);
+    for (int it = 0; it < kOccSegRows; it++) {
+        const int ty = ty0 + it, y0 = 4 * ty;
+        uint32_t nw[CDS_NUM_SECTORS][4];                  // rows y0 + 2 .. y0 + 5
+#pragma unroll
+        for (int s = 0; s < CDS_NUM_SECTORS; s++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) nw[s][j] = raw(s, y0 + 2 + j);
+        if (seg < segs) {
+#pragma unroll
+            for (int s = 0; s < CDS_NUM_SECTORS; s++) {
+                sv(s, 0)[k + 1] = carry[s][0] | carry[s][2] | nw[s][0];
+                sv(s, 1)[k + 1] = carry[s][1] | carry[s][3] | nw[s][1];
+                sv(s, 2)[k + 1] = carry[s][2] | nw[s][0] | nw[s][2];
+                sv(s, 3)[k + 1] = carry[s][3] | nw[s][1] | nw[s][3];
+#pragma unroll
+                for (int j = 0; j < 4; j++) carry[s][j] = nw[s][j];
+            }
+        }
+        __syncthreads();
+        if (active && ty < HT) {
+            uint32_t *trow = occ + ((size_t) (t0 + tl) * HT + ty) * rowpitch;
+            uint4 *orow = reinterpret_cast<uint4 *>(trow) + k;
+            uint32_t *nz = trow + (CDS_NUM_SECTORS + 1) * tp;
+            uint32_t any[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int s = 0; s < CDS_NUM_SECTORS; s++) {
+                uint32_t o[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t *v = sv(s, r) + k;
+                    const uint32_t l = v[0], c = v[1], rr = v[2];
+                    o[r] = y0 + r < H ? (c | (c << 2) | (c >> 2) | (l >> 30) | (rr << 30)) : 0u;
+                    any[r] |= o[r];
+                }
+                const uint4 t = strip_to_tiles(o);
+                orow[(size_t) s * (tp / 4)] = t;
+                const uint32_t nib = (t.x != 0u ? 1u : 0u) | (t.y != 0u ? 2u : 0u) | (t.z != 0u ? 4u : 0u) | (t.w != 0u ? 8u : 0u);
+                if (nib) {
+                    const int bit = s * tp + 4 * k;
+                    atomicOr(&nz[bit >> 5], nib << (bit & 31));
+                }
+            }
+            orow[(size_t) CDS_NUM_SECTORS * (tp / 4)] = strip_to_tiles(any);
+        }
+        __syncthreads();
+    }
+}
+
+int &occupancy_kernel_version()
+{
+    static int v = 1;       // 1: occupancy_ring1_kernel for xyShift 2; 0: the generic kernel everywhere (cross-check)
+    return v;
+}
+
 static void launch_occupancy_kernel(const uint32_t *valid, int H, int vp, int tp, int64_t t0, int64_t n, int rings, uint32_t *occ, cudaStream_t s)
 {
     // the non-empty bits behind every tile row start from zero: one strided clear instead of the separate pass that used to read every
@@ -337,6 +424,14 @@ static void launch_occupancy_kernel(const uint32_t *valid, int H, int vp, int tp
     const int HT = occupancy_tile_rows(H);
     cudaMemset2DAsync(occ + (size_t) t0 * HT * rowpitch + (size_t) (CDS_NUM_SECTORS + 1) * tp, (size_t) rowpitch * sizeof(uint32_t), 0,
                       (size_t) occupancy_nz_words(tp) * sizeof(uint32_t), (size_t) n * HT, s);
+    const int kc = tp / 4;
+    if (rings == 1 && occupancy_kernel_version() == 1 && kc >= 1 && kc <= kOccThreads / 2 && n * 64 < (1ll << 31)) {
+        const int segs = std::min(kOccThreads / kc, 8);          // segments per block; keeps the exchange buffer below 32 kB
+        const int blocks_per_target = (HT + segs * kOccSegRows - 1) / (segs * kOccSegRows);
+        const size_t smem = (size_t) CDS_NUM_SECTORS * 4 * segs * (kc + 2) * sizeof(uint32_t);
+        occupancy_ring1_kernel<<<(unsigned) (n * blocks_per_target), kOccThreads, smem, s>>>(valid, H, vp, tp, t0, occ, segs, blocks_per_target);
+        return;
+    }
     if (rings == 0) occupancy_kernel<0><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
     else if (rings == 1) occupancy_kernel<1><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
     else occupancy_kernel<2><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);

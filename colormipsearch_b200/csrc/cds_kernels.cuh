@@ -91,6 +91,7 @@ __host__ __device__ inline int occupancy_tile_rows(int H) { return (H + 3) / 4; 
 __host__ __device__ inline int occupancy_nz_words(int tp) { return ((CDS_NUM_SECTORS * tp + 31) / 32 + 3) / 4 * 4; }
 __host__ __device__ inline int occupancy_row_pitch(int tp) { return (CDS_NUM_SECTORS + 1) * tp + occupancy_nz_words(tp); }
 __host__ __device__ inline size_t occupancy_target_words(int W, int H) { return (size_t) occupancy_tile_rows(H) * occupancy_row_pitch(occupancy_tile_pitch(W)); }
+int &occupancy_kernel_version();      // cds_ctx_set_option("occupancy_kernel")
 void launch_occupancy(const uint32_t *planes, PlaneGeom g, int64_t t0, int64_t n, int rings, int tp,
                       uint32_t *valid_scratch, int64_t scratch_targets, uint32_t *occ, cudaStream_t s, bool valid_ready = false);
 

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 
 #include "cds_runtime.h"
@@ -290,8 +291,22 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         }
     } drain{ctx, used_devs};
 
+    // profiling aid (CDSGPU_STREAM_TRACE=1): device events around every phase of every chunk and the host's own clock, printed to
+    // stderr when the call ends
+    static const bool trace = std::getenv("CDSGPU_STREAM_TRACE") != nullptr;
+    struct ChunkTrace { int d; int64_t cnt; cudaEvent_t ev[5]; double host_parse_ms, host_wait_ms, host_enqueue_at_ms; };
+    std::vector<ChunkTrace> traces;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(); };
+    auto mark = [&](ChunkTrace *tr, int i, cudaStream_t st) {
+        if (!tr) return;
+        cudaEventCreate(&tr->ev[i]);
+        cudaEventRecord(tr->ev[i], st);
+    };
+
     // enqueue every chunk; nothing below blocks the host when the source is pinned memory
     std::vector<int64_t> per_dev(D, 0);
+    if (trace) traces.reserve(plan.size());
     for (const Chunk &ch : plan) {
         const int d = ch.d;
         DevState &ds = ctx->devs[d];
@@ -301,6 +316,9 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         const int64_t first = ch.first, cnt = ch.cnt;
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
         const uint32_t *planes = sb.planes;
+        ChunkTrace *tr = nullptr;
+        if (trace) { traces.push_back(ChunkTrace{d, cnt, {}, 0, 0, 0}); tr = &traces.back(); }
+        const double t_chunk0 = trace ? host_ms() : 0;
         if (resident) {
             planes = resident->shards[d].planes + (size_t) first * g.plane_stride();      // the same geometry, starting at plane `first`
         } else if (tiff) {
@@ -315,7 +333,9 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
                 if (st != CDS_OK) return ctx->fail(st, "cds_search_stream_tiff: file " + std::to_string(first + i) + ": " + err);
             }
             CDS_TRY(ensure_tiff_bufs(ctx, ds, tiff_comp_bytes, strips.size()));
+            const double t_parsed = trace ? host_ms() : 0;
             if (j >= 2) CDS_CUDA(ctx, cudaEventSynchronize(sb.h2d_done[slot]));        // the slot's previous table has left the host
+            if (tr) { tr->host_parse_ms = t_parsed - t_chunk0; tr->host_wait_ms = host_ms() - t_parsed; }
             memcpy(sb.h_strips[slot], strips.data(), strips.size() * sizeof(TiffStrip));
             if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
             const size_t bytes = (size_t) (tiff->offsets[first + cnt] - base);
@@ -323,7 +343,9 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             CDS_CUDA(ctx, cudaMemcpyAsync(sb.d_strips[slot], sb.h_strips[slot], strips.size() * sizeof(TiffStrip), cudaMemcpyHostToDevice, sb.copy_stream));
             ctx->stats.h2d_bytes += (int64_t) bytes + (int64_t) (strips.size() * sizeof(TiffStrip));
             CDS_CUDA(ctx, cudaEventRecord(sb.h2d_done[slot], sb.copy_stream));
+            mark(tr, 0, ds.stream);                  // the compute stream's position BEFORE it waits for the upload
             CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
+            mark(tr, 1, ds.stream);
             if (fused_ingest) {
                 // strips -> code words + per-sector valid bits in one kernel, no RGB image in HBM in between
                 launch_tiff_encode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.planes, g, 0, ds.d_rank_tab, thr,
@@ -336,6 +358,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
                 ctx->stats.kernel_launches += 2;
             }
             CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ds.stream));
+            mark(tr, 2, ds.stream);
         } else {
             if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
             CDS_CUDA(ctx, cudaMemcpyAsync(sb.staging[slot], targets_rgb + (size_t) first * img_bytes, (size_t) cnt * img_bytes,
@@ -357,6 +380,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             tv.occ_ready = true;
         }
         CDS_CUDA(ctx, cudaGetLastError());
+        if (tr && tiff) mark(tr, 3, ds.stream);
         CDS_TRY(launch_match_view(ctx, ms, tv, d, 0, M, sb.scores, ds.stream, sb.timing[2 * j], sb.timing[2 * j + 1]));
         if (all) {
             launch_collect_matches(sb.scores, M, cnt, sb.min_score, 0, first, all_keys[d], all_masks[d], all_counter[d],
@@ -367,6 +391,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             launch_topk_merge(sb.keys_run, sb.counts_run, sb.keys_chunk, sb.counts_chunk, M, k, ds.stream);
             ctx->stats.kernel_launches += 2;
         }
+        if (tr && tiff) { mark(tr, 4, ds.stream); tr->host_enqueue_at_ms = host_ms(); }
         CDS_CUDA(ctx, cudaGetLastError());
     }
 
@@ -401,6 +426,24 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         match_ms = std::max(match_ms, dev_match);
         cudaEventElapsedTime(&ms_f, ds.ev0, ds.ev2);
         total_ms = std::max(total_ms, (double) ms_f);
+    }
+    if (trace && tiff) {
+        std::fprintf(stderr, "# chunk dev targets | host: parse wait enqueued_at | device: start(since ev0) wait_h2d ingest occupancy match topk | match events\n");
+        std::vector<int64_t> jj(D, 0);
+        for (size_t c = 0; c < traces.size(); c++) {
+            ChunkTrace &t = traces[c];
+            float a0 = 0, w = 0, ing = 0, occm = 0, rest = 0, mm = 0;
+            cudaEventElapsedTime(&a0, ctx->devs[t.d].ev0, t.ev[0]);
+            cudaEventElapsedTime(&w, t.ev[0], t.ev[1]);
+            cudaEventElapsedTime(&ing, t.ev[1], t.ev[2]);
+            cudaEventElapsedTime(&occm, t.ev[2], t.ev[3]);
+            cudaEventElapsedTime(&rest, t.ev[3], t.ev[4]);
+            const int64_t j = jj[t.d]++;
+            cudaEventElapsedTime(&mm, ctx->devs[t.d].sb.timing[2 * j], ctx->devs[t.d].sb.timing[2 * j + 1]);
+            std::fprintf(stderr, "%3zu %d %5lld | %7.3f %7.3f %8.3f | %8.3f %7.3f %7.3f %7.3f %7.3f %7.3f\n", c, t.d, (long long) t.cnt, t.host_parse_ms, t.host_wait_ms,
+                         t.host_enqueue_at_ms, a0, w, ing, occm, mm, rest - mm);
+            for (int i = 0; i < 5; i++) cudaEventDestroy(t.ev[i]);
+        }
     }
     ctx->stats.match_kernel_ms = match_ms;
     ctx->stats.total_device_ms = total_ms;

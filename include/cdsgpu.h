@@ -99,7 +99,8 @@ int32_t    cds_abi_version(void);
  * falls back to building them per target chunk inside cds_search_topk when they do not fit; 0 always builds them per chunk.
  * "fused_ingest": 1 (default) = the streaming searches over TIFF files turn the strips straight into the library's code words;
  * 0 = decode to RGB pixels first, then encode (the two-kernel path, kept as a cross-check).
- * "cand_wait_mode", "cand_l2_hint", "cand_warps": tuning knobs of the candidate kernel (csrc/cds_cand.cuh), process-wide.
+ * "cand_wait_mode", "cand_l2_hint", "cand_warps", "cand_stages", "cand_max_rows": tuning knobs of the candidate kernel (csrc/cds_cand.cuh),
+ *   process-wide.  "occupancy_kernel": 1 (default) = the single-pass occupancy kernel for xyShift 2, 0 = the generic one (cross-check).
  * Unknown names: CDS_ERR_BAD_ARG. */
 cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t value);
 
@@ -432,6 +433,12 @@ cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, const int64_t
                                 int32_t data_threshold, int32_t fused, uint32_t *codes_out, uint32_t *valid_out);
 /* Drives cds_pairq_score from n_threads native threads over a list of pairs, the way the reference's thread pool drives
  * calculateMatchingScore: thread-safety tests and the throughput number of the single-pair entry point (bench.py). */
+/* Test hook: per-sector valid bits [n][height][6][vp] (vp = ((width + 31) / 32 rounded up to a multiple of 4) words per row and sector,
+ * bit x % 32 of word x / 32) -> the occupancy tile rows built from them for xy_shift 0 / 2 / 4, [n][(height + 3) / 4][row pitch] with
+ * row pitch = 7 * tp + nz words (tp = (width + 7) / 8 rounded up to a multiple of 4; nz = ((6 * tp + 31) / 32 rounded up to a multiple of
+ * 4): six sector rows of 8 x 4 tile words, their OR row, one "non-empty" bit per sector tile word.  The words between the rows are all written. */
+cds_status cds_debug_occupancy(cds_ctx *ctx, const uint32_t *valid, int64_t n, int32_t width, int32_t height, int32_t xy_shift,
+                               uint32_t *occ_out);
 cds_status cds_debug_pairq_drive(cds_pairq *q, const uint8_t *targets_rgb, int64_t n_targets, const uint64_t *keys,
                                  const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs, int32_t n_threads,
                                  int32_t *scores_out, uint8_t *mirrored_out, double *seconds_out);
