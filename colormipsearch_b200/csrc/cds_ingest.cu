@@ -205,9 +205,8 @@ tiff_encode_kernel(const uint8_t *__restrict__ src, const TiffStrip *__restrict_
     const uint32_t in_len = st.src_len, out_len = st.dst_len & ~kTiffStripPacked;
     const bool packed = (st.dst_len & kTiffStripPacked) != 0;
     const uint32_t row_bytes = (uint32_t) g.W * 3u;
-    const uint32_t img_bytes = row_bytes * (uint32_t) g.H;
-    const int64_t img = st.dst / img_bytes;
-    int y = (int) ((st.dst % img_bytes) / row_bytes);                                 // strips and stored pieces are whole rows
+    const int64_t img = st.dst / (uint32_t) g.H;                                      // strips and stored pieces are whole rows: dst counts rows
+    int y = (int) (st.dst % (uint32_t) g.H);
     const int y_end = y + (int) (out_len / row_bytes);
     const uint32_t black = (uint32_t) CDS_SR_NONE << CDS_CODE_SR_SHIFT | (0 > thr ? 0u : CDS_CODE_BELOW_BIT);
 
@@ -650,7 +649,8 @@ extern "C" cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, co
         for (int64_t i = 0; i < n; i++) {
             const int64_t a = offsets[i], b = offsets[i + 1];
             if (a < 0 || b < a) return ctx->fail(CDS_ERR_BAD_ARG, "cds_debug_tiff_codes: offsets must be non-decreasing");
-            cds_status st = tiff_collect_strips(blob + a, (size_t) (b - a), width, height, (uint64_t) (a - offsets[0]), (uint64_t) i * img_bytes, strips, err, fused != 0);
+            cds_status st = tiff_collect_strips(blob + a, (size_t) (b - a), width, height, (uint64_t) (a - offsets[0]),
+                                                fused ? (uint64_t) i * height : (uint64_t) i * img_bytes, strips, err, fused != 0);
             if (st != CDS_OK) return ctx->fail(st, "cds_debug_tiff_codes: file " + std::to_string(i) + ": " + err);
         }
         const size_t comp_bytes = (size_t) (offsets[n] - offsets[0]);

@@ -28,6 +28,7 @@ struct StreamBufs {
     int64_t chunk = 0;                  // targets per chunk the buffers are sized for
     int64_t m_cap = 0, key_cap = 0;     // masks / (masks * k) the score and key buffers are sized for
     cudaStream_t copy_stream = nullptr;
+    size_t staging_cap[2] = {0, 0};
     uint8_t *staging[2] = {nullptr, nullptr};   // RGB chunks as uploaded (double buffered: the next upload overlaps this chunk's kernels)
     uint32_t *planes = nullptr, *occ = nullptr, *valid = nullptr;
     int32_t *scores = nullptr;          // [masks][chunk]
@@ -113,7 +114,7 @@ struct cds_ctx {
     int resident_occupancy = 1;   // cds_ctx_set_option("resident_occupancy"): 0 = always build occupancy bitmaps per target chunk
     int64_t stream_chunk = 256;   // cds_ctx_set_option("stream_chunk"): targets per chunk of cds_search_stream_rgb
     int fused_ingest = 1;         // cds_ctx_set_option("fused_ingest"): 1 = TIFF strips go straight to code words (tiff_encode_kernel), 0 = decode to RGB, then encode
-    int64_t stream_chunk_tiff = 1024;   // cds_ctx_set_option("stream_chunk_tiff"): targets per chunk of cds_search_stream_tiff
+    int64_t stream_chunk_tiff = 4096;   // cds_ctx_set_option("stream_chunk_tiff"): targets per chunk of cds_search_stream_tiff
 
     cds_status fail(cds_status code, const std::string &msg) const;
     cds_status check(cudaError_t e, const char *what) const;

@@ -52,7 +52,8 @@ void cds::StreamBufs::release()
 
 namespace {
 
-cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, int bpitch, int64_t chunk, int64_t M, int64_t k, bool upload)
+cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, int bpitch, int64_t chunk, int64_t M, int64_t k, bool upload,
+                              int staging_slots)
 {
     StreamBufs &sb = ds.sb;
     CDS_CUDA(ctx, cudaSetDevice(ds.dev));
@@ -67,7 +68,7 @@ cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, in
     if (sb.W != g.W || sb.H != g.H || sb.chunk < chunk) {
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
         CDS_CUDA(ctx, cudaStreamSynchronize(sb.copy_stream));
-        for (int i = 0; i < 2; i++) if (sb.staging[i]) { cudaFree(sb.staging[i]); sb.staging[i] = nullptr; }
+        for (int i = 0; i < 2; i++) if (sb.staging[i]) { cudaFree(sb.staging[i]); sb.staging[i] = nullptr; sb.staging_cap[i] = 0; }
         if (sb.planes) { cudaFree(sb.planes); sb.planes = nullptr; }
         if (sb.occ) { cudaFree(sb.occ); sb.occ = nullptr; }
         if (sb.valid) { cudaFree(sb.valid); sb.valid = nullptr; }
@@ -83,12 +84,21 @@ cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, in
         sb.W = g.W; sb.H = g.H; sb.chunk = chunk;
     }
     if (upload && !sb.planes) {
-        // staging for the uploads and code planes of one chunk: only searches over host targets need them
+        // code planes of one chunk: only searches over host targets need them
         const size_t words = g.total_words(sb.chunk);
-        for (int i = 0; i < 2; i++) CDS_CUDA(ctx, cudaMalloc(&sb.staging[i], (size_t) sb.chunk * img_bytes + 64));
         CDS_CUDA(ctx, cudaMalloc(&sb.planes, words * sizeof(uint32_t)));
         launch_fill_words(sb.planes, words, CDS_CODE_PAD_WORD, ds.stream);      // guard rows stay pad words for ever
         CDS_CUDA(ctx, cudaGetLastError());
+    }
+    // RGB staging: two halves for uploaded pixels, one for the two-kernel TIFF path, none for the fused TIFF ingest
+    for (int i = 0; i < staging_slots; i++) {
+        const size_t need = (size_t) chunk * img_bytes + 64;
+        if (sb.staging_cap[i] >= need) continue;
+        CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        CDS_CUDA(ctx, cudaStreamSynchronize(sb.copy_stream));
+        if (sb.staging[i]) { cudaFree(sb.staging[i]); sb.staging[i] = nullptr; sb.staging_cap[i] = 0; }
+        CDS_CUDA(ctx, cudaMalloc(&sb.staging[i], need));
+        sb.staging_cap[i] = need;
     }
     if (sb.m_cap < M) {
         CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
@@ -199,7 +209,10 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         g = resident->g;
         CDS_TRY(resident->bake(ms->params.data_threshold));
     }
-    const int64_t chunk = std::min<int64_t>(tiff ? ctx->stream_chunk_tiff : ctx->stream_chunk, n_targets);
+    const bool fused_ingest = ctx->fused_ingest != 0 && g.W <= 2048;      // the fused kernel marks 32-pixel chunks in a 64-bit mask
+    int64_t chunk = std::min<int64_t>(tiff ? ctx->stream_chunk_tiff : ctx->stream_chunk, n_targets);
+    // the two-kernel TIFF path addresses the chunk's decoded pixels with 32 bits
+    if (tiff && !fused_ingest) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (int64_t) (0xF0000000ull / img_bytes)));
     // the chunk plan: (device, first target, count); host targets go round-robin over the devices, a resident library is
     // walked shard by shard (first = index LOCAL to the shard)
     struct Chunk { int d; int64_t first, cnt; };
@@ -211,13 +224,32 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             for (int d = 0; d < D; d++)
                 if (f < resident->local_size(d)) plan.push_back({d, f, std::min<int64_t>(chunk, resident->local_size(d) - f)});
     } else {
-        // TIFF files: the first chunks of every device are short (256, 512, ...) so that the match kernel starts early -- a full
-        // chunk of 1 024 files needs ~10 ms of parsing, upload, decode and encode before its first comparison
+        // TIFF files: the first chunks of every device are short (256, 512, ...) so that the match kernel starts early -- a full chunk
+        // needs milliseconds of parsing, upload and ingest before its first comparison -- and what is left after the ramp is cut into
+        // equal chunks (a short last chunk would leave most SMs idle during its match kernel: the kernel hands out whole targets).
+        // A chunk also ends where its files would exceed what the strip table addresses with 32 bits.
         int64_t f = 0;
+        int64_t even = 0;                      // chunk length after the ramp (0: not there yet)
         for (int64_t c = 0; f < n_targets; c++) {
             int64_t want = chunk;
-            if (tiff) want = std::min<int64_t>(chunk, (int64_t) 256 << std::min<int64_t>(c / D, 8));
-            const int64_t cnt = std::min<int64_t>(want, n_targets - f);
+            if (tiff) {
+                const int64_t ramp = (int64_t) 256 << std::min<int64_t>(c / D, 8);
+                if (ramp < chunk) {
+                    want = ramp;
+                } else {
+                    if (even == 0) {
+                        const int64_t rest = n_targets - f, per_round = chunk * D;
+                        const int64_t rounds = (rest + per_round - 1) / per_round;
+                        even = std::max<int64_t>(1, (rest + rounds * D - 1) / (rounds * D));
+                    }
+                    want = std::min(chunk, even);
+                }
+            }
+            int64_t cnt = std::min<int64_t>(want, n_targets - f);
+            if (tiff) {
+                const uint64_t cap = 0xC0000000ull;
+                while (cnt > 1 && (uint64_t) (tiff->offsets[f + cnt] - tiff->offsets[f]) > cap) cnt = (cnt + 1) / 2;
+            }
             plan.push_back({(int) (c % D), f, cnt});
             f += cnt;
         }
@@ -229,9 +261,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
 
     size_t tiff_comp_bytes = 0;
     std::vector<TiffStrip> strips;
-    const bool fused_ingest = ctx->fused_ingest != 0 && g.W <= 2048;      // the fused kernel marks 32-pixel chunks in a 64-bit mask
     if (tiff) {
-        if ((uint64_t) chunk * img_bytes > 0xF0000000ull) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_search_stream_tiff: stream_chunk too large for this image size");
         for (const Chunk &ch : plan) {
             const int64_t a = tiff->offsets[ch.first], b = tiff->offsets[ch.first + ch.cnt];
             if (a < 0 || b < a) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_tiff: offsets must be non-decreasing");
@@ -258,7 +288,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     struct Releaser { std::function<void()> f; ~Releaser() { f(); } } releaser{release_all};
     for (int d = 0; d < used_devs; d++) {
         DevState &ds = ctx->devs[d];
-        CDS_TRY(ensure_stream_bufs(ctx, ds, g, bpitch, chunk, M, k, resident == nullptr));
+        CDS_TRY(ensure_stream_bufs(ctx, ds, g, bpitch, chunk, M, k, resident == nullptr, resident ? 0 : (tiff ? (fused_ingest ? 0 : 1) : 2)));
         if (tiff) CDS_TRY(ensure_tiff_bufs(ctx, ds, tiff_comp_bytes, (size_t) chunk * 128));
         CDS_CUDA(ctx, cudaMemcpyAsync(ds.sb.min_score, min_score.data(), (size_t) M * sizeof(int32_t), cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaMemsetAsync(ds.sb.counts_run, 0, (size_t) M * sizeof(int32_t), ds.stream));
@@ -329,7 +359,8 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             for (int64_t i = 0; i < cnt; i++) {
                 const int64_t a = tiff->offsets[first + i], b = tiff->offsets[first + i + 1];
                 if (b < a) return ctx->fail(CDS_ERR_BAD_ARG, "cds_search_stream_tiff: offsets must be non-decreasing");
-                cds_status st = tiff_collect_strips(tiff->blob + a, (size_t) (b - a), g.W, g.H, (uint64_t) (a - base), (uint64_t) i * img_bytes, strips, err, fused_ingest);
+                cds_status st = tiff_collect_strips(tiff->blob + a, (size_t) (b - a), g.W, g.H, (uint64_t) (a - base),
+                                                    fused_ingest ? (uint64_t) i * g.H : (uint64_t) i * img_bytes, strips, err, fused_ingest);
                 if (st != CDS_OK) return ctx->fail(st, "cds_search_stream_tiff: file " + std::to_string(first + i) + ": " + err);
             }
             CDS_TRY(ensure_tiff_bufs(ctx, ds, tiff_comp_bytes, strips.size()));

@@ -161,8 +161,9 @@ cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int h
     for (int i = 0; i < info.n_strips; i++) {
         const uint64_t row0 = (uint64_t) i * info.rows_per_strip;
         const uint64_t rows = std::min<uint64_t>(info.rows_per_strip, (uint64_t) height - row0);
-        const uint64_t src = src_base + offs[i], dst = dst_base + row0 * row_bytes, dlen = rows * row_bytes;
-        if (src + lens[i] > 0xFFFFFFFFull || dst + dlen > 0xFFFFFFFFull || dlen >= kTiffStripPacked) {
+        // whole_rows (the fused ingest): `dst` counts image ROWS from the start of the chunk, so a chunk is not bounded by 4 GB of pixels
+        const uint64_t src = src_base + offs[i], dst = whole_rows ? dst_base + row0 : dst_base + row0 * row_bytes, dlen = rows * row_bytes;
+        if (src + lens[i] > 0xFFFFFFFFull || dst + (whole_rows ? rows : dlen) > 0xFFFFFFFFull || dlen >= kTiffStripPacked) {
             err = "TIFF: chunk too large for the strip table (lower stream_chunk)";
             return CDS_ERR_UNSUPPORTED;
         }
@@ -173,7 +174,7 @@ cds_status tiff_collect_strips(const uint8_t *file, size_t len, int width, int h
         for (uint64_t o = 0; o < dlen; o += step) {
             const uint64_t piece = std::min<uint64_t>(step, dlen - o);
             const uint64_t avail = o < have ? std::min<uint64_t>(piece, have - o) : 0;
-            out.push_back(TiffStrip{(uint32_t) (src + o), (uint32_t) avail, (uint32_t) (dst + o), (uint32_t) piece});
+            out.push_back(TiffStrip{(uint32_t) (src + o), (uint32_t) avail, (uint32_t) (whole_rows ? dst + o / row_bytes : dst + o), (uint32_t) piece});
         }
     }
     return CDS_OK;

@@ -15,7 +15,8 @@
 namespace cds {
 
 // One strip of one image, as the decode kernel sees it: `src` = first byte of the strip relative to the start of the uploaded
-// byte range, `dst` = first decoded byte relative to the start of the chunk's RGB area.  Bit 31 of dst_len: the strip is
+// byte range, `dst` = first decoded byte relative to the start of the chunk's RGB area (tiff_collect_strips with whole_rows, the fused
+// ingest: first decoded image ROW, image index * height + row, so that a chunk may hold more than 4 GB of pixels).  Bit 31 of dst_len: the strip is
 // PackBits-compressed (otherwise stored bytes are copied).
 struct TiffStrip {
     uint32_t src, src_len, dst, dst_len;

@@ -134,7 +134,7 @@ def test_stream_search_over_tiff_files_equals_rgb(ctx, synth_files, chunk):
             ms.close()
     finally:
         ctx.set_option("stream_chunk", 256)
-        ctx.set_option("stream_chunk_tiff", 1024)
+        ctx.set_option("stream_chunk_tiff", 4096)
 
 
 def test_stream_search_reports_the_bad_file(ctx, synth_files, tiffs):

@@ -13,6 +13,8 @@ fused = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rects = O.label_rects(W, H)
 ctx = capi.Context(device_ids=[0])
 ctx.set_option("fused_ingest", fused)
+if len(sys.argv) > 3:
+    ctx.set_option("stream_chunk_tiff", int(sys.argv[3]))
 masks = np.concatenate([ctx.synth_rgb(0, SEED, i, min(64, 1000 - i), W, H, on_device=True) for i in range(0, 1000, 64)])
 targets = np.concatenate([ctx.synth_rgb(1, SEED, i, 64, W, H, on_device=True) for i in range(0, n, 64)])
 with ThreadPoolExecutor(16) as ex:
