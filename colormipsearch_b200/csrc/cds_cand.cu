@@ -176,7 +176,8 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const u
     const uint32_t len = ((iv >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
     const uint32_t *pc = band + (cand.x & (kCandOffsetMask));
     // accumulators of this mask: [0, NS) unmirrored, [NS, 2 NS) mirrored
-    const int *acc = acc_base + (cand.x >> kCandOffsetBits) * (uint32_t) NS;
+    const int *acc = acc_base + (cand.x >> kCandOffsetBits);
+    (void) NS;
     uint32_t cw[NS];
     EvalUnroll<NRINGS, 0>::load(pc, pitch, cw);          // all shifted reads first, then the compares
     EvalUnroll<NRINGS, 0>::count(cw, acc, lo, len);
@@ -201,7 +202,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
     uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + L.queue_off);                  // [NCW][kQueue] candidates
     uint2 *s_wqueue = reinterpret_cast<uint2 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] {candidate bits, entry index} of words with candidates
-    int *s_acc = p.acc + (size_t) blockIdx.x * GROUP * NV;                              // this CTA's accumulators [GROUP][NV], global memory, zero on entry
+    constexpr int NVP = (NV + 3) / 4 * 4;             // a mask's accumulators padded to whole 16-byte words (the epilogue reads them as int4)
+    int *s_acc = p.acc + (size_t) blockIdx.x * GROUP * NVP;                             // this CTA's accumulators [GROUP][NVP], global memory, zero on entry
     uint2 *s_band = reinterpret_cast<uint2 *>(smem_raw + L.band_off);                   // [kStages] range of the group's word list inside the staged band
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
     unsigned long long *s_empty = s_full + kMaxStages;
@@ -349,10 +351,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             // candidates, 32 per round, and evaluates them.
             auto peel = [&](uint32_t c, uint4 e) {
                 const uint32_t wbits = e.x, lrec = e.z;
-                // offset of the tile's first pixel inside the staged band | (mask * 2 + orientation) << 15; a set bit adds
-                // (bit & 7) + (bit >> 3) * pitch
+                // offset of the tile's first pixel inside the staged band | index of the (mask, orientation)'s first accumulator << 15;
+                // a set bit adds (bit & 7) + (bit >> 3) * pitch
                 const uint32_t base = (uint32_t) (((int) (e.w & 255u) * 4 - y0 + S) * pitch) + (((e.w >> kWordMetaColShift) & 255u) << 3) +
-                                      ((((e.w >> kWordMetaMaskShift) << 1) | ((e.w >> kWordMetaOrientBit) & 1u)) << kCandOffsetBits);
+                                      (((e.w >> kWordMetaMaskShift) * (uint32_t) NVP + ((e.w >> kWordMetaOrientBit) & 1u) * (uint32_t) NS) << kCandOffsetBits);
                 // Load-balanced expansion: the batch's T candidate bits are numbered word by word (prefix sums of the popcounts),
                 // and in every round lane j takes candidate number j0 + j -- whichever word it belongs to -- so a round costs the
                 // same whether the bits sit in one dense tile or are spread over all 32.
@@ -536,16 +538,26 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
         __threadfence();                    // this thread's reductions are performed before anybody reads the accumulators
         consumer_barrier<NCT>();
         for (int mi = tid; mi < mb; mi += NCT) {
+            // a mask's counters as whole 16-byte words; most masks have no hit at all on most targets, and then nothing is written back
+            int4 *a4 = reinterpret_cast<int4 *>(s_acc + mi * NVP);
+            int a[NVP];
+#pragma unroll
+            for (int v = 0; v < NVP / 4; v++) {
+                const int4 q4 = __ldcg(a4 + v);
+                a[4 * v] = q4.x; a[4 * v + 1] = q4.y; a[4 * v + 2] = q4.z; a[4 * v + 3] = q4.w;
+            }
             int best = 0, bestm = 0;
 #pragma unroll
-            for (int v = 0; v < NS; v++) best = max(best, __ldcg(&s_acc[mi * NV + v]));
+            for (int v = 0; v < NS; v++) best = max(best, a[v]);
 #pragma unroll
-            for (int v = 0; v < NS; v++) bestm = max(bestm, __ldcg(&s_acc[mi * NV + NS + v]));
+            for (int v = 0; v < NS; v++) bestm = max(bestm, a[NS + v]);
             int word = best;
             if (bestm > best) word = bestm | CDS_SCORE_MIRROR_BIT;          // no mirrored words in the lists -> bestm stays 0
             p.scores[(size_t) (m0 + mi) * p.n_targets + t] = word;
+            if ((best | bestm) != 0) {
 #pragma unroll
-            for (int v = 0; v < NV; v++) __stcg(&s_acc[mi * NV + v], 0);
+                for (int v = 0; v < NVP / 4; v++) __stcg(a4 + v, make_int4(0, 0, 0, 0));
+            }
         }
         consumer_barrier<NCT>();
         iseq++;

@@ -60,7 +60,7 @@ struct MatchScratch {
     unsigned long long *work_counter = nullptr;
     int *acc = nullptr;                       // kMatchAccBytes, zero between launches
 };
-constexpr size_t kMatchAccBytes = (size_t) 256 * CDS_PALETTE_GROUP * CDS_MAX_VARIANTS * sizeof(int);   // [<= 256 CTAs][masks of a group][variants]
+constexpr size_t kMatchAccBytes = (size_t) 256 * CDS_PALETTE_GROUP * ((CDS_MAX_VARIANTS + 3) / 4 * 4) * sizeof(int);   // [<= 256 CTAs][masks of a group][variants, padded to 16 bytes]
 
 // score word written by the match kernels: matching pixels | mirrored << 30
 #define CDS_SCORE_MIRROR_BIT 0x40000000
