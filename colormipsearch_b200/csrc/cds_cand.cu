@@ -94,6 +94,16 @@ __device__ __forceinline__ void count_hit(const int *acc, uint32_t c, uint32_t l
     // __threadfence() and a named barrier (a volatile asm with a memory clobber), and volatile asms keep their order
 }
 
+// Published by the producer with every stage, so that 31 warps do not each work it out again: the band's part of the group's word list
+// and its part of the occupancy rows.
+struct __align__(16) BandInfo {
+    uint32_t first, end;            // entries [first, end) of the group's word list fall into the band's tile rows
+    uint32_t band_lo, band_hi;      // first / last occupancy word index of those tile rows
+    uint32_t j_first, n_tk;         // first ticket (of 32 entries) that touches the range, and how many do
+    uint32_t n_batches;             // batches of 32 tickets, a multiple of the number of consumer warps
+    uint32_t pad;
+};
+
 template <int GROUP>
 struct CandSmem {
     size_t stage_off, bits_off, pal_off, band_off, queue_off, wqueue_off, bar_off, next_off, item_off, sel_off, total;
@@ -106,9 +116,10 @@ struct CandSmem {
         wqueue_off = o; o += (size_t) n_warps * kWordQueue * 8;
         queue_off = o; o += (size_t) n_warps * kQueue * 8;
         bar_off = o;   o += 2 * kMaxStages * 8;
-        item_off = o;  o += 16;
+        item_off = o;  o += 32;                                                 // two published work items {target, group}
         next_off = o;  o += 16;
-        band_off = o;  o += (size_t) kMaxStages * 8;                               // per stage: {first, end} entry of the group's word list
+        o = (o + 15) & ~(size_t) 15;
+        band_off = o;  o += (size_t) kMaxStages * 32;                              // per stage: BandInfo
         sel_off = o;   o += 64;                                                 // position of the r-th set bit of a nibble
         (void) NS;
         total = o;
@@ -204,11 +215,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     uint2 *s_wqueue = reinterpret_cast<uint2 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] {candidate bits, entry index} of words with candidates
     constexpr int NVP = (NV + 3) / 4 * 4;             // a mask's accumulators padded to whole 16-byte words (the epilogue reads them as int4)
     int *s_acc = p.acc + (size_t) blockIdx.x * GROUP * NVP;                             // this CTA's accumulators [GROUP][NVP], global memory, zero on entry
-    uint2 *s_band = reinterpret_cast<uint2 *>(smem_raw + L.band_off);                   // [kStages] range of the group's word list inside the staged band
+    BandInfo *s_band = reinterpret_cast<BandInfo *>(smem_raw + L.band_off);             // [kMaxStages] what the consumers need to know about the staged band
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
     unsigned long long *s_empty = s_full + kMaxStages;
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
-    long long *s_item = reinterpret_cast<long long *>(smem_raw + L.item_off);           // [2] published work items
+    long long *s_item = reinterpret_cast<long long *>(smem_raw + L.item_off);           // [2][2] published work items: {target, group}; target -1 = no more work
     uint8_t *s_sel = smem_raw + L.sel_off;                                               // [16][4] r-th set bit of a nibble
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -259,8 +270,19 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     if (use > 0) mbar_wait(smem_u32(s_empty + stage), (use - 1) & 1);
                     if (trace && iseq < (uint32_t) kTraceItems) trace[(((size_t) iseq * kMaxBands + b) * 32 + 31) * 2] = clock64();
                     s_next[stage] = 0;
-                    s_band[stage] = range;
-                    if (b == 0) s_item[iseq & 1] = done ? -1 : w;
+                    {
+                        BandInfo bi;
+                        bi.first = range.x; bi.end = range.y;
+                        bi.band_lo = (uint32_t) ((y0 / 4) * rowpitch);
+                        bi.band_hi = (uint32_t) (((y1 + 3) / 4) * rowpitch) - 1u;
+                        bi.j_first = range.x >> 5;
+                        bi.n_tk = range.y > range.x ? ((range.y - 1u) >> 5) - bi.j_first + 1u : 0u;
+                        // a multiple of the number of consumer warps, so that every warp gets the same number of (partly filled) batches
+                        bi.n_batches = (uint32_t) NCW * ((bi.n_tk + 32u * NCW - 1u) / (32u * NCW));
+                        bi.pad = 0u;
+                        s_band[stage] = bi;
+                    }
+                    if (b == 0) { s_item[2 * (iseq & 1)] = done ? -1 : t; s_item[2 * (iseq & 1) + 1] = done ? 0 : w / p.n_targets; }
                     const uint32_t bar = smem_u32(s_full + stage);
                     if (done) { mbar_arrive(bar); break; }
                     const uint32_t bytes = (uint32_t) ((y1 - y0 + 2 * S) * pitch) * 4u;
@@ -302,10 +324,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     };
     for (;;) {
         wait_full();
-        const long long w = *reinterpret_cast<volatile long long *>(s_item + (iseq & 1));
-        if (w < 0) break;
-        const int gi = (int) (w / p.n_targets);
-        const int64_t t = w % p.n_targets;
+        const int64_t t = *reinterpret_cast<volatile long long *>(s_item + 2 * (iseq & 1));     // the producer did the 64-bit divisions
+        if (t < 0) break;
+        const int gi = (int) *reinterpret_cast<volatile long long *>(s_item + 2 * (iseq & 1) + 1);
         const int m0 = gi * GROUP;
         const int mb = min(GROUP, p.n_masks - m0);
 
@@ -325,9 +346,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             if (b > 0) wait_full();
             if (trace && iseq < (uint32_t) kTraceItems && lane == 0) trace[(((size_t) iseq * kMaxBands + b) * 32 + warp) * 2] = clock64();
             const uint32_t *band = s_stage + (size_t) stage * stage_stride;
-            const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - (size_t) (b * R / 4) * rowpitch;   // indexed by the entries' absolute occupancy word index
             const int y0 = b * R;
-            const uint2 range = s_band[stage];                                   // the group's word-list entries of this band
+            const volatile BandInfo *bi = s_band + stage;                      // read where needed: cheaper than six more live registers
+            const uint2 range = make_uint2(bi->first, bi->end);                 // the group's word-list entries of this band
 
             uint32_t qh = 0, qt = 0;            // candidate queue head / tail (free running, slot = index & (kQueue - 1))
             uint32_t wh = 0, wt = 0;            // word queue head / tail
@@ -421,14 +442,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             // one per lane -- is any occupancy word of the ticket's run set? -- and then scans only the tickets that passed.
             // Tickets are dealt out strided (lane i of batch b gets ticket b + i * n_batches): neighbouring tickets, which tend
             // to pass or fail together, go to different warps.
-            const uint32_t band_lo = (uint32_t) ((y0 / 4) * rowpitch);
-            const uint32_t band_hi = (uint32_t) (((min(y0 + R, H) + 3) / 4) * rowpitch) - 1u;
+            const uint32_t band_lo = bi->band_lo;
+            const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - band_lo;          // indexed by the entries' absolute occupancy word index
             const uint32_t sec_words = (uint32_t) (CDS_NUM_SECTORS * p.bpitch);
             const uint32_t nz_off = (uint32_t) ((CDS_NUM_SECTORS + 1) * p.bpitch);    // the non-empty bits of a tile row, behind its OR row
-            const uint32_t j_first = range.x >> 5;
-            const uint32_t n_tk = range.y > range.x ? ((range.y - 1u) >> 5) - j_first + 1u : 0u;
-            // a multiple of the number of consumer warps, so that every warp gets the same number of (partly filled) batches
-            const uint32_t n_batches = (uint32_t) NCW * ((n_tk + 32u * NCW - 1u) / (32u * NCW));
             const uint2 idle = make_uint2(0u, band_lo);
             auto scan_one = [&](uint2 w, uint32_t entry) {
                 const uint32_t c = w.x & bits_y0[w.y];                  // mask pixels of this word that can match
@@ -456,12 +473,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 uint32_t bt = 0;
                 if (lane == 0) bt = (uint32_t) atomicAdd(&s_next[stage], 1);
                 bt = __shfl_sync(0xffffffffu, bt, 0);
+                const uint32_t n_batches = bi->n_batches;
                 if (bt >= n_batches || p.debug_skip) break;
                 const uint32_t k = bt + (uint32_t) lane * n_batches;
-                const uint32_t jt = j_first + k;
+                const uint32_t jt = bi->j_first + k;
                 bool pass = false;
-                if (k < n_tk) {
+                if (k < bi->n_tk) {
                     // tickets cut by the band's ends take the band's bound (their neighbours belong to other tile rows)
+                    const uint32_t band_hi = bi->band_hi;
                     uint32_t o_lo = band_lo, o_hi = band_hi;
                     if ((jt << 5) >= range.x) o_lo = max(band_lo, HINT ? ldg_hint_u32(gtocc + jt, pol_keep) : __ldg(gtocc + jt));
                     if (((jt + 1u) << 5) < range.y) o_hi = min(band_hi, HINT ? ldg_hint_u32(gtocc + jt + 1u, pol_keep) : __ldg(gtocc + jt + 1u));
