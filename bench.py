@@ -471,16 +471,20 @@ def pair_provider_bench(ctx, masks_host, n_masks=64, n_targets=256, threads=40):
     pm = np.repeat(np.arange(n_masks, dtype=np.int32), n_targets)
     pt = np.tile(np.arange(n_targets, dtype=np.int64), n_masks)
     keys = np.arange(n_targets, dtype=np.uint64) + 1
-    q = capi.PairQueue(ctx, ms, max_batch=64, max_wait_us=60, cache_targets=max(512, 2 * n_targets))
+    q = capi.PairQueue(ctx, ms, max_batch=128, max_wait_us=60, cache_targets=max(512, 2 * n_targets))
     sc, mir, cold_s = q.drive(targets, keys, pm, pt, threads)
     st_cold = q.stats()
     sc2, mir2, warm_s = q.drive(targets, keys, pm, pt, threads)
     st = q.stats()
     ok = bool(np.array_equal(sc, dense[pm, pt]) and np.array_equal(sc2, dense[pm, pt]) and np.array_equal(mir2, dmir[pm, pt].astype(bool)))
+    # the same with twice the callers (the reference sizes its pool by the host: 2 x cores - 1 threads)
+    sc3, mir3, warm2_s = q.drive(targets, keys, pm, pt, 2 * threads)
+    ok = ok and bool(np.array_equal(sc3, dense[pm, pt]))
     q.close()
     ms.close()
     n = len(pm)
     return {"metric": "single-pair calls/sec through cds_pairq_score", "threads": threads, "masks": n_masks, "targets": n_targets, "pairs": n,
+            "warm_twice_the_threads": {"value": n / warm2_s, "unit": "pairs/s", "threads": 2 * threads},
             "cold": {"value": n / cold_s, "unit": "pairs/s", "uploads": st_cold["uploads"], "batches": st_cold["batches"]},
             "warm": {"value": n / warm_s, "unit": "pairs/s", "uploads": st["uploads"] - st_cold["uploads"], "batches": st["batches"] - st_cold["batches"],
                      "mean_batch": n / max(1, st["batches"] - st_cold["batches"])},

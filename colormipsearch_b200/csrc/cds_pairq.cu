@@ -21,6 +21,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
+#include <shared_mutex>
 #include <deque>
 #include <list>
 #include <thread>
@@ -49,6 +51,16 @@ __device__ __forceinline__ bool pair_code_matches(uint32_t c, uint32_t lo1, uint
 // pinned host memory the dispatcher reads after the stream has drained (no copy back), and the last CTA of a pair leaves the
 // pair's accumulators zero for the next launch (no memset): a batch is ONE launch and one synchronisation.
 constexpr int kPairsPerLaunch = 128;
+constexpr int32_t kScorePending = -1;     // a score word is a count below 2^24 plus the mirror bit: never all ones
+constexpr int kIdleSpinUs = 30;          // how long an idle dispatcher polls before it goes to sleep
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
 struct PairList {
     int32_t mask[kPairsPerLaunch];
     int32_t slot[kPairsPerLaunch];
@@ -131,6 +143,9 @@ inline void futex_wake_all(std::atomic<uint32_t> *addr)
 {
     syscall(SYS_futex, reinterpret_cast<uint32_t *>(addr), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
 }
+// (Measured and dropped: callers sleeping in eight groups, the dispatcher waking one sleeper per group and every woken thread waking the
+// rest of its group.  The callers then come back staggered, batches shrink from 40 to 34 requests, and 40 / 80 threads reach 414 k / 213 k
+// pairs/s instead of 515 k / 589 k with the one broadcast.)
 
 struct CacheSlot {
     uint64_t key = 0;
@@ -150,6 +165,8 @@ struct PairDev {
     std::list<int> lru;                  // least recently used first
     std::unordered_map<uint64_t, int> by_key;
     std::deque<PairRequest *> queue;
+    std::atomic<int> queued{0};          // queue.size(), readable without the mutex (the dispatcher polls it while it waits for company)
+    std::atomic<bool> disp_sleeping{false};     // the dispatcher sleeps on cv_work: only then does a push pay for a notify
     std::mutex mu;
     std::condition_variable cv_work, cv_slot;
     std::atomic<uint32_t> generation{0};  // batches completed: what callers sleep on
@@ -180,7 +197,7 @@ struct cds_pairq {
     // mask the queue has not seen quiesces the dispatchers, rebuilds the device descriptors and goes on
     std::atomic<int> n_masks{0};
     std::vector<int32_t> sizes;          // getQuerySize() of the masks the queue knows (a private copy: the mask set's vector may grow)
-    std::mutex refresh_mu;
+    std::shared_mutex refresh_mu;        // readers (every call) share it; a refresh takes it alone
 };
 
 namespace {
@@ -208,23 +225,38 @@ void dispatcher(cds_pairq *q, PairDev *pdp)
     for (;;) {
         batch.clear();
         {
-            std::unique_lock<std::mutex> lk(pd.mu);
-            pd.cv_work.wait(lk, [&] { return q->stop.load() || !pd.queue.empty(); });
-            if (pd.queue.empty() && q->stop.load()) return;
+            // Nothing queued: poll for a moment (the callers of the batch that has just been answered are on their way back), then
+            // sleep.  Polling reads one atomic counter and takes no lock, so it does not stand in the callers' way.
+            if (pd.queued.load(std::memory_order_acquire) == 0 && !q->stop.load()) {
+                const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(kIdleSpinUs);
+                while (pd.queued.load(std::memory_order_acquire) == 0 && !q->stop.load() && std::chrono::steady_clock::now() < spin_until) cpu_relax();
+            }
+            if (pd.queued.load(std::memory_order_acquire) == 0) {
+                std::unique_lock<std::mutex> lk(pd.mu);
+                pd.disp_sleeping.store(true, std::memory_order_seq_cst);
+                pd.cv_work.wait(lk, [&] { return q->stop.load() || !pd.queue.empty(); });
+                pd.disp_sleeping.store(false, std::memory_order_seq_cst);
+                if (pd.queue.empty() && q->stop.load()) return;
+            }
             // wait a little for company: a batch of one costs the same launch and round trip as a batch of sixty-four
             // (as many as came last time -- the callers are a pool of threads that come back together -- or the deadline)
             const int expect = std::min(q->max_batch, std::max(1, last_n));
-            if ((int) pd.queue.size() < expect && q->max_wait_us > 0) {
+            if (pd.queued.load(std::memory_order_acquire) < expect && q->max_wait_us > 0) {
                 const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(q->max_wait_us);
-                pd.cv_work.wait_until(lk, deadline, [&] { return q->stop.load() || (int) pd.queue.size() >= expect; });
+                while (pd.queued.load(std::memory_order_acquire) < expect && !q->stop.load() && std::chrono::steady_clock::now() < deadline) cpu_relax();
             }
+            std::unique_lock<std::mutex> lk(pd.mu);
             while (!pd.queue.empty() && (int) batch.size() < q->max_batch) { batch.push_back(pd.queue.front()); pd.queue.pop_front(); }
+            pd.queued.store((int) pd.queue.size(), std::memory_order_release);
             pd.busy = !batch.empty();
         }
         const int n = (int) batch.size();
         if (n == 0) continue;
         last_n = n;
         cudaError_t e = cudaSuccess;
+        // the kernel writes every pair's score word into mapped host memory: a word that no score can be marks "not yet"
+        volatile int32_t *hs = pd.h_scores;
+        for (int i = 0; i < n; i++) hs[i] = kScorePending;
         for (int i = 0; i < n; i++)
             if (batch[i]->ready && e == cudaSuccess) e = cudaStreamWaitEvent(pd.stream, batch[i]->ready, 0);
         for (int first = 0; first < n && e == cudaSuccess; first += kPairsPerLaunch) {
@@ -235,8 +267,24 @@ void dispatcher(cds_pairq *q, PairDev *pdp)
             launch_pair_gather(q, pd, pl, first, cnt, q->ms->d_descs[pd.d]);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(pd.stream);
-        if (e != cudaSuccess) cudaGetLastError();
+        if (e == cudaSuccess) {
+            // wait for the words themselves (a microsecond after the kernel's last store) rather than for the stream; every 200 us of
+            // waiting the stream is asked whether it failed
+            auto next_query = std::chrono::steady_clock::now() + std::chrono::microseconds(200);
+            for (int i = 0; i < n && e == cudaSuccess; i++) {
+                while (hs[i] == kScorePending) {
+                    cpu_relax();
+                    if (std::chrono::steady_clock::now() >= next_query) {
+                        const cudaError_t qe = cudaStreamQuery(pd.stream);
+                        if (qe == cudaSuccess) { if (hs[i] == kScorePending) e = cudaErrorUnknown; break; }     // finished without writing: cannot happen
+                        if (qe != cudaErrorNotReady) { e = qe; break; }
+                        next_query = std::chrono::steady_clock::now() + std::chrono::microseconds(200);
+                    }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        if (e != cudaSuccess) { cudaStreamSynchronize(pd.stream); cudaGetLastError(); }
         {
             std::lock_guard<std::mutex> lk(pd.mu);
             pd.batches++;
@@ -280,9 +328,15 @@ extern "C" cds_status cds_pairq_create(cds_ctx *ctx, const cds_maskset *ms, int3
         q->sizes = ms->sizes;
         q->n_masks.store((int) ms->sizes.size());
         const size_t img_bytes = (size_t) ms->W * ms->H * 3;
-        const int n_lanes = 8;
         const int nv_max = 2 * CDS_MAX_SHIFT_OFFSETS + 1;
-        for (size_t d = 0; d < ctx->devs.size() && st == CDS_OK; d++) {
+        // Several independent queues per device (targets are spread over them by key, each has its share of the cache, its stream and its
+        // dispatcher): a batch's turn-around is dominated by waking its callers and letting them back in, which costs ~1 us per caller ON
+        // TOP of ~35 us per batch, so four batches of ten in flight answer more calls per second than one batch of forty.
+        static const int queues_per_dev = std::max(1, std::min(16, std::getenv("CDSGPU_PAIRQ_QUEUES") ? std::atoi(std::getenv("CDSGPU_PAIRQ_QUEUES")) : 4));
+        const int n_lanes = std::max(2, 8 / queues_per_dev);
+        cache_targets = std::max(2 * max_batch, (cache_targets + queues_per_dev - 1) / queues_per_dev);
+        for (size_t dq = 0; dq < ctx->devs.size() * (size_t) queues_per_dev && st == CDS_OK; dq++) {
+            const size_t d = dq / (size_t) queues_per_dev;
             std::unique_ptr<PairDev> pd(new PairDev());
             pd->d = (int) d;
             st = ctx->check(cudaSetDevice(ctx->devs[d].dev), "cudaSetDevice");
@@ -348,7 +402,7 @@ extern "C" cds_status cds_pairq_score(cds_pairq *q, int32_t mask_index, uint64_t
         const cds_maskset *ms = q->ms;
         if (mask_index >= q->n_masks.load(std::memory_order_acquire) && mask_index >= 0) {
             // a mask added after the queue was created: stop the dispatchers between two batches, rebuild the descriptors, go on
-            std::lock_guard<std::mutex> rl(q->refresh_mu);
+            std::unique_lock<std::shared_mutex> rl(q->refresh_mu);
             if (mask_index >= q->n_masks.load()) {
                 std::lock_guard<std::recursive_mutex> cl(q->ctx->mu);
                 if (mask_index < (int) ms->sizes.size()) {
@@ -367,7 +421,7 @@ extern "C" cds_status cds_pairq_score(cds_pairq *q, int32_t mask_index, uint64_t
         if (mask_index < 0 || mask_index >= q->n_masks.load(std::memory_order_acquire)) { set_tls_error("cds_pairq_score: mask index out of range"); return CDS_ERR_BAD_ARG; }
         int P;
         {
-            std::lock_guard<std::mutex> rl(q->refresh_mu);     // short: guards the vector against a concurrent refresh
+            std::shared_lock<std::shared_mutex> rl(q->refresh_mu);     // short: guards the vector against a concurrent refresh
             P = q->sizes[mask_index];
         }
         if (P == 0) { *score_out = 0; *ratio_out = 0; *mirrored_out = 0; return CDS_OK; }   // PixelMatch...:169-170 (before the size check)
@@ -387,6 +441,7 @@ extern "C" cds_status cds_pairq_score(cds_pairq *q, int32_t mask_index, uint64_t
         PairRequest req;
         req.mask = mask_index;
         int lane = -1;
+        bool pushed = false;                 // a resident target: the request is queued inside the lookup's critical section
         {
             std::unique_lock<std::mutex> lk(pd.mu);
             auto it = anonymous ? pd.by_key.end() : pd.by_key.find(target_key);
@@ -419,9 +474,12 @@ extern "C" cds_status cds_pairq_score(cds_pairq *q, int32_t mask_index, uint64_t
             }
             CacheSlot &cs = pd.slots[req.slot];
             cs.refs++;
-            pd.lru.erase(cs.lru);
-            pd.lru.push_back(req.slot);
-            cs.lru = std::prev(pd.lru.end());
+            pd.lru.splice(pd.lru.end(), pd.lru, cs.lru);       // most recently used (the iterator stays valid)
+            if (lane < 0) {
+                pd.queue.push_back(&req);
+                pd.queued.store((int) pd.queue.size(), std::memory_order_release);
+                pushed = true;
+            }
         }
         cds_status st = CDS_OK;
         if (lane >= 0) {
@@ -456,11 +514,12 @@ extern "C" cds_status cds_pairq_score(cds_pairq *q, int32_t mask_index, uint64_t
             pd.cv_slot.notify_all();
         }
         if (st != CDS_OK) return st;
-        {
+        if (!pushed) {
             std::lock_guard<std::mutex> lk(pd.mu);
             pd.queue.push_back(&req);
+            pd.queued.store((int) pd.queue.size(), std::memory_order_release);
         }
-        pd.cv_work.notify_one();
+        if (pd.disp_sleeping.load(std::memory_order_seq_cst)) pd.cv_work.notify_one();
         for (;;) {
             const uint32_t g = pd.generation.load(std::memory_order_acquire);
             if (req.done.load(std::memory_order_acquire)) break;
