@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <cctype>
 
@@ -771,13 +772,22 @@ static cds_status maskset_append_body(cds_maskset *ms, int32_t n, int32_t *mask_
         CDS_CUDA(ctx, cudaEventRecord(d0.up_done[slot], up_stream));
         return CDS_OK;
     };
+    // profiling aid (CDSGPU_MASK_TRACE=1): the host's clock at every step of the append, printed to stderr
+    static const bool trace = std::getenv("CDSGPU_MASK_TRACE") != nullptr;
+    const auto t_trace0 = std::chrono::steady_clock::now();
+    auto tmark = [&](const char *what, int i0) {
+        if (trace) std::fprintf(stderr, "# maskset_append %-28s chunk@%-5d %8.3f ms\n", what, i0, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_trace0).count());
+    };
     CDS_CUDA(ctx, cudaStreamSynchronize(d0.stream));        // earlier users of the staging buffer are done
+    tmark("start", 0);
     CDS_TRY(enqueue_upload(0));
+    tmark("first upload enqueued", 0);
     for (int i0 = 0; i0 < n; i0 += kChunk) {
         const int cnt = std::min(kChunk, n - i0);
         const int slot = (i0 / kChunk) & 1;
         uint8_t *stage = (uint8_t *) d0.staging + (size_t) slot * kChunk * img_bytes;
         if (i0 + kChunk < n) CDS_TRY(enqueue_upload(i0 + kChunk));
+        tmark("next upload enqueued", i0);
         CDS_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d0.up_done[slot], 0));
         uint32_t *rowstart = (uint32_t *) ((uint8_t *) s0.rowstart.p + s0.rowstart.used);
         launch_mask_count_rows(stage, cnt, ms->W, H, ms->params.mask_threshold, ms->rects, rowstart, d0.stream);
@@ -786,6 +796,7 @@ static cds_status maskset_append_body(cds_maskset *ms, int32_t n, int32_t *mask_
         std::vector<int32_t> sizes(cnt);
         CDS_CUDA(ctx, cudaMemcpyAsync(sizes.data(), d_sizes, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d0.stream));
         CDS_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+        tmark("sizes on the host", i0);
         std::vector<uint64_t> off(cnt);
         uint64_t total = 0;
         const uint64_t base = s0.records.used / sizeof(cds_mask_record);      // records, classes and crec advance in lock step
@@ -813,7 +824,9 @@ static cds_status maskset_append_body(cds_maskset *ms, int32_t n, int32_t *mask_
             if (mask_size_out) mask_size_out[i0 + i] = sizes[i];
         }
     }
+    tmark("all chunks enqueued", n);
     CDS_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+    tmark("records written", n);
     // replicate the new parts on the other devices
     for (int d = 1; d < D; d++) {
         DevState &dd = ctx->devs[d];
