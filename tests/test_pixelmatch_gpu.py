@@ -298,7 +298,7 @@ def test_generated_library_equals_uploaded_library(ctx):
         x.close()
 
 
-@pytest.mark.parametrize("shape", [(100, 50), (100, 300), (37, 23), (640, 480)])
+@pytest.mark.parametrize("shape", [(100, 50), (100, 300), (37, 23), (640, 480), (2048, 36), (257, 1024)])
 def test_small_and_odd_image_sizes(ctx, shape):
     w, h = shape
     rng = np.random.default_rng(w * 1000 + h)
