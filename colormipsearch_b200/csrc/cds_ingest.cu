@@ -607,15 +607,50 @@ extern "C" cds_status cds_maskset_add_tiff(cds_maskset *ms, const uint8_t *blob,
         for (int64_t i = 0; i < n; i++) comp_cap = std::max(comp_cap, (size_t) std::max<int64_t>(offsets[std::min<int64_t>(n, i + chunk)] - offsets[i], 0) + 64);
         DevState &d0 = ctx->devs[0];
         CDS_CUDA(ctx, cudaSetDevice(d0.dev));
-        uint8_t *d_comp = nullptr;
-        TiffStrip *d_strips = nullptr;
-        auto release = [&]() { cudaStreamSynchronize(d0.copy_stream); cudaStreamSynchronize(d0.stream); d0.pool.free(d_comp); d0.pool.free(d_strips); };
+        // Two sets of upload buffers and a stream of their own for the copies: the files of chunk i + 1 cross PCIe while chunk i is
+        // being decoded (maskset_append asks for the chunks in order, one ahead of the preparation kernels).
+        uint8_t *d_comp[2] = {nullptr, nullptr};
+        TiffStrip *d_strips[2] = {nullptr, nullptr};
+        cudaStream_t h2d = nullptr;
+        cudaEvent_t up[2] = {nullptr, nullptr}, decoded[2] = {nullptr, nullptr};
+        auto release = [&]() {
+            if (h2d) cudaStreamSynchronize(h2d);
+            cudaStreamSynchronize(d0.copy_stream); cudaStreamSynchronize(d0.stream);
+            for (int i = 0; i < 2; i++) {
+                d0.pool.free(d_comp[i]); d0.pool.free(d_strips[i]);
+                if (up[i]) cudaEventDestroy(up[i]);
+                if (decoded[i]) cudaEventDestroy(decoded[i]);
+            }
+            if (h2d) cudaStreamDestroy(h2d);
+        };
         struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
-        CDS_CUDA(ctx, d0.pool.alloc((void **) &d_comp, comp_cap));
-        CDS_CUDA(ctx, d0.pool.alloc((void **) &d_strips, strips_cap * sizeof(TiffStrip)));
+        CDS_CUDA(ctx, cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CDS_CUDA(ctx, d0.pool.alloc((void **) &d_comp[i], comp_cap));
+            CDS_CUDA(ctx, d0.pool.alloc((void **) &d_strips[i], strips_cap * sizeof(TiffStrip)));
+            CDS_CUDA(ctx, cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming));
+            CDS_CUDA(ctx, cudaEventCreateWithFlags(&decoded[i], cudaEventDisableTiming));
+        }
         std::vector<TiffStrip> strips;
+        int64_t calls = 0;
         return maskset_append(ms, n, mask_size_out, [&](int i0, int cnt, uint8_t *stage, cudaStream_t stream) -> cds_status {
-            return ingest_chunk(ctx, "cds_maskset_add_tiff", blob, offsets, i0, cnt, W, H, d_comp, comp_cap, d_strips, strips_cap, stage, stream, strips);
+            const int slot = (int) (calls & 1);
+            CDS_TRY(collect_chunk(ctx, "cds_maskset_add_tiff", blob, offsets, i0, cnt, W, H, strips));
+            const size_t bytes = (size_t) (offsets[i0 + cnt] - offsets[i0]);
+            if (bytes > comp_cap || strips.size() > strips_cap) return ctx->fail(CDS_ERR_CAPACITY, "cds_maskset_add_tiff: internal staging too small");
+            if (calls >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(h2d, decoded[slot], 0));       // the slot's previous files have been decoded
+            CDS_CUDA(ctx, cudaMemcpyAsync(d_comp[slot], blob + offsets[i0], bytes, cudaMemcpyHostToDevice, h2d));
+            // (the table is pageable host memory: the runtime stages it before the call returns, so `strips` may be reused)
+            CDS_CUDA(ctx, cudaMemcpyAsync(d_strips[slot], strips.data(), strips.size() * sizeof(TiffStrip), cudaMemcpyHostToDevice, h2d));
+            CDS_CUDA(ctx, cudaEventRecord(up[slot], h2d));
+            ctx->stats.h2d_bytes += (int64_t) bytes + (int64_t) (strips.size() * sizeof(TiffStrip));
+            CDS_CUDA(ctx, cudaStreamWaitEvent(stream, up[slot], 0));
+            launch_tiff_decode(d_comp[slot], d_strips[slot], (int64_t) strips.size(), stage, stream);
+            ctx->stats.kernel_launches++;
+            CDS_CUDA(ctx, cudaGetLastError());
+            CDS_CUDA(ctx, cudaEventRecord(decoded[slot], stream));
+            calls++;
+            return CDS_OK;
         });
     });
 }
