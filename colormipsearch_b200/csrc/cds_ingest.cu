@@ -184,15 +184,13 @@ __device__ __forceinline__ uint32_t fuse_encode(int r, int g, int b, const uint1
 constexpr int kFuseWarps = 8;
 constexpr int kFuseQueue = 64;
 
-__global__ void __launch_bounds__(kFuseWarps * 32)
-tiff_encode_kernel(const uint8_t *__restrict__ src, const TiffStrip *__restrict__ strips, int64_t n_strips, uint32_t *__restrict__ planes,
-                   PlaneGeom g, int64_t first_slot, const uint16_t *__restrict__ rank_tab, int thr, int vp,
-                   uint32_t *__restrict__ valid /* chunk-relative [n][H][sectors][vp], or nullptr */, int row_buf_bytes)
+// One strip, by one warp (below: warps fetch strips from a counter until none is left -- strips differ a lot in cost, and a CTA of eight
+// warps that each took exactly one strip kept its registers and shared memory until its slowest warp was done: 34 % achieved occupancy).
+__device__ __forceinline__ void tiff_encode_strip(const int64_t w, const uint32_t lane, const uint32_t warp, uint4 *s_fuse4,
+                                                  const uint8_t *__restrict__ src, const TiffStrip *__restrict__ strips, uint32_t *__restrict__ planes,
+                                                  const PlaneGeom &g, int64_t first_slot, const uint16_t *__restrict__ rank_tab, int thr, int vp,
+                                                  uint32_t *__restrict__ valid, int row_buf_bytes)
 {
-    extern __shared__ uint4 s_fuse4[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t w = (int64_t) blockIdx.x * kFuseWarps + warp;
-    if (w >= n_strips) return;
     const int valid_words = CDS_NUM_SECTORS * vp;
     const int per_warp = row_buf_bytes + valid_words * 4 + kFuseQueue * 4;           // multiples of 16
     uint8_t *rowbuf = reinterpret_cast<uint8_t *>(s_fuse4) + (size_t) warp * per_warp;
@@ -439,10 +437,28 @@ tiff_encode_kernel(const uint8_t *__restrict__ src, const TiffStrip *__restrict_
     }
 }
 
+__global__ void __launch_bounds__(kFuseWarps * 32)
+tiff_encode_kernel(const uint8_t *__restrict__ src, const TiffStrip *__restrict__ strips, int64_t n_strips, uint32_t *__restrict__ planes,
+                   PlaneGeom g, int64_t first_slot, const uint16_t *__restrict__ rank_tab, int thr, int vp,
+                   uint32_t *__restrict__ valid /* chunk-relative [n][H][sectors][vp], or nullptr */, int row_buf_bytes,
+                   unsigned long long *__restrict__ next_strip /* zero on entry */)
+{
+    extern __shared__ uint4 s_fuse4[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(next_strip, 1ull);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= (unsigned long long) n_strips) return;
+        tiff_encode_strip((int64_t) w, lane, warp, s_fuse4, src, strips, planes, g, first_slot, rank_tab, thr, vp, valid, row_buf_bytes);
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 void cds::launch_tiff_encode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint32_t *planes, PlaneGeom g, int64_t first_slot,
-                             const uint16_t *rank_tab, int data_threshold, uint32_t *valid, cudaStream_t s)
+                             const uint16_t *rank_tab, int data_threshold, uint32_t *valid, unsigned long long *work_counter, cudaStream_t s)
 {
     if (n_strips <= 0) return;
     const int vp = occupancy_valid_pitch(g.W);
@@ -450,8 +466,19 @@ void cds::launch_tiff_encode(const uint8_t *src, const TiffStrip *strips, int64_
     const size_t smem = (size_t) kFuseWarps * (row_buf + CDS_NUM_SECTORS * vp * 4 + kFuseQueue * 4);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(tiff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-    const int64_t blocks = (n_strips + kFuseWarps - 1) / kFuseWarps;
-    tiff_encode_kernel<<<(unsigned) blocks, kFuseWarps * 32, smem, s>>>(src, strips, n_strips, planes, g, first_slot, rank_tab, data_threshold, vp, valid, row_buf);
+    // a persistent grid: as many CTAs as fit the device at once, every warp takes strips until the counter runs out
+    static int resident_blocks = 0;
+    if (resident_blocks == 0) {
+        int per_sm = 0, dev = 0, n_sm = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiff_encode_kernel, kFuseWarps * 32, smem);
+        resident_blocks = std::max(1, per_sm) * n_sm;
+    }
+    const int64_t blocks = std::min<int64_t>((n_strips + kFuseWarps - 1) / kFuseWarps, resident_blocks);
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
+    tiff_encode_kernel<<<(unsigned) blocks, kFuseWarps * 32, smem, s>>>(src, strips, n_strips, planes, g, first_slot, rank_tab, data_threshold, vp, valid, row_buf,
+                                                                        work_counter);
 }
 
 void cds::launch_tiff_decode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint8_t *dst_rgb, cudaStream_t s)
@@ -677,7 +704,8 @@ extern "C" cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, co
         uint8_t *d_comp = nullptr, *d_rgb = nullptr;
         TiffStrip *d_strips = nullptr;
         uint32_t *d_planes = nullptr, *d_valid = nullptr;
-        auto release = [&]() { cudaStreamSynchronize(ds.stream); for (void *p : {(void *) d_comp, (void *) d_rgb, (void *) d_strips, (void *) d_planes, (void *) d_valid}) ds.pool.free(p); };
+        unsigned long long *d_counter = nullptr;
+        auto release = [&]() { cudaStreamSynchronize(ds.stream); for (void *p : {(void *) d_comp, (void *) d_rgb, (void *) d_strips, (void *) d_planes, (void *) d_valid, (void *) d_counter}) ds.pool.free(p); };
         struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{release};
         std::vector<TiffStrip> strips;
         std::string err;
@@ -694,11 +722,12 @@ extern "C" cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, co
         CDS_CUDA(ctx, ds.pool.alloc((void **) &d_planes, g.total_words(n) * sizeof(uint32_t)));
         CDS_CUDA(ctx, ds.pool.alloc((void **) &d_valid, (size_t) n * valid_words * sizeof(uint32_t)));
         if (!fused) CDS_CUDA(ctx, ds.pool.alloc((void **) &d_rgb, (size_t) n * img_bytes + 64));
+        CDS_CUDA(ctx, ds.pool.alloc((void **) &d_counter, 64));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_comp, blob + offsets[0], comp_bytes, cudaMemcpyHostToDevice, ds.stream));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_strips, strips.data(), strips.size() * sizeof(TiffStrip), cudaMemcpyHostToDevice, ds.stream));
         launch_fill_words(d_planes, g.total_words(n), CDS_CODE_PAD_WORD, ds.stream);
         if (fused) {
-            launch_tiff_encode(d_comp, d_strips, (int64_t) strips.size(), d_planes, g, 0, ds.d_rank_tab, data_threshold, d_valid, ds.stream);
+            launch_tiff_encode(d_comp, d_strips, (int64_t) strips.size(), d_planes, g, 0, ds.d_rank_tab, data_threshold, d_valid, d_counter, ds.stream);
         } else {
             CDS_CUDA(ctx, cudaMemsetAsync(d_rgb, 0, (size_t) n * img_bytes, ds.stream));
             launch_tiff_decode(d_comp, d_strips, (int64_t) strips.size(), d_rgb, ds.stream);

@@ -29,6 +29,7 @@ struct StreamBufs {
     int64_t m_cap = 0, key_cap = 0;     // masks / (masks * k) the score and key buffers are sized for
     cudaStream_t copy_stream = nullptr;
     size_t staging_cap[2] = {0, 0};
+    unsigned long long *strip_counter = nullptr;   // the fused ingest kernel's work counter
     uint8_t *staging[2] = {nullptr, nullptr};   // RGB chunks as uploaded (double buffered: the next upload overlaps this chunk's kernels)
     uint32_t *planes = nullptr, *occ = nullptr, *valid = nullptr;
     int32_t *scores = nullptr;          // [masks][chunk]

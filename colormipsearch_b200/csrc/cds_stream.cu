@@ -32,8 +32,9 @@ void cds::StreamBufs::release()
         if (enc_done[i]) cudaEventDestroy(enc_done[i]);
         staging[i] = nullptr; h2d_done[i] = nullptr; enc_done[i] = nullptr;
     }
-    void *bufs[] = {planes, occ, valid, scores, keys_chunk, keys_run, counts_chunk, counts_run, min_score};
+    void *bufs[] = {planes, occ, valid, scores, keys_chunk, keys_run, counts_chunk, counts_run, min_score, strip_counter};
     for (void *b : bufs) if (b) cudaFree(b);
+    strip_counter = nullptr;
     planes = occ = valid = nullptr; scores = nullptr; keys_chunk = keys_run = nullptr;
     counts_chunk = counts_run = min_score = nullptr;
     for (int i = 0; i < 2; i++) {
@@ -129,8 +130,9 @@ cds_status ensure_stream_bufs(cds_ctx *ctx, DevState &ds, const PlaneGeom &g, in
 cds_status ensure_tiff_bufs(cds_ctx *ctx, DevState &ds, size_t comp_bytes, size_t n_strips)
 {
     StreamBufs &sb = ds.sb;
-    if (sb.comp_cap >= comp_bytes && sb.strips_cap >= n_strips) return CDS_OK;
     CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+    if (!sb.strip_counter) CDS_CUDA(ctx, cudaMalloc(&sb.strip_counter, 64));
+    if (sb.comp_cap >= comp_bytes && sb.strips_cap >= n_strips) return CDS_OK;
     CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
     CDS_CUDA(ctx, cudaStreamSynchronize(sb.copy_stream));
     if (sb.comp_cap < comp_bytes) {
@@ -380,7 +382,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             if (fused_ingest) {
                 // strips -> code words + per-sector valid bits in one kernel, no RGB image in HBM in between
                 launch_tiff_encode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.planes, g, 0, ds.d_rank_tab, thr,
-                                   want_occ ? sb.valid : nullptr, ds.stream);
+                                   want_occ ? sb.valid : nullptr, sb.strip_counter, ds.stream);
                 ctx->stats.kernel_launches += 1;
             } else {
                 // decode into one RGB area (stream order protects it), then the usual encoder

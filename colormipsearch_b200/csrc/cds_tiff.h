@@ -62,8 +62,9 @@ void launch_tiff_decode(const uint8_t *src, const TiffStrip *strips, int64_t n_s
 // Fused ingest (cds_ingest.cu): the same strips straight to code words (planes, slot first_slot + image) and, when `valid` is
 // given, the per-sector "can match" bits of every row (launch_occupancy with valid_ready).  Needs a strip table whose stored
 // pieces are whole rows (tiff_collect_strips with whole_rows = true); every row of every image must be covered by a strip.
+// `work_counter`: 8 bytes of device memory for the kernel's strip counter (cleared on the stream by the launcher)
 void launch_tiff_encode(const uint8_t *src, const TiffStrip *strips, int64_t n_strips, uint32_t *planes, PlaneGeom g, int64_t first_slot,
-                        const uint16_t *rank_tab, int data_threshold, uint32_t *valid, cudaStream_t s);
+                        const uint16_t *rank_tab, int data_threshold, uint32_t *valid, unsigned long long *work_counter, cudaStream_t s);
 
 }  // namespace cds
 #endif
