@@ -35,7 +35,7 @@ constexpr int kMaxStages = 4;     // band stages of the pipeline: CandParams::n_
 constexpr int kMaxBands = 256;
 constexpr int kPrePad = 4;          // words (16 bytes, keeps the bulk-copy destination aligned)
 constexpr int kQueue = 64;          // candidate slots per warp (power of two, >= 2 * 32)
-constexpr int kWordQueue = 64;      // word slots per warp (power of two, >= 2 * 32)
+constexpr int kWordQueue = 32;      // word slots per warp: one batch (16 bytes each: candidate bits and what the expansion needs of the entry)
 constexpr int kCandOffsetBits = 15; // a staged band has fewer than 2^15 words (227 kB of shared memory hold 2 of them)
 constexpr uint32_t kCandOffsetMask = (1u << kCandOffsetBits) - 1u;
 
@@ -113,7 +113,7 @@ struct CandSmem {
         stage_off = o; o += (size_t) n_stages * (stage_words + kPrePad) * 4;
         bits_off = o;  o += (size_t) n_stages * bits_words * 4;
         pal_off = o;   o += (size_t) CDS_PALETTE_SIZE * 8;
-        wqueue_off = o; o += (size_t) n_warps * kWordQueue * 8;
+        wqueue_off = o; o += (size_t) n_warps * kWordQueue * 16;
         queue_off = o; o += (size_t) n_warps * kQueue * 8;
         bar_off = o;   o += 2 * kMaxStages * 8;
         item_off = o;  o += 32;                                                 // two published work items {target, group}
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const uint32_t *s_bits = reinterpret_cast<const uint32_t *>(smem_raw + L.bits_off);  // [kStages][R * bpitch]
     uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
     uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + L.queue_off);                  // [NCW][kQueue] candidates
-    uint2 *s_wqueue = reinterpret_cast<uint2 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] {candidate bits, entry index} of words with candidates
+    uint4 *s_wqueue = reinterpret_cast<uint4 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] {candidate bits, the word's bits, lrec, meta} of words with candidates
     constexpr int NVP = (NV + 3) / 4 * 4;             // a mask's accumulators padded to whole 16-byte words (the epilogue reads them as int4)
     int *s_acc = p.acc + (size_t) blockIdx.x * GROUP * NVP;                             // this CTA's accumulators [GROUP][NVP], global memory, zero on entry
     BandInfo *s_band = reinterpret_cast<BandInfo *>(smem_raw + L.band_off);             // [kMaxStages] what the consumers need to know about the staged band
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const uint16_t *glpal = nullptr;                 // palette references of its entries' set bits
     const uint32_t *gtocc = nullptr;                 // occupancy word of the first entry of every ticket of 32 entries
     uint2 *myq = s_queue + warp * kQueue;
-    uint2 *mywq = s_wqueue + warp * kWordQueue;
+    uint4 *mywq = s_wqueue + warp * kWordQueue;
     const uint32_t mywq_addr = smem_u32(mywq);
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int *acc_base = s_acc;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const uint2 range = make_uint2(bi->first, bi->end);                 // the group's word-list entries of this band
 
             uint32_t qh = 0, qt = 0;            // candidate queue head / tail (free running, slot = index & (kQueue - 1))
-            uint32_t wh = 0, wt = 0;            // word queue head / tail
+            uint32_t wcnt = 0;                  // words in the word queue
             // Both queues live for the whole band: words and candidates of different masks mix freely (they carry the mask's
             // index), so only the LAST batch of a band runs on a partly filled warp.
 
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             };
             // Turns the candidate bits `c` of 32 queued words (one word per lane, `e` its list entry; c = 0 for idle lanes) into
             // candidates, 32 per round, and evaluates them.
-            auto peel = [&](uint32_t c, uint4 e) {
+            auto peel = [&](uint32_t c, uint4 e) {          // e = {bits, -, lrec, meta} of the word's list entry
                 const uint32_t wbits = e.x, lrec = e.z;
                 // offset of the tile's first pixel inside the staged band | index of the (mask, orientation)'s first accumulator << 15;
                 // a set bit adds (bit & 7) + (bit >> 3) * pitch
@@ -423,16 +423,15 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                     }
                 }
             };
-            // A full batch of words with candidates: re-read their list entries (the scan only carried bits and position), peel
-            // the batch whose entries were requested one batch earlier.
-            uint32_t wpend_c = 0;
-            uint4 wpend_e = make_uint4(0u, 0u, 0u, 0u);
-            bool wpend = false;
-            auto submit_words = [&](uint2 qe, bool live) {
+            // The queued words (at most 32, one per lane) are expanded and evaluated.  The queue holds everything the expansion needs
+            // of a word's entry, so nothing is read again (round 1 queued {bits, entry index} and re-read the entries a batch later).
+            auto drain_words = [&]() {
+                __syncwarp();
                 uint4 e = make_uint4(0u, 0u, 0u, 0u);
-                if (live) e = HINT ? ldg_hint_v4(gwords + qe.y, pol_keep) : __ldg(gwords + qe.y);
-                if (wpend) peel(wpend_c, wpend_e);
-                wpend_c = live ? qe.x : 0u; wpend_e = e; wpend = true;
+                if (lane < (int) wcnt) e = mywq[lane];
+                wcnt = 0;
+                __syncwarp();                                           // the slots may be written again
+                peel(e.x, make_uint4(e.y, 0u, e.z, e.w));
             };
 
             // Tickets.  Inside a tile row the entries are ordered by occupancy word (sector, tile column), so the 32 entries of
@@ -446,27 +445,24 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             const uint32_t *bits_y0 = s_bits + (size_t) stage * bits_words - band_lo;          // indexed by the entries' absolute occupancy word index
             const uint32_t sec_words = (uint32_t) (CDS_NUM_SECTORS * p.bpitch);
             const uint32_t nz_off = (uint32_t) ((CDS_NUM_SECTORS + 1) * p.bpitch);    // the non-empty bits of a tile row, behind its OR row
-            const uint2 idle = make_uint2(0u, band_lo);
-            auto scan_one = [&](uint2 w, uint32_t entry) {
+            const uint4 idle = make_uint4(0u, band_lo, 0u, 0u);
+            auto scan_one = [&](uint4 w) {
                 const uint32_t c = w.x & bits_y0[w.y];                  // mask pixels of this word that can match
-                // words with candidates are compacted first, so that the bit expansion runs on full warps
+                // words with candidates are compacted first, so that the bit expansion runs on (nearly) full warps: when the new ones
+                // do not fit behind the queued ones, those are expanded first
                 const unsigned has = __ballot_sync(0xffffffffu, c != 0);
+                const uint32_t n_new = (uint32_t) __popc(has);
+                if (wcnt + n_new > (uint32_t) kWordQueue) drain_words();
                 if (c) {
-                    const uint32_t slot = (wt + (uint32_t) __popc(has & lt_mask)) & (kWordQueue - 1);
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(mywq_addr + slot * 8u), "r"(c), "r"(entry) : "memory");
+                    const uint32_t slot = wcnt + (uint32_t) __popc(has & lt_mask);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mywq_addr + slot * 16u), "r"(c), "r"(w.x), "r"(w.z), "r"(w.w) : "memory");
                 }
-                wt += (uint32_t) __popc(has);
-                if (wt - wh >= 32) {
-                    __syncwarp();
-                    const uint2 qe = mywq[(wh + lane) & (kWordQueue - 1)];
-                    wh += 32;
-                    submit_words(qe, true);
-                }
+                wcnt += n_new;
             };
-            auto load = [&](uint32_t jt) -> uint2 {                     // this lane's entry of ticket jt: {bits, occupancy word index}
+            auto load = [&](uint32_t jt) -> uint4 {                     // this lane's entry of ticket jt
                 const uint32_t i = (jt << 5) + (uint32_t) lane;
-                uint2 w = idle;
-                if (i >= range.x && i < range.y) w = HINT ? ldg_hint_v2(gwords + i, pol_keep) : __ldg(reinterpret_cast<const uint2 *>(gwords + i));
+                uint4 w = idle;
+                if (i >= range.x && i < range.y) w = HINT ? ldg_hint_v4(gwords + i, pol_keep) : __ldg(gwords + i);
                 return w;
             };
             for (;;) {
@@ -514,10 +510,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 int src = __ffs((int) live) - 1;
                 live &= live - 1;
                 uint32_t jc = __shfl_sync(0xffffffffu, jt, src);
-                uint2 wn = load(jc);
+                uint4 wn = load(jc);
                 for (;;) {
-                    const uint2 w = wn;
-                    const uint32_t entry = (jc << 5) + (uint32_t) lane;
+                    const uint4 w = wn;
                     const bool more = live != 0;
                     if (more) {
                         src = __ffs((int) live) - 1;
@@ -525,19 +520,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                         jc = __shfl_sync(0xffffffffu, jt, src);
                         wn = load(jc);
                     }
-                    scan_one(w, entry);
+                    scan_one(w);
                     if (!more) break;
                 }
             }
             // the band's last, partly filled batches: everything queued reads this stage, so it is evaluated before the release
-            if (wt != wh) {
-                __syncwarp();
-                const bool live = lane < (int) (wt - wh);
-                uint2 qe = make_uint2(0u, 0u);
-                if (live) qe = mywq[(wh + lane) & (kWordQueue - 1)];
-                submit_words(qe, live);
-            }
-            if (wpend) peel(wpend_c, wpend_e);
+            if (wcnt) drain_words();
             if (qt != qh) {
                 __syncwarp();
                 const bool live = lane < (int) (qt - qh);

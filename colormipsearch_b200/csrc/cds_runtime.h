@@ -2,6 +2,7 @@
 #ifndef CDS_RUNTIME_H
 #define CDS_RUNTIME_H
 
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <functional>
@@ -213,7 +214,12 @@ cds_status library_append(cds_library *lib, int64_t n,
                           const std::function<cds_status(DevState &, int64_t i0, int64_t cnt, uint8_t *d_rgb)> &src,
                           int64_t *first_index);
 // masks per chunk of maskset_append (and therefore the most consecutive files a TIFF source has to stage at once)
-inline int maskset_append_chunk(int n) { return n <= 64 ? 64 : 256; }
+inline int maskset_append_chunk(int n)
+{
+    static const int forced = std::getenv("CDSGPU_MASK_CHUNK") ? std::atoi(std::getenv("CDSGPU_MASK_CHUNK")) : 0;      // tuning aid
+    if (forced > 0) return forced;
+    return n <= 64 ? 64 : 256;
+}
 // Appends n masks whose pixels `fill` puts into device staging memory (cds_api.cu).
 cds_status maskset_append(cds_maskset *ms, int32_t n, int32_t *mask_size_out,
                           const std::function<cds_status(int i0, int cnt, uint8_t *stage, cudaStream_t stream)> &fill);
