@@ -26,7 +26,7 @@ INNER_MARKS = [("__device__ __forceinline__ void count_hit", "evaluation"), ("st
                ("__device__ __forceinline__ void eval_candidates", "evaluation"), ("__global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel", None)]
 OUTER_MARKS = [("pixelmatch_cand_kernel(const CandParams p)", "kernel prologue / misc"), ("if (warp == NCW) {", "producer"), ("// ---------------------------------------------------------------------- consumers", "kernel prologue / misc"),
                ("auto wait_full = ", "wait for band (call site)"), ("    for (;;) {\n        wait_full();", "item / band setup"), ("auto run_pending = ", "submit"),
-               ("auto peel = ", "expansion: peel"), ("uint32_t wpend_c = 0;", "submit_words"), ("// Tickets.  Inside a tile row", "item / band setup"),
+               ("auto peel = ", "expansion: peel"), ("auto drain_words = ", "drain of the word queue"), ("// Tickets.  Inside a tile row", "item / band setup"),
                ("auto scan_one = ", "scan of passing tickets"), ("uint32_t bt = 0;", "ticket test"), ("// scan the tickets that passed", "scan of passing tickets"),
                ("// the band's last, partly filled batches", "band flush + release"), ("// item epilogue", "item epilogue"), ("struct CandConfig", None)]
 def mark_lines(marks):
