@@ -510,17 +510,27 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
                 int src = __ffs((int) live) - 1;
                 live &= live - 1;
                 uint32_t jc = __shfl_sync(0xffffffffu, jt, src);
-                uint4 wn = load(jc);
+                // (two tickets per trip, in two sets of registers: a single set would need the requested entries MOVED into the scanned
+                // ones, and a move waits for the load -- the request would hide nothing)
+                uint4 wa = load(jc), wb = idle;
                 for (;;) {
-                    const uint4 w = wn;
-                    const bool more = live != 0;
+                    bool more = live != 0;
                     if (more) {
                         src = __ffs((int) live) - 1;
                         live &= live - 1;
                         jc = __shfl_sync(0xffffffffu, jt, src);
-                        wn = load(jc);
+                        wb = load(jc);
                     }
-                    scan_one(w);
+                    scan_one(wa);
+                    if (!more) break;
+                    more = live != 0;
+                    if (more) {
+                        src = __ffs((int) live) - 1;
+                        live &= live - 1;
+                        jc = __shfl_sync(0xffffffffu, jt, src);
+                        wa = load(jc);
+                    }
+                    scan_one(wb);
                     if (!more) break;
                 }
             }
