@@ -333,6 +333,11 @@ extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t
             ctx->stream_chunk = value;
             return CDS_OK;
         }
+        if (std::strcmp(name, "stream_chunk_bytes") == 0) {
+            if (value < 1 || value > 0xC0000000ll) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk_bytes must be 1..3221225472");
+            ctx->stream_chunk_bytes = value;
+            return CDS_OK;
+        }
         if (std::strcmp(name, "stream_chunk_tiff") == 0) {
             if (value < 1 || value > 32768) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: stream_chunk_tiff must be 1..32768");
             ctx->stream_chunk_tiff = value;

@@ -116,6 +116,7 @@ struct cds_ctx {
     int resident_occupancy = 1;   // cds_ctx_set_option("resident_occupancy"): 0 = always build occupancy bitmaps per target chunk
     int64_t stream_chunk = 256;   // cds_ctx_set_option("stream_chunk"): targets per chunk of cds_search_stream_rgb
     int fused_ingest = 1;         // cds_ctx_set_option("fused_ingest"): 1 = TIFF strips go straight to code words (tiff_encode_kernel), 0 = decode to RGB, then encode
+    int64_t stream_chunk_bytes = 0xC0000000ll;   // cds_ctx_set_option("stream_chunk_bytes"): most file bytes per chunk (the strip table addresses them with 32 bits)
     int64_t stream_chunk_tiff = 4096;   // cds_ctx_set_option("stream_chunk_tiff"): targets per chunk of cds_search_stream_tiff
 
     cds_status fail(cds_status code, const std::string &msg) const;

@@ -249,7 +249,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             }
             int64_t cnt = std::min<int64_t>(want, n_targets - f);
             if (tiff) {
-                const uint64_t cap = 0xC0000000ull;
+                const uint64_t cap = (uint64_t) ctx->stream_chunk_bytes;
                 while (cnt > 1 && (uint64_t) (tiff->offsets[f + cnt] - tiff->offsets[f]) > cap) cnt = (cnt + 1) / 2;
             }
             plan.push_back({(int) (c % D), f, cnt});

@@ -93,10 +93,11 @@ int32_t    cds_abi_version(void);
  * a kernel that does not support the search's parameters falls through to the next one.  All three compute the same
  * scores bit for bit (tests/test_pixelmatch_gpu.py cross-checks them).
  * "stream_chunk": targets per chunk of the chunked searches (default 256).
- * "stream_chunk_tiff": targets per chunk of cds_search_stream_tiff (default 1024: compressed files upload fast, larger chunks
- *   keep the match kernel's grid full).
+ * "stream_chunk_tiff": most targets per chunk of cds_search_stream_tiff (default 4096: the match kernel hands out whole targets to its
+ *   persistent CTAs, so long chunks keep its grid full; the first chunks of a call are 256, 512, ... files so that matching starts early).
  * "resident_occupancy": 1 (default) keeps a library's occupancy bitmaps on the device next to its code planes (+23 % memory) and
  * falls back to building them per target chunk inside cds_search_topk when they do not fit; 0 always builds them per chunk.
+ * "stream_chunk_bytes": most file bytes per chunk of cds_search_stream_tiff (default and maximum 3 GiB; a chunk also ends there).
  * "fused_ingest": 1 (default) = the streaming searches over TIFF files turn the strips straight into the library's code words;
  * 0 = decode to RGB pixels first, then encode (the two-kernel path, kept as a cross-check).
  * "cand_wait_mode", "cand_l2_hint", "cand_warps", "cand_stages", "cand_max_rows": tuning knobs of the candidate kernel (csrc/cds_cand.cuh),

@@ -137,6 +137,28 @@ def test_stream_search_over_tiff_files_equals_rgb(ctx, synth_files, chunk):
         ctx.set_option("stream_chunk_tiff", 4096)
 
 
+def test_stream_chunks_end_at_the_byte_cap(ctx, synth_files):
+    """A chunk of the file search also ends where its files would exceed what the strip table addresses: forced here with a tiny cap."""
+    masks, targets, files = synth_files
+    rects = O.label_rects(W, H)
+    ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    ms.add_rgb(masks[:12])
+    exp = ms.search_stream_tiff(files, 50, 0.0)
+    biggest = max(len(f) for f in files)
+    try:
+        for cap in (biggest + 1, 3 * biggest, 1):                    # one file per chunk at most / a few / a cap below every file (one file per chunk)
+            ctx.set_option("stream_chunk_bytes", cap)
+            got = ms.search_stream_tiff(files, 50, 0.0)
+            assert np.array_equal(got[3], exp[3])
+            for m in range(12):
+                c = exp[3][m]
+                for a, b in zip(got[:3], exp[:3]):
+                    assert np.array_equal(a[m, :c], b[m, :c]), (cap, m)
+    finally:
+        ctx.set_option("stream_chunk_bytes", 0xC0000000)
+    ms.close()
+
+
 def test_stream_search_reports_the_bad_file(ctx, synth_files, tiffs):
     masks, targets, files = synth_files
     ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, O.label_rects(W, H))
