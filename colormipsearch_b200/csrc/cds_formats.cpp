@@ -307,7 +307,6 @@ extern "C" cds_status cds_png_encode_gray16(const uint16_t *pixels, int32_t widt
         std::vector<uint8_t> raw((size_t) height * (1 + rb)), cur(rb), prev(rb, 0), cand(rb);
         for (int y = 0; y < height; y++) {
             for (int x = 0; x < width; x++) { cur[2 * x] = (uint8_t) (pixels[(size_t) y * width + x] >> 8); cur[2 * x + 1] = (uint8_t) pixels[(size_t) y * width + x]; }
-            int best_f = 0;
             long best_cost = -1;
             uint8_t *dst = raw.data() + (size_t) y * (1 + rb);
             for (int f = 0; f < 5; f++) {
@@ -323,9 +322,8 @@ extern "C" cds_status cds_png_encode_gray16(const uint16_t *pixels, int32_t widt
                     cand[i] = (uint8_t) (cur[i] - pred);
                     cost += std::abs((int) (int8_t) cand[i]);
                 }
-                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_f = f; dst[0] = (uint8_t) f; memcpy(dst + 1, cand.data(), rb); }
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; dst[0] = (uint8_t) f; memcpy(dst + 1, cand.data(), rb); }
             }
-            (void) best_f;
             prev = cur;
         }
         uLongf zlen = compressBound((uLong) raw.size());
