@@ -175,7 +175,7 @@ cds_status png_parse(const uint8_t *file, size_t len, cds_png_info &info, std::v
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     if (!file || len < 8 + 25 || memcmp(file, sig, 8) != 0) { err = "not a PNG file"; return CDS_ERR_BAD_ARG; }
     size_t pos = 8;
-    bool have_hdr = false, have_end = false;
+    bool have_hdr = false;
     while (pos + 12 <= len) {
         const size_t n = be32(file + pos);
         const uint8_t *type = file + pos + 4;
@@ -190,13 +190,11 @@ cds_status png_parse(const uint8_t *file, size_t len, cds_png_info &info, std::v
             if (idat) idat->push_back({pos + 8, n});
             info.data_bytes += (int64_t) n;
         } else if (memcmp(type, "IEND", 4) == 0) {
-            have_end = true;
             break;
         }
         pos += 12 + n;
     }
     if (!have_hdr || info.width <= 0 || info.height <= 0) { err = "PNG: no header"; return CDS_ERR_BAD_ARG; }
-    (void) have_end;
     // grayscale, 8 or 16 bits, not interlaced, compression / filter method 0
     info.decodable = (info.color_type == 0 && (info.bit_depth == 8 || info.bit_depth == 16) && info.interlace == 0) ? 1 : 0;
     return CDS_OK;

@@ -256,11 +256,11 @@ template <int RINGS>
 __device__ __forceinline__ void occupancy_strip(const uint32_t *__restrict__ vsec /* sector's words of row 0 */, int vrow_words, int H,
                                                 int vp, int k, int y0, uint32_t o[4])
 {
-    if (RINGS == 0) {
+    if constexpr (RINGS == 0) {
 #pragma unroll
         for (int r = 0; r < 4; r++) o[r] = y0 + r < H ? vsec[(size_t) (y0 + r) * vrow_words + k] : 0u;
         return;
-    }
+    } else {
     uint32_t h2[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -281,6 +281,7 @@ __device__ __forceinline__ void occupancy_strip(const uint32_t *__restrict__ vse
     }
 #pragma unroll
     for (int r = 0; r < 4; r++) if (y0 + r >= H) o[r] = 0u;       // rows of the last tile row that lie below the image
+    }
 }
 
 // rows o[0..3] of a 32-pixel strip -> its four tile words (byte r of word j = byte j of row r)
