@@ -137,6 +137,30 @@ def test_stream_search_over_tiff_files_equals_rgb(ctx, synth_files, chunk):
         ctx.set_option("stream_chunk_tiff", 4096)
 
 
+def test_stream_search_two_kernel_ingest_equals_fused(ctx, synth_files):
+    """cds_ctx_set_option("fused_ingest", 0): the streaming search decodes to RGB and encodes (its staging half is sized lazily) and returns
+    the fused path's lists."""
+    masks, targets, files = synth_files
+    rects = O.label_rects(W, H)
+    ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
+    ms.add_rgb(masks[:12])
+    exp = ms.search_stream_tiff(files, 40, 0.0)
+    try:
+        ctx.set_option("fused_ingest", 0)
+        for chunk in (4096, 16):
+            ctx.set_option("stream_chunk_tiff", chunk)
+            got = ms.search_stream_tiff(files, 40, 0.0)
+            assert np.array_equal(got[3], exp[3])
+            for m in range(12):
+                c = exp[3][m]
+                for a, b in zip(got[:3], exp[:3]):
+                    assert np.array_equal(a[m, :c], b[m, :c]), (chunk, m)
+    finally:
+        ctx.set_option("fused_ingest", 1)
+        ctx.set_option("stream_chunk_tiff", 4096)
+    ms.close()
+
+
 def test_stream_chunks_end_at_the_byte_cap(ctx, synth_files):
     """A chunk of the file search also ends where its files would exceed what the strip table addresses: forced here with a tiny cap."""
     masks, targets, files = synth_files
