@@ -358,6 +358,10 @@ __global__ void __launch_bounds__(kOccThreads) occupancy_ring1_kernel(const uint
     if (seg < segs && kc == 1)
         for (int i = 0; i < CDS_NUM_SECTORS * 4; i++) (s_v + (i * segs + seg) * cw)[0] = 0u;
     auto raw = [&](int s, int y) -> uint32_t { return (active && y >= 0 && y < H) ? __ldg(vimg + (size_t) y * vrow_words + s * vp) : 0u; };
+    // the tile row's non-empty bits are collected in shared memory and leave as plain stores: no clearing pass over the rows beforehand,
+    // no atomics on global memory (word i of a segment's row is written, read and cleared by the same thread)
+    const int nzw = occupancy_nz_words(tp);
+    uint32_t *s_nz = s_v + (size_t) CDS_NUM_SECTORS * 4 * segs * cw + (size_t) (seg < segs ? seg : 0) * nzw;
     uint32_t carry[CDS_NUM_SECTORS][4];                   // image rows y0 - 2 .. y0 + 1 of the coming tile row
 #pragma unroll
     for (int s = 0; s < CDS_NUM_SECTORS; s++)
@@ -371,6 +375,7 @@ __global__ void __launch_bounds__(kOccThreads) occupancy_ring1_kernel(const uint
 #pragma unroll
             for (int j = 0; j < 4; j++) nw[s][j] = raw(s, y0 + 2 + j);
         if (seg < segs) {
+            for (int i = k; i < nzw; i += kc) s_nz[i] = 0u;
 #pragma unroll
             for (int s = 0; s < CDS_NUM_SECTORS; s++) {
                 sv(s, 0)[k + 1] = carry[s][0] | carry[s][2] | nw[s][0];
@@ -385,7 +390,6 @@ __global__ void __launch_bounds__(kOccThreads) occupancy_ring1_kernel(const uint
         if (active && ty < HT) {
             uint32_t *trow = occ + ((size_t) (t0 + tl) * HT + ty) * rowpitch;
             uint4 *orow = reinterpret_cast<uint4 *>(trow) + k;
-            uint32_t *nz = trow + (CDS_NUM_SECTORS + 1) * tp;
             uint32_t any[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int s = 0; s < CDS_NUM_SECTORS; s++) {
@@ -402,12 +406,16 @@ __global__ void __launch_bounds__(kOccThreads) occupancy_ring1_kernel(const uint
                 const uint32_t nib = (t.x != 0u ? 1u : 0u) | (t.y != 0u ? 2u : 0u) | (t.z != 0u ? 4u : 0u) | (t.w != 0u ? 8u : 0u);
                 if (nib) {
                     const int bit = s * tp + 4 * k;
-                    atomicOr(&nz[bit >> 5], nib << (bit & 31));
+                    atomicOr(&s_nz[bit >> 5], nib << (bit & 31));
                 }
             }
             orow[(size_t) CDS_NUM_SECTORS * (tp / 4)] = strip_to_tiles(any);
         }
         __syncthreads();
+        if (active && ty < HT) {
+            uint32_t *nz = occ + ((size_t) (t0 + tl) * HT + ty) * rowpitch + (CDS_NUM_SECTORS + 1) * tp;
+            for (int i = k; i < nzw; i += kc) nz[i] = s_nz[i];
+        }
     }
 }
 
@@ -423,16 +431,17 @@ static void launch_occupancy_kernel(const uint32_t *valid, int H, int vp, int tp
     // tile word back (occupancy_nz_kernel, 0.26 ms per 1 024 targets)
     const int rowpitch = occupancy_row_pitch(tp);
     const int HT = occupancy_tile_rows(H);
-    cudaMemset2DAsync(occ + (size_t) t0 * HT * rowpitch + (size_t) (CDS_NUM_SECTORS + 1) * tp, (size_t) rowpitch * sizeof(uint32_t), 0,
-                      (size_t) occupancy_nz_words(tp) * sizeof(uint32_t), (size_t) n * HT, s);
     const int kc = tp / 4;
     if (rings == 1 && occupancy_kernel_version() == 1 && kc >= 1 && kc <= kOccThreads / 2 && n * 64 < (1ll << 31)) {
         const int segs = std::min(kOccThreads / kc, 8);          // segments per block; keeps the exchange buffer below 32 kB
         const int blocks_per_target = (HT + segs * kOccSegRows - 1) / (segs * kOccSegRows);
-        const size_t smem = (size_t) CDS_NUM_SECTORS * 4 * segs * (kc + 2) * sizeof(uint32_t);
+        const size_t smem = ((size_t) CDS_NUM_SECTORS * 4 * segs * (kc + 2) + (size_t) segs * occupancy_nz_words(tp)) * sizeof(uint32_t);
         occupancy_ring1_kernel<<<(unsigned) (n * blocks_per_target), kOccThreads, smem, s>>>(valid, H, vp, tp, t0, occ, segs, blocks_per_target);
         return;
     }
+    // the generic kernel ORs its non-empty bits into rows that start from zero: one strided clear
+    cudaMemset2DAsync(occ + (size_t) t0 * HT * rowpitch + (size_t) (CDS_NUM_SECTORS + 1) * tp, (size_t) rowpitch * sizeof(uint32_t), 0,
+                      (size_t) occupancy_nz_words(tp) * sizeof(uint32_t), (size_t) n * HT, s);
     if (rings == 0) occupancy_kernel<0><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
     else if (rings == 1) occupancy_kernel<1><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
     else occupancy_kernel<2><<<148 * 8, 256, 0, s>>>(valid, H, vp, tp, t0, n, occ);
