@@ -199,7 +199,11 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
     ctx->stats = cds_search_stats{};
     if (!all) for (int m = 0; m < M; m++) out_count[m] = 0;
     if (n_targets == 0) return CDS_OK;
-    CDS_TRY(ms->sync_descs());
+    // A mask set that has changed since its last search still needs its palettes and word lists (sync_descs: a few small kernels and
+    // several host round trips, ~3 ms for 1 000 masks).  The search over files does not wait for that: the first chunk's upload, ingest
+    // and occupancy rows are put on the copy stream first and run while the lists are built; its match kernel waits for both.
+    bool descs_pending = tiff != nullptr && ms->descs_dirty;
+    if (!descs_pending) CDS_TRY(ms->sync_descs());
 
     const int D = (int) ctx->devs.size();
     PlaneGeom g;
@@ -348,6 +352,7 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         const int64_t first = ch.first, cnt = ch.cnt;
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
         const uint32_t *planes = sb.planes;
+        cudaStream_t ist = ds.stream;             // where this chunk's ingest and occupancy kernels run
         ChunkTrace *tr = nullptr;
         if (trace) { traces.push_back(ChunkTrace{d, cnt, {}, 0, 0, 0}); tr = &traces.back(); }
         const double t_chunk0 = trace ? host_ms() : 0;
@@ -377,20 +382,21 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             ctx->stats.h2d_bytes += (int64_t) bytes + (int64_t) (strips.size() * sizeof(TiffStrip));
             CDS_CUDA(ctx, cudaEventRecord(sb.h2d_done[slot], sb.copy_stream));
             mark(tr, 0, ds.stream);                  // the compute stream's position BEFORE it waits for the upload
-            CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
+            if (descs_pending) ist = sb.copy_stream;          // (this chunk's preprocessing runs beside the list build, see above)
+            if (ist == ds.stream) CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, sb.h2d_done[slot], 0));
             mark(tr, 1, ds.stream);
             if (fused_ingest) {
                 // strips -> code words + per-sector valid bits in one kernel, no RGB image in HBM in between
                 launch_tiff_encode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.planes, g, 0, ds.d_rank_tab, thr,
-                                   want_occ ? sb.valid : nullptr, sb.strip_counter, ds.stream);
+                                   want_occ ? sb.valid : nullptr, sb.strip_counter, ist);
                 ctx->stats.kernel_launches += 1;
             } else {
                 // decode into one RGB area (stream order protects it), then the usual encoder
-                launch_tiff_decode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.staging[0], ds.stream);
-                launch_encode_rgb(sb.staging[0], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ds.stream, want_occ ? sb.valid : nullptr);
+                launch_tiff_decode(sb.comp[slot], (const TiffStrip *) sb.d_strips[slot], (int64_t) strips.size(), sb.staging[0], ist);
+                launch_encode_rgb(sb.staging[0], cnt, sb.planes, g, 0, ds.d_rank_tab, thr, ist, want_occ ? sb.valid : nullptr);
                 ctx->stats.kernel_launches += 2;
             }
-            CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ds.stream));
+            CDS_CUDA(ctx, cudaEventRecord(sb.enc_done[slot], ist));
             mark(tr, 2, ds.stream);
         } else {
             if (j >= 2) CDS_CUDA(ctx, cudaStreamWaitEvent(sb.copy_stream, sb.enc_done[slot], 0));
@@ -407,12 +413,21 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
         tv.planes = planes; tv.g = g; tv.bpitch = bpitch; tv.n = cnt; tv.occ = nullptr; tv.occ_ready = false;
         if (want_occ) {
             // host targets: the encoder has just written the valid bits of this chunk
-            launch_occupancy(planes, g, 0, cnt, rings, bpitch, sb.valid, sb.chunk, sb.occ, ds.stream, resident == nullptr);
+            launch_occupancy(planes, g, 0, cnt, rings, bpitch, sb.valid, sb.chunk, sb.occ, ist, resident == nullptr);
             ctx->stats.kernel_launches += resident ? 2 : 1;      // (valid bits,) occupancy incl. the non-empty bits
             tv.occ = sb.occ;
             tv.occ_ready = true;
         }
         CDS_CUDA(ctx, cudaGetLastError());
+        if (ist != ds.stream) {
+            // the lists, now; then the compute stream joins the side stream
+            cudaEvent_t pre = sb.h2d_done[slot ^ 1];          // (free: no chunk of this device has used the other slot yet)
+            CDS_CUDA(ctx, cudaEventRecord(pre, ist));
+            CDS_TRY(ms->sync_descs());
+            descs_pending = false;
+            CDS_CUDA(ctx, cudaSetDevice(ds.dev));
+            CDS_CUDA(ctx, cudaStreamWaitEvent(ds.stream, pre, 0));
+        }
         if (tr && tiff) mark(tr, 3, ds.stream);
         CDS_TRY(launch_match_view(ctx, ms, tv, d, 0, M, sb.scores, ds.stream, sb.timing[2 * j], sb.timing[2 * j + 1]));
         if (all) {
