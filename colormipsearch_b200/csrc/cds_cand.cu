@@ -209,7 +209,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     const CandSmem<GROUP> L(p.stage_words, NS, bits_words, NCW, NSTG);
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw + L.stage_off) + kPrePad;
     const int stage_stride = p.stage_words + kPrePad;
-    const uint32_t *s_bits = reinterpret_cast<const uint32_t *>(smem_raw + L.bits_off);  // [kStages][R * bpitch]
+    const uint32_t *s_bits = reinterpret_cast<const uint32_t *>(smem_raw + L.bits_off);  // [stages][tile rows of a band * row pitch]
     uint2 *s_pal = reinterpret_cast<uint2 *>(smem_raw + L.pal_off);                      // palette of the current group
     uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + L.queue_off);                  // [NCW][kQueue] candidates
     uint4 *s_wqueue = reinterpret_cast<uint4 *>(smem_raw + L.wqueue_off);                // [NCW][kWordQueue] {candidate bits, the word's bits, lrec, meta} of words with candidates
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
     BandInfo *s_band = reinterpret_cast<BandInfo *>(smem_raw + L.band_off);             // [kMaxStages] what the consumers need to know about the staged band
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(smem_raw + L.bar_off);
     unsigned long long *s_empty = s_full + kMaxStages;
-    int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [kStages] ticket counters
+    int *s_next = reinterpret_cast<int *>(smem_raw + L.next_off);                       // [stages] batch counters
     long long *s_item = reinterpret_cast<long long *>(smem_raw + L.item_off);           // [2][2] published work items: {target, group}; target -1 = no more work
     uint8_t *s_sel = smem_raw + L.sel_off;                                               // [16][4] r-th set bit of a nibble
 

@@ -19,8 +19,8 @@ namespace cds {
 //     occ  : index of the matching occupancy word inside a target's bitmaps: tile row * occupancy_row_pitch + sector * pitch + tile column
 //     lrec : index into the group's `lpal` array of the palette reference of the word's LOWEST set bit; set bit b has
 //            lpal[lrec + popc(bits below b)] = palette index | 0x8000 when the pixel is in this list through its interval 2
-//     meta : tile row | tile column << 8 | orientation << 16 | sector << 17 | mask index inside the group << 22 (8 bits)   (H <= 1024, W <= 2048)
-// The scan touches only {bits, occ}; the second half is read for the words that have candidates.
+//     meta : tile row | tile column << 8 | orientation << 16 | sector << 17 | mask index inside the group << 22 (10 bits)   (H <= 1024, W <= 2048)
+// The scan reads whole entries (16 bytes, one 128-bit load) and uses {bits, occ}; {lrec, meta} travel with the words that have candidates.
 // ANDing `bits` with the library's occupancy word of the same (tile row, sector, tile column) leaves exactly the mask pixels
 // that can match in some shifted variant of that orientation -- 32 pixels per instruction -- and an evaluation tests ONE
 // interval: the two lists of a boundary pixel partition its matches by target sector, so nothing is counted twice.
