@@ -164,3 +164,15 @@ def test_host_only_generator_equals_the_library_generator():
     for kind, idx in ((0, 3), (1, 11), (1, 20)):
         assert np.array_equal(S.synth_rgb(kind, 0xC0FFEE, idx, 1, 1210, 566), capi.synth_rgb_host(kind, 0xC0FFEE, idx, 1, 1210, 566))
     assert np.array_equal(S.synth_gradient(0xC0FFEE, 5, 1, 301, 97), capi.synth_gradient_host(0xC0FFEE, 5, 1, 301, 97))
+
+
+def test_profile_tool_markers_exist_in_the_kernel_source():
+    """tools/ncu_phases.py groups an ncu report by marker lines of cds_cand.cu; a marker that an edit removed must fail here, not when the
+    next profile is read."""
+    import importlib.util
+    path = os.path.join(ROOT, "tools", "ncu_phases.py")
+    spec = importlib.util.spec_from_file_location("ncu_phases", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                     # raises SystemExit("marker not found ...") when a marker is gone
+    lines = [l for l, _ in mod.OUTER]
+    assert lines == sorted(lines) and len(set(lines)) == len(lines)
