@@ -238,9 +238,11 @@ __device__ __forceinline__ void tiff_encode_strip(const int64_t w, const uint32_
             // the whole row black, pad columns as pad words (the row is 16-byte aligned and a multiple of four words long)
             for (int v4 = (int) lane; v4 < g.pitch / 4; v4 += 32) {
                 const int x = 4 * v4;
-                uint4 w4;
-                w4.x = x < g.W ? black : CDS_CODE_PAD_WORD; w4.y = x + 1 < g.W ? black : CDS_CODE_PAD_WORD;
-                w4.z = x + 2 < g.W ? black : CDS_CODE_PAD_WORD; w4.w = x + 3 < g.W ? black : CDS_CODE_PAD_WORD;
+                uint4 w4 = make_uint4(black, black, black, black);
+                if (x + 3 >= g.W) {                            // the one or two words where the image ends
+                    w4.x = x < g.W ? black : CDS_CODE_PAD_WORD; w4.y = x + 1 < g.W ? black : CDS_CODE_PAD_WORD;
+                    w4.z = x + 2 < g.W ? black : CDS_CODE_PAD_WORD; w4.w = CDS_CODE_PAD_WORD;
+                }
                 reinterpret_cast<uint4 *>(drow)[v4] = w4;
             }
             const bool dirty = (dirty_lo | dirty_hi) != 0u;
