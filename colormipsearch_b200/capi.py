@@ -144,6 +144,7 @@ SIGNATURES = {
     "cds_debug_pairq_drive": (C.c_int32, [_vp, _vp, C.c_int64, C.POINTER(C.c_uint64), _i32p, _i64p, C.c_int64, C.c_int32, _i32p, _u8p, _f64p]),
     "cds_debug_slice_numbers": (C.c_int32, [_vp, _vp, C.c_int64, _u16p]),
     "cds_debug_occupancy": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "cds_debug_stream_plan": (C.c_int32, [C.c_int32, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "cds_debug_tiff_codes": (C.c_int32, [_vp, _vp, _i64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _u32p, _u32p]),
 }
 
@@ -742,6 +743,17 @@ def tiff_decode_rgb(ctx, files, W, H):
     out = np.empty((n, H, W, 3), np.uint8)
     _check(lib().cds_tiff_decode_rgb(ctx.h, _ptr(blob), offsets.ctypes.data_as(_i64p), n, W, H, _ptr(out)), ctx.h)
     return out
+
+
+def stream_plan(n_devices, n_targets, chunk, offsets=None, byte_cap=0xC0000000):
+    """cds_debug_stream_plan: the chunk plan of the streaming searches, as arrays (device, first, count).  No device needed."""
+    cap = int(n_targets) + 64
+    dev = np.zeros(cap, np.int32); first = np.zeros(cap, np.int64); cnt = np.zeros(cap, np.int64)
+    n = C.c_int64()
+    off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+    _check(lib().cds_debug_stream_plan(int(n_devices), int(n_targets), int(chunk), None if off is None else off.ctypes.data_as(_vp), int(byte_cap), cap,
+                                        dev.ctypes.data_as(_vp), first.ctypes.data_as(_vp), cnt.ctypes.data_as(_vp), C.byref(n)))
+    return dev[:n.value], first[:n.value], cnt[:n.value]
 
 
 def tiff_decode_rgb_host(data, W, H):

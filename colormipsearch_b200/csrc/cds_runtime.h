@@ -214,6 +214,9 @@ cds_status search_library_chunked(cds_ctx *ctx, const cds_maskset *ms, cds_libra
 cds_status library_append(cds_library *lib, int64_t n,
                           const std::function<cds_status(DevState &, int64_t i0, int64_t cnt, uint8_t *d_rgb)> &src,
                           int64_t *first_index);
+// one chunk of a search over host targets (cds_stream.cu)
+struct StreamChunk { int d; int64_t first, cnt; };
+std::vector<StreamChunk> stream_chunk_plan(int D, int64_t n_targets, int64_t chunk, const int64_t *offsets, uint64_t byte_cap);
 // masks per chunk of maskset_append (and therefore the most consecutive files a TIFF source has to stage at once)
 inline int maskset_append_chunk(int n)
 {

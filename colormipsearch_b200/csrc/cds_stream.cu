@@ -157,6 +157,63 @@ cds_status ensure_tiff_bufs(cds_ctx *ctx, DevState &ds, size_t comp_bytes, size_
 
 }  // namespace
 
+namespace cds {
+
+// The chunk plan of a search over host targets: (device, first target, count), chunks dealt round-robin over the devices.  Pixels
+// (offsets == nullptr): equal chunks.  TIFF files: the first chunks of every device are short (256, 512, ...) so that the match kernel
+// starts early -- a full chunk needs milliseconds of parsing, upload and ingest before its first comparison -- and what is left after
+// the ramp is cut into equal chunks (a short last chunk would leave most SMs idle during its match kernel: the kernel hands out whole
+// targets).  A chunk of files also ends where its bytes would exceed `byte_cap` (what the strip table addresses with 32 bits).
+std::vector<StreamChunk> stream_chunk_plan(int D, int64_t n_targets, int64_t chunk, const int64_t *offsets, uint64_t byte_cap)
+{
+    std::vector<StreamChunk> plan;
+    if (D < 1 || chunk < 1) return plan;
+    int64_t f = 0;
+    int64_t even = 0;                      // chunk length after the ramp (0: not there yet)
+    for (int64_t c = 0; f < n_targets; c++) {
+        int64_t want = chunk;
+        if (offsets) {
+            const int64_t ramp = (int64_t) 256 << std::min<int64_t>(c / D, 8);
+            if (ramp < chunk) {
+                want = ramp;
+            } else {
+                if (even == 0) {
+                    const int64_t rest = n_targets - f, per_round = chunk * D;
+                    const int64_t rounds = (rest + per_round - 1) / per_round;
+                    even = std::max<int64_t>(1, (rest + rounds * D - 1) / (rounds * D));
+                }
+                want = std::min(chunk, even);
+            }
+        }
+        int64_t cnt = std::min<int64_t>(want, n_targets - f);
+        if (offsets)
+            while (cnt > 1 && (uint64_t) (offsets[f + cnt] - offsets[f]) > byte_cap) cnt = (cnt + 1) / 2;
+        plan.push_back({(int) (c % D), f, cnt});
+        f += cnt;
+    }
+    return plan;
+}
+
+}  // namespace cds
+
+// Test hook: the plan above, without a device.
+extern "C" cds_status cds_debug_stream_plan(int32_t n_devices, int64_t n_targets, int64_t chunk, const int64_t *offsets, int64_t byte_cap,
+                                            int64_t capacity, int32_t *dev_out, int64_t *first_out, int64_t *count_out, int64_t *n_out)
+{
+    return cds::abi_guard("cds_debug_stream_plan", [&]() -> cds_status {
+        if (!n_out || n_devices < 1 || chunk < 1 || n_targets < 0 || byte_cap < 1 || capacity < 0) { set_tls_error("cds_debug_stream_plan: bad argument"); return CDS_ERR_BAD_ARG; }
+        const std::vector<cds::StreamChunk> plan = cds::stream_chunk_plan(n_devices, n_targets, chunk, offsets, (uint64_t) byte_cap);
+        *n_out = (int64_t) plan.size();
+        if ((int64_t) plan.size() > capacity) { set_tls_error("cds_debug_stream_plan: capacity too small"); return CDS_ERR_CAPACITY; }
+        for (size_t i = 0; i < plan.size(); i++) {
+            if (dev_out) dev_out[i] = plan[i].d;
+            if (first_out) first_out[i] = plan[i].first;
+            if (count_out) count_out[i] = plan[i].cnt;
+        }
+        return CDS_OK;
+    });
+}
+
 namespace {
 
 // targets given as TIFF files stored back to back (cds_search_stream_tiff)
@@ -230,35 +287,8 @@ cds_status stream_search_impl(cds_ctx *ctx, const cds_maskset *ms_c, const uint8
             for (int d = 0; d < D; d++)
                 if (f < resident->local_size(d)) plan.push_back({d, f, std::min<int64_t>(chunk, resident->local_size(d) - f)});
     } else {
-        // TIFF files: the first chunks of every device are short (256, 512, ...) so that the match kernel starts early -- a full chunk
-        // needs milliseconds of parsing, upload and ingest before its first comparison -- and what is left after the ramp is cut into
-        // equal chunks (a short last chunk would leave most SMs idle during its match kernel: the kernel hands out whole targets).
-        // A chunk also ends where its files would exceed what the strip table addresses with 32 bits.
-        int64_t f = 0;
-        int64_t even = 0;                      // chunk length after the ramp (0: not there yet)
-        for (int64_t c = 0; f < n_targets; c++) {
-            int64_t want = chunk;
-            if (tiff) {
-                const int64_t ramp = (int64_t) 256 << std::min<int64_t>(c / D, 8);
-                if (ramp < chunk) {
-                    want = ramp;
-                } else {
-                    if (even == 0) {
-                        const int64_t rest = n_targets - f, per_round = chunk * D;
-                        const int64_t rounds = (rest + per_round - 1) / per_round;
-                        even = std::max<int64_t>(1, (rest + rounds * D - 1) / (rounds * D));
-                    }
-                    want = std::min(chunk, even);
-                }
-            }
-            int64_t cnt = std::min<int64_t>(want, n_targets - f);
-            if (tiff) {
-                const uint64_t cap = (uint64_t) ctx->stream_chunk_bytes;
-                while (cnt > 1 && (uint64_t) (tiff->offsets[f + cnt] - tiff->offsets[f]) > cap) cnt = (cnt + 1) / 2;
-            }
-            plan.push_back({(int) (c % D), f, cnt});
-            f += cnt;
-        }
+        for (const StreamChunk &pc : stream_chunk_plan(D, n_targets, chunk, tiff ? tiff->offsets : nullptr, (uint64_t) ctx->stream_chunk_bytes))
+            plan.push_back({pc.d, pc.first, pc.cnt});
     }
     const int64_t n_chunks = (int64_t) plan.size();
     const int thr = ms->params.data_threshold;

@@ -442,6 +442,12 @@ cds_status cds_debug_tiff_codes(cds_ctx *ctx, const uint8_t *blob, const int64_t
  * 4): six sector rows of 8 x 4 tile words, their OR row, one "non-empty" bit per sector tile word.  The words between the rows are all written. */
 cds_status cds_debug_occupancy(cds_ctx *ctx, const uint32_t *valid, int64_t n, int32_t width, int32_t height, int32_t xy_shift,
                                uint32_t *occ_out);
+/* Test hook (no device needed): the chunk plan of the streaming searches over host targets -- entry i = (device, first target, count).
+ * offsets == NULL: pixels (equal chunks of `chunk` targets, round-robin over the devices); otherwise the files' offsets [n_targets + 1]:
+ * the first chunks of every device are 256, 512, ... files, what is left after the ramp is cut into equal chunks of at most `chunk`, and a
+ * chunk ends where its files would exceed byte_cap.  *n_out = entries; CDS_ERR_CAPACITY when capacity is too small. */
+cds_status cds_debug_stream_plan(int32_t n_devices, int64_t n_targets, int64_t chunk, const int64_t *offsets, int64_t byte_cap,
+                                 int64_t capacity, int32_t *dev_out, int64_t *first_out, int64_t *count_out, int64_t *n_out);
 cds_status cds_debug_pairq_drive(cds_pairq *q, const uint8_t *targets_rgb, int64_t n_targets, const uint64_t *keys,
                                  const int32_t *pair_mask, const int64_t *pair_target, int64_t n_pairs, int32_t n_threads,
                                  int32_t *scores_out, uint8_t *mirrored_out, double *seconds_out);
