@@ -301,7 +301,7 @@ cds_status cds_score_pair_rgb(cds_ctx *ctx, const cds_maskset *ms, int32_t mask_
  *   max_batch     most requests per launch (<= 0: 64)
  *   max_wait_us   how long the dispatcher waits for company before it launches a partly filled batch
  *   cache_targets code planes kept on every device (2.8 MB each for 1210 x 566); least recently used are replaced.  A device runs several
- *                 independent queues (4; environment CDSGPU_PAIRQ_QUEUES), targets are spread over them by key and each keeps
+ *                 independent queues (a third of the host's hardware threads, 2 .. 8; environment CDSGPU_PAIRQ_QUEUES), targets are spread over them by key and each keeps
  *                 cache_targets / queues planes (at least 2 * max_batch)
  *   target_key    the caller's identity of the image (the Java side passes the cache key / System.identityHashCode of the
  *                 ImageArray); equal keys MUST mean equal pixels; 0 = do not cache
