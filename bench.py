@@ -390,7 +390,9 @@ def data_dependence(ctx, masks_synth, n_masks=1000, n_targets=1024, reps=3):
     comparisons/s (device time of cds_search_topk over a resident library) and an oracle check of sampled cells:
       real_fixture     masks = the reference's three EM fixtures, targets = its four LM fixtures, label regions cleared, replicated
                        with translation (and brightness scaling for the targets) jitter
-      dense_synthetic  the synthetic masks against targets that overlay six synthetic targets each (~20-30 % of the pixels lit)"""
+      dense_synthetic  the synthetic masks against targets that overlay six synthetic targets each (~20-30 % of the pixels lit)
+      reverse_search   the LM fixtures (brightness-scaled: tens of thousands of colour classes per mask group) as masks against the
+                       EM fixtures as targets -- the word lists then carry rank intervals instead of palette references"""
     from colormipsearch_b200 import capi
     from oracle import oracle as O
     rects = label_rects()
@@ -448,6 +450,9 @@ def data_dependence(ctx, masks_synth, n_masks=1000, n_targets=1024, reps=3):
     masks = np.stack([jitter(em[i % 3], 1.0) for i in range(n_masks)])
     targets = np.stack([jitter(lm[i % 4], float(rng.uniform(0.5, 1.0))) for i in range(n_targets)])
     legs["real_fixture"] = leg(masks, targets, "the reference's EM / LM fixture images (labels cleared), replicated with jitter")
+    n_rev = max(16, min(128, n_masks // 8))
+    legs["reverse_search"] = leg(targets[:n_rev], masks,
+                                 "the LM fixture images (brightness-scaled, jittered) as %d masks x the EM fixture images as targets" % n_rev)
     del masks, targets
     base = np.concatenate([ctx.synth_rgb(1, SEED, 100000 + i, min(64, 6 * 128 - i), W, H, on_device=True) for i in range(0, 6 * 128, 64)])
     pool = []

@@ -348,6 +348,7 @@ extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t
         if (std::strcmp(name, "cand_l2_hint") == 0) { cand_tuning().l2_hint = value != 0; return CDS_OK; }
         if (std::strcmp(name, "cand_warps") == 0) { cand_tuning().warps = (int) value; return CDS_OK; }
         if (std::strcmp(name, "occupancy_kernel") == 0) { occupancy_kernel_version() = value != 0; return CDS_OK; }
+        if (std::strcmp(name, "wide_lists") == 0) { ctx->wide_lists = value != 0; return CDS_OK; }
         if (std::strcmp(name, "cand_stages") == 0) { cand_tuning().stages = (int) value; return CDS_OK; }
         if (std::strcmp(name, "cand_max_rows") == 0) { cand_tuning().max_rows = (int) value; return CDS_OK; }
         return ctx->fail(CDS_ERR_BAD_ARG, std::string("cds_ctx_set_option: unknown option ") + name);
@@ -959,9 +960,12 @@ cds_status cds_maskset::sync_descs()
         CDS_CUDA(ctx, ds.pool.alloc((void **) &d_groups[d], groups.size() * sizeof(PaletteGroup)));
         CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
         // word lists of the candidate kernel (cds_cand.cuh): per-(mask, row) counts, per-(group, row) runs, row starts, fill.
-        // They reference the groups' palettes, so they exist only when every group is compact.
+        // They reference the groups' palettes; when a group has more classes than a palette holds, the lists of the whole set
+        // carry the packed intervals instead (WIDE, 32 instead of 16 bits per mask pixel and list).
         const bool words_ok = M > 0 && W <= 2048 && H <= 1024 && (params.xy_shift == 0 || params.xy_shift == 2 || params.xy_shift == 4) &&
-                              compact_ok && n_compact_groups == n_groups;
+                              compact_ok;
+        const bool wide = words_ok && (n_compact_groups != n_groups || ctx->wide_lists);
+        if (d == 0) wide_lpal = wide;
         if (words_ok) {
             uint32_t *d_grow = nullptr;
             const int HT = occupancy_tile_rows(H);              // the lists are ordered by rows of 8 x 4 tiles
@@ -998,7 +1002,7 @@ cds_status cds_maskset::sync_descs()
                 // d_words: the entries, the ticket bounds, then the palette references
                 const size_t n_tocc = words_tocc_count((uint32_t) total[0]);
                 CDS_CUDA(ctx, ds.pool.alloc((void **) &d_words[d], std::max<uint64_t>(total[0], 1) * sizeof(uint4) + n_tocc * sizeof(uint32_t) +
-                                                                       std::max<uint64_t>(total[1], 1) * sizeof(uint16_t)));
+                                                                       std::max<uint64_t>(total[1], 1) * (wide ? sizeof(uint32_t) : sizeof(uint16_t))));
                 uint4 *d_entries = reinterpret_cast<uint4 *>(d_words[d]);
                 uint32_t *d_tocc = reinterpret_cast<uint32_t *>(d_entries + std::max<uint64_t>(total[0], 1));
                 uint16_t *d_lpal = reinterpret_cast<uint16_t *>(d_tocc + n_tocc);
@@ -1011,7 +1015,7 @@ cds_status cds_maskset::sync_descs()
                     groups[g].tocc = d_tocc;
                 }
                 CDS_CUDA(ctx, cudaMemcpyAsync(d_descs[d], h.data(), h.size() * sizeof(MaskDesc), cudaMemcpyHostToDevice, ds.stream));
-                launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, class_tab, d_gstart, d_bstart, d_bcount, d_entries, d_lpal, ds.stream);
+                launch_words_fill(d_descs[d], M, W, H, params.mirror != 0, class_tab, d_gstart, d_bstart, d_bcount, d_entries, d_lpal, ds.stream, wide);
                 ctx->stats.kernel_launches++;
                 CDS_CUDA(ctx, cudaGetLastError());
                 {
@@ -1067,7 +1071,7 @@ cds_status launch_match_view(cds_ctx *ctx, const cds_maskset *ms, const TargetVi
     if (cand_ok) {
         int launches = launch_pixelmatch_cand(ms->d_descs[d] + m0, mc, tv.planes, tv.g, tv.n, tv.occ, tv.bpitch,
                                               ms->d_groups[d] + m0 / CDS_PALETTE_GROUP, ms->params.xy_shift, ms->params.mirror != 0,
-                                              d_scores, scratch, stream);
+                                              d_scores, scratch, stream, ms->wide_lpal);
         ctx->stats.kernel_launches += launches;
         ctx->stats.match_kernel_launches += launches;
         ctx->stats.match_kernel = 1;

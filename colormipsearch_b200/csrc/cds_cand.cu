@@ -24,6 +24,7 @@
 #include "cds_ptx.cuh"
 
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 #include <vector>
 
@@ -169,20 +170,27 @@ __device__ __forceinline__ uint32_t select_bit(uint32_t c, uint32_t r, const uin
 
 // First half of an evaluation: the candidate's palette reference (palette index | 0x8000 for the second interval), an L2
 // access whose latency the caller hides behind the evaluation of the previous batch.
+// WIDE (groups with more colour classes than a shared-memory palette holds): lpal carries the packed interval itself, 32 bits per
+// set bit, and there is no palette.
+template <bool WIDE>
 __device__ __forceinline__ uint32_t fetch_palette_ref(uint2 cand, bool live, const uint16_t *__restrict__ lpal, uint64_t policy)
 {
+    if (WIDE) return live ? __ldg(reinterpret_cast<const uint32_t *>(lpal) + cand.y) : CDS_PAL_EMPTY_LO;
     uint32_t pr = CDS_PALETTE_SIZE - 1;                                         // the never-matching entry
     if (live) pr = policy ? ldg_hint_u16(lpal + cand.y, policy) : (uint32_t) __ldg(lpal + cand.y);
     return pr;
 }
 
-template <int NRINGS>
+template <int NRINGS, bool WIDE>
 __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const uint32_t *__restrict__ band, int pitch,
                                                 const uint2 *__restrict__ s_pal, const int *acc_base)
 {
     constexpr int NS = Offsets<NRINGS>::N;
-    const uint2 pe = s_pal[pr & (CDS_PALETTE_SIZE - 1)];
-    const uint32_t iv = (pr & 0x8000u) ? pe.y : pe.x;                           // the interval that lives in this candidate's sector
+    uint32_t iv = pr;                                                           // WIDE: the reference IS the interval
+    if (!WIDE) {
+        const uint2 pe = s_pal[pr & (CDS_PALETTE_SIZE - 1)];
+        iv = (pr & 0x8000u) ? pe.y : pe.x;                                      // the interval that lives in this candidate's sector
+    }
     const uint32_t lo = (iv & ((1u << CDS_PAL_LO_BITS) - 1)) << CDS_CODE_SR_SHIFT;
     const uint32_t len = ((iv >> CDS_PAL_LO_BITS) << CDS_CODE_SR_SHIFT) | 0xFFu;
     const uint32_t *pc = band + (cand.x & (kCandOffsetMask));
@@ -194,7 +202,7 @@ __device__ __forceinline__ void eval_candidates(uint2 cand, uint32_t pr, const u
     EvalUnroll<NRINGS, 0>::count(cw, acc, lo, len);
 }
 
-template <int NRINGS, int GROUP, int NCW, bool HINT>
+template <int NRINGS, int GROUP, int NCW, bool HINT, bool WIDE>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(const CandParams p)
 {
     constexpr int NS = Offsets<NRINGS>::N;            // shift offsets = variants per orientation
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             gwords = pg.words;
             glpal = pg.lpal;
             gtocc = pg.tocc;
-            for (int i = tid; i < pg.n_pal; i += NCT) s_pal[i] = pg.palette[i];
+            if (!WIDE) for (int i = tid; i < pg.n_pal; i += NCT) s_pal[i] = pg.palette[i];
             if (tid == 0) s_pal[CDS_PALETTE_SIZE - 1] = make_uint2(CDS_PAL_EMPTY_LO, CDS_PAL_EMPTY_LO);   // idle lanes point here
             consumer_barrier<NCT>();
             cur_gi = gi;
@@ -362,9 +370,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pixelmatch_cand_kernel(cons
             uint2 pend_cand = idle_cand;
             uint32_t pend_pr = 0;
             bool pend = false;
-            auto run_pending = [&]() { eval_candidates<NRINGS>(pend_cand, pend_pr, band, pitch, s_pal, acc_base); };
+            auto run_pending = [&]() { eval_candidates<NRINGS, WIDE>(pend_cand, pend_pr, band, pitch, s_pal, acc_base); };
             auto submit = [&](uint2 cand, bool live) {
-                const uint32_t pr = fetch_palette_ref(cand, live, glpal, pol_keep);
+                const uint32_t pr = fetch_palette_ref<WIDE>(cand, live, glpal, pol_keep);
                 if (pend) run_pending();
                 pend_cand = cand; pend_pr = pr; pend = true;
             };
@@ -622,7 +630,7 @@ int env_int(const char *name, int dflt)
 template <int GROUP, int NCW>
 int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, int32_t *scores,
-               const MatchScratch &scratch, cudaStream_t s, int dev)
+               const MatchScratch &scratch, cudaStream_t s, int dev, bool wide)
 {
     const int n_stages = std::max(2, std::min(kMaxStages, cand_tuning().stages));
     CandConfig c = cand_config<GROUP>(xy_shift, g, NCW, n_stages, cand_tuning().max_rows);
@@ -654,9 +662,13 @@ int launch_cfg(const MaskDesc *masks, int n_masks, const uint32_t *planes, Plane
     int grid = (int) std::min<long long>(std::min(n_sm, 256), n_items);
     void (*kern)(const CandParams) = nullptr;
     const int rings = xy_shift / 2;
-    if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW, false>;
-    else if (rings == 1) kern = hint ? pixelmatch_cand_kernel<1, GROUP, NCW, true> : pixelmatch_cand_kernel<1, GROUP, NCW, false>;
-    else kern = pixelmatch_cand_kernel<2, GROUP, NCW, false>;
+    if (wide) {
+        if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW, false, true>;
+        else if (rings == 1) kern = pixelmatch_cand_kernel<1, GROUP, NCW, false, true>;
+        else kern = pixelmatch_cand_kernel<2, GROUP, NCW, false, true>;
+    } else if (rings == 0) kern = pixelmatch_cand_kernel<0, GROUP, NCW, false, false>;
+    else if (rings == 1) kern = hint ? pixelmatch_cand_kernel<1, GROUP, NCW, true, false> : pixelmatch_cand_kernel<1, GROUP, NCW, false, false>;
+    else kern = pixelmatch_cand_kernel<2, GROUP, NCW, false, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem_bytes);
     kern<<<grid, (NCW + 1) * 32, c.smem_bytes, s>>>(p);
     if (p.trace) {
@@ -688,7 +700,7 @@ constexpr int kLists = 2 * CDS_NUM_SECTORS;      // (orientation, sector) bitmap
 // receives, per (y % 4, x), the pixel's palette index | own sector << 11.
 __device__ __forceinline__ void build_tile_row_lists(const MaskDesc &md, int ty, int W, int H, bool mirror,
                                                      const cds_class_interval *__restrict__ class_tab,
-                                                     uint32_t (*bm)[kRowTiles] /* [kLists] */, uint16_t *pix)
+                                                     uint32_t (*bm)[kRowTiles] /* [kLists] */, uint16_t *pix, uint32_t *pix_cls = nullptr)
 {
     const int lane = threadIdx.x & 31;
     for (int k = lane; k < kLists * kRowTiles; k += 32) bm[0][k] = 0;
@@ -703,6 +715,7 @@ __device__ __forceinline__ void build_tile_row_lists(const MaskDesc &md, int ty,
         const int s1 = (int) (cls / CDS_NUM_RANKS);
         const cds_class_interval iv = class_tab[cls];
         if (pix) pix[yy * (kRowTiles * 8) + x] = (uint16_t) ((md.crec ? (__ldg(md.crec + i) >> 21) : 0u) | ((uint32_t) s1 << 11));
+        if (pix_cls) pix_cls[yy * (kRowTiles * 8) + x] = cls;
         const uint32_t bn = 1u << (yy * 8 + (x & 7)), bmr = 1u << (yy * 8 + (xm & 7));
         if (iv.lo1 != CDS_IV_EMPTY) {
             atomicOr(&bm[s1][x >> 3], bn);
@@ -761,6 +774,14 @@ __global__ void __launch_bounds__(128) words_group_rows_kernel(uint32_t *__restr
     grow[(size_t) g * (H + 1) + y] = acc;
 }
 
+// one interval as a palette word (cds_common.h): lo | len << 18, SR units
+__device__ __forceinline__ uint32_t pack_interval_word(uint32_t lo, uint32_t len)
+{
+    if (lo == CDS_IV_EMPTY || len > CDS_PAL_MAX_LEN) return CDS_PAL_EMPTY_LO;
+    return lo | (len << CDS_PAL_LO_BITS);
+}
+
+template <bool WIDE>
 __global__ void __launch_bounds__(32) words_fill_kernel(const MaskDesc *__restrict__ masks, int first_mask, int W, int H, bool mirror,
                                                         const cds_class_interval *__restrict__ class_tab,
                                                         const uint32_t *__restrict__ gstart /* [n_groups][HT+1] entries */,
@@ -769,12 +790,14 @@ __global__ void __launch_bounds__(32) words_fill_kernel(const MaskDesc *__restri
                                                         uint4 *__restrict__ words, uint16_t *__restrict__ lpal)
 {
     __shared__ uint32_t s_bm[kLists][kRowTiles];
-    __shared__ uint16_t s_pix[4 * kRowTiles * 8];
+    // per (y % 4, x): palette index | own sector << 11, or (WIDE) the pixel's colour class
+    __shared__ typename std::conditional<WIDE, uint32_t, uint16_t>::type s_pix[4 * kRowTiles * 8];
     const int lane = threadIdx.x;
     const int ty = blockIdx.x, HT = gridDim.x;
     const int m = first_mask + blockIdx.y;
     const MaskDesc md = masks[blockIdx.y];
-    build_tile_row_lists(md, ty, W, H, mirror, class_tab, s_bm, s_pix);
+    if constexpr (WIDE) build_tile_row_lists(md, ty, W, H, mirror, class_tab, s_bm, nullptr, s_pix);
+    else build_tile_row_lists(md, ty, W, H, mirror, class_tab, s_bm, s_pix);
     const int g = m / CDS_PALETTE_GROUP;
     const uint32_t mtag = (uint32_t) (m % CDS_PALETTE_GROUP) << kWordMetaMaskShift;
     uint32_t out_w = __ldg(gstart + (size_t) g * (HT + 1) + ty) + __ldg(md.wstart + ty);       // start of the tile row's run + this mask's offset in it
@@ -808,7 +831,14 @@ __global__ void __launch_bounds__(32) words_fill_kernel(const MaskDesc *__restri
                     wbits &= wbits - 1;
                     const int xt = k * 8 + (bit & 7);
                     const uint32_t pv = s_pix[(bit >> 3) * (kRowTiles * 8) + (o ? W - 1 - xt : xt)];
-                    lpal[lrec++] = (uint16_t) ((pv & 0x7FFu) | (((pv >> 11) & 7u) != (uint32_t) sec ? 0x8000u : 0u));
+                    if constexpr (WIDE) {
+                        // the interval of this list's sector, packed like a palette word (cds_common.h)
+                        const cds_class_interval iv = class_tab[pv];
+                        const bool own = pv / CDS_NUM_RANKS == (uint32_t) sec;
+                        reinterpret_cast<uint32_t *>(lpal)[lrec++] = pack_interval_word(own ? iv.lo1 : iv.lo2, own ? iv.len1 : iv.len2);
+                    } else {
+                        lpal[lrec++] = (uint16_t) ((pv & 0x7FFu) | (((pv >> 11) & 7u) != (uint32_t) sec ? 0x8000u : 0u));
+                    }
                 }
             }
             out_w += (uint32_t) __popc(bal);
@@ -937,18 +967,20 @@ void launch_words_group_rows(uint32_t *count, int n_masks, int H, uint32_t *grow
 }
 
 void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,
-                       const uint32_t *gstart, const uint32_t *bstart, const uint32_t *boff, uint4 *words, uint16_t *lpal, cudaStream_t s)
+                       const uint32_t *gstart, const uint32_t *bstart, const uint32_t *boff, uint4 *words, uint16_t *lpal, cudaStream_t s,
+                       bool wide_lpal)
 {
     for (int m0 = 0; m0 < n_masks; m0 += 32768) {
         int cnt = n_masks - m0 < 32768 ? n_masks - m0 : 32768;
         dim3 grid(occupancy_tile_rows(H), cnt);
-        words_fill_kernel<<<grid, 32, 0, s>>>(masks + m0, m0, W, H, mirror, class_tab, gstart, bstart, boff, words, lpal);
+        if (wide_lpal) words_fill_kernel<true><<<grid, 32, 0, s>>>(masks + m0, m0, W, H, mirror, class_tab, gstart, bstart, boff, words, lpal);
+        else words_fill_kernel<false><<<grid, 32, 0, s>>>(masks + m0, m0, W, H, mirror, class_tab, gstart, bstart, boff, words, lpal);
     }
 }
 
 int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                            const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror,
-                           int32_t *scores, const MatchScratch &scratch, cudaStream_t s)
+                           int32_t *scores, const MatchScratch &scratch, cudaStream_t s, bool wide_lpal)
 {
     (void) mirror;      // the word lists already say which orientations exist
     if (n_masks == 0 || n_targets == 0) return 0;
@@ -965,7 +997,7 @@ int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *p
     if (warps >= 31 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 31, n_stages, cand_tuning().max_rows).ok) warps = 28;
     if (warps >= 28 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 28, n_stages, cand_tuning().max_rows).ok) warps = 24;
     if (warps >= 24 && !cand_config<CDS_PALETTE_GROUP>(xy_shift, g, 24, n_stages, cand_tuning().max_rows).ok) warps = 16;
-#define CDS_CAND_LAUNCH(NCW) launch_cfg<CDS_PALETTE_GROUP, NCW>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, scratch, s, dev)
+#define CDS_CAND_LAUNCH(NCW) launch_cfg<CDS_PALETTE_GROUP, NCW>(masks, n_masks, planes, g, n_targets, occ, bpitch, groups, xy_shift, scores, scratch, s, dev, wide_lpal)
     if (warps >= 31) return CDS_CAND_LAUNCH(31);
     if (warps >= 28) return CDS_CAND_LAUNCH(28);
     if (warps >= 24) return CDS_CAND_LAUNCH(24);

@@ -19,6 +19,9 @@ namespace cds {
 //     occ  : index of the matching occupancy word inside a target's bitmaps: tile row * occupancy_row_pitch + sector * pitch + tile column
 //     lrec : index into the group's `lpal` array of the palette reference of the word's LOWEST set bit; set bit b has
 //            lpal[lrec + popc(bits below b)] = palette index | 0x8000 when the pixel is in this list through its interval 2
+//            WIDE lists (a group of the set has more colour classes than a palette holds, e.g. brightness-scaled LM images used
+//            as masks): `lpal` has 32 bits per set bit and holds the packed interval of this list's sector itself
+//            (lo | len << 18 like a palette word); the kernel's WIDE instantiation then needs no palette.
 //     meta : tile row | tile column << 8 | orientation << 16 | sector << 17 | mask index inside the group << 22 (10 bits)   (H <= 1024, W <= 2048)
 // The scan reads whole entries (16 bytes, one 128-bit load) and uses {bits, occ}; {lrec, meta} travel with the words that have candidates.
 // ANDing `bits` with the library's occupancy word of the same (tile row, sector, tile column) leaves exactly the mask pixels
@@ -51,7 +54,8 @@ void launch_words_count(const MaskDesc *masks, int n_masks, int W, int H, bool m
                         uint32_t *wcount, uint32_t *bcount, cudaStream_t s);
 void launch_words_group_rows(uint32_t *count, int n_masks, int H, uint32_t *grow, cudaStream_t s);
 void launch_words_fill(const MaskDesc *masks, int n_masks, int W, int H, bool mirror, const cds_class_interval *class_tab,
-                       const uint32_t *gstart, const uint32_t *bstart, const uint32_t *boff, uint4 *words, uint16_t *lpal, cudaStream_t s);
+                       const uint32_t *gstart, const uint32_t *bstart, const uint32_t *boff, uint4 *words, uint16_t *lpal, cudaStream_t s,
+                       bool wide_lpal = false);
 
 // Reorders every tile row's entries by occupancy word (`occ`), i.e. by (sector, tile column): afterwards the entries that meet one
 // target tile are neighbours, and the kernel skips the tickets whose occupancy words are all empty.  `tables` = scratch of
@@ -66,7 +70,7 @@ void launch_words_tocc(const uint4 *words, uint32_t n_entries, uint32_t *tocc, c
 // (PaletteGroup::palette / words / gstart / lpal).
 int launch_pixelmatch_cand(const MaskDesc *masks, int n_masks, const uint32_t *planes, PlaneGeom g, int64_t n_targets,
                            const uint32_t *occ, int bpitch, const PaletteGroup *groups, int xy_shift, bool mirror,
-                           int32_t *scores, const MatchScratch &scratch, cudaStream_t s);
+                           int32_t *scores, const MatchScratch &scratch, cudaStream_t s, bool wide_lpal = false);
 
 }  // namespace cds
 #endif

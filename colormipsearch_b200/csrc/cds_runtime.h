@@ -112,6 +112,7 @@ struct cds_ctx {
     mutable std::recursive_mutex mu;
     mutable std::string err;
     cds_search_stats stats{};
+    bool wide_lists = false;   // cds_ctx_set_option("wide_lists"): mask sets prepared from now on get interval-carrying word lists even when palettes would do
     int match_kernel = 0;      // cds_ctx_set_option("match_kernel"): 0 automatic, 1 candidate, 2 band, 3 gather
     int resident_occupancy = 1;   // cds_ctx_set_option("resident_occupancy"): 0 = always build occupancy bitmaps per target chunk
     int64_t stream_chunk = 256;   // cds_ctx_set_option("stream_chunk"): targets per chunk of cds_search_stream_rgb
@@ -181,6 +182,7 @@ struct cds_maskset {
     std::vector<uint32_t *> d_words;                   // per device, word-list entries of all groups followed by their palette references (cds_cand.cuh)
     std::vector<uint32_t *> d_wstart;                  // per device, per-mask offsets and per-group row starts of the word lists
     int n_compact_groups = 0;                          // groups whose colour classes fit a shared-memory palette
+    bool wide_lpal = false;                            // the word lists carry intervals instead of palette references (cds_cand.cuh: WIDE)
     bool words_built = false;                          // the candidate kernel's word lists exist on every device
     bool descs_dirty = true;
     cds_status sync_descs();

@@ -102,6 +102,9 @@ int32_t    cds_abi_version(void);
  * 0 = decode to RGB pixels first, then encode (the two-kernel path, kept as a cross-check).
  * "cand_wait_mode", "cand_l2_hint", "cand_warps", "cand_stages", "cand_max_rows": tuning knobs of the candidate kernel (csrc/cds_cand.cuh),
  *   process-wide.  "occupancy_kernel": 1 (default) = the single-pass occupancy kernel for xyShift 2, 0 = the generic one (cross-check).
+ * "wide_lists": 1 = mask sets prepared from now on carry each mask pixel's rank interval in the candidate kernel's lists (4 bytes per
+ *   pixel and list) instead of a reference into a per-group palette (2 bytes).  0 (default): only sets with a group of more than
+ *   2 047 colour classes do (brightness-scaled LM images as masks -- the reverse search); scores are the same either way.
  * Unknown names: CDS_ERR_BAD_ARG. */
 cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t value);
 

@@ -165,6 +165,58 @@ def test_wide_tolerance_uses_16_byte_records(ctx, synth):
     ms.close()
 
 
+def test_many_colour_classes_run_on_the_candidate_kernel(ctx, synth):
+    """The reverse search: brightness-scaled LM images used as masks (any ImageArray is a legal query,
+    ColorDepthSearchAlgorithmProvider.java:20-32).  A group of such masks has more colour classes than a shared-memory palette
+    holds (2 047), so the word lists carry the rank intervals themselves (cds_cand.cuh: WIDE) and the candidate kernel still runs;
+    the band kernel uses the 16-byte records for such a group."""
+    masks, targets, lib = synth
+    rects = O.label_rects(W, H)
+    rng = np.random.default_rng(5)
+    lm = (targets[:18].astype(np.float32) * rng.uniform(0.35, 1.0, size=(18, H, W, 1)).astype(np.float32)).astype(np.uint8)
+    codes = _np_expected_codes(lm.reshape(-1, 3), 20)
+    classes = np.unique(codes[(codes & 0x80000000) == 0] >> 8)
+    assert len(classes) > 4096, len(classes)            # far more than one palette
+    params = (20, 20, 0.01, 2, True)
+    ms = _maskset(ctx, params, rects)
+    sizes = ms.add_rgb(lm)
+    oms = [O.PixelMatchMask(x, 20, True, 20, 0.01, 2, rects) for x in lm]
+    assert sizes.tolist() == [m.size for m in oms]
+    es, em, _ = O.search_dense(oms, targets[:24])
+    assert es.max() > 1000          # a scaled image still matches its original within the tolerance in places
+    for kern in BATCHED_KERNELS:
+        ctx.set_match_kernel(kern)
+        scores, mirrored = ms.search_dense(lib)
+        assert ctx.last_stats()["match_kernel"] == {"cand": 1, "band": 2}[kern]
+        assert np.array_equal(scores[:, :24], es), kern
+        assert np.array_equal(mirrored[:, :24], em), kern
+    ctx.set_match_kernel("auto")
+    ms.close()
+    # a set that mixes a many-class group with ordinary masks (one group here): still one consistent list format
+    ms = _maskset(ctx, params, rects)
+    mixed = np.concatenate([masks[:8], lm[:10]])
+    ms.add_rgb(mixed)
+    oms = [O.PixelMatchMask(x, 20, True, 20, 0.01, 2, rects) for x in mixed]
+    es, em, _ = O.search_dense(oms, targets[:12])
+    scores, mirrored = ms.search_dense(lib)
+    assert ctx.last_stats()["match_kernel"] == 1
+    assert np.array_equal(scores[:, :12], es) and np.array_equal(mirrored[:, :12], em)
+    ms.close()
+    # ordinary masks with the interval-carrying lists forced on ("wide_lists"), every supported xyShift: the palette lists' scores
+    for xys in (0, 2, 4):
+        got = []
+        for wide in (0, 1):
+            ctx.set_option("wide_lists", wide)
+            ms = _maskset(ctx, (20, 20, 0.01, xys, True), rects)
+            ms.add_rgb(masks)
+            got.append(ms.search_dense(lib))
+            assert ctx.last_stats()["match_kernel"] == 1
+            ms.close()
+        ctx.set_option("wide_lists", 0)
+        assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1]), xys
+        assert got[0][0].max() > 200
+
+
 def test_topk_matches_sorted_dense(ctx, synth):
     masks, targets, lib = synth
     rects = O.label_rects(W, H)

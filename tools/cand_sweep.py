@@ -17,6 +17,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--width", type=int, default=1210)
 ap.add_argument("--height", type=int, default=566)
 ap.add_argument("--settings", default="wait=0;wait=1;wait=32;wait=64;wait=100;wait=200;wait=400;wait=0,hint=1")
+ap.add_argument("--wide", type=int, default=0, help="1: word lists that carry the rank intervals (cds_ctx_set_option wide_lists)")
 a = ap.parse_args()
 W, H = a.width, a.height
 rects = O.label_rects(W, H)
@@ -24,6 +25,7 @@ ctx = capi.Context(device_ids=[0])
 lib = capi.Library(ctx, W, H, a.targets)
 lib.generate_synthetic(SEED, 0, a.targets)
 masks = np.concatenate([ctx.synth_rgb(0, SEED, i, min(64, a.masks - i), W, H, on_device=True) for i in range(0, a.masks, 64)])
+ctx.set_option("wide_lists", a.wide)
 ms = capi.MaskSet(ctx, W, H, 20, 20, 0.01, 2, True, rects)
 ms.add_rgb(masks)
 base = None
@@ -44,5 +46,5 @@ for setting in a.settings.split(";"):
         base = res
     else:
         same = bool(np.array_equal(res[3], base[3]) and np.array_equal(res[0], base[0]) and np.array_equal(res[1], base[1]))
-    print(json.dumps({"setting": setting, "comparisons_per_s": a.masks * a.targets * a.reps / (ms_total * 1e-3), "ms_per_search": ms_total / a.reps,
+    print(json.dumps({"setting": setting, "wide_lists": a.wide, "comparisons_per_s": a.masks * a.targets * a.reps / (ms_total * 1e-3), "ms_per_search": ms_total / a.reps,
                       "same_result_as_first": same}), flush=True)
