@@ -257,7 +257,14 @@ extern "C" cds_status cds_tiff_to_packbits(const uint8_t *file, int64_t len, uin
         std::string err;
         cds_status s = tiff_parse(file, (size_t) len, info, nullptr, nullptr, err);
         if (s != CDS_OK) { set_tls_error("cds_tiff_to_packbits: " + err); return s; }
-        std::vector<uint8_t> rgb((size_t) info.width * info.height * 3);
+        // PackBits shrinks a run of 128 bytes to 2: an image that cannot fit `capacity` even then is refused before anything of the
+        // size the FILE states is allocated (a corrupted size tag must not become a terabyte request)
+        const uint64_t rgb_bytes = (uint64_t) info.width * (uint64_t) info.height * 3;
+        if (capacity < 0 || rgb_bytes / 64 > (uint64_t) capacity) {
+            set_tls_error("cds_tiff_to_packbits: the output buffer cannot hold an image of the size the file states");
+            return CDS_ERR_BAD_ARG;
+        }
+        std::vector<uint8_t> rgb((size_t) rgb_bytes);
         s = tiff_decode_host(file, (size_t) len, info.width, info.height, rgb.data(), err);
         if (s != CDS_OK) { set_tls_error("cds_tiff_to_packbits: " + err); return s; }
         return cds_tiff_encode_rgb(rgb.data(), info.width, info.height, 8, 32773, out, capacity, out_len);
@@ -369,6 +376,8 @@ extern "C" cds_status cds_zip_index(const uint8_t *archive, int64_t len, cds_zip
             if (p + 46 + nlen > (uint64_t) len || lho + 30 > (uint64_t) len || le32(archive + lho) != 0x04034b50u) { set_tls_error("cds_zip_index: corrupt entry"); return CDS_ERR_BAD_ARG; }
             const uint64_t data = lho + 30 + le16(archive + lho + 26) + le16(archive + lho + 28);
             if (data + csize > (uint64_t) len) { set_tls_error("cds_zip_index: entry data outside the archive"); return CDS_ERR_BAD_ARG; }
+            // a stored entry IS the file (callers point into the archive with `size`): its two sizes must agree
+            if (method == 0 && csize != usize) { set_tls_error("cds_zip_index: stored entry whose sizes differ"); return CDS_ERR_BAD_ARG; }
             if (n < capacity) {
                 cds_zip_entry &z = entries[n];
                 z.name_offset = (int64_t) (p + 46); z.name_len = (int32_t) nlen; z.method = (int32_t) method;
@@ -407,7 +416,12 @@ extern "C" int64_t cds_zip_find(const uint8_t *archive, const cds_zip_entry *ent
 extern "C" cds_status cds_zip_read(const uint8_t *archive, int64_t len, const cds_zip_entry *entry, uint8_t *out, int64_t capacity)
 {
     return cds::abi_guard("cds_zip_read", [&]() -> cds_status {
-        if (!archive || !entry || !out || entry->data_offset < 0 || entry->data_offset + entry->compressed_size > len) { set_tls_error("cds_zip_read: bad argument"); return CDS_ERR_BAD_ARG; }
+        if (!archive || !entry || !out || len < 0 || entry->data_offset < 0 || entry->compressed_size < 0 || entry->size < 0 ||
+            entry->data_offset > len || entry->compressed_size > len - entry->data_offset || entry->size > (int64_t) 0xFFFFFFFFll ||
+            (entry->method == 0 && entry->size != entry->compressed_size)) {
+            set_tls_error("cds_zip_read: bad argument");
+            return CDS_ERR_BAD_ARG;
+        }
         if (capacity < entry->size) { set_tls_error("cds_zip_read: capacity below the entry's size"); return CDS_ERR_CAPACITY; }
         const uint8_t *src = archive + entry->data_offset;
         if (entry->method == 0) {
