@@ -303,7 +303,7 @@ def shape_roofline(kernel_pairs_s, bytes_per_pair, peak, peak_src):
     return out
 
 
-def shape_config2_mix(ctx, topk, n_masks, t_first, t_limit=4096):
+def shape_config2_mix(ctx, topk, n_masks, t_first, t_limit=4096, inflate_windows=(0,)):
     """BASELINE configs[2] with its REAL pair mix: the pairs are the top-300 isMatch targets of every mask from the pixel-match
     step this bench has just run (about 8 pairs per target, not 32), restricted to the first `t_limit` targets of the shard so
     that targets + gradients fit comfortably in pinned host memory.  End to end through cds_shape_score_pairs(_tiff) with host buffers."""
@@ -366,12 +366,56 @@ def shape_config2_mix(ctx, topk, n_masks, t_first, t_limit=4096):
         best_t = dt if best_t is None else min(best_t, dt)
     st_t = ctx.last_stats()
     same = bool(np.array_equal(gap2, gap) and np.array_equal(he2, he) and np.array_equal(mir2, mir))
+    # the same pairs with BOTH inputs as files, the way gradientScores meets them on disk: targets as PackBits TIFF, gradients as 16-bit
+    # PNG.  Writing PNG files is host work outside the timed region (70 ms each), so only P distinct gradient files are written and target
+    # i gets file i % P; the scores are checked against the pixel call on the targets below P and between the two inflate paths on all.
+    # Gradient streams are inflated on the device (one warp per stream) or, for comparison, by host threads (zlib).
+    n_f, P = min(n_t, 4096), min(n_t, 512)
+    kf = pt < n_f
+    files_leg = None
+    if kf.sum() >= 64:
+        with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+            pngs = list(ex.map(lambda i: capi.png_encode_gray16(grads[i], 2), range(P)))
+        poff = np.zeros(n_f + 1, np.int64)
+        np.cumsum([len(pngs[i % P]) for i in range(n_f)], out=poff[1:])
+        p_arr, p_ptr = ctx.host_alloc(int(poff[-1]) + 64)
+        for i in range(n_f):
+            p_arr[poff[i]:poff[i + 1]] = np.frombuffer(pngs[i % P], np.uint8)
+        del pngs
+        tsub = (f_arr[:int(foff[n_f])], foff[:n_f + 1])
+        psub = (p_arr[:int(poff[-1])], poff)
+        in_p = pt[kf] < P
+        files_leg = {"pairs": int(kf.sum()), "targets": int(n_f), "distinct_gradient_files": int(P), "png_bytes_mean": float(poff[-1]) / n_f,
+                     "tiff_bytes_mean": float(foff[n_f]) / n_f}
+        res = {}
+        legs = [(1, w, "device_inflate" if w == 0 else "device_inflate_window_%d" % w) for w in inflate_windows] + [(0, 0, "host_inflate")]
+        for mode, window, key in legs:
+            ctx.set_option("device_inflate", mode)
+            ctx.set_option("shape_inflate_window", window)
+            sms.score_pairs_files(tsub, psub, None, pm[kf][:64], pt[kf][:64])
+            best_f = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                res[key] = sms.score_pairs_files(tsub, psub, None, pm[kf], pt[kf])
+                dt = time.perf_counter() - t0
+                best_f = dt if best_f is None else min(best_f, dt)
+            st_f = ctx.last_stats()
+            gap3, he3, mir3 = res[key]
+            files_leg[key] = {"value": int(kf.sum()) / best_f, "unit": "pairs/s", "ms": best_f * 1e3, "h2d_bytes": int(st_f["h2d_bytes"]),
+                              "targets_per_s": int(len(np.unique(pt[kf]))) / best_f, "host_inflate_fallbacks": int(st_f["host_inflate_fallbacks"]),
+                              "equals_pixel_call_below_P": bool(np.array_equal(gap3[in_p], gap[kf][in_p]) and np.array_equal(he3[in_p], he[kf][in_p])
+                                                                and np.array_equal(mir3[in_p], mir[kf][in_p]))}
+        files_leg["inflate_paths_agree"] = bool(all(np.array_equal(x, y) for x, y in zip(res["device_inflate"], res["host_inflate"])))
+        ctx.set_option("device_inflate", 1)
+        ctx.set_option("shape_inflate_window", 0)
+        ctx.host_free(p_ptr)
     n_active = int(len(np.unique(pt)))
     out = {"pairs": int(n_pairs), "distinct_targets": n_active, "masks": n_masks,
            "e2e": {"value": n_pairs / best, "unit": "pairs/s", "ms": best * 1e3, "h2d_bytes": int(st["h2d_bytes"]),
                    "h2d_gbs": st["h2d_bytes"] / best / 1e9},
            "e2e_tiff": {"value": n_pairs / best_t, "unit": "pairs/s", "ms": best_t * 1e3, "h2d_bytes": int(st_t["h2d_bytes"]),
                         "h2d_gbs": st_t["h2d_bytes"] / best_t / 1e9, "equals_pixel_call": same},
+           "e2e_files": files_leg,
            "pair_kernel_ms": st["match_kernel_ms"], "pair_kernel_pairs_per_s": n_pairs / (st["match_kernel_ms"] * 1e-3),
            "mask_prep_ms_per_mask": prep_s / n_masks * 1e3, "mask_prep_first_use_ms_per_mask": prep_first_s / n_masks * 1e3,
            "mask_prep_h2d_bytes_per_mask": 3 * W * H,

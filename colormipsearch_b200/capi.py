@@ -46,7 +46,7 @@ class PixParams(C.Structure):
 class SearchStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("match_kernel_launches", C.c_int64), ("match_kernel_ms", C.c_double),
                 ("total_device_ms", C.c_double), ("comparisons", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("match_kernel", C.c_int64), ("chunked", C.c_int64)]
+                ("match_kernel", C.c_int64), ("chunked", C.c_int64), ("host_inflate_fallbacks", C.c_int64)]
 
 
 class TiffInfo(C.Structure):
@@ -131,6 +131,7 @@ SIGNATURES = {
     "cds_tiff_to_packbits": (C.c_int32, [_vp, C.c_int64, _vp, C.c_int64, _i64p]),
     "cds_png_probe": (C.c_int32, [_vp, C.c_int64, C.POINTER(PngInfo)]),
     "cds_png_decode_gray16": (C.c_int32, [_vp, _vp, _i64p, C.c_int64, C.c_int32, C.c_int32, _vp]),
+    "cds_debug_inflate_host": (C.c_int32, [_vp, C.c_int64, _vp, C.c_int64, _i64p, _i32p]),
     "cds_png_encode_bound": (C.c_int64, [C.c_int32, C.c_int32]),
     "cds_png_encode_gray16": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int64, _i64p]),
     "cds_zip_index": (C.c_int32, [_vp, C.c_int64, C.POINTER(ZipEntry), C.c_int64, _i64p]),
@@ -772,6 +773,16 @@ def tiff_to_packbits(data):
     n = C.c_int64()
     _check(lib().cds_tiff_to_packbits(_ptr(buf), len(buf), _ptr(out), cap, C.byref(n)))
     return out[: n.value].tobytes()
+
+
+def debug_inflate_host(data, capacity):
+    """raw DEFLATE data through the device's decoder built for one lane -> (bytes produced so far, reason: 0 = inflated)"""
+    buf = np.frombuffer(bytes(data) + b"\0", np.uint8)      # never an empty array
+    out = np.empty(max(1, capacity), np.uint8)
+    n = C.c_int64()
+    why = C.c_int32()
+    lib().cds_debug_inflate_host(_ptr(buf), len(data), _ptr(out), int(capacity), C.byref(n), C.byref(why))
+    return out[: n.value].tobytes(), int(why.value)
 
 
 def png_probe(data):

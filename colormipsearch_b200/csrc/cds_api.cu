@@ -348,6 +348,16 @@ extern "C" cds_status cds_ctx_set_option(cds_ctx *ctx, const char *name, int64_t
         if (std::strcmp(name, "cand_l2_hint") == 0) { cand_tuning().l2_hint = value != 0; return CDS_OK; }
         if (std::strcmp(name, "cand_warps") == 0) { cand_tuning().warps = (int) value; return CDS_OK; }
         if (std::strcmp(name, "occupancy_kernel") == 0) { occupancy_kernel_version() = value != 0; return CDS_OK; }
+        if (std::strcmp(name, "shape_inflate_window") == 0) {
+            if (value < 0 || value > 8192) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: shape_inflate_window must be 0..8192");
+            ctx->shape_inflate_window = value;
+            return CDS_OK;
+        }
+        if (std::strcmp(name, "device_inflate") == 0) {
+            if (value < 0 || value > 2) return ctx->fail(CDS_ERR_BAD_ARG, "cds_ctx_set_option: device_inflate must be 0..2");
+            ctx->device_inflate = (int) value;
+            return CDS_OK;
+        }
         if (std::strcmp(name, "wide_lists") == 0) { ctx->wide_lists = value != 0; return CDS_OK; }
         if (std::strcmp(name, "cand_stages") == 0) { cand_tuning().stages = (int) value; return CDS_OK; }
         if (std::strcmp(name, "cand_max_rows") == 0) { cand_tuning().max_rows = (int) value; return CDS_OK; }

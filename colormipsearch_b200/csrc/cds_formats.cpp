@@ -19,6 +19,9 @@
 
 #include <zlib.h>
 
+#include <memory>
+
+#include "cds_inflate.h"
 #include "cds_runtime.h"
 #include "cds_tiff.h"
 
@@ -235,7 +238,51 @@ cds_status png_inflate(const uint8_t *file, size_t len, int width, int height, i
     return CDS_OK;
 }
 
+// the IDAT payloads of a PNG, back to back: its zlib stream, for the device inflate (cds_inflate.cu)
+cds_status png_collect_idat(const uint8_t *file, size_t len, int W, int H, uint8_t *dst, size_t cap, size_t base, size_t *used, InflateJob *job,
+                            uint8_t *bps, std::string &err)
+{
+    cds_png_info info;
+    std::vector<std::pair<size_t, size_t>> idat;
+    cds_status s = png_parse(file, len, info, &idat, err);
+    if (s != CDS_OK) return s;
+    if (!info.decodable) { err = "PNG is not a non-interlaced 8- or 16-bit grayscale image"; return CDS_ERR_UNSUPPORTED; }
+    if (info.width != W || info.height != H) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "Invalid image size - PNG image size (%d, %d) must match (%d, %d)", info.width, info.height, W, H);
+        err = buf;
+        return CDS_ERR_SIZE_MISMATCH;
+    }
+    size_t total = 0;
+    for (const auto &c : idat) total += c.second;
+    if (total > cap || base + total > 0xFFFFFFFFull) { err = "PNG: internal staging too small"; return CDS_ERR_CAPACITY; }
+    size_t o = 0;
+    for (const auto &c : idat) { memcpy(dst + o, file + c.first, c.second); o += c.second; }
+    *bps = (uint8_t) (info.bit_depth / 8);
+    *used = total;
+    // zlib header (RFC 1950): deflate, window <= 32 kB, no preset dictionary, check bits; anything else goes to the host path (src_len 0)
+    const bool hdr_ok = total >= 2 && (dst[0] & 0x0F) == 8 && (dst[0] >> 4) <= 7 && (dst[1] & 0x20) == 0 && (((uint32_t) dst[0] << 8) | dst[1]) % 31 == 0;
+    job->src = (uint32_t) (base + 2);
+    job->src_len = hdr_ok ? (uint32_t) (total - 2) : 0u;
+    return CDS_OK;
+}
+
 }  // namespace cds
+
+// raw DEFLATE through the decoder the device runs, built for one lane (cds_inflate.h): what the CPU tests pin against zlib
+extern "C" cds_status cds_debug_inflate_host(const uint8_t *in, int64_t len, uint8_t *out, int64_t capacity, int64_t *out_len, int32_t *reason)
+{
+    return cds::abi_guard("cds_debug_inflate_host", [&]() -> cds_status {
+        if (!in || len < 0 || capacity < 0 || (capacity > 0 && !out) || !out_len) { set_tls_error("cds_debug_inflate_host: bad argument"); return CDS_ERR_BAD_ARG; }
+        std::unique_ptr<cds::InflateTables> t(new cds::InflateTables);
+        size_t produced = 0;
+        const int st = cds::inflate_stream<1>(in, (size_t) len, out, (size_t) capacity, *t, 0, &produced);
+        *out_len = (int64_t) produced;
+        if (reason) *reason = st;
+        if (st != cds::kInfOk) { set_tls_error("cds_debug_inflate_host: stream refused (reason " + std::to_string(st) + ")"); return st == cds::kInfOutputFull ? CDS_ERR_CAPACITY : CDS_ERR_BAD_ARG; }
+        return CDS_OK;
+    });
+}
 
 // ------------------------------------------------------------------------------------------------------------------ C ABI (host only)
 extern "C" cds_status cds_tiff_decode_rgb_host(const uint8_t *file, int64_t len, int32_t width, int32_t height, uint8_t *out_rgb)

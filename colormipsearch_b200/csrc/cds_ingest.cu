@@ -908,6 +908,7 @@ extern "C" cds_status cds_png_decode_gray16(cds_ctx *ctx, const uint8_t *blob, c
         if (n < 0 || width <= 0 || height <= 0 || width > 16384 || height > 16384) return ctx->fail(CDS_ERR_BAD_ARG, "cds_png_decode_gray16: bad size");
         if (n == 0) return CDS_OK;
         if (!blob || !offsets || !out) return ctx->fail(CDS_ERR_BAD_ARG, "cds_png_decode_gray16: NULL argument");
+        ctx->stats = cds_search_stats{};
         DevState &ds = ctx->devs[0];
         CDS_CUDA(ctx, cudaSetDevice(ds.dev));
         const size_t stride = ((size_t) height * (1 + (size_t) width * 2) + 15) / 16 * 16;
@@ -922,11 +923,65 @@ extern "C" cds_status cds_png_decode_gray16(cds_ctx *ctx, const uint8_t *blob, c
         CDS_CUDA(ctx, ds.pool.alloc((void **) &d_f, (size_t) chunk * stride));
         CDS_CUDA(ctx, ds.pool.alloc((void **) &d_bps, (size_t) chunk));
         CDS_CUDA(ctx, ds.pool.alloc((void **) &d_out, (size_t) chunk * px * sizeof(uint16_t)));
+        // device inflate (cds_inflate.cu): the files' zlib streams are uploaded as stored; the pinned staging area (sized for scanlines)
+        // holds {jobs, bytes per sample, streams, statuses} with room to spare
+        uint8_t *d_z = nullptr;
+        int32_t *d_stat = nullptr;
+        const size_t z_head = ((size_t) chunk * (sizeof(InflateJob) + 1) + 15) / 16 * 16, z_stat = (size_t) chunk * sizeof(int32_t);
+        const size_t z_cap = (size_t) chunk * (stride + 16) - z_head - z_stat;
+        auto release_z = [&]() { cudaStreamSynchronize(ds.stream); ds.pool.free(d_z); ds.pool.free(d_stat); };
+        Guard guard_z{release_z};
+        if (ctx->device_inflate) {
+            CDS_CUDA(ctx, ds.pool.alloc((void **) &d_z, z_head + z_cap));
+            CDS_CUDA(ctx, ds.pool.alloc((void **) &d_stat, z_stat));
+        }
         for (int64_t i0 = 0; i0 < n; i0 += chunk) {
             const int64_t cnt = std::min(chunk, n - i0);
-            CDS_TRY(png_inflate_many(ctx, "cds_png_decode_gray16", blob, offsets + i0, nullptr, cnt, width, height, h_f, stride, h_bps));
-            CDS_CUDA(ctx, cudaMemcpyAsync(d_f, h_f, (size_t) cnt * stride, cudaMemcpyHostToDevice, ds.stream));
-            CDS_CUDA(ctx, cudaMemcpyAsync(d_bps, h_bps, (size_t) cnt, cudaMemcpyHostToDevice, ds.stream));
+            bool inflated = false;
+            if (ctx->device_inflate) {
+                InflateJob *h_jobs = (InflateJob *) h_f;
+                uint8_t *h_b = h_f + (size_t) chunk * sizeof(InflateJob), *h_z = h_f + z_head;
+                int32_t *h_stat = (int32_t *) (h_f + z_head + z_cap);
+                size_t zo = 0;
+                bool staged = true;
+                for (int64_t i = 0; i < cnt && staged; i++) {
+                    const int64_t a = offsets[i0 + i], b = offsets[i0 + i + 1];
+                    std::string err;
+                    size_t used = 0;
+                    if (a < 0 || b < a) return ctx->fail(CDS_ERR_BAD_ARG, "cds_png_decode_gray16: offsets must be non-decreasing");
+                    const cds_status ps = png_collect_idat(blob + a, (size_t) (b - a), width, height, h_z + zo, z_cap - zo, z_head + zo, &used, &h_jobs[i], &h_b[i], err);
+                    if (ps == CDS_ERR_CAPACITY) { staged = false; break; }      // streams larger than their images: the host path takes the chunk
+                    if (ps != CDS_OK) return ctx->fail(ps, "cds_png_decode_gray16: file " + std::to_string(i0 + i) + ": " + err);
+                    zo += used;
+                }
+                if (staged) {
+                    CDS_CUDA(ctx, cudaMemcpyAsync(d_z, h_f, z_head + zo, cudaMemcpyHostToDevice, ds.stream));
+                    const uint8_t *d_b = d_z + (size_t) chunk * sizeof(InflateJob);
+                    launch_png_inflate(d_z, (const InflateJob *) d_z, cnt, d_f, stride, d_b, width, height, d_stat, ds.stream);
+                    CDS_CUDA(ctx, cudaMemcpyAsync(h_stat, d_stat, (size_t) cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.stream));
+                    CDS_CUDA(ctx, cudaMemcpyAsync(d_bps, d_b, (size_t) cnt, cudaMemcpyDeviceToDevice, ds.stream));
+                    CDS_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+                    ctx->stats.kernel_launches++;
+                    // refused streams: zlib on the host decides, and its scanlines replace the device's
+                    std::vector<uint8_t> lines;
+                    for (int64_t i = 0; i < cnt; i++) {
+                        if (h_stat[i] == 0 && !(ctx->device_inflate == 2 && (i & 1))) continue;
+                        lines.resize(stride);
+                        std::string err;
+                        int depth = 16;
+                        const cds_status ps = png_inflate(blob + offsets[i0 + i], (size_t) (offsets[i0 + i + 1] - offsets[i0 + i]), width, height, &depth, lines.data(), stride, err);
+                        if (ps != CDS_OK) return ctx->fail(ps, "cds_png_decode_gray16: file " + std::to_string(i0 + i) + ": " + err);
+                        CDS_CUDA(ctx, cudaMemcpy(d_f + (size_t) i * stride, lines.data(), stride, cudaMemcpyHostToDevice));
+                        ctx->stats.host_inflate_fallbacks++;
+                    }
+                    inflated = true;
+                }
+            }
+            if (!inflated) {
+                CDS_TRY(png_inflate_many(ctx, "cds_png_decode_gray16", blob, offsets + i0, nullptr, cnt, width, height, h_f, stride, h_bps));
+                CDS_CUDA(ctx, cudaMemcpyAsync(d_f, h_f, (size_t) cnt * stride, cudaMemcpyHostToDevice, ds.stream));
+                CDS_CUDA(ctx, cudaMemcpyAsync(d_bps, h_bps, (size_t) cnt, cudaMemcpyHostToDevice, ds.stream));
+            }
             launch_png_unfilter(d_f, stride, d_bps, cnt, width, height, d_out, ds.stream);
             CDS_CUDA(ctx, cudaGetLastError());
             CDS_CUDA(ctx, cudaMemcpyAsync(out + (size_t) i0 * px, d_out, (size_t) cnt * px * sizeof(uint16_t), cudaMemcpyDeviceToHost, ds.stream));

@@ -112,6 +112,9 @@ struct cds_ctx {
     mutable std::recursive_mutex mu;
     mutable std::string err;
     cds_search_stats stats{};
+    int64_t shape_inflate_window = 0;   // cds_ctx_set_option("shape_inflate_window"): most targets per window of cds_shape_score_pairs_files with device inflate (0 = 2048)
+    int device_inflate = 1;       // cds_ctx_set_option("device_inflate"): 1 = gradient PNG files are inflated on the device (cds_inflate.cu), 0 = by host threads,
+                                  // 2 = on the device, and every odd image is treated as refused (exercises the zlib fallback in tests)
     bool wide_lists = false;   // cds_ctx_set_option("wide_lists"): mask sets prepared from now on get interval-carrying word lists even when palettes would do
     int match_kernel = 0;      // cds_ctx_set_option("match_kernel"): 0 automatic, 1 candidate, 2 band, 3 gather
     int resident_occupancy = 1;   // cds_ctx_set_option("resident_occupancy"): 0 = always build occupancy bitmaps per target chunk

@@ -1029,6 +1029,10 @@ extern "C" cds_status cds_debug_slice_numbers(cds_ctx *ctx, const uint8_t *rgb, 
 
 namespace {
 
+// Gradient PNG files inflated on the device, one warp per stream: a stream takes tens of milliseconds whatever else runs, so the rate is
+// the number of streams in flight over that latency -- windows are as large as the call's size allows (2 048 targets: ~20 GB of
+// window buffers per device; measured: profiles/r02_shape_files.txt)
+constexpr int64_t kShapeWindowInflate = 2048;
 constexpr int64_t kShapeWindowSmall = 32, kShapeWindowLarge = 128;      // targets per window: large calls use large windows (pair-kernel launches that fill the GPU)
 
 // What one device holds while it works through its windows.
@@ -1040,6 +1044,9 @@ struct ShapeDevWork {
     uint8_t *d_comp = nullptr;
     TiffStrip *d_strips = nullptr;
     uint8_t *d_pngraw = nullptr, *d_bps = nullptr;
+    uint8_t *d_zstage = nullptr;            // device inflate: {jobs, bytes per sample, the files' zlib streams} of one window, as staged by the host
+    int32_t *d_zstat = nullptr;             // ... per image: 0 or why the device refused the stream
+    uint8_t *d_zfallback = nullptr;         // ... one image's scanlines inflated by the host after a refusal (+ its bytes per sample)
     int32_t *d_pm = nullptr, *d_ps = nullptr;
     long long *d_gap = nullptr, *d_he = nullptr;
     uint8_t *d_mir = nullptr;
@@ -1101,7 +1108,15 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
     const size_t px = (size_t) W * H, bytes = px * 3;
     const size_t bm_words = (size_t) H * bpitch;
     const int D = (int) ctx->devs.size();
-    const int64_t win = (int64_t) active.size() >= 4 * kShapeWindowLarge * D ? kShapeWindowLarge : kShapeWindowSmall;
+    const bool dev_inflate = png_blob != nullptr && png_offsets != nullptr && ctx->device_inflate != 0;
+    int64_t win = (int64_t) active.size() >= 4 * kShapeWindowLarge * D ? kShapeWindowLarge : kShapeWindowSmall;
+    if (dev_inflate) {
+        // the largest of 2048, 1024, 512, 256 that still gives every device two windows (so that uploads overlap the scoring)
+        int64_t cap = ctx->shape_inflate_window > 0 ? ctx->shape_inflate_window : kShapeWindowInflate;
+        while (cap > 256 && (uint64_t) cap * bytes > 0xFFFFFFFFull) cap /= 2;      // the strip table addresses a window's pixels with 32 bits
+        for (int64_t w = cap; w >= 256; w /= 2)
+            if ((int64_t) active.size() * 4 >= 7 * w * D) { win = w; break; }      // "two": the second may be three quarters full
+    }
     const int64_t n_windows = ((int64_t) active.size() + win - 1) / win;
     const int used = (int) std::min<int64_t>(D, n_windows);
     const DiscSpec disc10 = make_disc(10);
@@ -1137,7 +1152,23 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
     }
     // gradient images as PNG files: inflated scanlines of a window go through two pinned host slots per device
     const size_t png_stride = ((size_t) H * (1 + (size_t) W * 2) + 15) / 16 * 16;
-    const size_t png_slot_bytes = (size_t) win * png_stride + (size_t) win;
+    // device inflate: a slot holds the window's jobs, bytes per sample and zlib streams (the files are an upper bound of those), then
+    // the statuses that come back; host inflate: the inflated scanlines
+    const size_t z_head = ((size_t) win * (sizeof(InflateJob) + 1) + 15) / 16 * 16;
+    size_t z_payload = 0;
+    if (dev_inflate) {
+        for (int64_t i = 0; i <= n_targets; i++)
+            if (png_offsets[i] < 0 || (i > 0 && png_offsets[i] < png_offsets[i - 1])) return ctx->fail(CDS_ERR_BAD_ARG, "cds_shape_score_pairs_files: offsets must be non-decreasing");
+        for (int64_t w = 0; w < n_windows; w++) {
+            size_t sum = 0;
+            for (int64_t a = w * win; a < std::min<int64_t>((int64_t) active.size(), (w + 1) * win); a++) sum += (size_t) (png_offsets[active[a] + 1] - png_offsets[active[a]]);
+            z_payload = std::max(z_payload, sum);
+        }
+        z_payload = (z_payload + 15) / 16 * 16;
+        if (z_head + z_payload > 0xFFFFFFF0ull) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_shape_score_pairs_files: gradient files of one window exceed 4 GB");
+    }
+    const size_t z_stat = ((size_t) win * sizeof(int32_t) + 15) / 16 * 16;
+    const size_t png_slot_bytes = dev_inflate ? z_head + z_payload + z_stat : (size_t) win * png_stride + (size_t) win;
     for (int d = 0; d < used; d++) {
         DevState &ds = ctx->devs[d];
         ShapeDevWork &wk = work[d];
@@ -1173,6 +1204,11 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
         if (from_png) {
             SH_CUDA(ctx, g.alloc((void **) &wk.d_pngraw, (size_t) win * png_stride));
             SH_CUDA(ctx, g.alloc((void **) &wk.d_bps, (size_t) win));
+            if (dev_inflate) {
+                SH_CUDA(ctx, g.alloc((void **) &wk.d_zstage, z_head + z_payload));
+                SH_CUDA(ctx, g.alloc((void **) &wk.d_zstat, z_stat));
+                SH_CUDA(ctx, g.alloc((void **) &wk.d_zfallback, png_stride + 16));
+            }
             if (ds.h_pinned2_bytes < 2 * png_slot_bytes) {
                 SH_CUDA(ctx, cudaStreamSynchronize(ds.copy_stream));
                 if (ds.h_pinned2) { cudaFreeHost(ds.h_pinned2); ds.h_pinned2 = nullptr; ds.h_pinned2_bytes = 0; }
@@ -1242,7 +1278,31 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
             a = e;
         }
         if (j >= 2 && (from_files || from_png)) SH_CUDA(ctx, cudaEventSynchronize(ds.up_done[slot]));      // the slot's previous tables / scanlines have left the host
-        if (from_png) {
+        if (dev_inflate) {
+            // the window's gradient files cross PCIe as stored: the host only strings every file's IDAT payloads together
+            uint8_t *h_slot = (uint8_t *) ds.h_pinned2 + (size_t) slot * png_slot_bytes;
+            InflateJob *h_jobs = (InflateJob *) h_slot;
+            uint8_t *h_bps = h_slot + (size_t) win * sizeof(InflateJob), *h_z = h_slot + z_head;
+            const int64_t cnt = a1 - a0;
+            size_t zo = 0;
+            for (int64_t i = 0; i < cnt; i++) {
+                const int64_t f = active[a0 + i];
+                std::string err;
+                size_t used_bytes = 0;
+                cds_status ps = png_collect_idat(png_blob + png_offsets[f], (size_t) (png_offsets[f + 1] - png_offsets[f]), W, H, h_z + zo, z_payload - zo,
+                                                 z_head + zo, &used_bytes, &h_jobs[i], &h_bps[i], err);
+                if (ps != CDS_OK) return ctx->fail(ps, "cds_shape_score_pairs_files: file " + std::to_string(f) + ": " + err);
+                zo += used_bytes;
+            }
+            SH_CUDA(ctx, cudaMemcpyAsync(wk.d_zstage, h_slot, z_head + zo, cudaMemcpyHostToDevice, ds.copy_stream));
+            ctx->stats.h2d_bytes += (int64_t) (z_head + zo);
+            const uint8_t *d_bps_w = wk.d_zstage + (size_t) win * sizeof(InflateJob);
+            launch_png_inflate(wk.d_zstage, (const InflateJob *) wk.d_zstage, cnt, wk.d_pngraw, png_stride, d_bps_w, W, H, wk.d_zstat, ds.copy_stream);
+            SH_CUDA(ctx, cudaMemcpyAsync(h_slot + z_head + z_payload, wk.d_zstat, (size_t) cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ds.copy_stream));
+            launch_png_unfilter(wk.d_pngraw, png_stride, d_bps_w, cnt, W, H, wk.d_grad[slot], ds.copy_stream);
+            ctx->stats.kernel_launches += 2;
+            SH_CUDA(ctx, cudaGetLastError());
+        } else if (from_png) {
             // inflate this window's gradient files on host threads (the devices are busy with earlier windows meanwhile)
             uint8_t *h_f = (uint8_t *) ds.h_pinned2 + (size_t) slot * png_slot_bytes, *h_bps = h_f + (size_t) win * png_stride;
             const int64_t cnt = a1 - a0;
@@ -1284,6 +1344,27 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
             st = ctx->check(cudaSetDevice(ds.dev), "cudaSetDevice");
             if (st == CDS_OK) st = ctx->check(cudaStreamWaitEvent(ds.stream, ds.up_done[slot], 0), "wait");
             if (st != CDS_OK) break;
+            if (dev_inflate) {
+                // a stream the device's decoder refused is inflated by zlib on the host (which also decides whether the file is at fault);
+                // its scanlines take the place of the device's on the main stream, before the window is scored
+                st = ctx->check(cudaEventSynchronize(ds.up_done[slot]), "gradient inflate");
+                const int32_t *h_stat = (const int32_t *) ((const uint8_t *) ds.h_pinned2 + (size_t) slot * png_slot_bytes + z_head + z_payload);
+                for (int64_t i = 0; i < cnt && st == CDS_OK; i++) {
+                    if (h_stat[i] == 0 && !(ctx->device_inflate == 2 && (i & 1))) continue;
+                    const int64_t f = active[w * win + i];
+                    std::vector<uint8_t> lines(png_stride + 16);
+                    std::string err;
+                    int depth = 16;
+                    const cds_status ps = png_inflate(png_blob + png_offsets[f], (size_t) (png_offsets[f + 1] - png_offsets[f]), W, H, &depth, lines.data(), png_stride, err);
+                    if (ps != CDS_OK) { st = ctx->fail(ps, "cds_shape_score_pairs_files: file " + std::to_string(f) + ": " + err); break; }
+                    lines[png_stride] = (uint8_t) (depth / 8);
+                    st = ctx->check(cudaMemcpyAsync(wk.d_zfallback, lines.data(), png_stride + 16, cudaMemcpyHostToDevice, ds.stream), "fallback scanlines H2D");
+                    if (st == CDS_OK) launch_png_unfilter(wk.d_zfallback, png_stride, wk.d_zfallback + png_stride, 1, W, H, wk.d_grad[slot] + (size_t) i * px, ds.stream);
+                    if (st == CDS_OK) st = ctx->check(cudaStreamSynchronize(ds.stream), "fallback unfilter");      // `lines` is pageable and about to go
+                    ctx->stats.host_inflate_fallbacks++;
+                }
+                if (st != CDS_OK) break;
+            }
             if (zgap_rgb) {
                 target_planes_kernel<<<dim3(H, (unsigned) cnt), 256, 0, ds.stream>>>(wk.d_t[slot], wk.d_z[slot], W, H, sms->rects, sms->query_threshold, bpitch,
                                                                                     ds.d_slice_tab, wk.d_zslice, wk.d_tsig);

@@ -48,6 +48,15 @@ cds_status png_inflate(const uint8_t *file, size_t len, int width, int height, i
 // out = uint16[n][height][width]
 cds_status png_inflate_many(cds_ctx *ctx, const char *who, const uint8_t *blob, const int64_t *offsets, const int64_t *which, int64_t cnt,
                             int W, int H, uint8_t *h_filtered, size_t stride, uint8_t *bps);
+// Device inflate (cds_inflate.cu): job i = the deflate data of image i (zlib header skipped) inside the uploaded byte range; out as
+// for png_inflate_many; status[i] = 0, or why the stream was refused (InflateStatus, 16 = not exactly the image's bytes).
+struct InflateJob { uint32_t src, src_len; };
+void launch_png_inflate(const uint8_t *comp, const InflateJob *jobs, int64_t n, uint8_t *out, size_t stride, const uint8_t *bytes_per_sample,
+                        int W, int H, int32_t *status, cudaStream_t s);
+// Host half of it: checks file `file` (a W x H grayscale PNG), appends its IDAT payloads to dst (capacity cap) and fills the job;
+// *bps = bytes per sample.  CDS_ERR_* with `err` set for a file that is no such PNG.
+cds_status png_collect_idat(const uint8_t *file, size_t len, int W, int H, uint8_t *dst, size_t cap, size_t base, size_t *used, InflateJob *job,
+                            uint8_t *bps, std::string &err);
 void launch_png_unfilter(const uint8_t *filtered, size_t stride, const uint8_t *bytes_per_sample, int64_t n, int width, int height,
                          uint16_t *out, cudaStream_t s);
 

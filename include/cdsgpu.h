@@ -102,6 +102,12 @@ int32_t    cds_abi_version(void);
  * 0 = decode to RGB pixels first, then encode (the two-kernel path, kept as a cross-check).
  * "cand_wait_mode", "cand_l2_hint", "cand_warps", "cand_stages", "cand_max_rows": tuning knobs of the candidate kernel (csrc/cds_cand.cuh),
  *   process-wide.  "occupancy_kernel": 1 (default) = the single-pass occupancy kernel for xyShift 2, 0 = the generic one (cross-check).
+ * "device_inflate": 1 (default) = cds_shape_score_pairs_files uploads the gradient PNG files as stored and inflates their zlib streams
+ *   on the device, one warp per stream (csrc/cds_inflate.h); 0 = host threads inflate them (zlib) and the scanlines are uploaded;
+ *   2 (tests) = like 1, with every odd image of a window treated as refused.  cds_png_decode_gray16 follows the same switch.
+ *   Same pixels either way: a stream the device refuses is read by zlib on the host (host_inflate_fallbacks in the stats).
+ * "shape_inflate_window": most targets per window of cds_shape_score_pairs_files when the gradient streams are inflated on the device
+ *   (0 = default 2048; halved until every device has two windows; a window's buffers are ~10 MB per target).
  * "wide_lists": 1 = mask sets prepared from now on carry each mask pixel's rank interval in the candidate kernel's lists (4 bytes per
  *   pixel and list) instead of a reference into a per-group palette (2 bytes).  0 (default): only sets with a group of more than
  *   2 047 colour classes do (brightness-scaled LM images as masks -- the reverse search); scores are the same either way.
@@ -264,6 +270,10 @@ cds_status cds_png_probe(const uint8_t *file, int64_t len, cds_png_info *info); 
  * like ImageArray.get on a ByteImageArray).  The zlib streams are inflated on host threads, the scanline filters (None, Sub, Up,
  * Average, Paeth) are undone and the samples byte-swapped on device 0. */
 cds_status cds_png_decode_gray16(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n, int32_t width, int32_t height, uint16_t *out);
+/* Host only, test hook: raw DEFLATE data (RFC 1951, no zlib header) through the decoder that the device runs one warp per stream
+ * (csrc/cds_inflate.h), built for a single lane.  *out_len = bytes produced; *reason (may be NULL) = 0 or why the stream was refused
+ * (1 input ends early, 2 bad block, 3 bad code lengths, 4 bad symbol, 5 distance before the start, 6 more than `capacity` bytes). */
+cds_status cds_debug_inflate_host(const uint8_t *in, int64_t len, uint8_t *out, int64_t capacity, int64_t *out_len, int32_t *reason);
 /* Host only: a 16-bit grayscale PNG writer for tests and the bench (filter_mode 0..4 = that filter on every row, -1 = per row the
  * filter with the smallest sum of absolute differences).  cds_png_encode_bound gives a capacity that suffices. */
 int64_t    cds_png_encode_bound(int32_t width, int32_t height);
@@ -424,6 +434,7 @@ typedef struct cds_search_stats {
     int64_t d2h_bytes;
     int64_t match_kernel;        /* which match kernel the last launch used: 1 candidate, 2 band, 3 gather */
     int64_t chunked;             /* 1 when the search walked its targets in chunks (streamed targets, or occupancy bitmaps built per chunk) */
+    int64_t host_inflate_fallbacks;   /* cds_shape_score_pairs_files: gradient PNG streams the device's inflate refused and zlib read on the host */
 } cds_search_stats;
 cds_status cds_get_last_stats(const cds_ctx *ctx, cds_search_stats *out);
 

@@ -131,6 +131,26 @@ void run_png(std::vector<uint8_t> d, Rng &r, uint64_t it)
             expect(depth == 8 || depth == 16, "png inflate: OK with an unknown bit depth", it);
         // and into a buffer that is too small for the stream
         (void) cds::png_inflate(d.data(), d.size(), wh[0], wh[1], &depth, out.data(), cap / 3, err);
+        // the device's decoder, built for one lane, on the same stream: it must agree with zlib whenever zlib accepts the stream,
+        // and end in a status otherwise
+        std::vector<uint8_t> stage(d.size() + 8);
+        size_t used = 0;
+        cds::InflateJob job{0, 0};
+        uint8_t bps = 0;
+        if (cds::png_collect_idat(d.data(), d.size(), wh[0], wh[1], stage.data(), stage.size(), 0, &used, &job, &bps, err) == CDS_OK && job.src_len) {
+            expect((size_t) job.src + job.src_len <= used, "collect_idat: job outside the staged bytes", it);
+            const size_t need = (size_t) wh[1] * (1 + (size_t) wh[0] * bps);
+            std::vector<uint8_t> mine(need + 1);
+            int64_t got = -1;
+            int32_t why = -1;
+            (void) cds_debug_inflate_host(stage.data() + job.src, job.src_len, mine.data(), (int64_t) need, &got, &why);
+            expect(got >= 0 && (size_t) got <= need, "inflate: produced count outside the buffer", it);
+            std::string e2;
+            int d2 = 0;
+            const bool zlib_ok = cds::png_inflate(d.data(), d.size(), wh[0], wh[1], &d2, out.data(), cap, e2) == CDS_OK;
+            if (zlib_ok) expect((why == 0 || why == 6) && (size_t) got == need && std::memcmp(mine.data(), out.data(), need) == 0, "inflate: differs from zlib on a stream zlib accepts", it);
+            (void) cds_debug_inflate_host(stage.data() + job.src, job.src_len, mine.data(), (int64_t) need / 3, &got, &why);
+        }
     }
 }
 

@@ -1,5 +1,6 @@
 """Device side of the PNG ingest and the file-fed shape score: the reference's own gradient PNG files through
-cds_png_decode_gray16 (host inflate, device filter reconstruction + byte swap) and through cds_shape_score_pairs_files."""
+cds_png_decode_gray16 (zlib streams inflated on the device one warp per stream -- or by host threads, "device_inflate" 0 --, device
+filter reconstruction + byte swap) and through cds_shape_score_pairs_files."""
 import os
 import struct
 import zlib
@@ -30,11 +31,71 @@ def fmt():
         return {k: z[k] for k in z.files}
 
 
-def test_reference_gradient_pngs(ctx, fmt):
+@pytest.fixture(params=[1, 0, 2], ids=["device_inflate", "host_inflate", "device_inflate_with_forced_fallbacks"])
+def inflate_mode(ctx, request):
+    ctx.set_option("device_inflate", request.param)
+    yield request.param
+    ctx.set_option("device_inflate", 1)
+
+
+def test_reference_gradient_pngs(ctx, fmt, inflate_mode):
     names = ["grad_BJD", "grad_VT016795", "grad_VT033614"]
     got = capi.png_decode_gray16(ctx, [fmt["file_" + k].tobytes() for k in names], W, H)
     for i, k in enumerate(names):
         assert np.array_equal(got[i], fmt["pixels_" + k]), k
+    assert ctx.last_stats()["host_inflate_fallbacks"] == {1: 0, 0: 0, 2: 1}[inflate_mode]
+
+
+def _png16(px, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, idat=1 << 30, wbits=15, tail=b""):
+    """a 16-bit grayscale PNG, filter 0 on every row, with the zlib stream made the way the arguments say and cut into IDAT chunks of
+    `idat` bytes; `tail` = bytes deflated after the image's own (a stream longer than the image)"""
+    raw = b"".join(b"\0" + row.astype(">u2").tobytes() for row in px) + tail
+    c = zlib.compressobj(level, zlib.DEFLATED, wbits, 9, strategy)
+    z = c.compress(raw) + c.flush()
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    body = b"".join(chunk(b"IDAT", z[i:i + idat]) for i in range(0, len(z), idat))
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", px.shape[1], px.shape[0], 16, 0, 0, 0, 0)) + body + chunk(b"IEND", b"")
+
+
+def test_png_streams_of_every_kind(ctx, inflate_mode):
+    """Stored, fixed and dynamic blocks, Huffman-only and run-length streams, small windows, streams cut into many IDAT chunks and
+    streams that go on after the image: the same pixels from the device's inflate as from zlib; damaged streams are errors in both."""
+    rng = np.random.default_rng(12)
+    Ws, Hs = 333, 61
+    px = np.zeros((Hs, Ws), np.uint16)
+    px[4:55, 10:300] = (rng.integers(0, 40, (51, 290)) * rng.integers(0, 2, (51, 290))).astype(np.uint16)
+    px[20:30, 50:250] = rng.integers(0, 65536, (10, 200))
+    files, want = [], []
+    for level in (0, 1, 6, 9):
+        for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+            files.append(_png16(px, level, strategy))
+    files.append(_png16(px, 6, idat=1))                    # one IDAT chunk per byte
+    files.append(_png16(px, 6, idat=100))
+    files.append(_png16(px, 6, wbits=9))                   # 512-byte window
+    files.append(_png16(px, 6, tail=b"more than the image holds" * 40))
+    files.append(_png16(np.zeros_like(px), 9))             # one long run
+    want = [px] * (len(files) - 1) + [np.zeros_like(px)]
+    got = capi.png_decode_gray16(ctx, files, Ws, Hs)
+    for i in range(len(files)):
+        assert np.array_equal(got[i], want[i]), i
+    if inflate_mode == 1:
+        assert ctx.last_stats()["host_inflate_fallbacks"] == 0
+    # a stream cut short, and one with a flipped bit in the middle of its Huffman data: errors that name the file (zlib has the last word)
+    good = _png16(px, 6)
+    pos = good.index(b"IDAT") + 4
+    n = struct.unpack(">I", good[pos - 8:pos - 4])[0]
+    z = good[pos:pos + n]
+
+    def rebuild(zz):
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+        return good[:pos - 8] + chunk(b"IDAT", zz) + chunk(b"IEND", b"")
+    for bad in (rebuild(z[:len(z) // 2]), rebuild(z[:2] + b"\x07" + z[3:])):
+        with pytest.raises(capi.CdsError) as e:
+            capi.png_decode_gray16(ctx, [good, bad, good], Ws, Hs)
+        assert "file 1" in str(e.value)
 
 
 def _png8(px):
@@ -67,7 +128,7 @@ def _png8(px):
     return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", Ww, Hh, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(bytes(raw))) + chunk(b"IEND", b"")
 
 
-def test_every_png_filter_and_bit_depth(ctx):
+def test_every_png_filter_and_bit_depth(ctx, inflate_mode):
     rng = np.random.default_rng(3)
     Ws, Hs = 301, 57
     px = np.zeros((Hs, Ws), np.uint16)
@@ -92,7 +153,7 @@ def test_every_png_filter_and_bit_depth(ctx):
     assert e.value.status == capi.CDS_ERR_SIZE_MISMATCH
 
 
-def test_shape_scores_from_files_golden(ctx, fixtures, fmt):
+def test_shape_scores_from_files_golden(ctx, fixtures, fmt, inflate_mode):
     """The reference's shape vectors (Shape2DMatchColorDepthSearchAlgorithmTest.java:86-132) with the inputs as FILES: targets as
     PackBits TIFF, gradients as the reference's own PNG files."""
     rects = O.label_rects(W, H)
@@ -120,6 +181,11 @@ def test_shape_scores_from_files_golden(ctx, fixtures, fmt):
     b = sms.score_pairs_files(tf, pf, None, pm, pt, has)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+    # 40 targets are two windows of 32: window 0 has 16 odd images, window 1 has 4 (of which #36 = target 36 is scored: has_variants)
+    if inflate_mode == 1:
+        assert ctx.last_stats()["host_inflate_fallbacks"] == 0
+    elif inflate_mode == 2:
+        assert ctx.last_stats()["host_inflate_fallbacks"] > 0
     bad = list(pf)
     bad[21] = b"\x89PNG\r\n\x1a\n" + b"\0" * 60
     with pytest.raises(capi.CdsError) as e:

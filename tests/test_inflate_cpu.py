@@ -1,0 +1,95 @@
+"""The DEFLATE decoder that the device runs one warp per stream (csrc/cds_inflate.h), built for a single lane on the host
+(cds_debug_inflate_host) and pinned against zlib: every block type, every zlib strategy and level, the reference's own gradient PNG
+streams, and what it says about damaged streams.  (tests/test_fuzz_cpu.py runs it on mutated PNG files under ASan.)"""
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from colormipsearch_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _deflate(data, level, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=-15, mem=9):
+    c = zlib.compressobj(level, zlib.DEFLATED, wbits, mem, strategy)
+    return c.compress(data) + c.flush()
+
+
+def _inputs():
+    rng = np.random.default_rng(1)
+    runs = np.repeat(rng.integers(0, 256, 3000, dtype=np.uint8), rng.integers(1, 300, 3000))
+    text = (b"the quick brown fox jumps over the lazy dog " * 50 + bytes(rng.integers(97, 123, 5000, dtype=np.uint8))) * 20
+    far = bytes(rng.integers(0, 256, 40000, dtype=np.uint8))
+    return {"empty": b"", "one": b"a", "period3": b"abc" * 1000, "noise": bytes(rng.integers(0, 256, 100000, dtype=np.uint8)),
+            "four_symbols": bytes(rng.integers(0, 4, 200000, dtype=np.uint8)), "runs": bytes(runs), "text": text,
+            "far_matches": far + far[5000:30000] + far[:32768]}       # distances up to the 32 kB window
+
+
+@pytest.mark.parametrize("name", list(_inputs()))
+def test_inflates_what_zlib_deflates(name):
+    data = _inputs()[name]
+    for level in (0, 1, 3, 6, 9):
+        for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+            comp = _deflate(data, level, strategy)
+            got, why = capi.debug_inflate_host(comp, len(data))
+            assert why == 0 and got == data, (level, strategy)
+            if data:
+                # one byte of room too few: the first len - 1 bytes, and reason 6
+                got, why = capi.debug_inflate_host(comp, len(data) - 1)
+                assert why == 6 and got == data[:-1], (level, strategy)
+    # small windows and little memory change the block structure
+    for wbits, mem in ((-9, 1), (-12, 4)):
+        comp = _deflate(data, 6, wbits=wbits, mem=mem)
+        got, why = capi.debug_inflate_host(comp, len(data))
+        assert why == 0 and got == data
+
+
+def _idat(png):
+    pos, out = 8, b""
+    while pos < len(png):
+        (n,) = struct.unpack(">I", png[pos:pos + 4])
+        if png[pos + 4:pos + 8] == b"IDAT":
+            out += png[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    return out
+
+
+def test_reference_gradient_streams():
+    with np.load(os.path.join(ROOT, "tests", "golden", "format_fixtures.npz")) as f:
+        for k in ("file_grad_BJD", "file_grad_VT016795", "file_grad_VT033614"):
+            z = _idat(f[k].tobytes())
+            want = zlib.decompress(z)
+            got, why = capi.debug_inflate_host(z[2:], len(want))       # past the zlib header; the Adler-32 trailer is ignored
+            assert why == 0 and got == want, k
+
+
+def test_damaged_streams_end_in_a_reason():
+    data = bytes(np.random.default_rng(2).integers(0, 16, 50000, dtype=np.uint8))
+    comp = _deflate(data, 6)
+    # cut short: reason 1 whatever the zeros that stand in for the missing bits decode to -- also when they fill the buffer
+    for cut in (1, 10, len(comp) // 2, len(comp) - 1):
+        for cap in (len(data), 1000):
+            got, why = capi.debug_inflate_host(comp[:cut], cap)
+            assert (why == 1) or (why == 6 and got == data[:cap]), (cut, cap, why)
+    assert capi.debug_inflate_host(b"", 10) == (b"", 1)
+    assert capi.debug_inflate_host(b"\x07", 10)[1] == 2                                   # block type 3
+    assert capi.debug_inflate_host(b"\x01\x05\x00\x00\x00hello", 10)[1] == 2              # stored: LEN and ~LEN disagree
+    assert capi.debug_inflate_host(b"\x01\x05\x00\xfa\xffhel", 10)[1] == 1                # stored: fewer bytes than LEN
+    assert capi.debug_inflate_host(b"\x01\x05\x00\xfa\xffhello", 10) == (b"hello", 0)
+    # a match that reaches back before the first byte: fixed block, length 3 at distance 1 with nothing written
+    bits = "1" + "10" + "0000001" + "00000"                                               # BFINAL, BTYPE 1 (low bit first), symbol 257, distance code 0
+    v = int(bits[::-1], 2)
+    assert capi.debug_inflate_host(v.to_bytes(3, "little"), 10)[1] == 5
+    # dynamic block whose code lengths over-subscribe: HLIT 0, HDIST 0, HCLEN 15 and every code-length code 1 bit long
+    bits = "1" + "0" + "1" + "00000" + "00000" + "1111" + "100" * 19                      # BFINAL=1, BTYPE=10 (LSB first: 0 then 1)
+    v = int(bits[::-1], 2)
+    assert capi.debug_inflate_host(v.to_bytes((len(bits) + 7) // 8, "little"), 10)[1] == 3
+    # random bytes: some reason, no crash, at most `capacity` bytes
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        junk = bytes(rng.integers(0, 256, int(rng.integers(1, 400)), dtype=np.uint8))
+        got, why = capi.debug_inflate_host(junk, 1000)
+        assert len(got) <= 1000 and 0 <= why <= 6
