@@ -775,13 +775,15 @@ def tiff_to_packbits(data):
     return out[: n.value].tobytes()
 
 
-def debug_inflate_host(data, capacity):
-    """raw DEFLATE data through the device's decoder built for one lane -> (bytes produced so far, reason: 0 = inflated)"""
-    buf = np.frombuffer(bytes(data) + b"\0", np.uint8)      # never an empty array
+def debug_inflate_host(data, capacity, misalign=0):
+    """raw DEFLATE data through the device's decoder built for one lane -> (bytes produced so far, reason: 0 = inflated);
+    the data starts `misalign` bytes behind an 8-byte boundary (the bit reader loads whole words from aligned data)"""
+    buf = np.zeros(len(data) + misalign + 8, np.uint64).view(np.uint8)
+    buf[misalign:misalign + len(data)] = np.frombuffer(bytes(data), np.uint8)
     out = np.empty(max(1, capacity), np.uint8)
     n = C.c_int64()
     why = C.c_int32()
-    lib().cds_debug_inflate_host(_ptr(buf), len(data), _ptr(out), int(capacity), C.byref(n), C.byref(why))
+    lib().cds_debug_inflate_host(C.c_void_p(buf.ctypes.data + misalign), len(data), _ptr(out), int(capacity), C.byref(n), C.byref(why))
     return out[: n.value].tobytes(), int(why.value)
 
 

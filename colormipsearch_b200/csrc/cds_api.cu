@@ -195,7 +195,14 @@ extern "C" cds_status cds_ctx_create(const int32_t *device_ids, int32_t n_dev, c
         for (DevState &d : ctx->devs) {
             cds_status s = ctx->check(cudaSetDevice(d.dev), "cudaSetDevice");
             if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-            if (s == CDS_OK) s = ctx->check(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            if (s == CDS_OK) {
+                // the upload stream feeds the main one (file decode, inflate): its CTAs go first when an SM has room, so that the
+                // latency-bound decoders stay resident next to the scoring kernels.  CDSGPU_COPY_PRIORITY=0 gives it the default priority.
+                static const bool high = !(std::getenv("CDSGPU_COPY_PRIORITY") && std::atoi(std::getenv("CDSGPU_COPY_PRIORITY")) == 0);
+                int lo = 0, hi = 0;
+                cudaDeviceGetStreamPriorityRange(&lo, &hi);
+                s = ctx->check(cudaStreamCreateWithPriority(&d.copy_stream, cudaStreamNonBlocking, high ? hi : lo), "cudaStreamCreate");
+            }
             for (int i = 0; i < 2 && s == CDS_OK; i++) {
                 s = ctx->check(cudaEventCreateWithFlags(&d.up_done[i], cudaEventDisableTiming), "cudaEventCreate");
                 if (s == CDS_OK) s = ctx->check(cudaEventCreateWithFlags(&d.up_free[i], cudaEventDisableTiming), "cudaEventCreate");

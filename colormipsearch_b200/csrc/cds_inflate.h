@@ -66,9 +66,15 @@ CDS_INF_HD void inf_refill(InflateBits &b)
 {
     if (b.cnt <= 32) {
         uint32_t w = 0;
+        const uint8_t *p = b.in + b.pos;
+        if (b.pos + 4 <= b.len && (reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
+            // the usual case: callers place the data on a 4-byte boundary, and the position then moves in steps of four
+            w = *reinterpret_cast<const uint32_t *>(p);            // little-endian hosts and devices only
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (b.pos + k < b.len) w |= (uint32_t) b.in[b.pos + k] << (8 * k);
+            for (int k = 0; k < 4; k++)
+                if (b.pos + k < b.len) w |= (uint32_t) p[k] << (8 * k);
+        }
         b.buf |= (uint64_t) w << b.cnt;
         b.cnt += 32;
         b.pos += 4;
@@ -306,12 +312,20 @@ CDS_INF_HD int inflate_stream(const uint8_t *in, size_t in_len, uint8_t *out, si
             if (dist <= kInfNear) {
                 // the source is among the last 8 kB: read from the ring; reads are below `op`, writes at or above it, and
                 // dist + mlen <= kInfRing keeps the two apart in the ring as well
-                const uint32_t base = (uint32_t) (op - dist);
-                for (uint32_t i = (uint32_t) lane; i < mlen; i += LANES) {
-                    const uint32_t j = dist >= mlen ? i : pow2 ? (i & (dist - 1u)) : i % dist;
-                    const uint8_t v = t.ring[(base + j) & (kInfRing - 1)];
-                    t.ring[((uint32_t) op + i) & (kInfRing - 1)] = v;
-                    dst[i] = v;
+                const uint32_t base = (uint32_t) (op - dist), top = (uint32_t) op;
+                if (dist >= mlen || pow2) {
+                    const uint32_t jm = dist >= mlen ? 0xFFFFFFFFu : dist - 1u;      // i mod dist without a division
+                    for (uint32_t i = (uint32_t) lane; i < mlen; i += LANES) {
+                        const uint8_t v = t.ring[(base + (i & jm)) & (kInfRing - 1)];
+                        t.ring[(top + i) & (kInfRing - 1)] = v;
+                        dst[i] = v;
+                    }
+                } else {
+                    for (uint32_t i = (uint32_t) lane; i < mlen; i += LANES) {
+                        const uint8_t v = t.ring[(base + i % dist) & (kInfRing - 1)];
+                        t.ring[(top + i) & (kInfRing - 1)] = v;
+                        dst[i] = v;
+                    }
                 }
                 inf_sync<LANES>();                                 // literals that follow (lane 0) reuse ring slots a slower lane may still be reading
             } else {

@@ -942,7 +942,7 @@ extern "C" cds_status cds_png_decode_gray16(cds_ctx *ctx, const uint8_t *blob, c
                 InflateJob *h_jobs = (InflateJob *) h_f;
                 uint8_t *h_b = h_f + (size_t) chunk * sizeof(InflateJob), *h_z = h_f + z_head;
                 int32_t *h_stat = (int32_t *) (h_f + z_head + z_cap);
-                size_t zo = 0;
+                size_t zo = 2;                                     // deflate data (behind the 2-byte zlib header) on 4-byte boundaries
                 bool staged = true;
                 for (int64_t i = 0; i < cnt && staged; i++) {
                     const int64_t a = offsets[i0 + i], b = offsets[i0 + i + 1];
@@ -952,7 +952,8 @@ extern "C" cds_status cds_png_decode_gray16(cds_ctx *ctx, const uint8_t *blob, c
                     const cds_status ps = png_collect_idat(blob + a, (size_t) (b - a), width, height, h_z + zo, z_cap - zo, z_head + zo, &used, &h_jobs[i], &h_b[i], err);
                     if (ps == CDS_ERR_CAPACITY) { staged = false; break; }      // streams larger than their images: the host path takes the chunk
                     if (ps != CDS_OK) return ctx->fail(ps, "cds_png_decode_gray16: file " + std::to_string(i0 + i) + ": " + err);
-                    zo += used;
+                    zo = (zo + used + 1) / 4 * 4 + 2;
+                    if (zo > z_cap) { staged = false; break; }
                 }
                 if (staged) {
                     CDS_CUDA(ctx, cudaMemcpyAsync(d_z, h_f, z_head + zo, cudaMemcpyHostToDevice, ds.stream));

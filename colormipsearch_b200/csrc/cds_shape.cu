@@ -1162,7 +1162,7 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
         for (int64_t w = 0; w < n_windows; w++) {
             size_t sum = 0;
             for (int64_t a = w * win; a < std::min<int64_t>((int64_t) active.size(), (w + 1) * win); a++) sum += (size_t) (png_offsets[active[a] + 1] - png_offsets[active[a]]);
-            z_payload = std::max(z_payload, sum);
+            z_payload = std::max(z_payload, sum + (size_t) 8 * win + 8);      // + alignment gaps
         }
         z_payload = (z_payload + 15) / 16 * 16;
         if (z_head + z_payload > 0xFFFFFFF0ull) return ctx->fail(CDS_ERR_UNSUPPORTED, "cds_shape_score_pairs_files: gradient files of one window exceed 4 GB");
@@ -1284,7 +1284,7 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
             InflateJob *h_jobs = (InflateJob *) h_slot;
             uint8_t *h_bps = h_slot + (size_t) win * sizeof(InflateJob), *h_z = h_slot + z_head;
             const int64_t cnt = a1 - a0;
-            size_t zo = 0;
+            size_t zo = 2;                                         // every stream starts 2 bytes before a 4-byte boundary: its deflate data (behind the zlib header) is aligned
             for (int64_t i = 0; i < cnt; i++) {
                 const int64_t f = active[a0 + i];
                 std::string err;
@@ -1292,7 +1292,7 @@ static cds_status shape_score_pairs_impl(cds_ctx *ctx, const cds_shape_maskset *
                 cds_status ps = png_collect_idat(png_blob + png_offsets[f], (size_t) (png_offsets[f + 1] - png_offsets[f]), W, H, h_z + zo, z_payload - zo,
                                                  z_head + zo, &used_bytes, &h_jobs[i], &h_bps[i], err);
                 if (ps != CDS_OK) return ctx->fail(ps, "cds_shape_score_pairs_files: file " + std::to_string(f) + ": " + err);
-                zo += used_bytes;
+                zo = (zo + used_bytes + 1) / 4 * 4 + 2;
             }
             SH_CUDA(ctx, cudaMemcpyAsync(wk.d_zstage, h_slot, z_head + zo, cudaMemcpyHostToDevice, ds.copy_stream));
             ctx->stats.h2d_bytes += (int64_t) (z_head + zo);

@@ -133,12 +133,14 @@ void run_png(std::vector<uint8_t> d, Rng &r, uint64_t it)
         (void) cds::png_inflate(d.data(), d.size(), wh[0], wh[1], &depth, out.data(), cap / 3, err);
         // the device's decoder, built for one lane, on the same stream: it must agree with zlib whenever zlib accepts the stream,
         // and end in a status otherwise
+        // staged the way the library does (deflate data on a 4-byte boundary) or one byte off it: both paths of the bit reader
+        const size_t lead = (it & 1) ? 2 : 3;
         std::vector<uint8_t> stage(d.size() + 8);
         size_t used = 0;
         cds::InflateJob job{0, 0};
         uint8_t bps = 0;
-        if (cds::png_collect_idat(d.data(), d.size(), wh[0], wh[1], stage.data(), stage.size(), 0, &used, &job, &bps, err) == CDS_OK && job.src_len) {
-            expect((size_t) job.src + job.src_len <= used, "collect_idat: job outside the staged bytes", it);
+        if (cds::png_collect_idat(d.data(), d.size(), wh[0], wh[1], stage.data() + lead, stage.size() - lead, lead, &used, &job, &bps, err) == CDS_OK && job.src_len) {
+            expect((size_t) job.src + job.src_len <= lead + used, "collect_idat: job outside the staged bytes", it);
             const size_t need = (size_t) wh[1] * (1 + (size_t) wh[0] * bps);
             std::vector<uint8_t> mine(need + 1);
             int64_t got = -1;

@@ -34,8 +34,9 @@ def test_inflates_what_zlib_deflates(name):
     for level in (0, 1, 3, 6, 9):
         for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
             comp = _deflate(data, level, strategy)
-            got, why = capi.debug_inflate_host(comp, len(data))
-            assert why == 0 and got == data, (level, strategy)
+            for misalign in (0, 1, 2, 3):          # whole-word loads from aligned data, byte loads otherwise
+                got, why = capi.debug_inflate_host(comp, len(data), misalign)
+                assert why == 0 and got == data, (level, strategy, misalign)
             if data:
                 # one byte of room too few: the first len - 1 bytes, and reason 6
                 got, why = capi.debug_inflate_host(comp, len(data) - 1)
