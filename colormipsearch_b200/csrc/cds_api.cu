@@ -23,7 +23,10 @@ void set_tls_error(const std::string &msg) { g_tls_err = msg; }
 }  // namespace cds
 
 namespace cds {
-static constexpr size_t kPoolLimit = (size_t) 8 << 30;
+// Most bytes a device's pool keeps for reuse (of 180 GB per B200).  The file-fed shape score works in windows of 2 048 targets
+// (~20 GB of window buffers): with the earlier 8 GB limit every call paid cudaMalloc + cudaFree for the rest -- 325 instead of ~150 ms
+// per 4 096 targets (bench.py shape.config2_mix.e2e_files).  An allocation that fails flushes the cache and retries (alloc below).
+static constexpr size_t kPoolLimit = (size_t) 32 << 30;
 
 cudaError_t DevPool::alloc(void **p, size_t bytes)
 {
