@@ -805,7 +805,7 @@ def png_encode_gray16(pixels, filter_mode=-1):
 
 
 def png_decode_gray16(ctx, files, W, H):
-    """cds_png_decode_gray16: PNG files (host inflate, device unfilter) -> uint16 [n][H][W]"""
+    """cds_png_decode_gray16: PNG files (inflate and filter reconstruction on the device) -> uint16 [n][H][W]"""
     blob, offsets = pack_files(files)
     n = len(offsets) - 1
     out = np.empty((n, H, W), np.uint16)

@@ -267,8 +267,11 @@ typedef struct cds_png_info {
 } cds_png_info;
 cds_status cds_png_probe(const uint8_t *file, int64_t len, cds_png_info *info);      /* host only */
 /* n PNG files stored back to back (blob / offsets as for the TIFF calls) -> out = uint16[n][height][width] (8-bit files are widened,
- * like ImageArray.get on a ByteImageArray).  The zlib streams are inflated on host threads, the scanline filters (None, Sub, Up,
- * Average, Paeth) are undone and the samples byte-swapped on device 0. */
+ * like ImageArray.get on a ByteImageArray).  The files are uploaded as stored; their zlib streams are inflated (one warp per stream,
+ * csrc/cds_inflate.h), the scanline filters (None, Sub, Up, Average, Paeth) undone and the samples byte-swapped on device 0.  The image
+ * is the first height * (1 + width * bytes per sample) bytes of the stream (data behind them is ignored, a shorter stream is an error;
+ * the Adler-32 trailer is not checked).  A stream the device refuses is read by zlib on the host, which then has the last word
+ * (cds_search_stats.host_inflate_fallbacks); "device_inflate" 0 (cds_ctx_set_option) inflates everything on host threads. */
 cds_status cds_png_decode_gray16(cds_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int64_t n, int32_t width, int32_t height, uint16_t *out);
 /* Host only, test hook: raw DEFLATE data (RFC 1951, no zlib header) through the decoder that the device runs one warp per stream
  * (csrc/cds_inflate.h), built for a single lane.  *out_len = bytes produced; *reason (may be NULL) = 0 or why the stream was refused
@@ -372,8 +375,8 @@ cds_status cds_shape_score_pairs_tiff(cds_ctx *ctx, const cds_shape_maskset *sms
 
 /* The same scoring with BOTH inputs as files in host memory, the way gradientScores finds them: targets as PackBits / stored RGB
  * TIFF files, gradient images as 16-bit (or 8-bit) grayscale PNG files (png_blob / png_offsets, n_targets + 1 offsets).  The PNG
- * streams of a window of targets are inflated on host threads while the device works on the previous window; filters and byte
- * order are undone on the device. */
+ * files of a window of targets (up to 2 048) are uploaded as stored and inflated on the device while it works on the previous window
+ * (see cds_png_decode_gray16; "device_inflate" 0 inflates them on host threads instead); filters and byte order are undone on the device. */
 cds_status cds_shape_score_pairs_files(cds_ctx *ctx, const cds_shape_maskset *sms, const uint8_t *tiff_blob, const int64_t *tiff_offsets,
                                        const uint8_t *png_blob, const int64_t *png_offsets, const uint8_t *zgap_rgb,
                                        const uint8_t *has_variants, int64_t n_targets,
