@@ -176,3 +176,45 @@ def test_profile_tool_markers_exist_in_the_kernel_source():
     spec.loader.exec_module(mod)                     # raises SystemExit("marker not found ...") when a marker is gone
     lines = [l for l, _ in mod.OUTER]
     assert lines == sorted(lines) and len(set(lines)) == len(lines)
+
+
+def test_every_context_option_is_documented_in_the_header():
+    """cds_ctx_set_option's names live in csrc/cds_api.cu; include/cdsgpu.h is where a caller learns about them."""
+    import re
+    src = open(os.path.join(ROOT, "colormipsearch_b200", "csrc", "cds_api.cu")).read()
+    body = src[src.index('extern "C" cds_status cds_ctx_set_option'):]
+    body = body[:body.index("unknown option")]
+    names = set(re.findall(r'std::strcmp\(name, "([a-z_0-9]+)"\)', body))
+    assert {"match_kernel", "stream_chunk", "device_inflate", "wide_lists", "shape_inflate_window"} <= names
+    header = open(os.path.join(ROOT, "include", "cdsgpu.h")).read()
+    doc = header[header.index("Tuning / test switches"):header.index("cds_status cds_ctx_set_option")]
+    missing = sorted(n for n in names if '"%s"' % n not in doc)
+    assert not missing, missing
+
+
+def test_ctypes_structs_follow_the_header():
+    """The structs that cross the ABI by value-in-memory: same fields, in the same order, with the same widths as include/cdsgpu.h."""
+    import ctypes as C
+    import re
+    header = open(os.path.join(ROOT, "include", "cdsgpu.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    widths = {"int32_t": 4, "uint32_t": 4, "int64_t": 8, "uint64_t": 8, "double": 8, "float": 4, "uint8_t": 1}
+
+    def fields_of(name):
+        m = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, flags=re.S)
+        assert m, name
+        out = []
+        for decl in m.group(1).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            typ, rest = decl.split(None, 1)
+            for f in rest.split(","):
+                out.append((f.strip(), widths[typ]))
+        return out
+
+    for cname, ctype in (("cds_search_stats", capi.SearchStats), ("cds_tiff_info", capi.TiffInfo), ("cds_png_info", capi.PngInfo),
+                         ("cds_zip_entry", capi.ZipEntry)):
+        want = fields_of(cname)
+        got = [(n, C.sizeof(t)) for n, t in ctype._fields_]
+        assert got == want, (cname, got, want)
