@@ -218,3 +218,31 @@ def test_ctypes_structs_follow_the_header():
         want = fields_of(cname)
         got = [(n, C.sizeof(t)) for n, t in ctype._fields_]
         assert got == want, (cname, got, want)
+
+
+def test_ctypes_signatures_follow_the_header():
+    """Every function the header declares has a Python prototype with the same number of arguments, scalar arguments of the same width
+    in the same places, and pointers where the header has pointers."""
+    import ctypes as C
+    import re
+    header = open(os.path.join(ROOT, "include", "cdsgpu.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    header = re.sub(r"typedef struct \w+ \{.*?\} \w+;", "", header, flags=re.S)
+    scalar = {"int32_t": C.c_int32, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "double": C.c_double, "float": C.c_float, "int": C.c_int32}
+    decls = re.findall(r"^\s*(?:const\s+)?(\w+)\s*(\*?)\s*(cds_\w+)\s*\(([^;{]*?)\)\s*;", header, flags=re.M)
+    assert len(decls) > 40
+    checked = 0
+    for ret, retptr, name, args in decls:
+        assert name in capi.SIGNATURES, "no Python prototype for " + name
+        restype, argtypes = capi.SIGNATURES[name]
+        args = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        assert len(args) == len(argtypes), (name, len(args), len(argtypes))
+        for decl, ct in zip(args, argtypes):
+            if "*" in decl:
+                assert ct is C.c_void_p or ct is C.c_char_p or hasattr(ct, "contents") or issubclass(ct, C._Pointer), (name, decl, ct)
+            else:
+                typ = [w for w in decl.split() if w != "const"][0]
+                if typ in scalar:
+                    assert C.sizeof(ct) == C.sizeof(scalar[typ]), (name, decl, ct)
+        checked += 1
+    assert checked == len(decls)
