@@ -420,7 +420,8 @@ def shape_config2_mix(ctx, topk, n_masks, t_first, t_limit=4096, inflate_windows
            "mask_prep_ms_per_mask": prep_s / n_masks * 1e3, "mask_prep_first_use_ms_per_mask": prep_first_s / n_masks * 1e3,
            "mask_prep_h2d_bytes_per_mask": 3 * W * H,
            "what": "pairs = top-300 isMatch targets per mask from this run's pixel-match search, targets < %d; only targets with pairs are "
-                   "uploaded (RGB or TIFF file + gray16 gradient), zgap dilation + slice planes + pair kernel per window of 32 targets" % t_limit}
+                   "uploaded (RGB or TIFF file + gray16 gradient, or TIFF + PNG files in e2e_files), zgap dilation + slice planes + pair kernel per window of "
+                   "32 / 128 targets (up to 2048 when the gradient PNG streams are inflated on the device)" % t_limit}
     sms.close()
     del targets, grads
     for q in (t_ptr, g_ptr, m_ptr, f_ptr):
