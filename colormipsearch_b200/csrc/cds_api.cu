@@ -27,6 +27,8 @@ namespace cds {
 // (~20 GB of window buffers): with the earlier 8 GB limit every call paid cudaMalloc + cudaFree for the rest -- 325 instead of ~150 ms
 // per 4 096 targets (bench.py shape.config2_mix.e2e_files).  An allocation that fails flushes the cache and retries (alloc below).
 static constexpr size_t kPoolLimit = (size_t) 32 << 30;
+static constexpr size_t kPoolBigBlock = (size_t) 256 << 20;      // blocks from this size on are cached only while ...
+static constexpr size_t kPoolReserve = (size_t) 16 << 30;        // ... this much of the device is free (the current device: callers set it)
 
 cudaError_t DevPool::alloc(void **p, size_t bytes)
 {
@@ -59,6 +61,13 @@ void DevPool::free(void *p)
     const size_t bytes = it->second;
     live.erase(it);
     if (cached_bytes + bytes > kPoolLimit) { cudaFree(p); return; }
+    if (bytes >= kPoolBigBlock) {
+        // a large block is kept only while the device has room to spare: allocations outside the pool (a library's planes, the
+        // streaming buffers) do not know how to ask the pool for memory back
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) cudaGetLastError();
+        else if (free_b < kPoolReserve) { cudaFree(p); return; }
+    }
     free_blocks.emplace(bytes, p);
     cached_bytes += bytes;
 }
