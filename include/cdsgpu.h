@@ -37,7 +37,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden; these are its only exports */
 #endif
 
-#define CDSGPU_ABI_VERSION 1
+#define CDSGPU_ABI_VERSION 2   /* 2: cds_search_stats grew by host_inflate_fallbacks (callers pass their own struct: sizes must agree) */
 
 typedef int32_t cds_status;
 enum {

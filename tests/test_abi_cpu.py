@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     # the Python binding knows exactly the same entry points
     assert sorted(capi.SIGNATURES) == names
     capi.lib()
-    assert capi.lib().cds_abi_version() == 1
+    assert capi.lib().cds_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
