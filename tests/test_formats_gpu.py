@@ -181,7 +181,7 @@ def test_shape_scores_from_files_golden(ctx, fixtures, fmt, inflate_mode):
     b = sms.score_pairs_files(tf, pf, None, pm, pt, has)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
-    # 40 targets are two windows of 32: window 0 has 16 odd images, window 1 has 4 (of which #36 = target 36 is scored: has_variants)
+    # (the scored targets span two windows of 32; mode 2 treats every odd image of a window as refused by the device)
     if inflate_mode == 1:
         assert ctx.last_stats()["host_inflate_fallbacks"] == 0
     elif inflate_mode == 2:
