@@ -160,6 +160,8 @@ CDS_INF_HD void inf_sync()
 {
 #ifdef __CUDA_ARCH__
     if (LANES > 1) __syncwarp();
+#elif defined(CDS_INF_HOST_SYNC)
+    if (LANES > 1) CDS_INF_HOST_SYNC();      // test builds: LANES host threads meet at a barrier (tests/inflate_lanes_main.cpp, under ThreadSanitizer)
 #endif
 }
 
