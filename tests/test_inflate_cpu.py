@@ -137,6 +137,34 @@ def _edge_stream():
     return zlib.compress(bytes(data), 9)
 
 
+def _many_blocks_stream():
+    """a block boundary every few hundred bytes (sync / full flushes: each ends a block and adds an empty stored one), with data that
+    makes the encoder choose different block types; -> (zlib stream, its data)"""
+    rng = np.random.default_rng(77)
+    c = zlib.compressobj(6, zlib.DEFLATED, 15, 9, zlib.Z_DEFAULT_STRATEGY)
+    out, data = b"", b""
+    for k in range(120):
+        kind = k % 4
+        if kind == 0:
+            chunk = bytes(rng.integers(0, 4, int(rng.integers(50, 900)), dtype=np.uint8))
+        elif kind == 1:
+            chunk = bytes(rng.integers(0, 256, int(rng.integers(20, 300)), dtype=np.uint8))
+        elif kind == 2:
+            chunk = b"abcabcabd" * int(rng.integers(5, 80))
+        else:
+            chunk = data[-int(rng.integers(1, min(len(data), 9000))):][:400]
+        data += chunk
+        out += c.compress(chunk) + c.flush(zlib.Z_SYNC_FLUSH if k % 3 else zlib.Z_FULL_FLUSH)
+    return out + c.flush(), data
+
+
+def test_streams_of_many_blocks():
+    z, data = _many_blocks_stream()
+    assert zlib.decompress(z) == data
+    for misalign in (0, 1, 2, 3):
+        assert capi.debug_inflate_host(z[2:], len(data), misalign) == (data, 0)
+
+
 def test_warp_protocol_is_race_free_under_tsan(tmp_path):
     import subprocess
     exe = _build_lanes(tmp_path)
@@ -145,7 +173,7 @@ def test_warp_protocol_is_race_free_under_tsan(tmp_path):
     px[4:55, 10:300] = (rng.integers(0, 40, (51, 290)) * rng.integers(0, 2, (51, 290))).astype(np.uint16)
     px[20:30, 50:250] = rng.integers(0, 65536, (10, 200))
     raw = b"".join(b"\0" + row.astype(">u2").tobytes() for row in px)
-    streams = {"edge": _edge_stream()}
+    streams = {"edge": _edge_stream(), "many_blocks": _many_blocks_stream()[0]}
     for name, level, strategy in (("dynamic", 6, zlib.Z_DEFAULT_STRATEGY), ("fixed", 6, zlib.Z_FIXED), ("stored", 0, zlib.Z_DEFAULT_STRATEGY),
                                   ("huffman", 6, zlib.Z_HUFFMAN_ONLY), ("rle", 9, zlib.Z_RLE)):
         c = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strategy)
